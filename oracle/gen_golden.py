@@ -1,0 +1,132 @@
+"""Generate golden fixtures by RUNNING THE REFERENCE (test infrastructure only).
+
+Runs in the build container only (needs /root/reference, which does not exist on
+the GPU box).  Imports the unmodified reference modules with the two shims of
+SURVEY.md section 0 (missing super() globals; `.cuda()` on a CPU host), runs them in
+float64 (arbiter) and float32 (the reference's own noise floor), and writes
+logits + every parameter gradient + the state_dict + the input recipe to
+tests/golden/<case>.npz.
+
+    python oracle/gen_golden.py            # regenerates every fixture
+
+Input recipe (reproducible without torch RNG): numpy RandomState(seed).rand(shape)
+for x, (rand(B,1) > .5) for y.  Weights: reference constructor under
+torch.manual_seed(wseed), then every parameter perturbed by a seeded numpy normal
+so that no term of the cell is at a degenerate init value (mu = gamma = 0, ...).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def load_reference():
+    sys.path.insert(0, REF)
+    from models import InT as RInT
+    from models import ffhgru_hierarchy as RH
+    RInT.FFhGRU = RInT.InT          # super(FFhGRU, self) in InT.__init__
+    RInT.hConvGRUCell = RInT.rCell  #                 super(hConvGRUCell, self) in rCell.__init__
+    torch.Tensor.cuda = lambda self, *a, **k: self  # SURVEY section 0.2 (CPU host only)
+    return RInT, RH
+
+
+def make_inputs(seed, B, T, H, W):
+    rs = np.random.RandomState(seed)
+    x = rs.rand(B, 3, T, H, W)
+    y = (rs.rand(B, 1) > 0.5).astype(np.float64)
+    return x, y
+
+
+def perturb(model, seed, scale=0.05):
+    rs = np.random.RandomState(seed)
+    with torch.no_grad():
+        for n, prm in model.named_parameters():
+            if n == "unit1.w":            # uninitialised + unused (InT.py:100,118): pin to a constant
+                prm.fill_(1.0)
+                continue
+            if not torch.isfinite(prm).all() or n in ("unit1.alpha", "unit1.mu") and prm.abs().max() > 1e3:
+                prm.fill_(0.5)            # no_inh leaves alpha/mu uninitialised (InT.py:112-114)
+            prm.add_(torch.from_numpy(rs.normal(0, scale, tuple(prm.shape))).to(prm.dtype))
+
+
+def run_case(name, ctor, B, T, H, W, seed, wseed, testmode=False):
+    x_np, y_np = make_inputs(seed, B, T, H, W)
+    res = {"x_seed": seed, "shape": np.array([B, T, H, W])}
+    # weights: fp32-representable, so the fixture stores them exactly as float32
+    torch.set_default_dtype(torch.float32)
+    torch.manual_seed(wseed)
+    m32 = ctor()
+    perturb(m32, wseed + 1)
+    sd32 = {k: v.detach().clone() for k, v in m32.state_dict().items()}
+    for k, v in sd32.items():
+        res["sd/" + k] = v.numpy()
+    grads = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        torch.set_default_dtype(dt)   # states are created with the default dtype (InT.py:217-218)
+        m = ctor().to(dt)
+        m.load_state_dict({k: v.to(dt) for k, v in sd32.items()})
+        x = torch.from_numpy(x_np).to(dt)
+        y = torch.from_numpy(y_np).to(dt)
+        out, _ = m(x)
+        loss = F.binary_cross_entropy_with_logits(out, y)
+        loss.backward()
+        grads[tag] = {n: prm.grad.detach().double() for n, prm in m.named_parameters() if prm.grad is not None}
+        grads[tag]["__logits__"] = out.detach().double()
+        if tag == "f64":
+            res["logits"] = out.detach().numpy()
+            res["loss"] = np.array(loss.item())
+            for n, gr in grads[tag].items():
+                if n == "__logits__":
+                    continue
+                big = gr.numel() > 4096   # the two 7x7 banks: float32 storage (6e-8 rel) keeps fixtures small
+                res["grad/" + n] = gr.numpy().astype(np.float32 if big else np.float64)
+            if testmode:
+                with torch.no_grad():
+                    o2, states, gates = m(x, testmode=True)
+                res["tm_logits"] = o2.numpy()
+                res["tm_states"] = states.numpy().astype(np.float32)
+                res["tm_gates"] = gates.numpy().astype(np.float32)
+    # the fp32 reference's own error vs fp64, per tensor: max|g32-g64| / max|g64|  
+    for n, g64 in grads["f64"].items():
+        e = (grads["f32"][n] - g64).abs().max().item() / max(g64.abs().max().item(), 1e-300)
+        res["f32err/" + n] = np.array(e)
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
+    worst = max((float(v), k) for k, v in res.items() if k.startswith("f32err/"))
+    print(name, "logits", res["logits"].ravel()[:4], "loss", res["loss"], "worst fp32-vs-fp64", worst)
+
+
+def main():
+    RInT, RH = load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    I = lambda **kw: (lambda: RInT.InT(dimensions=32, timesteps=8, kernel_size=7, **kw))
+    run_case("int_small", I(), 2, 4, 16, 16, seed=11, wseed=3, testmode=True)
+    run_case("int_tile", I(), 3, 3, 32, 32, seed=12, wseed=4)          # batch not a multiple of anything
+    run_case("int_cfg1", I(), 4, 32, 32, 32, seed=13, wseed=5)         # BASELINE configs[0] shape
+    run_case("int_64px", I(), 1, 3, 64, 64, seed=14, wseed=6)          # cfg-3 frame size, short
+    run_case("int_tanh_small", I(nl=torch.tanh), 2, 4, 16, 16, seed=15, wseed=7)
+    run_case("int_noinh_small", I(no_inh=True), 2, 4, 16, 16, seed=16, wseed=8)
+    run_case("int_lesion_small", I(lesion_alpha=True, lesion_gamma=True), 2, 4, 16, 16, seed=17, wseed=9)
+    H = lambda: RH.FFhGRU(dimensions=32, timesteps=8, kernel_size=7)
+    run_case("hgru_small", H, 2, 4, 16, 16, seed=21, wseed=10, testmode=True)
+    run_case("hgru_tile", H, 3, 3, 32, 32, seed=22, wseed=11)
+    # non-normative fingerprint of SURVEY 8c: seed 0, InT(32,32,7), x = torch.rand right after ctor
+    torch.manual_seed(0)
+    m = RInT.InT(dimensions=32, timesteps=32, kernel_size=7)
+    x = torch.rand(4, 3, 32, 32, 32)
+    with torch.no_grad():
+        out, _ = m(x)
+    np.savez_compressed(os.path.join(OUT, "int_fingerprint.npz"), logits=out.numpy(),
+                        init_sums=np.array([v.double().sum().item() for k, v in m.state_dict().items()
+                                            if k != "unit1.w"]),
+                        init_keys=np.array([k for k in m.state_dict().keys() if k != "unit1.w"]))
+    print("fingerprint", out.flatten())
+
+
+if __name__ == "__main__":
+    main()
