@@ -1,0 +1,123 @@
+/*
+ * ptk_b200.h -- C ABI of the B200-native PathTracker recurrent core (libptk_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of pathtracker-code/pathtracker-models:
+ * the per-timestep recurrent circuit of models/InT.py (InT), models/ffhgru_hierarchy.py (FFhGRU)
+ * and models/convlstm.py (ConvLSTM), forward and BPTT backward.  The reference has no native
+ * code and no FFI: the interface being replaced is the *body* of the nn.Module.forward methods
+ * (and the autograd graph they build).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types.  All pointers are CALLER-OWNED DEVICE memory (fp32 unless noted)
+ *     on the device that is current when the call is made; `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream).  The library allocates nothing persistent, never
+ *     synchronises the device, and is re-entrant per (device, stream).
+ *   - return 0 on success, a PTK_E* code otherwise; ptk_last_error() returns a thread-local
+ *     human-readable message for the last failure on the calling thread.
+ *   - state-sized tensors are [B, C, H, W] fp32, contiguous (NCHW), C = 32.
+ *   - parameters travel as ONE flat fp32 vector in the canonical order of ptk_int_param_offsets
+ *     (the reference's state_dict order without the dead `unit1.w`); gradients come back in the
+ *     same layout, which is also the bucket handed to the NCCL all-reduce.
+ */
+#ifndef PTK_B200_H
+#define PTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTK_VERSION 100
+
+#if defined(__GNUC__)
+#define PTK_API __attribute__((visibility("default")))
+#else
+#define PTK_API
+#endif
+
+enum {
+  PTK_OK = 0,
+  PTK_EINVAL = 1,      /* bad argument / unsupported shape (message says which)          */
+  PTK_ENOMEM = 2,      /* caller-provided workspace / saved buffer too small             */
+  PTK_ECUDA = 3,       /* a CUDA runtime call or launch failed                            */
+  PTK_EUNSUPPORTED = 4 /* variant not built (e.g. kernel_size other than 7)               */
+};
+
+enum { PTK_CELL_INT = 0,   /* models/InT.py:157            gated_inhibition = inhibition  */
+       PTK_CELL_HGRU = 1   /* models/ffhgru_hierarchy.py:147  gated_inhibition = att_gate */ };
+enum { PTK_ACT_SOFTPLUS = 0, /* F.softplus beta=1 threshold=20 (InT.py:184 default nl)    */
+       PTK_ACT_TANH = 1      /* utils/engine.py:138-146 InT_tanh                          */ };
+enum { PTK_CONV_FP32 = 0,     /* strict fp32 FFMA convolutions (parity-gated default)     */
+       PTK_CONV_BF16X3 = 1    /* 3-pass split-bf16 tcgen05 tiles, fp32 accumulate         */ };
+
+typedef struct PtkDims {
+  int32_t B, T, H, W;  /* clip batch / frames / frame size.  x is [B,3,T,H,W]              */
+  int32_t C;           /* hidden channels ("dimensions"); must be 32 (utils/engine.py:75)  */
+  int32_t K;           /* horizontal kernel size; must be 7  (utils/engine.py:75)          */
+  int32_t cell;        /* PTK_CELL_*                                                       */
+  int32_t act;         /* PTK_ACT_*                                                        */
+  int32_t no_inh;      /* InT(no_inh=True), models/InT.py:167-168                          */
+  int32_t conv_mode;   /* PTK_CONV_*                                                       */
+} PtkDims;
+
+/* Number of parameter tensors in the flat vector and their canonical order. */
+#define PTK_INT_NPARAM 30
+enum {
+  PTK_P_PREPROC_W = 0, PTK_P_PREPROC_B, PTK_P_W_EXC, PTK_P_W_INH, PTK_P_ALPHA, PTK_P_MU,
+  PTK_P_GAMMA, PTK_P_KAPPA,
+  PTK_P_AW_W, PTK_P_AW_B, PTK_P_AU_W, PTK_P_AU_B, PTK_P_IW_W, PTK_P_IW_B, PTK_P_IU_W, PTK_P_IU_B,
+  PTK_P_EW_W, PTK_P_EW_B, PTK_P_EU_W, PTK_P_EU_B,
+  PTK_P_BN0_W, PTK_P_BN0_B, PTK_P_BN1_W, PTK_P_BN1_B,
+  PTK_P_READOUT_W, PTK_P_READOUT_B, PTK_P_TARGET_W, PTK_P_TARGET_B, PTK_P_DENSE_W, PTK_P_DENSE_B
+};
+
+PTK_API int ptk_version(void);
+PTK_API const char* ptk_last_error(void);
+
+/* Element offsets (PTK_INT_NPARAM + 1 entries; last = total count) of each parameter tensor in
+ * the flat vector.  Shapes are those of rCell.__init__ / InT.__init__ (models/InT.py:63-143,
+ * 184-208): preproc [C,3]+[C]; w_exc,w_inh [C,C,K,K]; alpha,mu,gamma,kappa [C]; six 1x1 gates
+ * [C,C]+[C]; two BatchNorm affine pairs [C]; readout_conv [C]+[1]; target_conv [2,5,5]+[1];
+ * readout_dense [1]+[1]. */
+PTK_API int ptk_int_param_offsets(const PtkDims* d, int64_t* offsets);
+
+/* Bytes of the checkpoint buffer forward fills for backward: I_t,E_t (t=0..T), the two
+ * pre-BatchNorm conv outputs per step and the 4*C batch statistics per step.  This replaces
+ * the autograd tape of models/InT.py:223-235 (21 state-sized tensors/step in the reference). */
+PTK_API size_t ptk_int_saved_bytes(const PtkDims* d);
+PTK_API size_t ptk_int_workspace_bytes(const PtkDims* d);
+
+/* Forward of InT.forward / FFhGRU.forward (models/InT.py:210-245,
+ * models/ffhgru_hierarchy.py:211-276): stem Conv3d(3->C)+nl, T cell steps (rCell.forward
+ * models/InT.py:145-179), readout.  x: [B,3,T,H,W] with arbitrary element strides
+ * (utils/engine.py:222-243 hands over a channels_last_3d-strided tensor).
+ *   logits  [B]            out
+ *   saved   ptk_int_saved_bytes, or NULL for inference (no backward possible)
+ *   gates   [B,T,C,H,W]    optional (testmode=True, InT.py:230-233), else NULL
+ *   states  [B,T,1,H,W]    optional (testmode=True), else NULL */
+PTK_API int ptk_int_forward(const PtkDims* d, const float* x, const int64_t x_strides[5],
+                    const float* params, float* logits, void* saved, float* gates, float* states,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* BPTT backward (replaces loss.backward() through the graph of InT.forward, mainclean.py:204).
+ *   dlogits [B] in;  dparams flat vector out (overwritten, canonical layout);
+ *   dx optional [B,3,T,H,W] contiguous (viz_model_att.py:189-196), else NULL. */
+PTK_API int ptk_int_backward(const PtkDims* d, const float* x, const int64_t x_strides[5],
+                     const float* params, const void* saved, const float* dlogits,
+                     float* dparams, float* dx, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* On-device synthetic PathTracker clips (stands in for utils/TFRDataset.py:6-53; data contract
+ * utils/TFRDataset.py:17-25 + utils/engine.py:222-226: values in {0,1}, x [B,3,T,H,W] fp32
+ * contiguous, y [B] fp32 labels).  Counter-based: sample i depends only on (seed, first_index+i),
+ * so every rank draws a disjoint deterministic shard. */
+PTK_API int ptk_synth_pathtracker(uint64_t seed, uint64_t first_index, int32_t B, int32_t T, int32_t H,
+                          int32_t W, int32_t n_distractors, int32_t speed, float* x, float* y,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTK_B200_H */

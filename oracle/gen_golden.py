@@ -105,15 +105,15 @@ def main():
     RInT, RH = load_reference()
     os.makedirs(OUT, exist_ok=True)
     I = lambda **kw: (lambda: RInT.InT(dimensions=32, timesteps=8, kernel_size=7, **kw))
-    run_case("int_small", I(), 2, 4, 16, 16, seed=11, wseed=3, testmode=True)
+    run_case("int_small", I(), 2, 4, 32, 32, seed=11, wseed=3, testmode=True)
     run_case("int_tile", I(), 3, 3, 32, 32, seed=12, wseed=4)          # batch not a multiple of anything
     run_case("int_cfg1", I(), 4, 32, 32, 32, seed=13, wseed=5)         # BASELINE configs[0] shape
     run_case("int_64px", I(), 1, 3, 64, 64, seed=14, wseed=6)          # cfg-3 frame size, short
-    run_case("int_tanh_small", I(nl=torch.tanh), 2, 4, 16, 16, seed=15, wseed=7)
-    run_case("int_noinh_small", I(no_inh=True), 2, 4, 16, 16, seed=16, wseed=8)
-    run_case("int_lesion_small", I(lesion_alpha=True, lesion_gamma=True), 2, 4, 16, 16, seed=17, wseed=9)
+    run_case("int_tanh_small", I(nl=torch.tanh), 2, 4, 32, 32, seed=15, wseed=7)
+    run_case("int_noinh_small", I(no_inh=True), 2, 4, 32, 32, seed=16, wseed=8)
+    run_case("int_lesion_small", I(lesion_alpha=True, lesion_gamma=True), 2, 4, 32, 32, seed=17, wseed=9)
     H = lambda: RH.FFhGRU(dimensions=32, timesteps=8, kernel_size=7)
-    run_case("hgru_small", H, 2, 4, 16, 16, seed=21, wseed=10, testmode=True)
+    run_case("hgru_small", H, 2, 4, 32, 32, seed=21, wseed=10, testmode=True)
     run_case("hgru_tile", H, 3, 3, 32, 32, seed=22, wseed=11)
     # non-normative fingerprint of SURVEY 8c: seed 0, InT(32,32,7), x = torch.rand right after ctor
     torch.manual_seed(0)
@@ -126,6 +126,11 @@ def main():
                                             if k != "unit1.w"]),
                         init_keys=np.array([k for k in m.state_dict().keys() if k != "unit1.w"]))
     print("fingerprint", out.flatten())
+    torch.manual_seed(0)
+    h = RH.FFhGRU(dimensions=32, timesteps=32, kernel_size=7)
+    np.savez_compressed(os.path.join(OUT, "hgru_fingerprint.npz"),
+                        init_sums=np.array([v.double().sum().item() for k, v in h.state_dict().items()]),
+                        init_keys=np.array(list(h.state_dict().keys())))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,75 @@
+"""ctypes binding of libptk_b200.so (the C ABI declared in include/ptk_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, the product
+path raises.  (The CPU oracle lives under oracle/ and is only ever used by tests / bench baselines.)
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libptk_b200.so")
+
+PTK_CELL_INT, PTK_CELL_HGRU = 0, 1
+PTK_ACT_SOFTPLUS, PTK_ACT_TANH = 0, 1
+PTK_CONV_FP32, PTK_CONV_BF16X3 = 0, 1
+PTK_INT_NPARAM = 30
+
+EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_saved_bytes",
+           "ptk_int_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker")
+
+
+class PtkDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("B", "T", "H", "W", "C", "K", "cell", "act", "no_inh", "conv_mode")]
+
+
+class PtkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if the native library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PtkError(
+            f"{LIB_PATH} not found: the CUDA library has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `python -m pathtracker_models_b200._build`). "
+            "There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64p, u64, i32, sz = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), ctypes.c_uint64, ctypes.c_int32, ctypes.c_size_t
+    dp = ctypes.POINTER(PtkDims)
+    L.ptk_version.restype = ctypes.c_int
+    L.ptk_version.argtypes = []
+    L.ptk_last_error.restype = ctypes.c_char_p
+    L.ptk_last_error.argtypes = []
+    L.ptk_int_param_offsets.restype = ctypes.c_int
+    L.ptk_int_param_offsets.argtypes = [dp, i64p]
+    L.ptk_int_saved_bytes.restype = sz
+    L.ptk_int_saved_bytes.argtypes = [dp]
+    L.ptk_int_workspace_bytes.restype = sz
+    L.ptk_int_workspace_bytes.argtypes = [dp]
+    L.ptk_int_forward.restype = ctypes.c_int
+    L.ptk_int_forward.argtypes = [dp, vp, i64p, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ptk_int_backward.restype = ctypes.c_int
+    L.ptk_int_backward.argtypes = [dp, vp, i64p, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ptk_synth_pathtracker.restype = ctypes.c_int
+    L.ptk_synth_pathtracker.argtypes = [u64, u64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ptk_last_error().decode("utf-8", "replace")
+        raise PtkError(f"{what} failed (code {rc}): {msg}")
+
+
+def param_offsets(dims):
+    arr = (ctypes.c_int64 * (PTK_INT_NPARAM + 1))()
+    check(lib().ptk_int_param_offsets(ctypes.byref(dims), arr), "ptk_int_param_offsets")
+    return list(arr)

@@ -1,0 +1,217 @@
+// C ABI of libptk_b200 (see include/ptk_b200.h): argument checking, workspace carving, dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ptk_common.cuh"
+#include "ptk_int.h"
+
+namespace ptk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int check_dims(const PtkDims* d, const char* who) {
+  if (!d) { set_error("%s: dims is NULL", who); return PTK_EINVAL; }
+  if (d->C != C || d->K != KS) {
+    set_error("%s: only dimensions=32, kernel_size=7 are built (got C=%d K=%d); utils/engine.py:75 never uses others",
+              who, d->C, d->K);
+    return PTK_EUNSUPPORTED;
+  }
+  if (d->B < 1 || d->T < 1 || d->H < 16 || d->W < 32 || d->H % 16 || d->W % 32) {
+    set_error("%s: unsupported shape B=%d T=%d H=%d W=%d (need B,T >= 1, H %% 16 == 0, W %% 32 == 0)", who, d->B,
+              d->T, d->H, d->W);
+    return PTK_EINVAL;
+  }
+  if (d->cell != PTK_CELL_INT && d->cell != PTK_CELL_HGRU) { set_error("%s: bad cell %d", who, d->cell); return PTK_EINVAL; }
+  if (d->act != PTK_ACT_SOFTPLUS && d->act != PTK_ACT_TANH) { set_error("%s: bad act %d", who, d->act); return PTK_EINVAL; }
+  if (d->no_inh) { set_error("%s: no_inh=True variant is not built yet", who); return PTK_EUNSUPPORTED; }
+  if (d->conv_mode != PTK_CONV_FP32) { set_error("%s: conv_mode %d is not built yet", who, d->conv_mode); return PTK_EUNSUPPORTED; }
+  return PTK_OK;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base((char*)p) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = base ? (T*)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+static size_t state_elems(const PtkDims* d) { return (size_t)d->B * C * d->H * d->W; }
+
+// carve the workspace into the IntDev scratch pointers; returns bytes needed
+static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, float** wprep, float** gateT) {
+  Carver cv(ws);
+  const size_t S = state_elems(dm);
+  const int tiles = (int)(S / C / PT);
+  float* w = cv.take<float>(4 * (size_t)C * C * TAPS);
+  float* gt = cv.take<float>(6 * C * C);
+  float* A = cv.take<float>(S);
+  float* Ge = cv.take<float>(S);
+  float* Gex = cv.take<float>(S);
+  float* big = cv.take<float>(7 * S);   // inference ring (6S) or backward scratch (7S)
+  float* ring_stats = cv.take<float>(4 * C);
+  float* bn_part = cv.take<float>((size_t)conv_num_ctas(dm->B, dm->H, dm->W) * C * 2);
+  unsigned* counter = cv.take<unsigned>(4);
+  float* acc = cv.take<float>((size_t)tiles * ACC_N);
+  float* bn_sums = cv.take<float>((size_t)tiles * 2 * C);
+  float* bn_tot = cv.take<float>(2 * C);
+  double* bn_acc = cv.take<double>(4 * C);
+  float* head = cv.take<float>((size_t)dm->B * HEAD_N);
+  float* wacc_exc = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
+  float* wacc_inh = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
+  if (d) {
+    d->A = A; d->Ge = Ge; d->Gex = Gex;
+    d->bn_part = bn_part; d->counter = counter;
+    d->acc = acc; d->bn_sums = bn_sums; d->bn_tot = bn_tot; d->bn_acc = bn_acc; d->head = head;
+    d->wacc_exc = wacc_exc; d->wacc_inh = wacc_inh;
+    // backward scratch view of `big`
+    d->gE = big; d->gI = big + S; d->geb = big + 2 * S; d->dAct = big + 3 * S; d->dGe = big + 4 * S;
+    d->dX = big + 5 * S; d->dS = big + 6 * S;
+    // inference ring view of `big` (only used when saved == NULL)
+    if (d->ck_ring) {
+      d->ckI = big; d->ckE = big + 2 * S; d->ck_stride = S;
+      d->Y0 = big + 4 * S; d->Y1 = big + 5 * S; d->y_stride = 0;
+      d->stats = ring_stats;
+    }
+    d->w_inh_f = w; d->w_inh_d = w + (size_t)C * C * TAPS;
+    d->w_exc_f = w + 2 * (size_t)C * C * TAPS; d->w_exc_d = w + 3 * (size_t)C * C * TAPS;
+    for (int i = 0; i < 6; ++i) d->gateT[i] = gt + i * C * C;
+  }
+  if (wprep) *wprep = w;
+  if (gateT) *gateT = gt;
+  return (cv.off + 255) & ~(size_t)255;
+}
+
+static void bind_params(IntDev* d, const float* p) {
+  const ParamOffsets po = param_offsets(C, KS);
+  d->Wp = p + po.o[PTK_P_PREPROC_W]; d->bp = p + po.o[PTK_P_PREPROC_B];
+  d->alpha = p + po.o[PTK_P_ALPHA]; d->mu = p + po.o[PTK_P_MU];
+  d->gamma = p + po.o[PTK_P_GAMMA]; d->kappa = p + po.o[PTK_P_KAPPA];
+  for (int i = 0; i < 6; ++i) {
+    d->gate[i] = p + po.o[PTK_P_AW_W + 2 * i];
+    d->gate_b[i] = p + po.o[PTK_P_AW_B + 2 * i];
+  }
+  d->bn_w[0] = p + po.o[PTK_P_BN0_W]; d->bn_b[0] = p + po.o[PTK_P_BN0_B];
+  d->bn_w[1] = p + po.o[PTK_P_BN1_W]; d->bn_b[1] = p + po.o[PTK_P_BN1_B];
+  d->Wr = p + po.o[PTK_P_READOUT_W]; d->br = p + po.o[PTK_P_READOUT_B];
+  d->Wt = p + po.o[PTK_P_TARGET_W]; d->bt = p + po.o[PTK_P_TARGET_B];
+  d->Wd = p + po.o[PTK_P_DENSE_W]; d->bd = p + po.o[PTK_P_DENSE_B];
+}
+
+static void bind_saved(IntDev* d, const PtkDims* dm, void* saved) {
+  const size_t S = state_elems(dm);
+  float* s = (float*)saved;
+  d->ck_ring = 0;
+  d->ckI = s; d->ckE = s + (size_t)(dm->T + 1) * S; d->ck_stride = S;
+  d->Y0 = s + 2 * (size_t)(dm->T + 1) * S; d->Y1 = d->Y0 + (size_t)dm->T * S; d->y_stride = S;
+  d->stats = d->Y1 + (size_t)dm->T * S;
+}
+
+static int prep(IntDev* d, const float* params, cudaStream_t st) {
+  const ParamOffsets po = param_offsets(C, KS);
+  IntGateSrc g;
+  for (int i = 0; i < 6; ++i) g.w[i] = d->gate[i];
+  return run_prep_weights(params + po.o[PTK_P_W_INH], params + po.o[PTK_P_W_EXC], (float*)d->w_inh_f,
+                          (float*)d->w_inh_d, (float*)d->w_exc_f, (float*)d->w_exc_d, g, (float*)d->gateT[0], st);
+}
+
+}  // namespace ptk
+
+using namespace ptk;
+
+extern "C" {
+
+int ptk_version(void) { return PTK_VERSION; }
+const char* ptk_last_error(void) { return g_err; }
+
+int ptk_int_param_offsets(const PtkDims* d, int64_t* offsets) {
+  if (!d || !offsets) { set_error("ptk_int_param_offsets: NULL argument"); return PTK_EINVAL; }
+  if (d->C < 1 || d->K < 1) { set_error("ptk_int_param_offsets: bad C/K"); return PTK_EINVAL; }
+  const ParamOffsets po = param_offsets(d->C, d->K);
+  memcpy(offsets, po.o, sizeof(po.o));
+  return PTK_OK;
+}
+
+size_t ptk_int_saved_bytes(const PtkDims* d) {
+  if (check_dims(d, "ptk_int_saved_bytes")) return 0;
+  const size_t S = state_elems(d);
+  return ((size_t)(2 * (d->T + 1) + 2 * d->T) * S + (size_t)d->T * 4 * C) * sizeof(float);
+}
+
+size_t ptk_int_workspace_bytes(const PtkDims* d) {
+  if (check_dims(d, "ptk_int_workspace_bytes")) return 0;
+  return carve_workspace(d, nullptr, nullptr, nullptr, nullptr);
+}
+
+int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5], const float* params,
+                    float* logits, void* saved, float* gates, float* states, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  int rc = check_dims(dm, "ptk_int_forward");
+  if (rc) return rc;
+  if (!x || !x_strides || !params || !logits || !workspace) { set_error("ptk_int_forward: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_int_workspace_bytes(dm)) {
+    set_error("ptk_int_forward: workspace too small (%zu < %zu)", workspace_bytes, ptk_int_workspace_bytes(dm));
+    return PTK_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  IntDev d;
+  memset(&d, 0, sizeof(d));
+  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W;
+  d.fv = FrameView{x, x_strides[0], x_strides[1], x_strides[2], x_strides[3], x_strides[4]};
+  bind_params(&d, params);
+  d.ck_ring = (saved == nullptr);
+  if (saved) bind_saved(&d, dm, saved);
+  carve_workspace(dm, workspace, &d, nullptr, nullptr);
+  const size_t S = state_elems(dm);
+  if (gates) { d.A = gates; d.a_tstride = (long long)C * d.H * d.W; d.a_bstride = (long long)d.T * C * d.H * d.W; }
+  else { d.a_tstride = 0; d.a_bstride = (long long)C * d.H * d.W; }
+  d.states = states;
+  d.logits = logits;
+  PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
+  PTK_CUDA_OK(cudaMemsetAsync(d.ckI, 0, S * sizeof(float), st));   // I_0 = 0 (models/InT.py:218)
+  PTK_CUDA_OK(cudaMemsetAsync(d.ckE, 0, S * sizeof(float), st));   // E_0 = 0 (models/InT.py:217)
+  if ((rc = prep(&d, params, st))) return rc;
+  return run_int_forward(d, dm->cell, dm->act, st);
+}
+
+int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[5], const float* params,
+                     const void* saved, const float* dlogits, float* dparams, float* dx, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  int rc = check_dims(dm, "ptk_int_backward");
+  if (rc) return rc;
+  if (!x || !x_strides || !params || !saved || !dlogits || !dparams || !workspace) {
+    set_error("ptk_int_backward: NULL argument (forward must have been given a `saved` buffer)");
+    return PTK_EINVAL;
+  }
+  if (workspace_bytes < ptk_int_workspace_bytes(dm)) {
+    set_error("ptk_int_backward: workspace too small (%zu < %zu)", workspace_bytes, ptk_int_workspace_bytes(dm));
+    return PTK_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  IntDev d;
+  memset(&d, 0, sizeof(d));
+  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W;
+  d.fv = FrameView{x, x_strides[0], x_strides[1], x_strides[2], x_strides[3], x_strides[4]};
+  bind_params(&d, params);
+  bind_saved(&d, dm, const_cast<void*>(saved));
+  carve_workspace(dm, workspace, &d, nullptr, nullptr);
+  d.a_tstride = 0; d.a_bstride = (long long)C * d.H * d.W;
+  d.dlogits = dlogits; d.dparams = dparams; d.dx = dx;
+  PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
+  if ((rc = prep(&d, params, st))) return rc;   // the workspace may have been reused since forward
+  return run_int_backward(d, dm->cell, dm->act, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// Shared device/host helpers for libptk_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ptk_b200.h"
+
+namespace ptk {
+
+constexpr int C = 32;        // hidden channels (utils/engine.py:75 dimensions=32)
+constexpr int KS = 7;        // horizontal kernel (utils/engine.py:75 fb_kernel_size=7)
+constexpr int TAPS = KS * KS;
+constexpr int PT = 128;      // pixels per point-wise tile (one thread per pixel)
+constexpr float BN_EPS = 1e-3f;  // models/InT.py:102
+
+// ---- error plumbing (thread-local message, see ptk_last_error) ----------------------------
+void set_error(const char* fmt, ...);
+#define PTK_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ptk::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                  \
+                     cudaGetErrorString(_e));                                              \
+      return PTK_ECUDA;                                                                    \
+    }                                                                                      \
+  } while (0)
+#define PTK_LAUNCH_OK(name)                                                                \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      ptk::set_error("launch of %s failed at %s:%d: %s", name, __FILE__, __LINE__,         \
+                     cudaGetErrorString(_e));                                              \
+      return PTK_ECUDA;                                                                    \
+    }                                                                                      \
+  } while (0)
+
+// ---- math ----------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// activation `nl` of InT.__init__ (models/InT.py:184,208): softplus(beta=1, threshold=20) or tanh
+template <int ACT>
+__device__ __forceinline__ float actf(float x) {
+  if (ACT == PTK_ACT_SOFTPLUS) return x > 20.0f ? x : log1pf(expf(x));
+  return tanhf(x);
+}
+template <int ACT>
+__device__ __forceinline__ float dactf(float x) {
+  if (ACT == PTK_ACT_SOFTPLUS) return x > 20.0f ? 1.0f : sigmoidf_(x);
+  float t = tanhf(x);
+  return 1.0f - t * t;
+}
+
+// acc[o] += sum_i sW[i*32 + o] * v[i]; sW in shared memory ([in][out]); every lane reads the
+// same address, so each float4 is one broadcast wavefront.
+__device__ __forceinline__ void matvec32(float (&acc)[C], const float* __restrict__ sW,
+                                         const float (&v)[C]) {
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const float4* w4 = reinterpret_cast<const float4*>(sW + i * C);
+    const float vi = v[i];
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+      const float4 w = w4[q];
+      acc[4 * q + 0] = fmaf(w.x, vi, acc[4 * q + 0]);
+      acc[4 * q + 1] = fmaf(w.y, vi, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(w.z, vi, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(w.w, vi, acc[4 * q + 3]);
+    }
+  }
+}
+
+// ---- cp.async (LDGSTS) ---------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+// 16-byte copy that zero-fills when !valid (src-size 0)
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, bool valid) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- frame addressing: x is [B,3,T,H,W] with arbitrary element strides ---------------------
+struct FrameView {
+  const float* x;
+  long long sb, sc, st, sy, sx;
+  __device__ __forceinline__ float at(int b, int c, int t, int y, int xx) const {
+    return __ldg(x + b * sb + c * sc + t * st + y * sy + xx * sx);
+  }
+};
+
+// ---- flat parameter vector -----------------------------------------------------------------
+struct ParamOffsets {
+  int64_t o[PTK_INT_NPARAM + 1];
+};
+inline ParamOffsets param_offsets(int Cc, int K) {
+  const int64_t sizes[PTK_INT_NPARAM] = {
+      Cc * 3, Cc, (int64_t)Cc * Cc * K * K, (int64_t)Cc * Cc * K * K, Cc, Cc, Cc, Cc,
+      Cc * Cc, Cc, Cc * Cc, Cc, Cc * Cc, Cc, Cc * Cc, Cc, Cc * Cc, Cc, Cc * Cc, Cc,
+      Cc, Cc, Cc, Cc, Cc, 1, 50, 1, 1, 1};
+  ParamOffsets r;
+  int64_t a = 0;
+  for (int i = 0; i < PTK_INT_NPARAM; ++i) {
+    r.o[i] = a;
+    a += sizes[i];
+  }
+  r.o[PTK_INT_NPARAM] = a;
+  return r;
+}
+
+}  // namespace ptk

@@ -1,0 +1,31 @@
+// Internal kernel argument structs + host launchers shared between translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptk {
+
+struct ConvArgs {
+  const float* in;     // [B,32,H,W]
+  const float* wT;     // [32 ic][49 taps][32 oc]
+  float* out;          // [B,32,H,W]
+  int B, H, W;
+  int accumulate;      // out += conv (dgrad into an existing gradient)
+  float* part;         // [nCTA][32][2] per-CTA (mean, M2) or nullptr (no statistics)
+  unsigned* counter;   // arrival counter for the last-CTA fold (self-resetting)
+  float* stats_out;    // [2][32] mean, rstd
+};
+
+struct WgradArgs {
+  const float* in;     // conv input [B,32,H,W]
+  const float* dy;     // gradient wrt conv output [B,32,H,W]
+  float* wacc;         // [4*G][49][256] per-CTA accumulators
+  int B, H, W;
+  int first;           // overwrite instead of accumulate
+};
+
+int conv_num_ctas(int B, int H, int W);
+int launch_conv7(const ConvArgs& a, cudaStream_t st);
+int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
+
+}  // namespace ptk

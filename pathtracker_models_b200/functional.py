@@ -1,0 +1,121 @@
+"""torch.autograd bridge to the C ABI: raw device pointers + the current CUDA stream go to
+ptk_int_forward / ptk_int_backward (include/ptk_b200.h); torch only owns memory and streams."""
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+
+class IntConfig:
+    """static configuration of one recurrent circuit instance (maps onto PtkDims)."""
+
+    def __init__(self, C=32, K=7, cell=_lib.PTK_CELL_INT, act=_lib.PTK_ACT_SOFTPLUS, no_inh=False,
+                 conv_mode=_lib.PTK_CONV_FP32):
+        self.C, self.K, self.cell, self.act, self.no_inh, self.conv_mode = C, K, cell, act, bool(no_inh), conv_mode
+
+    def dims(self, x):
+        B, ch, T, H, W = x.shape
+        if ch != 3:
+            raise ValueError(f"expected x of shape [B,3,T,H,W], got {tuple(x.shape)}")
+        return _lib.PtkDims(B, T, H, W, self.C, self.K, self.cell, self.act, int(self.no_inh), self.conv_mode)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _strides(x):
+    return (ctypes.c_int64 * 5)(*x.stride())
+
+
+def _check_inputs(x, flat):
+    if not x.is_cuda:
+        raise _lib.PtkError("pathtracker_models_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    if x.dtype != torch.float32 or flat.dtype != torch.float32:
+        raise _lib.PtkError("the recurrent core computes in float32; got x=%s params=%s" % (x.dtype, flat.dtype))
+    if flat.device != x.device:
+        raise _lib.PtkError("parameters and input are on different devices")
+
+
+def _buffers(L, dims, device, want_saved):
+    ws_bytes = L.ptk_int_workspace_bytes(ctypes.byref(dims))
+    if ws_bytes == 0:
+        _lib.check(1, "ptk_int_workspace_bytes")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    saved = None
+    if want_saved:
+        saved = torch.empty(L.ptk_int_saved_bytes(ctypes.byref(dims)), dtype=torch.uint8, device=device)
+    return ws, ws_bytes, saved
+
+
+def int_forward_raw(x, flat, cfg, want_saved, testmode=False):
+    """one call of ptk_int_forward on x.device's current stream. returns logits[B], saved, gates, states"""
+    _check_inputs(x, flat)
+    L = _lib.lib()
+    dims = cfg.dims(x)
+    B, _, T, H, W = x.shape
+    flat = flat.contiguous()
+    with torch.cuda.device(x.device):
+        ws, ws_bytes, saved = _buffers(L, dims, x.device, want_saved)
+        logits = torch.empty(B, dtype=torch.float32, device=x.device)
+        gates = states = None
+        if testmode:
+            gates = torch.empty(B, T, cfg.C, H, W, dtype=torch.float32, device=x.device)
+            states = torch.empty(B, T, 1, H, W, dtype=torch.float32, device=x.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        rc = L.ptk_int_forward(ctypes.byref(dims), _ptr(x), _strides(x), _ptr(flat), _ptr(logits), _ptr(saved),
+                               _ptr(gates), _ptr(states), _ptr(ws), ws_bytes, stream)
+        _lib.check(rc, "ptk_int_forward")
+    return logits, saved, gates, states
+
+
+class _IntFunction(torch.autograd.Function):
+    """logits = InT/FFhGRU time loop (x, flat parameters); backward = hand-written BPTT kernels."""
+
+    @staticmethod
+    def forward(ctx, x, flat, cfg):
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        logits, saved, _, _ = int_forward_raw(x, flat, cfg, want_saved=need)
+        ctx.cfg = cfg
+        ctx.saved_buf = saved
+        ctx.save_for_backward(x, flat)
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dlogits):
+        x, flat = ctx.saved_tensors
+        cfg = ctx.cfg
+        L = _lib.lib()
+        dims = cfg.dims(x)
+        flat = flat.contiguous()
+        dlogits = dlogits.contiguous().float()
+        with torch.cuda.device(x.device):
+            ws, ws_bytes, _ = _buffers(L, dims, x.device, False)
+            dflat = torch.empty_like(flat)
+            dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
+            stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            rc = L.ptk_int_backward(ctypes.byref(dims), _ptr(x), _strides(x), _ptr(flat), _ptr(ctx.saved_buf),
+                                    _ptr(dlogits), _ptr(dflat), _ptr(dx), _ptr(ws), ws_bytes, stream)
+            _lib.check(rc, "ptk_int_backward")
+        ctx.saved_buf = None
+        return dx, dflat, None
+
+
+def int_apply(x, flat, cfg):
+    return _IntFunction.apply(x, flat, cfg)
+
+
+def synth_pathtracker(B, T, H=32, W=32, n_distractors=14, speed=1, seed=1234, first_index=0, device="cuda"):
+    """on-device synthetic PathTracker batch: (x [B,3,T,H,W] float32 in {0,1}, y [B,1] float32)."""
+    L = _lib.lib()
+    device = torch.device(device)
+    with torch.cuda.device(device):
+        x = torch.empty(B, 3, T, H, W, dtype=torch.float32, device=device)
+        y = torch.empty(B, dtype=torch.float32, device=device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        rc = L.ptk_synth_pathtracker(seed, first_index, B, T, H, W, n_distractors, speed, _ptr(x), _ptr(y), stream)
+        _lib.check(rc, "ptk_synth_pathtracker")
+    return x, y.view(B, 1)

@@ -1,0 +1,168 @@
+"""GPU parity: the CUDA path (through the C ABI, via the nn.Module mirror) against
+ (a) golden fixtures produced by running the reference in fp64 (tests/golden), and
+ (b) the CPU oracle on the same seeded inputs, tensor by tensor.
+Tolerance: per tensor max|a-b|/max|b| <= 1e-4 against the fp64 reference, or <= 4x the
+fp32 reference's own error vs fp64 for that tensor."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import REL_TOL, check_parity, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(case, kind, **kw):
+    from pathtracker_models_b200 import InT, ffhgru_hierarchy
+    if kind == "int":
+        m = InT.InT(dimensions=32, timesteps=8, kernel_size=7, **kw)
+    else:
+        m = ffhgru_hierarchy.FFhGRU(dimensions=32, timesteps=8, kernel_size=7)
+    m.load_state_dict(case["sd"])
+    return m.cuda()
+
+
+def _run(case, m, x=None):
+    x = case["x"].float().cuda() if x is None else x
+    y = case["y"].float().cuda()
+    out, pen = m(x)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    return out, loss, grads, pen
+
+
+CASES = [("int_small", "int", {}), ("int_tile", "int", {}), ("int_cfg1", "int", {}), ("int_64px", "int", {}),
+         ("int_tanh_small", "int", {"nl": torch.tanh}),
+         ("int_lesion_small", "int", {"lesion_alpha": True, "lesion_gamma": True}),
+         ("hgru_small", "hgru", {}), ("hgru_tile", "hgru", {})]
+
+
+@pytest.mark.parametrize("name,kind,kw", CASES)
+def test_logits_and_all_grads_vs_fp64_reference(name, kind, kw):
+    case = load_case(name)
+    m = _model(case, kind, **kw)
+    out, loss, grads, pen = _run(case, m)
+    assert out.shape == (case["shape"][0], 1) and pen.shape == (1,) and pen.device == out.device
+    assert abs(loss.item() - case["loss"]) < 1e-5
+    bad = check_parity(case, out, grads)
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+    assert grads["unit1.w"] is None          # dead parameter gets no gradient
+
+
+def test_per_step_checkpoints_vs_oracle():
+    """localises a failure: every I_t, E_t, pre-BN conv output and BN statistic of the CUDA forward."""
+    from oracle import int_oracle as O
+    from pathtracker_models_b200.functional import int_forward_raw
+    case = load_case("int_small")
+    m = _model(case, "int")
+    x = case["x"].float().cuda()
+    logits, saved, _, _ = int_forward_raw(x, m.flat_parameters().detach(), m._config(), want_saved=True)
+    B, T, H, W = case["shape"]
+    S = B * 32 * H * W
+    sv = saved.view(torch.float32).cpu()
+    ckI = sv[:(T + 1) * S].view(T + 1, B, 32, H, W)
+    ckE = sv[(T + 1) * S:2 * (T + 1) * S].view(T + 1, B, 32, H, W)
+    Y0 = sv[2 * (T + 1) * S:2 * (T + 1) * S + T * S].view(T, B, 32, H, W)
+    Y1 = sv[2 * (T + 1) * S + T * S:2 * (T + 1) * S + 2 * T * S].view(T, B, 32, H, W)
+    st = sv[2 * (T + 1) * S + 2 * T * S:].view(T, 2, 2, 32)
+    p = O.unpack(case["sd"])
+    with torch.no_grad():
+        lo, so = O.forward(case["x"], p)
+    for t in range(T):
+        assert rel_err(Y0[t], so["Y0"][t]) < 2e-5 or so["Y0"][t].abs().max() == 0, f"Y0[{t}]"
+        assert rel_err(st[t, 0, 0], so["m0"][t]) < 2e-5 or t == 0, f"mean0[{t}]"
+        assert rel_err(st[t, 0, 1], so["r0"][t]) < 2e-5, f"rstd0[{t}]"
+        assert rel_err(ckI[t + 1], so["I"][t + 1]) < 2e-5, f"I[{t + 1}]"
+        assert rel_err(Y1[t], so["Y1"][t]) < 2e-5, f"Y1[{t}]"
+        assert rel_err(st[t, 1, 0], so["m1"][t]) < 2e-5, f"mean1[{t}]"
+        assert rel_err(st[t, 1, 1], so["r1"][t]) < 2e-5, f"rstd1[{t}]"
+        assert rel_err(ckE[t + 1], so["E"][t + 1]) < 2e-5, f"E[{t + 1}]"
+    assert rel_err(logits, lo) < 1e-5
+
+
+@pytest.mark.parametrize("name,kind", [("int_small", "int"), ("hgru_small", "hgru")])
+def test_testmode_outputs(name, kind):
+    case = load_case(name)
+    m = _model(case, kind)
+    out, states, gates = m(case["x"].float().cuda(), testmode=True)
+    B, T, H, W = case["shape"]
+    assert states.shape == (B, T, 1, H, W) and gates.shape == (B, T, 32, H, W)
+    assert rel_err(out, case["extra"]["tm_logits"]) < REL_TOL
+    assert rel_err(states, case["extra"]["tm_states"]) < REL_TOL
+    assert rel_err(gates, case["extra"]["tm_gates"]) < REL_TOL
+
+
+def test_channels_last_3d_input_and_eval_mode():
+    """utils/engine.py:222-243 hands over a channels_last_3d-strided tensor; eval() == train()."""
+    case = load_case("int_small")
+    m = _model(case, "int")
+    xc = case["x"].float().cuda()
+    xs = xc.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+    assert not xs.is_contiguous()
+    o1, _, g1, _ = _run(case, m, xc)
+    m.zero_grad(set_to_none=True)
+    o2, _, g2, _ = _run(case, m, xs)
+    assert torch.equal(o1, o2)
+    for n in g1:
+        assert (g1[n] is None and g2[n] is None) or torch.equal(g1[n], g2[n]), n
+    m.eval()
+    with torch.no_grad():
+        o3, _ = m(xc)
+    assert torch.equal(o1, o3)
+
+
+def test_determinism_and_input_gradient():
+    case = load_case("int_tile")
+    m = _model(case, "int")
+    x = case["x"].float().cuda().requires_grad_(True)
+    outs = []
+    for _ in range(2):
+        m.zero_grad(set_to_none=True)
+        x.grad = None
+        out, _ = m(x)
+        out.sum().backward()
+        outs.append((out.detach().clone(), x.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for n in outs[0][2]:
+        assert torch.equal(outs[0][2][n], outs[1][2][n]), n
+    # input gradient (viz_model_att.py:189-196) against oracle autograd in fp64
+    from oracle import int_oracle as O
+    p = O.unpack(case["sd"])
+    xo = case["x"].clone().requires_grad_(True)
+    lo, _ = O.forward(xo, p)
+    lo.sum().backward()
+    assert rel_err(outs[0][1], xo.grad) < REL_TOL
+
+
+def test_synth_generator_bit_exact_and_well_formed():
+    from oracle.synth_oracle import synth
+    from pathtracker_models_b200 import synth_pathtracker
+    for (B, T, H, W, D, speed, first) in [(5, 16, 32, 32, 14, 1, 0), (3, 8, 64, 64, 0, 4, 1000), (4, 12, 32, 32, 25, 2, 7)]:
+        x, y = synth_pathtracker(B, T, H, W, n_distractors=D, speed=speed, seed=1234, first_index=first)
+        xo, yo = synth(1234, first, B, T, H, W, D, speed)
+        assert np.array_equal(x.cpu().numpy(), xo) and np.array_equal(y.cpu().numpy().ravel(), yo)
+        assert set(np.unique(xo)) <= {0.0, 1.0} and x.shape == (B, 3, T, H, W) and y.shape == (B, 1)
+        assert (xo[:, 0].reshape(B, T, -1).sum(-1) >= 1).all()          # the target is always drawn
+        assert (xo[:, 1].reshape(B, T, -1).sum(-1) == 9).all() and (xo[:, 2].reshape(B, T, -1).sum(-1) == 9).all()
+    # disjoint deterministic shards: rank r's shard == slice of the global batch
+    xa, _ = synth_pathtracker(8, 8, 32, 32, first_index=0)
+    xb, _ = synth_pathtracker(4, 8, 32, 32, first_index=4)
+    assert torch.equal(xa[4:], xb)
+
+
+def test_errors_are_loud():
+    from pathtracker_models_b200 import InT, _lib
+    m = InT.InT(dimensions=32, timesteps=4, kernel_size=7).cuda()
+    with pytest.raises(_lib.PtkError):
+        m(torch.rand(2, 3, 4, 20, 20, device="cuda"))          # unsupported frame size
+    with pytest.raises(_lib.PtkError):
+        m(torch.rand(2, 3, 4, 32, 32))                         # CPU tensor: no fallback
+    with pytest.raises(_lib.PtkError):
+        InT.InT(dimensions=32, timesteps=4, kernel_size=15).cuda()(torch.rand(1, 3, 2, 32, 32, device="cuda"))
+    d = _lib.PtkDims(1, 1, 32, 32, 32, 7, 0, 0, 0, 0)
+    L = _lib.lib()
+    rc = L.ptk_int_forward(ctypes.byref(d), None, None, None, None, None, None, None, None, 0, None)
+    assert rc == 1 and b"NULL" in L.ptk_last_error()
