@@ -117,6 +117,15 @@ PTK_API int ptk_synth_pathtracker(uint64_t seed, uint64_t first_index, int32_t B
                           int32_t W, int32_t n_distractors, int32_t speed, float* x, float* y,
                           void* stream);
 
+/* Measurement hooks (used by bench.py; off by default, no effect on results).
+ * ptk_profile_start(): from now on every kernel-class launch is bracketed by cudaEvents on its stream.
+ * ptk_profile_stop(ms, count): synchronises those events; fills ms[k] / count[k] for the 7 classes
+ *   0 conv fwd, 1 conv dgrad, 2 wgrad, 3 point-wise fwd, 4 point-wise bwd, 5 bn-apply, 6 misc.
+ * ptk_launch_count(): kernels launched by this library in this process so far. */
+PTK_API void ptk_profile_start(void);
+PTK_API int ptk_profile_stop(double* ms, long long* count);
+PTK_API long long ptk_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

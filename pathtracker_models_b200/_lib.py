@@ -15,7 +15,8 @@ PTK_CONV_FP32, PTK_CONV_BF16X3 = 0, 1
 PTK_INT_NPARAM = 30
 
 EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_saved_bytes",
-           "ptk_int_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker")
+           "ptk_int_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker",
+           "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count")
 
 
 class PtkDims(ctypes.Structure):
@@ -59,6 +60,12 @@ def lib():
     L.ptk_int_backward.argtypes = [dp, vp, i64p, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_synth_pathtracker.restype = ctypes.c_int
     L.ptk_synth_pathtracker.argtypes = [u64, u64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.ptk_profile_start.restype = None
+    L.ptk_profile_start.argtypes = []
+    L.ptk_profile_stop.restype = ctypes.c_int
+    L.ptk_profile_stop.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]
+    L.ptk_launch_count.restype = ctypes.c_longlong
+    L.ptk_launch_count.argtypes = []
     _lib = L
     return L
 
@@ -73,3 +80,22 @@ def param_offsets(dims):
     arr = (ctypes.c_int64 * (PTK_INT_NPARAM + 1))()
     check(lib().ptk_int_param_offsets(ctypes.byref(dims), arr), "ptk_int_param_offsets")
     return list(arr)
+
+
+PROF_KINDS = ("conv_fwd", "conv_dgrad", "wgrad", "pointwise_fwd", "pointwise_bwd", "bn_apply", "misc")
+
+
+def profile_start():
+    lib().ptk_profile_start()
+
+
+def profile_stop():
+    """-> {kind: (total_ms, launches)} measured with CUDA events on the launching stream."""
+    ms = (ctypes.c_double * len(PROF_KINDS))()
+    cnt = (ctypes.c_longlong * len(PROF_KINDS))()
+    lib().ptk_profile_stop(ms, cnt)
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(PROF_KINDS)}
+
+
+def launch_count():
+    return int(lib().ptk_launch_count())

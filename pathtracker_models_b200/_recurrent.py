@@ -32,7 +32,8 @@ class _CellParams(nn.Module):
     """Parameters of one recurrent cell.  `order` reproduces the RNG consumption order of the
     reference constructor so that torch.manual_seed(s); Cell(...) is bit-identical to it."""
 
-    def __init__(self, hidden_size, kernel_size, timesteps, order, no_inh=False, init_w=None, lesions=()):
+    def __init__(self, hidden_size, kernel_size, timesteps, order, no_inh=False, init_w=None, lesions=(),
+                 scalars=("alpha", "mu", "gamma", "kappa", "w")):
         super().__init__()
         self.hidden_size, self.kernel_size, self.timesteps = hidden_size, kernel_size, timesteps
         self.padding = self.h_padding = kernel_size // 2
@@ -51,7 +52,7 @@ class _CellParams(nn.Module):
         for name in order:                       # InT: exc then inh; hGRU: inh then exc
             if hasattr(self, name):
                 init.orthogonal_(getattr(self, name))
-        for n in ("alpha", "mu", "gamma", "kappa", "w"):
+        for n in scalars:                        # registration order == state_dict order of the reference
             setattr(self, n, nn.Parameter(torch.empty(C, 1, 1)))
         self.bn = nn.ModuleList([nn.BatchNorm2d(C, eps=1e-03, affine=True, track_running_stats=False)
                                  for _ in range(2)])
@@ -119,6 +120,10 @@ class _RecurrentModel(nn.Module):
             with torch.no_grad():
                 logits, _, gates, states = int_forward_raw(x, flat, cfg, want_saved=False, testmode=True)
             return logits.view(B, 1), states, gates
+        if getattr(self, "_dp_enabled", False) and flat.requires_grad:
+            from .parallel import average_flat_gradient_
+            group = self._dp_group
+            flat.register_hook(lambda g: average_flat_gradient_(g.contiguous(), group))
         logits = int_apply(x, flat, cfg)
         jv_penalty = torch.ones(1, dtype=torch.float32, device=x.device)   # models/InT.py:243
         return logits.view(B, 1), jv_penalty

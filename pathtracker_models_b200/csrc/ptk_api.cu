@@ -69,12 +69,13 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, float** wp
   float* bn_tot = cv.take<float>(2 * C);
   double* bn_acc = cv.take<double>(4 * C);
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);
+  float* dgoal = cv.take<float>(S / C);
   float* wacc_exc = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
   float* wacc_inh = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
   if (d) {
     d->A = A; d->Ge = Ge; d->Gex = Gex;
     d->bn_part = bn_part; d->counter = counter;
-    d->acc = acc; d->bn_sums = bn_sums; d->bn_tot = bn_tot; d->bn_acc = bn_acc; d->head = head;
+    d->acc = acc; d->bn_sums = bn_sums; d->bn_tot = bn_tot; d->bn_acc = bn_acc; d->head = head; d->dgoal = dgoal;
     d->wacc_exc = wacc_exc; d->wacc_inh = wacc_inh;
     // backward scratch view of `big`
     d->gE = big; d->gI = big + S; d->geb = big + 2 * S; d->dAct = big + 3 * S; d->dGe = big + 4 * S;

@@ -50,6 +50,7 @@ struct IntDev {
   float* bn_tot;           // [2][C]  (sum dV)/N, (sum dV*xhat)/N of the current BatchNorm
   double* bn_acc;          // [2 bn][2][C] accumulated over steps: d(bn weight), d(bn bias)
   float* head;             // [B][HEAD_N]
+  float* dgoal;            // [B][P] gradient of the goal map x[:,2,0] through the readout
   float *wacc_exc, *wacc_inh;
   float* dx;               // optional [B,3,T,H,W]
   float* dparams;

@@ -20,6 +20,7 @@
 // `finalize` folds the tiles in double precision.
 #include "ptk_common.cuh"
 #include "ptk_int.h"
+#include "ptk_profile.h"
 
 namespace ptk {
 
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(PT) int_bwd_d_kernel(IntDev d, int t, int firs
   if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
     const size_t plane = (size_t)d.T * P;
     float* o = d.dx + (size_t)b * 3 * plane + (size_t)t * P + pix;
+    if (t == 0) dx2 += d.dgoal[(size_t)b * P + pix];
     o[0] = dx0; o[plane] = dx1; o[2 * plane] = dx2;
   }
   __syncthreads();
@@ -536,15 +538,16 @@ __global__ void __launch_bounds__(256) int_readout_bwd_kernel(IntDev d, const fl
   float sbr = 0.f;
   for (int pix = tid; pix < P; pix += 256) {
     const int y = pix / W, x = pix % W;
-    float wsum = 0.f;
+    float wsum = 0.f, gsum = 0.f;
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         const int yy = y - ky + 2, xx = x - kx + 2;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) wsum += sWt[ky * 5 + kx];
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) { wsum += sWt[ky * 5 + kx]; gsum += sWt[25 + ky * 5 + kx]; }
       }
     const float dr = dov * wsum;
+    d.dgoal[(size_t)b * P + pix] = dov * gsum;   // d x[b,2,0,y,x] via torch.cat(..., x[:,2,0]) (InT.py:236)
     sDr[pix] = dr;
     sbr += dr;
   }
@@ -635,36 +638,47 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
   PTK_CUDA_OK(cudaFuncSetAttribute(int_readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-  int_readout_bwd_kernel<<<d.B, 256, smr, st>>>(d, d.ckE + d.ck_stride * d.T);
+  { ProfileScope ps(PTK_PROF_MISC, st);
+  int_readout_bwd_kernel<<<d.B, 256, smr, st>>>(d, d.ckE + d.ck_stride * d.T); }
   PTK_LAUNCH_OK("int_readout_bwd_kernel");
   const int ew_blocks = 148 * 4;
   for (int t = d.T - 1; t >= 0; --t) {
     const int first = (t == d.T - 1);
     int rc;
-    int_bwd_a_kernel<CELL, ACT><<<tiles, PT, SM_BWD_A, st>>>(d, t, first);
+    { ProfileScope ps(PTK_PROF_POINT_BWD, st);
+    int_bwd_a_kernel<CELL, ACT><<<tiles, PT, SM_BWD_A, st>>>(d, t, first); }
     PTK_LAUNCH_OK("int_bwd_a_kernel");
-    bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1 + d.y_stride * t, t, 1);
+    { ProfileScope ps(PTK_PROF_BN_APPLY, st);
+    bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1 + d.y_stride * t, t, 1); }
     PTK_LAUNCH_OK("bn_apply_kernel");
     ConvArgs c1{d.dAct, d.w_exc_d, d.gI, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr};
-    if ((rc = launch_conv7(c1, st))) return rc;
+    { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
+    if (rc) return rc;
     WgradArgs w1{d.ckI + d.ck_stride * (t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
-    if ((rc = launch_wgrad7(w1, WGRAD_GROUPS, st))) return rc;
-    int_bwd_c_kernel<CELL, ACT><<<tiles, PT, SM_BWD_C, st>>>(d, t, first);
+    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w1, WGRAD_GROUPS, st); }
+    if (rc) return rc;
+    { ProfileScope ps(PTK_PROF_POINT_BWD, st);
+    int_bwd_c_kernel<CELL, ACT><<<tiles, PT, SM_BWD_C, st>>>(d, t, first); }
     PTK_LAUNCH_OK("int_bwd_c_kernel");
-    bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0 + d.y_stride * t, t, 0);
+    { ProfileScope ps(PTK_PROF_BN_APPLY, st);
+    bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0 + d.y_stride * t, t, 0); }
     PTK_LAUNCH_OK("bn_apply_kernel");
     ConvArgs c0{d.dAct, d.w_inh_d, d.dGe, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr};
-    if ((rc = launch_conv7(c0, st))) return rc;
+    { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
+    if (rc) return rc;
     WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
-    if ((rc = launch_wgrad7(w0, WGRAD_GROUPS, st))) return rc;
-    int_bwd_d_kernel<CELL, ACT><<<tiles, PT, SM_BWD_D, st>>>(d, t, first);
+    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w0, WGRAD_GROUPS, st); }
+    if (rc) return rc;
+    { ProfileScope ps(PTK_PROF_POINT_BWD, st);
+    int_bwd_d_kernel<CELL, ACT><<<tiles, PT, SM_BWD_D, st>>>(d, t, first); }
     PTK_LAUNCH_OK("int_bwd_d_kernel");
   }
   FinalizeArgs f;
   f.nTiles = tiles; f.B = d.B; f.wgroups = WGRAD_GROUPS;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
-  int_finalize_kernel<<<148 * 2, 256, 0, st>>>(d, f);
+  { ProfileScope ps(PTK_PROF_MISC, st);
+  int_finalize_kernel<<<148 * 2, 256, 0, st>>>(d, f); }
   PTK_LAUNCH_OK("int_finalize_kernel");
   return PTK_OK;
 }

@@ -9,6 +9,7 @@
 // 32x32 mat-vecs against shared-memory weights ([in][out], broadcast float4 reads).
 #include "ptk_common.cuh"
 #include "ptk_int.h"
+#include "ptk_profile.h"
 
 namespace ptk {
 
@@ -255,28 +256,33 @@ template <int ACT>
 static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   const int P = d.H * d.W;
   const int tiles = d.B * P / PT;
-  int_pre_kernel<ACT><<<tiles, PT, 0, st>>>(d, 0);
+  { ProfileScope ps(PTK_PROF_POINT_FWD, st);
+  int_pre_kernel<ACT><<<tiles, PT, 0, st>>>(d, 0); }
   PTK_LAUNCH_OK("int_pre_kernel");
   for (int t = 0; t < d.T; ++t) {
     const int slot_in = d.slot(t), slot_out = d.slot(t + 1);
     ConvArgs c0{d.Ge, d.w_inh_f, d.Y0 + d.y_stride * d.yslot(t), d.B, d.H, d.W, 0,
                 d.bn_part, d.counter, d.stat_w(t, 0)};
-    int rc = launch_conv7(c0, st);
+    int rc;
+    { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
     if (rc) return rc;
+    { ProfileScope ps(PTK_PROF_POINT_FWD, st);
     if (cell == PTK_CELL_INT) int_mid_kernel<PTK_CELL_INT, ACT><<<tiles, PT, 0, st>>>(d, t);
-    else int_mid_kernel<PTK_CELL_HGRU, ACT><<<tiles, PT, 0, st>>>(d, t);
+    else int_mid_kernel<PTK_CELL_HGRU, ACT><<<tiles, PT, 0, st>>>(d, t); }
     PTK_LAUNCH_OK("int_mid_kernel");
     ConvArgs c1{d.ckI + d.ck_stride * slot_out, d.w_exc_f, d.Y1 + d.y_stride * d.yslot(t), d.B, d.H,
                 d.W, 0, d.bn_part, d.counter, d.stat_w(t, 1)};
-    rc = launch_conv7(c1, st);
+    { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
-    int_post_kernel<ACT><<<tiles, PT, 0, st>>>(d, t, t + 1 < d.T);
+    { ProfileScope ps(PTK_PROF_POINT_FWD, st);
+    int_post_kernel<ACT><<<tiles, PT, 0, st>>>(d, t, t + 1 < d.T); }
     PTK_LAUNCH_OK("int_post_kernel");
     (void)slot_in;
   }
   const int slot_T = d.slot(d.T);
   const size_t sm = (size_t)2 * (d.H + 4) * (d.W + 4) * sizeof(float);
-  int_readout_kernel<<<d.B, 256, sm, st>>>(d, d.ckE + d.ck_stride * slot_T, d.logits);
+  { ProfileScope ps(PTK_PROF_MISC, st);
+  int_readout_kernel<<<d.B, 256, sm, st>>>(d, d.ckE + d.ck_stride * slot_T, d.logits); }
   PTK_LAUNCH_OK("int_readout_kernel");
   return PTK_OK;
 }
@@ -289,6 +295,7 @@ int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st) {
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st) {
   const int n = C * C * TAPS;
+  ProfileScope ps(PTK_PROF_MISC, st, 3);
   prep_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_inh, inh_f, inh_d);
   prep_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_exc, exc_f, exc_d);
   prep_gates_kernel<<<(6 * C * C + 255) / 256, 256, 0, st>>>(g, gateT);

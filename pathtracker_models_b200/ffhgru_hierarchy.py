@@ -13,7 +13,8 @@ class hConvGRUCell(_CellParams):
     def __init__(self, hidden_size, kernel_size, timesteps, batchnorm=True, grad_method='bptt', use_attention=False):
         if not use_attention:
             raise NotImplementedError("use_attention=False is unrunnable in the reference (ffhgru_hierarchy.py:148-152)")
-        super().__init__(hidden_size, kernel_size, timesteps, order=("w_inh", "w_exc"), init_w=1.)
+        super().__init__(hidden_size, kernel_size, timesteps, order=("w_inh", "w_exc"), init_w=1.,
+                         scalars=("alpha", "gamma", "kappa", "w", "mu"))   # ffhgru_hierarchy.py:101-105
 
 
 class FFhGRU(_RecurrentModel):

@@ -1,0 +1,42 @@
+"""Batch-data-parallel training of the recurrent core: one process per GPU, each rank runs the
+fused time loop on its own shard (per-replica BatchNorm statistics, exactly like the reference's
+nn.DataParallel replicas, mainclean.py:132-134) and ONE fp32 all-reduce of the flat gradient vector
+per step (NCCL over NVLink on GPUs; gloo in the CPU tests).  There is no data-path collective.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_first_index(step, rank, world, per_rank_batch):
+    """global sample index of this rank's first clip at `step` (disjoint, deterministic shards)."""
+    return (step * world + rank) * per_rank_batch
+
+
+def average_flat_gradient_(flat_grad, group=None):
+    """in-place mean over ranks of the flat gradient bucket (equals DataParallel's gradient of the
+    global-batch mean loss for equal shards).  Returns the tensor."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat_grad
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    flat_grad.div_(world)
+    return flat_grad
+
+
+def attach_data_parallel(model, group=None):
+    """make `model` (InT / FFhGRU mirror) average its flat gradient across `group` during backward.
+
+    The hook fires on the flat parameter vector right after the reverse-time kernels have been
+    enqueued, i.e. before autograd scatters the bucket back into the 30 parameter tensors, so the
+    collective is a single 0.43 MB all-reduce issued from the backward stream."""
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    model._dp_group = group
+    model._dp_enabled = True
+    return model
+
+
+def broadcast_parameters(model, src=0, group=None):
+    """replicate rank `src`'s parameters (DataParallel's replicate(), mainclean.py:133)."""
+    for p in model.parameters():
+        dist.broadcast(p.data, src=src, group=group)

@@ -1,0 +1,103 @@
+"""CPU: the drop-in boundary -- constructors, state_dict names/shapes, init RNG order, the C ABI
+library loads and exports every symbol include/ptk_b200.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import GOLDEN, load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pathtracker_models_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "ptk_b200.h")).read()
+    declared = set(re.findall(r"PTK_API\s+[\w\s\*]+?\b(ptk_\w+)\s*\(", hdr))
+    assert declared and declared == set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().ptk_version() == 100
+
+
+def test_param_layout_matches_module():
+    from pathtracker_models_b200 import InT, _lib
+    from pathtracker_models_b200._recurrent import PARAM_ORDER
+    m = InT.InT(dimensions=32, timesteps=4, kernel_size=7)
+    off = _lib.param_offsets(_lib.PtkDims(1, 1, 32, 32, 32, 7, 0, 0, 0, 0))
+    named = dict(m.named_parameters())
+    assert len(PARAM_ORDER) == _lib.PTK_INT_NPARAM
+    assert [off[i + 1] - off[i] for i in range(30)] == [named[n].numel() for n in PARAM_ORDER]
+    assert off[-1] == m.flat_parameters().numel() == 107190 - 32      # minus the dead unit1.w
+
+
+def test_dims_validation_without_gpu():
+    from pathtracker_models_b200 import _lib
+    L = _lib.lib()
+    assert L.ptk_int_workspace_bytes(ctypes.byref(_lib.PtkDims(64, 64, 32, 32, 32, 7, 0, 0, 0, 0))) > 0
+    assert L.ptk_int_saved_bytes(ctypes.byref(_lib.PtkDims(64, 64, 32, 32, 32, 7, 0, 0, 0, 0))) == \
+        ((2 * 65 + 2 * 64) * 64 * 32 * 1024 + 64 * 128) * 4
+    assert L.ptk_int_workspace_bytes(ctypes.byref(_lib.PtkDims(2, 4, 20, 20, 32, 7, 0, 0, 0, 0))) == 0
+    assert b"unsupported shape" in L.ptk_last_error()
+    assert L.ptk_int_workspace_bytes(ctypes.byref(_lib.PtkDims(2, 4, 32, 32, 32, 15, 0, 0, 0, 0))) == 0
+    assert b"kernel_size=7" in L.ptk_last_error()
+
+
+@pytest.mark.parametrize("which", ["int", "hgru"])
+def test_constructor_is_bit_identical_to_reference_init(which):
+    """torch.manual_seed(0); New(...) consumes the RNG exactly like the reference constructor
+    (fixture written by oracle/gen_golden.py from the reference's own state_dict)."""
+    from pathtracker_models_b200 import InT, ffhgru_hierarchy
+    z = np.load(os.path.join(GOLDEN, f"{which}_fingerprint.npz"))
+    torch.manual_seed(0)
+    m = InT.InT(dimensions=32, timesteps=32, kernel_size=7) if which == "int" else \
+        ffhgru_hierarchy.FFhGRU(dimensions=32, timesteps=32, kernel_size=7)
+    sd = m.state_dict()
+    keys = [k for k in sd if not (which == "int" and k == "unit1.w")]
+    assert keys == list(z["init_keys"])
+    sums = np.array([sd[k].double().sum().item() for k in keys])
+    assert np.array_equal(sums, z["init_sums"])
+
+
+def test_state_dict_round_trip_and_variants():
+    from pathtracker_models_b200 import InT, ffhgru_hierarchy
+    case = load_case("int_small")
+    m = InT.InT(dimensions=32, timesteps=8, kernel_size=7)
+    m.load_state_dict(case["sd"])                       # a reference checkpoint loads, incl. dead unit1.w
+    assert set(m.state_dict().keys()) == set(case["sd"].keys()) and len(m.state_dict()) == 31
+    for k, v in m.state_dict().items():
+        assert v.shape == case["sd"][k].shape, k
+    h = ffhgru_hierarchy.FFhGRU(dimensions=32, timesteps=8, kernel_size=7)
+    h.load_state_dict(load_case("hgru_small")["sd"])
+    assert len(h.state_dict()) == 33                    # + unused BatchNorm3d (ffhgru_hierarchy.py:186)
+    les = InT.InT(32, 8, 7, lesion_alpha=True, lesion_gamma=True)
+    assert not les.unit1.alpha.requires_grad and not les.unit1.gamma.requires_grad
+    assert float(les.unit1.alpha.mean()) == 1.0          # frozen at init, not zeroed (InT.py:132-143)
+    ni = InT.InT(32, 8, 7, no_inh=True)
+    assert "unit1.w_inh" not in ni.state_dict()
+    with pytest.raises(NotImplementedError):
+        InT.InT(32, 8, 7, nl=torch.relu)._config()
+    # DataParallel-style key prefixing (earlystopping.py:55 saves module.* keys)
+    dp_sd = {"module." + k: v for k, v in m.state_dict().items()}
+    m2 = InT.InT(dimensions=32, timesteps=8, kernel_size=7)
+    m2.load_state_dict({k[len("module."):]: v for k, v in dp_sd.items()})
+
+
+def test_no_cpu_fallback():
+    from pathtracker_models_b200 import InT, _lib
+    m = InT.InT(dimensions=32, timesteps=4, kernel_size=7)
+    with pytest.raises(_lib.PtkError):
+        m(torch.rand(1, 3, 2, 32, 32))
+
+
+def test_synth_oracle_is_deterministic_and_binary():
+    from oracle.synth_oracle import synth
+    x, y = synth(1234, 0, 3, 8, 32, 32, 14, 1)
+    x2, y2 = synth(1234, 0, 3, 8, 32, 32, 14, 1)
+    assert np.array_equal(x, x2) and np.array_equal(y, y2) and set(np.unique(x)) <= {0.0, 1.0}
+    xs, _ = synth(1234, 1, 2, 8, 32, 32, 14, 1)
+    assert np.array_equal(x[1:], xs)
