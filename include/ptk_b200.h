@@ -83,8 +83,8 @@ PTK_API const char* ptk_last_error(void);
  * readout_dense [1]+[1]. */
 PTK_API int ptk_int_param_offsets(const PtkDims* d, int64_t* offsets);
 
-/* Bytes of the checkpoint buffer forward fills for backward: I_t,E_t (t=0..T), the two
- * pre-BatchNorm conv outputs per step and the 4*C batch statistics per step.  This replaces
+/* Bytes of the checkpoint buffer forward fills for backward: I_t,E_t (t=0..T), and per step the two
+ * pre-BatchNorm conv outputs, the three gates (A, G_i, G_e) and the 4*C batch statistics.  This replaces
  * the autograd tape of models/InT.py:223-235 (21 state-sized tensors/step in the reference). */
 PTK_API size_t ptk_int_saved_bytes(const PtkDims* d);
 PTK_API size_t ptk_int_workspace_bytes(const PtkDims* d);
@@ -119,8 +119,8 @@ PTK_API int ptk_synth_pathtracker(uint64_t seed, uint64_t first_index, int32_t B
 
 /* Measurement hooks (used by bench.py; off by default, no effect on results).
  * ptk_profile_start(): from now on every kernel-class launch is bracketed by cudaEvents on its stream.
- * ptk_profile_stop(ms, count): synchronises those events; fills ms[k] / count[k] for the 7 classes
- *   0 conv fwd, 1 conv dgrad, 2 wgrad, 3 point-wise fwd, 4 point-wise bwd, 5 bn-apply, 6 misc.
+ * ptk_profile_stop(ms, count): synchronises those events; fills ms[k] / count[k] for the 8 classes
+ *   0 conv fwd, 1 conv dgrad, 2 wgrad, 3 point-wise fwd, 4 point-wise bwd, 5 bn-apply, 6 misc, 7 gate wgrad.
  * ptk_launch_count(): kernels launched by this library in this process so far. */
 PTK_API void ptk_profile_start(void);
 PTK_API int ptk_profile_stop(double* ms, long long* count);

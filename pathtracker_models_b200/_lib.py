@@ -82,7 +82,7 @@ def param_offsets(dims):
     return list(arr)
 
 
-PROF_KINDS = ("conv_fwd", "conv_dgrad", "wgrad", "pointwise_fwd", "pointwise_bwd", "bn_apply", "misc")
+PROF_KINDS = ("conv_fwd", "conv_dgrad", "wgrad", "pointwise_fwd", "pointwise_bwd", "bn_apply", "misc", "gate_wgrad")
 
 
 def profile_start():

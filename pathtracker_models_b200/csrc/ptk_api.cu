@@ -51,21 +51,20 @@ struct Carver {
 static size_t state_elems(const PtkDims* d) { return (size_t)d->B * C * d->H * d->W; }
 
 // carve the workspace into the IntDev scratch pointers; returns bytes needed
-static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, float** wprep, float** gateT) {
+static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   Carver cv(ws);
   const size_t S = state_elems(dm);
-  const int tiles = (int)(S / C / PT);
+  const int pw = pw_grid(dm->B, dm->H, dm->W);
   float* w = cv.take<float>(4 * (size_t)C * C * TAPS);
   float* gt = cv.take<float>(6 * C * C);
-  float* A = cv.take<float>(S);
   float* Ge = cv.take<float>(S);
-  float* Gex = cv.take<float>(S);
-  float* big = cv.take<float>(7 * S);   // inference ring (6S) or backward scratch (7S)
+  float* big = cv.take<float>(10 * S);   // inference ring (9S) or backward scratch (10S)
   float* ring_stats = cv.take<float>(4 * C);
   float* bn_part = cv.take<float>((size_t)conv_num_ctas(dm->B, dm->H, dm->W) * C * 2);
   unsigned* counter = cv.take<unsigned>(4);
-  float* acc = cv.take<float>((size_t)tiles * ACC_N);
-  float* bn_sums = cv.take<float>((size_t)tiles * 2 * C);
+  float* acc = cv.take<float>((size_t)pw * ACC_N);
+  float* gacc = cv.take<float>((size_t)GATE_CTAS * GACC_N);
+  float* bn_sums = cv.take<float>((size_t)pw * 2 * C);
   float* bn_tot = cv.take<float>(2 * C);
   double* bn_acc = cv.take<double>(4 * C);
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);
@@ -73,25 +72,25 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, float** wp
   float* wacc_exc = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
   float* wacc_inh = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
   if (d) {
-    d->A = A; d->Ge = Ge; d->Gex = Gex;
-    d->bn_part = bn_part; d->counter = counter;
-    d->acc = acc; d->bn_sums = bn_sums; d->bn_tot = bn_tot; d->bn_acc = bn_acc; d->head = head; d->dgoal = dgoal;
+    d->Ge = Ge;
+    d->bn_part = bn_part; d->counter = counter; d->pw_ctas = pw;
+    d->acc = acc; d->gacc = gacc; d->bn_sums = bn_sums; d->bn_tot = bn_tot; d->bn_acc = bn_acc;
+    d->head = head; d->dgoal = dgoal;
     d->wacc_exc = wacc_exc; d->wacc_inh = wacc_inh;
     // backward scratch view of `big`
     d->gE = big; d->gI = big + S; d->geb = big + 2 * S; d->dAct = big + 3 * S; d->dGe = big + 4 * S;
-    d->dX = big + 5 * S; d->dS = big + 6 * S;
+    d->dX = big + 5 * S; d->dS = big + 6 * S; d->giS = big + 7 * S; d->aS = big + 8 * S; d->Xs = big + 9 * S;
     // inference ring view of `big` (only used when saved == NULL)
     if (d->ck_ring) {
       d->ckI = big; d->ckE = big + 2 * S; d->ck_stride = S;
-      d->Y0 = big + 4 * S; d->Y1 = big + 5 * S; d->y_stride = 0;
+      d->Y0 = big + 4 * S; d->Y1 = big + 5 * S; d->Gi = big + 6 * S; d->Gex = big + 7 * S; d->y_stride = 0;
+      d->A = big + 8 * S; d->a_tstride = 0; d->a_bstride = (long long)C * dm->H * dm->W;
       d->stats = ring_stats;
     }
     d->w_inh_f = w; d->w_inh_d = w + (size_t)C * C * TAPS;
     d->w_exc_f = w + 2 * (size_t)C * C * TAPS; d->w_exc_d = w + 3 * (size_t)C * C * TAPS;
     for (int i = 0; i < 6; ++i) d->gateT[i] = gt + i * C * C;
   }
-  if (wprep) *wprep = w;
-  if (gateT) *gateT = gt;
   return (cv.off + 255) & ~(size_t)255;
 }
 
@@ -113,11 +112,14 @@ static void bind_params(IntDev* d, const float* p) {
 
 static void bind_saved(IntDev* d, const PtkDims* dm, void* saved) {
   const size_t S = state_elems(dm);
+  const size_t T = (size_t)dm->T;
   float* s = (float*)saved;
   d->ck_ring = 0;
-  d->ckI = s; d->ckE = s + (size_t)(dm->T + 1) * S; d->ck_stride = S;
-  d->Y0 = s + 2 * (size_t)(dm->T + 1) * S; d->Y1 = d->Y0 + (size_t)dm->T * S; d->y_stride = S;
-  d->stats = d->Y1 + (size_t)dm->T * S;
+  d->ckI = s; d->ckE = s + (T + 1) * S; d->ck_stride = S;
+  d->Y0 = s + 2 * (T + 1) * S; d->Y1 = d->Y0 + T * S; d->A = d->Y1 + T * S; d->Gi = d->A + T * S;
+  d->Gex = d->Gi + T * S; d->y_stride = S;
+  d->a_tstride = (long long)S; d->a_bstride = (long long)C * dm->H * dm->W;
+  d->stats = d->Gex + T * S;
 }
 
 static int prep(IntDev* d, const float* params, cudaStream_t st) {
@@ -148,12 +150,12 @@ int ptk_int_param_offsets(const PtkDims* d, int64_t* offsets) {
 size_t ptk_int_saved_bytes(const PtkDims* d) {
   if (check_dims(d, "ptk_int_saved_bytes")) return 0;
   const size_t S = state_elems(d);
-  return ((size_t)(2 * (d->T + 1) + 2 * d->T) * S + (size_t)d->T * 4 * C) * sizeof(float);
+  return ((size_t)(2 * (d->T + 1) + 5 * d->T) * S + (size_t)d->T * 4 * C) * sizeof(float);
 }
 
 size_t ptk_int_workspace_bytes(const PtkDims* d) {
   if (check_dims(d, "ptk_int_workspace_bytes")) return 0;
-  return carve_workspace(d, nullptr, nullptr, nullptr, nullptr);
+  return carve_workspace(d, nullptr, nullptr);
 }
 
 int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5], const float* params,
@@ -174,10 +176,11 @@ int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5
   bind_params(&d, params);
   d.ck_ring = (saved == nullptr);
   if (saved) bind_saved(&d, dm, saved);
-  carve_workspace(dm, workspace, &d, nullptr, nullptr);
+  carve_workspace(dm, workspace, &d);
   const size_t S = state_elems(dm);
-  if (gates) { d.A = gates; d.a_tstride = (long long)C * d.H * d.W; d.a_bstride = (long long)d.T * C * d.H * d.W; }
-  else { d.a_tstride = 0; d.a_bstride = (long long)C * d.H * d.W; }
+  if (gates) {   // testmode: the attention gate of every step goes straight into the [B,T,C,H,W] output
+    d.A = gates; d.a_tstride = (long long)C * d.H * d.W; d.a_bstride = (long long)d.T * C * d.H * d.W;
+  }
   d.states = states;
   d.logits = logits;
   PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
@@ -207,8 +210,7 @@ int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[
   d.fv = FrameView{x, x_strides[0], x_strides[1], x_strides[2], x_strides[3], x_strides[4]};
   bind_params(&d, params);
   bind_saved(&d, dm, const_cast<void*>(saved));
-  carve_workspace(dm, workspace, &d, nullptr, nullptr);
-  d.a_tstride = 0; d.a_bstride = (long long)C * d.H * d.W;
+  carve_workspace(dm, workspace, &d);
   d.dlogits = dlogits; d.dparams = dparams; d.dx = dx;
   PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
   if ((rc = prep(&d, params, st))) return rc;   // the workspace may have been reused since forward

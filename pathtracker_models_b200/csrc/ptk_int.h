@@ -9,14 +9,17 @@ struct IntGateSrc {
   const float* w[6];
 };
 
-// per-tile accumulator layout of the backward point-wise kernels (floats)
+// per-CTA accumulator layout of the backward point-wise kernels (floats)
+enum { ACC_KAPPA = 0, ACC_GAMMA = 32, ACC_ALPHA = 64, ACC_MU = 96, ACC_BP = 128, ACC_WP = 160, ACC_N = 256 };
+// per-CTA accumulator layout of the gate weight-gradient kernel
 enum {
-  ACC_KAPPA = 0, ACC_GAMMA = 32, ACC_ALPHA = 64, ACC_MU = 96, ACC_BE = 128, ACC_BI = 160, ACC_BA = 192,
-  ACC_BP = 224, ACC_WP = 256, ACC_WEW = 352, ACC_WEU = ACC_WEW + 1024, ACC_WIW = ACC_WEU + 1024,
-  ACC_WIU = ACC_WIW + 1024, ACC_WAW = ACC_WIU + 1024, ACC_WAU = ACC_WAW + 1024, ACC_N = ACC_WAU + 1024
+  GACC_WEW = 0, GACC_WEU = 1024, GACC_WIW = 2048, GACC_WIU = 3072, GACC_WAW = 4096, GACC_WAU = 5120,
+  GACC_BE = 6144, GACC_BI = 6176, GACC_BA = 6208, GACC_N = 6240
 };
-constexpr int HEAD_N = 96;   // per-sample readout-head partials (86 used), see int_readout_bwd_kernel
+constexpr int HEAD_N = 96;        // per-sample readout-head partials (86 used), see int_readout_bwd_kernel
 constexpr int WGRAD_GROUPS = 37;  // 4 ic-chunks x 37 groups = 148 CTAs (one per SM)
+constexpr int GATE_CTAS = 148;    // gate weight-gradient kernel: one persistent CTA per SM
+constexpr int PW_MAX_CTAS = 148 * 3;
 
 struct IntDev {
   int B, T, H, W;
@@ -29,26 +32,28 @@ struct IntDev {
   const float *bn_w[2], *bn_b[2];
   const float *Wr, *br, *Wt, *bt, *Wd, *bd;
   const float *w_inh_f, *w_exc_f, *w_inh_d, *w_exc_d;
-  // checkpoints (saved for backward) -- or a 2-slot ring when inference-only
-  float *ckI, *ckE;
+  // checkpoints (saved for backward) -- or a small ring when inference-only
+  float *ckI, *ckE;        // [T+1 or 2][B,C,P]
   size_t ck_stride;
   int ck_ring;
-  float *Y0, *Y1;
+  float *Y0, *Y1, *Gi, *Gex;   // [T or 1][B,C,P]: pre-BN conv outputs, inhibition / excitation gates
   size_t y_stride;
+  float* A;                // attention gate per step: saved [T][B,C,P], ring scratch, or gates output [B,T,C,P]
+  long long a_tstride, a_bstride;
   float* stats;            // [T or 1][2 bn][2 (mean,rstd)][C]
   // forward scratch / outputs
-  float* A;                // attention gate: scratch [B,C,P] or gates output [B,T,C,P]
-  long long a_tstride, a_bstride;
-  float *Ge, *Gex;
+  float* Ge;
   float *states, *logits;
   float* bn_part;
   unsigned* counter;
   // backward scratch
-  float *gE, *gI, *geb, *dAct, *dGe, *dX, *dS;
-  float* acc;              // [tiles][ACC_N]
-  float* bn_sums;          // [tiles][2][C] step-local partials
+  float *gE, *gI, *geb, *dAct, *dGe, *dX, *dS, *giS, *aS, *Xs;
+  int pw_ctas;             // grid of the backward point-wise kernels (fixed => deterministic slots)
+  float* acc;              // [pw_ctas][ACC_N]
+  float* gacc;             // [GATE_CTAS][GACC_N]
+  float* bn_sums;          // [pw_ctas][2][C] step-local partials
   float* bn_tot;           // [2][C]  (sum dV)/N, (sum dV*xhat)/N of the current BatchNorm
-  double* bn_acc;          // [2 bn][2][C] accumulated over steps: d(bn weight), d(bn bias)
+  double* bn_acc;          // [2 bn][2][C] accumulated over steps: d(bn bias), d(bn weight)
   float* head;             // [B][HEAD_N]
   float* dgoal;            // [B][P] gradient of the goal map x[:,2,0] through the readout
   float *wacc_exc, *wacc_inh;
@@ -58,13 +63,20 @@ struct IntDev {
 
   __host__ __device__ int slot(int t) const { return ck_ring ? (t & 1) : t; }
   __host__ __device__ int yslot(int t) const { return ck_ring ? 0 : t; }
-  __host__ __device__ const float* stat(int t, int bn) const { return stats + ((size_t)yslot(t) * 2 + bn) * 2 * C; }
-  __host__ __device__ float* stat_w(int t, int bn) const { return stats + ((size_t)yslot(t) * 2 + bn) * 2 * C; }
+  __host__ __device__ float* stat(int t, int bn) const { return stats + ((size_t)yslot(t) * 2 + bn) * 2 * C; }
+  __host__ __device__ float* I_at(int t) const { return ckI + ck_stride * slot(t); }
+  __host__ __device__ float* E_at(int t) const { return ckE + ck_stride * slot(t); }
+  __host__ __device__ float* Y0_at(int t) const { return Y0 + y_stride * yslot(t); }
+  __host__ __device__ float* Y1_at(int t) const { return Y1 + y_stride * yslot(t); }
+  __host__ __device__ float* Gi_at(int t) const { return Gi + y_stride * yslot(t); }
+  __host__ __device__ float* Gex_at(int t) const { return Gex + y_stride * yslot(t); }
+  __host__ __device__ float* A_at(int t) const { return A + (size_t)t * a_tstride; }
 };
 
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st);
 int run_int_backward(const IntDev& d, int cell, int act, cudaStream_t st);
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st);
+int pw_grid(int B, int H, int W);
 
 }  // namespace ptk

@@ -4,104 +4,66 @@
 // models/InT.py:223-235.  Per step the kernels below implement eqs (b1)-(b12) of SURVEY.md
 // section 8 (restated and verified against autograd in oracle/int_oracle.py:backward_manual):
 //
-//   bwd_a   (b1)-(b2)  + BatchNorm1 backward sums          point-wise, recomputes A, Ge, G_e
-//   bn_apply (b3)      dV -> dY1 in place                   element-wise
-//   conv7   (b4)       dI' += dY1 *7^T W_exc                 (ptk_conv.cu, flipped weights)
-//   wgrad7  (b4)       dW_exc += I' (star) dY1
-//   bwd_c   (b5)-(b8)  + BatchNorm0 backward sums          point-wise, recomputes G_i, U, P, Q
-//   bn_apply (b9)      dU -> dY0
-//   conv7   (b9)       dGe += dY0 *7^T W_inh
-//   wgrad7  (b9)       dW_inh += Ge (star) dY0
-//   bwd_d   (b10)-(b12) attention gate + stem
+//   bwd_a     (b1)-(b2)   + BatchNorm1 backward sums     element-wise (gates A, G_e come from the checkpoint)
+//   bn_apply  (b3)        dV -> dY1 in place
+//   conv7     (b4)        dI' += dY1 *7^T W_exc           (ptk_conv.cu, flipped weights)
+//   wgrad7    (b4)        dW_exc += I' (star) dY1
+//   bwd_c     (b5)-(b8)   + BatchNorm0 backward sums     element-wise + 4 transposed 1x1 products
+//   bn_apply  (b9)        dU -> dY0
+//   conv7     (b9)        dGe += dY0 *7^T W_inh
+//   wgrad7    (b9)        dW_inh += Ge (star) dY0
+//   bwd_d     (b10)-(b12) attention gate + stem           element-wise + 2 transposed 1x1 products
+//   gate_wgrad            the six 32x32 gate-weight gradients + gate-bias gradients of the step
 //
-// One thread = one pixel (32 channels in registers).  Sums over pixels (per-channel scalars and the
-// 32x32 gate-weight outer products) are staged through shared memory per 128-pixel tile and
-// accumulated per tile in global memory (read-add-write by the owning tile only => deterministic);
-// `finalize` folds the tiles in double precision.
-#include "ptk_common.cuh"
+// Point-wise kernels use the warp-tile scheme of ptk_pw.cuh.  Sums over pixels live in registers
+// across a persistent CTA's tiles and are accumulated per CTA slot in global memory (read-add-write
+// by the owning CTA only => deterministic); `finalize` folds the slots in double precision.
 #include "ptk_int.h"
 #include "ptk_profile.h"
+#include "ptk_pw.cuh"
 
 namespace ptk {
 
-constexpr int SP = PT + 4;   // staging pitch (floats): LDS.128-aligned rows, conflict-free
+constexpr int TILE_F = C * TP;
 
-__device__ __forceinline__ void smem_fill_b(float* dst, const float* __restrict__ src, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
-}
-
-template <int ACT>
-__device__ __forceinline__ void stem_pixel_pre(const FrameView& fv, int b, int t, int y, int x,
-                                               const float* sWp, const float* sbp, float (&pre)[C],
-                                               float (&xin)[3]) {
-  xin[0] = fv.at(b, 0, t, y, x); xin[1] = fv.at(b, 1, t, y, x); xin[2] = fv.at(b, 2, t, y, x);
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-    pre[c] = fmaf(sWp[c * 3 + 2], xin[2], fmaf(sWp[c * 3 + 1], xin[1], fmaf(sWp[c * 3 + 0], xin[0], sbp[c])));
-}
-
-// sum over the tile's 128 pixels of a staged [32][SP] buffer: thread k reduces a quarter of row k/4;
-// after the two shuffles every thread of the 4-group holds the row sum.
-__device__ __forceinline__ float tile_rowsum(const float* sQ) {
-  const int k = threadIdx.x, row = k >> 2, q = k & 3;
-  const float4* p = reinterpret_cast<const float4*>(sQ + row * SP + q * 32);
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 v = p[i];
-    s += (v.x + v.y) + (v.z + v.w);
-  }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  return s;
-}
 __device__ __forceinline__ void acc_store(float* dst, float v, int first) {
   if (first) *dst = v; else *dst += v;
 }
-// dst[oc*32+ic] (+)= sum_px sG[oc][px] * sV[ic][px]
-__device__ __forceinline__ void tile_outer(const float* sG, const float* sV, float* dst, int first) {
-  const int k = threadIdx.x, oc = k >> 2, icg = k & 3;
-  float acc[8];
+
+// CTA-level fold of per-thread channel partials: part[q][o] (thread's 8 channels) -> sTot[q][32].
+template <int NQ>
+__device__ __forceinline__ void cta_channel_sums(float (&part)[NQ][8], float* sRed /*[4][NQ][32]*/, float* sTot,
+                                                 const Lane& L) {
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  const float4* g4 = reinterpret_cast<const float4*>(sG + oc * SP);
-#pragma unroll 4
-  for (int p = 0; p < PT / 4; ++p) {
-    const float4 g = g4[p];
+  for (int q = 0; q < NQ; ++q)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 v = *reinterpret_cast<const float4*>(sV + (icg + 4 * j) * SP + 4 * p);
-      acc[j] = fmaf(g.x, v.x, fmaf(g.y, v.y, fmaf(g.z, v.z, fmaf(g.w, v.w, acc[j]))));
+    for (int o = 0; o < 8; ++o) {
+      const float v = reduce_pg(part[q][o]);
+      if (L.pg == 0) sRed[(warp * NQ + q) * C + L.oc0 + o] = v;
     }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc_store(dst + oc * C + icg + 4 * j, acc[j], first);
-}
-__device__ __forceinline__ void stage(float* sQ, const float (&v)[C]) {
-#pragma unroll
-  for (int c = 0; c < C; ++c) sQ[c * SP + threadIdx.x] = v[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * C; i += blockDim.x)
+    sTot[i] = (sRed[i] + sRed[NQ * C + i]) + (sRed[2 * NQ * C + i] + sRed[3 * NQ * C + i]);
+  __syncthreads();
 }
 
-// step-local BatchNorm-backward sums: per-tile partials -> last CTA folds them (double) into
+// step-local BatchNorm-backward sums: per-CTA partials -> last CTA folds them (double) into
 // bn_tot = (sum dV)/N, (sum dV*xhat)/N and accumulates d(bn bias), d(bn weight).
-__device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, float s0, float s1, int first,
+__device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const float* sPart /*[2][32]*/, int first,
                                              int* sIsLast) {
-  const int k = threadIdx.x, row = k >> 2, q = k & 3;
-  const int nTiles = gridDim.x;
-  if (q == 0) {
-    d.bn_sums[((size_t)blockIdx.x * 2 + 0) * C + row] = s0;
-    d.bn_sums[((size_t)blockIdx.x * 2 + 1) * C + row] = s1;
-  }
+  const int k = threadIdx.x, nCta = gridDim.x;
+  if (k < 2 * C) d.bn_sums[(size_t)blockIdx.x * 2 * C + k] = sPart[k];
   __threadfence();
   __syncthreads();
-  if (k == 0) *sIsLast = (atomicAdd(d.counter, 1u) == (unsigned)(nTiles - 1));
+  if (k == 0) *sIsLast = (atomicAdd(d.counter, 1u) == (unsigned)(nCta - 1));
   __syncthreads();
   if (*sIsLast) {
     __threadfence();
     if (k < 2 * C) {
       double s = 0;
 #pragma unroll 8
-      for (int i = 0; i < nTiles; ++i) s += (double)__ldcg(d.bn_sums + (size_t)i * 2 * C + k);
+      for (int i = 0; i < nCta; ++i) s += (double)__ldcg(d.bn_sums + (size_t)i * 2 * C + k);
       const double N = (double)d.B * d.H * d.W;
       d.bn_tot[k] = (float)(s / N);
       // k < C: sum dV -> d(bn bias); k >= C: sum dV*xhat -> d(bn weight)
@@ -113,106 +75,87 @@ __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, float s0, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// (b1)-(b2): needs dE', dI' (in gE, gI), E_t, I_t, I_{t+1}, Y1_t, BN1 stats, x_t.
-// writes: A, Ge (scratch), geb = dG_e*G_e*(1-G_e), gE <- dE'*(1-G_e), gI += dR*V*kappa, dAct <- dV.
-template <int CELL, int ACT>
-__global__ void __launch_bounds__(PT) int_bwd_a_kernel(IntDev d, int t, int first) {
-  extern __shared__ __align__(16) float dsm[];
-  float* sWaw = dsm;              float* sWau = sWaw + C * C;
-  float* sWew = sWau + C * C;     float* sWeu = sWew + C * C;
-  float* sQ0 = sWeu + C * C;      float* sQ1 = sQ0 + C * SP;
-  float* sQ2 = sQ1 + C * SP;      float* sQ3 = sQ2 + C * SP;
-  __shared__ float sWp[C * 3], sbp[C], sba[C], sbe[C], sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
+// (b1)-(b2): dE', dI' (gE, gI) + checkpointed E_t, A_t, I_{t+1}, Y1_t, G_e.
+// writes Ge = A*E (scratch, for wgrad / gate_wgrad), geb = dG_e*G_e*(1-G_e), gE <- dE'*(1-G_e),
+// gI += dR*V*kappa, dAct <- dV.
+template <int ACT>
+__global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int first) {
+  __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
+  __shared__ float sRed[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
-  smem_fill_b(sWaw, d.gateT[0], C * C);
-  smem_fill_b(sWau, d.gateT[1], C * C);
-  smem_fill_b(sWew, d.gateT[4], C * C);
-  smem_fill_b(sWeu, d.gateT[5], C * C);
-  smem_fill_b(sWp, d.Wp, C * 3);
-  smem_fill_b(sbp, d.bp, C);
-  smem_fill_b(sKa, d.kappa, C);
-  smem_fill_b(sGa, d.gamma, C);
-  smem_fill_b(sW1, d.bn_w[1], C);
-  smem_fill_b(sB1, d.bn_b[1], C);
+  cta_fill(sKa, d.kappa, C);
+  cta_fill(sGa, d.gamma, C);
+  cta_fill(sW1, d.bn_w[1], C);
+  cta_fill(sB1, d.bn_b[1], C);
   if (threadIdx.x < C) {
-    const int c = threadIdx.x;
-    sba[c] = __ldg(d.gate_b[0] + c) + __ldg(d.gate_b[1] + c);
-    sbe[c] = __ldg(d.gate_b[4] + c) + __ldg(d.gate_b[5] + c);
     const float* st = d.stat(t, 1);
-    sM1[c] = st[c];
-    sR1[c] = st[C + c];
+    sM1[threadIdx.x] = st[threadIdx.x];
+    sR1[threadIdx.x] = st[C + threadIdx.x];
   }
   __syncthreads();
-  const int P = d.H * d.W, tilesPer = P / PT;
-  const int b = blockIdx.x / tilesPer, pix = (blockIdx.x % tilesPer) * PT + threadIdx.x;
-  const size_t base = (size_t)b * C * P + pix;
-  const float* Et = d.ckE + d.ck_stride * t;
-  const float* It = d.ckI + d.ck_stride * t;
-  const float* I2t = d.ckI + d.ck_stride * (t + 1);
-  const float* Y1 = d.Y1 + d.y_stride * t;
-
-  float E[C], S[C], Ge[C], Gx[C];
-  {
-    float X[C], xin[3];
-    stem_pixel_pre<ACT>(d.fv, b, t, pix / d.W, pix % d.W, sWp, sbp, X, xin);
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* Et = d.E_at(t);
+  const float* At = d.A_at(t);
+  const float* I2t = d.I_at(t + 1);
+  const float* Y1 = d.Y1_at(t);
+  const float* Gxt = d.Gex_at(t);
+  float part[4][8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) X[c] = actf<ACT>(X[c]);
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int c = 0; c < C; ++c) E[c] = Et[base + (size_t)c * P];
-    float acc[C];
+    for (int o = 0; o < 8; ++o) part[q][o] = 0.f;
+  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = sba[c];
-    matvec32(acc, sWaw, X);
-    matvec32(acc, sWau, E);
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
+      const size_t idx = base + (size_t)c * P;
+      float e[4], a[4], i2[4], y1[4], gx[4], ge_in[4], gi_in[4], oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4];
+      ld4v(Et + idx, e);
+      ld4v(At + idx, a);
+      ld4v(I2t + idx, i2);
+      ld4v(Y1 + idx, y1);
+      ld4v(Gxt + idx, gx);
+      ld4v(d.gE + idx, ge_in);
+      if (!first) ld4v(d.gI + idx, gi_in);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float A = sigmoidf_(acc[c]);
-      Ge[c] = A * E[c];
-      d.A[base + (size_t)c * P] = A;           // backward always uses the [B,C,P] scratch
-      d.Ge[base + (size_t)c * P] = Ge[c];
-      S[c] = (CELL == PTK_CELL_INT) ? It[base + (size_t)c * P] : A;
+      for (int p = 0; p < 4; ++p) {
+        const float xh = (y1[p] - sM1[c]) * sR1[c];
+        const float V = fmaf(sW1[c], xh, sB1[c]);
+        const float kIg = fmaf(sKa[c], i2[p], sGa[c]);
+        const float R = V * kIg;
+        const float Ehat = actf<ACT>(R);
+        const float gEn = ge_in[p];
+        const float dGx = gEn * (Ehat - e[p]);
+        oGE[p] = gEn * (1.0f - gx[p]);
+        const float dR = gEn * gx[p] * dactf<ACT>(R);
+        const float dV = dR * kIg;
+        const float dRV = dR * V;
+        oGI[p] = fmaf(dRV, sKa[c], first ? 0.0f : gi_in[p]);
+        oGeb[p] = dGx * gx[p] * (1.0f - gx[p]);
+        oDv[p] = dV;
+        oGe[p] = a[p] * e[p];
+        part[0][o] = fmaf(dRV, i2[p], part[0][o]);   // -> d kappa
+        part[1][o] += dRV;                            // -> d gamma
+        part[2][o] += dV;                             // -> sum dV
+        part[3][o] = fmaf(dV, xh, part[3][o]);        // -> sum dV * xhat
+      }
+      st4(d.gE + idx, oGE);
+      st4(d.gI + idx, oGI);
+      st4(d.geb + idx, oGeb);
+      st4(d.dAct + idx, oDv);
+      st4(d.Ge + idx, oGe);
     }
   }
-  {
-    float acc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = sbe[c];
-    matvec32(acc, sWew, S);
-    matvec32(acc, sWeu, Ge);
-#pragma unroll
-    for (int c = 0; c < C; ++c) Gx[c] = sigmoidf_(acc[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const size_t idx = base + (size_t)c * P;
-    const float I2 = I2t[idx];
-    const float xh = (Y1[idx] - sM1[c]) * sR1[c];
-    const float V = fmaf(sW1[c], xh, sB1[c]);
-    const float kIg = fmaf(sKa[c], I2, sGa[c]);
-    const float R = V * kIg;
-    const float Ehat = actf<ACT>(R);
-    const float gEn = d.gE[idx];
-    const float dGx = gEn * (Ehat - E[c]);
-    d.gE[idx] = gEn * (1.0f - Gx[c]);
-    const float dR = gEn * Gx[c] * dactf<ACT>(R);
-    const float dV = dR * kIg;
-    const float dRV = dR * V;
-    d.gI[idx] = fmaf(dRV, sKa[c], first ? 0.0f : d.gI[idx]);
-    d.geb[idx] = dGx * Gx[c] * (1.0f - Gx[c]);
-    d.dAct[idx] = dV;
-    sQ0[c * SP + threadIdx.x] = dRV * I2;   // -> d kappa
-    sQ1[c * SP + threadIdx.x] = dRV;        // -> d gamma
-    sQ2[c * SP + threadIdx.x] = dV;         // -> sum dV
-    sQ3[c * SP + threadIdx.x] = dV * xh;    // -> sum dV * xhat
-  }
-  __syncthreads();
-  const float r0 = tile_rowsum(sQ0), r1 = tile_rowsum(sQ1), r2 = tile_rowsum(sQ2), r3 = tile_rowsum(sQ3);
+  cta_channel_sums<4>(part, sRed, sTot, L);
   float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
-  if ((threadIdx.x & 3) == 0) {
-    acc_store(acc + ACC_KAPPA + (threadIdx.x >> 2), r0, first);
-    acc_store(acc + ACC_GAMMA + (threadIdx.x >> 2), r1, first);
+  if (threadIdx.x < C) {
+    acc_store(acc + ACC_KAPPA + threadIdx.x, sTot[threadIdx.x], first);
+    acc_store(acc + ACC_GAMMA + threadIdx.x, sTot[C + threadIdx.x], first);
   }
-  bn_sums_fold(d, 1, r2, r3, first, &sIsLast);
+  bn_sums_fold(d, 1, sTot + 2 * C, first, &sIsLast);
 }
 
 // (b3)/(b9): dAct <- w*rstd*(dAct - mean(dAct) - xhat*mean(dAct*xhat)), xhat from the saved conv output.
@@ -235,238 +178,327 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// (b5)-(b8): needs complete dI' (gI), geb, A/Ge (scratch), I_t, Y0_t, BN0 stats, x_t.
-// writes: dAct <- dU, dGe, dX, gI <- dI (+ dS for InT), dS (hGRU), per-tile sums.
+// (b5)-(b8): complete dI' (gI), geb, checkpointed I_t, A_t, Y0_t, G_i, x_t.
+// writes dAct <- dU, dGe, dX, gI <- dI (+ dS for InT), dS (hGRU), gi and X (scratch for gate_wgrad).
 template <int CELL, int ACT>
-__global__ void __launch_bounds__(PT) int_bwd_c_kernel(IntDev d, int t, int first) {
+__global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
-  float* sWiwT = dsm;             float* sWiuT = sWiwT + C * C;   // [in][out] for the G_i recompute
-  float* sWiw = sWiuT + C * C;    float* sWiu = sWiw + C * C;     // [out][in] for the transposed mat-vecs
-  float* sWew = sWiu + C * C;     float* sWeu = sWew + C * C;
-  float* sQ0 = sWeu + C * C;      float* sQ1 = sQ0 + C * SP;
-  float* sQ2 = sQ1 + C * SP;      float* sQ3 = sQ2 + C * SP;
-  __shared__ float sWp[C * 3], sbp[C], sbi[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
+  float* sWiw = dsm;              // [out][in] = [k][n] of the transposed products
+  float* sWiu = sWiw + C * C;
+  float* sWew = sWiu + C * C;
+  float* sWeu = sWew + C * C;
+  float* tiles = sWeu + C * C;
+  __shared__ float sWp[C * 3], sbp[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
+  __shared__ float sRed[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
-  smem_fill_b(sWiwT, d.gateT[2], C * C);
-  smem_fill_b(sWiuT, d.gateT[3], C * C);
-  smem_fill_b(sWiw, d.gate[2], C * C);
-  smem_fill_b(sWiu, d.gate[3], C * C);
-  smem_fill_b(sWew, d.gate[4], C * C);
-  smem_fill_b(sWeu, d.gate[5], C * C);
-  smem_fill_b(sWp, d.Wp, C * 3);
-  smem_fill_b(sbp, d.bp, C);
-  smem_fill_b(sAl, d.alpha, C);
-  smem_fill_b(sMu, d.mu, C);
-  smem_fill_b(sW0, d.bn_w[0], C);
-  smem_fill_b(sB0, d.bn_b[0], C);
+  cta_fill(sWiw, d.gate[2], C * C);
+  cta_fill(sWiu, d.gate[3], C * C);
+  cta_fill(sWew, d.gate[4], C * C);
+  cta_fill(sWeu, d.gate[5], C * C);
+  cta_fill(sWp, d.Wp, C * 3);
+  cta_fill(sbp, d.bp, C);
+  cta_fill(sAl, d.alpha, C);
+  cta_fill(sMu, d.mu, C);
+  cta_fill(sW0, d.bn_w[0], C);
+  cta_fill(sB0, d.bn_b[0], C);
   if (threadIdx.x < C) {
-    const int c = threadIdx.x;
-    sbi[c] = __ldg(d.gate_b[2] + c) + __ldg(d.gate_b[3] + c);
     const float* st = d.stat(t, 0);
-    sM0[c] = st[c];
-    sR0[c] = st[C + c];
+    sM0[threadIdx.x] = st[threadIdx.x];
+    sR0[threadIdx.x] = st[C + threadIdx.x];
   }
   __syncthreads();
-  const int P = d.H * d.W, tilesPer = P / PT;
-  const int b = blockIdx.x / tilesPer, pix = (blockIdx.x % tilesPer) * PT + threadIdx.x;
-  const size_t base = (size_t)b * C * P + pix;
-  const float* It = d.ckI + d.ck_stride * t;
-  const float* Y0 = d.Y0 + d.y_stride * t;
-  float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
-  const int k = threadIdx.x;
-
-  float X[C], S[C], gi[C], dS[C];
-  {
-    float xin[3];
-    stem_pixel_pre<ACT>(d.fv, b, t, pix / d.W, pix % d.W, sWp, sbp, X, xin);
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  float* sGi = tiles + warp * 2 * TILE_F;
+  float* sGe = sGi + TILE_F;
+  const float* It = d.I_at(t);
+  const float* At = d.A_at(t);
+  const float* Y0 = d.Y0_at(t);
+  const float* Git = d.Gi_at(t);
+  float part[4][8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) X[c] = actf<ACT>(X[c]);
-  }
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-  for (int c = 0; c < C; ++c)
-    S[c] = (CELL == PTK_CELL_INT) ? It[base + (size_t)c * P] : d.A[base + (size_t)c * P];
-  float z[C];
-  {
-    float Gi[C];
+    for (int o = 0; o < 8; ++o) part[q][o] = 0.f;
+  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    warp_tile_load_async(sGe, d.geb, (size_t)C * P, b, pix_base, P);
+    cp_async_commit();
+    float xin[3][4];
+    frame_px(d.fv, b, t, pix, d.W, xin);
+    float z[4][8], ds[4][8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) Gi[c] = sbi[c];
-    matvec32(Gi, sWiwT, X);
-    matvec32(Gi, sWiuT, S);
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      const float G = sigmoidf_(Gi[c]);
-      const float I = (CELL == PTK_CELL_INT) ? S[c] : It[idx];
-      const float xh = (Y0[idx] - sM0[c]) * sR0[c];
-      const float U = fmaf(sW0[c], xh, sB0[c]);
-      const float aSm = fmaf(sAl[c], S[c], sMu[c]);
-      const float Pp = U * aSm;
-      const float Q = actf<ACT>(Pp);
-      const float d1 = X[c] - Q;
-      const float Ihat = actf<ACT>(d1);
-      const float gIn = d.gI[idx];
-      const float dGi = gIn * (Ihat - I);
-      d.gI[idx] = gIn * (1.0f - G);                 // dI (InT adds dS below)
-      const float zz = gIn * G * dactf<ACT>(d1);
-      z[c] = zz;
-      gi[c] = dGi * G * (1.0f - G);
-      const float dP = -zz * dactf<ACT>(Pp);
-      const float dPU = dP * U;
-      const float dU = dP * aSm;
-      dS[c] = dPU * sAl[c];
-      d.dAct[idx] = dU;
-      sQ0[c * SP + k] = dPU * S[c];   // -> d alpha
-      sQ1[c * SP + k] = dPU;          // -> d mu
-      sQ2[c * SP + k] = dU;           // -> sum dU
-      sQ3[c * SP + k] = dU * xh;      // -> sum dU * xhat
+      float gIn[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oDI[4];
+      ld4v(d.gI + idx, gIn);
+      ld4v(It + idx, I);
+      if (CELL == PTK_CELL_INT) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) S[p] = I[p];
+      } else {
+        ld4v(At + idx, S);
+      }
+      ld4v(Y0 + idx, y0);
+      ld4v(Git + idx, G);
+      stem_pre(sWp, sbp, c, xin, X);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        X[p] = actf<ACT>(X[p]);
+        const float xh = (y0[p] - sM0[c]) * sR0[c];
+        const float U = fmaf(sW0[c], xh, sB0[c]);
+        const float aSm = fmaf(sAl[c], S[p], sMu[c]);
+        const float Pp = U * aSm;
+        const float Q = actf<ACT>(Pp);
+        const float d1 = X[p] - Q;
+        const float Ihat = actf<ACT>(d1);
+        const float dGi = gIn[p] * (Ihat - I[p]);
+        oDI[p] = gIn[p] * (1.0f - G[p]);
+        const float zz = gIn[p] * G[p] * dactf<ACT>(d1);
+        oGi[p] = dGi * G[p] * (1.0f - G[p]);
+        const float dP = -zz * dactf<ACT>(Pp);
+        const float dPU = dP * U;
+        const float dU = dP * aSm;
+        oDu[p] = dU;
+        z[p][o] = zz;
+        ds[p][o] = dPU * sAl[c] + (CELL == PTK_CELL_INT ? oDI[p] : 0.0f);   // InT: dI + dS lands in gI
+        part[0][o] = fmaf(dPU, S[p], part[0][o]);   // -> d alpha
+        part[1][o] += dPU;                           // -> d mu
+        part[2][o] += dU;                            // -> sum dU
+        part[3][o] = fmaf(dU, xh, part[3][o]);       // -> sum dU * xhat
+      }
+      st4(d.dAct + idx, oDu);
+      st4(d.giS + idx, oGi);
+      st4(d.Xs + idx, X);
+      tile_st(sGi, L, o, oGi);
+      if (CELL == PTK_CELL_HGRU) st4(d.gI + idx, oDI);
     }
-  }
-  __syncthreads();
-  {
-    const float r0 = tile_rowsum(sQ0), r1 = tile_rowsum(sQ1), r2 = tile_rowsum(sQ2), r3 = tile_rowsum(sQ3);
-    if ((k & 3) == 0) {
-      acc_store(acc + ACC_ALPHA + (k >> 2), r0, first);
-      acc_store(acc + ACC_MU + (k >> 2), r1, first);
+    cp_async_wait<0>();
+    __syncwarp();
+    warp_gemm(z, sGi, sWiw, L);      // dX = z + Wi_w^T gi
+    warp_gemm(ds, sGi, sWiu, L);     // dS += Wi_u^T gi
+    warp_gemm(ds, sGe, sWew, L);     //     + We_w^T ge
+    float dge[4][8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) dge[p][o] = 0.f;
+    warp_gemm(dge, sGe, sWeu, L);    // dGe = We_u^T ge
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const size_t idx = base + (size_t)(L.oc0 + o) * P;
+      float v0[4], v1[4], v2[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { v0[p] = z[p][o]; v1[p] = ds[p][o]; v2[p] = dge[p][o]; }
+      st4(d.dX + idx, v0);
+      if (CELL == PTK_CELL_INT) st4(d.gI + idx, v1);   // (b10) InT: dI += dS
+      else st4(d.dS + idx, v1);                         //       hGRU: dA += dS (in bwd_d)
+      st4(d.dGe + idx, v2);
     }
-    bn_sums_fold(d, 0, r2, r3, first, &sIsLast);   // contains __syncthreads: staging buffers free again
+    __syncwarp();
   }
-  // dX = z + Wi_w^T gi
-  matvec32(z, sWiw, gi);
-#pragma unroll
-  for (int c = 0; c < C; ++c) d.dX[base + (size_t)c * P] = z[c];
-  // dS += Wi_u^T gi + We_w^T ge ;  dGe = We_u^T ge
-  matvec32(dS, sWiu, gi);
-  float ge[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) ge[c] = d.geb[base + (size_t)c * P];
-  matvec32(dS, sWew, ge);
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const size_t idx = base + (size_t)c * P;
-    if (CELL == PTK_CELL_INT) d.gI[idx] += dS[c];   // (b10) InT: dI += dS
-    else d.dS[idx] = dS[c];                          //       hGRU: dA += dS (in bwd_d)
+  cta_channel_sums<4>(part, sRed, sTot, L);
+  float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
+  if (threadIdx.x < C) {
+    acc_store(acc + ACC_ALPHA + threadIdx.x, sTot[threadIdx.x], first);
+    acc_store(acc + ACC_MU + threadIdx.x, sTot[C + threadIdx.x], first);
   }
-  {
-    float dGe[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) dGe[c] = 0.f;
-    matvec32(dGe, sWeu, ge);
-#pragma unroll
-    for (int c = 0; c < C; ++c) d.dGe[base + (size_t)c * P] = dGe[c];
-  }
-  // gate-weight outer products and bias sums
-  stage(sQ0, ge);
-  stage(sQ1, S);
-  stage(sQ2, gi);
-  stage(sQ3, X);
-  __syncthreads();
-  {
-    const float rge = tile_rowsum(sQ0), rgi = tile_rowsum(sQ2);
-    if ((k & 3) == 0) {
-      acc_store(acc + ACC_BE + (k >> 2), rge, first);
-      acc_store(acc + ACC_BI + (k >> 2), rgi, first);
-    }
-  }
-  tile_outer(sQ0, sQ1, acc + ACC_WEW, first);   // ge (x) S
-  tile_outer(sQ2, sQ3, acc + ACC_WIW, first);   // gi (x) X
-  tile_outer(sQ2, sQ1, acc + ACC_WIU, first);   // gi (x) S
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < C; ++c) sQ1[c * SP + k] = d.Ge[base + (size_t)c * P];
-  __syncthreads();
-  tile_outer(sQ0, sQ1, acc + ACC_WEU, first);   // ge (x) Ge
+  bn_sums_fold(d, 0, sTot + 2 * C, first, &sIsLast);
 }
 
 // ------------------------------------------------------------------------------------------------
-// (b10)-(b12): needs complete dGe, dE partial (gE), A, E_t, dX, [dS], x_t.
-// writes gE <- dE (for step t-1), stem / attention-gate parameter sums, optional dx.
+// (b10)-(b12): complete dGe, dE partial (gE), A_t, E_t, dX, [dS], x_t.
+// writes gE <- dE (for step t-1), a (scratch for gate_wgrad), stem parameter sums, optional dx.
 template <int CELL, int ACT>
-__global__ void __launch_bounds__(PT) int_bwd_d_kernel(IntDev d, int t, int first) {
+__global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
-  float* sWaw = dsm;              float* sWau = sWaw + C * C;   // [out][in]
-  float* sQ0 = sWau + C * C;      float* sQ1 = sQ0 + C * SP;
-  float* sQ2 = sQ1 + C * SP;
-  __shared__ float sWp[C * 3], sbp[C], sXin[3][PT];
-  smem_fill_b(sWaw, d.gate[0], C * C);
-  smem_fill_b(sWau, d.gate[1], C * C);
-  smem_fill_b(sWp, d.Wp, C * 3);
-  smem_fill_b(sbp, d.bp, C);
+  float* sWaw = dsm;              // [out][in]
+  float* sWau = sWaw + C * C;
+  float* tiles = sWau + C * C;
+  __shared__ float sWp[C * 3], sbp[C];
+  __shared__ float sRed[4 * 4 * C], sTot[4 * C];
+  cta_fill(sWaw, d.gate[0], C * C);
+  cta_fill(sWau, d.gate[1], C * C);
+  cta_fill(sWp, d.Wp, C * 3);
+  cta_fill(sbp, d.bp, C);
   __syncthreads();
-  const int P = d.H * d.W, tilesPer = P / PT;
-  const int b = blockIdx.x / tilesPer, pix = (blockIdx.x % tilesPer) * PT + threadIdx.x;
-  const int py = pix / d.W, px = pix % d.W;
-  const size_t base = (size_t)b * C * P + pix;
-  const float* Et = d.ckE + d.ck_stride * t;
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  float* sA = tiles + warp * TILE_F;
+  const float* Et = d.E_at(t);
+  const float* At = d.A_at(t);
+  float part[4][8];   // [0] d bp, [1..3] d Wp[:, i]
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) part[q][o] = 0.f;
+  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    float xin[3][4];
+    frame_px(d.fv, b, t, pix, d.W, xin);
+    float de[4][8], dxv[4][8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const size_t idx = base + (size_t)(L.oc0 + o) * P;
+      float A[4], dGe[4], E[4], gE[4], dS[4], oa[4], dxin[4];
+      ld4v(At + idx, A);
+      ld4v(d.dGe + idx, dGe);
+      ld4v(Et + idx, E);
+      ld4v(d.gE + idx, gE);
+      ld4v(d.dX + idx, dxin);
+      if (CELL == PTK_CELL_HGRU) ld4v(d.dS + idx, dS);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float dA = dGe[p] * E[p];
+        if (CELL == PTK_CELL_HGRU) dA += dS[p];
+        oa[p] = dA * A[p] * (1.0f - A[p]);
+        de[p][o] = fmaf(dGe[p], A[p], gE[p]);
+        dxv[p][o] = dxin[p];
+      }
+      st4(d.aS + idx, oa);
+      tile_st(sA, L, o, oa);
+    }
+    __syncwarp();
+    warp_gemm(de, sA, sWau, L);     // dE += Wa_u^T a
+    warp_gemm(dxv, sA, sWaw, L);    // dX += Wa_w^T a
+    float dxs[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) dxs[i][p] = 0.f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
+      float pre[4], v[4];
+      stem_pre(sWp, sbp, c, xin, pre);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        v[p] = de[p][o];
+        const float dp = dxv[p][o] * dactf<ACT>(pre[p]);
+        part[0][o] += dp;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          part[1 + i][o] = fmaf(dp, xin[i][p], part[1 + i][o]);
+          dxs[i][p] = fmaf(sWp[c * 3 + i], dp, dxs[i][p]);
+        }
+      }
+      st4(d.gE + base + (size_t)c * P, v);
+    }
+    if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          dxs[i][p] += __shfl_xor_sync(0xffffffffu, dxs[i][p], 8);
+          dxs[i][p] += __shfl_xor_sync(0xffffffffu, dxs[i][p], 16);
+        }
+      if (L.og == 0) {
+        const size_t plane = (size_t)d.T * P;
+        float* o = d.dx + (size_t)b * 3 * plane + (size_t)t * P + pix;
+        if (t == 0) {
+          float g[4];
+          ld4v(d.dgoal + (size_t)b * P + pix, g);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) dxs[2][p] += g[p];
+        }
+        st4(o, dxs[0]);
+        st4(o + plane, dxs[1]);
+        st4(o + 2 * plane, dxs[2]);
+      }
+    }
+    __syncwarp();
+  }
+  cta_channel_sums<4>(part, sRed, sTot, L);
   float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
-  const int k = threadIdx.x;
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    acc_store(acc + ACC_BP + c, sTot[c], first);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc_store(acc + ACC_WP + c * 3 + i, sTot[(1 + i) * C + c], first);
+  }
+}
 
-  float a[C], E[C], dE[C];
+// ------------------------------------------------------------------------------------------------
+// gate weight / bias gradients of one step: six 32x32 outer-product sums over all pixels
+//   dWe_w += ge (x) S, dWe_u += ge (x) Ge, dWi_w += gi (x) X, dWi_u += gi (x) S, dWa_w += a (x) X,
+//   dWa_u += a (x) E;  d(bias) += sum ge / gi / a.
+// 384 threads = 6 matrices x 64 threads (4x4 outputs each); 64-pixel tiles, cp.async double-buffered.
+constexpr int GPX = 64, GSP = GPX + 4, GT_F = C * GSP;
+
+template <int CELL>
+__global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {
+  extern __shared__ __align__(16) float dsm[];
+  const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
+  const float* src[7] = {d.geb, d.giS, d.aS, (CELL == PTK_CELL_INT) ? d.I_at(t) : d.A_at(t), d.Ge, d.Xs, d.E_at(t)};
+  auto issue = [&](int tile, int buf) {
+    const int b = tile / tpi, pix_base = (tile - b * tpi) * GPX;
+    float* dstb = dsm + (size_t)buf * 7 * GT_F;
+    for (int q = tid; q < 7 * C * (GPX / 4); q += 384) {
+      const int k = q / (C * (GPX / 4)), r = q - k * (C * (GPX / 4)), c = r / (GPX / 4), part = r % (GPX / 4);
+      cp_async16(dstb + k * GT_F + c * GSP + part * 4, src[k] + ((size_t)b * C + c) * P + pix_base + part * 4);
+    }
+  };
+  const int m = tid >> 6, r = tid & 63, ocq = r >> 3, icq = r & 7;
+  const int gsel = m >> 1;                       // 0: ge, 1: gi, 2: a
+  const int vsel = (m == 0 || m == 3) ? 3 : (m == 1 ? 4 : (m == 5 ? 6 : 5));   // S, Ge, X, S, X, E
+  float acc[4][4];
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const size_t idx = base + (size_t)c * P;
-    const float A = d.A[idx], dGe = d.dGe[idx];
-    E[c] = Et[idx];
-    float dA = dGe * E[c];
-    if (CELL == PTK_CELL_HGRU) dA += d.dS[idx];
-    a[c] = dA * A * (1.0f - A);
-    dE[c] = fmaf(dGe, A, d.gE[idx]);              // dE partial, finished below
-  }
-  matvec32(dE, sWau, a);                           // dE += Wa_u^T a
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-  for (int c = 0; c < C; ++c) d.gE[base + (size_t)c * P] = dE[c];
-  float dXv[C];
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;
+  int buf = 0;
+  if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
+  cp_async_commit();
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < nTiles) issue(nxt, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* base = dsm + (size_t)buf * 7 * GT_F;
+    const float* gT = base + gsel * GT_F + ocq * GSP;
+    const float* vT = base + vsel * GT_F + icq * GSP;
+#pragma unroll 2
+    for (int p = 0; p < GPX / 4; ++p) {
+      float4 g[4], v[4];
 #pragma unroll
-  for (int c = 0; c < C; ++c) dXv[c] = d.dX[base + (size_t)c * P];
-  matvec32(dXv, sWaw, a);                          // dX += Wa_w^T a
-  float pre[C], xin[3];
-  stem_pixel_pre<ACT>(d.fv, b, t, py, px, sWp, sbp, pre, xin);
-  // stage: a, X, E  -> outer products; then dpre
-  stage(sQ0, a);
+      for (int i = 0; i < 4; ++i) g[i] = *reinterpret_cast<const float4*>(gT + i * 8 * GSP + 4 * p);
 #pragma unroll
-  for (int c = 0; c < C; ++c) sQ1[c * SP + k] = actf<ACT>(pre[c]);
-  stage(sQ2, E);
-  __syncthreads();
-  {
-    const float ra = tile_rowsum(sQ0);
-    if ((k & 3) == 0) acc_store(acc + ACC_BA + (k >> 2), ra, first);
-  }
-  tile_outer(sQ0, sQ1, acc + ACC_WAW, first);   // a (x) X
-  tile_outer(sQ0, sQ2, acc + ACC_WAU, first);   // a (x) E
-  __syncthreads();
-  float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+      for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(vT + j * 8 * GSP + 4 * p);
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float dp = dXv[c] * dactf<ACT>(pre[c]);
-    sQ0[c * SP + k] = dp;
-    dx0 = fmaf(sWp[c * 3 + 0], dp, dx0);
-    dx1 = fmaf(sWp[c * 3 + 1], dp, dx1);
-    dx2 = fmaf(sWp[c * 3 + 2], dp, dx2);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[i][j] = fmaf(g[i].x, v[j].x, fmaf(g[i].y, v[j].y, fmaf(g[i].z, v[j].z, fmaf(g[i].w, v[j].w, acc[i][j]))));
+    }
+    if (tid < 3 * C) {   // bias sums: row sums of ge / gi / a
+      const float4* row = reinterpret_cast<const float4*>(base + (tid >> 5) * GT_F + (tid & 31) * GSP);
+#pragma unroll 4
+      for (int p = 0; p < GPX / 4; ++p) {
+        const float4 v = row[p];
+        bsum += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
   }
-  sXin[0][k] = xin[0]; sXin[1][k] = xin[1]; sXin[2][k] = xin[2];
-  if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
-    const size_t plane = (size_t)d.T * P;
-    float* o = d.dx + (size_t)b * 3 * plane + (size_t)t * P + pix;
-    if (t == 0) dx2 += d.dgoal[(size_t)b * P + pix];
-    o[0] = dx0; o[plane] = dx1; o[2 * plane] = dx2;
-  }
-  __syncthreads();
-  {
-    const float rp = tile_rowsum(sQ0);
-    if ((k & 3) == 0) acc_store(acc + ACC_BP + (k >> 2), rp, first);
-  }
-  if (k < C * 3) {   // dWp[c][i] += sum_px dpre[c][px] * x[i][px]
-    const int c = k / 3, i = k % 3;
-    float s = 0.f;
-#pragma unroll 8
-    for (int p = 0; p < PT; ++p) s = fmaf(sQ0[c * SP + p], sXin[i][p], s);
-    acc_store(acc + ACC_WP + k, s, first);
-  }
+  cp_async_wait<0>();
+  float* ga = d.gacc + (size_t)blockIdx.x * GACC_N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc_store(ga + m * 1024 + (ocq + 8 * i) * C + icq + 8 * j, acc[i][j], first);
+  if (tid < 3 * C) acc_store(ga + GACC_BE + tid, bsum, first);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Readout backward (reverse of models/InT.py:236-241); one CTA per sample.
 // head partial layout per sample: [0..31] dWr, [32] dbr, [33..82] dWt, [83] dbt, [84] dWd, [85] dbd
-constexpr int HD_WR = 0, HD_BR = 32, HD_WT = 33, HD_BT = 83, HD_WD = 84, HD_BD = 85, HD_N = 86;
+constexpr int HD_WR = 0, HD_BR = 32, HD_WT = 33, HD_BT = 83, HD_WD = 84, HD_BD = 85;
 
 __global__ void __launch_bounds__(256) int_readout_bwd_kernel(IntDev d, const float* __restrict__ E) {
   extern __shared__ float sm[];
@@ -474,7 +506,7 @@ __global__ void __launch_bounds__(256) int_readout_bwd_kernel(IntDev d, const fl
   float* sR = sm;                 // zero-padded readout map r
   float* sG = sm + Hp2 * Wp2;     // zero-padded goal map
   float* sDr = sG + Hp2 * Wp2;    // [P] d r
-  __shared__ float sWt[50], sWr[C], sRed[8], sPool;
+  __shared__ float sWt[50], sWr[C], sRed[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < 50) sWt[tid] = __ldg(d.Wt + tid);
   if (tid < C) sWr[tid] = __ldg(d.Wr + tid);
@@ -528,9 +560,9 @@ __global__ void __launch_bounds__(256) int_readout_bwd_kernel(IntDev d, const fl
   // d target_conv weight: window sums of the padded maps
   for (int w = 0; w < 50; ++w) {
     const int ch = w / 25, ky = (w % 25) / 5, kx = w % 5;
-    const float* src = ch ? sG : sR;
+    const float* srcm = ch ? sG : sR;
     float v = 0.f;
-    for (int pix = tid; pix < P; pix += 256) v += src[(pix / W + ky) * Wp2 + pix % W + kx];
+    for (int pix = tid; pix < P; pix += 256) v += srcm[(pix / W + ky) * Wp2 + pix % W + kx];
     v = block_sum(v);
     if (tid == 0) hd[HD_WT + w] = dov * v;
   }
@@ -568,9 +600,9 @@ __global__ void __launch_bounds__(256) int_readout_bwd_kernel(IntDev d, const fl
 }
 
 // ------------------------------------------------------------------------------------------------
-// finalize: fold per-tile / per-CTA / per-sample partials (double) into the flat gradient vector.
+// finalize: fold per-CTA / per-sample partials (double) into the flat gradient vector.
 struct FinalizeArgs {
-  int nTiles, B, wgroups;
+  int pw_ctas, gate_ctas, B, wgroups;
   int64_t off[PTK_INT_NPARAM + 1];
 };
 
@@ -581,7 +613,7 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
     while (e >= f.off[p + 1]) ++p;
     const int j = (int)(e - f.off[p]);
     double s = 0;
-    int accoff = -1, headoff = -1;
+    int accoff = -1, gaccoff = -1, headoff = -1;
     switch (p) {
       case PTK_P_PREPROC_W: accoff = ACC_WP + j; break;
       case PTK_P_PREPROC_B: accoff = ACC_BP + j; break;
@@ -589,15 +621,15 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
       case PTK_P_MU: accoff = ACC_MU + j; break;
       case PTK_P_GAMMA: accoff = ACC_GAMMA + j; break;
       case PTK_P_KAPPA: accoff = ACC_KAPPA + j; break;
-      case PTK_P_AW_W: accoff = ACC_WAW + j; break;
-      case PTK_P_AU_W: accoff = ACC_WAU + j; break;
-      case PTK_P_IW_W: accoff = ACC_WIW + j; break;
-      case PTK_P_IU_W: accoff = ACC_WIU + j; break;
-      case PTK_P_EW_W: accoff = ACC_WEW + j; break;
-      case PTK_P_EU_W: accoff = ACC_WEU + j; break;
-      case PTK_P_AW_B: case PTK_P_AU_B: accoff = ACC_BA + j; break;
-      case PTK_P_IW_B: case PTK_P_IU_B: accoff = ACC_BI + j; break;
-      case PTK_P_EW_B: case PTK_P_EU_B: accoff = ACC_BE + j; break;
+      case PTK_P_AW_W: gaccoff = GACC_WAW + j; break;
+      case PTK_P_AU_W: gaccoff = GACC_WAU + j; break;
+      case PTK_P_IW_W: gaccoff = GACC_WIW + j; break;
+      case PTK_P_IU_W: gaccoff = GACC_WIU + j; break;
+      case PTK_P_EW_W: gaccoff = GACC_WEW + j; break;
+      case PTK_P_EU_W: gaccoff = GACC_WEU + j; break;
+      case PTK_P_AW_B: case PTK_P_AU_B: gaccoff = GACC_BA + j; break;
+      case PTK_P_IW_B: case PTK_P_IU_B: gaccoff = GACC_BI + j; break;
+      case PTK_P_EW_B: case PTK_P_EU_B: gaccoff = GACC_BE + j; break;
       case PTK_P_READOUT_W: headoff = HD_WR + j; break;
       case PTK_P_READOUT_B: headoff = HD_BR; break;
       case PTK_P_TARGET_W: headoff = HD_WT + j; break;
@@ -607,7 +639,9 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
       default: break;
     }
     if (accoff >= 0) {
-      for (int i = 0; i < f.nTiles; ++i) s += (double)d.acc[(size_t)i * ACC_N + accoff];
+      for (int i = 0; i < f.pw_ctas; ++i) s += (double)d.acc[(size_t)i * ACC_N + accoff];
+    } else if (gaccoff >= 0) {
+      for (int i = 0; i < f.gate_ctas; ++i) s += (double)d.gacc[(size_t)i * GACC_N + gaccoff];
     } else if (headoff >= 0) {
       for (int i = 0; i < f.B; ++i) s += (double)d.head[(size_t)i * HEAD_N + headoff];
     } else if (p == PTK_P_W_EXC || p == PTK_P_W_INH) {
@@ -625,43 +659,56 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
 }
 
 // ---- host ----------------------------------------------------------------------------------
-static constexpr size_t SM_BWD_A = (size_t)(4 * C * C + 4 * C * SP) * sizeof(float);
-static constexpr size_t SM_BWD_C = (size_t)(6 * C * C + 4 * C * SP) * sizeof(float);
-static constexpr size_t SM_BWD_D = (size_t)(2 * C * C + 3 * C * SP) * sizeof(float);
+static constexpr size_t SM_BWD_C = (size_t)(4 * C * C + 4 * 2 * TILE_F) * sizeof(float);
+static constexpr size_t SM_BWD_D = (size_t)(2 * C * C + 4 * 1 * TILE_F) * sizeof(float);
+static constexpr size_t SM_GATE = (size_t)(2 * 7 * GT_F) * sizeof(float);
 
 template <int CELL, int ACT>
 static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int P = d.H * d.W;
-  const int tiles = d.B * P / PT;
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_a_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_A));
+  const int grid = d.pw_ctas;
+  const int grid_c = grid < 148 * 2 ? grid : 148 * 2;   // bwd_c needs > 170 registers: 2 CTAs per SM
+  PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)grid * ACC_N * sizeof(float), st));
+  const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
+  PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
   PTK_CUDA_OK(cudaFuncSetAttribute(int_readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-  { ProfileScope ps(PTK_PROF_MISC, st);
-  int_readout_bwd_kernel<<<d.B, 256, smr, st>>>(d, d.ckE + d.ck_stride * d.T); }
+  {
+    ProfileScope ps(PTK_PROF_MISC, st);
+    int_readout_bwd_kernel<<<d.B, 256, smr, st>>>(d, d.E_at(d.T));
+  }
   PTK_LAUNCH_OK("int_readout_bwd_kernel");
   const int ew_blocks = 148 * 4;
   for (int t = d.T - 1; t >= 0; --t) {
     const int first = (t == d.T - 1);
     int rc;
-    { ProfileScope ps(PTK_PROF_POINT_BWD, st);
-    int_bwd_a_kernel<CELL, ACT><<<tiles, PT, SM_BWD_A, st>>>(d, t, first); }
+    {
+      ProfileScope ps(PTK_PROF_POINT_BWD, st);
+      int_bwd_a_kernel<ACT><<<grid, 128, 0, st>>>(d, t, first);
+    }
     PTK_LAUNCH_OK("int_bwd_a_kernel");
-    { ProfileScope ps(PTK_PROF_BN_APPLY, st);
-    bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1 + d.y_stride * t, t, 1); }
+    {
+      ProfileScope ps(PTK_PROF_BN_APPLY, st);
+      bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1_at(t), t, 1);
+    }
     PTK_LAUNCH_OK("bn_apply_kernel");
     ConvArgs c1{d.dAct, d.w_exc_d, d.gI, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
-    WgradArgs w1{d.ckI + d.ck_stride * (t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
+    WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
     { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w1, WGRAD_GROUPS, st); }
     if (rc) return rc;
-    { ProfileScope ps(PTK_PROF_POINT_BWD, st);
-    int_bwd_c_kernel<CELL, ACT><<<tiles, PT, SM_BWD_C, st>>>(d, t, first); }
+    {
+      ProfileScope ps(PTK_PROF_POINT_BWD, st);
+      int_bwd_c_kernel<CELL, ACT><<<grid_c, 128, SM_BWD_C, st>>>(d, t, first);
+    }
     PTK_LAUNCH_OK("int_bwd_c_kernel");
-    { ProfileScope ps(PTK_PROF_BN_APPLY, st);
-    bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0 + d.y_stride * t, t, 0); }
+    {
+      ProfileScope ps(PTK_PROF_BN_APPLY, st);
+      bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0_at(t), t, 0);
+    }
     PTK_LAUNCH_OK("bn_apply_kernel");
     ConvArgs c0{d.dAct, d.w_inh_d, d.dGe, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
@@ -669,16 +716,25 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
     { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w0, WGRAD_GROUPS, st); }
     if (rc) return rc;
-    { ProfileScope ps(PTK_PROF_POINT_BWD, st);
-    int_bwd_d_kernel<CELL, ACT><<<tiles, PT, SM_BWD_D, st>>>(d, t, first); }
+    {
+      ProfileScope ps(PTK_PROF_POINT_BWD, st);
+      int_bwd_d_kernel<CELL, ACT><<<grid, 128, SM_BWD_D, st>>>(d, t, first);
+    }
     PTK_LAUNCH_OK("int_bwd_d_kernel");
+    {
+      ProfileScope ps(PTK_PROF_GATE_WGRAD, st);
+      gate_wgrad_kernel<CELL><<<gate_grid, 384, SM_GATE, st>>>(d, t, first);
+    }
+    PTK_LAUNCH_OK("gate_wgrad_kernel");
   }
   FinalizeArgs f;
-  f.nTiles = tiles; f.B = d.B; f.wgroups = WGRAD_GROUPS;
+  f.pw_ctas = grid; f.gate_ctas = gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
-  { ProfileScope ps(PTK_PROF_MISC, st);
-  int_finalize_kernel<<<148 * 2, 256, 0, st>>>(d, f); }
+  {
+    ProfileScope ps(PTK_PROF_MISC, st);
+    int_finalize_kernel<<<148 * 2, 256, 0, st>>>(d, f);
+  }
   PTK_LAUNCH_OK("int_finalize_kernel");
   return PTK_OK;
 }

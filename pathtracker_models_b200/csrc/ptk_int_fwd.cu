@@ -5,147 +5,209 @@
 // models/ffhgru_hierarchy.py:135-173 (hConvGRUCell.forward); stem models/InT.py:212-213;
 // readout models/InT.py:236-241.  Equation numbers (1)-(13) are those of SURVEY.md section 8.
 //
-// One thread = one pixel holding all 32 channels in registers; the 1x1 gate convolutions are
-// 32x32 mat-vecs against shared-memory weights ([in][out], broadcast float4 reads).
-#include "ptk_common.cuh"
+// Warp-tile kernels (ptk_pw.cuh): a warp owns 32 pixels x 32 channels, the six 1x1 gate
+// convolutions are register-tiled 32x32x32 products against shared-memory tiles; CTAs are
+// persistent (weights staged once) and warps stride over the tiles.
 #include "ptk_int.h"
 #include "ptk_profile.h"
+#include "ptk_pw.cuh"
 
 namespace ptk {
 
-__device__ __forceinline__ void smem_fill(float* dst, const float* __restrict__ src, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
-}
+constexpr int TILE_F = C * TP;   // floats per warp tile
 
-// stem of one pixel: X = nl(Wp x_t + bp)   (models/InT.py:192,212-213)
+// eqs (1)-(2) for frame t: A = sigmoid(Wa_w X + Wa_u E + b), Ge = A*E.  sE must hold E_t.
 template <int ACT>
-__device__ __forceinline__ void stem_pixel(const FrameView& fv, int b, int t, int y, int x,
-                                           const float* sWp, const float* sbp, float (&X)[C]) {
-  const float x0 = fv.at(b, 0, t, y, x), x1 = fv.at(b, 1, t, y, x), x2 = fv.at(b, 2, t, y, x);
+__device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, int pix_base, float* sX,
+                                               const float* sE, const float* sWaw, const float* sWau,
+                                               const float* sba, const float* sWp, const float* sbp,
+                                               const Lane& L) {
+  const int P = d.H * d.W, pix = pix_base + L.pxo;
+  float xin[3][4];
+  frame_px(d.fv, b, t, pix, d.W, xin);
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float pre = fmaf(sWp[c * 3 + 2], x2, fmaf(sWp[c * 3 + 1], x1, fmaf(sWp[c * 3 + 0], x0, sbp[c])));
-    X[c] = actf<ACT>(pre);
+  for (int o = 0; o < 8; ++o) {
+    float pre[4];
+    stem_pre(sWp, sbp, L.oc0 + o, xin, pre);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) pre[p] = actf<ACT>(pre[p]);
+    tile_st(sX, L, o, pre);
+  }
+  __syncwarp();
+  float acc[4][8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float bb = sba[L.oc0 + o];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p][o] = bb;
+  }
+  warp_gemm(acc, sX, sWaw, L);
+  warp_gemm(acc, sE, sWau, L);
+  float* Aout = d.A_at(t) + (size_t)b * d.a_bstride + pix;
+  float* Geout = d.Ge + (size_t)b * C * P + pix;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    float e[4], a[4], ge[4];
+    tile_ld(sE, L, o, e);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { a[p] = sigmoidf_(acc[p][o]); ge[p] = a[p] * e[p]; }
+    st4(Aout + (size_t)(L.oc0 + o) * P, a);
+    st4(Geout + (size_t)(L.oc0 + o) * P, ge);
   }
 }
 
-// eqs (1)-(2) for frame t given E_t: A = sigmoid(Wa_w X + Wa_u E), Ge = A*E
 template <int ACT>
-__device__ __forceinline__ void attention_pixel(const IntDev& d, const float* sWaw, const float* sWau,
-                                                const float* sba, const float (&X)[C], const float (&E)[C],
-                                                int b, int pix, int P, float* Aout, long long a_bstride) {
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = sba[c];
-  matvec32(acc, sWaw, X);
-  matvec32(acc, sWau, E);
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float A = sigmoidf_(acc[c]);
-    Aout[b * a_bstride + (size_t)c * P + pix] = A;
-    d.Ge[((size_t)b * C + c) * P + pix] = A * E[c];
-  }
-}
-
-template <int ACT>
-__global__ void __launch_bounds__(PT) int_pre_kernel(IntDev d, int t) {
-  __shared__ __align__(16) float sWaw[C * C], sWau[C * C];
+__global__ void __launch_bounds__(128) int_pre_kernel(IntDev d, int t) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWaw = dsm;
+  float* sWau = sWaw + C * C;
+  float* tiles = sWau + C * C;
   __shared__ float sWp[C * 3], sbp[C], sba[C];
-  smem_fill(sWaw, d.gateT[0], C * C);
-  smem_fill(sWau, d.gateT[1], C * C);
-  smem_fill(sWp, d.Wp, C * 3);
-  smem_fill(sbp, d.bp, C);
+  cta_fill(sWaw, d.gateT[0], C * C);
+  cta_fill(sWau, d.gateT[1], C * C);
+  cta_fill(sWp, d.Wp, C * 3);
+  cta_fill(sbp, d.bp, C);
   if (threadIdx.x < C) sba[threadIdx.x] = __ldg(d.gate_b[0] + threadIdx.x) + __ldg(d.gate_b[1] + threadIdx.x);
   __syncthreads();
-  const int P = d.H * d.W, tilesPer = P / PT;
-  const int b = blockIdx.x / tilesPer, pix = (blockIdx.x % tilesPer) * PT + threadIdx.x;
-  float X[C], E[C];
-  stem_pixel<ACT>(d.fv, b, t, pix / d.W, pix % d.W, sWp, sbp, X);
-  const float* Et = d.ckE + d.ck_stride * d.slot(t);
-#pragma unroll
-  for (int c = 0; c < C; ++c) E[c] = Et[((size_t)b * C + c) * P + pix];
-  attention_pixel<ACT>(d, sWaw, sWau, sba, X, E, b, pix, P, d.A + (size_t)t * d.a_tstride, d.a_bstride);
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  float* sX = tiles + warp * 2 * TILE_F;
+  float* sE = sX + TILE_F;
+  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async(sE, d.E_at(t), (size_t)C * P, b, pix_base, P);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    attention_tile<ACT>(d, t, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, L);
+    __syncwarp();
+  }
 }
 
 // eqs (3b)-(9): BatchNorm0 apply, inhibition drive, inhibition gate + blend, excitation gate.
 template <int CELL, int ACT>
-__global__ void __launch_bounds__(PT) int_mid_kernel(IntDev d, int t) {
-  __shared__ __align__(16) float sWiw[C * C], sWiu[C * C], sWew[C * C], sWeu[C * C];
+__global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWiw = dsm;
+  float* sWiu = sWiw + C * C;
+  float* sWew = sWiu + C * C;
+  float* sWeu = sWew + C * C;
+  float* tiles = sWeu + C * C;
   __shared__ float sWp[C * 3], sbp[C], sbi[C], sbe[C], sAl[C], sMu[C], sScale[C], sShift[C];
-  smem_fill(sWiw, d.gateT[2], C * C);
-  smem_fill(sWiu, d.gateT[3], C * C);
-  smem_fill(sWew, d.gateT[4], C * C);
-  smem_fill(sWeu, d.gateT[5], C * C);
-  smem_fill(sWp, d.Wp, C * 3);
-  smem_fill(sbp, d.bp, C);
-  smem_fill(sAl, d.alpha, C);
-  smem_fill(sMu, d.mu, C);
+  cta_fill(sWiw, d.gateT[2], C * C);
+  cta_fill(sWiu, d.gateT[3], C * C);
+  cta_fill(sWew, d.gateT[4], C * C);
+  cta_fill(sWeu, d.gateT[5], C * C);
+  cta_fill(sWp, d.Wp, C * 3);
+  cta_fill(sbp, d.bp, C);
+  cta_fill(sAl, d.alpha, C);
+  cta_fill(sMu, d.mu, C);
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
     sbi[c] = __ldg(d.gate_b[2] + c) + __ldg(d.gate_b[3] + c);
     sbe[c] = __ldg(d.gate_b[4] + c) + __ldg(d.gate_b[5] + c);
     const float* st = d.stat(t, 0);   // BN0 of step t: mean, rstd
     const float sc = __ldg(d.bn_w[0] + c) * st[C + c];
-    sScale[c] = sc;                                            // U = Y0*scale + shift
+    sScale[c] = sc;                   // U = Y0*scale + shift
     sShift[c] = __ldg(d.bn_b[0] + c) - st[c] * sc;
   }
   __syncthreads();
-  const int P = d.H * d.W, tilesPer = P / PT;
-  const int b = blockIdx.x / tilesPer, pix = (blockIdx.x % tilesPer) * PT + threadIdx.x;
-  const size_t base = (size_t)b * C * P + pix;
-  const int slot_in = d.slot(t), slot_out = d.slot(t + 1);
-  const float* It = d.ckI + d.ck_stride * slot_in;
-  float* Iout = d.ckI + d.ck_stride * slot_out;
-  const float* At = d.A + (size_t)t * d.a_tstride + (size_t)b * d.a_bstride + pix;
-
-  float X[C], I[C], S[C];
-  stem_pixel<ACT>(d.fv, b, t, pix / d.W, pix % d.W, sWp, sbp, X);
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  float* sX = tiles + warp * 3 * TILE_F;
+  float* sS = sX + TILE_F;
+  float* sGe = sS + TILE_F;
+  const float* It = d.I_at(t);
+  float* Iout = d.I_at(t + 1);
+  const float* Y0 = d.Y0_at(t);
+  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
+    else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
+    warp_tile_load_async(sGe, d.Ge, (size_t)C * P, b, pix_base, P);
+    cp_async_commit();
+    float xin[3][4];
+    frame_px(d.fv, b, t, pix, d.W, xin);
 #pragma unroll
-  for (int c = 0; c < C; ++c) I[c] = It[base + (size_t)c * P];
+    for (int o = 0; o < 8; ++o) {
+      float pre[4];
+      stem_pre(sWp, sbp, L.oc0 + o, xin, pre);
 #pragma unroll
-  for (int c = 0; c < C; ++c) S[c] = (CELL == PTK_CELL_INT) ? I[c] : At[(size_t)c * P];
-  {
-    float acc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = sbi[c];
-    matvec32(acc, sWiw, X);
-    matvec32(acc, sWiu, S);
-    const float* Y0 = d.Y0 + d.y_stride * d.yslot(t);
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float Gi = sigmoidf_(acc[c]);
-      const float U = fmaf(Y0[base + (size_t)c * P], sScale[c], sShift[c]);
-      const float Pp = U * fmaf(sAl[c], S[c], sMu[c]);
-      const float Q = actf<ACT>(Pp);
-      const float Ihat = actf<ACT>(X[c] - Q);
-      Iout[base + (size_t)c * P] = (1.0f - Gi) * I[c] + Gi * Ihat;
+      for (int p = 0; p < 4; ++p) pre[p] = actf<ACT>(pre[p]);
+      tile_st(sX, L, o, pre);
     }
-  }
-  {
-    float acc[C], Ge[C];
+    cp_async_wait<0>();
+    __syncwarp();
+    float acc[4][8];
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = sbe[c];
-    matvec32(acc, sWew, S);
+    for (int o = 0; o < 8; ++o) {
+      const float bb = sbi[L.oc0 + o];
 #pragma unroll
-    for (int c = 0; c < C; ++c) Ge[c] = d.Ge[base + (size_t)c * P];
-    matvec32(acc, sWeu, Ge);
+      for (int p = 0; p < 4; ++p) acc[p][o] = bb;
+    }
+    warp_gemm(acc, sX, sWiw, L);
+    warp_gemm(acc, sS, sWiu, L);
 #pragma unroll
-    for (int c = 0; c < C; ++c) d.Gex[base + (size_t)c * P] = sigmoidf_(acc[c]);
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
+      const size_t idx = base + (size_t)c * P;
+      float X[4], S[4], I[4], y0[4], gi[4], out[4];
+      tile_ld(sX, L, o, X);
+      tile_ld(sS, L, o, S);
+      if (CELL == PTK_CELL_INT) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) I[p] = S[p];
+      } else {
+        ld4v(It + idx, I);
+      }
+      ld4v(Y0 + idx, y0);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        gi[p] = sigmoidf_(acc[p][o]);
+        const float U = fmaf(y0[p], sScale[c], sShift[c]);
+        const float Pp = U * fmaf(sAl[c], S[p], sMu[c]);
+        const float Q = actf<ACT>(Pp);
+        const float Ihat = actf<ACT>(X[p] - Q);
+        out[p] = (1.0f - gi[p]) * I[p] + gi[p] * Ihat;
+      }
+      st4(d.Gi_at(t) + idx, gi);
+      st4(Iout + idx, out);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const float bb = sbe[L.oc0 + o];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[p][o] = bb;
+    }
+    warp_gemm(acc, sS, sWew, L);
+    warp_gemm(acc, sGe, sWeu, L);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float gx[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) gx[p] = sigmoidf_(acc[p][o]);
+      st4(d.Gex_at(t) + base + (size_t)(L.oc0 + o) * P, gx);
+    }
+    __syncwarp();
   }
 }
 
 // eqs (10b)-(13) for step t, then (1)-(2) for step t+1 (if any).
 template <int ACT>
-__global__ void __launch_bounds__(PT) int_post_kernel(IntDev d, int t, int has_next) {
-  __shared__ __align__(16) float sWaw[C * C], sWau[C * C];
+__global__ void __launch_bounds__(128) int_post_kernel(IntDev d, int t, int has_next) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWaw = dsm;
+  float* sWau = sWaw + C * C;
+  float* tiles = sWau + C * C;
   __shared__ float sWp[C * 3], sbp[C], sba[C], sKa[C], sGa[C], sScale[C], sShift[C], sWr[C];
-  smem_fill(sWaw, d.gateT[0], C * C);
-  smem_fill(sWau, d.gateT[1], C * C);
-  smem_fill(sWp, d.Wp, C * 3);
-  smem_fill(sbp, d.bp, C);
-  smem_fill(sKa, d.kappa, C);
-  smem_fill(sGa, d.gamma, C);
-  smem_fill(sWr, d.Wr, C);
+  cta_fill(sWaw, d.gateT[0], C * C);
+  cta_fill(sWau, d.gateT[1], C * C);
+  cta_fill(sWp, d.Wp, C * 3);
+  cta_fill(sbp, d.bp, C);
+  cta_fill(sKa, d.kappa, C);
+  cta_fill(sGa, d.gamma, C);
+  cta_fill(sWr, d.Wr, C);
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
     sba[c] = __ldg(d.gate_b[0] + c) + __ldg(d.gate_b[1] + c);
@@ -155,34 +217,51 @@ __global__ void __launch_bounds__(PT) int_post_kernel(IntDev d, int t, int has_n
     sShift[c] = __ldg(d.bn_b[1] + c) - st[c] * sc;
   }
   __syncthreads();
-  const int P = d.H * d.W, tilesPer = P / PT;
-  const int b = blockIdx.x / tilesPer, pix = (blockIdx.x % tilesPer) * PT + threadIdx.x;
-  const size_t base = (size_t)b * C * P + pix;
-  const int slot_in = d.slot(t), slot_out = d.slot(t + 1);
-  const float* Et = d.ckE + d.ck_stride * slot_in;
-  const float* I2 = d.ckI + d.ck_stride * slot_out;
-  float* Eout = d.ckE + d.ck_stride * slot_out;
-  const float* Y1 = d.Y1 + d.y_stride * d.yslot(t);
-
-  float E2[C];
-  float sread = __ldg(d.br);
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  float* sX = tiles + warp * 2 * TILE_F;
+  float* sE = sX + TILE_F;
+  const float* Et = d.E_at(t);
+  const float* I2 = d.I_at(t + 1);
+  float* Eout = d.E_at(t + 1);
+  const float* Y1 = d.Y1_at(t);
+  const float* Gx = d.Gex_at(t);
+  const float br = __ldg(d.br);
+  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    float sread[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float V = fmaf(Y1[base + (size_t)c * P], sScale[c], sShift[c]);
-    const float R = V * fmaf(sKa[c], I2[base + (size_t)c * P], sGa[c]);
-    const float Ehat = actf<ACT>(R);
-    const float Gx = d.Gex[base + (size_t)c * P];
-    const float e = (1.0f - Gx) * Et[base + (size_t)c * P] + Gx * Ehat;
-    E2[c] = e;
-    Eout[base + (size_t)c * P] = e;
-    sread = fmaf(sWr[c], e, sread);
-  }
-  if (d.states != nullptr)  // testmode: states.append(readout_conv(excitation)), InT.py:233
-    d.states[((size_t)b * d.T + t) * P + pix] = sread;
-  if (has_next) {
-    float X[C];
-    stem_pixel<ACT>(d.fv, b, t + 1, pix / d.W, pix % d.W, sWp, sbp, X);
-    attention_pixel<ACT>(d, sWaw, sWau, sba, X, E2, b, pix, P, d.A + (size_t)(t + 1) * d.a_tstride, d.a_bstride);
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
+      const size_t idx = base + (size_t)c * P;
+      float y1[4], i2[4], e[4], gx[4], e2[4];
+      ld4v(Y1 + idx, y1);
+      ld4v(I2 + idx, i2);
+      ld4v(Et + idx, e);
+      ld4v(Gx + idx, gx);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float V = fmaf(y1[p], sScale[c], sShift[c]);
+        const float R = V * fmaf(sKa[c], i2[p], sGa[c]);
+        const float Ehat = actf<ACT>(R);
+        e2[p] = (1.0f - gx[p]) * e[p] + gx[p] * Ehat;
+        sread[p] = fmaf(sWr[c], e2[p], sread[p]);
+      }
+      st4(Eout + idx, e2);
+      tile_st(sE, L, o, e2);
+    }
+    if (d.states != nullptr) {   // testmode: states.append(readout_conv(excitation)), InT.py:233
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        sread[p] += __shfl_xor_sync(0xffffffffu, sread[p], 8);
+        sread[p] += __shfl_xor_sync(0xffffffffu, sread[p], 16);
+        sread[p] += br;
+      }
+      if (L.og == 0) st4(d.states + ((size_t)b * d.T + t) * P + pix, sread);
+    }
+    if (has_next) attention_tile<ACT>(d, t + 1, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, L);
+    __syncwarp();
   }
 }
 
@@ -252,37 +331,52 @@ __global__ void prep_gates_kernel(IntGateSrc g, float* gateT) {
 }
 
 // ---- host ----------------------------------------------------------------------------------
+int pw_grid(int B, int H, int W) {
+  const int nWT = B * H * W / WPX;
+  const int g = (nWT + 3) / 4;
+  return g < PW_MAX_CTAS ? g : PW_MAX_CTAS;
+}
+
+static constexpr size_t SM_PRE = (size_t)(2 * C * C + 4 * 2 * TILE_F) * sizeof(float);
+static constexpr size_t SM_MID = (size_t)(4 * C * C + 4 * 3 * TILE_F) * sizeof(float);
+
 template <int ACT>
 static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
-  const int P = d.H * d.W;
-  const int tiles = d.B * P / PT;
-  { ProfileScope ps(PTK_PROF_POINT_FWD, st);
-  int_pre_kernel<ACT><<<tiles, PT, 0, st>>>(d, 0); }
+  const int grid = pw_grid(d.B, d.H, d.W);
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_pre_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_PRE));
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_post_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_PRE));
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_mid_kernel<PTK_CELL_INT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MID));
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_mid_kernel<PTK_CELL_HGRU, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MID));
+  {
+    ProfileScope ps(PTK_PROF_POINT_FWD, st);
+    int_pre_kernel<ACT><<<grid, 128, SM_PRE, st>>>(d, 0);
+  }
   PTK_LAUNCH_OK("int_pre_kernel");
   for (int t = 0; t < d.T; ++t) {
-    const int slot_in = d.slot(t), slot_out = d.slot(t + 1);
-    ConvArgs c0{d.Ge, d.w_inh_f, d.Y0 + d.y_stride * d.yslot(t), d.B, d.H, d.W, 0,
-                d.bn_part, d.counter, d.stat_w(t, 0)};
     int rc;
+    ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0)};
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
     if (rc) return rc;
-    { ProfileScope ps(PTK_PROF_POINT_FWD, st);
-    if (cell == PTK_CELL_INT) int_mid_kernel<PTK_CELL_INT, ACT><<<tiles, PT, 0, st>>>(d, t);
-    else int_mid_kernel<PTK_CELL_HGRU, ACT><<<tiles, PT, 0, st>>>(d, t); }
+    {
+      ProfileScope ps(PTK_PROF_POINT_FWD, st);
+      if (cell == PTK_CELL_INT) int_mid_kernel<PTK_CELL_INT, ACT><<<grid, 128, SM_MID, st>>>(d, t);
+      else int_mid_kernel<PTK_CELL_HGRU, ACT><<<grid, 128, SM_MID, st>>>(d, t);
+    }
     PTK_LAUNCH_OK("int_mid_kernel");
-    ConvArgs c1{d.ckI + d.ck_stride * slot_out, d.w_exc_f, d.Y1 + d.y_stride * d.yslot(t), d.B, d.H,
-                d.W, 0, d.bn_part, d.counter, d.stat_w(t, 1)};
+    ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1)};
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
-    { ProfileScope ps(PTK_PROF_POINT_FWD, st);
-    int_post_kernel<ACT><<<tiles, PT, 0, st>>>(d, t, t + 1 < d.T); }
+    {
+      ProfileScope ps(PTK_PROF_POINT_FWD, st);
+      int_post_kernel<ACT><<<grid, 128, SM_PRE, st>>>(d, t, t + 1 < d.T);
+    }
     PTK_LAUNCH_OK("int_post_kernel");
-    (void)slot_in;
   }
-  const int slot_T = d.slot(d.T);
   const size_t sm = (size_t)2 * (d.H + 4) * (d.W + 4) * sizeof(float);
-  { ProfileScope ps(PTK_PROF_MISC, st);
-  int_readout_kernel<<<d.B, 256, sm, st>>>(d, d.ckE + d.ck_stride * slot_T, d.logits); }
+  {
+    ProfileScope ps(PTK_PROF_MISC, st);
+    int_readout_kernel<<<d.B, 256, sm, st>>>(d, d.E_at(d.T), d.logits);
+  }
   PTK_LAUNCH_OK("int_readout_kernel");
   return PTK_OK;
 }

@@ -4,7 +4,7 @@
 // kernel classes reported by ptk_profile_stop
 enum {
   PTK_PROF_CONV_FWD = 0, PTK_PROF_CONV_DGRAD = 1, PTK_PROF_WGRAD = 2, PTK_PROF_POINT_FWD = 3,
-  PTK_PROF_POINT_BWD = 4, PTK_PROF_BN_APPLY = 5, PTK_PROF_MISC = 6, PTK_PROF_NKINDS = 7
+  PTK_PROF_POINT_BWD = 4, PTK_PROF_BN_APPLY = 5, PTK_PROF_MISC = 6, PTK_PROF_GATE_WGRAD = 7, PTK_PROF_NKINDS = 8
 };
 
 namespace ptk {

@@ -40,7 +40,7 @@ def test_dims_validation_without_gpu():
     L = _lib.lib()
     assert L.ptk_int_workspace_bytes(ctypes.byref(_lib.PtkDims(64, 64, 32, 32, 32, 7, 0, 0, 0, 0))) > 0
     assert L.ptk_int_saved_bytes(ctypes.byref(_lib.PtkDims(64, 64, 32, 32, 32, 7, 0, 0, 0, 0))) == \
-        ((2 * 65 + 2 * 64) * 64 * 32 * 1024 + 64 * 128) * 4
+        ((2 * 65 + 5 * 64) * 64 * 32 * 1024 + 64 * 128) * 4
     assert L.ptk_int_workspace_bytes(ctypes.byref(_lib.PtkDims(2, 4, 20, 20, 32, 7, 0, 0, 0, 0))) == 0
     assert b"unsupported shape" in L.ptk_last_error()
     assert L.ptk_int_workspace_bytes(ctypes.byref(_lib.PtkDims(2, 4, 32, 32, 32, 15, 0, 0, 0, 0))) == 0

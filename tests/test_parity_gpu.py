@@ -63,11 +63,14 @@ def test_per_step_checkpoints_vs_oracle():
     B, T, H, W = case["shape"]
     S = B * 32 * H * W
     sv = saved.view(torch.float32).cpu()
-    ckI = sv[:(T + 1) * S].view(T + 1, B, 32, H, W)
-    ckE = sv[(T + 1) * S:2 * (T + 1) * S].view(T + 1, B, 32, H, W)
-    Y0 = sv[2 * (T + 1) * S:2 * (T + 1) * S + T * S].view(T, B, 32, H, W)
-    Y1 = sv[2 * (T + 1) * S + T * S:2 * (T + 1) * S + 2 * T * S].view(T, B, 32, H, W)
-    st = sv[2 * (T + 1) * S + 2 * T * S:].view(T, 2, 2, 32)
+    off = [0]
+    for n in (T + 1, T + 1, T, T, T, T, T):      # ckI, ckE, Y0, Y1, A, Gi, Gex (ptk_api.cu:bind_saved)
+        off.append(off[-1] + n * S)
+    ckI = sv[off[0]:off[1]].view(T + 1, B, 32, H, W)
+    ckE = sv[off[1]:off[2]].view(T + 1, B, 32, H, W)
+    Y0 = sv[off[2]:off[3]].view(T, B, 32, H, W)
+    Y1 = sv[off[3]:off[4]].view(T, B, 32, H, W)
+    st = sv[off[7]:].view(T, 2, 2, 32)
     p = O.unpack(case["sd"])
     with torch.no_grad():
         lo, so = O.forward(case["x"], p)
