@@ -140,6 +140,7 @@ def run_b200(args):
 
     torch.manual_seed(0)
     model = InT.InT(dimensions=C, timesteps=T, kernel_size=K).to(dev)
+    model.conv_mode = _lib.PTK_CONV_BF16X3 if args.conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
     if world > 1:
         broadcast_parameters(model)
         attach_data_parallel(model)
@@ -220,14 +221,14 @@ def run_b200(args):
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "InT 64 frames 32x32, 14 distractors, batch %d/GPU (BASELINE configs[1])" % B,
-                       "global_batch": B * world, "parallelism": "dp%d" % world, "conv_mode": "fp32-ffma",
+                       "global_batch": B * world, "parallelism": "dp%d" % world, "conv_mode": args.conv_mode,
                        "l2": "no flush: per-step working set (2.2 GB of checkpoints per GPU) exceeds the 126 MB L2; "
                              "%d distinct input batches rotate" % nbuf},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 4),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "clocks": sampler.result(),
-            "roofline": {"bound": "tensor", "kernel": "conv7_ffma_kernel (fwd + dgrad launches)",
+            "roofline": {"bound": "tensor", "kernel": ("conv7_tc_kernel" if args.conv_mode == "bf16x3" else "conv7_ffma_kernel") + " (fwd + dgrad launches)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tensor_peak) if achieved else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % src,
@@ -255,6 +256,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3"],
+                    help="7x7 convolutions: strict-fp32 FFMA, or 3-pass split-bf16 tcgen05 (both parity-gated)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -117,6 +117,16 @@ PTK_API int ptk_synth_pathtracker(uint64_t seed, uint64_t first_index, int32_t B
                           int32_t W, int32_t n_distractors, int32_t speed, float* x, float* y,
                           void* stream);
 
+/* One horizontal-connection convolution on its own (test / measurement entry; the time loop calls the
+ * same kernels internally): out (+)= conv2d(in, weight, padding=3) (transpose=0, models/InT.py:161,172)
+ * or conv_transpose2d(in, weight, padding=3) (transpose=1, its data gradient).  in/out [B,32,H,W],
+ * weight [32,32,7,7] as stored by torch; stats optional [2][32] out: batch mean and 1/sqrt(var+1e-3)
+ * of the convolution result (the BatchNorm that follows it). */
+PTK_API size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W);
+PTK_API int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transpose, int32_t accumulate,
+                      const float* in, const float* weight, float* out, float* stats, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* Measurement hooks (used by bench.py; off by default, no effect on results).
  * ptk_profile_start(): from now on every kernel-class launch is bracketed by cudaEvents on its stream.
  * ptk_profile_stop(ms, count): synchronises those events; fills ms[k] / count[k] for the 8 classes

@@ -16,7 +16,7 @@ PTK_INT_NPARAM = 30
 
 EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_saved_bytes",
            "ptk_int_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker",
-           "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count")
+           "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes")
 
 
 class PtkDims(ctypes.Structure):
@@ -60,6 +60,10 @@ def lib():
     L.ptk_int_backward.argtypes = [dp, vp, i64p, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_synth_pathtracker.restype = ctypes.c_int
     L.ptk_synth_pathtracker.argtypes = [u64, u64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.ptk_conv7_workspace_bytes.restype = sz
+    L.ptk_conv7_workspace_bytes.argtypes = [i32, i32, i32]
+    L.ptk_conv7.restype = ctypes.c_int
+    L.ptk_conv7.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_profile_start.restype = None
     L.ptk_profile_start.argtypes = []
     L.ptk_profile_stop.restype = ctypes.c_int

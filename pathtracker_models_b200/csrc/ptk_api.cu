@@ -31,7 +31,7 @@ static int check_dims(const PtkDims* d, const char* who) {
   if (d->cell != PTK_CELL_INT && d->cell != PTK_CELL_HGRU) { set_error("%s: bad cell %d", who, d->cell); return PTK_EINVAL; }
   if (d->act != PTK_ACT_SOFTPLUS && d->act != PTK_ACT_TANH) { set_error("%s: bad act %d", who, d->act); return PTK_EINVAL; }
   if (d->no_inh) { set_error("%s: no_inh=True variant is not built yet", who); return PTK_EUNSUPPORTED; }
-  if (d->conv_mode != PTK_CONV_FP32) { set_error("%s: conv_mode %d is not built yet", who, d->conv_mode); return PTK_EUNSUPPORTED; }
+  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3) { set_error("%s: bad conv_mode %d", who, d->conv_mode); return PTK_EINVAL; }
   return PTK_OK;
 }
 
@@ -126,8 +126,17 @@ static int prep(IntDev* d, const float* params, cudaStream_t st) {
   const ParamOffsets po = param_offsets(C, KS);
   IntGateSrc g;
   for (int i = 0; i < 6; ++i) g.w[i] = d->gate[i];
-  return run_prep_weights(params + po.o[PTK_P_W_INH], params + po.o[PTK_P_W_EXC], (float*)d->w_inh_f,
-                          (float*)d->w_inh_d, (float*)d->w_exc_f, (float*)d->w_exc_d, g, (float*)d->gateT[0], st);
+  const float* w_inh = params + po.o[PTK_P_W_INH];
+  const float* w_exc = params + po.o[PTK_P_W_EXC];
+  if (d->conv_mode == PTK_CONV_BF16X3) {
+    // the four 200,704-byte banks hold the bf16 hi/lo tap streams instead of fp32 re-layouts
+    int rc = launch_prep_weights_tc(w_inh, (void*)d->w_inh_f, (void*)d->w_inh_d, st);
+    if (rc) return rc;
+    if ((rc = launch_prep_weights_tc(w_exc, (void*)d->w_exc_f, (void*)d->w_exc_d, st))) return rc;
+    return run_prep_weights(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, g, (float*)d->gateT[0], st);
+  }
+  return run_prep_weights(w_inh, w_exc, (float*)d->w_inh_f, (float*)d->w_inh_d, (float*)d->w_exc_f,
+                          (float*)d->w_exc_d, g, (float*)d->gateT[0], st);
 }
 
 }  // namespace ptk
@@ -171,7 +180,7 @@ int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5
   cudaStream_t st = (cudaStream_t)stream;
   IntDev d;
   memset(&d, 0, sizeof(d));
-  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W;
+  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W; d.conv_mode = dm->conv_mode;
   d.fv = FrameView{x, x_strides[0], x_strides[1], x_strides[2], x_strides[3], x_strides[4]};
   bind_params(&d, params);
   d.ck_ring = (saved == nullptr);
@@ -206,7 +215,7 @@ int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[
   cudaStream_t st = (cudaStream_t)stream;
   IntDev d;
   memset(&d, 0, sizeof(d));
-  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W;
+  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W; d.conv_mode = dm->conv_mode;
   d.fv = FrameView{x, x_strides[0], x_strides[1], x_strides[2], x_strides[3], x_strides[4]};
   bind_params(&d, params);
   bind_saved(&d, dm, const_cast<void*>(saved));
@@ -215,6 +224,43 @@ int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[
   PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
   if ((rc = prep(&d, params, st))) return rc;   // the workspace may have been reused since forward
   return run_int_backward(d, dm->cell, dm->act, st);
+}
+
+
+int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transpose, int32_t accumulate,
+              const float* in, const float* weight, float* out, float* stats, void* workspace,
+              size_t workspace_bytes, void* stream) {
+  PtkDims dm = {B, 1, H, W, C, KS, 0, 0, 0, conv_mode};
+  int rc = check_dims(&dm, "ptk_conv7");
+  if (rc) return rc;
+  if (!in || !weight || !out || !workspace) { set_error("ptk_conv7: NULL argument"); return PTK_EINVAL; }
+  const size_t need = ptk_conv7_workspace_bytes(B, H, W);
+  if (workspace_bytes < need) { set_error("ptk_conv7: workspace too small (%zu < %zu)", workspace_bytes, need); return PTK_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  float* wf = cv.take<float>((size_t)C * C * TAPS);
+  float* wd = cv.take<float>((size_t)C * C * TAPS);
+  float* part = cv.take<float>((size_t)conv_num_ctas(B, H, W) * C * 2);
+  unsigned* counter = cv.take<unsigned>(4);
+  PTK_CUDA_OK(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned), st));
+  if (conv_mode == PTK_CONV_BF16X3) rc = launch_prep_weights_tc(weight, wf, wd, st);
+  else {
+    IntGateSrc g = {};
+    rc = run_prep_weights(weight, nullptr, wf, wd, nullptr, nullptr, g, nullptr, st);
+  }
+  if (rc) return rc;
+  ConvArgs a{in, transpose ? wd : wf, out, B, H, W, accumulate, stats ? part : nullptr, counter, stats, conv_mode};
+  return launch_conv7(a, st);
+}
+
+size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+  if (B < 1 || H < 16 || W < 32 || H % 16 || W % 32) return 0;
+  Carver cv(nullptr);
+  cv.take<float>((size_t)C * C * TAPS);
+  cv.take<float>((size_t)C * C * TAPS);
+  cv.take<float>((size_t)conv_num_ctas(B, H, W) * C * 2);
+  cv.take<unsigned>(4);
+  return (cv.off + 255) & ~(size_t)255;
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 // 8-pixel x 8-channel register tile (64 accumulators); weights and the zero-padded input tile
 // are staged in shared memory by cp.async in chunks of 8 input channels.
 #include "ptk_common.cuh"
+#include "ptk_conv_stats.cuh"
 #include "ptk_kernels.h"
 
 namespace ptk {
@@ -159,35 +160,7 @@ __global__ void __launch_bounds__(256, 1) conv7_ffma_kernel(ConvArgs a) {
         dst[1] = sRed[warp][o] + sRed[warp + 4][o];
       }
     }
-    // last CTA to arrive folds all partials (Chan et al. parallel variance, in double)
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sIsLast = (atomicAdd(a.counter, 1u) == (unsigned)(nCta - 1));
-    __syncthreads();
-    if (sIsLast) {
-      __threadfence();
-      const int c = tid & 31, g = tid >> 5;
-      double s1 = 0, s2 = 0, s3 = 0;
-      for (int i = g; i < nCta; i += 8) {
-        const float2 pm = __ldcg(reinterpret_cast<const float2*>(a.part + ((size_t)i * C + c) * 2));
-        s1 += pm.x;
-        s2 += (double)pm.x * pm.x;
-        s3 += pm.y;
-      }
-      sFin[g][c][0] = s1; sFin[g][c][1] = s2; sFin[g][c][2] = s3;
-      __syncthreads();
-      if (tid < C) {
-        s1 = s2 = s3 = 0;
-        for (int gg = 0; gg < 8; ++gg) { s1 += sFin[gg][tid][0]; s2 += sFin[gg][tid][1]; s3 += sFin[gg][tid][2]; }
-        const double n = nCta, m = s1 / n;
-        double m2 = s3 + (double)(TH * TW) * (s2 - n * m * m);
-        if (m2 < 0) m2 = 0;
-        const double var = m2 / (n * TH * TW);
-        a.stats_out[tid] = (float)m;
-        a.stats_out[C + tid] = (float)(1.0 / sqrt(var + (double)BN_EPS));
-      }
-      if (tid == 0) *a.counter = 0u;
-    }
+    conv_stats_fold(a, nCta, TH * TW, sFin, &sIsLast);
   }
 
   // ---- store ----------------------------------------------------------------------------------
@@ -288,6 +261,7 @@ static constexpr size_t WGRAD_SMEM = (size_t)(C * TH * TW + ICC * WG_IN_PITCH) *
 int conv_num_ctas(int B, int H, int W) { return B * (H / TH) * (W / TW); }
 
 int launch_conv7(const ConvArgs& a, cudaStream_t st) {
+  if (a.mode == PTK_CONV_BF16X3) return launch_conv7_tc(a, st);
   static thread_local int configured_dev = -1;
   int dev;
   PTK_CUDA_OK(cudaGetDevice(&dev));

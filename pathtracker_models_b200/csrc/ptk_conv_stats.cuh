@@ -1,0 +1,44 @@
+// Last-CTA fold of the per-CTA BatchNorm partial statistics written by the convolution kernels.
+#pragma once
+#include "ptk_common.cuh"
+#include "ptk_kernels.h"
+
+namespace ptk {
+
+// Every CTA has written part[cta][c] = (mean, M2) over its `npix` conv outputs of channel c.
+// The last CTA to arrive folds all partials (Chan et al. parallel variance, in double) into
+// stats_out = mean[32], rstd[32] (biased variance, eps 1e-3: models/InT.py:102).  256 threads.
+__device__ __forceinline__ void conv_stats_fold(const ConvArgs& a, int nCta, int npix, double (*sFin)[C][3],
+                                                int* sIsLast) {
+  const int tid = threadIdx.x;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *sIsLast = (atomicAdd(a.counter, 1u) == (unsigned)(nCta - 1));
+  __syncthreads();
+  if (*sIsLast) {
+    __threadfence();
+    const int c = tid & 31, g = tid >> 5;
+    double s1 = 0, s2 = 0, s3 = 0;
+    for (int i = g; i < nCta; i += 8) {
+      const float2 pm = __ldcg(reinterpret_cast<const float2*>(a.part + ((size_t)i * C + c) * 2));
+      s1 += pm.x;
+      s2 += (double)pm.x * pm.x;
+      s3 += pm.y;
+    }
+    sFin[g][c][0] = s1; sFin[g][c][1] = s2; sFin[g][c][2] = s3;
+    __syncthreads();
+    if (tid < C) {
+      s1 = s2 = s3 = 0;
+      for (int gg = 0; gg < 8; ++gg) { s1 += sFin[gg][tid][0]; s2 += sFin[gg][tid][1]; s3 += sFin[gg][tid][2]; }
+      const double n = nCta, m = s1 / n;
+      double m2 = s3 + (double)npix * (s2 - n * m * m);
+      if (m2 < 0) m2 = 0;
+      const double var = m2 / (n * npix);
+      a.stats_out[tid] = (float)m;
+      a.stats_out[C + tid] = (float)(1.0 / sqrt(var + (double)BN_EPS));
+    }
+    if (tid == 0) *a.counter = 0u;
+  }
+}
+
+}  // namespace ptk

@@ -1,0 +1,336 @@
+// Tensor-core horizontal-connection convolution: implicit GEMM on tcgen05 / TMEM (sm_100a).
+//
+//   Y[b, :, y, x] = sum_{tap, ic} In[b, ic, y+ky-3, x+kx-3] * W[:, ic, tap]      (models/InT.py:161,172)
+//
+// fp32 parity through a 3-pass bf16 split: In = Ih + Il, W = Wh + Wl (bf16 each),
+//   Y ~= Ih*Wh + Ih*Wl + Il*Wh, accumulated in fp32 in TMEM.
+// Per CTA: 16 rows x 32 columns of one sample (same tiling / arguments as conv7_ffma_kernel).
+//   * the zero-padded input tile lives in shared memory as bf16 hi / lo in "channel-chunk planar"
+//     form [chunk = ic/8][pixel][8 ic] (pixel pitch 16 B, row pitch 38 pixels), which is exactly the
+//     K-major no-swizzle UMMA canonical layout with SBO = 128 B, LBO = plane size -- so every tap
+//     of the 7x7 window is the SAME shared-memory image addressed at a different start pixel
+//     (ky*38 + kx): no im2col copies.
+//   * GEMM shape per MMA: M = 128 consecutive padded pixels (5 M-tiles cover the 16x38 padded tile),
+//     K = 16 input channels, N = 64 = [Wh | Wl] for the Ih operand (one instruction yields both
+//     Ih*Wh and Ih*Wl) and N = 32 (Wh only) for the Il operand.  The two N-halves are summed in the epilogue.
+//   * weights stream per tap (4 KB: hi+lo) through a cp.async.bulk + mbarrier ring; one elected
+//     thread issues tcgen05.mma; tcgen05.commit releases ring slots and signals the epilogue.
+//   * epilogue: tcgen05.ld -> registers -> BatchNorm batch statistics partials -> global (NCHW fp32).
+#include <cuda_bf16.h>
+
+#include "ptk_common.cuh"
+#include "ptk_conv_stats.cuh"
+#include "ptk_kernels.h"
+
+namespace ptk {
+
+constexpr int TC_TH = 16, TC_TW = 32;
+constexpr int TC_WP = TC_TW + 6;                       // 38: padded row pitch (pixels)
+constexpr int TC_ROWS = TC_TH + 6;                     // 22 input rows
+constexpr int TC_MT = 5;                               // M-tiles: 5*128 = 640 >= 16*38 = 608
+constexpr int TC_NPIX = 880;                           // >= 640 + 6*38 + 6 = 874 pixels incl. slack
+constexpr int TC_PLANE = TC_NPIX * 16;                 // bytes per channel-chunk plane
+constexpr int TC_A_BYTES = 2 * 4 * TC_PLANE;           // hi + lo, 4 chunks
+constexpr int TC_WTAP = 4 * 64 * 16;                   // bytes of one tap's weights: 4 chunks x 64 rows x 8 bf16
+constexpr int TC_NST = 6;                              // weight ring stages
+constexpr int TC_SMEM = TC_A_BYTES + TC_NST * TC_WTAP + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// accumulator row of one pixel: 32 channels = cols [0,32) + cols [32,64) of M-tile j
+__device__ __forceinline__ void tc_load_pixel(uint32_t tmem_base, int quad, int j, float (&v)[32]) {
+  float lo[32];
+  const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 64);
+  tmem_ld32(ta, v);
+  tmem_ld32(ta + 32, lo);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += lo[i];
+}
+// sum over the warp of 32 per-lane values per channel; lane l returns the total of channel l
+__device__ __forceinline__ float warp_transpose_sum(float (&s)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = up ? s[i + half] : s[i];
+      const float send = up ? s[i] : s[i + half];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return s[0];
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sA = smem_raw;                                   // [hi|lo][4 chunks][880 px][16 B]
+  uint8_t* sWr = smem_raw + TC_A_BYTES;                     // weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_A_BYTES + TC_NST * TC_WTAP);
+  uint64_t* full = bars;                                    // [TC_NST]
+  uint64_t* empty = bars + TC_NST;                          // [TC_NST]
+  uint64_t* accum_bar = bars + 2 * TC_NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NST + 1);
+  __shared__ float sRed[8][C];
+  __shared__ float sMean[C];
+  __shared__ double sFin[8][C][3];
+  __shared__ int sIsLast;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * TC_TW, y0 = blockIdx.y * TC_TH, b = blockIdx.z;
+  const int H = a.H, W = a.W;
+
+  // ---- one-time setup: barriers, TMEM, zero the operand image ------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < TC_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < TC_A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  // ---- stage the input tile: fp32 NCHW -> bf16 hi/lo, channel-chunk planar -------------------------
+  for (int it = tid; it < 4 * TC_ROWS * TC_WP; it += 256) {
+    const int q = it / (TC_ROWS * TC_WP), rem = it - q * (TC_ROWS * TC_WP), r = rem / TC_WP, c = rem - r * TC_WP;
+    const int gy = y0 + r - 3, gx = x0 + c - 3;
+    if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
+    const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + gx;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      hi[e] = pack_bf16x2(h0, h1);
+      lo[e] = pack_bf16x2(l0, l1);
+    }
+    const int p = r * TC_WP + c;
+    *reinterpret_cast<uint4*>(sA + q * TC_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- main loop: weight producer (warp 0) / MMA issuer (warp 1) ----------------------------------
+  if (warp == 0 && lane == 0) {
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wT);
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const int st = tap % TC_NST, round = tap / TC_NST;
+      if (round > 0) mbar_wait(&empty[st], (uint32_t)((round - 1) & 1));
+      mbar_expect_tx(&full[st], TC_WTAP);
+      bulk_g2s(sWr + st * TC_WTAP, wsrc + (size_t)tap * TC_WTAP, TC_WTAP, &full[st]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // descriptors differ only in the 14-bit start-address field of the low word: precompute the
+    // per-(operand, k-step) bases and add the pixel offset per instruction (1 IADD per MMA).
+    const uint32_t aHi = smem_u32(sA), aLo = aHi + 4 * TC_PLANE, wBase = smem_u32(sWr);
+    const uint64_t dA0 = umma_desc(0, TC_PLANE, 128), dB0 = umma_desc(0, 1024, 128);
+    const uint32_t aHiW = (uint32_t)(dA0 >> 32), bHiW = (uint32_t)(dB0 >> 32);
+    const uint32_t aLoW = (uint32_t)dA0, bLoW = (uint32_t)dB0;
+    uint32_t aH[2], aL[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      aH[s] = aLoW + ((aHi + (uint32_t)(2 * s) * TC_PLANE) >> 4);
+      aL[s] = aLoW + ((aLo + (uint32_t)(2 * s) * TC_PLANE) >> 4);
+    }
+    constexpr uint32_t ID64 = umma_idesc(64), ID32 = umma_idesc(32);
+    for (int tap = 0; tap < TAPS; ++tap) {
+      const int st = tap % TC_NST, round = tap / TC_NST;
+      mbar_wait(&full[st], (uint32_t)(round & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int ky = tap / KS, kx = tap - ky * KS;
+      const uint32_t poff = (uint32_t)(ky * TC_WP + kx);          // in 16-byte units == pixels
+      const uint32_t bW = bLoW + ((wBase + (uint32_t)st * TC_WTAP) >> 4);
+#pragma unroll
+      for (int j = 0; j < TC_MT; ++j) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const uint32_t po = poff + (uint32_t)(j * 128);
+          const uint64_t dB = ((uint64_t)bHiW << 32) | (bW + (uint32_t)(2 * s) * (1024 >> 4));
+          const uint32_t dcol = tmem_base + (uint32_t)(j * 64);
+          umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (tap | s) ? 1u : 0u);
+          umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+        }
+      }
+      umma_commit(&empty[st]);   // frees this ring slot once the MMAs above have read it
+    }
+    umma_commit(accum_bar);
+  }
+  __syncwarp();
+
+  // ---- epilogue -----------------------------------------------------------------------------------
+  mbar_wait(accum_bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int quad = warp & 3, jpar = warp >> 2;   // warps 0-3: tiles 0,2,4; warps 4-7: tiles 1,3
+  const int nCta = gridDim.x * gridDim.y * gridDim.z;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const bool stats = (a.part != nullptr);
+  if (stats) {
+    float s[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] = 0.f;
+    for (int j = jpar; j < TC_MT; j += 2) {
+      const int m = j * 128 + quad * 32 + lane, ro = m / TC_WP, xo = m - ro * TC_WP;
+      float v[32];
+      tc_load_pixel(tmem_base, quad, j, v);
+      if (ro < TC_TH && xo < TC_TW) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] += v[i];
+      }
+    }
+    const float tot = warp_transpose_sum(s, lane);
+    sRed[warp][lane] = tot;
+    __syncthreads();
+    if (tid < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sRed[w][tid];
+      sMean[tid] = t * (1.0f / (TC_TH * TC_TW));
+    }
+    __syncthreads();
+  }
+  {
+    float s[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s[i] = 0.f;
+    for (int j = jpar; j < TC_MT; j += 2) {
+      const int m = j * 128 + quad * 32 + lane, ro = m / TC_WP, xo = m - ro * TC_WP;
+      float v[32];
+      tc_load_pixel(tmem_base, quad, j, v);
+      if (ro < TC_TH && xo < TC_TW) {
+        float* dst = a.out + ((size_t)(b * C) * H + y0 + ro) * W + x0 + xo;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (stats) {
+            const float dl = v[i] - sMean[i];
+            s[i] = fmaf(dl, dl, s[i]);
+          }
+          float* p = dst + (size_t)i * H * W;
+          *p = a.accumulate ? (*p + v[i]) : v[i];
+        }
+      }
+    }
+    if (stats) {
+      const float tot = warp_transpose_sum(s, lane);
+      __syncthreads();
+      sRed[warp][lane] = tot;
+      __syncthreads();
+      if (tid < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sRed[w][tid];
+        float* dstp = a.part + ((size_t)cta * C + tid) * 2;
+        dstp[0] = sMean[tid];
+        dstp[1] = t;
+      }
+      conv_stats_fold(a, nCta, TC_TH * TC_TW, sFin, &sIsLast);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+// weights fp32 [oc][ic][49] -> bf16 hi/lo per tap: [tap][chunk = k/8][row n: 0-31 hi, 32-63 lo][k%8]
+//   forward: n = oc, k = ic, tap as is;  dgrad (conv_transpose): n = ic, k = oc, tap -> 48 - tap.
+__global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat16* wf, __nv_bfloat16* wd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * C * TAPS) return;
+  const int oc = i / (C * TAPS), ic = (i / TAPS) % C, tap = i % TAPS;
+  const float v = w[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  if (wf) {
+    const size_t base = (size_t)tap * (TC_WTAP / 2) + (size_t)(ic >> 3) * 512 + (ic & 7);
+    wf[base + (size_t)oc * 8] = h;
+    wf[base + (size_t)(32 + oc) * 8] = l;
+  }
+  if (wd) {
+    const size_t base = (size_t)(TAPS - 1 - tap) * (TC_WTAP / 2) + (size_t)(oc >> 3) * 512 + (oc & 7);
+    wd[base + (size_t)ic * 8] = h;
+    wd[base + (size_t)(32 + ic) * 8] = l;
+  }
+}
+
+int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
+  PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+  dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
+  conv7_tc_kernel<<<grid, 256, TC_SMEM, st>>>(a);
+  PTK_LAUNCH_OK("conv7_tc_kernel");
+  return PTK_OK;
+}
+
+int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st) {
+  const int n = C * C * TAPS;
+  prep_weights_tc_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
+  PTK_LAUNCH_OK("prep_weights_tc_kernel");
+  return PTK_OK;
+}
+
+}  // namespace ptk

@@ -23,6 +23,7 @@ constexpr int PW_MAX_CTAS = 148 * 3;
 
 struct IntDev {
   int B, T, H, W;
+  int conv_mode;           // PTK_CONV_*
   FrameView fv;
   // parameters (views into the flat vector) and re-laid-out copies (workspace)
   const float *Wp, *bp, *alpha, *mu, *gamma, *kappa;

@@ -694,7 +694,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1_at(t), t, 1);
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c1{d.dAct, d.w_exc_d, d.gI, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr};
+    ConvArgs c1{d.dAct, d.w_exc_d, d.gI, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr, d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
@@ -710,7 +710,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0_at(t), t, 0);
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c0{d.dAct, d.w_inh_d, d.dGe, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr};
+    ConvArgs c0{d.dAct, d.w_inh_d, d.dGe, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr, d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
     if (rc) return rc;
     WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};

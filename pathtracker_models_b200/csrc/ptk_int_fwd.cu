@@ -354,7 +354,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   PTK_LAUNCH_OK("int_pre_kernel");
   for (int t = 0; t < d.T; ++t) {
     int rc;
-    ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0)};
+    ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
     if (rc) return rc;
     {
@@ -363,7 +363,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
       else int_mid_kernel<PTK_CELL_HGRU, ACT><<<grid, 128, SM_MID, st>>>(d, t);
     }
     PTK_LAUNCH_OK("int_mid_kernel");
-    ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1)};
+    ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1), d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     {
@@ -390,9 +390,9 @@ int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st) {
   const int n = C * C * TAPS;
   ProfileScope ps(PTK_PROF_MISC, st, 3);
-  prep_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_inh, inh_f, inh_d);
-  prep_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_exc, exc_f, exc_d);
-  prep_gates_kernel<<<(6 * C * C + 255) / 256, 256, 0, st>>>(g, gateT);
+  if (w_inh) prep_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_inh, inh_f, inh_d);
+  if (w_exc) prep_weights_kernel<<<(n + 255) / 256, 256, 0, st>>>(w_exc, exc_f, exc_d);
+  if (gateT) prep_gates_kernel<<<(6 * C * C + 255) / 256, 256, 0, st>>>(g, gateT);
   PTK_LAUNCH_OK("prep_weights");
   return PTK_OK;
 }

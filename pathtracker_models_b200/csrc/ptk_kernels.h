@@ -14,6 +14,7 @@ struct ConvArgs {
   float* part;         // [nCTA][32][2] per-CTA (mean, M2) or nullptr (no statistics)
   unsigned* counter;   // arrival counter for the last-CTA fold (self-resetting)
   float* stats_out;    // [2][32] mean, rstd
+  int mode;            // PTK_CONV_FP32: wT is fp32 [ic][tap][oc]; PTK_CONV_BF16X3: wT is the bf16 hi/lo tap stream
 };
 
 struct WgradArgs {
@@ -27,5 +28,7 @@ struct WgradArgs {
 int conv_num_ctas(int B, int H, int W);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
+int launch_conv7_tc(const ConvArgs& a, cudaStream_t st);
+int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st);
 
 }  // namespace ptk

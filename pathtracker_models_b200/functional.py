@@ -119,3 +119,22 @@ def synth_pathtracker(B, T, H=32, W=32, n_distractors=14, speed=1, seed=1234, fi
         rc = L.ptk_synth_pathtracker(seed, first_index, B, T, H, W, n_distractors, speed, _ptr(x), _ptr(y), stream)
         _lib.check(rc, "ptk_synth_pathtracker")
     return x, y.view(B, 1)
+
+
+def conv7(x, weight, conv_mode=_lib.PTK_CONV_FP32, transpose=False, out=None, want_stats=False):
+    """one 7x7 horizontal-connection convolution through ptk_conv7 (test / measurement entry)."""
+    L = _lib.lib()
+    B, Cc, H, W = x.shape
+    x, weight = x.contiguous(), weight.contiguous()
+    with torch.cuda.device(x.device):
+        accumulate = out is not None
+        if out is None:
+            out = torch.empty_like(x)
+        stats = torch.empty(2, Cc, dtype=torch.float32, device=x.device) if want_stats else None
+        nbytes = L.ptk_conv7_workspace_bytes(B, H, W)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        rc = L.ptk_conv7(B, H, W, conv_mode, int(transpose), int(accumulate), _ptr(x), _ptr(weight), _ptr(out),
+                         _ptr(stats), _ptr(ws), nbytes, stream)
+        _lib.check(rc, "ptk_conv7")
+    return (out, stats) if want_stats else out

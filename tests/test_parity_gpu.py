@@ -169,3 +169,43 @@ def test_errors_are_loud():
     L = _lib.lib()
     rc = L.ptk_int_forward(ctypes.byref(d), None, None, None, None, None, None, None, None, 0, None)
     assert rc == 1 and b"NULL" in L.ptk_last_error()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(3, 32, 32), (2, 64, 64)])
+def test_conv7_operator_vs_torch(mode, shape):
+    """ptk_conv7 (fp32 FFMA path and 3-pass split-bf16 tcgen05 path) against torch conv2d in fp64:
+    forward, conv_transpose (data gradient), accumulate, and the BatchNorm batch statistics."""
+    import torch.nn.functional as F
+    from pathtracker_models_b200.functional import conv7
+    B, H, W = shape
+    g = torch.Generator().manual_seed(5 + mode)
+    x = torch.randn(B, 32, H, W, generator=g) * torch.rand(B, 32, 1, 1, generator=g) * 3
+    w = torch.randn(32, 32, 7, 7, generator=g) * 0.05
+    xd, wd = x.double(), w.double()
+    tol = 2e-6 if mode == 0 else 3e-5
+    y, st = conv7(x.cuda(), w.cuda(), conv_mode=mode, want_stats=True)
+    ref = F.conv2d(xd, wd, padding=3)
+    assert rel_err(y, ref) < tol
+    mean = ref.mean(dim=(0, 2, 3))
+    rstd = 1 / torch.sqrt(ref.var(dim=(0, 2, 3), unbiased=False) + 1e-3)
+    assert rel_err(st[0], mean) < 1e-4 and rel_err(st[1], rstd) < 1e-5
+    yt = conv7(x.cuda(), w.cuda(), conv_mode=mode, transpose=True)
+    assert rel_err(yt, F.conv_transpose2d(xd, wd, padding=3)) < tol
+    acc = torch.randn(B, 32, H, W, generator=g)
+    ya = conv7(x.cuda(), w.cuda(), conv_mode=mode, out=acc.clone().cuda())
+    assert rel_err(ya, ref + acc.double()) < tol
+    y2 = conv7(x.cuda(), w.cuda(), conv_mode=mode)
+    assert torch.equal(y, y2)                       # deterministic
+
+
+@pytest.mark.parametrize("name,kind,kw", CASES)
+def test_bf16x3_tensor_core_mode_parity(name, kind, kw):
+    """conv_mode = PTK_CONV_BF16X3 (tcgen05 convolutions, FFMA weight gradient): same parity gate."""
+    from pathtracker_models_b200 import _lib
+    case = load_case(name)
+    m = _model(case, kind, **kw)
+    m.conv_mode = _lib.PTK_CONV_BF16X3
+    out, loss, grads, _ = _run(case, m)
+    bad = check_parity(case, out, grads)
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
