@@ -1,0 +1,25 @@
+"""micro-benchmark of the 7x7 convolution operator (ptk_conv7) in both modes; CUDA-event timing."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pathtracker_models_b200.functional import conv7
+
+B, H, W = int(os.environ.get("B", 64)), 32, 32
+iters = int(os.environ.get("ITERS", 20))
+x = torch.randn(B, 32, H, W, device="cuda")
+w = torch.randn(32, 32, 7, 7, device="cuda") * 0.05
+flop = 2 * B * H * W * 32 * 32 * 49
+for mode, name in ((0, "fp32-ffma"), (1, "bf16x3-tcgen05")):
+    for acc in (False, True):
+        out = torch.zeros_like(x) if acc else None
+        for _ in range(3):
+            conv7(x, w, conv_mode=mode, out=out, want_stats=not acc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            conv7(x, w, conv_mode=mode, out=out, want_stats=not acc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"{name:16s} accumulate={acc!s:5s} {ms*1e3:8.1f} us/call (incl. weight prep launch)  {flop/ms/1e9:8.1f} TFLOP/s")
