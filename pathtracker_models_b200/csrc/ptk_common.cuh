@@ -36,18 +36,23 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ---- math ----------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// The transcendental maps are deliberately NOT inlined: expf/log1pf expand to ~100 instructions and the
+// point-wise kernels evaluate several of them per element; inlining made each kernel > 60 KB of SASS
+// (instruction-cache misses showed up as the top stall reason, profiles/r1b_pointwise_wgrad_full.txt).
+static __device__ __noinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+static __device__ __noinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+static __device__ __noinline__ float tanhf_(float x) { return tanhf(x); }
 
 // activation `nl` of InT.__init__ (models/InT.py:184,208): softplus(beta=1, threshold=20) or tanh
 template <int ACT>
 __device__ __forceinline__ float actf(float x) {
-  if (ACT == PTK_ACT_SOFTPLUS) return x > 20.0f ? x : log1pf(expf(x));
-  return tanhf(x);
+  if (ACT == PTK_ACT_SOFTPLUS) return softplusf_(x);
+  return tanhf_(x);
 }
 template <int ACT>
 __device__ __forceinline__ float dactf(float x) {
   if (ACT == PTK_ACT_SOFTPLUS) return x > 20.0f ? 1.0f : sigmoidf_(x);
-  float t = tanhf(x);
+  const float t = tanhf_(x);
   return 1.0f - t * t;
 }
 

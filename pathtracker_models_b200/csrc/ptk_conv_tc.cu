@@ -32,8 +32,9 @@ constexpr int TC_NPIX = 880;                           // >= 640 + 6*38 + 6 = 87
 constexpr int TC_PLANE = TC_NPIX * 16;                 // bytes per channel-chunk plane
 constexpr int TC_A_BYTES = 2 * 4 * TC_PLANE;           // hi + lo, 4 chunks
 constexpr int TC_WTAP = 4 * 64 * 16;                   // bytes of one tap's weights: 4 chunks x 64 rows x 8 bf16
-constexpr int TC_NST = 6;                              // weight ring stages
-constexpr int TC_SMEM = TC_A_BYTES + TC_NST * TC_WTAP + 256;
+constexpr int TC_STAGE = KS * TC_WTAP;                 // one ring stage = one kernel row (7 taps, 28 KB)
+constexpr int TC_NST = 3;                              // weight ring stages
+constexpr int TC_SMEM = TC_A_BYTES + TC_NST * TC_STAGE + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -120,11 +121,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+__device__ long long g_tc_dbg[8];
+#define TC_STAMP(i) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 64) g_tc_dbg[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sA = smem_raw;                                   // [hi|lo][4 chunks][880 px][16 B]
   uint8_t* sWr = smem_raw + TC_A_BYTES;                     // weight ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_A_BYTES + TC_NST * TC_WTAP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + TC_A_BYTES + TC_NST * TC_STAGE);
   uint64_t* full = bars;                                    // [TC_NST]
   uint64_t* empty = bars + TC_NST;                          // [TC_NST]
   uint64_t* accum_bar = bars + 2 * TC_NST;
@@ -138,6 +142,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   const int x0 = blockIdx.x * TC_TW, y0 = blockIdx.y * TC_TH, b = blockIdx.z;
   const int H = a.H, W = a.W;
 
+  TC_STAMP(0);
   // ---- one-time setup: barriers, TMEM, zero the operand image ------------------------------------
   if (tid == 0) {
     for (int i = 0; i < TC_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -150,41 +155,77 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   }
   for (int i = tid; i < TC_A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  TC_STAMP(1);
+  // weights do not depend on the input tile: start streaming the first kernel rows right away
+  if (tid == 0) {
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wT);
+    for (int ky = 0; ky < TC_NST; ++ky) {
+      mbar_expect_tx(&full[ky], TC_STAGE);
+      bulk_g2s(sWr + ky * TC_STAGE, wsrc + (size_t)ky * TC_STAGE, TC_STAGE, &full[ky]);
+    }
+  }
 
   // ---- stage the input tile: fp32 NCHW -> bf16 hi/lo, channel-chunk planar -------------------------
-  for (int it = tid; it < 4 * TC_ROWS * TC_WP; it += 256) {
-    const int q = it / (TC_ROWS * TC_WP), rem = it - q * (TC_ROWS * TC_WP), r = rem / TC_WP, c = rem - r * TC_WP;
-    const int gy = y0 + r - 3, gx = x0 + c - 3;
-    if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
-    const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + gx;
-    uint32_t hi[4], lo[4];
+  // interior columns: one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels
+  for (int it = tid; it < 4 * TC_ROWS * (TC_TW / 4); it += 256) {
+    const int q = it / (TC_ROWS * (TC_TW / 4)), rem = it - q * (TC_ROWS * (TC_TW / 4)), r = rem / (TC_TW / 4), g = rem % (TC_TW / 4);
+    const int gy = y0 + r - 3;
+    if (gy < 0 || gy >= H) continue;
+    const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
+    float4 v[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-      hi[e] = pack_bf16x2(h0, h1);
-      lo[e] = pack_bf16x2(l0, l1);
+    for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
+    const int p = r * TC_WP + 3 + 4 * g;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v0 = reinterpret_cast<const float*>(&v[2 * e])[px], v1 = reinterpret_cast<const float*>(&v[2 * e + 1])[px];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        hi[e] = pack_bf16x2(h0, h1);
+        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+      }
+      *reinterpret_cast<uint4*>(sA + q * TC_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    const int p = r * TC_WP + c;
-    *reinterpret_cast<uint4*>(sA + q * TC_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  // halo columns (only inside the image when W > 32)
+  if (W > TC_TW) {
+    for (int it = tid; it < 4 * TC_ROWS * 6; it += 256) {
+      const int q = it / (TC_ROWS * 6), rem = it - q * (TC_ROWS * 6), r = rem / 6, hc = rem % 6;
+      const int c = hc < 3 ? hc : (TC_TW + hc);          // padded columns 0..2 and 35..37
+      const int gy = y0 + r - 3, gx = x0 + c - 3;
+      if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
+      const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + gx;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        hi[e] = pack_bf16x2(h0, h1);
+        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+      }
+      const int p = r * TC_WP + c;
+      *reinterpret_cast<uint4*>(sA + q * TC_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  TC_STAMP(2);
 
   // ---- main loop: weight producer (warp 0) / MMA issuer (warp 1) ----------------------------------
   if (warp == 0 && lane == 0) {
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wT);
-    for (int tap = 0; tap < TAPS; ++tap) {
-      const int st = tap % TC_NST, round = tap / TC_NST;
-      if (round > 0) mbar_wait(&empty[st], (uint32_t)((round - 1) & 1));
-      mbar_expect_tx(&full[st], TC_WTAP);
-      bulk_g2s(sWr + st * TC_WTAP, wsrc + (size_t)tap * TC_WTAP, TC_WTAP, &full[st]);
+    for (int ky = TC_NST; ky < KS; ++ky) {   // refill a slot as soon as the MMAs that read it have retired
+      const int st = ky % TC_NST, round = ky / TC_NST;
+      mbar_wait(&empty[st], (uint32_t)((round - 1) & 1));
+      mbar_expect_tx(&full[st], TC_STAGE);
+      bulk_g2s(sWr + st * TC_STAGE, wsrc + (size_t)ky * TC_STAGE, TC_STAGE, &full[st]);
     }
   } else if (warp == 1 && lane == 0) {
     // descriptors differ only in the 14-bit start-address field of the low word: precompute the
@@ -200,22 +241,24 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
       aL[s] = aLoW + ((aLo + (uint32_t)(2 * s) * TC_PLANE) >> 4);
     }
     constexpr uint32_t ID64 = umma_idesc(64), ID32 = umma_idesc(32);
-    for (int tap = 0; tap < TAPS; ++tap) {
-      const int st = tap % TC_NST, round = tap / TC_NST;
+    for (int ky = 0; ky < KS; ++ky) {
+      const int st = ky % TC_NST, round = ky / TC_NST;
       mbar_wait(&full[st], (uint32_t)(round & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int ky = tap / KS, kx = tap - ky * KS;
-      const uint32_t poff = (uint32_t)(ky * TC_WP + kx);          // in 16-byte units == pixels
-      const uint32_t bW = bLoW + ((wBase + (uint32_t)st * TC_WTAP) >> 4);
+#pragma unroll 1
+      for (int kx = 0; kx < KS; ++kx) {
+        const uint32_t poff = (uint32_t)(ky * TC_WP + kx);          // in 16-byte units == pixels
+        const uint32_t bW = bLoW + ((wBase + (uint32_t)st * TC_STAGE + (uint32_t)kx * TC_WTAP) >> 4);
 #pragma unroll
-      for (int j = 0; j < TC_MT; ++j) {
+        for (int j = 0; j < TC_MT; ++j) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const uint32_t po = poff + (uint32_t)(j * 128);
-          const uint64_t dB = ((uint64_t)bHiW << 32) | (bW + (uint32_t)(2 * s) * (1024 >> 4));
-          const uint32_t dcol = tmem_base + (uint32_t)(j * 64);
-          umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (tap | s) ? 1u : 0u);
-          umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+          for (int s = 0; s < 2; ++s) {
+            const uint32_t po = poff + (uint32_t)(j * 128);
+            const uint64_t dB = ((uint64_t)bHiW << 32) | (bW + (uint32_t)(2 * s) * (1024 >> 4));
+            const uint32_t dcol = tmem_base + (uint32_t)(j * 64);
+            umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (ky | kx | s) ? 1u : 0u);
+            umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+          }
         }
       }
       umma_commit(&empty[st]);   // frees this ring slot once the MMAs above have read it
@@ -226,6 +269,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
 
   // ---- epilogue -----------------------------------------------------------------------------------
   mbar_wait(accum_bar, 0);
+  TC_STAMP(3);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int quad = warp & 3, jpar = warp >> 2;   // warps 0-3: tiles 0,2,4; warps 4-7: tiles 1,3
   const int nCta = gridDim.x * gridDim.y * gridDim.z;
@@ -292,6 +336,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
       conv_stats_fold(a, nCta, TC_TH * TC_TW, sFin, &sIsLast);
     }
   }
+  TC_STAMP(4);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -323,6 +368,11 @@ int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
   conv7_tc_kernel<<<grid, 256, TC_SMEM, st>>>(a);
   PTK_LAUNCH_OK("conv7_tc_kernel");
+  return PTK_OK;
+}
+
+int read_tc_debug(long long* out) {
+  PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 8));
   return PTK_OK;
 }
 

@@ -30,24 +30,6 @@ __device__ __forceinline__ void acc_store(float* dst, float v, int first) {
   if (first) *dst = v; else *dst += v;
 }
 
-// CTA-level fold of per-thread channel partials: part[q][o] (thread's 8 channels) -> sTot[q][32].
-template <int NQ>
-__device__ __forceinline__ void cta_channel_sums(float (&part)[NQ][8], float* sRed /*[4][NQ][32]*/, float* sTot,
-                                                 const Lane& L) {
-  const int warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int q = 0; q < NQ; ++q)
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float v = reduce_pg(part[q][o]);
-      if (L.pg == 0) sRed[(warp * NQ + q) * C + L.oc0 + o] = v;
-    }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NQ * C; i += blockDim.x)
-    sTot[i] = (sRed[i] + sRed[NQ * C + i]) + (sRed[2 * NQ * C + i] + sRed[3 * NQ * C + i]);
-  __syncthreads();
-}
-
 // step-local BatchNorm-backward sums: per-CTA partials -> last CTA folds them (double) into
 // bn_tot = (sum dV)/N, (sum dV*xhat)/N and accumulates d(bn bias), d(bn weight).
 __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const float* sPart /*[2][32]*/, int first,
@@ -81,12 +63,13 @@ __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const floa
 template <int ACT>
 __global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int first) {
   __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
-  __shared__ float sRed[4 * 4 * C], sTot[4 * C];
+  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
   cta_fill(sKa, d.kappa, C);
   cta_fill(sGa, d.gamma, C);
   cta_fill(sW1, d.bn_w[1], C);
   cta_fill(sB1, d.bn_b[1], C);
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
   if (threadIdx.x < C) {
     const float* st = d.stat(t, 1);
     sM1[threadIdx.x] = st[threadIdx.x];
@@ -100,19 +83,16 @@ __global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int fir
   const float* I2t = d.I_at(t + 1);
   const float* Y1 = d.Y1_at(t);
   const float* Gxt = d.Gex_at(t);
-  float part[4][8];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int o = 0; o < 8; ++o) part[q][o] = 0.f;
+  float* sPw = sPart + warp * 4 * C;
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float e[4], a[4], i2[4], y1[4], gx[4], ge_in[4], gi_in[4], oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4];
+      float e[4], a[4], i2[4], y1[4], gx[4], ge_in[4], gi_in[4] = {0.f, 0.f, 0.f, 0.f};
+      float oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4], part[4] = {0.f, 0.f, 0.f, 0.f};
       ld4v(Et + idx, e);
       ld4v(At + idx, a);
       ld4v(I2t + idx, i2);
@@ -133,23 +113,24 @@ __global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int fir
         const float dR = gEn * gx[p] * dactf<ACT>(R);
         const float dV = dR * kIg;
         const float dRV = dR * V;
-        oGI[p] = fmaf(dRV, sKa[c], first ? 0.0f : gi_in[p]);
+        oGI[p] = fmaf(dRV, sKa[c], gi_in[p]);
         oGeb[p] = dGx * gx[p] * (1.0f - gx[p]);
         oDv[p] = dV;
         oGe[p] = a[p] * e[p];
-        part[0][o] = fmaf(dRV, i2[p], part[0][o]);   // -> d kappa
-        part[1][o] += dRV;                            // -> d gamma
-        part[2][o] += dV;                             // -> sum dV
-        part[3][o] = fmaf(dV, xh, part[3][o]);        // -> sum dV * xhat
+        part[0] = fmaf(dRV, i2[p], part[0]);   // -> d kappa
+        part[1] += dRV;                         // -> d gamma
+        part[2] += dV;                          // -> sum dV
+        part[3] = fmaf(dV, xh, part[3]);        // -> sum dV * xhat
       }
       st4(d.gE + idx, oGE);
       st4(d.gI + idx, oGI);
       st4(d.geb + idx, oGeb);
       st4(d.dAct + idx, oDv);
       st4(d.Ge + idx, oGe);
+      part_add<4>(sPw, c, L, part);
     }
   }
-  cta_channel_sums<4>(part, sRed, sTot, L);
+  part_fold<4>(sPart, sTot);
   float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
   if (threadIdx.x < C) {
     acc_store(acc + ACC_KAPPA + threadIdx.x, sTot[threadIdx.x], first);
@@ -189,7 +170,7 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
   float* sWeu = sWew + C * C;
   float* tiles = sWeu + C * C;
   __shared__ float sWp[C * 3], sbp[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
-  __shared__ float sRed[4 * 4 * C], sTot[4 * C];
+  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
   cta_fill(sWiw, d.gate[2], C * C);
   cta_fill(sWiu, d.gate[3], C * C);
@@ -201,6 +182,7 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
   cta_fill(sMu, d.mu, C);
   cta_fill(sW0, d.bn_w[0], C);
   cta_fill(sB0, d.bn_b[0], C);
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
   if (threadIdx.x < C) {
     const float* st = d.stat(t, 0);
     sM0[threadIdx.x] = st[threadIdx.x];
@@ -211,15 +193,11 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   float* sGi = tiles + warp * 2 * TILE_F;
   float* sGe = sGi + TILE_F;
+  float* sPw = sPart + warp * 4 * C;
   const float* It = d.I_at(t);
   const float* At = d.A_at(t);
   const float* Y0 = d.Y0_at(t);
   const float* Git = d.Gi_at(t);
-  float part[4][8];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int o = 0; o < 8; ++o) part[q][o] = 0.f;
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
@@ -227,12 +205,12 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
     cp_async_commit();
     float xin[3][4];
     frame_px(d.fv, b, t, pix, d.W, xin);
-    float z[4][8], ds[4][8];
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float gIn[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oDI[4];
+      float gIn[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oDI[4], oZ[4], oDs[4];
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
       ld4v(d.gI + idx, gIn);
       ld4v(It + idx, I);
       if (CELL == PTK_CELL_INT) {
@@ -262,44 +240,39 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
         const float dPU = dP * U;
         const float dU = dP * aSm;
         oDu[p] = dU;
-        z[p][o] = zz;
-        ds[p][o] = dPU * sAl[c] + (CELL == PTK_CELL_INT ? oDI[p] : 0.0f);   // InT: dI + dS lands in gI
-        part[0][o] = fmaf(dPU, S[p], part[0][o]);   // -> d alpha
-        part[1][o] += dPU;                           // -> d mu
-        part[2][o] += dU;                            // -> sum dU
-        part[3][o] = fmaf(dU, xh, part[3][o]);       // -> sum dU * xhat
+        oZ[p] = zz;
+        oDs[p] = dPU * sAl[c] + (CELL == PTK_CELL_INT ? oDI[p] : 0.0f);   // InT: dI + dS lands in gI
+        part[0] = fmaf(dPU, S[p], part[0]);   // -> d alpha
+        part[1] += dPU;                        // -> d mu
+        part[2] += dU;                         // -> sum dU
+        part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
       }
       st4(d.dAct + idx, oDu);
       st4(d.giS + idx, oGi);
       st4(d.Xs + idx, X);
+      st4(d.dX + idx, oZ);        // parked: completed by the transposed products below
+      st4(d.dS + idx, oDs);
       tile_st(sGi, L, o, oGi);
       if (CELL == PTK_CELL_HGRU) st4(d.gI + idx, oDI);
+      part_add<4>(sPw, c, L, part);
     }
     cp_async_wait<0>();
     __syncwarp();
-    warp_gemm(z, sGi, sWiw, L);      // dX = z + Wi_w^T gi
-    warp_gemm(ds, sGi, sWiu, L);     // dS += Wi_u^T gi
-    warp_gemm(ds, sGe, sWew, L);     //     + We_w^T ge
-    float dge[4][8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o)
-#pragma unroll
-      for (int p = 0; p < 4; ++p) dge[p][o] = 0.f;
-    warp_gemm(dge, sGe, sWeu, L);    // dGe = We_u^T ge
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const size_t idx = base + (size_t)(L.oc0 + o) * P;
-      float v0[4], v1[4], v2[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) { v0[p] = z[p][o]; v1[p] = ds[p][o]; v2[p] = dge[p][o]; }
-      st4(d.dX + idx, v0);
-      if (CELL == PTK_CELL_INT) st4(d.gI + idx, v1);   // (b10) InT: dI += dS
-      else st4(d.dS + idx, v1);                         //       hGRU: dA += dS (in bwd_d)
-      st4(d.dGe + idx, v2);
-    }
+    float acc[4][8];
+    acc_from_global(acc, d.dX, base, P, L);
+    warp_gemm(acc, sGi, sWiw, L);      // dX = z + Wi_w^T gi
+    acc_to_global(d.dX, base, P, L, acc);
+    acc_from_global(acc, d.dS, base, P, L);
+    warp_gemm(acc, sGi, sWiu, L);      // dS += Wi_u^T gi
+    warp_gemm(acc, sGe, sWew, L);      //     + We_w^T ge
+    if (CELL == PTK_CELL_INT) acc_to_global(d.gI, base, P, L, acc);   // (b10) InT: dI += dS
+    else acc_to_global(d.dS, base, P, L, acc);                         //       hGRU: dA += dS (in bwd_d)
+    acc_fill(acc, nullptr, L);
+    warp_gemm(acc, sGe, sWeu, L);      // dGe = We_u^T ge
+    acc_to_global(d.dGe, base, P, L, acc);
     __syncwarp();
   }
-  cta_channel_sums<4>(part, sRed, sTot, L);
+  part_fold<4>(sPart, sTot);
   float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
   if (threadIdx.x < C) {
     acc_store(acc + ACC_ALPHA + threadIdx.x, sTot[threadIdx.x], first);
@@ -318,74 +291,74 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
   float* sWau = sWaw + C * C;
   float* tiles = sWau + C * C;
   __shared__ float sWp[C * 3], sbp[C];
-  __shared__ float sRed[4 * 4 * C], sTot[4 * C];
+  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
   cta_fill(sWaw, d.gate[0], C * C);
   cta_fill(sWau, d.gate[1], C * C);
   cta_fill(sWp, d.Wp, C * 3);
   cta_fill(sbp, d.bp, C);
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
   __syncthreads();
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   float* sA = tiles + warp * TILE_F;
+  float* sPw = sPart + warp * 4 * C;   // [0] d bp, [1..3] d Wp[:, i]
   const float* Et = d.E_at(t);
   const float* At = d.A_at(t);
-  float part[4][8];   // [0] d bp, [1..3] d Wp[:, i]
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int o = 0; o < 8; ++o) part[q][o] = 0.f;
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
     float xin[3][4];
     frame_px(d.fv, b, t, pix, d.W, xin);
-    float de[4][8], dxv[4][8];
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const size_t idx = base + (size_t)(L.oc0 + o) * P;
-      float A[4], dGe[4], E[4], gE[4], dS[4], oa[4], dxin[4];
+      float A[4], dGe[4], E[4], gE[4], dS[4] = {0.f, 0.f, 0.f, 0.f}, oa[4], ode[4];
       ld4v(At + idx, A);
       ld4v(d.dGe + idx, dGe);
       ld4v(Et + idx, E);
       ld4v(d.gE + idx, gE);
-      ld4v(d.dX + idx, dxin);
       if (CELL == PTK_CELL_HGRU) ld4v(d.dS + idx, dS);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        float dA = dGe[p] * E[p];
-        if (CELL == PTK_CELL_HGRU) dA += dS[p];
+        const float dA = fmaf(dGe[p], E[p], dS[p]);
         oa[p] = dA * A[p] * (1.0f - A[p]);
-        de[p][o] = fmaf(dGe[p], A[p], gE[p]);
-        dxv[p][o] = dxin[p];
+        ode[p] = fmaf(dGe[p], A[p], gE[p]);
       }
       st4(d.aS + idx, oa);
+      st4(d.gE + idx, ode);          // parked: completed by the transposed product below
       tile_st(sA, L, o, oa);
     }
     __syncwarp();
-    warp_gemm(de, sA, sWau, L);     // dE += Wa_u^T a
-    warp_gemm(dxv, sA, sWaw, L);    // dX += Wa_w^T a
+    float acc[4][8];
+    acc_from_global(acc, d.gE, base, P, L);
+    warp_gemm(acc, sA, sWau, L);     // dE += Wa_u^T a
+    acc_to_global(d.gE, base, P, L, acc);
+    acc_from_global(acc, d.dX, base, P, L);
+    warp_gemm(acc, sA, sWaw, L);     // dX += Wa_w^T a
+    __syncwarp();
+    acc_to_tile(sA, L, acc);         // park dX; each thread re-reads only its own patch
     float dxs[3][4];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
       for (int p = 0; p < 4; ++p) dxs[i][p] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
-      float pre[4], v[4];
+      float pre[4], dxv[4], part[4] = {0.f, 0.f, 0.f, 0.f};
       stem_pre(sWp, sbp, c, xin, pre);
+      tile_ld(sA, L, o, dxv);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        v[p] = de[p][o];
-        const float dp = dxv[p][o] * dactf<ACT>(pre[p]);
-        part[0][o] += dp;
+        const float dp = dxv[p] * dactf<ACT>(pre[p]);
+        part[0] += dp;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          part[1 + i][o] = fmaf(dp, xin[i][p], part[1 + i][o]);
+          part[1 + i] = fmaf(dp, xin[i][p], part[1 + i]);
           dxs[i][p] = fmaf(sWp[c * 3 + i], dp, dxs[i][p]);
         }
       }
-      st4(d.gE + base + (size_t)c * P, v);
+      part_add<4>(sPw, c, L, part);
     }
     if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
 #pragma unroll
@@ -411,7 +384,7 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
     }
     __syncwarp();
   }
-  cta_channel_sums<4>(part, sRed, sTot, L);
+  part_fold<4>(sPart, sTot);
   float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
@@ -667,7 +640,7 @@ template <int CELL, int ACT>
 static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int P = d.H * d.W;
   const int grid = d.pw_ctas;
-  const int grid_c = grid < 148 * 2 ? grid : 148 * 2;   // bwd_c needs > 170 registers: 2 CTAs per SM
+  const int grid_c = grid;
   PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)grid * ACC_N * sizeof(float), st));
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));

@@ -16,6 +16,20 @@ namespace ptk {
 
 constexpr int TILE_F = C * TP;   // floats per warp tile
 
+// stem of the thread's patch into the X tile (rolled: softplus is ~100 instructions per element)
+template <int ACT>
+__device__ __forceinline__ void stem_to_tile(float* sX, const float* sWp, const float* sbp, const float (&xin)[3][4],
+                                             const Lane& L) {
+#pragma unroll 1
+  for (int o = 0; o < 8; ++o) {
+    float pre[4];
+    stem_pre(sWp, sbp, L.oc0 + o, xin, pre);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) pre[p] = actf<ACT>(pre[p]);
+    tile_st(sX, L, o, pre);
+  }
+}
+
 // eqs (1)-(2) for frame t: A = sigmoid(Wa_w X + Wa_u E + b), Ge = A*E.  sE must hold E_t.
 template <int ACT>
 __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, int pix_base, float* sX,
@@ -25,32 +39,23 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
   const int P = d.H * d.W, pix = pix_base + L.pxo;
   float xin[3][4];
   frame_px(d.fv, b, t, pix, d.W, xin);
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    float pre[4];
-    stem_pre(sWp, sbp, L.oc0 + o, xin, pre);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) pre[p] = actf<ACT>(pre[p]);
-    tile_st(sX, L, o, pre);
-  }
+  stem_to_tile<ACT>(sX, sWp, sbp, xin, L);
   __syncwarp();
   float acc[4][8];
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    const float bb = sba[L.oc0 + o];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) acc[p][o] = bb;
-  }
+  acc_fill(acc, sba, L);
   warp_gemm(acc, sX, sWaw, L);
   warp_gemm(acc, sE, sWau, L);
+  __syncwarp();
+  acc_to_tile(sX, L, acc);          // park the pre-activations; only this thread re-reads its patch
   float* Aout = d.A_at(t) + (size_t)b * d.a_bstride + pix;
   float* Geout = d.Ge + (size_t)b * C * P + pix;
-#pragma unroll
+#pragma unroll 1
   for (int o = 0; o < 8; ++o) {
     float e[4], a[4], ge[4];
     tile_ld(sE, L, o, e);
+    tile_ld(sX, L, o, a);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) { a[p] = sigmoidf_(acc[p][o]); ge[p] = a[p] * e[p]; }
+    for (int p = 0; p < 4; ++p) { a[p] = sigmoidf_(a[p]); ge[p] = a[p] * e[p]; }
     st4(Aout + (size_t)(L.oc0 + o) * P, a);
     st4(Geout + (size_t)(L.oc0 + o) * P, ge);
   }
@@ -123,38 +128,38 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
+    const float* Sg = (CELL == PTK_CELL_INT) ? It + base : d.A_at(t) + (size_t)b * d.a_bstride + pix;
     if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
     else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
     warp_tile_load_async(sGe, d.Ge, (size_t)C * P, b, pix_base, P);
     cp_async_commit();
     float xin[3][4];
     frame_px(d.fv, b, t, pix, d.W, xin);
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      float pre[4];
-      stem_pre(sWp, sbp, L.oc0 + o, xin, pre);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) pre[p] = actf<ACT>(pre[p]);
-      tile_st(sX, L, o, pre);
-    }
+    stem_to_tile<ACT>(sX, sWp, sbp, xin, L);
     cp_async_wait<0>();
     __syncwarp();
     float acc[4][8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float bb = sbi[L.oc0 + o];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[p][o] = bb;
-    }
+    // excitation gate pre-activation first, parked in the Ge tile (no longer needed afterwards)
+    acc_fill(acc, sbe, L);
+    warp_gemm(acc, sS, sWew, L);
+    warp_gemm(acc, sGe, sWeu, L);
+    __syncwarp();
+    acc_to_tile(sGe, L, acc);
+    // inhibition gate pre-activation, parked in the S tile (S is re-read from global below)
+    acc_fill(acc, sbi, L);
     warp_gemm(acc, sX, sWiw, L);
     warp_gemm(acc, sS, sWiu, L);
-#pragma unroll
+    __syncwarp();
+    acc_to_tile(sS, L, acc);
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float X[4], S[4], I[4], y0[4], gi[4], out[4];
+      float X[4], S[4], I[4], y0[4], gi[4], gx[4], out[4];
       tile_ld(sX, L, o, X);
-      tile_ld(sS, L, o, S);
+      tile_ld(sS, L, o, gi);
+      tile_ld(sGe, L, o, gx);
+      ld4v(Sg + (size_t)c * P, S);
       if (CELL == PTK_CELL_INT) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) I[p] = S[p];
@@ -164,7 +169,8 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
       ld4v(Y0 + idx, y0);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        gi[p] = sigmoidf_(acc[p][o]);
+        gi[p] = sigmoidf_(gi[p]);
+        gx[p] = sigmoidf_(gx[p]);
         const float U = fmaf(y0[p], sScale[c], sShift[c]);
         const float Pp = U * fmaf(sAl[c], S[p], sMu[c]);
         const float Q = actf<ACT>(Pp);
@@ -172,22 +178,8 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
         out[p] = (1.0f - gi[p]) * I[p] + gi[p] * Ihat;
       }
       st4(d.Gi_at(t) + idx, gi);
+      st4(d.Gex_at(t) + idx, gx);
       st4(Iout + idx, out);
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float bb = sbe[L.oc0 + o];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[p][o] = bb;
-    }
-    warp_gemm(acc, sS, sWew, L);
-    warp_gemm(acc, sGe, sWeu, L);
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      float gx[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) gx[p] = sigmoidf_(acc[p][o]);
-      st4(d.Gex_at(t) + base + (size_t)(L.oc0 + o) * P, gx);
     }
     __syncwarp();
   }
@@ -231,7 +223,7 @@ __global__ void __launch_bounds__(128) int_post_kernel(IntDev d, int t, int has_
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
     float sread[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;

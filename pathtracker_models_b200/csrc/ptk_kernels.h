@@ -30,5 +30,6 @@ int launch_conv7(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st);
 int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st);
+int read_tc_debug(long long* out);   // cycle stamps of CTA 0 of the last conv7_tc_kernel (tuning aid)
 
 }  // namespace ptk

@@ -87,12 +87,63 @@ __device__ __forceinline__ void cta_fill(float* dst, const float* __restrict__ s
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
+// registers <-> the thread's patch of a tile, all 8 channels (static indices; used to park GEMM
+// accumulators in shared memory so that the element-wise math can run in a rolled loop)
+__device__ __forceinline__ void acc_to_tile(float* tile, const Lane& L, const float (&acc)[4][8]) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float v[4] = {acc[0][o], acc[1][o], acc[2][o], acc[3][o]};
+    tile_st(tile, L, o, v);
+  }
+}
+__device__ __forceinline__ void acc_fill(float (&acc)[4][8], const float* sBias, const Lane& L) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float bb = sBias ? sBias[L.oc0 + o] : 0.0f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p][o] = bb;
+  }
+}
+// acc <- [B,C,P] global patch (static)
+__device__ __forceinline__ void acc_from_global(float (&acc)[4][8], const float* src, size_t base, int P, const Lane& L) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float4 t = ld4(src + base + (size_t)(L.oc0 + o) * P);
+    acc[0][o] = t.x; acc[1][o] = t.y; acc[2][o] = t.z; acc[3][o] = t.w;
+  }
+}
+__device__ __forceinline__ void acc_to_global(float* dst, size_t base, int P, const Lane& L, const float (&acc)[4][8]) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float v[4] = {acc[0][o], acc[1][o], acc[2][o], acc[3][o]};
+    st4(dst + base + (size_t)(L.oc0 + o) * P, v);
+  }
+}
+
 // reduce per-thread channel partials (thread owns channels oc0..oc0+7) over the 8 pixel-group lanes
 __device__ __forceinline__ float reduce_pg(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   return v;
+}
+
+// per-warp channel-sum accumulators in shared memory: sPart[warp][q][c]
+template <int NQ>
+__device__ __forceinline__ void part_add(float* sPartWarp, int c, const Lane& L, const float (&v)[NQ]) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float r = reduce_pg(v[q]);
+    if (L.pg == 0) sPartWarp[q * C + c] += r;
+  }
+}
+// fold the 4 warps' partials: sTot[q][c]  (all threads; contains __syncthreads)
+template <int NQ>
+__device__ __forceinline__ void part_fold(const float* sPart /*[4][NQ][32]*/, float* sTot) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < NQ * C; i += blockDim.x)
+    sTot[i] = (sPart[i] + sPart[NQ * C + i]) + (sPart[2 * NQ * C + i] + sPart[3 * NQ * C + i]);
+  __syncthreads();
 }
 
 }  // namespace ptk

@@ -23,3 +23,17 @@ for mode, name in ((0, "fp32-ffma"), (1, "bf16x3-tcgen05")):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         print(f"{name:16s} accumulate={acc!s:5s} {ms*1e3:8.1f} us/call (incl. weight prep launch)  {flop/ms/1e9:8.1f} TFLOP/s")
+
+import ctypes
+from pathtracker_models_b200 import _lib
+L = _lib.lib()
+buf = (ctypes.c_longlong * 8)()
+conv7(x, w, conv_mode=1, want_stats=True); torch.cuda.synchronize()
+L.ptk_debug_tc_stamps(buf)
+t = list(buf)
+print("tc conv CTA(0) cycles: setup+zero %d, staging %d, mma %d, epilogue %d, total %d" % (t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[4]-t[0]))
+out = torch.zeros_like(x)
+conv7(x, w, conv_mode=1, out=out); torch.cuda.synchronize()
+L.ptk_debug_tc_stamps(buf)
+t = list(buf)
+print("tc conv (accumulate) cycles: setup+zero %d, staging %d, mma %d, epilogue %d, total %d" % (t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[4]-t[0]))
