@@ -69,8 +69,10 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   double* bn_acc = cv.take<double>(4 * C);
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);
   float* dgoal = cv.take<float>(S / C);
-  float* wacc_exc = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
-  float* wacc_inh = cv.take<float>((size_t)4 * WGRAD_GROUPS * TAPS * 256);
+  size_t wacc_n = (size_t)4 * WGRAD_GROUPS * TAPS * 256;
+  if (dm->conv_mode == PTK_CONV_BF16X3) wacc_n = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
+  float* wacc_exc = cv.take<float>(wacc_n);
+  float* wacc_inh = cv.take<float>(wacc_n);
   if (d) {
     d->Ge = Ge;
     d->bn_part = bn_part; d->counter = counter; d->pw_ctas = pw;

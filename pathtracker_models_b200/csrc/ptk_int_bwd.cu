@@ -576,6 +576,7 @@ __global__ void __launch_bounds__(256) int_readout_bwd_kernel(IntDev d, const fl
 // finalize: fold per-CTA / per-sample partials (double) into the flat gradient vector.
 struct FinalizeArgs {
   int pw_ctas, gate_ctas, B, wgroups;
+  int wgrad_tc;   // > 0: number of CTA slots of the tensor-core weight gradient ([cta][tap][oc][ic])
   int64_t off[PTK_INT_NPARAM + 1];
 };
 
@@ -621,8 +622,12 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
       // dW[oc][ic][tap] = sum_groups wacc[(grp*4 + ic/8)][tap][oc*8 + ic%8]
       const float* wa = (p == PTK_P_W_EXC) ? d.wacc_exc : d.wacc_inh;
       const int oc = j / (C * TAPS), ic = (j / TAPS) % C, tap = j % TAPS;
-      for (int g = 0; g < f.wgroups; ++g)
-        s += (double)wa[((size_t)(g * 4 + ic / 8) * TAPS + tap) * 256 + oc * 8 + (ic & 7)];
+      if (f.wgrad_tc > 0) {
+        for (int g = 0; g < f.wgrad_tc; ++g) s += (double)wa[((size_t)g * TAPS + tap) * C * C + oc * C + ic];
+      } else {
+        for (int g = 0; g < f.wgroups; ++g)
+          s += (double)wa[((size_t)(g * 4 + ic / 8) * TAPS + tap) * 256 + oc * 8 + (ic & 7)];
+      }
     } else if (p == PTK_P_BN0_W) s = d.bn_acc[0 * 2 * C + C + j];
     else if (p == PTK_P_BN0_B) s = d.bn_acc[0 * 2 * C + j];
     else if (p == PTK_P_BN1_W) s = d.bn_acc[1 * 2 * C + C + j];
@@ -641,6 +646,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int P = d.H * d.W;
   const int grid = d.pw_ctas;
   const int grid_c = grid;
+  const bool tc = (d.conv_mode == PTK_CONV_BF16X3);
   PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)grid * ACC_N * sizeof(float), st));
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
@@ -671,7 +677,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
-    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w1, WGRAD_GROUPS, st); }
+    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w1, st) : launch_wgrad7(w1, WGRAD_GROUPS, st); }
     if (rc) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
@@ -687,7 +693,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
     if (rc) return rc;
     WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
-    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w0, WGRAD_GROUPS, st); }
+    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w0, st) : launch_wgrad7(w0, WGRAD_GROUPS, st); }
     if (rc) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
@@ -702,6 +708,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   }
   FinalizeArgs f;
   f.pw_ctas = grid; f.gate_ctas = gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
+  f.wgrad_tc = tc ? conv_num_ctas(d.B, d.H, d.W) : 0;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
   {

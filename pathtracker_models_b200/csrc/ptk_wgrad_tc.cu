@@ -1,0 +1,226 @@
+// Tensor-core weight gradient of the 7x7 horizontal-connection convolutions (tcgen05 / TMEM).
+//
+//   dW[oc][ic][ky][kx] += sum_{y,x} dY[b,oc,y,x] * In[b,ic,y+ky-3,x+kx-3]       (per CTA: 16 rows x 32 cols of one sample)
+//
+// GEMM view per tap: D[m = oc][n = ic] = sum_{k = pixel} dY[k][m] * In[k + shift(tap)][n]; the pixel
+// axis is K, so both operands are MN-major.  Both tiles sit in shared memory in the channel-chunk
+// planar form of ptk_conv_tc.cu ([chunk][pixel][8 ch], 16 B per pixel) with the hi planes followed by
+// the lo planes.  One instruction with M = 64 rows = [dYh(32 oc) ; dYl(32 oc)] and N = 64 columns =
+// [Ih(32 ic) | Il(32 ic)] therefore produces all four products of the split
+//   (dYh + dYl) * (Ih + Il)
+// at once; the epilogue adds the two row halves and the two column halves.  A tap is just a different
+// start pixel of the In operand (ky*38 + kx), exactly as in the forward kernel.
+//
+// Taps are processed in rounds of 4 (4 x 64 = 256 TMEM columns, double buffered): while the MMA
+// thread accumulates round r+1 over the 38 K-steps, four epilogue warps drain round r and add it into
+// this CTA's private accumulator slot in global memory (read-add-write by the owning CTA only =>
+// deterministic; `finalize` folds the slots).
+#include "ptk_common.cuh"
+#include "ptk_kernels.h"
+#include "ptk_tc.cuh"
+
+namespace ptk {
+
+constexpr int WT_TH = 16, WT_TW = 32, WT_WP = 38, WT_ROWS = 22;
+constexpr int WT_KPIX = WT_TH * WT_WP;               // 608 pixels = 38 K-steps of 16
+constexpr int WT_KSTEPS = WT_KPIX / 16;
+constexpr int WT_DY_PLANE = WT_KPIX * 16;            // 9728 B
+constexpr int WT_IN_NPIX = 880;                      // >= 608 + 6*38 + 6
+constexpr int WT_IN_PLANE = WT_IN_NPIX * 16;         // 14080 B
+constexpr int WT_DY_BYTES = 8 * WT_DY_PLANE;         // hi chunks 0-3, lo chunks 4-7
+constexpr int WT_IN_BYTES = 8 * WT_IN_PLANE;
+constexpr int WT_RT = 4;                             // taps per round
+constexpr int WT_ROUNDS = (TAPS + WT_RT - 1) / WT_RT;
+constexpr int WT_OP = 36;                            // staging row pitch (floats)
+constexpr int WT_OUT_BYTES = WT_RT * 2 * C * WT_OP * 4;
+constexpr int WT_SMEM = WT_DY_BYTES + WT_IN_BYTES + WT_OUT_BYTES + 128;
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both MN-major, M=64, N=64
+__host__ __device__ constexpr uint32_t wt_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) |
+         ((uint32_t)(64 >> 4) << 24);
+}
+
+// fp32 NCHW rows -> bf16 hi/lo channel-chunk planar tile (pixel pitch 16 B, row pitch 38 pixels).
+// rows [r0, r0+nrows) of the tile map to image rows gy0 + r; columns: 32 interior (+3 halo each side when
+// `halo` and the neighbour exists).  `col0` = padded column of image column x0.
+__device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_bytes, const float* __restrict__ src,
+                                         int b, int gy0, int nrows, int x0, int H, int W, int col0, bool halo) {
+  const int tid = threadIdx.x;
+  for (int it = tid; it < 4 * nrows * (WT_TW / 4); it += 256) {
+    const int q = it / (nrows * (WT_TW / 4)), rem = it - q * (nrows * (WT_TW / 4)), r = rem / (WT_TW / 4), g = rem % (WT_TW / 4);
+    const int gy = gy0 + r;
+    if (gy < 0 || gy >= H) continue;
+    const float* p0 = src + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
+    float4 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(p0 + (size_t)e * H * W);
+    const int p = r * WT_WP + col0 + 4 * g;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(reinterpret_cast<const float*>(&v[2 * e])[px], h0, l0);
+        split_bf16(reinterpret_cast<const float*>(&v[2 * e + 1])[px], h1, l1);
+        hi[e] = pack_bf16x2(h0, h1);
+        lo[e] = pack_bf16x2(l0, l1);
+      }
+      *reinterpret_cast<uint4*>(sHi + q * plane_bytes + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sLo + q * plane_bytes + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  if (halo && W > WT_TW) {
+    for (int it = tid; it < 4 * nrows * 6; it += 256) {
+      const int q = it / (nrows * 6), rem = it - q * (nrows * 6), r = rem / 6, hc = rem % 6;
+      const int c = hc < 3 ? hc : (WT_TW + hc);
+      const int gy = gy0 + r, gx = x0 + c - 3;
+      if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
+      const float* p0 = src + ((size_t)(b * C + q * 8) * H + gy) * W + gx;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(p0[(size_t)(2 * e) * H * W], h0, l0);
+        split_bf16(p0[(size_t)(2 * e + 1) * H * W], h1, l1);
+        hi[e] = pack_bf16x2(h0, h1);
+        lo[e] = pack_bf16x2(l0, l1);
+      }
+      const int p = r * WT_WP + c;
+      *reinterpret_cast<uint4*>(sHi + q * plane_bytes + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sLo + q * plane_bytes + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sDY = smem_raw;                                  // [8 planes][608 px][16 B]
+  uint8_t* sIN = smem_raw + WT_DY_BYTES;                    // [8 planes][880 px][16 B]
+  float* sOut = reinterpret_cast<float*>(smem_raw + WT_DY_BYTES + WT_IN_BYTES);   // [4 taps][hi/lo][32 oc][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + WT_DY_BYTES + WT_IN_BYTES + WT_OUT_BYTES);
+  uint64_t* tfull = bars;        // [2]
+  uint64_t* tempty = bars + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * WT_TW, y0 = blockIdx.y * WT_TH, b = blockIdx.z;
+  const int H = a.H, W = a.W;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+    mbar_init(&tempty[0], 128); mbar_init(&tempty[1], 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < (WT_DY_BYTES + WT_IN_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // dY tile: 16 rows, interior columns only (pad columns stay zero => contribute nothing)
+  wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, b, y0, WT_TH, x0, H, W, 0, false);
+  // In tile: 22 rows with the 3-pixel halo, interior at padded column 3
+  wt_stage(sIN, sIN + 4 * WT_IN_PLANE, WT_IN_PLANE, a.in, b, y0 - 3, WT_ROWS, x0, H, W, 3, true);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- MMA issuer ------------------------------------------------------------------------------
+    // MN-major no-swizzle descriptors: LBO = stride between 8-pixel K groups (128 B), SBO = plane stride
+    const uint64_t dA0 = umma_desc(smem_u32(sDY), 128, WT_DY_PLANE);
+    const uint64_t dB0 = umma_desc(smem_u32(sIN), 128, WT_IN_PLANE);
+    const uint32_t aHiW = (uint32_t)(dA0 >> 32), aLoW = (uint32_t)dA0;
+    const uint32_t bHiW = (uint32_t)(dB0 >> 32), bLoW = (uint32_t)dB0;
+    constexpr uint32_t IDESC = wt_idesc();
+    for (int r = 0; r < WT_ROUNDS; ++r) {
+      const int buf = r & 1, use = r >> 1;
+      if (use > 0) mbar_wait(&tempty[buf], (uint32_t)((use - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int t0 = r * WT_RT, nt = (TAPS - t0) < WT_RT ? (TAPS - t0) : WT_RT;
+      for (int tl = 0; tl < nt; ++tl) {
+        const int tap = t0 + tl, ky = tap / KS, kx = tap - ky * KS;
+        const uint32_t bOff = bLoW + (uint32_t)(ky * WT_WP + kx);      // 16-byte units == pixels
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + tl * 64);
+#pragma unroll 2
+        for (int ks = 0; ks < WT_KSTEPS; ++ks) {
+          const uint64_t dA = ((uint64_t)aHiW << 32) | (aLoW + (uint32_t)(ks * 16));
+          const uint64_t dB = ((uint64_t)bHiW << 32) | (bOff + (uint32_t)(ks * 16));
+          umma_bf16(dcol, dA, dB, IDESC, ks ? 1u : 0u);
+        }
+      }
+      umma_commit(&tfull[buf]);
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue warps: drain a round, combine the four split products, add into the CTA's slot ----
+    const int quad = warp & 3, et = tid - 128;
+    const int half = quad >> 1, oc = (quad & 1) * 16 + lane;      // valid for lane < 16 (M = 64 TMEM layout)
+    float* slot = a.wacc + (size_t)cta * TAPS * C * C;
+    for (int r = 0; r < WT_ROUNDS; ++r) {
+      const int buf = r & 1, use = r >> 1;
+      const int t0 = r * WT_RT, nt = (TAPS - t0) < WT_RT ? (TAPS - t0) : WT_RT;
+      mbar_wait(&tfull[buf], (uint32_t)(use & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int tl = 0; tl < nt; ++tl) {
+        float v[32], w[32];
+        const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + tl * 64);
+        tmem_ld32(ta, v);
+        tmem_ld32(ta + 32, w);
+        if (lane < 16) {
+          float* dst = sOut + ((tl * 2 + half) * C + oc) * WT_OP;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] + w[i], v[i + 1] + w[i + 1], v[i + 2] + w[i + 2], v[i + 3] + w[i + 3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tempty[buf]);                     // TMEM buffer may be overwritten by round r+2
+      named_bar_sync(1, 128);
+      // 4 taps x 1024 floats = 8 float4 per thread: issue all loads first, then add and store
+      {
+        float4 prev[8], val[8];
+        float* gp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int i4 = et + 128 * k;                         // float4 index inside the round
+          const int tl = i4 >> 8, o = (i4 >> 3) & 31, ic = (i4 & 7) * 4;
+          gp[k] = slot + (size_t)(t0 + tl) * C * C + o * C + ic;
+          const bool on = tl < nt;
+          if (on && !a.first) prev[k] = *reinterpret_cast<const float4*>(gp[k]);
+          else prev[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 h = *reinterpret_cast<const float4*>(sOut + ((tl * 2 + 0) * C + o) * WT_OP + ic);
+          const float4 l = *reinterpret_cast<const float4*>(sOut + ((tl * 2 + 1) * C + o) * WT_OP + ic);
+          val[k] = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int tl = (et + 128 * k) >> 8;
+          if (tl < nt)
+            *reinterpret_cast<float4*>(gp[k]) = make_float4(prev[k].x + val[k].x, prev[k].y + val[k].y,
+                                                            prev[k].z + val[k].z, prev[k].w + val[k].w);
+        }
+      }
+      named_bar_sync(1, 128);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+size_t wgrad_tc_acc_floats(int B, int H, int W) { return (size_t)B * (H / WT_TH) * (W / WT_TW) * TAPS * C * C; }
+
+int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st) {
+  PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+  dim3 grid(a.W / WT_TW, a.H / WT_TH, a.B);
+  wgrad7_tc_kernel<<<grid, 256, WT_SMEM, st>>>(a);
+  PTK_LAUNCH_OK("wgrad7_tc_kernel");
+  return PTK_OK;
+}
+
+}  // namespace ptk
