@@ -36,23 +36,36 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // ---- math ----------------------------------------------------------------------------------
-// The transcendental maps are deliberately NOT inlined: expf/log1pf expand to ~100 instructions and the
-// point-wise kernels evaluate several of them per element; inlining made each kernel > 60 KB of SASS
-// (instruction-cache misses showed up as the top stall reason, profiles/r1b_pointwise_wgrad_full.txt).
-static __device__ __noinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-static __device__ __noinline__ float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
-static __device__ __noinline__ float tanhf_(float x) { return tanhf(x); }
+// Precise transcendental maps are deliberately NOT inlined: expf/log1pf expand to ~100 instructions and
+// the point-wise kernels evaluate several of them per element; inlining made each kernel > 60 KB of SASS
+// (instruction-cache misses were the top stall reason, profiles/r1b_pointwise_wgrad_full.txt).
+static __device__ __noinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+static __device__ __noinline__ float softplus_precise(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+static __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
+// MUFU-based variants (ex2.approx / lg2.approx / rcp.approx, ~2 ulp): used by the split-bf16 tensor-core
+// mode, whose convolutions are already ~1e-5 accurate; same parity gate (tests/test_parity_gpu.py).
+static __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+static __device__ __forceinline__ float softplus_fast(float x) {
+  return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x)));   // = log(1 + e^x), no overflow, threshold-free
+}
 
+// Activation codes: PTK_ACT_SOFTPLUS (0), PTK_ACT_TANH (1) as in the C ABI; +2 selects the fast variants.
+constexpr int ACT_FAST = 2;
+template <int ACT>
+__device__ __forceinline__ float sigm(float x) {
+  if (ACT & ACT_FAST) return sigmoid_fast(x);
+  return sigmoid_precise(x);
+}
 // activation `nl` of InT.__init__ (models/InT.py:184,208): softplus(beta=1, threshold=20) or tanh
 template <int ACT>
 __device__ __forceinline__ float actf(float x) {
-  if (ACT == PTK_ACT_SOFTPLUS) return softplusf_(x);
-  return tanhf_(x);
+  if ((ACT & 1) == PTK_ACT_SOFTPLUS) return (ACT & ACT_FAST) ? softplus_fast(x) : softplus_precise(x);
+  return tanh_precise(x);
 }
 template <int ACT>
 __device__ __forceinline__ float dactf(float x) {
-  if (ACT == PTK_ACT_SOFTPLUS) return x > 20.0f ? 1.0f : sigmoidf_(x);
-  const float t = tanhf_(x);
+  if ((ACT & 1) == PTK_ACT_SOFTPLUS) return (ACT & ACT_FAST) ? sigmoid_fast(x) : (x > 20.0f ? 1.0f : sigmoid_precise(x));
+  const float t = tanh_precise(x);
   return 1.0f - t * t;
 }
 

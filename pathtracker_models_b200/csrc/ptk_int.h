@@ -49,6 +49,7 @@ struct IntDev {
   unsigned* counter;
   // backward scratch
   float *gE, *gI, *geb, *dAct, *dGe, *dX, *dS, *giS, *aS, *Xs;
+  float *cgI, *cGe;        // data-gradient outputs of the two transposed convolutions (added by the consumers)
   int pw_ctas;             // grid of the backward point-wise kernels (fixed => deterministic slots)
   float* acc;              // [pw_ctas][ACC_N]
   float* gacc;             // [GATE_CTAS][GACC_N]

@@ -6,11 +6,11 @@
 //
 //   bwd_a     (b1)-(b2)   + BatchNorm1 backward sums     element-wise (gates A, G_e come from the checkpoint)
 //   bn_apply  (b3)        dV -> dY1 in place
-//   conv7     (b4)        dI' += dY1 *7^T W_exc           (ptk_conv.cu, flipped weights)
+//   conv7     (b4)        dY1 *7^T W_exc -> cgI (added to dI' by bwd_c; ptk_conv*.cu, flipped weights)
 //   wgrad7    (b4)        dW_exc += I' (star) dY1
 //   bwd_c     (b5)-(b8)   + BatchNorm0 backward sums     element-wise + 4 transposed 1x1 products
 //   bn_apply  (b9)        dU -> dY0
-//   conv7     (b9)        dGe += dY0 *7^T W_inh
+//   conv7     (b9)        dY0 *7^T W_inh -> cGe (added to dGe by bwd_d)
 //   wgrad7    (b9)        dW_inh += Ge (star) dY0
 //   bwd_d     (b10)-(b12) attention gate + stem           element-wise + 2 transposed 1x1 products
 //   gate_wgrad            the six 32x32 gate-weight gradients + gate-bias gradients of the step
@@ -211,7 +211,13 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
       const size_t idx = base + (size_t)c * P;
       float gIn[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oDI[4], oZ[4], oDs[4];
       float part[4] = {0.f, 0.f, 0.f, 0.f};
-      ld4v(d.gI + idx, gIn);
+      {
+        float cg[4];
+        ld4v(d.gI + idx, gIn);
+        ld4v(d.cgI + idx, cg);      // + dY1 *7^T W_exc (b4), written by the transposed convolution
+#pragma unroll
+        for (int p = 0; p < 4; ++p) gIn[p] += cg[p];
+      }
       ld4v(It + idx, I);
       if (CELL == PTK_CELL_INT) {
 #pragma unroll
@@ -314,7 +320,13 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
       const size_t idx = base + (size_t)(L.oc0 + o) * P;
       float A[4], dGe[4], E[4], gE[4], dS[4] = {0.f, 0.f, 0.f, 0.f}, oa[4], ode[4];
       ld4v(At + idx, A);
-      ld4v(d.dGe + idx, dGe);
+      {
+        float cg[4];
+        ld4v(d.dGe + idx, dGe);
+        ld4v(d.cGe + idx, cg);      // + dY0 *7^T W_inh (b9)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) dGe[p] += cg[p];
+      }
       ld4v(Et + idx, E);
       ld4v(d.gE + idx, gE);
       if (CELL == PTK_CELL_HGRU) ld4v(d.dS + idx, dS);
@@ -673,7 +685,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1_at(t), t, 1);
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c1{d.dAct, d.w_exc_d, d.gI, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr, d.conv_mode};
+    ConvArgs c1{d.dAct, d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
@@ -689,7 +701,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0_at(t), t, 0);
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c0{d.dAct, d.w_inh_d, d.dGe, d.B, d.H, d.W, 1, nullptr, nullptr, nullptr, d.conv_mode};
+    ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
     if (rc) return rc;
     WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
@@ -719,13 +731,16 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   return PTK_OK;
 }
 
+template <int CELL>
+static int run_backward_c(const IntDev& d, int act, cudaStream_t st) {
+  const bool fast = (d.conv_mode == PTK_CONV_BF16X3);
+  if (act == PTK_ACT_SOFTPLUS) return fast ? run_backward_t<CELL, PTK_ACT_SOFTPLUS | ACT_FAST>(d, st)
+                                           : run_backward_t<CELL, PTK_ACT_SOFTPLUS>(d, st);
+  return fast ? run_backward_t<CELL, PTK_ACT_TANH | ACT_FAST>(d, st) : run_backward_t<CELL, PTK_ACT_TANH>(d, st);
+}
+
 int run_int_backward(const IntDev& d, int cell, int act, cudaStream_t st) {
-  if (cell == PTK_CELL_INT) {
-    if (act == PTK_ACT_SOFTPLUS) return run_backward_t<PTK_CELL_INT, PTK_ACT_SOFTPLUS>(d, st);
-    return run_backward_t<PTK_CELL_INT, PTK_ACT_TANH>(d, st);
-  }
-  if (act == PTK_ACT_SOFTPLUS) return run_backward_t<PTK_CELL_HGRU, PTK_ACT_SOFTPLUS>(d, st);
-  return run_backward_t<PTK_CELL_HGRU, PTK_ACT_TANH>(d, st);
+  return cell == PTK_CELL_INT ? run_backward_c<PTK_CELL_INT>(d, act, st) : run_backward_c<PTK_CELL_HGRU>(d, act, st);
 }
 
 }  // namespace ptk

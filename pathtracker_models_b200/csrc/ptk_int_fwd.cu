@@ -55,7 +55,7 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
     tile_ld(sE, L, o, e);
     tile_ld(sX, L, o, a);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) { a[p] = sigmoidf_(a[p]); ge[p] = a[p] * e[p]; }
+    for (int p = 0; p < 4; ++p) { a[p] = sigm<ACT>(a[p]); ge[p] = a[p] * e[p]; }
     st4(Aout + (size_t)(L.oc0 + o) * P, a);
     st4(Geout + (size_t)(L.oc0 + o) * P, ge);
   }
@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
       ld4v(Y0 + idx, y0);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        gi[p] = sigmoidf_(gi[p]);
-        gx[p] = sigmoidf_(gx[p]);
+        gi[p] = sigm<ACT>(gi[p]);
+        gx[p] = sigm<ACT>(gx[p]);
         const float U = fmaf(y0[p], sScale[c], sShift[c]);
         const float Pp = U * fmaf(sAl[c], S[p], sMu[c]);
         const float Q = actf<ACT>(Pp);
@@ -374,8 +374,10 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
 }
 
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st) {
-  if (act == PTK_ACT_SOFTPLUS) return run_forward_act<PTK_ACT_SOFTPLUS>(d, cell, st);
-  return run_forward_act<PTK_ACT_TANH>(d, cell, st);
+  const bool fast = (d.conv_mode == PTK_CONV_BF16X3);
+  if (act == PTK_ACT_SOFTPLUS) return fast ? run_forward_act<PTK_ACT_SOFTPLUS | ACT_FAST>(d, cell, st)
+                                           : run_forward_act<PTK_ACT_SOFTPLUS>(d, cell, st);
+  return fast ? run_forward_act<PTK_ACT_TANH | ACT_FAST>(d, cell, st) : run_forward_act<PTK_ACT_TANH>(d, cell, st);
 }
 
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,
