@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   __shared__ double sFin[8][C][3];
   __shared__ int sIsLast;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform => uniform branches / registers
   const int x0 = blockIdx.x * TC_TW, y0 = blockIdx.y * TC_TH, b = blockIdx.z;
   const int H = a.H, W = a.W;
 
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
       mbar_expect_tx(&full[st], TC_STAGE);
       bulk_g2s(sWr + st * TC_STAGE, wsrc + (size_t)ky * TC_STAGE, TC_STAGE, &full[st]);
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // descriptors differ only in the 14-bit start-address field of the low word: precompute the
     // per-(operand, k-step) bases and add the pixel offset per instruction (1 IADD per MMA).
     const uint32_t aHi = smem_u32(sA), aLo = aHi + 4 * TC_PLANE, wBase = smem_u32(sWr);
@@ -181,14 +182,17 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
             const uint32_t po = poff + (uint32_t)(j * 128);
             const uint64_t dB = ((uint64_t)bHiW << 32) | (bW + (uint32_t)(2 * s) * (1024 >> 4));
             const uint32_t dcol = tmem_base + (uint32_t)(j * 64);
-            umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (ky | kx | s) ? 1u : 0u);
-            umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+            if (elect_one()) {
+              umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (ky | kx | s) ? 1u : 0u);
+              umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+            }
           }
         }
       }
-      umma_commit(&empty[st]);   // frees this ring slot once the MMAs above have read it
+      __syncwarp();
+      if (elect_one()) umma_commit(&empty[st]);   // frees this ring slot once the MMAs above have read it
     }
-    umma_commit(accum_bar);
+    if (elect_one()) umma_commit(accum_bar);
   }
   __syncwarp();
 

@@ -89,6 +89,18 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloa
   l = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+// one elected lane of a fully converged warp (the warp-uniform way to issue single-thread tcgen05 ops:
+// with divergent `if (lane == 0)` code ptxas wraps every UTCHMMA in an R2UR.BROADCAST waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // mbarrier arrive (count 1) by the calling thread
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -24,9 +24,9 @@ namespace ptk {
 constexpr int WT_TH = 16, WT_TW = 32, WT_WP = 38, WT_ROWS = 22;
 constexpr int WT_KPIX = WT_TH * WT_WP;               // 608 pixels = 38 K-steps of 16
 constexpr int WT_KSTEPS = WT_KPIX / 16;
-constexpr int WT_DY_PLANE = WT_KPIX * 16;            // 9728 B
+constexpr int WT_DY_PLANE = WT_KPIX * 16 + 16;       // 9744 B: +16 so the 8 channel-chunk planes of one K row hit 8 different bank groups
 constexpr int WT_IN_NPIX = 880;                      // >= 608 + 6*38 + 6
-constexpr int WT_IN_PLANE = WT_IN_NPIX * 16;         // 14080 B
+constexpr int WT_IN_PLANE = WT_IN_NPIX * 16 + 16;    // 14096 B (same reason)
 constexpr int WT_DY_BYTES = 8 * WT_DY_PLANE;         // hi chunks 0-3, lo chunks 4-7
 constexpr int WT_IN_BYTES = 8 * WT_IN_PLANE;
 constexpr int WT_RT = 4;                             // taps per round
@@ -94,6 +94,9 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
   }
 }
 
+__device__ long long g_wt_dbg[8];
+#define WT_STAMP(i, t) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == (t)) g_wt_dbg[i] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sDY = smem_raw;                                  // [8 planes][608 px][16 B]
@@ -104,11 +107,13 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   uint64_t* tempty = bars + 2;   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform => uniform branches / registers
   const int x0 = blockIdx.x * WT_TW, y0 = blockIdx.y * WT_TH, b = blockIdx.z;
   const int H = a.H, W = a.W;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 
+  WT_STAMP(0, 0);
   if (tid == 0) {
     mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
     mbar_init(&tempty[0], 128); mbar_init(&tempty[1], 128);
@@ -120,6 +125,7 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   }
   for (int i = tid; i < (WT_DY_BYTES + WT_IN_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  WT_STAMP(1, 0);
   // dY tile: 16 rows, interior columns only (pad columns stay zero => contribute nothing)
   wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, b, y0, WT_TH, x0, H, W, 0, false);
   // In tile: 22 rows with the 3-pixel halo, interior at padded column 3
@@ -129,9 +135,10 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  WT_STAMP(2, 0);
 
-  if (warp == 0 && lane == 0) {
-    // ---- MMA issuer ------------------------------------------------------------------------------
+  if (warp == 0) {
+    // ---- MMA issuer (whole warp converged; one elected lane issues) ------------------------------------------------------------------------------
     // MN-major no-swizzle descriptors: LBO = stride between 8-pixel K groups (128 B), SBO = plane stride
     const uint64_t dA0 = umma_desc(smem_u32(sDY), 128, WT_DY_PLANE);
     const uint64_t dB0 = umma_desc(smem_u32(sIN), 128, WT_IN_PLANE);
@@ -151,11 +158,13 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
         for (int ks = 0; ks < WT_KSTEPS; ++ks) {
           const uint64_t dA = ((uint64_t)aHiW << 32) | (aLoW + (uint32_t)(ks * 16));
           const uint64_t dB = ((uint64_t)bHiW << 32) | (bOff + (uint32_t)(ks * 16));
-          umma_bf16(dcol, dA, dB, IDESC, ks ? 1u : 0u);
+          if (elect_one()) umma_bf16(dcol, dA, dB, IDESC, ks ? 1u : 0u);
         }
       }
-      umma_commit(&tfull[buf]);
+      __syncwarp();
+      if (elect_one()) umma_commit(&tfull[buf]);
     }
+    WT_STAMP(3, 0);
   } else if (warp >= 4) {
     // ---- epilogue warps: drain a round, combine the four split products, add into the CTA's slot ----
     const int quad = warp & 3, et = tid - 128;
@@ -208,9 +217,15 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
       named_bar_sync(1, 128);
     }
   }
+  WT_STAMP(4, 128);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+int read_wt_debug(long long* out) {
+  PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_wt_dbg, sizeof(long long) * 8));
+  return PTK_OK;
 }
 
 size_t wgrad_tc_acc_floats(int B, int H, int W) { return (size_t)B * (H / WT_TH) * (W / WT_TW) * TAPS * C * C; }
