@@ -62,9 +62,9 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   float* ring_stats = cv.take<float>(4 * C);
   float* bn_part = cv.take<float>((size_t)conv_num_ctas(dm->B, dm->H, dm->W) * C * 2);
   unsigned* counter = cv.take<unsigned>(4);
-  float* acc = cv.take<float>((size_t)pw * ACC_N);
+  float* acc = cv.take<float>((size_t)PW_EW_CTAS * ACC_N);
   float* gacc = cv.take<float>((size_t)GATE_CTAS * GACC_N);
-  float* bn_sums = cv.take<float>((size_t)pw * 2 * C);
+  float* bn_sums = cv.take<float>((size_t)PW_EW_CTAS * 2 * C);
   float* bn_tot = cv.take<float>(2 * C);
   double* bn_acc = cv.take<double>(4 * C);
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);

@@ -19,7 +19,8 @@ enum {
 constexpr int HEAD_N = 96;        // per-sample readout-head partials (86 used), see int_readout_bwd_kernel
 constexpr int WGRAD_GROUPS = 37;  // 4 ic-chunks x 37 groups = 148 CTAs (one per SM)
 constexpr int GATE_CTAS = 148;    // gate weight-gradient kernel: one persistent CTA per SM
-constexpr int PW_MAX_CTAS = 148 * 3;
+constexpr int PW_MAX_CTAS = 148 * 3;   // grid of the gate-product kernels (smem-limited to 3 CTAs/SM)
+constexpr int PW_EW_CTAS = 148 * 4;    // grid of the purely element-wise bwd_a kernel; also the number of accumulator slots
 
 struct IntDev {
   int B, T, H, W;

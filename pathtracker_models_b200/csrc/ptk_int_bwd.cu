@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int fir
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
-#pragma unroll 1
+#pragma unroll 2
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
@@ -659,7 +659,9 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int grid = d.pw_ctas;
   const int grid_c = grid;
   const bool tc = (d.conv_mode == PTK_CONV_BF16X3);
-  PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)grid * ACC_N * sizeof(float), st));
+  const int nWT = d.B * P / WPX;
+  const int grid_a = (nWT + 3) / 4 < PW_EW_CTAS ? (nWT + 3) / 4 : PW_EW_CTAS;
+  PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)PW_EW_CTAS * ACC_N * sizeof(float), st));
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
@@ -677,7 +679,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     int rc;
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      int_bwd_a_kernel<ACT><<<grid, 128, 0, st>>>(d, t, first);
+      int_bwd_a_kernel<ACT><<<grid_a, 128, 0, st>>>(d, t, first);
     }
     PTK_LAUNCH_OK("int_bwd_a_kernel");
     {
@@ -719,7 +721,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     PTK_LAUNCH_OK("gate_wgrad_kernel");
   }
   FinalizeArgs f;
-  f.pw_ctas = grid; f.gate_ctas = gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
+  f.pw_ctas = PW_EW_CTAS; f.gate_ctas = gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
   f.wgrad_tc = tc ? conv_num_ctas(d.B, d.H, d.W) : 0;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
