@@ -123,7 +123,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
-    from pathtracker_models_b200 import InT, _lib, synth_pathtracker
+    from pathtracker_models_b200 import InT, _lib, ffhgru_hierarchy, synth_pathtracker
     from pathtracker_models_b200.parallel import attach_data_parallel, broadcast_parameters, shard_first_index
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -136,10 +136,14 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    B = args.batch
+    B, T, HW = args.batch, args.frames, args.size      # defaults = the headline workload
+    flop_per_seq = (T * HW * HW * (2 * (2 * C * C * K * K) + 6 * (2 * C * C) + 2 * 3 * C) + HW * HW * (2 * C + 100)
+                    + 2 * T * HW * HW * (2 * (2 * C * C * K * K) + 6 * (2 * C * C)) + T * HW * HW * 6 * C
+                    + 2 * HW * HW * (2 * C + 100))
 
     torch.manual_seed(0)
-    model = InT.InT(dimensions=C, timesteps=T, kernel_size=K).to(dev)
+    ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
+    model = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev)
     model.conv_mode = _lib.PTK_CONV_BF16X3 if args.conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
     if world > 1:
         broadcast_parameters(model)
@@ -228,9 +232,11 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "InT 64 frames 32x32, 14 distractors, batch %d/GPU (BASELINE configs[1])" % B,
+            "config": {"workload": "%s %d frames %dx%d, 14 distractors, batch %d/GPU%s" % (
+                           "InT" if args.model == "int" else "FFhGRU", T, HW, HW, B,
+                           " (BASELINE configs[1])" if (args.model, T, HW, B) == ("int", 64, 32, 64) else ""),
                        "global_batch": B * world, "parallelism": "dp%d" % world, "conv_mode": args.conv_mode,
-                       "l2": "no flush: per-step working set (2.2 GB of checkpoints per GPU) exceeds the 126 MB L2; "
+                       "l2": "no flush: per-step working set (GBs of checkpoints per GPU) exceeds the 126 MB L2; "
                              "%d distinct input batches rotate" % nbuf},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 4),
                     "d2h_bytes_per_step": 4},
@@ -246,8 +252,8 @@ def run_b200(args):
                                   "is 1/3 of the bf16 peak (frac_of_third_peak)" if args.conv_mode == "bf16x3" else
                                   "strict-fp32 CUDA-core conv: its own pipe peaks at 74.4 TFLOP/s nominal"),
                          "frac_of_third_peak": (3 * achieved / tensor_peak) if achieved else None,
-                         "step_tflops": value / world * FLOP_PER_SEQ / 1e12,
-                         "step_frac_of_tensor_peak": value / world * FLOP_PER_SEQ / 1e12 / tensor_peak,
+                         "step_tflops": value / world * flop_per_seq / 1e12,
+                         "step_frac_of_tensor_peak": value / world * flop_per_seq / 1e12 / tensor_peak,
                          "kernel_time_share": shares,
                          "measured": "second pass of the same %d steps with per-kernel CUDA events (%.2f ms/step "
                                      "instrumented vs %.2f ms/step plain)" % (steps, ms_prof / steps, ms_total / steps)},
@@ -268,6 +274,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="int", choices=["int", "hgru"], help="non-headline configs (BASELINE configs[2..3])")
+    ap.add_argument("--frames", type=int, default=T)
+    ap.add_argument("--size", type=int, default=HW)
     ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3"],
                     help="7x7 convolutions: strict-fp32 FFMA, or 3-pass split-bf16 tcgen05 (both parity-gated)")
     args = ap.parse_args()

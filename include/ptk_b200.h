@@ -117,6 +117,27 @@ PTK_API int ptk_synth_pathtracker(uint64_t seed, uint64_t first_index, int32_t B
                           int32_t W, int32_t n_distractors, int32_t speed, float* x, float* y,
                           void* stream);
 
+/* ---- ConvLSTM baseline (models/convlstm.py) --------------------------------------------------------------
+ * Flat parameter vector in the reference's state_dict order: conv0.{weight[25,1,7,7],bias}, then for each gate
+ * k in (i,f,c,o): unit1.Wx<k>.{weight[25,25,K,K],bias[25]}, unit1.Wh<k>.weight[25,25,K,K]; bn.{weight,bias}[25];
+ * conv6.{weight[2,25,1,1],bias[2]}.  ptk_convlstm_param_offsets fills 19 entries (18 tensors + total). */
+typedef struct PtkLstmDims {
+  int32_t B, T, H, W;  /* x is [B,1,H,W]; T = timesteps (models/convlstm.py:138 loops self.timesteps) */
+  int32_t K;           /* filt_size: 15 (default, models/convlstm.py:95) or 7                         */
+} PtkLstmDims;
+PTK_API int ptk_convlstm_param_offsets(const PtkLstmDims* d, int64_t* offsets);
+PTK_API size_t ptk_convlstm_saved_bytes(const PtkLstmDims* d);
+PTK_API size_t ptk_convlstm_workspace_bytes(const PtkLstmDims* d);
+/* ConvLSTM.forward up to `output = conv6(bn(h_T))` (models/convlstm.py:116-147, bptt branch); the criterion
+ * (:148) stays with the caller.  penalty: optional [B,25,H,W] out, the Jacobian penalty of :152-163
+ * (training mode, create_graph=False); needs T >= 2.  saved: ptk_convlstm_saved_bytes, always required. */
+PTK_API int ptk_convlstm_forward(const PtkLstmDims* d, const float* x, const float* params, float* output,
+                                 float* penalty, void* saved, void* workspace, size_t workspace_bytes, void* stream);
+/* BPTT: doutput [B,2,H,W] -> dparams (flat, overwritten). */
+PTK_API int ptk_convlstm_backward(const PtkLstmDims* d, const float* x, const float* params, const void* saved,
+                                  const float* doutput, float* dparams, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
 /* One horizontal-connection convolution on its own (test / measurement entry; the time loop calls the
  * same kernels internally): out (+)= conv2d(in, weight, padding=3) (transpose=0, models/InT.py:161,172)
  * or conv_transpose2d(in, weight, padding=3) (transpose=1, its data gradient).  in/out [B,32,H,W],
@@ -135,6 +156,9 @@ PTK_API int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_
 PTK_API void ptk_profile_start(void);
 PTK_API int ptk_profile_stop(double* ms, long long* count);
 PTK_API long long ptk_launch_count(void);
+/* tuning aids: in-kernel cycle stamps of CTA 0 of the last tcgen05 conv / weight-gradient launch */
+PTK_API int ptk_debug_tc_stamps(long long* out);
+PTK_API int ptk_debug_wt_stamps(long long* out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,84 @@
+"""CPU oracle for the ConvLSTM baseline (models/convlstm.py).  TEST INFRASTRUCTURE ONLY.
+
+Restates ConvLSTMCell.forward (models/convlstm.py:84-90) and ConvLSTM.forward (:116-173, bptt branch):
+Gabor stem conv0 -> square, T cell steps on the time-invariant input, batch-stat BatchNorm + 1x1 conv head,
+and the two vector-Jacobian products of the Jacobian penalty (:152-163).  The input-path convolutions
+Wx*(x) + b are hoisted out of the time loop (the reference recomputes them every step; identical values).
+
+Pinned against outputs of the reference itself: oracle/gen_golden.py -> tests/golden/convlstm_*.npz.
+"""
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3
+GATES = ("i", "f", "c", "o")   # stacking order of the 4 x 25 gate channels used by the CUDA path
+
+
+def unpack(sd, dtype=torch.float64):
+    g = lambda k: sd[k].detach().to(dtype).clone()
+    p = {"w0": g("conv0.weight"), "b0": g("conv0.bias"), "bn_w": g("bn.weight"), "bn_b": g("bn.bias"),
+         "w6": g("conv6.weight"), "b6": g("conv6.bias")}
+    for k in GATES:
+        p["wx" + k] = g(f"unit1.Wx{k}.weight")
+        p["bx" + k] = g(f"unit1.Wx{k}.bias")
+        p["wh" + k] = g(f"unit1.Wh{k}.weight")
+    return p
+
+
+def cell(Xg, h, c, p, pad):
+    """Xg: dict of hoisted input terms; returns h', c' and the gate activations."""
+    i = torch.sigmoid(Xg["i"] + F.conv2d(h, p["whi"], padding=pad))      # convlstm.py:85
+    f = torch.sigmoid(Xg["f"] + F.conv2d(h, p["whf"], padding=pad))      # :86
+    g = torch.tanh(Xg["c"] + F.conv2d(h, p["whc"], padding=pad))         # :87
+    c2 = f * c + i * g
+    o = torch.sigmoid(Xg["o"] + F.conv2d(h, p["who"], padding=pad))      # :88
+    h2 = o * torch.tanh(c2)                                              # :89
+    return h2, c2, (i, f, g, o)
+
+
+def forward(x, p, timesteps, keep=False):
+    """x [B,1,H,W] -> (output [B,2,H,W], saved)."""
+    pad = p["whi"].shape[-1] // 2
+    xt = F.conv2d(x, p["w0"], p["b0"], padding=p["w0"].shape[-1] // 2) ** 2      # :118-119
+    Xg = {k: F.conv2d(xt, p["wx" + k], p["bx" + k], padding=pad) for k in GATES}
+    h = torch.zeros_like(xt)
+    c = torch.zeros_like(xt)
+    saved = {"h": [h], "c": [c], "gates": [], "xt": xt}
+    for _ in range(timesteps):
+        h, c, gates = cell(Xg, h, c, p, pad)
+        if keep:
+            saved["h"].append(h); saved["c"].append(c); saved["gates"].append(gates)
+    saved["h_last"], saved["c_last"] = h, c
+    mean = h.mean(dim=(0, 2, 3))
+    var = ((h - mean.view(1, -1, 1, 1)) ** 2).mean(dim=(0, 2, 3))
+    hn = (h - mean.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + BN_EPS)
+    hn = hn * p["bn_w"].view(1, -1, 1, 1) + p["bn_b"].view(1, -1, 1, 1)             # :146
+    out = F.conv2d(hn, p["w6"], p["b6"])                                             # :147
+    return out, saved
+
+
+def jv_penalty(x, p, timesteps):
+    """(1^T dh_T/dh_{T-1} - 0.9)+^2 + (1^T dc_T/dc_{T-1} - 0.9)+^2   (convlstm.py:152-163, no graph kept).
+
+    As in the reference, h_{T-1} and c_{T-1} are the live graph tensors, so the second product also
+    contains the path c_{T-1} -> h_{T-1} = o tanh(c_{T-1}) -> gates_T -> c_T, not only f_T."""
+    pad = p["whi"].shape[-1] // 2
+    xt = F.conv2d(x, p["w0"], p["b0"], padding=p["w0"].shape[-1] // 2) ** 2
+    Xg = {k: F.conv2d(xt, p["wx" + k], p["bx" + k], padding=pad) for k in GATES}
+    h = torch.zeros_like(xt).requires_grad_(True)      # T == 1 is an error in the reference (needs T >= 2)
+    c = torch.zeros_like(xt).requires_grad_(True)
+    for _ in range(timesteps - 1):
+        h, c, _ = cell(Xg, h, c, p, pad)
+    h2, c2, _ = cell(Xg, h, c, p, pad)
+    ones = torch.ones_like(h2)
+    jh = torch.autograd.grad(h2, h, grad_outputs=ones, retain_graph=True)[0]
+    jc = torch.autograd.grad(c2, c, grad_outputs=ones)[0]
+    return ((jh - 0.9).clamp(0) ** 2 + (jc - 0.9).clamp(0) ** 2).detach()
+
+
+STATE_KEYS = {"w0": "conv0.weight", "b0": "conv0.bias", "bn_w": "bn.weight", "bn_b": "bn.bias",
+              "w6": "conv6.weight", "b6": "conv6.bias"}
+for _k in GATES:
+    STATE_KEYS["wx" + _k] = f"unit1.Wx{_k}.weight"
+    STATE_KEYS["bx" + _k] = f"unit1.Wx{_k}.bias"
+    STATE_KEYS["wh" + _k] = f"unit1.Wh{_k}.weight"

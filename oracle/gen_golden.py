@@ -133,5 +133,88 @@ def main():
                         init_keys=np.array(list(h.state_dict().keys())))
 
 
+def convlstm_weights(sd_like, seed):
+    """deterministic, fp32-representable weights for the ConvLSTM fixtures (numpy recipe, so that the
+    large filt_size=15 case does not have to store 1.1 M parameters)."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for k, v in sd_like.items():
+        shape = tuple(v.shape)
+        if k.endswith("Wxi.weight") or "unit1.W" in k and k.endswith("weight"):
+            fan = shape[1] * shape[2] * shape[3]
+            a = rs.normal(0, 1.0 / np.sqrt(fan), shape)
+        elif k == "conv0.weight":
+            a = v.numpy() + rs.normal(0, 0.02, shape)          # the Gabor bank, perturbed
+        elif k == "bn.weight":
+            a = 1.0 + rs.normal(0, 0.1, shape)
+        elif k == "conv6.weight":
+            a = rs.normal(0, 0.3, shape)
+        elif k == "conv6.bias":
+            a = rs.normal(0, 0.5, shape)
+        else:
+            a = rs.normal(0, 0.1, shape)
+        out[k] = torch.from_numpy(a.astype(np.float32))
+    return out
+
+
+def run_convlstm_case(name, filt, B, T, H, W, seed, store_full):
+    cwd = os.getcwd()
+    os.chdir(REF)                                   # ConvLSTM.__init__ loads 'utils/gabor_serre.npy' (convlstm.py:105)
+    from models import convlstm as RC
+    rs = np.random.RandomState(seed)
+    x_np = rs.rand(B, 1, H, W)
+    tgt_np = (rs.rand(B, H, W) > 0.5).astype(np.int64)
+    res = {"x_seed": seed, "shape": np.array([B, T, H, W]), "filt": np.array(filt)}
+    torch.set_default_dtype(torch.float32)
+    m0 = RC.ConvLSTM(timesteps=T, filt_size=filt)
+    sd32 = convlstm_weights(m0.state_dict(), seed + 1)
+    grads = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        torch.set_default_dtype(dt)
+        m = RC.ConvLSTM(timesteps=T, filt_size=filt).to(dt)
+        m.load_state_dict({k: v.to(dt) for k, v in sd32.items()})
+        m.train()
+        x = torch.from_numpy(x_np).to(dt)
+        tgt = torch.from_numpy(tgt_np)
+        out, pen, loss = m(x, 0, 0, tgt, torch.nn.CrossEntropyLoss())
+        loss.backward()
+        grads[tag] = {n: prm.grad.detach().double() for n, prm in m.named_parameters()}
+        grads[tag]["__output__"] = out.detach().double()
+        grads[tag]["__penalty__"] = pen.detach().double()
+        if tag == "f64":
+            res["output"] = out.detach().numpy()
+            res["loss"] = np.array(loss.item())
+            res["penalty"] = pen.detach().numpy()
+            prs = np.random.RandomState(seed + 2)
+            for n, gr in grads[tag].items():
+                if n.startswith("__"):
+                    continue
+                if store_full:
+                    res["grad/" + n] = gr.numpy().astype(np.float32 if gr.numel() > 4096 else np.float64)
+                else:   # compact pin: 4 seeded random projections + max-abs
+                    v = prs.normal(0, 1, (4, gr.numel()))
+                    res["proj/" + n] = v @ gr.numpy().ravel()
+                    res["gmax/" + n] = np.array(gr.abs().max().item())
+    for n, g64 in grads["f64"].items():
+        e = (grads["f32"][n] - g64).abs().max().item() / max(g64.abs().max().item(), 1e-300)
+        res["f32err/" + n] = np.array(e)
+    if store_full:
+        for k, v in sd32.items():
+            res["sd/" + k] = v.numpy()
+    res["wseed"] = np.array(seed + 1)
+    res["gabor"] = m0.state_dict()["conv0.weight"].numpy()       # the reference's Gabor bank (data fixture, 4.9 KB)
+    torch.set_default_dtype(torch.float32)
+    os.chdir(cwd)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
+    worst = max((float(v), k) for k, v in res.items() if k.startswith("f32err/"))
+    print(name, "loss", res["loss"], "penalty max", res["penalty"].max(), "worst fp32-vs-fp64", worst)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "convlstm":
+        load_reference()
+        run_convlstm_case("convlstm_k7_small", 7, 2, 3, 32, 32, seed=31, store_full=True)
+        run_convlstm_case("convlstm_k15_small", 15, 2, 3, 32, 32, seed=32, store_full=False)
+        run_convlstm_case("convlstm_k15_b3", 15, 3, 4, 32, 32, seed=33, store_full=False)
+    else:
+        main()

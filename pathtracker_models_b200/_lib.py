@@ -16,12 +16,18 @@ PTK_INT_NPARAM = 30
 
 EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_saved_bytes",
            "ptk_int_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker",
-           "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes")
+           "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes",
+           "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
+           "ptk_convlstm_forward", "ptk_convlstm_backward", "ptk_debug_tc_stamps", "ptk_debug_wt_stamps")
 
 
 class PtkDims(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("B", "T", "H", "W", "C", "K", "cell", "act", "no_inh", "conv_mode")]
+
+
+class PtkLstmDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K")]
 
 
 class PtkError(RuntimeError):
@@ -64,6 +70,17 @@ def lib():
     L.ptk_conv7_workspace_bytes.argtypes = [i32, i32, i32]
     L.ptk_conv7.restype = ctypes.c_int
     L.ptk_conv7.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    ldp = ctypes.POINTER(PtkLstmDims)
+    L.ptk_convlstm_param_offsets.restype = ctypes.c_int
+    L.ptk_convlstm_param_offsets.argtypes = [ldp, i64p]
+    L.ptk_convlstm_saved_bytes.restype = sz
+    L.ptk_convlstm_saved_bytes.argtypes = [ldp]
+    L.ptk_convlstm_workspace_bytes.restype = sz
+    L.ptk_convlstm_workspace_bytes.argtypes = [ldp]
+    L.ptk_convlstm_forward.restype = ctypes.c_int
+    L.ptk_convlstm_forward.argtypes = [ldp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ptk_convlstm_backward.restype = ctypes.c_int
+    L.ptk_convlstm_backward.argtypes = [ldp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_profile_start.restype = None
     L.ptk_profile_start.argtypes = []
     L.ptk_profile_stop.restype = ctypes.c_int

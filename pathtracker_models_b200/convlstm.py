@@ -1,0 +1,126 @@
+"""Drop-in for models/convlstm.py of the reference (ConvLSTMCell :57-90, ConvLSTM :93-173): same
+constructors, parameter names and forward(x, epoch, itr, target, criterion, testmode) contract; the
+Gabor stem, the T cell steps, the BatchNorm + 1x1 head, BPTT and the Jacobian penalty run in
+libptk_b200 (ptk_convlstm_forward / ptk_convlstm_backward)."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd.function import once_differentiable
+from torch.nn import init
+
+from . import _lib
+from .functional import _ptr
+
+
+class ConvLSTMCell(nn.Module):
+    """parameter container of the cell (models/convlstm.py:57-82); executed inside the CUDA time loop."""
+
+    def __init__(self, input_channels, hidden_channels, kernel_size):
+        super().__init__()
+        self.input_channels, self.hidden_channels, self.kernel_size = input_channels, hidden_channels, kernel_size
+        self.num_features = 4
+        self.padding = int((kernel_size - 1) / 2)
+        for g in "ifco":            # registration (and RNG) order of the reference: Wx<g> then Wh<g>
+            setattr(self, "Wx" + g, nn.Conv2d(input_channels, hidden_channels, kernel_size, 1, self.padding, bias=True))
+            setattr(self, "Wh" + g, nn.Conv2d(hidden_channels, hidden_channels, kernel_size, 1, self.padding, bias=False))
+        self.Wci = self.Wcf = self.Wco = None
+
+    def forward(self, *a, **k):
+        raise RuntimeError("the cell is executed inside the fused CUDA time loop; call the model, not the cell")
+
+
+def _find_gabor(gabor, gabor_path):
+    if gabor is not None:
+        return torch.as_tensor(gabor, dtype=torch.float32)
+    for cand in (gabor_path, os.environ.get("PTK_GABOR_PATH"), "utils/gabor_serre.npy"):   # convlstm.py:105
+        if cand and os.path.exists(cand):
+            return torch.from_numpy(np.load(cand)).float()
+    raise FileNotFoundError("ConvLSTM needs the Gabor bank 'utils/gabor_serre.npy' (models/convlstm.py:105): run from "
+                            "the reference root, set PTK_GABOR_PATH, or pass gabor=/gabor_path=")
+
+
+class _ConvLSTMFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, flat, dims, want_penalty):
+        L = _lib.lib()
+        B, _, H, W = x.shape
+        flat = flat.contiguous()
+        x = x.contiguous()
+        with torch.cuda.device(x.device):
+            ws_bytes = L.ptk_convlstm_workspace_bytes(ctypes.byref(dims))
+            sv_bytes = L.ptk_convlstm_saved_bytes(ctypes.byref(dims))
+            if ws_bytes == 0 or sv_bytes == 0:
+                _lib.check(1, "ptk_convlstm_workspace_bytes")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            saved = torch.empty(sv_bytes, dtype=torch.uint8, device=x.device)
+            out = torch.empty(B, 2, H, W, dtype=torch.float32, device=x.device)
+            pen = torch.empty(B, 25, H, W, dtype=torch.float32, device=x.device) if want_penalty else None
+            stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            rc = L.ptk_convlstm_forward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(out), _ptr(pen), _ptr(saved),
+                                        _ptr(ws), ws_bytes, stream)
+            _lib.check(rc, "ptk_convlstm_forward")
+        ctx.dims, ctx.saved_buf = dims, saved
+        ctx.save_for_backward(x, flat)
+        if pen is None:
+            pen = torch.ones(1, dtype=torch.float32, device=x.device)    # convlstm.py:151 placeholder
+        ctx.mark_non_differentiable(pen)
+        return out, pen
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, _dpen):
+        x, flat = ctx.saved_tensors
+        L = _lib.lib()
+        dims = ctx.dims
+        with torch.cuda.device(x.device):
+            ws_bytes = L.ptk_convlstm_workspace_bytes(ctypes.byref(dims))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            dflat = torch.empty_like(flat)
+            dout = dout.contiguous().float()
+            stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            rc = L.ptk_convlstm_backward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
+                                         _ptr(dflat), _ptr(ws), ws_bytes, stream)
+            _lib.check(rc, "ptk_convlstm_backward")
+        ctx.saved_buf = None
+        return None, dflat, None, None
+
+
+class ConvLSTM(nn.Module):
+    """models/convlstm.py:93-173 (bptt branch)."""
+
+    def __init__(self, timesteps=8, filt_size=15, num_iter=50, exp_name='exp1', jacobian_penalty=False,
+                 grad_method='bptt', gabor=None, gabor_path=None):
+        super().__init__()
+        self.timesteps, self.num_iter, self.exp_name = timesteps, num_iter, exp_name
+        self.jacobian_penalty, self.grad_method = jacobian_penalty, grad_method
+        if grad_method != 'bptt':
+            raise NotImplementedError("grad_method='rbp' (models/convlstm.py:124-135) is not built yet")
+        if jacobian_penalty:
+            raise NotImplementedError("jacobian_penalty=True needs a second-order graph; only the value is computed")
+        self.conv0 = nn.Conv2d(1, 25, kernel_size=7, padding=3)
+        self.conv0.weight.data = _find_gabor(gabor, gabor_path).reshape(25, 1, 7, 7).clone()
+        self.unit1 = ConvLSTMCell(25, 25, filt_size)
+        self.bn = nn.BatchNorm2d(25, eps=1e-03, track_running_stats=False)
+        self.conv6 = nn.Conv2d(25, 2, kernel_size=1)
+        init.xavier_normal_(self.conv6.weight)
+        init.constant_(self.conv6.bias, math.log((1 - 0.01) / 0.01))
+
+    def flat_parameters(self):
+        return torch.cat([p.reshape(-1) for p in self.parameters()])   # registration order == C ABI order
+
+    def forward(self, x, epoch, itr, target, criterion, testmode=False):
+        if not x.is_cuda:
+            raise _lib.PtkError("pathtracker_models_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        B, ch, H, W = x.shape
+        if ch != 1:
+            raise ValueError(f"expected x of shape [B,1,H,W], got {tuple(x.shape)}")
+        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size)
+        output, pen = _ConvLSTMFunction.apply(x.float(), self.flat_parameters(), dims, bool(self.training))
+        loss = criterion(output, target)                                # convlstm.py:148
+        if testmode:
+            return output, [], loss                                      # bptt branch never fills `states`
+        return output, pen, loss

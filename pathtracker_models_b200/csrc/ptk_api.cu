@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "ptk_common.cuh"
+#include "ptk_convlstm.h"
 #include "ptk_int.h"
 
 namespace ptk {
@@ -267,6 +268,130 @@ size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
   cv.take<float>((size_t)conv_num_ctas(B, H, W) * C * 2);
   cv.take<unsigned>(4);
   return (cv.off + 255) & ~(size_t)255;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// ConvLSTM (models/convlstm.py)
+static int lstm_check(const PtkLstmDims* d, const char* who) {
+  if (!d) { set_error("%s: dims is NULL", who); return PTK_EINVAL; }
+  if (d->K != 7 && d->K != 15) { set_error("%s: filt_size %d not built (7 and 15 are)", who, d->K); return PTK_EUNSUPPORTED; }
+  if (d->B < 1 || d->T < 1 || d->H < 16 || d->W < 32 || d->H % 16 || d->W % 32) {
+    set_error("%s: unsupported shape B=%d T=%d H=%d W=%d", who, d->B, d->T, d->H, d->W);
+    return PTK_EINVAL;
+  }
+  return PTK_OK;
+}
+static void lstm_offsets(int K, int64_t* o) {   // conv0.w, conv0.b, 4 x (Wx.w, Wx.b, Wh.w), bn.w, bn.b, conv6.w, conv6.b
+  const int64_t n = (int64_t)25 * 25 * K * K;
+  int i = 0;
+  int64_t a = 0;
+  o[i++] = a; a += 25 * 49;
+  o[i++] = a; a += 25;
+  for (int k = 0; k < 4; ++k) { o[i++] = a; a += n; o[i++] = a; a += 25; o[i++] = a; a += n; }
+  o[i++] = a; a += 25;
+  o[i++] = a; a += 25;
+  o[i++] = a; a += 50;
+  o[i++] = a; a += 2;
+  o[i] = a;
+}
+static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* d, size_t* saved_bytes) {
+  const size_t P = (size_t)dm->H * dm->W, S = (size_t)dm->B * 25 * P, SG = 4 * S, taps = (size_t)dm->K * dm->K;
+  const int groups = 3;
+  Carver sv(saved);
+  float* hs = sv.take<float>((size_t)(dm->T + 1) * S);
+  float* cs = sv.take<float>((size_t)(dm->T + 1) * S);
+  float* gates = sv.take<float>((size_t)dm->T * SG);
+  float* u = sv.take<float>(S);
+  float* xt = sv.take<float>(S);
+  float* hstats = sv.take<float>(64);
+  if (saved_bytes) *saved_bytes = (sv.off + 255) & ~(size_t)255;
+  Carver cv(ws);
+  float* w0T = cv.take<float>(49 * 32);
+  float* wxT = cv.take<float>(3200 * taps);
+  float* whT = cv.take<float>(3200 * taps);
+  float* whD = cv.take<float>(3200 * taps);
+  float* wxD = cv.take<float>(3200 * taps);
+  float* bx = cv.take<float>(128);
+  float* Xg = cv.take<float>(SG);
+  float* G = cv.take<float>(SG);
+  float* delta = cv.take<float>(SG);
+  float* dsum = cv.take<float>(SG);
+  float* dh = cv.take<float>(S);
+  float* dc = cv.take<float>(S);
+  float* slots_h = cv.take<float>((size_t)groups * 2500 * taps);
+  float* slots_x = cv.take<float>((size_t)groups * 2500 * taps);
+  float* slots_0 = cv.take<float>((size_t)groups * 25 * 49);
+  float* bxg = cv.take<float>(128);
+  float* b0g = cv.take<float>(32);
+  float* hg = cv.take<float>(128);
+  if (d) {
+    d->groups = groups;
+    d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;
+    d->w0T = w0T; d->wxT = wxT; d->whT = whT; d->whD = whD; d->wxD = wxD; d->bx = bx; d->Xg = Xg; d->G = G;
+    d->delta = delta; d->delta_sum = dsum; d->dh = dh; d->dc = dc; d->slots_h = slots_h; d->slots_x = slots_x;
+    d->slots_0 = slots_0; d->bx_grad = bxg; d->b0_grad = b0g; d->head_grads = hg;
+  }
+  return (cv.off + 255) & ~(size_t)255;
+}
+static int lstm_bind(LstmDev* d, const PtkLstmDims* dm, const float* x, const float* params, void* saved, void* ws,
+                     cudaStream_t st) {
+  memset(d, 0, sizeof(*d));
+  d->B = dm->B; d->T = dm->T; d->H = dm->H; d->W = dm->W; d->KS = dm->K;
+  d->x = x;
+  int64_t o[20];
+  lstm_offsets(dm->K, o);
+  d->w0 = params + o[0]; d->b0 = params + o[1];
+  for (int k = 0; k < 4; ++k) { d->wx[k] = params + o[2 + 3 * k]; d->wh[k] = params + o[4 + 3 * k]; }
+  d->bn_w = params + o[14]; d->bn_b = params + o[15]; d->w6 = params + o[16]; d->b6 = params + o[17];
+  d->off_w0 = o[0]; d->off_b0 = o[1]; d->off_wx = o[2]; d->off_bx = o[3]; d->off_wh = o[4]; d->off_head = o[14];
+  lstm_carve(dm, saved, ws, d, nullptr);
+  for (int k = 0; k < 4; ++k)   // gather the four Wx biases into one [100] vector
+    PTK_CUDA_OK(cudaMemcpyAsync((float*)d->bx + 25 * k, params + o[3 + 3 * k], 25 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PTK_OK;
+}
+
+int ptk_convlstm_param_offsets(const PtkLstmDims* d, int64_t* offsets) {
+  if (!d || !offsets) { set_error("ptk_convlstm_param_offsets: NULL argument"); return PTK_EINVAL; }
+  lstm_offsets(d->K, offsets);
+  return PTK_OK;
+}
+size_t ptk_convlstm_saved_bytes(const PtkLstmDims* d) {
+  if (lstm_check(d, "ptk_convlstm_saved_bytes")) return 0;
+  size_t sb = 0;
+  lstm_carve(d, nullptr, nullptr, nullptr, &sb);
+  return sb;
+}
+size_t ptk_convlstm_workspace_bytes(const PtkLstmDims* d) {
+  if (lstm_check(d, "ptk_convlstm_workspace_bytes")) return 0;
+  return lstm_carve(d, nullptr, nullptr, nullptr, nullptr);
+}
+int ptk_convlstm_forward(const PtkLstmDims* dm, const float* x, const float* params, float* output, float* penalty,
+                         void* saved, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = lstm_check(dm, "ptk_convlstm_forward");
+  if (rc) return rc;
+  if (!x || !params || !output || !saved || !workspace) { set_error("ptk_convlstm_forward: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_convlstm_workspace_bytes(dm)) { set_error("ptk_convlstm_forward: workspace too small"); return PTK_ENOMEM; }
+  if (penalty && dm->T < 2) { set_error("ptk_convlstm_forward: the Jacobian penalty needs timesteps >= 2 (models/convlstm.py:140-144)"); return PTK_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmDev d;
+  if ((rc = lstm_bind(&d, dm, x, params, saved, workspace, st))) return rc;
+  d.out = output; d.penalty = penalty;
+  if ((rc = run_convlstm_forward(d, st))) return rc;
+  if (penalty) rc = run_convlstm_penalty(d, st);
+  return rc;
+}
+int ptk_convlstm_backward(const PtkLstmDims* dm, const float* x, const float* params, const void* saved,
+                          const float* doutput, float* dparams, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = lstm_check(dm, "ptk_convlstm_backward");
+  if (rc) return rc;
+  if (!x || !params || !saved || !doutput || !dparams || !workspace) { set_error("ptk_convlstm_backward: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_convlstm_workspace_bytes(dm)) { set_error("ptk_convlstm_backward: workspace too small"); return PTK_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmDev d;
+  if ((rc = lstm_bind(&d, dm, x, params, const_cast<void*>(saved), workspace, st))) return rc;
+  d.dout = doutput; d.dparams = dparams;
+  return run_convlstm_backward(d, st);
 }
 
 }  // extern "C"

@@ -1,0 +1,43 @@
+// Device-side view of one ConvLSTM problem instance (models/convlstm.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ptk {
+
+struct LstmDev {
+  int B, T, H, W, KS, groups;
+  const float* x;                       // [B,1,H,W]
+  // parameters (views into the flat vector)
+  const float *w0, *b0;                 // conv0 [25,1,7,7], [25]
+  const float* wx[4];                   // Wxi, Wxf, Wxc, Wxo  [25,25,KS,KS]
+  const float* wh[4];                   // Whi, Whf, Whc, Who
+  const float* bx;                      // NOT contiguous in the flat vector: gathered copy [100] in workspace
+  const float *bn_w, *bn_b, *w6, *b6;
+  // re-laid-out weight banks (workspace)
+  float *w0T, *wxT, *whT, *whD, *wxD;
+  // checkpoints
+  float *hs, *cs;                       // [T+1][B,25,P]
+  float* gates;                         // [T][B,100,P] post-activation (i,f,g,o)
+  float *u, *xt, *Xg;                   // conv0 output, its square, hoisted input terms
+  float* head_stats;                    // [2][25]
+  // scratch
+  float *G, *delta, *delta_sum, *dh, *dc;
+  float *slots_h, *slots_x, *slots_0, *bx_grad, *b0_grad, *head_grads;
+  // I/O
+  float* out;                           // [B,2,H,W]
+  const float* dout;
+  float* penalty;                       // [B,25,H,W]
+  float* dparams;
+  long long off_w0, off_b0, off_wx, off_bx, off_wh, off_head;
+
+  __host__ __device__ float* h_at(int t) const { return hs + (size_t)t * B * 25 * H * W; }
+  __host__ __device__ float* c_at(int t) const { return cs + (size_t)t * B * 25 * H * W; }
+  __host__ __device__ float* gates_at(int t) const { return gates + (size_t)(t - 1) * B * 100 * H * W; }   // t = 1..T
+};
+
+int run_convlstm_forward(const LstmDev& d, cudaStream_t st);
+int run_convlstm_penalty(const LstmDev& d, cudaStream_t st);
+int run_convlstm_backward(const LstmDev& d, cudaStream_t st);
+
+}  // namespace ptk

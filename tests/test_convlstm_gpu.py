@@ -1,0 +1,53 @@
+"""GPU parity of the ConvLSTM path (through the C ABI) against fixtures from the reference and the fp64 oracle."""
+import pytest
+import torch
+
+from tests.convlstm_util import load_convlstm_case, oracle_run
+from tests.golden_util import NOISE_MULT, REL_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case):
+    from pathtracker_models_b200 import convlstm
+    B, T, H, W = case["shape"]
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"])
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    loss.backward()
+    return m, out, pen, loss
+
+
+@pytest.mark.parametrize("name", ["convlstm_k7_small", "convlstm_k15_small", "convlstm_k15_b3"])
+def test_convlstm_output_penalty_and_grads(name):
+    case = load_convlstm_case(name)
+    m, out, pen, loss = _run(case)
+    B, T, H, W = case["shape"]
+    assert out.shape == (B, 2, H, W) and pen.shape == (B, 25, H, W)
+    assert rel_err(out, case["output"]) < REL_TOL
+    assert abs(loss.item() - case["loss"]) < 1e-5
+    assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))
+    _, _, _, g64 = oracle_run(case)                 # fp64 oracle (itself pinned to the reference on the CPU suite)
+    bad = []
+    for n, p in m.named_parameters():
+        e = rel_err(p.grad, g64[n])
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+
+
+def test_convlstm_eval_mode_and_determinism():
+    from pathtracker_models_b200 import convlstm
+    case = load_convlstm_case("convlstm_k7_small")
+    B, T, H, W = case["shape"]
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=7, gabor=case["gabor"])
+    m.load_state_dict(case["sd"])
+    m = m.cuda().eval()
+    x, tgt = case["x"].float().cuda(), case["target"].cuda()
+    with torch.no_grad():
+        o1, pen, l1 = m(x, 0, 0, tgt, torch.nn.CrossEntropyLoss())
+        o2, states, l2 = m(x, 0, 0, tgt, torch.nn.CrossEntropyLoss(), testmode=True)
+    assert pen.shape == (1,) and states == [] and torch.equal(o1, o2)
+    assert rel_err(o1, case["output"]) < REL_TOL
