@@ -142,6 +142,8 @@ def run_b200(args):
                     + 2 * HW * HW * (2 * C + 100))
 
     torch.manual_seed(0)
+    if args.model == "convlstm":
+        return run_convlstm(args, dev, world, rank)
     ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
     model = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev)
     model.conv_mode = _lib.PTK_CONV_BF16X3 if args.conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
@@ -266,6 +268,50 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_convlstm(args, dev, world, rank):
+    """BASELINE configs[4]: ConvLSTM(timesteps=64, filt_size=15), x [64,1,32,32], CrossEntropy, train mode
+    (so the Jacobian-penalty branch runs, as in the reference).  Secondary line, not the headline."""
+    import numpy as np
+    import torch
+    from pathtracker_models_b200 import _lib, convlstm, synth_pathtracker
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    B, T, HW = args.batch, args.frames, args.size
+    rs = np.random.RandomState(0)
+    gabor = torch.from_numpy(rs.normal(0, 0.3, (25, 1, 7, 7)).astype(np.float32))   # the .npy is not on the GPU box
+    torch.manual_seed(0)
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=15, gabor=gabor).to(dev).train()
+    clips, y = synth_pathtracker(B, 2, HW, HW, device=dev)
+    x = clips[:, 0:1, 0].contiguous()                                               # [B,1,H,W] static image
+    tgt = (clips[:, 2, 0] > 0).long()
+    crit = torch.nn.CrossEntropyLoss()
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        out, pen, loss = m(x, 0, 0, tgt, crit)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    flop = 3 * 2.0 * B * HW * HW * 100 * 25 * 225 * T          # fwd + dgrad + wgrad of the recurrent conv
+    print(json.dumps({"metric": "train seq/s (fwd+bwd) ConvLSTM", "value": B * steps / (ms / 1e3), "unit": UNIT,
+                      "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T, B, HW, HW)},
+                      "gpu_launches": _lib.launch_count() - l0,
+                      "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
+                                   "note": "strict-fp32 CUDA-core path; recurrent-conv FLOPs only"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -274,7 +320,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="int", choices=["int", "hgru"], help="non-headline configs (BASELINE configs[2..3])")
+    ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm"], help="non-headline configs (BASELINE configs[2..3])")
     ap.add_argument("--frames", type=int, default=T)
     ap.add_argument("--size", type=int, default=HW)
     ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3"],

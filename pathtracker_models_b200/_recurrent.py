@@ -108,7 +108,14 @@ class _RecurrentModel(nn.Module):
     def flat_parameters(self):
         """the 30 live parameters, concatenated in the C ABI's canonical order (differentiable)."""
         mods = dict(self.named_parameters())
-        return torch.cat([mods[n].reshape(-1) for n in PARAM_ORDER])
+        parts = []
+        for n in PARAM_ORDER:
+            if n in mods:
+                parts.append(mods[n].reshape(-1))
+            else:   # InT(no_inh=True) has no w_inh (models/InT.py:91-93): the slot stays, filled with zeros
+                ref = mods["unit1.w_exc"]
+                parts.append(torch.zeros(ref.numel(), dtype=ref.dtype, device=ref.device))
+        return torch.cat(parts)
 
     def forward(self, x, testmode=False):
         cfg = self._config()

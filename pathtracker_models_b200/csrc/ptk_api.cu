@@ -31,7 +31,7 @@ static int check_dims(const PtkDims* d, const char* who) {
   }
   if (d->cell != PTK_CELL_INT && d->cell != PTK_CELL_HGRU) { set_error("%s: bad cell %d", who, d->cell); return PTK_EINVAL; }
   if (d->act != PTK_ACT_SOFTPLUS && d->act != PTK_ACT_TANH) { set_error("%s: bad act %d", who, d->act); return PTK_EINVAL; }
-  if (d->no_inh) { set_error("%s: no_inh=True variant is not built yet", who); return PTK_EUNSUPPORTED; }
+  if (d->no_inh && d->cell != PTK_CELL_INT) { set_error("%s: no_inh exists for the InT cell only (models/InT.py:167)", who); return PTK_EINVAL; }
   if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3) { set_error("%s: bad conv_mode %d", who, d->conv_mode); return PTK_EINVAL; }
   return PTK_OK;
 }
@@ -200,7 +200,7 @@ int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5
   PTK_CUDA_OK(cudaMemsetAsync(d.ckI, 0, S * sizeof(float), st));   // I_0 = 0 (models/InT.py:218)
   PTK_CUDA_OK(cudaMemsetAsync(d.ckE, 0, S * sizeof(float), st));   // E_0 = 0 (models/InT.py:217)
   if ((rc = prep(&d, params, st))) return rc;
-  return run_int_forward(d, dm->cell, dm->act, st);
+  return run_int_forward(d, dm->no_inh ? 2 : dm->cell, dm->act, st);
 }
 
 int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[5], const float* params,
@@ -227,7 +227,7 @@ int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[
   d.dlogits = dlogits; d.dparams = dparams; d.dx = dx;
   PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
   if ((rc = prep(&d, params, st))) return rc;   // the workspace may have been reused since forward
-  return run_int_backward(d, dm->cell, dm->act, st);
+  return run_int_backward(d, dm->no_inh ? 2 : dm->cell, dm->act, st);
 }
 
 

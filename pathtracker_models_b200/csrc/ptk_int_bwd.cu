@@ -25,6 +25,7 @@
 namespace ptk {
 
 constexpr int TILE_F = C * TP;
+constexpr int CELL_NOINH = 2;   // internal: InT(no_inh=True), models/InT.py:167-168
 
 __device__ __forceinline__ void acc_store(float* dst, float v, int first) {
   if (first) *dst = v; else *dst += v;
@@ -205,6 +206,34 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
     cp_async_commit();
     float xin[3][4];
     frame_px(d.fv, b, t, pix, d.W, xin);
+    if (CELL == CELL_NOINH) {
+      // InT(no_inh=True): only (b5) exists.  dS = We_w^T ge feeds dE (S = E), dGe = dI' + We_u^T ge.
+#pragma unroll 1
+      for (int o = 0; o < 8; ++o) {     // X is still needed by the gate weight gradients
+        float X[4];
+        stem_pre(sWp, sbp, L.oc0 + o, xin, X);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) X[p] = actf<ACT>(X[p]);
+        st4(d.Xs + base + (size_t)(L.oc0 + o) * P, X);
+      }
+      cp_async_wait<0>();
+      __syncwarp();
+      float acc[4][8];
+      acc_fill(acc, nullptr, L);
+      warp_gemm(acc, sGe, sWew, L);
+      acc_to_global(d.dS, base, P, L, acc);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const float4 g1 = ld4(d.gI + base + (size_t)(L.oc0 + o) * P), g2 = ld4(d.cgI + base + (size_t)(L.oc0 + o) * P);
+        acc[0][o] = g1.x + g2.x; acc[1][o] = g1.y + g2.y; acc[2][o] = g1.z + g2.z; acc[3][o] = g1.w + g2.w;
+      }
+      warp_gemm(acc, sGe, sWeu, L);
+      acc_to_global(d.dGe, base, P, L, acc);
+      acc_fill(acc, nullptr, L);
+      acc_to_global(d.gI, base, P, L, acc);   // the step ignores its inhibition input: dI for step t-1 is zero
+      __syncwarp();
+      continue;
+    }
 #pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
@@ -278,6 +307,7 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
     acc_to_global(d.dGe, base, P, L, acc);
     __syncwarp();
   }
+  if (CELL == CELL_NOINH) return;      // no alpha / mu / BatchNorm0 in this variant
   part_fold<4>(sPart, sTot);
   float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
   if (threadIdx.x < C) {
@@ -329,12 +359,13 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
       }
       ld4v(Et + idx, E);
       ld4v(d.gE + idx, gE);
-      if (CELL == PTK_CELL_HGRU) ld4v(d.dS + idx, dS);
+      if (CELL != PTK_CELL_INT) ld4v(d.dS + idx, dS);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const float dA = fmaf(dGe[p], E[p], dS[p]);
+        // hGRU: S = A, so dS joins dA;  no_inh: S = E, so dS joins dE
+        const float dA = fmaf(dGe[p], E[p], CELL == PTK_CELL_HGRU ? dS[p] : 0.0f);
         oa[p] = dA * A[p] * (1.0f - A[p]);
-        ode[p] = fmaf(dGe[p], A[p], gE[p]);
+        ode[p] = fmaf(dGe[p], A[p], gE[p]) + (CELL == CELL_NOINH ? dS[p] : 0.0f);
       }
       st4(d.aS + idx, oa);
       st4(d.gE + idx, ode);          // parked: completed by the transposed product below
@@ -417,7 +448,8 @@ template <int CELL>
 __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
-  const float* src[7] = {d.geb, d.giS, d.aS, (CELL == PTK_CELL_INT) ? d.I_at(t) : d.A_at(t), d.Ge, d.Xs, d.E_at(t)};
+  const float* src[7] = {d.geb, d.giS, d.aS,
+                         (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.Ge, d.Xs, d.E_at(t)};
   auto issue = [&](int tile, int buf) {
     const int b = tile / tpi, pix_base = (tile - b * tpi) * GPX;
     float* dstb = dsm + (size_t)buf * 7 * GT_F;
@@ -662,6 +694,14 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int nWT = d.B * P / WPX;
   const int grid_a = (nWT + 3) / 4 < PW_EW_CTAS ? (nWT + 3) / 4 : PW_EW_CTAS;
   PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)PW_EW_CTAS * ACC_N * sizeof(float), st));
+  if (CELL == CELL_NOINH) {   // buffers the skipped inhibition branch would have written
+    const size_t Sb = (size_t)d.B * C * P * sizeof(float);
+    PTK_CUDA_OK(cudaMemsetAsync(d.cGe, 0, Sb, st));
+    PTK_CUDA_OK(cudaMemsetAsync(d.dX, 0, Sb, st));
+    PTK_CUDA_OK(cudaMemsetAsync(d.giS, 0, Sb, st));
+    PTK_CUDA_OK(cudaMemsetAsync(d.bn_acc, 0, 4 * C * sizeof(double), st));
+    PTK_CUDA_OK(cudaMemsetAsync(d.wacc_inh, 0, (tc ? wgrad_tc_acc_floats(d.B, d.H, d.W) : (size_t)4 * WGRAD_GROUPS * TAPS * 256) * sizeof(float), st));
+  }
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
@@ -698,17 +738,19 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       int_bwd_c_kernel<CELL, ACT><<<grid_c, 128, SM_BWD_C, st>>>(d, t, first);
     }
     PTK_LAUNCH_OK("int_bwd_c_kernel");
-    {
-      ProfileScope ps(PTK_PROF_BN_APPLY, st);
-      bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0_at(t), t, 0);
+    if (CELL != CELL_NOINH) {
+      {
+        ProfileScope ps(PTK_PROF_BN_APPLY, st);
+        bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0_at(t), t, 0);
+      }
+      PTK_LAUNCH_OK("bn_apply_kernel");
+      ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
+      { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
+      if (rc) return rc;
+      WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
+      { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w0, st) : launch_wgrad7(w0, WGRAD_GROUPS, st); }
+      if (rc) return rc;
     }
-    PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
-    { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
-    if (rc) return rc;
-    WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
-    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w0, st) : launch_wgrad7(w0, WGRAD_GROUPS, st); }
-    if (rc) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       int_bwd_d_kernel<CELL, ACT><<<grid, 128, SM_BWD_D, st>>>(d, t, first);
@@ -742,6 +784,7 @@ static int run_backward_c(const IntDev& d, int act, cudaStream_t st) {
 }
 
 int run_int_backward(const IntDev& d, int cell, int act, cudaStream_t st) {
+  if (cell == CELL_NOINH) return run_backward_c<CELL_NOINH>(d, act, st);
   return cell == PTK_CELL_INT ? run_backward_c<PTK_CELL_INT>(d, act, st) : run_backward_c<PTK_CELL_HGRU>(d, act, st);
 }
 

@@ -31,10 +31,13 @@ __device__ __forceinline__ void stem_to_tile(float* sX, const float* sWp, const 
 }
 
 // eqs (1)-(2) for frame t: A = sigmoid(Wa_w X + Wa_u E + b), Ge = A*E.  sE must hold E_t.
-template <int ACT>
+// NOINH (InT(no_inh=True), models/InT.py:167-168): inhibition := Ge, gated_inhibition := E, so the step's
+// excitation gate G_e = sigmoid(We_w E + We_u Ge + b) (eq. 9) is formed here as well and Ge becomes I_{t+1}.
+template <int ACT, bool NOINH>
 __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, int pix_base, float* sX,
                                                const float* sE, const float* sWaw, const float* sWau,
                                                const float* sba, const float* sWp, const float* sbp,
+                                               const float* sWew, const float* sWeu, const float* sbe,
                                                const Lane& L) {
   const int P = d.H * d.W, pix = pix_base + L.pxo;
   float xin[3][4];
@@ -49,6 +52,7 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
   acc_to_tile(sX, L, acc);          // park the pre-activations; only this thread re-reads its patch
   float* Aout = d.A_at(t) + (size_t)b * d.a_bstride + pix;
   float* Geout = d.Ge + (size_t)b * C * P + pix;
+  float* Iout = d.I_at(t + 1) + (size_t)b * C * P + pix;
 #pragma unroll 1
   for (int o = 0; o < 8; ++o) {
     float e[4], a[4], ge[4];
@@ -58,21 +62,45 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
     for (int p = 0; p < 4; ++p) { a[p] = sigm<ACT>(a[p]); ge[p] = a[p] * e[p]; }
     st4(Aout + (size_t)(L.oc0 + o) * P, a);
     st4(Geout + (size_t)(L.oc0 + o) * P, ge);
+    if (NOINH) {
+      st4(Iout + (size_t)(L.oc0 + o) * P, ge);
+      tile_st(sX, L, o, ge);
+    }
+  }
+  if (NOINH) {
+    __syncwarp();
+    acc_fill(acc, sbe, L);
+    warp_gemm(acc, sE, sWew, L);
+    warp_gemm(acc, sX, sWeu, L);
+    float* Gx = d.Gex_at(t) + (size_t)b * C * P + pix;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float g[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) g[p] = sigm<ACT>(acc[p][o]);
+      st4(Gx + (size_t)(L.oc0 + o) * P, g);
+    }
   }
 }
 
-template <int ACT>
+template <int ACT, bool NOINH>
 __global__ void __launch_bounds__(128) int_pre_kernel(IntDev d, int t) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;
   float* sWau = sWaw + C * C;
-  float* tiles = sWau + C * C;
-  __shared__ float sWp[C * 3], sbp[C], sba[C];
+  float* sWew = sWau + C * C;                       // only staged when NOINH
+  float* sWeu = sWew + (NOINH ? C * C : 0);
+  float* tiles = sWeu + (NOINH ? C * C : 0);
+  __shared__ float sWp[C * 3], sbp[C], sba[C], sbe[C];
   cta_fill(sWaw, d.gateT[0], C * C);
   cta_fill(sWau, d.gateT[1], C * C);
+  if (NOINH) { cta_fill(sWew, d.gateT[4], C * C); cta_fill(sWeu, d.gateT[5], C * C); }
   cta_fill(sWp, d.Wp, C * 3);
   cta_fill(sbp, d.bp, C);
-  if (threadIdx.x < C) sba[threadIdx.x] = __ldg(d.gate_b[0] + threadIdx.x) + __ldg(d.gate_b[1] + threadIdx.x);
+  if (threadIdx.x < C) {
+    sba[threadIdx.x] = __ldg(d.gate_b[0] + threadIdx.x) + __ldg(d.gate_b[1] + threadIdx.x);
+    sbe[threadIdx.x] = __ldg(d.gate_b[4] + threadIdx.x) + __ldg(d.gate_b[5] + threadIdx.x);
+  }
   __syncthreads();
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
@@ -84,7 +112,7 @@ __global__ void __launch_bounds__(128) int_pre_kernel(IntDev d, int t) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
-    attention_tile<ACT>(d, t, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, L);
+    attention_tile<ACT, NOINH>(d, t, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L);
     __syncwarp();
   }
 }
@@ -186,15 +214,18 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
 }
 
 // eqs (10b)-(13) for step t, then (1)-(2) for step t+1 (if any).
-template <int ACT>
+template <int ACT, bool NOINH>
 __global__ void __launch_bounds__(128) int_post_kernel(IntDev d, int t, int has_next) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;
   float* sWau = sWaw + C * C;
-  float* tiles = sWau + C * C;
-  __shared__ float sWp[C * 3], sbp[C], sba[C], sKa[C], sGa[C], sScale[C], sShift[C], sWr[C];
+  float* sWew = sWau + C * C;                       // only staged when NOINH
+  float* sWeu = sWew + (NOINH ? C * C : 0);
+  float* tiles = sWeu + (NOINH ? C * C : 0);
+  __shared__ float sWp[C * 3], sbp[C], sba[C], sbe[C], sKa[C], sGa[C], sScale[C], sShift[C], sWr[C];
   cta_fill(sWaw, d.gateT[0], C * C);
   cta_fill(sWau, d.gateT[1], C * C);
+  if (NOINH) { cta_fill(sWew, d.gateT[4], C * C); cta_fill(sWeu, d.gateT[5], C * C); }
   cta_fill(sWp, d.Wp, C * 3);
   cta_fill(sbp, d.bp, C);
   cta_fill(sKa, d.kappa, C);
@@ -203,6 +234,7 @@ __global__ void __launch_bounds__(128) int_post_kernel(IntDev d, int t, int has_
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
     sba[c] = __ldg(d.gate_b[0] + c) + __ldg(d.gate_b[1] + c);
+    sbe[c] = __ldg(d.gate_b[4] + c) + __ldg(d.gate_b[5] + c);
     const float* st = d.stat(t, 1);   // BN1 of step t
     const float sc = __ldg(d.bn_w[1] + c) * st[C + c];
     sScale[c] = sc;
@@ -252,7 +284,7 @@ __global__ void __launch_bounds__(128) int_post_kernel(IntDev d, int t, int has_
       }
       if (L.og == 0) st4(d.states + ((size_t)b * d.T + t) * P + pix, sread);
     }
-    if (has_next) attention_tile<ACT>(d, t + 1, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, L);
+    if (has_next) attention_tile<ACT, NOINH>(d, t + 1, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L);
     __syncwarp();
   }
 }
@@ -332,35 +364,41 @@ int pw_grid(int B, int H, int W) {
 static constexpr size_t SM_PRE = (size_t)(2 * C * C + 4 * 2 * TILE_F) * sizeof(float);
 static constexpr size_t SM_MID = (size_t)(4 * C * C + 4 * 3 * TILE_F) * sizeof(float);
 
-template <int ACT>
+constexpr int CELL_NOINH = 2;   // internal: InT(no_inh=True)
+static constexpr size_t SM_PRE_NI = SM_PRE + 2 * C * C * sizeof(float);
+
+template <int ACT, bool NOINH>
 static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   const int grid = pw_grid(d.B, d.H, d.W);
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_pre_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_PRE));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_post_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_PRE));
+  const size_t sm_pre = NOINH ? SM_PRE_NI : SM_PRE;
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_pre_kernel<ACT, NOINH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pre));
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_post_kernel<ACT, NOINH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pre));
   PTK_CUDA_OK(cudaFuncSetAttribute(int_mid_kernel<PTK_CELL_INT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MID));
   PTK_CUDA_OK(cudaFuncSetAttribute(int_mid_kernel<PTK_CELL_HGRU, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MID));
   {
     ProfileScope ps(PTK_PROF_POINT_FWD, st);
-    int_pre_kernel<ACT><<<grid, 128, SM_PRE, st>>>(d, 0);
+    int_pre_kernel<ACT, NOINH><<<grid, 128, sm_pre, st>>>(d, 0);
   }
   PTK_LAUNCH_OK("int_pre_kernel");
   for (int t = 0; t < d.T; ++t) {
     int rc;
-    ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode};
-    { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
-    if (rc) return rc;
-    {
-      ProfileScope ps(PTK_PROF_POINT_FWD, st);
-      if (cell == PTK_CELL_INT) int_mid_kernel<PTK_CELL_INT, ACT><<<grid, 128, SM_MID, st>>>(d, t);
-      else int_mid_kernel<PTK_CELL_HGRU, ACT><<<grid, 128, SM_MID, st>>>(d, t);
+    if (!NOINH) {
+      ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode};
+      { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
+      if (rc) return rc;
+      {
+        ProfileScope ps(PTK_PROF_POINT_FWD, st);
+        if (cell == PTK_CELL_INT) int_mid_kernel<PTK_CELL_INT, ACT><<<grid, 128, SM_MID, st>>>(d, t);
+        else int_mid_kernel<PTK_CELL_HGRU, ACT><<<grid, 128, SM_MID, st>>>(d, t);
+      }
+      PTK_LAUNCH_OK("int_mid_kernel");
     }
-    PTK_LAUNCH_OK("int_mid_kernel");
     ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1), d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_FWD, st);
-      int_post_kernel<ACT><<<grid, 128, SM_PRE, st>>>(d, t, t + 1 < d.T);
+      int_post_kernel<ACT, NOINH><<<grid, 128, sm_pre, st>>>(d, t, t + 1 < d.T);
     }
     PTK_LAUNCH_OK("int_post_kernel");
   }
@@ -373,11 +411,16 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   return PTK_OK;
 }
 
+template <int ACT>
+static int run_forward_ni(const IntDev& d, int cell, cudaStream_t st) {
+  return cell == CELL_NOINH ? run_forward_act<ACT, true>(d, cell, st) : run_forward_act<ACT, false>(d, cell, st);
+}
+
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st) {
   const bool fast = (d.conv_mode == PTK_CONV_BF16X3);
-  if (act == PTK_ACT_SOFTPLUS) return fast ? run_forward_act<PTK_ACT_SOFTPLUS | ACT_FAST>(d, cell, st)
-                                           : run_forward_act<PTK_ACT_SOFTPLUS>(d, cell, st);
-  return fast ? run_forward_act<PTK_ACT_TANH | ACT_FAST>(d, cell, st) : run_forward_act<PTK_ACT_TANH>(d, cell, st);
+  if (act == PTK_ACT_SOFTPLUS) return fast ? run_forward_ni<PTK_ACT_SOFTPLUS | ACT_FAST>(d, cell, st)
+                                           : run_forward_ni<PTK_ACT_SOFTPLUS>(d, cell, st);
+  return fast ? run_forward_ni<PTK_ACT_TANH | ACT_FAST>(d, cell, st) : run_forward_ni<PTK_ACT_TANH>(d, cell, st);
 }
 
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,

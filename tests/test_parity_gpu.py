@@ -35,7 +35,7 @@ def _run(case, m, x=None):
 
 
 CASES = [("int_small", "int", {}), ("int_tile", "int", {}), ("int_cfg1", "int", {}), ("int_64px", "int", {}),
-         ("int_tanh_small", "int", {"nl": torch.tanh}),
+         ("int_tanh_small", "int", {"nl": torch.tanh}), ("int_noinh_small", "int", {"no_inh": True}),
          ("int_lesion_small", "int", {"lesion_alpha": True, "lesion_gamma": True}),
          ("hgru_small", "hgru", {}), ("hgru_tile", "hgru", {})]
 
@@ -50,6 +50,9 @@ def test_logits_and_all_grads_vs_fp64_reference(name, kind, kw):
     bad = check_parity(case, out, grads)
     assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
     assert grads["unit1.w"] is None          # dead parameter gets no gradient
+    if kw.get("no_inh"):                     # parameters of the skipped inhibition branch: zero gradient
+        for n in ("unit1.alpha", "unit1.mu", "unit1.i_w_gate.weight", "unit1.bn.0.weight"):
+            assert float(grads[n].abs().max()) == 0.0, n
 
 
 def test_per_step_checkpoints_vs_oracle():
