@@ -59,7 +59,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   float* w = cv.take<float>(4 * (size_t)C * C * TAPS);
   float* gt = cv.take<float>(6 * C * C);
   float* Ge = cv.take<float>(S);
-  float* big = cv.take<float>(12 * S);   // inference ring (9S) or backward scratch (12S)
+  float* big = cv.take<float>(14 * S);   // inference ring (9S) or backward scratch (14S)
   float* ring_stats = cv.take<float>(4 * C);
   float* bn_part = cv.take<float>((size_t)conv_num_ctas(dm->B, dm->H, dm->W) * C * 2);
   unsigned* counter = cv.take<unsigned>(4);
@@ -84,6 +84,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
     d->gE = big; d->gI = big + S; d->geb = big + 2 * S; d->dAct = big + 3 * S; d->dGe = big + 4 * S;
     d->dX = big + 5 * S; d->dS = big + 6 * S; d->giS = big + 7 * S; d->aS = big + 8 * S; d->Xs = big + 9 * S;
     d->cgI = big + 10 * S; d->cGe = big + 11 * S;
+    d->GeB[0] = Ge; d->GeB[1] = big + 12 * S; d->gebB[0] = d->geb; d->gebB[1] = big + 13 * S;
     // inference ring view of `big` (only used when saved == NULL)
     if (d->ck_ring) {
       d->ckI = big; d->ckE = big + 2 * S; d->ck_stride = S;

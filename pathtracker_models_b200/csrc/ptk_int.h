@@ -19,7 +19,7 @@ enum {
 constexpr int HEAD_N = 96;        // per-sample readout-head partials (86 used), see int_readout_bwd_kernel
 constexpr int WGRAD_GROUPS = 37;  // 4 ic-chunks x 37 groups = 148 CTAs (one per SM)
 constexpr int GATE_CTAS = 148;    // gate weight-gradient kernel: one persistent CTA per SM
-constexpr int PW_MAX_CTAS = 148 * 3;   // grid of the gate-product kernels (smem-limited to 3 CTAs/SM)
+constexpr int PW_MAX_CTAS = 148 * 4;   // grid of the point-wise kernels: 4 CTAs/SM so that (cfg 2: 512 CTAs) every warp owns ONE tile
 constexpr int PW_EW_CTAS = 148 * 4;    // grid of the purely element-wise bwd_a kernel; also the number of accumulator slots
 
 struct IntDev {
@@ -50,6 +50,8 @@ struct IntDev {
   unsigned* counter;
   // backward scratch
   float *gE, *gI, *geb, *dAct, *dGe, *dX, *dS, *giS, *aS, *Xs;
+  float *GeB[2], *gebB[2]; // per-step-parity copies of Ge and geb (the fused bwd_d(t)+bwd_a(t-1) kernel writes step t-1's
+                           // while gate_wgrad(t) still reads step t's)
   float *cgI, *cGe;        // data-gradient outputs of the two transposed convolutions (added by the consumers)
   int pw_ctas;             // grid of the backward point-wise kernels (fixed => deterministic slots)
   float* acc;              // [pw_ctas][ACC_N]

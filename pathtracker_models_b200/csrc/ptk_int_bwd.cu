@@ -58,32 +58,75 @@ __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// (b1)-(b2): dE', dI' (gE, gI) + checkpointed E_t, A_t, I_{t+1}, Y1_t, G_e.
+// (b1)-(b2) for one channel of the thread's patch: dE', dI' + checkpointed E_t, A_t, I_{t+1}, Y1_t, G_e.
 // writes Ge = A*E (scratch, for wgrad / gate_wgrad), geb = dG_e*G_e*(1-G_e), gE <- dE'*(1-G_e),
-// gI += dR*V*kappa, dAct <- dV.
+// gI += dR*V*kappa, dAct <- dV; returns the four per-channel partial sums of the patch.
+struct BwdAConst {
+  const float *Ka, *Ga, *W1, *B1, *M1, *R1;   // shared-memory per-channel constants of step t
+};
 template <int ACT>
-__global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int first) {
-  __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
-  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
-  __shared__ int sIsLast;
+__device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, int first, size_t idx, int c, const float (&gEn)[4],
+                                              const BwdAConst& k, float (&part)[4]) {
+  float e[4], a[4], i2[4], y1[4], gx[4], gi_in[4] = {0.f, 0.f, 0.f, 0.f};
+  float oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4];
+  ld4v(d.E_at(t) + idx, e);
+  ld4v(d.A_at(t) + idx, a);
+  ld4v(d.I_at(t + 1) + idx, i2);
+  ld4v(d.Y1_at(t) + idx, y1);
+  ld4v(d.Gex_at(t) + idx, gx);
+  if (!first) ld4v(d.gI + idx, gi_in);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float xh = (y1[p] - k.M1[c]) * k.R1[c];
+    const float V = fmaf(k.W1[c], xh, k.B1[c]);
+    const float kIg = fmaf(k.Ka[c], i2[p], k.Ga[c]);
+    const float R = V * kIg;
+    const float Ehat = actf<ACT>(R);
+    const float dGx = gEn[p] * (Ehat - e[p]);
+    oGE[p] = gEn[p] * (1.0f - gx[p]);
+    const float dR = gEn[p] * gx[p] * dactf<ACT>(R);
+    const float dV = dR * kIg;
+    const float dRV = dR * V;
+    oGI[p] = fmaf(dRV, k.Ka[c], gi_in[p]);
+    oGeb[p] = dGx * gx[p] * (1.0f - gx[p]);
+    oDv[p] = dV;
+    oGe[p] = a[p] * e[p];
+    part[0] = fmaf(dRV, i2[p], part[0]);   // -> d kappa
+    part[1] += dRV;                         // -> d gamma
+    part[2] += dV;                          // -> sum dV
+    part[3] = fmaf(dV, xh, part[3]);        // -> sum dV * xhat
+  }
+  st4(d.gE + idx, oGE);
+  st4(d.gI + idx, oGI);
+  st4(d.gebB[t & 1] + idx, oGeb);
+  st4(d.dAct + idx, oDv);
+  st4(d.GeB[t & 1] + idx, oGe);
+}
+__device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* sKa, float* sGa, float* sW1, float* sB1,
+                                                 float* sM1, float* sR1) {
   cta_fill(sKa, d.kappa, C);
   cta_fill(sGa, d.gamma, C);
   cta_fill(sW1, d.bn_w[1], C);
   cta_fill(sB1, d.bn_b[1], C);
-  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
   if (threadIdx.x < C) {
     const float* st = d.stat(t, 1);
     sM1[threadIdx.x] = st[threadIdx.x];
     sR1[threadIdx.x] = st[C + threadIdx.x];
   }
+}
+
+// stand-alone (b1)-(b2) kernel: only used for the last time step (the others are fused into bwd_d).
+template <int ACT>
+__global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int first) {
+  __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
+  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
+  __shared__ int sIsLast;
+  bwd_a_fill_const(d, t, sKa, sGa, sW1, sB1, sM1, sR1);
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
   __syncthreads();
+  const BwdAConst k{sKa, sGa, sW1, sB1, sM1, sR1};
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
-  const float* Et = d.E_at(t);
-  const float* At = d.A_at(t);
-  const float* I2t = d.I_at(t + 1);
-  const float* Y1 = d.Y1_at(t);
-  const float* Gxt = d.Gex_at(t);
   float* sPw = sPart + warp * 4 * C;
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
@@ -92,42 +135,9 @@ __global__ void __launch_bounds__(128) int_bwd_a_kernel(IntDev d, int t, int fir
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float e[4], a[4], i2[4], y1[4], gx[4], ge_in[4], gi_in[4] = {0.f, 0.f, 0.f, 0.f};
-      float oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4], part[4] = {0.f, 0.f, 0.f, 0.f};
-      ld4v(Et + idx, e);
-      ld4v(At + idx, a);
-      ld4v(I2t + idx, i2);
-      ld4v(Y1 + idx, y1);
-      ld4v(Gxt + idx, gx);
-      ld4v(d.gE + idx, ge_in);
-      if (!first) ld4v(d.gI + idx, gi_in);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float xh = (y1[p] - sM1[c]) * sR1[c];
-        const float V = fmaf(sW1[c], xh, sB1[c]);
-        const float kIg = fmaf(sKa[c], i2[p], sGa[c]);
-        const float R = V * kIg;
-        const float Ehat = actf<ACT>(R);
-        const float gEn = ge_in[p];
-        const float dGx = gEn * (Ehat - e[p]);
-        oGE[p] = gEn * (1.0f - gx[p]);
-        const float dR = gEn * gx[p] * dactf<ACT>(R);
-        const float dV = dR * kIg;
-        const float dRV = dR * V;
-        oGI[p] = fmaf(dRV, sKa[c], gi_in[p]);
-        oGeb[p] = dGx * gx[p] * (1.0f - gx[p]);
-        oDv[p] = dV;
-        oGe[p] = a[p] * e[p];
-        part[0] = fmaf(dRV, i2[p], part[0]);   // -> d kappa
-        part[1] += dRV;                         // -> d gamma
-        part[2] += dV;                          // -> sum dV
-        part[3] = fmaf(dV, xh, part[3]);        // -> sum dV * xhat
-      }
-      st4(d.gE + idx, oGE);
-      st4(d.gI + idx, oGI);
-      st4(d.geb + idx, oGeb);
-      st4(d.dAct + idx, oDv);
-      st4(d.Ge + idx, oGe);
+      float gEn[4], part[4] = {0.f, 0.f, 0.f, 0.f};
+      ld4v(d.gE + idx, gEn);
+      bwd_a_channel<ACT>(d, t, first, idx, c, gEn, k, part);
       part_add<4>(sPw, c, L, part);
     }
   }
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __
 // (b5)-(b8): complete dI' (gI), geb, checkpointed I_t, A_t, Y0_t, G_i, x_t.
 // writes dAct <- dU, dGe, dX, gI <- dI (+ dS for InT), dS (hGRU), gi and X (scratch for gate_wgrad).
 template <int CELL, int ACT>
-__global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int first) {
+__global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   float* sWiw = dsm;              // [out][in] = [k][n] of the transposed products
   float* sWiu = sWiw + C * C;
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
-    warp_tile_load_async(sGe, d.geb, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
     cp_async_commit();
     float xin[3][4];
     frame_px(d.fv, b, t, pix, d.W, xin);
@@ -320,24 +330,32 @@ __global__ void __launch_bounds__(128) int_bwd_c_kernel(IntDev d, int t, int fir
 // ------------------------------------------------------------------------------------------------
 // (b10)-(b12): complete dGe, dE partial (gE), A_t, E_t, dX, [dS], x_t.
 // writes gE <- dE (for step t-1), a (scratch for gate_wgrad), stem parameter sums, optional dx.
+// When t > 0 the kernel continues with (b1)-(b2) of step t-1 on the same patch (dE stays on chip).
 template <int CELL, int ACT>
-__global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int first) {
+__global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;              // [out][in]
   float* sWau = sWaw + C * C;
   float* tiles = sWau + C * C;
   __shared__ float sWp[C * 3], sbp[C];
   __shared__ float sPart[4 * 4 * C], sTot[4 * C];
+  __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C], sPartA[4 * 4 * C], sTotA[4 * C];
+  __shared__ int sIsLast;
+  const bool fuse = (t > 0);
   cta_fill(sWaw, d.gate[0], C * C);
   cta_fill(sWau, d.gate[1], C * C);
   cta_fill(sWp, d.Wp, C * 3);
   cta_fill(sbp, d.bp, C);
-  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  if (fuse) bwd_a_fill_const(d, t - 1, sKa, sGa, sW1, sB1, sM1, sR1);
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) { sPart[i] = 0.f; sPartA[i] = 0.f; }
   __syncthreads();
+  const BwdAConst ka{sKa, sGa, sW1, sB1, sM1, sR1};
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
-  float* sA = tiles + warp * TILE_F;
+  float* sA = tiles + warp * 2 * TILE_F;
+  float* sB = sA + TILE_F;             // parked dE for the fused (b1)-(b2) tail
   float* sPw = sPart + warp * 4 * C;   // [0] d bp, [1..3] d Wp[:, i]
+  float* sPwA = sPartA + warp * 4 * C;
   const float* Et = d.E_at(t);
   const float* At = d.A_at(t);
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
@@ -374,8 +392,8 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
     __syncwarp();
     float acc[4][8];
     acc_from_global(acc, d.gE, base, P, L);
-    warp_gemm(acc, sA, sWau, L);     // dE += Wa_u^T a
-    acc_to_global(d.gE, base, P, L, acc);
+    warp_gemm(acc, sA, sWau, L);     // dE += Wa_u^T a   (= dE' of step t-1)
+    if (fuse) acc_to_tile(sB, L, acc);
     acc_from_global(acc, d.dX, base, P, L);
     warp_gemm(acc, sA, sWaw, L);     // dX += Wa_w^T a
     __syncwarp();
@@ -402,6 +420,16 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
         }
       }
       part_add<4>(sPw, c, L, part);
+    }
+    if (fuse) {              // (b1)-(b2) of step t-1, dE' taken from the parked tile
+#pragma unroll 2
+      for (int o = 0; o < 8; ++o) {
+        const int c = L.oc0 + o;
+        float gEn[4], part[4] = {0.f, 0.f, 0.f, 0.f};
+        tile_ld(sB, L, o, gEn);
+        bwd_a_channel<ACT>(d, t - 1, 0, base + (size_t)c * P, c, gEn, ka, part);
+        part_add<4>(sPwA, c, L, part);
+      }
     }
     if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
 #pragma unroll
@@ -435,6 +463,14 @@ __global__ void __launch_bounds__(128) int_bwd_d_kernel(IntDev d, int t, int fir
 #pragma unroll
     for (int i = 0; i < 3; ++i) acc_store(acc + ACC_WP + c * 3 + i, sTot[(1 + i) * C + c], first);
   }
+  if (fuse) {
+    part_fold<4>(sPartA, sTotA);
+    if (threadIdx.x < C) {
+      acc_store(acc + ACC_KAPPA + threadIdx.x, sTotA[threadIdx.x], 0);
+      acc_store(acc + ACC_GAMMA + threadIdx.x, sTotA[C + threadIdx.x], 0);
+    }
+    bn_sums_fold(d, 1, sTotA + 2 * C, 0, &sIsLast);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,8 +484,8 @@ template <int CELL>
 __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
-  const float* src[7] = {d.geb, d.giS, d.aS,
-                         (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.Ge, d.Xs, d.E_at(t)};
+  const float* src[7] = {d.gebB[t & 1], d.giS, d.aS,
+                         (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB[t & 1], d.Xs, d.E_at(t)};
   auto issue = [&](int tile, int buf) {
     const int b = tile / tpi, pix_base = (tile - b * tpi) * GPX;
     float* dstb = dsm + (size_t)buf * 7 * GT_F;
@@ -682,7 +718,7 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
 
 // ---- host ----------------------------------------------------------------------------------
 static constexpr size_t SM_BWD_C = (size_t)(4 * C * C + 4 * 2 * TILE_F) * sizeof(float);
-static constexpr size_t SM_BWD_D = (size_t)(2 * C * C + 4 * 1 * TILE_F) * sizeof(float);
+static constexpr size_t SM_BWD_D = (size_t)(2 * C * C + 4 * 2 * TILE_F) * sizeof(float);
 static constexpr size_t SM_GATE = (size_t)(2 * 7 * GT_F) * sizeof(float);
 
 template <int CELL, int ACT>
@@ -692,7 +728,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int grid_c = grid;
   const bool tc = (d.conv_mode == PTK_CONV_BF16X3);
   const int nWT = d.B * P / WPX;
-  const int grid_a = (nWT + 3) / 4 < PW_EW_CTAS ? (nWT + 3) / 4 : PW_EW_CTAS;
+  const int grid_a = grid;
   PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)PW_EW_CTAS * ACC_N * sizeof(float), st));
   if (CELL == CELL_NOINH) {   // buffers the skipped inhibition branch would have written
     const size_t Sb = (size_t)d.B * C * P * sizeof(float);
@@ -717,11 +753,11 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   for (int t = d.T - 1; t >= 0; --t) {
     const int first = (t == d.T - 1);
     int rc;
-    {
+    if (first) {   // later steps: (b1)-(b2) run as the tail of the previous iteration's bwd_d kernel
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       int_bwd_a_kernel<ACT><<<grid_a, 128, 0, st>>>(d, t, first);
+      PTK_LAUNCH_OK("int_bwd_a_kernel");
     }
-    PTK_LAUNCH_OK("int_bwd_a_kernel");
     {
       ProfileScope ps(PTK_PROF_BN_APPLY, st);
       bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1_at(t), t, 1);
@@ -747,7 +783,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
       { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
-      WgradArgs w0{d.Ge, d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
+      WgradArgs w0{d.GeB[t & 1], d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
       { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w0, st) : launch_wgrad7(w0, WGRAD_GROUPS, st); }
       if (rc) return rc;
     }

@@ -84,7 +84,7 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
 }
 
 template <int ACT, bool NOINH>
-__global__ void __launch_bounds__(128) int_pre_kernel(IntDev d, int t) {
+__global__ void __launch_bounds__(128, 4) int_pre_kernel(IntDev d, int t) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;
   float* sWau = sWaw + C * C;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) int_pre_kernel(IntDev d, int t) {
 
 // eqs (3b)-(9): BatchNorm0 apply, inhibition drive, inhibition gate + blend, excitation gate.
 template <int CELL, int ACT>
-__global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
+__global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   extern __shared__ __align__(16) float dsm[];
   float* sWiw = dsm;
   float* sWiu = sWiw + C * C;
@@ -147,9 +147,8 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
   __syncthreads();
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
-  float* sX = tiles + warp * 3 * TILE_F;
-  float* sS = sX + TILE_F;
-  float* sGe = sS + TILE_F;
+  float* sS = tiles + warp * 2 * TILE_F;
+  float* sGX = sS + TILE_F;            // holds Ge for the excitation-gate product, then X
   const float* It = d.I_at(t);
   float* Iout = d.I_at(t + 1);
   const float* Y0 = d.Y0_at(t);
@@ -159,23 +158,30 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
     const float* Sg = (CELL == PTK_CELL_INT) ? It + base : d.A_at(t) + (size_t)b * d.a_bstride + pix;
     if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
     else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
-    warp_tile_load_async(sGe, d.Ge, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
     cp_async_commit();
     float xin[3][4];
     frame_px(d.fv, b, t, pix, d.W, xin);
-    stem_to_tile<ACT>(sX, sWp, sbp, xin, L);
     cp_async_wait<0>();
     __syncwarp();
     float acc[4][8];
-    // excitation gate pre-activation first, parked in the Ge tile (no longer needed afterwards)
+    // excitation gate (eq. 9) first: G_e = sigmoid(We_w S + We_u Ge + b), written straight to the checkpoint
     acc_fill(acc, sbe, L);
     warp_gemm(acc, sS, sWew, L);
-    warp_gemm(acc, sGe, sWeu, L);
+    warp_gemm(acc, sGX, sWeu, L);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      float gx[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) gx[p] = sigm<ACT>(acc[p][o]);
+      st4(d.Gex_at(t) + base + (size_t)(L.oc0 + o) * P, gx);
+    }
     __syncwarp();
-    acc_to_tile(sGe, L, acc);
-    // inhibition gate pre-activation, parked in the S tile (S is re-read from global below)
+    stem_to_tile<ACT>(sGX, sWp, sbp, xin, L);     // the Ge tile is free now: X takes its place
+    __syncwarp();
+    // inhibition gate pre-activation (eq. 7), parked in the S tile (S is re-read from global below)
     acc_fill(acc, sbi, L);
-    warp_gemm(acc, sX, sWiw, L);
+    warp_gemm(acc, sGX, sWiw, L);
     warp_gemm(acc, sS, sWiu, L);
     __syncwarp();
     acc_to_tile(sS, L, acc);
@@ -183,10 +189,9 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float X[4], S[4], I[4], y0[4], gi[4], gx[4], out[4];
-      tile_ld(sX, L, o, X);
+      float X[4], S[4], I[4], y0[4], gi[4], out[4];
+      tile_ld(sGX, L, o, X);
       tile_ld(sS, L, o, gi);
-      tile_ld(sGe, L, o, gx);
       ld4v(Sg + (size_t)c * P, S);
       if (CELL == PTK_CELL_INT) {
 #pragma unroll
@@ -198,7 +203,6 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         gi[p] = sigm<ACT>(gi[p]);
-        gx[p] = sigm<ACT>(gx[p]);
         const float U = fmaf(y0[p], sScale[c], sShift[c]);
         const float Pp = U * fmaf(sAl[c], S[p], sMu[c]);
         const float Q = actf<ACT>(Pp);
@@ -206,7 +210,6 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
         out[p] = (1.0f - gi[p]) * I[p] + gi[p] * Ihat;
       }
       st4(d.Gi_at(t) + idx, gi);
-      st4(d.Gex_at(t) + idx, gx);
       st4(Iout + idx, out);
     }
     __syncwarp();
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(128) int_mid_kernel(IntDev d, int t) {
 
 // eqs (10b)-(13) for step t, then (1)-(2) for step t+1 (if any).
 template <int ACT, bool NOINH>
-__global__ void __launch_bounds__(128) int_post_kernel(IntDev d, int t, int has_next) {
+__global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int has_next) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;
   float* sWau = sWaw + C * C;
@@ -362,7 +365,7 @@ int pw_grid(int B, int H, int W) {
 }
 
 static constexpr size_t SM_PRE = (size_t)(2 * C * C + 4 * 2 * TILE_F) * sizeof(float);
-static constexpr size_t SM_MID = (size_t)(4 * C * C + 4 * 3 * TILE_F) * sizeof(float);
+static constexpr size_t SM_MID = (size_t)(4 * C * C + 4 * 2 * TILE_F) * sizeof(float);
 
 constexpr int CELL_NOINH = 2;   // internal: InT(no_inh=True)
 static constexpr size_t SM_PRE_NI = SM_PRE + 2 * C * C * sizeof(float);
