@@ -298,7 +298,7 @@ static void lstm_offsets(int K, int64_t* o) {   // conv0.w, conv0.b, 4 x (Wx.w, 
 }
 static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* d, size_t* saved_bytes) {
   const size_t P = (size_t)dm->H * dm->W, S = (size_t)dm->B * 25 * P, SG = 4 * S, taps = (size_t)dm->K * dm->K;
-  const int groups = 3;
+  const int groups = 7;   // (4 oc-blocks x 25 ic) x 7 = 700 CTAs: 5 per SM at most vs 4.73 on average (wave quantisation)
   Carver sv(saved);
   float* hs = sv.take<float>((size_t)(dm->T + 1) * S);
   float* cs = sv.take<float>((size_t)(dm->T + 1) * S);

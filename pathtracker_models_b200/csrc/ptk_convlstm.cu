@@ -141,7 +141,7 @@ struct WgradGArgs {
 };
 
 template <int KS>
-__global__ void __launch_bounds__(32 * KS, 1) wgradg_kernel(WgradGArgs a) {
+__global__ void __launch_bounds__(32 * KS, 2) wgradg_kernel(WgradGArgs a) {
   using G = ConvG<KS>;
   extern __shared__ __align__(16) float smem[];
   float* sDY = smem;                          // [32][16*32]

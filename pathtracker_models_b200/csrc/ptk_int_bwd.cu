@@ -64,17 +64,24 @@ __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const floa
 struct BwdAConst {
   const float *Ka, *Ga, *W1, *B1, *M1, *R1;   // shared-memory per-channel constants of step t
 };
+struct BwdAIn {   // operands of one channel of the patch (prefetched one channel ahead)
+  float4 e, a, i2, y1, gx, gi;
+};
+__device__ __forceinline__ void bwd_a_load(const IntDev& d, int t, int first, size_t idx, BwdAIn& r) {
+  r.e = ld4(d.E_at(t) + idx);
+  r.a = ld4(d.A_at(t) + idx);
+  r.i2 = ld4(d.I_at(t + 1) + idx);
+  r.y1 = ld4(d.Y1_at(t) + idx);
+  r.gx = ld4(d.Gex_at(t) + idx);
+  r.gi = first ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(d.gI + idx);
+}
 template <int ACT>
-__device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, int first, size_t idx, int c, const float (&gEn)[4],
-                                              const BwdAConst& k, float (&part)[4]) {
-  float e[4], a[4], i2[4], y1[4], gx[4], gi_in[4] = {0.f, 0.f, 0.f, 0.f};
+__device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, size_t idx, int c, const float (&gEn)[4],
+                                              const BwdAIn& r, const BwdAConst& k, float (&part)[4]) {
+  const float e[4] = {r.e.x, r.e.y, r.e.z, r.e.w}, a[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+  const float i2[4] = {r.i2.x, r.i2.y, r.i2.z, r.i2.w}, y1[4] = {r.y1.x, r.y1.y, r.y1.z, r.y1.w};
+  const float gx[4] = {r.gx.x, r.gx.y, r.gx.z, r.gx.w}, gi_in[4] = {r.gi.x, r.gi.y, r.gi.z, r.gi.w};
   float oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4];
-  ld4v(d.E_at(t) + idx, e);
-  ld4v(d.A_at(t) + idx, a);
-  ld4v(d.I_at(t + 1) + idx, i2);
-  ld4v(d.Y1_at(t) + idx, y1);
-  ld4v(d.Gex_at(t) + idx, gx);
-  if (!first) ld4v(d.gI + idx, gi_in);
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const float xh = (y1[p] - k.M1[c]) * k.R1[c];
@@ -131,14 +138,19 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
-#pragma unroll 2
+    BwdAIn cur, nxt;
+    float4 gcur = ld4(d.gE + base + (size_t)L.oc0 * P), gnxt = gcur;
+    bwd_a_load(d, t, first, base + (size_t)L.oc0 * P, cur);
+#pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float gEn[4], part[4] = {0.f, 0.f, 0.f, 0.f};
-      ld4v(d.gE + idx, gEn);
-      bwd_a_channel<ACT>(d, t, first, idx, c, gEn, k, part);
+      if (o < 7) { bwd_a_load(d, t, first, idx + P, nxt); gnxt = ld4(d.gE + idx + P); }   // prefetch next channel
+      const float gEn[4] = {gcur.x, gcur.y, gcur.z, gcur.w};
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+      bwd_a_channel<ACT>(d, t, idx, c, gEn, cur, k, part);
       part_add<4>(sPw, c, L, part);
+      cur = nxt; gcur = gnxt;
     }
   }
   part_fold<4>(sPart, sTot);
@@ -422,13 +434,18 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
       part_add<4>(sPw, c, L, part);
     }
     if (fuse) {              // (b1)-(b2) of step t-1, dE' taken from the parked tile
-#pragma unroll 2
+      BwdAIn cur, nxt;
+      bwd_a_load(d, t - 1, 0, base + (size_t)L.oc0 * P, cur);
+#pragma unroll 1
       for (int o = 0; o < 8; ++o) {
         const int c = L.oc0 + o;
+        const size_t idx = base + (size_t)c * P;
+        if (o < 7) bwd_a_load(d, t - 1, 0, idx + P, nxt);          // prefetch next channel
         float gEn[4], part[4] = {0.f, 0.f, 0.f, 0.f};
         tile_ld(sB, L, o, gEn);
-        bwd_a_channel<ACT>(d, t - 1, 0, base + (size_t)c * P, c, gEn, ka, part);
+        bwd_a_channel<ACT>(d, t - 1, idx, c, gEn, cur, ka, part);
         part_add<4>(sPwA, c, L, part);
+        cur = nxt;
       }
     }
     if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
