@@ -97,7 +97,9 @@ class _RecurrentModel(nn.Module):
         init.zeros_(self.target_conv.bias)
         self.readout_dense = nn.Linear(1, 1)
         self.nl = nl
-        self.conv_mode = _lib.PTK_CONV_FP32
+        # 7x7 convolutions: 3-pass split-bf16 tcgen05 tiles (default) or strict-fp32 CUDA cores; both pass the
+        # same parity gate against the fp64 reference (tests/test_parity_gpu.py)
+        self.conv_mode = _lib.PTK_CONV_BF16X3
         if grad_method != "bptt":
             raise NotImplementedError("only grad_method='bptt' is implemented (utils/engine.py always passes it)")
 

@@ -47,6 +47,8 @@ __device__ __forceinline__ void tc_load_pixel(uint32_t tmem_base, int quad, int 
   for (int i = 0; i < 32; ++i) v[i] += lo[i];
 }
 __device__ long long g_tc_dbg[8];
+__device__ unsigned long long g_tc_times[1024][3];   // per CTA: start, mma-done, end (globaltimer ns)
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TC_STAMP(i) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 64) g_tc_dbg[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   const int H = a.H, W = a.W;
 
   TC_STAMP(0);
+  const int dbg_cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][0] = gtimer();
   // ---- one-time setup: barriers, TMEM, zero the operand image ------------------------------------
   if (tid == 0) {
     for (int i = 0; i < TC_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   // ---- epilogue -----------------------------------------------------------------------------------
   mbar_wait(accum_bar, 0);
   TC_STAMP(3);
+  if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][1] = gtimer();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int quad = warp & 3, jpar = warp >> 2;   // warps 0-3: tiles 0,2,4; warps 4-7: tiles 1,3
   const int nCta = gridDim.x * gridDim.y * gridDim.z;
@@ -266,6 +271,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
     }
   }
   TC_STAMP(4);
+  if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][2] = gtimer();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -297,6 +303,11 @@ int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
   conv7_tc_kernel<<<grid, 256, TC_SMEM, st>>>(a);
   PTK_LAUNCH_OK("conv7_tc_kernel");
+  return PTK_OK;
+}
+
+int read_tc_times(unsigned long long* out, int n) {
+  PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_tc_times, sizeof(unsigned long long) * 3 * n));
   return PTK_OK;
 }
 

@@ -33,6 +33,7 @@ int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st);
 int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st);   // wacc: [nCTA][49][32 oc][32 ic]
 size_t wgrad_tc_acc_floats(int B, int H, int W);
 int read_tc_debug(long long* out);
-int read_wt_debug(long long* out);   // cycle stamps of CTA 0 of the last conv7_tc_kernel (tuning aid)
+int read_wt_debug(long long* out);
+int read_tc_times(unsigned long long* out, int n);   // cycle stamps of CTA 0 of the last conv7_tc_kernel (tuning aid)
 
 }  // namespace ptk

@@ -40,10 +40,14 @@ CASES = [("int_small", "int", {}), ("int_tile", "int", {}), ("int_cfg1", "int", 
          ("hgru_small", "hgru", {}), ("hgru_tile", "hgru", {})]
 
 
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("name,kind,kw", CASES)
-def test_logits_and_all_grads_vs_fp64_reference(name, kind, kw):
+def test_logits_and_all_grads_vs_fp64_reference(name, kind, kw, conv_mode):
+    """both precisions of the path: tcgen05 split-bf16 convolutions (default) and strict-fp32 CUDA cores."""
+    from pathtracker_models_b200 import _lib
     case = load_case(name)
     m = _model(case, kind, **kw)
+    m.conv_mode = _lib.PTK_CONV_BF16X3 if conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
     out, loss, grads, pen = _run(case, m)
     assert out.shape == (case["shape"][0], 1) and pen.shape == (1,) and pen.device == out.device
     assert abs(loss.item() - case["loss"]) < 1e-5
@@ -59,8 +63,10 @@ def test_per_step_checkpoints_vs_oracle():
     """localises a failure: every I_t, E_t, pre-BN conv output and BN statistic of the CUDA forward."""
     from oracle import int_oracle as O
     from pathtracker_models_b200.functional import int_forward_raw
+    from pathtracker_models_b200 import _lib
     case = load_case("int_small")
     m = _model(case, "int")
+    m.conv_mode = _lib.PTK_CONV_FP32          # strict mode: per-step tensors agree to ~1e-6
     x = case["x"].float().cuda()
     logits, saved, _, _ = int_forward_raw(x, m.flat_parameters().detach(), m._config(), want_saved=True)
     B, T, H, W = case["shape"]
@@ -200,15 +206,3 @@ def test_conv7_operator_vs_torch(mode, shape):
     assert rel_err(ya, ref + acc.double()) < tol
     y2 = conv7(x.cuda(), w.cuda(), conv_mode=mode)
     assert torch.equal(y, y2)                       # deterministic
-
-
-@pytest.mark.parametrize("name,kind,kw", CASES)
-def test_bf16x3_tensor_core_mode_parity(name, kind, kw):
-    """conv_mode = PTK_CONV_BF16X3 (tcgen05 convolutions, FFMA weight gradient): same parity gate."""
-    from pathtracker_models_b200 import _lib
-    case = load_case(name)
-    m = _model(case, kind, **kw)
-    m.conv_mode = _lib.PTK_CONV_BF16X3
-    out, loss, grads, _ = _run(case, m)
-    bad = check_parity(case, out, grads)
-    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)

@@ -37,3 +37,19 @@ conv7(x, w, conv_mode=1, out=out); torch.cuda.synchronize()
 L.ptk_debug_tc_stamps(buf)
 t = list(buf)
 print("tc conv (accumulate) cycles: setup+zero %d, staging %d, mma %d, epilogue %d, total %d" % (t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[4]-t[0]))
+
+import numpy as np
+for acc in (False,):
+    conv7(x, w, conv_mode=1, want_stats=True); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); conv7(x, w, conv_mode=1, want_stats=True); e1.record(); torch.cuda.synchronize()
+    n = B * 2
+    tb = (ctypes.c_ulonglong * (3 * n))()
+    L.ptk_debug_tc_times(tb, n)
+    t = np.array(list(tb), dtype=np.float64).reshape(n, 3)
+    t0 = t[:, 0].min()
+    print("event time of the call (prep + memset + conv): %.1f us" % (e0.elapsed_time(e1) * 1e3))
+    print("CTA start skew (us): min %.1f  median %.1f  max %.1f" % (0, np.median(t[:, 0] - t0) / 1e3, (t[:, 0].max() - t0) / 1e3))
+    print("CTA lifetime (us): min %.1f median %.1f max %.1f" % tuple(np.percentile(t[:, 2] - t[:, 0], [0, 50, 100]) / 1e3))
+    print("CTA mma-done - start (us): median %.1f max %.1f" % tuple(np.percentile(t[:, 1] - t[:, 0], [50, 100]) / 1e3))
+    print("kernel span first start -> last end: %.1f us" % ((t[:, 2].max() - t0) / 1e3))
