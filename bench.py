@@ -149,7 +149,7 @@ def run_b200(args):
         return run_convlstm(args, dev, world, rank)
     ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
     model = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev)
-    model.conv_mode = _lib.PTK_CONV_BF16X3 if args.conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
+    model.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
     if world > 1:
         broadcast_parameters(model)
         attach_data_parallel(model)
@@ -236,7 +236,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "bf16" if args.conv_mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "%s %d frames %dx%d, 14 distractors, batch %d/GPU%s" % (
                            "InT" if args.model == "int" else "FFhGRU", T, HW, HW, B,
                            " (BASELINE configs[1])" if (args.model, T, HW, B) == ("int", 64, 32, 64) else ""),
@@ -247,7 +247,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "clocks": sampler.result(),
-            "roofline": {"bound": "tensor", "kernel": ("conv7_tc_kernel" if args.conv_mode == "bf16x3" else "conv7_ffma_kernel") + " (fwd + dgrad launches)",
+            "roofline": {"bound": "tensor", "kernel": ("conv7_ffma_kernel" if args.conv_mode == "fp32" else "conv7_tc_kernel") + " (fwd + dgrad launches)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tensor_peak) if achieved else None,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.conv_mode) if (args.model, T, HW, B) == ("int", 64, 32, 64) else None,
@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm"], help="non-headline configs (BASELINE configs[2..3])")
     ap.add_argument("--frames", type=int, default=T)
     ap.add_argument("--size", type=int, default=HW)
-    ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3"],
+    ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="7x7 convolutions: strict-fp32 FFMA, or 3-pass split-bf16 tcgen05 (both parity-gated)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -50,7 +50,8 @@ enum { PTK_CELL_INT = 0,   /* models/InT.py:157            gated_inhibition = in
 enum { PTK_ACT_SOFTPLUS = 0, /* F.softplus beta=1 threshold=20 (InT.py:184 default nl)    */
        PTK_ACT_TANH = 1      /* utils/engine.py:138-146 InT_tanh                          */ };
 enum { PTK_CONV_FP32 = 0,     /* strict fp32 FFMA convolutions (parity-gated default)     */
-       PTK_CONV_BF16X3 = 1    /* 3-pass split-bf16 tcgen05 tiles, fp32 accumulate         */ };
+       PTK_CONV_BF16X3 = 1,   /* 3-pass split-bf16 tcgen05 tiles, fp32 accumulate         */
+       PTK_CONV_BF16 = 2      /* single-pass bf16 tcgen05 tiles (NOT fp32-parity: ~1e-3 ..1e-2 on gradients; reported separately) */ };
 
 typedef struct PtkDims {
   int32_t B, T, H, W;  /* clip batch / frames / frame size.  x is [B,3,T,H,W]              */

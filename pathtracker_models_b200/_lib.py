@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libptk_b200.so")
 
 PTK_CELL_INT, PTK_CELL_HGRU = 0, 1
 PTK_ACT_SOFTPLUS, PTK_ACT_TANH = 0, 1
-PTK_CONV_FP32, PTK_CONV_BF16X3 = 0, 1
+PTK_CONV_FP32, PTK_CONV_BF16X3, PTK_CONV_BF16 = 0, 1, 2
 PTK_INT_NPARAM = 30
 
 EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_saved_bytes",

@@ -32,7 +32,7 @@ static int check_dims(const PtkDims* d, const char* who) {
   if (d->cell != PTK_CELL_INT && d->cell != PTK_CELL_HGRU) { set_error("%s: bad cell %d", who, d->cell); return PTK_EINVAL; }
   if (d->act != PTK_ACT_SOFTPLUS && d->act != PTK_ACT_TANH) { set_error("%s: bad act %d", who, d->act); return PTK_EINVAL; }
   if (d->no_inh && d->cell != PTK_CELL_INT) { set_error("%s: no_inh exists for the InT cell only (models/InT.py:167)", who); return PTK_EINVAL; }
-  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3) { set_error("%s: bad conv_mode %d", who, d->conv_mode); return PTK_EINVAL; }
+  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3 && d->conv_mode != PTK_CONV_BF16) { set_error("%s: bad conv_mode %d", who, d->conv_mode); return PTK_EINVAL; }
   return PTK_OK;
 }
 
@@ -71,7 +71,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);
   float* dgoal = cv.take<float>(S / C);
   size_t wacc_n = (size_t)4 * WGRAD_GROUPS * TAPS * 256;
-  if (dm->conv_mode == PTK_CONV_BF16X3) wacc_n = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
+  if (dm->conv_mode != PTK_CONV_FP32) wacc_n = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
   float* wacc_exc = cv.take<float>(wacc_n);
   float* wacc_inh = cv.take<float>(wacc_n);
   if (d) {
@@ -133,7 +133,7 @@ static int prep(IntDev* d, const float* params, cudaStream_t st) {
   for (int i = 0; i < 6; ++i) g.w[i] = d->gate[i];
   const float* w_inh = params + po.o[PTK_P_W_INH];
   const float* w_exc = params + po.o[PTK_P_W_EXC];
-  if (d->conv_mode == PTK_CONV_BF16X3) {
+  if (d->conv_mode != PTK_CONV_FP32) {
     // the four 200,704-byte banks hold the bf16 hi/lo tap streams instead of fp32 re-layouts
     int rc = launch_prep_weights_tc(w_inh, (void*)d->w_inh_f, (void*)d->w_inh_d, st);
     if (rc) return rc;
@@ -248,7 +248,7 @@ int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transp
   float* part = cv.take<float>((size_t)conv_num_ctas(B, H, W) * C * 2);
   unsigned* counter = cv.take<unsigned>(4);
   PTK_CUDA_OK(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned), st));
-  if (conv_mode == PTK_CONV_BF16X3) rc = launch_prep_weights_tc(weight, wf, wd, st);
+  if (conv_mode != PTK_CONV_FP32) rc = launch_prep_weights_tc(weight, wf, wd, st);
   else {
     IntGateSrc g = {};
     rc = run_prep_weights(weight, nullptr, wf, wd, nullptr, nullptr, g, nullptr, st);

@@ -261,7 +261,7 @@ static constexpr size_t WGRAD_SMEM = (size_t)(C * TH * TW + ICC * WG_IN_PITCH) *
 int conv_num_ctas(int B, int H, int W) { return B * (H / TH) * (W / TW); }
 
 int launch_conv7(const ConvArgs& a, cudaStream_t st) {
-  if (a.mode == PTK_CONV_BF16X3) return launch_conv7_tc(a, st);
+  if (a.mode != PTK_CONV_FP32) return launch_conv7_tc(a, st);
   static thread_local int configured_dev = -1;
   int dev;
   PTK_CUDA_OK(cudaGetDevice(&dev));

@@ -38,10 +38,11 @@ constexpr int TC_NST = 3;                              // weight ring stages
 constexpr int TC_SMEM = TC_A_BYTES + TC_NST * TC_STAGE + 256;
 
 // accumulator row of one pixel: 32 channels = cols [0,32) + cols [32,64) of M-tile j
-__device__ __forceinline__ void tc_load_pixel(uint32_t tmem_base, int quad, int j, float (&v)[32]) {
+__device__ __forceinline__ void tc_load_pixel(uint32_t tmem_base, int quad, int j, float (&v)[32], bool single) {
   float lo[32];
   const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 64);
   tmem_ld32(ta, v);
+  if (single) return;
   tmem_ld32(ta + 32, lo);
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] += lo[i];
@@ -51,6 +52,7 @@ __device__ unsigned long long g_tc_times[1024][3];   // per CTA: start, mma-done
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TC_STAMP(i) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 64) g_tc_dbg[i] = clock64(); } while (0)
 
+template <bool SINGLE>
 __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sA = smem_raw;                                   // [hi|lo][4 chunks][880 px][16 B]
@@ -187,8 +189,12 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
             const uint64_t dB = ((uint64_t)bHiW << 32) | (bW + (uint32_t)(2 * s) * (1024 >> 4));
             const uint32_t dcol = tmem_base + (uint32_t)(j * 64);
             if (elect_one()) {
-              umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (ky | kx | s) ? 1u : 0u);
-              umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+              if (SINGLE) {   // PTK_CONV_BF16: Ih*Wh only
+                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID32, (ky | kx | s) ? 1u : 0u);
+              } else {
+                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (ky | kx | s) ? 1u : 0u);
+                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+              }
             }
           }
         }
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
     for (int j = jpar; j < TC_MT; j += 2) {
       const int m = j * 128 + quad * 32 + lane, ro = m / TC_WP, xo = m - ro * TC_WP;
       float v[32];
-      tc_load_pixel(tmem_base, quad, j, v);
+      tc_load_pixel(tmem_base, quad, j, v, SINGLE);
       if (ro < TC_TH && xo < TC_TW) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[i] += v[i];
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
     for (int j = jpar; j < TC_MT; j += 2) {
       const int m = j * 128 + quad * 32 + lane, ro = m / TC_WP, xo = m - ro * TC_WP;
       float v[32];
-      tc_load_pixel(tmem_base, quad, j, v);
+      tc_load_pixel(tmem_base, quad, j, v, SINGLE);
       if (ro < TC_TH && xo < TC_TW) {
         float* dst = a.out + ((size_t)(b * C) * H + y0 + ro) * W + x0 + xo;
 #pragma unroll
@@ -299,9 +305,14 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
 }
 
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
-  PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
   dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
-  conv7_tc_kernel<<<grid, 256, TC_SMEM, st>>>(a);
+  if (a.mode == PTK_CONV_BF16) {
+    PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    conv7_tc_kernel<true><<<grid, 256, TC_SMEM, st>>>(a);
+  } else {
+    PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    conv7_tc_kernel<false><<<grid, 256, TC_SMEM, st>>>(a);
+  }
   PTK_LAUNCH_OK("conv7_tc_kernel");
   return PTK_OK;
 }

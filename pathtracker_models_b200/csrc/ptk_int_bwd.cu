@@ -743,7 +743,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int P = d.H * d.W;
   const int grid = d.pw_ctas;
   const int grid_c = grid;
-  const bool tc = (d.conv_mode == PTK_CONV_BF16X3);
+  const bool tc = (d.conv_mode != PTK_CONV_FP32);
   const int nWT = d.B * P / WPX;
   const int grid_a = grid;
   PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)PW_EW_CTAS * ACC_N * sizeof(float), st));
@@ -783,7 +783,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     ConvArgs c1{d.dAct, d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
-    WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first};
+    WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first, d.conv_mode};
     { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w1, st) : launch_wgrad7(w1, WGRAD_GROUPS, st); }
     if (rc) return rc;
     {
@@ -800,7 +800,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
       { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
-      WgradArgs w0{d.GeB[t & 1], d.dAct, d.wacc_inh, d.B, d.H, d.W, first};
+      WgradArgs w0{d.GeB[t & 1], d.dAct, d.wacc_inh, d.B, d.H, d.W, first, d.conv_mode};
       { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w0, st) : launch_wgrad7(w0, WGRAD_GROUPS, st); }
       if (rc) return rc;
     }
@@ -830,7 +830,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
 
 template <int CELL>
 static int run_backward_c(const IntDev& d, int act, cudaStream_t st) {
-  const bool fast = (d.conv_mode == PTK_CONV_BF16X3);
+  const bool fast = (d.conv_mode != PTK_CONV_FP32);
   if (act == PTK_ACT_SOFTPLUS) return fast ? run_backward_t<CELL, PTK_ACT_SOFTPLUS | ACT_FAST>(d, st)
                                            : run_backward_t<CELL, PTK_ACT_SOFTPLUS>(d, st);
   return fast ? run_backward_t<CELL, PTK_ACT_TANH | ACT_FAST>(d, st) : run_backward_t<CELL, PTK_ACT_TANH>(d, st);

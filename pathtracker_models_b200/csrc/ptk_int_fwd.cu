@@ -420,7 +420,7 @@ static int run_forward_ni(const IntDev& d, int cell, cudaStream_t st) {
 }
 
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st) {
-  const bool fast = (d.conv_mode == PTK_CONV_BF16X3);
+  const bool fast = (d.conv_mode != PTK_CONV_FP32);
   if (act == PTK_ACT_SOFTPLUS) return fast ? run_forward_ni<PTK_ACT_SOFTPLUS | ACT_FAST>(d, cell, st)
                                            : run_forward_ni<PTK_ACT_SOFTPLUS>(d, cell, st);
   return fast ? run_forward_ni<PTK_ACT_TANH | ACT_FAST>(d, cell, st) : run_forward_ni<PTK_ACT_TANH>(d, cell, st);

@@ -23,6 +23,7 @@ struct WgradArgs {
   float* wacc;         // [4*G][49][256] per-CTA accumulators
   int B, H, W;
   int first;           // overwrite instead of accumulate
+  int mode;            // PTK_CONV_BF16: single pass (hi parts only)
 };
 
 int conv_num_ctas(int B, int H, int W);

@@ -97,6 +97,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
 __device__ long long g_wt_dbg[8];
 #define WT_STAMP(i, t) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == (t)) g_wt_dbg[i] = clock64(); } while (0)
 
+template <bool SINGLE>
 __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sDY = smem_raw;                                  // [8 planes][608 px][16 B]
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
     const uint64_t dB0 = umma_desc(smem_u32(sIN), 128, WT_IN_PLANE);
     const uint32_t aHiW = (uint32_t)(dA0 >> 32), aLoW = (uint32_t)dA0;
     const uint32_t bHiW = (uint32_t)(dB0 >> 32), bLoW = (uint32_t)dB0;
-    constexpr uint32_t IDESC = wt_idesc();
+    constexpr uint32_t IDESC = SINGLE ? ((wt_idesc() & ~(0x3Fu << 17)) | ((uint32_t)(32 >> 3) << 17)) : wt_idesc();   // bf16: N = 32 (Ih only)
     for (int r = 0; r < WT_ROUNDS; ++r) {
       const int buf = r & 1, use = r >> 1;
       if (use > 0) mbar_wait(&tempty[buf], (uint32_t)((use - 1) & 1));
@@ -179,7 +180,12 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
         float v[32], w[32];
         const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256 + tl * 64);
         tmem_ld32(ta, v);
-        tmem_ld32(ta + 32, w);
+        if (SINGLE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = 0.f;
+        } else {
+          tmem_ld32(ta + 32, w);
+        }
         if (lane < 16) {
           float* dst = sOut + ((tl * 2 + half) * C + oc) * WT_OP;
 #pragma unroll
@@ -231,9 +237,14 @@ int read_wt_debug(long long* out) {
 size_t wgrad_tc_acc_floats(int B, int H, int W) { return (size_t)B * (H / WT_TH) * (W / WT_TW) * TAPS * C * C; }
 
 int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st) {
-  PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
   dim3 grid(a.W / WT_TW, a.H / WT_TH, a.B);
-  wgrad7_tc_kernel<<<grid, 256, WT_SMEM, st>>>(a);
+  if (a.mode == PTK_CONV_BF16) {
+    PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    wgrad7_tc_kernel<true><<<grid, 256, WT_SMEM, st>>>(a);
+  } else {
+    PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    wgrad7_tc_kernel<false><<<grid, 256, WT_SMEM, st>>>(a);
+  }
   PTK_LAUNCH_OK("wgrad7_tc_kernel");
   return PTK_OK;
 }

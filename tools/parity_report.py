@@ -8,7 +8,7 @@ from pathtracker_models_b200 import _lib
 
 for name, kind, kw in CASES:
     case = load_case(name)
-    for mode, mname in ((0, "fp32"), (1, "bf16x3")):
+    for mode, mname in ((0, "fp32"), (1, "bf16x3"), (2, "bf16")):
         m = _model(case, kind, **kw)
         m.conv_mode = mode
         out, loss, grads, _ = _run(case, m)
