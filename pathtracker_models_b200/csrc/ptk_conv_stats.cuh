@@ -18,8 +18,17 @@ __device__ __forceinline__ void conv_stats_fold(const ConvArgs& a, int nCta, int
   if (*sIsLast) {
     __threadfence();
     const int c = tid & 31, g = tid >> 5;
+    // the whole grid waits for this CTA: keep 16 independent loads in flight per thread
     double s1 = 0, s2 = 0, s3 = 0;
-    for (int i = g; i < nCta; i += 8) {
+    int i = g;
+    for (; i + 8 * 15 < nCta; i += 8 * 16) {
+      float2 pm[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pm[j] = __ldcg(reinterpret_cast<const float2*>(a.part + ((size_t)(i + 8 * j) * C + c) * 2));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s1 += pm[j].x; s2 += (double)pm[j].x * pm[j].x; s3 += pm[j].y; }
+    }
+    for (; i < nCta; i += 8) {
       const float2 pm = __ldcg(reinterpret_cast<const float2*>(a.part + ((size_t)i * C + c) * 2));
       s1 += pm.x;
       s2 += (double)pm.x * pm.x;

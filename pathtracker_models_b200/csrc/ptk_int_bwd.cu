@@ -34,7 +34,7 @@ __device__ __forceinline__ void acc_store(float* dst, float v, int first) {
 // step-local BatchNorm-backward sums: per-CTA partials -> last CTA folds them (double) into
 // bn_tot = (sum dV)/N, (sum dV*xhat)/N and accumulates d(bn bias), d(bn weight).
 __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const float* sPart /*[2][32]*/, int first,
-                                             int* sIsLast) {
+                                             int* sIsLast, float* sScratch /* >= 2 KB, 8-byte aligned, free */) {
   const int k = threadIdx.x, nCta = gridDim.x;
   if (k < 2 * C) d.bn_sums[(size_t)blockIdx.x * 2 * C + k] = sPart[k];
   __threadfence();
@@ -42,16 +42,40 @@ __device__ __forceinline__ void bn_sums_fold(const IntDev& d, int bn, const floa
   if (k == 0) *sIsLast = (atomicAdd(d.counter, 1u) == (unsigned)(nCta - 1));
   __syncthreads();
   if (*sIsLast) {
+    // The whole grid waits for this CTA, so the fold is latency-critical: 128 threads, 16 independent
+    // 16-byte loads in flight per thread (a dependent chain of nCta L2 round trips used to cost ~25 us).
+    // thread (q, g): float4 q of the 64 sums, rows g, g+8, g+16, ...; fixed order => deterministic.
     __threadfence();
+    const int q = k & 15, g = k >> 4;
+    double s[4] = {0, 0, 0, 0};
+    const float4* src = reinterpret_cast<const float4*>(d.bn_sums) + q;
+    int i = g;
+    for (; i + 8 * 15 < nCta; i += 8 * 16) {
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __ldcg(src + (size_t)(i + 8 * j) * (2 * C / 4));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s[0] += (double)v[j].x; s[1] += (double)v[j].y; s[2] += (double)v[j].z; s[3] += (double)v[j].w; }
+    }
+    for (; i < nCta; i += 8) {
+      const float4 v = __ldcg(src + (size_t)i * (2 * C / 4));
+      s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);   // rows g and g^1
+    double* sD = reinterpret_cast<double*>(sScratch);   // [4 warps][64]
+    if ((k & 31) < 16) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sD[(k >> 5) * 2 * C + 4 * q + e] = s[e];
+    }
+    __syncthreads();
     if (k < 2 * C) {
-      double s = 0;
-#pragma unroll 8
-      for (int i = 0; i < nCta; ++i) s += (double)__ldcg(d.bn_sums + (size_t)i * 2 * C + k);
+      const double t = (sD[k] + sD[2 * C + k]) + (sD[4 * C + k] + sD[6 * C + k]);
       const double N = (double)d.B * d.H * d.W;
-      d.bn_tot[k] = (float)(s / N);
+      d.bn_tot[k] = (float)(t / N);
       // k < C: sum dV -> d(bn bias); k >= C: sum dV*xhat -> d(bn weight)
       double* a = d.bn_acc + (size_t)bn * 2 * C + k;
-      *a = first ? s : (*a + s);
+      *a = first ? t : (*a + t);
     }
     if (k == 0) *d.counter = 0u;
   }
@@ -111,10 +135,10 @@ __device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, size_t idx
 }
 __device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* sKa, float* sGa, float* sW1, float* sB1,
                                                  float* sM1, float* sR1) {
-  cta_fill(sKa, d.kappa, C);
-  cta_fill(sGa, d.gamma, C);
-  cta_fill(sW1, d.bn_w[1], C);
-  cta_fill(sB1, d.bn_b[1], C);
+  cta_fill_async(sKa, d.kappa, C);     // the caller commits / waits (cp.async)
+  cta_fill_async(sGa, d.gamma, C);
+  cta_fill_async(sW1, d.bn_w[1], C);
+  cta_fill_async(sB1, d.bn_b[1], C);
   if (threadIdx.x < C) {
     const float* st = d.stat(t, 1);
     sM1[threadIdx.x] = st[threadIdx.x];
@@ -125,11 +149,13 @@ __device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* 
 // stand-alone (b1)-(b2) kernel: only used for the last time step (the others are fused into bwd_d).
 template <int ACT>
 __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int first) {
-  __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
-  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
+  __shared__ __align__(16) float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
+  __shared__ __align__(16) float sPart[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
   bwd_a_fill_const(d, t, sKa, sGa, sW1, sB1, sM1, sR1);
+  cp_async_commit();
   for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  cp_async_wait<0>();
   __syncthreads();
   const BwdAConst k{sKa, sGa, sW1, sB1, sM1, sR1};
   const Lane L;
@@ -159,7 +185,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
     acc_store(acc + ACC_KAPPA + threadIdx.x, sTot[threadIdx.x], first);
     acc_store(acc + ACC_GAMMA + threadIdx.x, sTot[C + threadIdx.x], first);
   }
-  bn_sums_fold(d, 1, sTot + 2 * C, first, &sIsLast);
+  bn_sums_fold(d, 1, sTot + 2 * C, first, &sIsLast, sPart);
 }
 
 // (b3)/(b9): dAct <- w*rstd*(dAct - mean(dAct) - xhat*mean(dAct*xhat)), xhat from the saved conv output.
@@ -184,6 +210,17 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __
 // ------------------------------------------------------------------------------------------------
 // (b5)-(b8): complete dI' (gI), geb, checkpointed I_t, A_t, Y0_t, G_i, x_t.
 // writes dAct <- dU, dGe, dX, gI <- dI (+ dS for InT), dS (hGRU), gi and X (scratch for gate_wgrad).
+struct BwdCIn { float4 gi, cg, I, S, y0, G; };   // one channel of the patch, prefetched one channel ahead
+template <int CELL>
+__device__ __forceinline__ void bwd_c_load(const IntDev& d, const float* It, const float* At, const float* Y0,
+                                           const float* Git, size_t idx, BwdCIn& r) {
+  r.gi = ld4(d.gI + idx);
+  r.cg = ld4(d.cgI + idx);      // dY1 *7^T W_exc (b4), written by the transposed convolution
+  r.I = ld4(It + idx);
+  if (CELL != PTK_CELL_INT) r.S = ld4(At + idx);
+  r.y0 = ld4(Y0 + idx);
+  r.G = ld4(Git + idx);
+}
 template <int CELL, int ACT>
 __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
@@ -192,26 +229,9 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   float* sWew = sWiu + C * C;
   float* sWeu = sWew + C * C;
   float* tiles = sWeu + C * C;
-  __shared__ float sWp[C * 3], sbp[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
-  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
+  __shared__ __align__(16) float sWp[C * 3], sbp[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
+  __shared__ __align__(16) float sPart[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
-  cta_fill(sWiw, d.gate[2], C * C);
-  cta_fill(sWiu, d.gate[3], C * C);
-  cta_fill(sWew, d.gate[4], C * C);
-  cta_fill(sWeu, d.gate[5], C * C);
-  cta_fill(sWp, d.Wp, C * 3);
-  cta_fill(sbp, d.bp, C);
-  cta_fill(sAl, d.alpha, C);
-  cta_fill(sMu, d.mu, C);
-  cta_fill(sW0, d.bn_w[0], C);
-  cta_fill(sB0, d.bn_b[0], C);
-  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
-  if (threadIdx.x < C) {
-    const float* st = d.stat(t, 0);
-    sM0[threadIdx.x] = st[threadIdx.x];
-    sR0[threadIdx.x] = st[C + threadIdx.x];
-  }
-  __syncthreads();
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   float* sGi = tiles + warp * 2 * TILE_F;
@@ -221,13 +241,43 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   const float* At = d.A_at(t);
   const float* Y0 = d.Y0_at(t);
   const float* Git = d.Gi_at(t);
-  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+  int wt = blockIdx.x * 4 + warp;
+  BwdCIn cur;
+  float xin[3][4];
+  if (wt < nWT) {     // first tile: operands requested before (and overlapping) the weight fill
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
+    if (CELL != CELL_NOINH) bwd_c_load<CELL>(d, It, At, Y0, Git, (size_t)b * C * P + pix_base + L.pxo + (size_t)L.oc0 * P, cur);
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+  }
+  cta_fill_async(sWiw, d.gate[2], C * C);
+  cta_fill_async(sWiu, d.gate[3], C * C);
+  cta_fill_async(sWew, d.gate[4], C * C);
+  cta_fill_async(sWeu, d.gate[5], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  cta_fill_async(sAl, d.alpha, C);
+  cta_fill_async(sMu, d.mu, C);
+  cta_fill_async(sW0, d.bn_w[0], C);
+  cta_fill_async(sB0, d.bn_b[0], C);
+  cp_async_commit();
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  if (threadIdx.x < C) {
+    const float* st = d.stat(t, 0);
+    sM0[threadIdx.x] = st[threadIdx.x];
+    sR0[threadIdx.x] = st[C + threadIdx.x];
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
-    warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
-    cp_async_commit();
-    float xin[3][4];
-    frame_px(d.fv, b, t, pix, d.W, xin);
+    if (!firstTile) {
+      warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
+      cp_async_commit();
+      if (CELL != CELL_NOINH) bwd_c_load<CELL>(d, It, At, Y0, Git, base + (size_t)L.oc0 * P, cur);
+      frame_px(d.fv, b, t, pix, d.W, xin);
+    }
     if (CELL == CELL_NOINH) {
       // InT(no_inh=True): only (b5) exists.  dS = We_w^T ge feeds dE (S = E), dGe = dI' + We_u^T ge.
 #pragma unroll 1
@@ -262,22 +312,18 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
       const size_t idx = base + (size_t)c * P;
       float gIn[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oDI[4], oZ[4], oDs[4];
       float part[4] = {0.f, 0.f, 0.f, 0.f};
-      {
-        float cg[4];
-        ld4v(d.gI + idx, gIn);
-        ld4v(d.cgI + idx, cg);      // + dY1 *7^T W_exc (b4), written by the transposed convolution
-#pragma unroll
-        for (int p = 0; p < 4; ++p) gIn[p] += cg[p];
-      }
-      ld4v(It + idx, I);
+      BwdCIn nxt;
+      if (o < 7) bwd_c_load<CELL>(d, It, At, Y0, Git, idx + P, nxt);     // prefetch the next channel
+      gIn[0] = cur.gi.x + cur.cg.x; gIn[1] = cur.gi.y + cur.cg.y; gIn[2] = cur.gi.z + cur.cg.z; gIn[3] = cur.gi.w + cur.cg.w;
+      I[0] = cur.I.x; I[1] = cur.I.y; I[2] = cur.I.z; I[3] = cur.I.w;
       if (CELL == PTK_CELL_INT) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) S[p] = I[p];
       } else {
-        ld4v(At + idx, S);
+        S[0] = cur.S.x; S[1] = cur.S.y; S[2] = cur.S.z; S[3] = cur.S.w;
       }
-      ld4v(Y0 + idx, y0);
-      ld4v(Git + idx, G);
+      y0[0] = cur.y0.x; y0[1] = cur.y0.y; y0[2] = cur.y0.z; y0[3] = cur.y0.w;
+      G[0] = cur.G.x; G[1] = cur.G.y; G[2] = cur.G.z; G[3] = cur.G.w;
       stem_pre(sWp, sbp, c, xin, X);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -312,6 +358,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
       tile_st(sGi, L, o, oGi);
       if (CELL == PTK_CELL_HGRU) st4(d.gI + idx, oDI);
       part_add<4>(sPw, c, L, part);
+      if (o < 7) cur = nxt;
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -336,10 +383,20 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
     acc_store(acc + ACC_ALPHA + threadIdx.x, sTot[threadIdx.x], first);
     acc_store(acc + ACC_MU + threadIdx.x, sTot[C + threadIdx.x], first);
   }
-  bn_sums_fold(d, 0, sTot + 2 * C, first, &sIsLast);
+  bn_sums_fold(d, 0, sTot + 2 * C, first, &sIsLast, sPart);
 }
 
 // ------------------------------------------------------------------------------------------------
+struct BwdDIn { float4 a, dge, cg, e, ge, ds; };   // one channel of the patch, prefetched one channel ahead
+template <int CELL>
+__device__ __forceinline__ void bwd_d_load(const IntDev& d, const float* At, const float* Et, size_t idx, BwdDIn& r) {
+  r.a = ld4(At + idx);
+  r.dge = ld4(d.dGe + idx);
+  r.cg = ld4(d.cGe + idx);
+  r.e = ld4(Et + idx);
+  r.ge = ld4(d.gE + idx);
+  if (CELL != PTK_CELL_INT) r.ds = ld4(d.dS + idx);
+}
 // (b10)-(b12): complete dGe, dE partial (gE), A_t, E_t, dX, [dS], x_t.
 // writes gE <- dE (for step t-1), a (scratch for gate_wgrad), stem parameter sums, optional dx.
 // When t > 0 the kernel continues with (b1)-(b2) of step t-1 on the same patch (dE stays on chip).
@@ -349,47 +406,54 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   float* sWaw = dsm;              // [out][in]
   float* sWau = sWaw + C * C;
   float* tiles = sWau + C * C;
-  __shared__ float sWp[C * 3], sbp[C];
-  __shared__ float sPart[4 * 4 * C], sTot[4 * C];
-  __shared__ float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C], sPartA[4 * 4 * C], sTotA[4 * C];
+  __shared__ __align__(16) float sWp[C * 3], sbp[C];
+  __shared__ __align__(16) float sPart[4 * 4 * C], sTot[4 * C];
+  __shared__ __align__(16) float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C], sPartA[4 * 4 * C], sTotA[4 * C];
   __shared__ int sIsLast;
   const bool fuse = (t > 0);
-  cta_fill(sWaw, d.gate[0], C * C);
-  cta_fill(sWau, d.gate[1], C * C);
-  cta_fill(sWp, d.Wp, C * 3);
-  cta_fill(sbp, d.bp, C);
-  if (fuse) bwd_a_fill_const(d, t - 1, sKa, sGa, sW1, sB1, sM1, sR1);
-  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) { sPart[i] = 0.f; sPartA[i] = 0.f; }
-  __syncthreads();
-  const BwdAConst ka{sKa, sGa, sW1, sB1, sM1, sR1};
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* Et = d.E_at(t);
+  const float* At = d.A_at(t);
+  int wt = blockIdx.x * 4 + warp;
+  BwdDIn cur;
+  float xin[3][4];
+  if (wt < nWT) {     // first tile: operands requested before (and overlapping) the weight fill
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    bwd_d_load<CELL>(d, At, Et, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
+    frame_px(d.fv, b, t, pix, d.W, xin);
+  }
+  cta_fill_async(sWaw, d.gate[0], C * C);
+  cta_fill_async(sWau, d.gate[1], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  if (fuse) bwd_a_fill_const(d, t - 1, sKa, sGa, sW1, sB1, sM1, sR1);
+  cp_async_commit();
+  for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) { sPart[i] = 0.f; sPartA[i] = 0.f; }
+  cp_async_wait<0>();
+  __syncthreads();
+  const BwdAConst ka{sKa, sGa, sW1, sB1, sM1, sR1};
   float* sA = tiles + warp * 2 * TILE_F;
   float* sB = sA + TILE_F;             // parked dE for the fused (b1)-(b2) tail
   float* sPw = sPart + warp * 4 * C;   // [0] d bp, [1..3] d Wp[:, i]
   float* sPwA = sPartA + warp * 4 * C;
-  const float* Et = d.E_at(t);
-  const float* At = d.A_at(t);
-  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
-    float xin[3][4];
-    frame_px(d.fv, b, t, pix, d.W, xin);
+    if (!firstTile) {
+      bwd_d_load<CELL>(d, At, Et, base + (size_t)L.oc0 * P, cur);
+      frame_px(d.fv, b, t, pix, d.W, xin);
+    }
 #pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const size_t idx = base + (size_t)(L.oc0 + o) * P;
-      float A[4], dGe[4], E[4], gE[4], dS[4] = {0.f, 0.f, 0.f, 0.f}, oa[4], ode[4];
-      ld4v(At + idx, A);
-      {
-        float cg[4];
-        ld4v(d.dGe + idx, dGe);
-        ld4v(d.cGe + idx, cg);      // + dY0 *7^T W_inh (b9)
-#pragma unroll
-        for (int p = 0; p < 4; ++p) dGe[p] += cg[p];
-      }
-      ld4v(Et + idx, E);
-      ld4v(d.gE + idx, gE);
-      if (CELL != PTK_CELL_INT) ld4v(d.dS + idx, dS);
+      BwdDIn nxt;
+      if (o < 7) bwd_d_load<CELL>(d, At, Et, idx + P, nxt);     // prefetch the next channel
+      const float A[4] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w}, E[4] = {cur.e.x, cur.e.y, cur.e.z, cur.e.w};
+      const float gE[4] = {cur.ge.x, cur.ge.y, cur.ge.z, cur.ge.w};
+      const float dGe[4] = {cur.dge.x + cur.cg.x, cur.dge.y + cur.cg.y, cur.dge.z + cur.cg.z, cur.dge.w + cur.cg.w};   // + dY0 *7^T W_inh (b9)
+      float dS[4] = {0.f, 0.f, 0.f, 0.f}, oa[4], ode[4];
+      if (CELL != PTK_CELL_INT) { dS[0] = cur.ds.x; dS[1] = cur.ds.y; dS[2] = cur.ds.z; dS[3] = cur.ds.w; }
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         // hGRU: S = A, so dS joins dA;  no_inh: S = E, so dS joins dE
@@ -397,6 +461,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
         oa[p] = dA * A[p] * (1.0f - A[p]);
         ode[p] = fmaf(dGe[p], A[p], gE[p]) + (CELL == CELL_NOINH ? dS[p] : 0.0f);
       }
+      if (o < 7) cur = nxt;
       st4(d.aS + idx, oa);
       st4(d.gE + idx, ode);          // parked: completed by the transposed product below
       tile_st(sA, L, o, oa);
@@ -410,6 +475,8 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
     warp_gemm(acc, sA, sWaw, L);     // dX += Wa_w^T a
     __syncwarp();
     acc_to_tile(sA, L, acc);         // park dX; each thread re-reads only its own patch
+    BwdAIn acur, anxt;
+    if (fuse) bwd_a_load(d, t - 1, 0, base + (size_t)L.oc0 * P, acur);   // in flight during the stem loop below
     float dxs[3][4];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -434,18 +501,16 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
       part_add<4>(sPw, c, L, part);
     }
     if (fuse) {              // (b1)-(b2) of step t-1, dE' taken from the parked tile
-      BwdAIn cur, nxt;
-      bwd_a_load(d, t - 1, 0, base + (size_t)L.oc0 * P, cur);
 #pragma unroll 1
       for (int o = 0; o < 8; ++o) {
         const int c = L.oc0 + o;
         const size_t idx = base + (size_t)c * P;
-        if (o < 7) bwd_a_load(d, t - 1, 0, idx + P, nxt);          // prefetch next channel
+        if (o < 7) bwd_a_load(d, t - 1, 0, idx + P, anxt);          // prefetch next channel
         float gEn[4], part[4] = {0.f, 0.f, 0.f, 0.f};
         tile_ld(sB, L, o, gEn);
-        bwd_a_channel<ACT>(d, t - 1, idx, c, gEn, cur, ka, part);
+        bwd_a_channel<ACT>(d, t - 1, idx, c, gEn, acur, ka, part);
         part_add<4>(sPwA, c, L, part);
-        cur = nxt;
+        acur = anxt;
       }
     }
     if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
@@ -486,7 +551,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
       acc_store(acc + ACC_KAPPA + threadIdx.x, sTotA[threadIdx.x], 0);
       acc_store(acc + ACC_GAMMA + threadIdx.x, sTotA[C + threadIdx.x], 0);
     }
-    bn_sums_fold(d, 1, sTotA + 2 * C, 0, &sIsLast);
+    bn_sums_fold(d, 1, sTotA + 2 * C, 0, &sIsLast, sPartA);
   }
 }
 

@@ -38,10 +38,8 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
                                                const float* sE, const float* sWaw, const float* sWau,
                                                const float* sba, const float* sWp, const float* sbp,
                                                const float* sWew, const float* sWeu, const float* sbe,
-                                               const Lane& L) {
+                                               const Lane& L, const float (&xin)[3][4]) {
   const int P = d.H * d.W, pix = pix_base + L.pxo;
-  float xin[3][4];
-  frame_px(d.fv, b, t, pix, d.W, xin);
   stem_to_tile<ACT>(sX, sWp, sbp, xin, L);
   __syncwarp();
   float acc[4][8];
@@ -110,14 +108,24 @@ __global__ void __launch_bounds__(128, 4) int_pre_kernel(IntDev d, int t) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
     warp_tile_load_async(sE, d.E_at(t), (size_t)C * P, b, pix_base, P);
     cp_async_commit();
+    float xin[3][4];
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
     cp_async_wait<0>();
     __syncwarp();
-    attention_tile<ACT, NOINH>(d, t, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L);
+    attention_tile<ACT, NOINH>(d, t, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L, xin);
     __syncwarp();
   }
 }
 
 // eqs (3b)-(9): BatchNorm0 apply, inhibition drive, inhibition gate + blend, excitation gate.
+struct MidIn { float4 s, i, y0; };
+template <int CELL>
+__device__ __forceinline__ void mid_load(const float* Sg, const float* It, const float* Y0, size_t base, int c, int P,
+                                         MidIn& r) {
+  r.s = ld4(Sg + (size_t)c * P);
+  if (CELL != PTK_CELL_INT) r.i = ld4(It + base + (size_t)c * P);
+  r.y0 = ld4(Y0 + base + (size_t)c * P);
+}
 template <int CELL, int ACT>
 __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   extern __shared__ __align__(16) float dsm[];
@@ -126,15 +134,32 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   float* sWew = sWiu + C * C;
   float* sWeu = sWew + C * C;
   float* tiles = sWeu + C * C;
-  __shared__ float sWp[C * 3], sbp[C], sbi[C], sbe[C], sAl[C], sMu[C], sScale[C], sShift[C];
-  cta_fill(sWiw, d.gateT[2], C * C);
-  cta_fill(sWiu, d.gateT[3], C * C);
-  cta_fill(sWew, d.gateT[4], C * C);
-  cta_fill(sWeu, d.gateT[5], C * C);
-  cta_fill(sWp, d.Wp, C * 3);
-  cta_fill(sbp, d.bp, C);
-  cta_fill(sAl, d.alpha, C);
-  cta_fill(sMu, d.mu, C);
+  __shared__ __align__(16) float sWp[C * 3], sbp[C], sbi[C], sbe[C], sAl[C], sMu[C], sScale[C], sShift[C];
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  float* sS = tiles + warp * 2 * TILE_F;
+  float* sGX = sS + TILE_F;            // holds Ge for the excitation-gate product, then X
+  const float* It = d.I_at(t);
+  float* Iout = d.I_at(t + 1);
+  const float* Y0 = d.Y0_at(t);
+  int wt = blockIdx.x * 4 + warp;
+  float xin[3][4];
+  if (wt < nWT) {     // the first tile's operands are requested before (and overlap) the weight fill
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
+    else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
+    warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+  }
+  cta_fill_async(sWiw, d.gateT[2], C * C);
+  cta_fill_async(sWiu, d.gateT[3], C * C);
+  cta_fill_async(sWew, d.gateT[4], C * C);
+  cta_fill_async(sWeu, d.gateT[5], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  cta_fill_async(sAl, d.alpha, C);
+  cta_fill_async(sMu, d.mu, C);
+  cp_async_commit();
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
     sbi[c] = __ldg(d.gate_b[2] + c) + __ldg(d.gate_b[3] + c);
@@ -144,26 +169,21 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
     sScale[c] = sc;                   // U = Y0*scale + shift
     sShift[c] = __ldg(d.bn_b[0] + c) - st[c] * sc;
   }
+  cp_async_wait<0>();
   __syncthreads();
-  const Lane L;
-  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
-  float* sS = tiles + warp * 2 * TILE_F;
-  float* sGX = sS + TILE_F;            // holds Ge for the excitation-gate product, then X
-  const float* It = d.I_at(t);
-  float* Iout = d.I_at(t + 1);
-  const float* Y0 = d.Y0_at(t);
-  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
     const float* Sg = (CELL == PTK_CELL_INT) ? It + base : d.A_at(t) + (size_t)b * d.a_bstride + pix;
-    if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
-    else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
-    warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
-    cp_async_commit();
-    float xin[3][4];
-    frame_px(d.fv, b, t, pix, d.W, xin);
-    cp_async_wait<0>();
-    __syncwarp();
+    if (!firstTile) {
+      if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
+      else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
+      warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
+      cp_async_commit();
+      frame_px(d.fv, b, t, pix, d.W, xin);
+      cp_async_wait<0>();
+      __syncwarp();
+    }
     float acc[4][8];
     // excitation gate (eq. 9) first: G_e = sigmoid(We_w S + We_u Ge + b), written straight to the checkpoint
     acc_fill(acc, sbe, L);
@@ -177,6 +197,8 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
       st4(d.Gex_at(t) + base + (size_t)(L.oc0 + o) * P, gx);
     }
     __syncwarp();
+    MidIn cur;                                    // channel 0 of the blend loop: in flight during the products below
+    mid_load<CELL>(Sg, It, Y0, base, L.oc0, P, cur);
     stem_to_tile<ACT>(sGX, sWp, sbp, xin, L);     // the Ge tile is free now: X takes its place
     __syncwarp();
     // inhibition gate pre-activation (eq. 7), parked in the S tile (S is re-read from global below)
@@ -189,17 +211,19 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float X[4], S[4], I[4], y0[4], gi[4], out[4];
+      MidIn nxt;
+      if (o < 7) mid_load<CELL>(Sg, It, Y0, base, c + 1, P, nxt);
+      float X[4], gi[4], out[4];
       tile_ld(sGX, L, o, X);
       tile_ld(sS, L, o, gi);
-      ld4v(Sg + (size_t)c * P, S);
+      const float S[4] = {cur.s.x, cur.s.y, cur.s.z, cur.s.w}, y0[4] = {cur.y0.x, cur.y0.y, cur.y0.z, cur.y0.w};
+      float I[4];
       if (CELL == PTK_CELL_INT) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) I[p] = S[p];
       } else {
-        ld4v(It + idx, I);
+        I[0] = cur.i.x; I[1] = cur.i.y; I[2] = cur.i.z; I[3] = cur.i.w;
       }
-      ld4v(Y0 + idx, y0);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         gi[p] = sigm<ACT>(gi[p]);
@@ -211,12 +235,21 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
       }
       st4(d.Gi_at(t) + idx, gi);
       st4(Iout + idx, out);
+      if (o < 7) cur = nxt;
     }
     __syncwarp();
   }
 }
 
 // eqs (10b)-(13) for step t, then (1)-(2) for step t+1 (if any).
+// Latency structure (profiles/r1f_pointwise_full.txt: global-load scoreboard stalls dominated): the first
+// tile's operands are requested before the weight fill, the fill itself is cp.async, and the per-channel
+// loop prefetches the next channel's operands while the current one is computed.
+struct PostIn { float4 y1, i2, e, gx; };
+__device__ __forceinline__ void post_load(const float* Y1, const float* I2, const float* Et, const float* Gx,
+                                          size_t idx, PostIn& r) {
+  r.y1 = ld4(Y1 + idx); r.i2 = ld4(I2 + idx); r.e = ld4(Et + idx); r.gx = ld4(Gx + idx);
+}
 template <int ACT, bool NOINH>
 __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int has_next) {
   extern __shared__ __align__(16) float dsm[];
@@ -225,15 +258,31 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
   float* sWew = sWau + C * C;                       // only staged when NOINH
   float* sWeu = sWew + (NOINH ? C * C : 0);
   float* tiles = sWeu + (NOINH ? C * C : 0);
-  __shared__ float sWp[C * 3], sbp[C], sba[C], sbe[C], sKa[C], sGa[C], sScale[C], sShift[C], sWr[C];
-  cta_fill(sWaw, d.gateT[0], C * C);
-  cta_fill(sWau, d.gateT[1], C * C);
-  if (NOINH) { cta_fill(sWew, d.gateT[4], C * C); cta_fill(sWeu, d.gateT[5], C * C); }
-  cta_fill(sWp, d.Wp, C * 3);
-  cta_fill(sbp, d.bp, C);
-  cta_fill(sKa, d.kappa, C);
-  cta_fill(sGa, d.gamma, C);
-  cta_fill(sWr, d.Wr, C);
+  __shared__ __align__(16) float sWp[C * 3], sbp[C], sba[C], sbe[C], sKa[C], sGa[C], sScale[C], sShift[C], sWr[C];
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* Et = d.E_at(t);
+  const float* I2 = d.I_at(t + 1);
+  float* Eout = d.E_at(t + 1);
+  const float* Y1 = d.Y1_at(t);
+  const float* Gx = d.Gex_at(t);
+  int wt = blockIdx.x * 4 + warp;
+  PostIn cur;
+  float xin[3][4];
+  if (wt < nWT) {    // first tile: operands of channel 0 and the next frame's pixels are in flight during the fill
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    post_load(Y1, I2, Et, Gx, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
+    if (has_next) frame_px(d.fv, b, t + 1, pix, d.W, xin);
+  }
+  cta_fill_async(sWaw, d.gateT[0], C * C);
+  cta_fill_async(sWau, d.gateT[1], C * C);
+  if (NOINH) { cta_fill_async(sWew, d.gateT[4], C * C); cta_fill_async(sWeu, d.gateT[5], C * C); }
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  cta_fill_async(sKa, d.kappa, C);
+  cta_fill_async(sGa, d.gamma, C);
+  cta_fill_async(sWr, d.Wr, C);
+  cp_async_commit();
   if (threadIdx.x < C) {
     const int c = threadIdx.x;
     sba[c] = __ldg(d.gate_b[0] + c) + __ldg(d.gate_b[1] + c);
@@ -243,30 +292,28 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
     sScale[c] = sc;
     sShift[c] = __ldg(d.bn_b[1] + c) - st[c] * sc;
   }
+  cp_async_wait<0>();
   __syncthreads();
-  const Lane L;
-  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   float* sX = tiles + warp * 2 * TILE_F;
   float* sE = sX + TILE_F;
-  const float* Et = d.E_at(t);
-  const float* I2 = d.I_at(t + 1);
-  float* Eout = d.E_at(t + 1);
-  const float* Y1 = d.Y1_at(t);
-  const float* Gx = d.Gex_at(t);
   const float br = __ldg(d.br);
-  for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
+    if (!firstTile) {
+      post_load(Y1, I2, Et, Gx, base + (size_t)L.oc0 * P, cur);
+      if (has_next) frame_px(d.fv, b, t + 1, pix, d.W, xin);
+    }
     float sread[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float y1[4], i2[4], e[4], gx[4], e2[4];
-      ld4v(Y1 + idx, y1);
-      ld4v(I2 + idx, i2);
-      ld4v(Et + idx, e);
-      ld4v(Gx + idx, gx);
+      PostIn nxt;
+      if (o < 7) post_load(Y1, I2, Et, Gx, idx + P, nxt);
+      const float y1[4] = {cur.y1.x, cur.y1.y, cur.y1.z, cur.y1.w}, i2[4] = {cur.i2.x, cur.i2.y, cur.i2.z, cur.i2.w};
+      const float e[4] = {cur.e.x, cur.e.y, cur.e.z, cur.e.w}, gx[4] = {cur.gx.x, cur.gx.y, cur.gx.z, cur.gx.w};
+      float e2[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const float V = fmaf(y1[p], sScale[c], sShift[c]);
@@ -277,6 +324,7 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
       }
       st4(Eout + idx, e2);
       tile_st(sE, L, o, e2);
+      if (o < 7) cur = nxt;
     }
     if (d.states != nullptr) {   // testmode: states.append(readout_conv(excitation)), InT.py:233
 #pragma unroll
@@ -287,7 +335,7 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
       }
       if (L.og == 0) st4(d.states + ((size_t)b * d.T + t) * P + pix, sread);
     }
-    if (has_next) attention_tile<ACT, NOINH>(d, t + 1, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L);
+    if (has_next) attention_tile<ACT, NOINH>(d, t + 1, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L, xin);
     __syncwarp();
   }
 }

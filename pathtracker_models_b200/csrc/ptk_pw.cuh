@@ -26,8 +26,11 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[4][8], const float* __res
                                           const float* __restrict__ sW, const Lane& L) {
   const float* tp = tile + L.pxo;
   const float* wp = sW + L.oc0;
+#ifndef PTK_GEMM_IC
+#define PTK_GEMM_IC C
+#endif
 #pragma unroll 8
-  for (int ic = 0; ic < C; ++ic) {
+  for (int ic = 0; ic < PTK_GEMM_IC; ++ic) {
     const float4 v = *reinterpret_cast<const float4*>(tp + ic * TP);
     const float4 w0 = *reinterpret_cast<const float4*>(wp + ic * C);
     const float4 w1 = *reinterpret_cast<const float4*>(wp + ic * C + 4);
@@ -85,6 +88,11 @@ __device__ __forceinline__ void stem_pre(const float* sWp, const float* sbp, int
 
 __device__ __forceinline__ void cta_fill(float* dst, const float* __restrict__ src, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+// asynchronous variant (cp.async, 16 B per request): n % 4 == 0, both pointers 16-byte aligned.  The caller
+// commits / waits; used so that the weight fill overlaps the first tile's operand loads.
+__device__ __forceinline__ void cta_fill_async(float* dst, const float* __restrict__ src, int n) {
+  for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4) cp_async16(dst + i, src + i);
 }
 
 // registers <-> the thread's patch of a tile, all 8 channels (static indices; used to park GEMM
