@@ -559,10 +559,26 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 // gate weight / bias gradients of one step: six 32x32 outer-product sums over all pixels
 //   dWe_w += ge (x) S, dWe_u += ge (x) Ge, dWi_w += gi (x) X, dWi_u += gi (x) S, dWa_w += a (x) X,
 //   dWa_u += a (x) E;  d(bias) += sum ge / gi / a.
-// 384 threads = 6 matrices x 64 threads (4x4 outputs each); 64-pixel tiles, cp.async double-buffered.
+// 64-pixel tiles, cp.async double-buffered; 384 threads.
+//   MMA = false (strict fp32 mode): 6 matrices x 64 threads, 4x4 outputs each, FFMA.
+//   MMA = true (tensor-core modes): 12 warps = 6 matrices x 2 row halves; each warp owns a 16 x 32 block of
+//     dW as mma.sync m16n8k8 tf32 fragments (K = pixels).  Operands are split x = hi + lo in registers
+//     (mask + subtract) and three products hi*hi + hi*lo + lo*hi are issued, so the result carries
+//     ~2^-21 relative error per product (same idea as the split-bf16 convolutions).  The [c][GSP] tile
+//     layout (GSP = 68 = 4 mod 32) makes every fragment load a conflict-free LDS.32.
 constexpr int GPX = 64, GSP = GPX + 4, GT_F = C * GSP;
 
-template <int CELL>
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;           // truncation: x - hi is exact and |lo| < 2^-10 |x|
+  lo = __float_as_uint(x - __uint_as_float(hi));   // the MMA reads only the tf32 bits of lo (error ~2^-20 |x|)
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int CELL, bool MMA>
 __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
@@ -576,7 +592,8 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
       cp_async16(dstb + k * GT_F + c * GSP + part * 4, src[k] + ((size_t)b * C + c) * P + pix_base + part * 4);
     }
   };
-  const int m = tid >> 6, r = tid & 63, ocq = r >> 3, icq = r & 7;
+  const int m = tid >> 6, r = tid & 63, ocq = r >> 3, icq = r & 7;   // MMA: m = warp / 2 as well
+  const int half = (tid >> 5) & 1, fg = (tid & 31) >> 2, ft = tid & 3;   // MMA fragment coordinates
   const int gsel = m >> 1;                       // 0: ge, 1: gi, 2: a
   const int vsel = (m == 0 || m == 3) ? 3 : (m == 1 ? 4 : (m == 5 ? 6 : 5));   // S, Ge, X, S, X, E
   float acc[4][4];
@@ -595,6 +612,28 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
     cp_async_wait<1>();
     __syncthreads();
     const float* base = dsm + (size_t)buf * 7 * GT_F;
+    if (MMA) {
+      const float* gA = base + gsel * GT_F + (half * 16 + fg) * GSP + ft;
+      const float* vB = base + vsel * GT_F + fg * GSP + ft;
+      // acc[nt][0..3]: rows fg / fg+8 of the half, columns 8 nt + 2 ft (+1)
+#pragma unroll 2
+      for (int ks = 0; ks < GPX / 8; ++ks) {
+        uint32_t ah[4], al[4];
+        split_tf32(gA[ks * 8], ah[0], al[0]);
+        split_tf32(gA[8 * GSP + ks * 8], ah[1], al[1]);
+        split_tf32(gA[ks * 8 + 4], ah[2], al[2]);
+        split_tf32(gA[8 * GSP + ks * 8 + 4], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t bh[2], bl[2];
+          split_tf32(vB[nt * 8 * GSP + ks * 8], bh[0], bl[0]);
+          split_tf32(vB[nt * 8 * GSP + ks * 8 + 4], bh[1], bl[1]);
+          mma_tf32(acc[nt], al, bh);
+          mma_tf32(acc[nt], ah, bl);
+          mma_tf32(acc[nt], ah, bh);
+        }
+      }
+    } else {
     const float* gT = base + gsel * GT_F + ocq * GSP;
     const float* vT = base + vsel * GT_F + icq * GSP;
 #pragma unroll 2
@@ -610,6 +649,7 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
         for (int j = 0; j < 4; ++j)
           acc[i][j] = fmaf(g[i].x, v[j].x, fmaf(g[i].y, v[j].y, fmaf(g[i].z, v[j].z, fmaf(g[i].w, v[j].w, acc[i][j]))));
     }
+    }
     if (tid < 3 * C) {   // bias sums: row sums of ge / gi / a
       const float4* row = reinterpret_cast<const float4*>(base + (tid >> 5) * GT_F + (tid & 31) * GSP);
 #pragma unroll 4
@@ -623,10 +663,18 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
   }
   cp_async_wait<0>();
   float* ga = d.gacc + (size_t)blockIdx.x * GACC_N;
+  if (MMA) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc_store(ga + m * 1024 + (ocq + 8 * i) * C + icq + 8 * j, acc[i][j], first);
+      for (int e = 0; e < 4; ++e)
+        acc_store(ga + m * 1024 + (half * 16 + fg + 8 * (e >> 1)) * C + nt * 8 + 2 * ft + (e & 1), acc[nt][e], first);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc_store(ga + m * 1024 + (ocq + 8 * i) * C + icq + 8 * j, acc[i][j], first);
+  }
   if (tid < 3 * C) acc_store(ga + GACC_BE + tid, bsum, first);
 }
 
@@ -823,7 +871,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
-  PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
+  PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
+  PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
   PTK_CUDA_OK(cudaFuncSetAttribute(int_readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
   {
@@ -876,7 +925,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     PTK_LAUNCH_OK("int_bwd_d_kernel");
     {
       ProfileScope ps(PTK_PROF_GATE_WGRAD, st);
-      gate_wgrad_kernel<CELL><<<gate_grid, 384, SM_GATE, st>>>(d, t, first);
+      if (tc) gate_wgrad_kernel<CELL, true><<<gate_grid, 384, SM_GATE, st>>>(d, t, first);
+      else gate_wgrad_kernel<CELL, false><<<gate_grid, 384, SM_GATE, st>>>(d, t, first);
     }
     PTK_LAUNCH_OK("gate_wgrad_kernel");
   }
