@@ -11,11 +11,17 @@
 //     of the 7x7 window is the SAME shared-memory image addressed at a different start pixel
 //     (ky*38 + kx): no im2col copies.
 //   * GEMM shape per MMA: M = 128 consecutive padded pixels (5 M-tiles cover the 16x38 padded tile),
-//     K = 16 input channels, N = 64 = [Wh | Wl] for the Ih operand (one instruction yields both
-//     Ih*Wh and Ih*Wl) and N = 32 (Wh only) for the Il operand.  The two N-halves are summed in the epilogue.
-//   * weights stream per tap (4 KB: hi+lo) through a cp.async.bulk + mbarrier ring; one elected
+//     K = 16 input channels, N = 96 = three horizontally adjacent taps x 32 output channels ("tap
+//     stacking").  The MMA phase is bound by shared-memory operand bandwidth (~128 B/clk/SM: an M=128,
+//     K=16 A tile is 4 KB however few columns it feeds), so one A read must feed as many columns as
+//     TMEM allows: with the A operand at start pixel ky*38 + kx0, column block dl holds
+//     sum In[p + (ky,kx0)] * W[ky, kx0+dl], i.e. the contribution to output pixel p - dl.  The blocks
+//     are realigned in the epilogue (out[m] = D0[m] + D1[m+1] + D2[m+2], a lane shift).  5 tiles x 96
+//     columns = 480 of the 512 TMEM columns.  Taps per kernel row: groups {0,1,2}, {3,4,5}, {6} (N = 32).
+//     Per group three instructions: Ih*Wh, Ih*Wl, Il*Wh, all accumulating into the same columns.
+//   * weights stream per kernel row (28 KB: hi+lo) through a cp.async.bulk + mbarrier ring; one elected
 //     thread issues tcgen05.mma; tcgen05.commit releases ring slots and signals the epilogue.
-//   * epilogue: tcgen05.ld -> registers -> BatchNorm batch statistics partials -> global (NCHW fp32).
+//   * epilogue: tcgen05.ld -> registers -> realign -> BatchNorm batch statistics partials -> global.
 #include <cuda_bf16.h>
 
 #include "ptk_common.cuh"
@@ -32,21 +38,20 @@ constexpr int TC_MT = 5;                               // M-tiles: 5*128 = 640 >
 constexpr int TC_NPIX = 880;                           // >= 640 + 6*38 + 6 = 874 pixels incl. slack
 constexpr int TC_PLANE = TC_NPIX * 16;                 // bytes per channel-chunk plane
 constexpr int TC_A_BYTES = 2 * 4 * TC_PLANE;           // hi + lo, 4 chunks
-constexpr int TC_WTAP = 4 * 64 * 16;                   // bytes of one tap's weights: 4 chunks x 64 rows x 8 bf16
+constexpr int TC_WTAP = 4 * 64 * 16;                   // bytes of one tap's weights: 4 chunks x (32 hi + 32 lo rows) x 8 bf16
 constexpr int TC_STAGE = KS * TC_WTAP;                 // one ring stage = one kernel row (7 taps, 28 KB)
+constexpr int TC_SP = TC_TH * TC_WP + 4;                // row pitch (floats) of the realigned output staging tile
+constexpr int TC_DCOLS = 96;                           // TMEM columns per M-tile: 3 stacked taps x 32 channels
+constexpr int TC_GRP_BYTES = 3 * TC_WTAP;              // a 3-tap group: [Wh: 4 chunks x 96 rows x 16 B][Wl: same]
+// byte offset of weight element (row n, k) of tap (ky, kx) inside the staged image
+__host__ __device__ constexpr size_t tc_woff(int ky, int kx, int n, int k, bool lo) {
+  const int gi = kx / 3, dl = kx - 3 * gi, N = gi < 2 ? 96 : 32;
+  return (size_t)ky * TC_STAGE + (size_t)gi * TC_GRP_BYTES + (lo ? 64 * N : 0) + (size_t)(k >> 3) * (N * 16) +
+         (size_t)(dl * 32 + n) * 16 + (size_t)(k & 7) * 2;
+}
 constexpr int TC_NST = 3;                              // weight ring stages
 constexpr int TC_SMEM = TC_A_BYTES + TC_NST * TC_STAGE + 256;
 
-// accumulator row of one pixel: 32 channels = cols [0,32) + cols [32,64) of M-tile j
-__device__ __forceinline__ void tc_load_pixel(uint32_t tmem_base, int quad, int j, float (&v)[32], bool single) {
-  float lo[32];
-  const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 64);
-  tmem_ld32(ta, v);
-  if (single) return;
-  tmem_ld32(ta + 32, lo);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] += lo[i];
-}
 __device__ long long g_tc_dbg[8];
 __device__ unsigned long long g_tc_times[1024][3];   // per CTA: start, mma-done, end (globaltimer ns)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -62,8 +67,6 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   uint64_t* empty = bars + TC_NST;                          // [TC_NST]
   uint64_t* accum_bar = bars + 2 * TC_NST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_NST + 1);
-  __shared__ float sRed[8][C];
-  __shared__ float sMean[C];
   __shared__ double sFin[8][C][3];
   __shared__ int sIsLast;
 
@@ -163,37 +166,43 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
     // descriptors differ only in the 14-bit start-address field of the low word: precompute the
     // per-(operand, k-step) bases and add the pixel offset per instruction (1 IADD per MMA).
     const uint32_t aHi = smem_u32(sA), aLo = aHi + 4 * TC_PLANE, wBase = smem_u32(sWr);
-    const uint64_t dA0 = umma_desc(0, TC_PLANE, 128), dB0 = umma_desc(0, 1024, 128);
-    const uint32_t aHiW = (uint32_t)(dA0 >> 32), bHiW = (uint32_t)(dB0 >> 32);
-    const uint32_t aLoW = (uint32_t)dA0, bLoW = (uint32_t)dB0;
+    const uint64_t dA0 = umma_desc(0, TC_PLANE, 128);
+    const uint64_t dB96 = umma_desc(0, 96 * 16, 128), dB32 = umma_desc(0, 32 * 16, 128);   // LBO = rows x 16 B between k-chunks
+    const uint32_t aHiW = (uint32_t)(dA0 >> 32), aLoW = (uint32_t)dA0;
     uint32_t aH[2], aL[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       aH[s] = aLoW + ((aHi + (uint32_t)(2 * s) * TC_PLANE) >> 4);
       aL[s] = aLoW + ((aLo + (uint32_t)(2 * s) * TC_PLANE) >> 4);
     }
-    constexpr uint32_t ID64 = umma_idesc(64), ID32 = umma_idesc(32);
+    constexpr uint32_t ID96 = umma_idesc(96), ID32 = umma_idesc(32);
     for (int ky = 0; ky < KS; ++ky) {
       const int st = ky % TC_NST, round = ky / TC_NST;
       mbar_wait(&full[st], (uint32_t)(round & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int kx = 0; kx < KS; ++kx) {
-        const uint32_t poff = (uint32_t)(ky * TC_WP + kx);          // in 16-byte units == pixels
-        const uint32_t bW = bLoW + ((wBase + (uint32_t)st * TC_STAGE + (uint32_t)kx * TC_WTAP) >> 4);
+      const uint32_t stBase = wBase + (uint32_t)st * TC_STAGE;
+#pragma unroll
+      for (int gi = 0; gi < 3; ++gi) {
+        const int N = gi < 2 ? 96 : 32;
+        const uint32_t idesc = gi < 2 ? ID96 : ID32;
+        const uint64_t dB0 = gi < 2 ? dB96 : dB32;
+        const uint32_t bHiW = (uint32_t)(dB0 >> 32);
+        const uint32_t bH = (uint32_t)dB0 + ((stBase + (uint32_t)gi * TC_GRP_BYTES) >> 4);   // Wh block of the group
+        const uint32_t bL = bH + (uint32_t)((64 * N) >> 4);                                  // Wl block
+        const uint32_t poff = (uint32_t)(ky * TC_WP + 3 * gi);                               // in 16-byte units == pixels
 #pragma unroll
         for (int j = 0; j < TC_MT; ++j) {
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             const uint32_t po = poff + (uint32_t)(j * 128);
-            const uint64_t dB = ((uint64_t)bHiW << 32) | (bW + (uint32_t)(2 * s) * (1024 >> 4));
-            const uint32_t dcol = tmem_base + (uint32_t)(j * 64);
+            const uint32_t kadv = (uint32_t)(s * ((2 * N * 16) >> 4));
+            const uint64_t dBh = ((uint64_t)bHiW << 32) | (bH + kadv), dBl = ((uint64_t)bHiW << 32) | (bL + kadv);
+            const uint32_t dcol = tmem_base + (uint32_t)(j * TC_DCOLS);
             if (elect_one()) {
-              if (SINGLE) {   // PTK_CONV_BF16: Ih*Wh only
-                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID32, (ky | kx | s) ? 1u : 0u);
-              } else {
-                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dB, ID64, (ky | kx | s) ? 1u : 0u);
-                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dB, ID32, 1u);
+              umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dBh, idesc, (ky | gi | s) ? 1u : 0u);
+              if (!SINGLE) {   // PTK_CONV_BF16 keeps Ih*Wh only
+                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aH[s] + po), dBl, idesc, 1u);
+                umma_bf16(dcol, ((uint64_t)aHiW << 32) | (aL[s] + po), dBh, idesc, 1u);
               }
             }
           }
@@ -215,66 +224,84 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   const int nCta = gridDim.x * gridDim.y * gridDim.z;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const bool stats = (a.part != nullptr);
-  if (stats) {
-    float s[32];
+  // Realign the stacked-tap column blocks: out[m] = D0[m] + D1[m+1] + D2[m+2] (m = TMEM lane = padded
+  // pixel).  Inside a 32-lane quadrant that is a shuffle; the two rows past a quadrant are handed over
+  // through a small edge buffer.  The realigned tile is staged in shared memory (the operand image is
+  // dead once accum_bar fired) as [channel][padded pixel], from which the output pass reads whole rows:
+  // compact rolled loops (an unrolled register-resident version spent 3x longer fetching instructions).
+  float* sS = reinterpret_cast<float*>(sA);      // [32][TC_SP]
+  float* sEdge = sS + C * TC_SP;                 // [20 quadrants][3][32]: D1 of lane 0, D2 of lane 0, D2 of lane 1
+#pragma unroll 1
+  for (int j = jpar; j < TC_MT; j += 2) {
+    float o[32], v1[32], v2[32];
+    const uint32_t ta = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * TC_DCOLS);
+    tmem_ld32(ta, o);
+    tmem_ld32(ta + 32, v1);
+    tmem_ld32(ta + 64, v2);
+    float* e = sEdge + (size_t)((j * 4 + quad) * 3) * 32;
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s[i] = 0.f;
-    for (int j = jpar; j < TC_MT; j += 2) {
-      const int m = j * 128 + quad * 32 + lane, ro = m / TC_WP, xo = m - ro * TC_WP;
-      float v[32];
-      tc_load_pixel(tmem_base, quad, j, v, SINGLE);
-      if (ro < TC_TH && xo < TC_TW) {
+      for (int i = 0; i < 32; ++i) { e[i] = v1[i]; e[32 + i] = v2[i]; }
+    } else if (lane == 1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[i] += v[i];
-      }
+      for (int i = 0; i < 32; ++i) e[64 + i] = v2[i];
     }
-    const float tot = warp_transpose_sum(s, lane);
-    sRed[warp][lane] = tot;
-    __syncthreads();
-    if (tid < C) {
-      float t = 0.f;
+    const int m = j * 128 + quad * 32 + lane;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += sRed[w][tid];
-      sMean[tid] = t * (1.0f / (TC_TH * TC_TW));
+    for (int i = 0; i < 32; ++i) {
+      const float t1 = __shfl_down_sync(0xffffffffu, v1[i], 1), t2 = __shfl_down_sync(0xffffffffu, v2[i], 2);
+      const float r = o[i] + ((lane < 31 ? t1 : 0.f) + (lane < 30 ? t2 : 0.f));
+      if (m < TC_TH * TC_WP) sS[i * TC_SP + m] = r;
     }
-    __syncthreads();
   }
+  __syncthreads();
+  // rows 30 / 31 of every quadrant take the missing terms from the next quadrant's edge rows
+  for (int e = tid; e < (TC_TH * TC_WP / 32) * 2 * C; e += 256) {
+    const int q = e >> 6, r = (e >> 5) & 1, c = e & 31, m = q * 32 + 30 + r;
+    const float* E = sEdge + (size_t)(q + 1) * 96;
+    if (m < TC_TH * TC_WP) sS[c * TC_SP + m] += r ? (E[c] + E[64 + c]) : E[32 + c];
+  }
+  __syncthreads();
+  // output pass: warp w owns channels 4w..4w+3; lane = (row, half row) -> 16 consecutive pixels
   {
-    float s[32];
+    const int row = lane >> 1, hx = (lane & 1) * 16;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = warp * 4 + cc;
+      const float* src = sS + c * TC_SP + row * TC_WP + hx;
+      float v[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s[i] = 0.f;
-    for (int j = jpar; j < TC_MT; j += 2) {
-      const int m = j * 128 + quad * 32 + lane, ro = m / TC_WP, xo = m - ro * TC_WP;
-      float v[32];
-      tc_load_pixel(tmem_base, quad, j, v, SINGLE);
-      if (ro < TC_TH && xo < TC_TW) {
-        float* dst = a.out + ((size_t)(b * C) * H + y0 + ro) * W + x0 + xo;
+      for (int k = 0; k < 8; ++k) {
+        const float2 t = *reinterpret_cast<const float2*>(src + 2 * k);
+        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+      }
+      if (stats) {   // per-CTA (mean, M2) of this channel over the 16x32 outputs
+        float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (stats) {
-            const float dl = v[i] - sMean[i];
-            s[i] = fmaf(dl, dl, s[i]);
-          }
-          float* p = dst + (size_t)i * H * W;
-          *p = a.accumulate ? (*p + v[i]) : v[i];
+        for (int k = 0; k < 16; ++k) sum += v[k];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float mean = sum * (1.0f / (TC_TH * TC_TW));
+        float m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const float dl = v[k] - mean; m2 = fmaf(dl, dl, m2); }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, off);
+        if (lane == 0) {
+          float* dstp = a.part + ((size_t)cta * C + c) * 2;
+          dstp[0] = mean;
+          dstp[1] = m2;
         }
       }
-    }
-    if (stats) {
-      const float tot = warp_transpose_sum(s, lane);
-      __syncthreads();
-      sRed[warp][lane] = tot;
-      __syncthreads();
-      if (tid < C) {
-        float t = 0.f;
+      float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(b * C + c) * H + y0 + row) * W + x0 + hx);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += sRed[w][tid];
-        float* dstp = a.part + ((size_t)cta * C + tid) * 2;
-        dstp[0] = sMean[tid];
-        dstp[1] = t;
+      for (int k = 0; k < 4; ++k) {
+        float4 t = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        if (a.accumulate) { const float4 p = dst[k]; t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w; }
+        dst[k] = t;
       }
-      conv_stats_fold(a, nCta, TC_TH * TC_TW, sFin, &sIsLast);
     }
+    if (stats) conv_stats_fold(a, nCta, TC_TH * TC_TW, sFin, &sIsLast);
   }
   TC_STAMP(4);
   if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][2] = gtimer();
@@ -283,24 +310,23 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 
-// weights fp32 [oc][ic][49] -> bf16 hi/lo per tap: [tap][chunk = k/8][row n: 0-31 hi, 32-63 lo][k%8]
+// weights fp32 [oc][ic][49] -> bf16 hi/lo in the staged layout (tc_woff): per kernel row, per tap group,
+// [Wh | Wl] blocks of [chunk = k/8][row = (tap in group, n)][k%8].
 //   forward: n = oc, k = ic, tap as is;  dgrad (conv_transpose): n = ic, k = oc, tap -> 48 - tap.
 __global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat16* wf, __nv_bfloat16* wd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * C * TAPS) return;
-  const int oc = i / (C * TAPS), ic = (i / TAPS) % C, tap = i % TAPS;
+  const int oc = i / (C * TAPS), ic = (i / TAPS) % C, tap = i % TAPS, ky = tap / KS, kx = tap - ky * KS;
   const float v = w[i];
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
   if (wf) {
-    const size_t base = (size_t)tap * (TC_WTAP / 2) + (size_t)(ic >> 3) * 512 + (ic & 7);
-    wf[base + (size_t)oc * 8] = h;
-    wf[base + (size_t)(32 + oc) * 8] = l;
+    wf[tc_woff(ky, kx, oc, ic, false) / 2] = h;
+    wf[tc_woff(ky, kx, oc, ic, true) / 2] = l;
   }
   if (wd) {
-    const size_t base = (size_t)(TAPS - 1 - tap) * (TC_WTAP / 2) + (size_t)(oc >> 3) * 512 + (oc & 7);
-    wd[base + (size_t)ic * 8] = h;
-    wd[base + (size_t)(32 + ic) * 8] = l;
+    wd[tc_woff(KS - 1 - ky, KS - 1 - kx, ic, oc, false) / 2] = h;
+    wd[tc_woff(KS - 1 - ky, KS - 1 - kx, ic, oc, true) / 2] = l;
   }
 }
 
