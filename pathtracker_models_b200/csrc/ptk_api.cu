@@ -6,7 +6,13 @@
 #include "ptk_convlstm.h"
 #include "ptk_int.h"
 
+#include <stdlib.h>
 namespace ptk {
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PTK_NO_PDL"); return !(e && e[0] == '1'); }();
+  return on;
+}
+
 
 static thread_local char g_err[512] = "";
 

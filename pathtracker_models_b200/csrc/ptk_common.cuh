@@ -110,6 +110,32 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// The time loop is a chain of ~13 short kernels per step whose CTAs fill a whole SM (shared memory), so
+// launch latency + prologue (barrier init, TMEM allocation, weight staging) of kernel N+1 would sit
+// exposed behind the tail of kernel N.  Loop kernels are launched with the programmatic-stream-
+// serialization attribute and follow one rule:
+//     prologue touching only parameters / shared memory / TMEM  ->  pdl_wait()  ->  pdl_launch_dependents()
+//     ->  everything that reads or writes activations.
+// pdl_wait() returns when the preceding kernel has completed and flushed; triggering only after the
+// wait means kernel N+2 can never start before kernel N has finished, so pre-wait code may read data
+// produced two or more kernels back (prepared weights) but nothing newer.  Without the launch attribute
+// both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // PTK_NO_PDL=1 disables the attribute (A/B measurements)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- frame addressing: x is [B,3,T,H,W] with arbitrary element strides ---------------------
 struct FrameView {
   const float* x;

@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
       bulk_g2s(sWr + ky * TC_STAGE, wsrc + (size_t)ky * TC_STAGE, TC_STAGE, &full[ky]);
     }
   }
+  // everything above touched only shared memory, TMEM and the prepared weights (written >= 2 kernels ago)
+  pdl_wait();
+  pdl_launch_dependents();
 
   // ---- stage the input tile: fp32 NCHW -> bf16 hi/lo, channel-chunk planar -------------------------
   // interior columns: one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels
@@ -334,10 +337,10 @@ int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
   if (a.mode == PTK_CONV_BF16) {
     PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    conv7_tc_kernel<true><<<grid, 256, TC_SMEM, st>>>(a);
+    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc_kernel<true>, grid, dim3(256), TC_SMEM, st, a));
   } else {
     PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    conv7_tc_kernel<false><<<grid, 256, TC_SMEM, st>>>(a);
+    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc_kernel<false>, grid, dim3(256), TC_SMEM, st, a));
   }
   PTK_LAUNCH_OK("conv7_tc_kernel");
   return PTK_OK;

@@ -190,6 +190,8 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
 
 // (b3)/(b9): dAct <- w*rstd*(dAct - mean(dAct) - xhat*mean(dAct*xhat)), xhat from the saved conv output.
 __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __restrict__ Y, int t, int bn) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int P = d.H * d.W;
   const size_t n4 = (size_t)d.B * C * P / 4;
   const float* st = d.stat(t, bn);
@@ -244,12 +246,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   int wt = blockIdx.x * 4 + warp;
   BwdCIn cur;
   float xin[3][4];
-  if (wt < nWT) {     // first tile: operands requested before (and overlapping) the weight fill
-    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
-    warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
-    if (CELL != CELL_NOINH) bwd_c_load<CELL>(d, It, At, Y0, Git, (size_t)b * C * P + pix_base + L.pxo + (size_t)L.oc0 * P, cur);
-    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
-  }
+  // prologue on parameters, forward statistics and the (read-only) clip: overlaps the previous kernel's tail (PDL)
   cta_fill_async(sWiw, d.gate[2], C * C);
   cta_fill_async(sWiu, d.gate[3], C * C);
   cta_fill_async(sWew, d.gate[4], C * C);
@@ -267,6 +264,18 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
     sM0[threadIdx.x] = st[threadIdx.x];
     sR0[threadIdx.x] = st[C + threadIdx.x];
   }
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {     // first tile's operands
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
+    if (CELL != CELL_NOINH) bwd_c_load<CELL>(d, It, At, Y0, Git, (size_t)b * C * P + pix_base + L.pxo + (size_t)L.oc0 * P, cur);
+  }
+  cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
   for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
@@ -418,11 +427,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   int wt = blockIdx.x * 4 + warp;
   BwdDIn cur;
   float xin[3][4];
-  if (wt < nWT) {     // first tile: operands requested before (and overlapping) the weight fill
-    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
-    bwd_d_load<CELL>(d, At, Et, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
-    frame_px(d.fv, b, t, pix, d.W, xin);
-  }
+  // prologue on parameters, forward statistics and the (read-only) clip: overlaps the previous kernel's tail (PDL)
   cta_fill_async(sWaw, d.gate[0], C * C);
   cta_fill_async(sWau, d.gate[1], C * C);
   cta_fill_async(sWp, d.Wp, C * 3);
@@ -430,6 +435,16 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   if (fuse) bwd_a_fill_const(d, t - 1, sKa, sGa, sW1, sB1, sM1, sR1);
   cp_async_commit();
   for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) { sPart[i] = 0.f; sPartA[i] = 0.f; }
+  if (wt < nWT) {
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    frame_px(d.fv, b, t, pix, d.W, xin);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {     // first tile's operands
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    bwd_d_load<CELL>(d, At, Et, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
+  }
   cp_async_wait<0>();
   __syncthreads();
   const BwdAConst ka{sKa, sGa, sW1, sB1, sM1, sR1};
@@ -581,6 +596,8 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 template <int CELL, bool MMA>
 __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
+  pdl_wait();
+  pdl_launch_dependents();
   const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
   const float* src[7] = {d.gebB[t & 1], d.giS, d.aS,
                          (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB[t & 1], d.Xs, d.E_at(t)};
@@ -891,10 +908,10 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     {
       ProfileScope ps(PTK_PROF_BN_APPLY, st);
-      bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y1_at(t), t, 1);
+      PTK_CUDA_OK(launch_pdl(true, bn_apply_kernel, dim3(ew_blocks), dim3(256), 0, st, d, (const float*)d.Y1_at(t), t, 1));
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c1{d.dAct, d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
+    ConvArgs c1{d.dAct, d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first, d.conv_mode};
@@ -902,16 +919,16 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     if (rc) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      int_bwd_c_kernel<CELL, ACT><<<grid_c, 128, SM_BWD_C, st>>>(d, t, first);
+      PTK_CUDA_OK(launch_pdl(true, int_bwd_c_kernel<CELL, ACT>, dim3(grid_c), dim3(128), SM_BWD_C, st, d, t, first));
     }
     PTK_LAUNCH_OK("int_bwd_c_kernel");
     if (CELL != CELL_NOINH) {
       {
         ProfileScope ps(PTK_PROF_BN_APPLY, st);
-        bn_apply_kernel<<<ew_blocks, 256, 0, st>>>(d, d.Y0_at(t), t, 0);
+        PTK_CUDA_OK(launch_pdl(true, bn_apply_kernel, dim3(ew_blocks), dim3(256), 0, st, d, (const float*)d.Y0_at(t), t, 0));
       }
       PTK_LAUNCH_OK("bn_apply_kernel");
-      ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode};
+      ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
       { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
       WgradArgs w0{d.GeB[t & 1], d.dAct, d.wacc_inh, d.B, d.H, d.W, first, d.conv_mode};
@@ -920,13 +937,13 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      int_bwd_d_kernel<CELL, ACT><<<grid, 128, SM_BWD_D, st>>>(d, t, first);
+      PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
     }
     PTK_LAUNCH_OK("int_bwd_d_kernel");
     {
       ProfileScope ps(PTK_PROF_GATE_WGRAD, st);
-      if (tc) gate_wgrad_kernel<CELL, true><<<gate_grid, 384, SM_GATE, st>>>(d, t, first);
-      else gate_wgrad_kernel<CELL, false><<<gate_grid, 384, SM_GATE, st>>>(d, t, first);
+      if (tc) PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, true>, dim3(gate_grid), dim3(384), SM_GATE, st, d, t, first));
+      else PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, false>, dim3(gate_grid), dim3(384), SM_GATE, st, d, t, first));
     }
     PTK_LAUNCH_OK("gate_wgrad_kernel");
   }

@@ -144,13 +144,7 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   const float* Y0 = d.Y0_at(t);
   int wt = blockIdx.x * 4 + warp;
   float xin[3][4];
-  if (wt < nWT) {     // the first tile's operands are requested before (and overlap) the weight fill
-    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
-    if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
-    else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
-    warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
-    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
-  }
+  // prologue on parameters and the (read-only) input clip only: overlaps the previous kernel's tail (PDL)
   cta_fill_async(sWiw, d.gateT[2], C * C);
   cta_fill_async(sWiu, d.gateT[3], C * C);
   cta_fill_async(sWew, d.gateT[4], C * C);
@@ -164,7 +158,23 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
     const int c = threadIdx.x;
     sbi[c] = __ldg(d.gate_b[2] + c) + __ldg(d.gate_b[3] + c);
     sbe[c] = __ldg(d.gate_b[4] + c) + __ldg(d.gate_b[5] + c);
-    const float* st = d.stat(t, 0);   // BN0 of step t: mean, rstd
+  }
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {     // the first tile's operands
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    if (CELL == PTK_CELL_INT) warp_tile_load_async(sS, It, (size_t)C * P, b, pix_base, P);
+    else warp_tile_load_async(sS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
+    warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
+  }
+  cp_async_commit();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const float* st = d.stat(t, 0);   // BN0 of step t: mean, rstd (written by the convolution just before)
     const float sc = __ldg(d.bn_w[0] + c) * st[C + c];
     sScale[c] = sc;                   // U = Y0*scale + shift
     sShift[c] = __ldg(d.bn_b[0] + c) - st[c] * sc;
@@ -269,11 +279,7 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
   int wt = blockIdx.x * 4 + warp;
   PostIn cur;
   float xin[3][4];
-  if (wt < nWT) {    // first tile: operands of channel 0 and the next frame's pixels are in flight during the fill
-    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
-    post_load(Y1, I2, Et, Gx, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
-    if (has_next) frame_px(d.fv, b, t + 1, pix, d.W, xin);
-  }
+  // prologue on parameters and the (read-only) input clip only: overlaps the previous kernel's tail (PDL)
   cta_fill_async(sWaw, d.gateT[0], C * C);
   cta_fill_async(sWau, d.gateT[1], C * C);
   if (NOINH) { cta_fill_async(sWew, d.gateT[4], C * C); cta_fill_async(sWeu, d.gateT[5], C * C); }
@@ -287,7 +293,20 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
     const int c = threadIdx.x;
     sba[c] = __ldg(d.gate_b[0] + c) + __ldg(d.gate_b[1] + c);
     sbe[c] = __ldg(d.gate_b[4] + c) + __ldg(d.gate_b[5] + c);
-    const float* st = d.stat(t, 1);   // BN1 of step t
+  }
+  if (wt < nWT && has_next) {
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    frame_px(d.fv, b, t + 1, pix, d.W, xin);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {    // first tile: operands of channel 0
+    const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
+    post_load(Y1, I2, Et, Gx, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
+  }
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const float* st = d.stat(t, 1);   // BN1 of step t (written by the convolution just before)
     const float sc = __ldg(d.bn_w[1] + c) * st[C + c];
     sScale[c] = sc;
     sShift[c] = __ldg(d.bn_b[1] + c) - st[c] * sc;
@@ -434,22 +453,22 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   for (int t = 0; t < d.T; ++t) {
     int rc;
     if (!NOINH) {
-      ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode};
+      ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode, 1};
       { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
       {
         ProfileScope ps(PTK_PROF_POINT_FWD, st);
-        if (cell == PTK_CELL_INT) int_mid_kernel<PTK_CELL_INT, ACT><<<grid, 128, SM_MID, st>>>(d, t);
-        else int_mid_kernel<PTK_CELL_HGRU, ACT><<<grid, 128, SM_MID, st>>>(d, t);
+        if (cell == PTK_CELL_INT) PTK_CUDA_OK(launch_pdl(true, int_mid_kernel<PTK_CELL_INT, ACT>, dim3(grid), dim3(128), SM_MID, st, d, t));
+        else PTK_CUDA_OK(launch_pdl(true, int_mid_kernel<PTK_CELL_HGRU, ACT>, dim3(grid), dim3(128), SM_MID, st, d, t));
       }
       PTK_LAUNCH_OK("int_mid_kernel");
     }
-    ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1), d.conv_mode};
+    ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1), d.conv_mode, 1};
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_FWD, st);
-      int_post_kernel<ACT, NOINH><<<grid, 128, sm_pre, st>>>(d, t, t + 1 < d.T);
+      PTK_CUDA_OK(launch_pdl(true, int_post_kernel<ACT, NOINH>, dim3(grid), dim3(128), sm_pre, st, d, t, (int)(t + 1 < d.T)));
     }
     PTK_LAUNCH_OK("int_post_kernel");
   }

@@ -15,6 +15,7 @@ struct ConvArgs {
   unsigned* counter;   // arrival counter for the last-CTA fold (self-resetting)
   float* stats_out;    // [2][32] mean, rstd
   int mode;            // PTK_CONV_FP32: wT is fp32 [ic][tap][oc]; PTK_CONV_BF16X3: wT is the bf16 hi/lo tap stream
+  int pdl = 0;         // launched inside the time loop: programmatic dependent launch allowed (ptk_common.cuh)
 };
 
 struct WgradArgs {

@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   }
   for (int i = tid; i < (WT_DY_BYTES + WT_IN_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  pdl_wait();                 // the prologue above touched only shared memory / TMEM (ptk_common.cuh, PDL)
+  pdl_launch_dependents();
   WT_STAMP(1, 0);
   // dY tile: 16 rows, interior columns only (pad columns stay zero => contribute nothing)
   wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, b, y0, WT_TH, x0, H, W, 0, false);
@@ -240,10 +242,10 @@ int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st) {
   dim3 grid(a.W / WT_TW, a.H / WT_TH, a.B);
   if (a.mode == PTK_CONV_BF16) {
     PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
-    wgrad7_tc_kernel<true><<<grid, 256, WT_SMEM, st>>>(a);
+    PTK_CUDA_OK(launch_pdl(true, wgrad7_tc_kernel<true>, grid, dim3(256), WT_SMEM, st, a));
   } else {
     PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
-    wgrad7_tc_kernel<false><<<grid, 256, WT_SMEM, st>>>(a);
+    PTK_CUDA_OK(launch_pdl(true, wgrad7_tc_kernel<false>, grid, dim3(256), WT_SMEM, st, a));
   }
   PTK_LAUNCH_OK("wgrad7_tc_kernel");
   return PTK_OK;
