@@ -205,18 +205,17 @@ def run_b200(args):
     hx = [b[0].permute(0, 2, 3, 4, 1).contiguous().cpu().pin_memory() for b in batches]
     hy = [b[1].cpu().pin_memory() for b in batches]
 
-    def e2e_step(i):
-        x = hx[i % nbuf].to(dev, non_blocking=True).permute(0, 4, 1, 2, 3)
-        y = hy[i % nbuf].to(dev, non_blocking=True)
-        return step(x, y).item()
+    from pathtracker_models_b200.data import DevicePrefetcher
 
-    for i in range(2):
-        e2e_step(i)
+    def e2e_run(n):     # every step's clip goes host -> device inside the loop (one batch in flight on a copy stream)
+        for x, y in DevicePrefetcher(((hx[i % nbuf], hy[i % nbuf]) for i in range(n)), dev):
+            step(x.permute(0, 4, 1, 2, 3), y).item()
+
+    e2e_run(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(steps):
-        e2e_step(i)
+    e2e_run(steps)
     f1.record()
     barrier()
     sampler.stop_flag = True

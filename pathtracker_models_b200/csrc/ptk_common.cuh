@@ -123,6 +123,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// L2 prefetch of a 128-byte line: harmless before pdl_wait() (a hint, no data is consumed), used to pull the
+// forward checkpoints a backward kernel is about to read out of HBM while the previous kernel drains.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 bool pdl_enabled();   // PTK_NO_PDL=1 disables the attribute (A/B measurements)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

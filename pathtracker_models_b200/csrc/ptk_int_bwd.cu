@@ -190,6 +190,12 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
 
 // (b3)/(b9): dAct <- w*rstd*(dAct - mean(dAct) - xhat*mean(dAct*xhat)), xhat from the saved conv output.
 __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __restrict__ Y, int t, int bn) {
+  {   // the saved conv output is a forward checkpoint: pull this thread's lines HBM -> L2 while the previous kernel drains
+    const size_t n4p = (size_t)d.B * C * d.H * d.W / 4;
+    if ((threadIdx.x & 7) == 0)
+      for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4p; i += (size_t)gridDim.x * blockDim.x)
+        prefetch_l2(Y + 4 * i);
+  }
   pdl_wait();
   pdl_launch_dependents();
   const int P = d.H * d.W;
@@ -267,6 +273,11 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   if (wt < nWT) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
     frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+    const size_t tb = (size_t)b * C * P + pix_base;      // forward checkpoints of this tile: HBM -> L2
+    warp_tile_prefetch(It, tb, P);
+    warp_tile_prefetch(Y0, tb, P);
+    warp_tile_prefetch(Git, tb, P);
+    if (CELL != PTK_CELL_INT) warp_tile_prefetch(At, tb, P);
   }
   pdl_wait();
   pdl_launch_dependents();
@@ -438,6 +449,15 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   if (wt < nWT) {
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
     frame_px(d.fv, b, t, pix, d.W, xin);
+    const size_t tb = (size_t)b * C * P + (wt - b * tpi) * WPX;   // forward checkpoints of this tile: HBM -> L2
+    warp_tile_prefetch(At, tb, P);
+    warp_tile_prefetch(Et, tb, P);
+    if (fuse) {
+      warp_tile_prefetch(d.E_at(t - 1), tb, P);
+      warp_tile_prefetch(d.A_at(t - 1), tb, P);
+      warp_tile_prefetch(d.Y1_at(t - 1), tb, P);
+      warp_tile_prefetch(d.Gex_at(t - 1), tb, P);
+    }
   }
   pdl_wait();
   pdl_launch_dependents();

@@ -54,6 +54,11 @@ __device__ __forceinline__ void warp_tile_load_async(float* tile, const float* _
   }
 }
 
+// L2 prefetch of the warp's [32 ch][32 px] tile of a [B,C,P] tensor: lane = channel, one 128-byte line each
+__device__ __forceinline__ void warp_tile_prefetch(const float* __restrict__ src, size_t tile_base, int P) {
+  prefetch_l2(src + tile_base + (size_t)(threadIdx.x & 31) * P);
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -125,6 +125,11 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < (WT_DY_BYTES + WT_IN_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  // the In operand is usually a forward checkpoint (I_{t+1}): pull the tile's lines HBM -> L2 before the wait
+  for (int it = tid; it < C * WT_ROWS; it += 256) {
+    const int ch = it / WT_ROWS, gy = y0 - 3 + (it - ch * WT_ROWS);
+    if (gy >= 0 && gy < H) prefetch_l2(a.in + ((size_t)(b * C + ch) * H + gy) * W + x0);
+  }
   __syncthreads();
   pdl_wait();                 // the prologue above touched only shared memory / TMEM (ptk_common.cuh, PDL)
   pdl_launch_dependents();

@@ -101,3 +101,13 @@ def test_synth_oracle_is_deterministic_and_binary():
     assert np.array_equal(x, x2) and np.array_equal(y, y2) and set(np.unique(x)) <= {0.0, 1.0}
     xs, _ = synth(1234, 1, 2, 8, 32, 32, 14, 1)
     assert np.array_equal(x[1:], xs)
+
+
+def test_device_prefetcher_preserves_order_and_count():
+    from pathtracker_models_b200.data import DevicePrefetcher
+    batches = [(torch.full((2, 3), float(i)), torch.tensor([float(i)])) for i in range(5)]
+    got = list(DevicePrefetcher(iter(batches), "cpu"))
+    assert len(got) == 5
+    for i, (x, y) in enumerate(got):
+        assert float(x[0, 0]) == i and float(y[0]) == i
+    assert list(DevicePrefetcher(iter([]), "cpu")) == []

@@ -227,3 +227,13 @@ def test_conv7_operator_vs_torch(mode, shape):
     assert rel_err(ya, ref + acc.double()) < tol
     y2 = conv7(x.cuda(), w.cuda(), conv_mode=mode)
     assert torch.equal(y, y2)                       # deterministic
+
+
+def test_device_prefetcher_copies_every_batch():
+    from pathtracker_models_b200.data import DevicePrefetcher
+    host = [(torch.randn(4, 8).pin_memory(), torch.randn(4, 1).pin_memory()) for _ in range(4)]
+    n = 0
+    for (hx, hy), (x, y) in zip(host, DevicePrefetcher(iter(host), "cuda")):
+        assert x.is_cuda and torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
+        n += 1
+    assert n == 4
