@@ -22,9 +22,10 @@
 namespace ptk {
 
 constexpr int WT_TH = 16, WT_TW = 32, WT_WP = 38, WT_ROWS = 22;
-constexpr int WT_KPIX = WT_TH * WT_WP;               // 608 pixels = 38 K-steps of 16
-constexpr int WT_KSTEPS = WT_KPIX / 16;
-constexpr int WT_DY_PLANE = WT_KPIX * 16 + 16;       // 9744 B: +16 so the 8 channel-chunk planes of one K row hit 8 different bank groups
+constexpr int WT_KPIX = WT_TH * WT_TW;               // 512 pixels = 32 K-steps of 16: the dY tile is stored compact (row pitch 32)
+constexpr int WT_KSTEPS = WT_KPIX / 16;              // a K-step = 16 consecutive pixels of ONE image row, so the In operand's
+                                                     // matching 16 pixels are contiguous too and the 6 pad columns cost no MMAs
+constexpr int WT_DY_PLANE = WT_KPIX * 16 + 16;       // 8208 B: +16 so the 8 channel-chunk planes of one K row hit 8 different bank groups
 constexpr int WT_IN_NPIX = 880;                      // >= 608 + 6*38 + 6
 constexpr int WT_IN_PLANE = WT_IN_NPIX * 16 + 16;    // 14096 B (same reason)
 constexpr int WT_DY_BYTES = 8 * WT_DY_PLANE;         // hi chunks 0-3, lo chunks 4-7
@@ -45,7 +46,7 @@ __host__ __device__ constexpr uint32_t wt_idesc() {
 // rows [r0, r0+nrows) of the tile map to image rows gy0 + r; columns: 32 interior (+3 halo each side when
 // `halo` and the neighbour exists).  `col0` = padded column of image column x0.
 __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_bytes, const float* __restrict__ src,
-                                         int b, int gy0, int nrows, int x0, int H, int W, int col0, bool halo) {
+                                         int b, int gy0, int nrows, int x0, int H, int W, int col0, bool halo, int pitch) {
   const int tid = threadIdx.x;
   for (int it = tid; it < 4 * nrows * (WT_TW / 4); it += 256) {
     const int q = it / (nrows * (WT_TW / 4)), rem = it - q * (nrows * (WT_TW / 4)), r = rem / (WT_TW / 4), g = rem % (WT_TW / 4);
@@ -55,7 +56,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
     float4 v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(p0 + (size_t)e * H * W);
-    const int p = r * WT_WP + col0 + 4 * g;
+    const int p = r * pitch + col0 + 4 * g;
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       uint32_t hi[4], lo[4];
@@ -87,7 +88,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
         hi[e] = pack_bf16x2(h0, h1);
         lo[e] = pack_bf16x2(l0, l1);
       }
-      const int p = r * WT_WP + c;
+      const int p = r * pitch + c;
       *reinterpret_cast<uint4*>(sHi + q * plane_bytes + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(sLo + q * plane_bytes + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
@@ -135,9 +136,9 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   pdl_launch_dependents();
   WT_STAMP(1, 0);
   // dY tile: 16 rows, interior columns only (pad columns stay zero => contribute nothing)
-  wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, b, y0, WT_TH, x0, H, W, 0, false);
+  wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, b, y0, WT_TH, x0, H, W, 0, false, WT_TW);
   // In tile: 22 rows with the 3-pixel halo, interior at padded column 3
-  wt_stage(sIN, sIN + 4 * WT_IN_PLANE, WT_IN_PLANE, a.in, b, y0 - 3, WT_ROWS, x0, H, W, 3, true);
+  wt_stage(sIN, sIN + 4 * WT_IN_PLANE, WT_IN_PLANE, a.in, b, y0 - 3, WT_ROWS, x0, H, W, 3, true, WT_WP);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -164,8 +165,9 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
         const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + tl * 64);
 #pragma unroll 2
         for (int ks = 0; ks < WT_KSTEPS; ++ks) {
+          // K-step ks = pixels 16h .. 16h+15 of tile row r: dY compact (pitch 32), In padded (pitch 38)
           const uint64_t dA = ((uint64_t)aHiW << 32) | (aLoW + (uint32_t)(ks * 16));
-          const uint64_t dB = ((uint64_t)bHiW << 32) | (bOff + (uint32_t)(ks * 16));
+          const uint64_t dB = ((uint64_t)bHiW << 32) | (bOff + (uint32_t)((ks >> 1) * WT_WP + (ks & 1) * 16));
           if (elect_one()) umma_bf16(dcol, dA, dB, IDESC, ks ? 1u : 0u);
         }
       }
