@@ -104,28 +104,42 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   pdl_launch_dependents();
 
   // ---- stage the input tile: fp32 NCHW -> bf16 hi/lo, channel-chunk planar -------------------------
-  // interior columns: one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels
-  for (int it = tid; it < 4 * TC_ROWS * (TC_TW / 4); it += 256) {
-    const int q = it / (TC_ROWS * (TC_TW / 4)), rem = it - q * (TC_ROWS * (TC_TW / 4)), r = rem / (TC_TW / 4), g = rem % (TC_TW / 4);
-    const int gy = y0 + r - 3;
-    if (gy < 0 || gy >= H) continue;
-    const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
-    float4 v[8];
+  // interior columns: one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels.
+  // All of a thread's items (<= 3) are requested before the first conversion: the tile is L2-latency bound.
+  {
+    constexpr int NIT = 4 * TC_ROWS * (TC_TW / 4), NR = (NIT + 255) / 256;
+    float4 v[NR][8];
+    int pp[NR], qq[NR];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
-    const int p = r * TC_WP + 3 + 4 * g;
+    for (int r = 0; r < NR; ++r) {
+      const int it = tid + 256 * r;
+      const int q = it / (TC_ROWS * (TC_TW / 4)), rem = it - q * (TC_ROWS * (TC_TW / 4)), row = rem / (TC_TW / 4), g = rem % (TC_TW / 4);
+      const int gy = y0 + row - 3;
+      pp[r] = -1; qq[r] = q;
+      if (it < NIT && gy >= 0 && gy < H) {
+        pp[r] = row * TC_WP + 3 + 4 * g;
+        const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float v0 = reinterpret_cast<const float*>(&v[2 * e])[px], v1 = reinterpret_cast<const float*>(&v[2 * e + 1])[px];
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
       }
-      *reinterpret_cast<uint4*>(sA + q * TC_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      if (pp[r] < 0) continue;
+      const int p = pp[r], q = qq[r];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = reinterpret_cast<const float*>(&v[r][2 * e])[px], v1 = reinterpret_cast<const float*>(&v[r][2 * e + 1])[px];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          hi[e] = pack_bf16x2(h0, h1);
+          lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        }
+        *reinterpret_cast<uint4*>(sA + q * TC_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
   }
   // halo columns (only inside the image when W > 32)

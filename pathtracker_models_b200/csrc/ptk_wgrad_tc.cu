@@ -48,28 +48,42 @@ __host__ __device__ constexpr uint32_t wt_idesc() {
 __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_bytes, const float* __restrict__ src,
                                          int b, int gy0, int nrows, int x0, int H, int W, int col0, bool halo, int pitch) {
   const int tid = threadIdx.x;
-  for (int it = tid; it < 4 * nrows * (WT_TW / 4); it += 256) {
-    const int q = it / (nrows * (WT_TW / 4)), rem = it - q * (nrows * (WT_TW / 4)), r = rem / (WT_TW / 4), g = rem % (WT_TW / 4);
-    const int gy = gy0 + r;
-    if (gy < 0 || gy >= H) continue;
-    const float* p0 = src + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
-    float4 v[8];
+  // two items per round: 16 LDG.128 in flight per thread before the first conversion (L2-latency bound)
+  const int nit = 4 * nrows * (WT_TW / 4);
+  for (int it0 = tid; it0 < nit; it0 += 512) {
+    float4 v[2][8];
+    int pp[2], qq[2];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(p0 + (size_t)e * H * W);
-    const int p = r * pitch + col0 + 4 * g;
+    for (int r = 0; r < 2; ++r) {
+      const int it = it0 + 256 * r;
+      const int q = it / (nrows * (WT_TW / 4)), rem = it - q * (nrows * (WT_TW / 4)), row = rem / (WT_TW / 4), g = rem % (WT_TW / 4);
+      const int gy = gy0 + row;
+      pp[r] = -1; qq[r] = q;
+      if (it < nit && gy >= 0 && gy < H) {
+        pp[r] = row * pitch + col0 + 4 * g;
+        const float* p0 = src + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
 #pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(reinterpret_cast<const float*>(&v[2 * e])[px], h0, l0);
-        split_bf16(reinterpret_cast<const float*>(&v[2 * e + 1])[px], h1, l1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(l0, l1);
+        for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(p0 + (size_t)e * H * W);
       }
-      *reinterpret_cast<uint4*>(sHi + q * plane_bytes + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(sLo + q * plane_bytes + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (pp[r] < 0) continue;
+      const int p = pp[r], q = qq[r];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(reinterpret_cast<const float*>(&v[r][2 * e])[px], h0, l0);
+          split_bf16(reinterpret_cast<const float*>(&v[r][2 * e + 1])[px], h1, l1);
+          hi[e] = pack_bf16x2(h0, h1);
+          lo[e] = pack_bf16x2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(sHi + q * plane_bytes + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sLo + q * plane_bytes + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
   }
   if (halo && W > WT_TW) {
