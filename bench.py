@@ -225,6 +225,45 @@ def run_b200(args):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * steps / (ms2.item() / 1e3)
 
+    # ---- the step either side of the path, reported separately ("optimizer step excluded and reported
+    # separately"): loss + metrics kernel and fused Adam + zero_grad vs torch.optim.Adam on the same gradients
+    from pathtracker_models_b200.optim import FusedAdam, bce_with_logits_and_scores
+
+    def time_ms(fn, n=10):
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / n
+
+    step(*batches[0])
+    saved_grads = [None if p.grad is None else p.grad.clone() for p in model.parameters()]
+
+    def restore():
+        for p, g in zip(model.parameters(), saved_grads):
+            p.grad = None if g is None else g.clone()
+
+    def opt_time(opt, fused):
+        def one():
+            restore()
+            if fused:
+                opt.step(zero_grad=True)
+            else:
+                opt.step()
+                opt.zero_grad()
+        one()
+        return time_ms(one) - time_ms(restore)
+
+    torch_adam_ms = opt_time(torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-6), False)
+    fused_adam_ms = opt_time(FusedAdam(model.parameters(), lr=1e-6), True)
+    zl, yl = torch.randn(B, 1, device=dev), batches[0][1]
+    loss_ms = time_ms(lambda: bce_with_logits_and_scores(zl, yl))
+    optimizer_block = {"fused_adam_zero_grad_ms": round(fused_adam_ms, 4), "torch_adam_zero_grad_ms": round(torch_adam_ms, 4),
+                       "bce_scores_ms": round(loss_ms, 4), "note": "outside the timed region; lr 1e-6 so the benchmark weights barely move"}
+
     if rank == 0:
         tensor_peak, hbm_peak, src = load_peaks()
         conv_ms, conv_n = prof["conv_fwd"][0] + prof["conv_dgrad"][0], prof["conv_fwd"][1] + prof["conv_dgrad"][1]
@@ -245,6 +284,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 4),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
+            "optimizer": optimizer_block,
             "clocks": sampler.result(),
             "roofline": {"bound": "tensor", "kernel": ("conv7_ffma_kernel" if args.conv_mode == "fp32" else "conv7_tc_kernel") + " (fwd + dgrad launches)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",

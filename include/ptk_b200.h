@@ -118,6 +118,18 @@ PTK_API int ptk_synth_pathtracker(uint64_t seed, uint64_t first_index, int32_t B
                           int32_t W, int32_t n_distractors, int32_t speed, float* x, float* y,
                           void* stream);
 
+/* ---- The step either side of the path -------------------------------------------------
+ * Loss + metrics in one launch: criterion = BCEWithLogitsLoss (mainclean.py:156,189) and acc_scores /
+ * metric_scores (utils/misc_functions.py:12-45; note the LOGIT is compared with 0.5 and recall divides by the
+ * batch size, exactly as written there).  logits, target: [B] fp32 device.  dlogits (optional, [B]) receives
+ * d(mean loss)/d(logit).  out5 (device) = {loss, bal_acc*100, precision, recall, f1}.  No host synchronisation. */
+PTK_API int ptk_bce_scores(int32_t B, const float* logits, const float* target, float* dlogits, float* out5,
+                   void* stream);
+/* torch.optim.Adam(lr) with PyTorch defaults (mainclean.py:157) over ONE flat fp32 vector, in place, plus
+ * optimizer.zero_grad() (mainclean.py:205-206) when zero_grad != 0.  step = 1 for the first update. */
+PTK_API int ptk_adam_step(int64_t n, float* params, float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                  float beta1, float beta2, float eps, int64_t step, int32_t zero_grad, void* stream);
+
 /* ---- ConvLSTM baseline (models/convlstm.py) --------------------------------------------------------------
  * Flat parameter vector in the reference's state_dict order: conv0.{weight[25,1,7,7],bias}, then for each gate
  * k in (i,f,c,o): unit1.Wx<k>.{weight[25,25,K,K],bias[25]}, unit1.Wh<k>.weight[25,25,K,K]; bn.{weight,bias}[25];
