@@ -420,7 +420,7 @@ __device__ __forceinline__ void bwd_d_load(const IntDev& d, const float* At, con
 // (b10)-(b12): complete dGe, dE partial (gE), A_t, E_t, dX, [dS], x_t.
 // writes gE <- dE (for step t-1), a (scratch for gate_wgrad), stem parameter sums, optional dx.
 // When t > 0 the kernel continues with (b1)-(b2) of step t-1 on the same patch (dE stays on chip).
-template <int CELL, int ACT>
+template <int CELL, int ACT, bool DX>   // DX: also form d(loss)/d(clip) (viz_model_att.py:189-196); training does not need it
 __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;              // [out][in]
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           part[1 + i] = fmaf(dp, xin[i][p], part[1 + i]);
-          dxs[i][p] = fmaf(sWp[c * 3 + i], dp, dxs[i][p]);
+          if (DX) dxs[i][p] = fmaf(sWp[c * 3 + i], dp, dxs[i][p]);
         }
       }
       part_add<4>(sPw, c, L, part);
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
         acur = anxt;
       }
     }
-    if (d.dx != nullptr) {   // contiguous [B,3,T,H,W]
+    if (DX) {   // contiguous [B,3,T,H,W]
 #pragma unroll
       for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -907,7 +907,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   }
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
+  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
   PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
   PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
@@ -957,7 +958,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
+      if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
+      else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
     }
     PTK_LAUNCH_OK("int_bwd_d_kernel");
     {
