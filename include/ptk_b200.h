@@ -151,6 +151,15 @@ PTK_API int ptk_convlstm_backward(const PtkLstmDims* d, const float* x, const fl
                                   const float* doutput, float* dparams, void* workspace, size_t workspace_bytes,
                                   void* stream);
 
+/* Recurrent back-propagation (`grad_method='rbp'`: dummyhgru.backward models/convlstm.py:9-54, forward branch
+ * :124-135): Neumann series g = sum_k (J^T)^k dL/dh_T on the last step's Jacobian, truncated after num_iter
+ * terms or by the reference's norm tests (|g| > 1, |v_k| > |v_{k-1}|, |v_k| < 1e-9); parameter gradients = one
+ * cell-step backward with dh_T := g.  The stop test runs on the device (no synchronisation); terms_out
+ * (optional, device, 1 float) receives the number of accepted terms.  Same forward / saved buffer as BPTT. */
+PTK_API int ptk_convlstm_backward_rbp(const PtkLstmDims* d, const float* x, const float* params, const void* saved,
+                                      const float* doutput, int32_t num_iter, float* dparams, float* terms_out,
+                                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* One horizontal-connection convolution on its own (test / measurement entry; the time loop calls the
  * same kernels internally): out (+)= conv2d(in, weight, padding=3) (transpose=0, models/InT.py:161,172)
  * or conv_transpose2d(in, weight, padding=3) (transpose=1, its data gradient).  in/out [B,32,H,W],

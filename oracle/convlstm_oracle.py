@@ -5,6 +5,8 @@ Gabor stem conv0 -> square, T cell steps on the time-invariant input, batch-stat
 and the two vector-Jacobian products of the Jacobian penalty (:152-163).  The input-path convolutions
 Wx*(x) + b are hoisted out of the time loop (the reference recomputes them every step; identical values).
 
+`rbp_grads` restates grad_method='rbp' (:124-135) with the Neumann series of `dummyhgru.backward` (:9-54).
+
 Pinned against outputs of the reference itself: oracle/gen_golden.py -> tests/golden/convlstm_*.npz.
 """
 import torch
@@ -82,3 +84,60 @@ for _k in GATES:
     STATE_KEYS["wx" + _k] = f"unit1.Wx{_k}.weight"
     STATE_KEYS["bx" + _k] = f"unit1.Wx{_k}.bias"
     STATE_KEYS["wh" + _k] = f"unit1.Wh{_k}.weight"
+
+
+def rbp_grads(x, p, timesteps, target, num_iter, criterion=None):
+    """grad_method='rbp' (models/convlstm.py:124-135 + dummyhgru :9-54): returns (output, loss, grads by parameter
+    key of `p`, accepted Neumann terms).  `p` values must be leaf tensors with requires_grad=True."""
+    crit = criterion or F.cross_entropy
+    u = F.conv2d(x, p["conv0.weight"], p["conv0.bias"], padding=3)
+    xt = u * u
+    pad = (p["unit1.Whi.weight"].shape[-1] - 1) // 2
+    h = torch.zeros_like(xt)
+    c = torch.zeros_like(xt)
+    with torch.no_grad():                                   # :125-128
+        for _ in range(timesteps - 1):
+            h, c = _cell_sd(xt, h, c, p, pad)
+    h2 = h.detach().requires_grad_()                        # state_2nd_last (:130-131)
+    c2 = c.detach().requires_grad_()
+    hT, _cT = _cell_sd(xt, h2, c2, p, pad)                  # :133, with graph to the parameters and conv0
+    # head: bn (batch statistics, eps 1e-3) + conv6 on a stand-in leaf, to obtain dL/dh_T
+    hT_leaf = hT.detach().requires_grad_()
+    out = F.conv2d(F.batch_norm(hT_leaf, None, None, p["bn.weight"], p["bn.bias"], True, 0.0, 1e-3), p["conv6.weight"], p["conv6.bias"])
+    loss = crit(out, target)
+    head_params = [p[k] for k in ("bn.weight", "bn.bias", "conv6.weight", "conv6.bias")]
+    gr = torch.autograd.grad(loss, [hT_leaf] + head_params)
+    grad = gr[0]
+    # dummyhgru.backward (:17-54)
+    g_prev, v_prev = grad.clone(), grad.clone()
+    normsv = [torch.norm(g_prev).item()]
+    terms = 0
+    for _ in range(num_iter):
+        v = torch.autograd.grad(hT, h2, grad_outputs=v_prev, retain_graph=True)[0]
+        normv = torch.norm(v)
+        g = g_prev + v
+        normg = torch.norm(g)
+        if normg > 1 or normv > normsv[-1] or normv < 1e-9:
+            break
+        v_prev, g_prev = v, g
+        normsv.append(normv.item())
+        terms += 1
+    cell_keys = [k for k in p if k not in ("bn.weight", "bn.bias", "conv6.weight", "conv6.bias")]
+    cg = torch.autograd.grad(hT, [p[k] for k in cell_keys], grad_outputs=g_prev, allow_unused=True)
+    grads = {k: v for k, v in zip(cell_keys, cg)}
+    grads.update({k: v for k, v in zip(("bn.weight", "bn.bias", "conv6.weight", "conv6.bias"), gr[1:])})
+    return out.detach(), loss.item(), grads, terms
+
+
+def _cell_sd(xt, h, c, p, pad):
+    """ConvLSTMCell.forward (models/convlstm.py:84-90) on state_dict-keyed parameters."""
+    def cx(k):
+        return F.conv2d(xt, p[f"unit1.Wx{k}.weight"], p[f"unit1.Wx{k}.bias"], padding=pad)
+
+    def ch(k):
+        return F.conv2d(h, p[f"unit1.Wh{k}.weight"], None, padding=pad)
+    i = torch.sigmoid(cx("i") + ch("i"))
+    f = torch.sigmoid(cx("f") + ch("f"))
+    cc = f * c + i * torch.tanh(cx("c") + ch("c"))
+    o = torch.sigmoid(cx("o") + ch("o"))
+    return o * torch.tanh(cc), cc

@@ -157,7 +157,7 @@ def convlstm_weights(sd_like, seed):
     return out
 
 
-def run_convlstm_case(name, filt, B, T, H, W, seed, store_full):
+def run_convlstm_case(name, filt, B, T, H, W, seed, store_full, grad_method='bptt', num_iter=50, wh_scale=1.0):
     cwd = os.getcwd()
     os.chdir(REF)                                   # ConvLSTM.__init__ loads 'utils/gabor_serre.npy' (convlstm.py:105)
     from models import convlstm as RC
@@ -168,16 +168,33 @@ def run_convlstm_case(name, filt, B, T, H, W, seed, store_full):
     torch.set_default_dtype(torch.float32)
     m0 = RC.ConvLSTM(timesteps=T, filt_size=filt)
     sd32 = convlstm_weights(m0.state_dict(), seed + 1)
+    if wh_scale != 1.0:     # rbp fixtures: scale the recurrent weights so that the Neumann series runs several terms
+        for k in sd32:
+            if ".Wh" in k:
+                sd32[k] = sd32[k] * wh_scale
+        res["wh_scale"] = np.array(wh_scale)
+    res["num_iter"] = np.array(num_iter)
     grads = {}
     for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
         torch.set_default_dtype(dt)
-        m = RC.ConvLSTM(timesteps=T, filt_size=filt).to(dt)
+        m = RC.ConvLSTM(timesteps=T, filt_size=filt, grad_method=grad_method, num_iter=num_iter).to(dt)
         m.load_state_dict({k: v.to(dt) for k, v in sd32.items()})
         m.train()
         x = torch.from_numpy(x_np).to(dt)
         tgt = torch.from_numpy(tgt_np)
         out, pen, loss = m(x, 0, 0, tgt, torch.nn.CrossEntropyLoss())
-        loss.backward()
+        calls = [0]
+        real_grad = torch.autograd.grad
+        def counting_grad(*a, **k):
+            calls[0] += 1
+            return real_grad(*a, **k)
+        torch.autograd.grad = counting_grad      # dummyhgru.backward calls it once per Neumann term it tries
+        try:
+            loss.backward()
+        finally:
+            torch.autograd.grad = real_grad
+        if tag == "f64":
+            res["rbp_grad_calls"] = np.array(calls[0])
         grads[tag] = {n: prm.grad.detach().double() for n, prm in m.named_parameters()}
         grads[tag]["__output__"] = out.detach().double()
         grads[tag]["__penalty__"] = pen.detach().double()
@@ -216,5 +233,9 @@ if __name__ == "__main__":
         run_convlstm_case("convlstm_k7_small", 7, 2, 3, 32, 32, seed=31, store_full=True)
         run_convlstm_case("convlstm_k15_small", 15, 2, 3, 32, 32, seed=32, store_full=False)
         run_convlstm_case("convlstm_k15_b3", 15, 3, 4, 32, 32, seed=33, store_full=False)
+    elif len(sys.argv) > 1 and sys.argv[1] == "convlstm_rbp":
+        load_reference()
+        run_convlstm_case("convlstm_k7_rbp", 7, 2, 4, 32, 32, seed=41, store_full=True, grad_method='rbp', num_iter=50)
+        run_convlstm_case("convlstm_k7_rbp_trunc", 7, 2, 3, 32, 32, seed=42, store_full=True, grad_method='rbp', num_iter=2)
     else:
         main()

@@ -19,7 +19,7 @@ EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_sa
            "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes",
            "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
            "ptk_convlstm_forward", "ptk_convlstm_backward", "ptk_debug_tc_stamps", "ptk_debug_wt_stamps",
-           "ptk_bce_scores", "ptk_adam_step")
+           "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp")
 
 
 class PtkDims(ctypes.Structure):
@@ -87,6 +87,8 @@ def lib():
     L.ptk_adam_step.restype = ctypes.c_int
     L.ptk_adam_step.argtypes = [ctypes.c_int64, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                 ctypes.c_float, ctypes.c_int64, i32, vp]
+    L.ptk_convlstm_backward_rbp.restype = ctypes.c_int
+    L.ptk_convlstm_backward_rbp.argtypes = [ldp, vp, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.ptk_profile_start.restype = None
     L.ptk_profile_start.argtypes = []
     L.ptk_profile_stop.restype = ctypes.c_int

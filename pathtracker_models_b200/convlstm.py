@@ -45,7 +45,7 @@ def _find_gabor(gabor, gabor_path):
 
 class _ConvLSTMFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, flat, dims, want_penalty):
+    def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False):
         L = _lib.lib()
         B, _, H, W = x.shape
         flat = flat.contiguous()
@@ -63,16 +63,21 @@ class _ConvLSTMFunction(torch.autograd.Function):
             rc = L.ptk_convlstm_forward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(out), _ptr(pen), _ptr(saved),
                                         _ptr(ws), ws_bytes, stream)
             _lib.check(rc, "ptk_convlstm_forward")
-        ctx.dims, ctx.saved_buf = dims, saved
+        ctx.dims, ctx.saved_buf, ctx.rbp_iters = dims, saved, rbp_iters
+        if want_states:      # testmode of the rbp branch: h_0 .. h_T (models/convlstm.py:127-135); hs is the first saved block
+            n = B * 25 * H * W
+            states = saved[: (dims.T + 1) * n * 4].view(torch.float32).view(dims.T + 1, B, 25, H, W).clone()
+        else:
+            states = torch.empty(0, device=x.device)
         ctx.save_for_backward(x, flat)
         if pen is None:
             pen = torch.ones(1, dtype=torch.float32, device=x.device)    # convlstm.py:151 placeholder
-        ctx.mark_non_differentiable(pen)
-        return out, pen
+        ctx.mark_non_differentiable(pen, states)
+        return out, pen, states
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dout, _dpen):
+    def backward(ctx, dout, _dpen, _dstates):
         x, flat = ctx.saved_tensors
         L = _lib.lib()
         dims = ctx.dims
@@ -82,23 +87,31 @@ class _ConvLSTMFunction(torch.autograd.Function):
             dflat = torch.empty_like(flat)
             dout = dout.contiguous().float()
             stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-            rc = L.ptk_convlstm_backward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
-                                         _ptr(dflat), _ptr(ws), ws_bytes, stream)
-            _lib.check(rc, "ptk_convlstm_backward")
+            if ctx.rbp_iters is None:
+                rc = L.ptk_convlstm_backward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
+                                             _ptr(dflat), _ptr(ws), ws_bytes, stream)
+                _lib.check(rc, "ptk_convlstm_backward")
+            else:
+                terms = torch.zeros(1, dtype=torch.float32, device=x.device)
+                rc = L.ptk_convlstm_backward_rbp(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
+                                                 int(ctx.rbp_iters), _ptr(dflat), _ptr(terms), _ptr(ws), ws_bytes, stream)
+                _lib.check(rc, "ptk_convlstm_backward_rbp")
+                _ConvLSTMFunction.last_rbp_terms = terms      # device tensor; read it only when you want the sync
         ctx.saved_buf = None
-        return None, dflat, None, None
+        return None, dflat, None, None, None, None
 
 
 class ConvLSTM(nn.Module):
-    """models/convlstm.py:93-173 (bptt branch)."""
+    """models/convlstm.py:93-173: grad_method 'bptt' (full back-propagation through time) or 'rbp' (recurrent
+    back-propagation: Neumann series on the last step, `dummyhgru` :9-54, truncated at `num_iter` terms)."""
 
     def __init__(self, timesteps=8, filt_size=15, num_iter=50, exp_name='exp1', jacobian_penalty=False,
                  grad_method='bptt', gabor=None, gabor_path=None):
         super().__init__()
         self.timesteps, self.num_iter, self.exp_name = timesteps, num_iter, exp_name
         self.jacobian_penalty, self.grad_method = jacobian_penalty, grad_method
-        if grad_method != 'bptt':
-            raise NotImplementedError("grad_method='rbp' (models/convlstm.py:124-135) is not built yet")
+        if grad_method not in ('bptt', 'rbp'):
+            raise ValueError(f"grad_method must be 'bptt' or 'rbp', got {grad_method!r}")   # the reference silently skips the loop
         if jacobian_penalty:
             raise NotImplementedError("jacobian_penalty=True needs a second-order graph; only the value is computed")
         self.conv0 = nn.Conv2d(1, 25, kernel_size=7, padding=3)
@@ -119,8 +132,10 @@ class ConvLSTM(nn.Module):
         if ch != 1:
             raise ValueError(f"expected x of shape [B,1,H,W], got {tuple(x.shape)}")
         dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size)
-        output, pen = _ConvLSTMFunction.apply(x.float(), self.flat_parameters(), dims, bool(self.training))
+        rbp = self.grad_method == 'rbp'
+        output, pen, states = _ConvLSTMFunction.apply(x.float(), self.flat_parameters(), dims, bool(self.training),
+                                                      int(self.num_iter) if rbp else None, bool(rbp and testmode))
         loss = criterion(output, target)                                # convlstm.py:148
-        if testmode:
-            return output, [], loss                                      # bptt branch never fills `states`
+        if testmode:                                                     # the bptt branch never fills `states`
+            return output, (list(states.unbind(0)) if rbp else []), loss
         return output, pen, loss

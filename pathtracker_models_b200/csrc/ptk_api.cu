@@ -333,7 +333,11 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   float* bxg = cv.take<float>(128);
   float* b0g = cv.take<float>(32);
   float* hg = cv.take<float>(128);
+  float* rbp_g = cv.take<float>(S);
+  float* rbp_state = cv.take<float>(64);
+  double* rbp_part = cv.take<double>(2 * 148 * 2);
   if (d) {
+    d->rbp_g = rbp_g; d->rbp_state = rbp_state; d->rbp_part = rbp_part;
     d->groups = groups;
     d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;
     d->w0T = w0T; d->wxT = wxT; d->whT = whT; d->whD = whD; d->wxD = wxD; d->bx = bx; d->Xg = Xg; d->G = G;
@@ -400,6 +404,23 @@ int ptk_convlstm_backward(const PtkLstmDims* dm, const float* x, const float* pa
   if ((rc = lstm_bind(&d, dm, x, params, const_cast<void*>(saved), workspace, st))) return rc;
   d.dout = doutput; d.dparams = dparams;
   return run_convlstm_backward(d, st);
+}
+
+int ptk_convlstm_backward_rbp(const PtkLstmDims* dm, const float* x, const float* params, const void* saved,
+                              const float* doutput, int32_t num_iter, float* dparams, float* terms_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  int rc = lstm_check(dm, "ptk_convlstm_backward_rbp");
+  if (rc) return rc;
+  if (!x || !params || !saved || !doutput || !dparams || !workspace) { set_error("ptk_convlstm_backward_rbp: NULL argument"); return PTK_EINVAL; }
+  if (num_iter < 0) { set_error("ptk_convlstm_backward_rbp: num_iter %d < 0", num_iter); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_convlstm_workspace_bytes(dm)) { set_error("ptk_convlstm_backward_rbp: workspace too small"); return PTK_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmDev d;
+  if ((rc = lstm_bind(&d, dm, x, params, const_cast<void*>(saved), workspace, st))) return rc;
+  d.dout = doutput; d.dparams = dparams;
+  if ((rc = run_convlstm_backward_rbp(d, num_iter, st))) return rc;
+  if (terms_out) PTK_CUDA_OK(cudaMemcpyAsync(terms_out, d.rbp_state + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PTK_OK;
 }
 
 }  // extern "C"

@@ -44,11 +44,13 @@ struct ConvGArgs {
   const float* addend;  // [B, Cout, H, W] or null
   float* out;           // [B, Cout, H, W]
   int B, H, W, Cin, Cout, accumulate;
+  const float* skip = nullptr;   // RBP: device state, skip[1] != 0 => the Neumann series has terminated, do nothing
 };
 
 template <int KS>
 __global__ void __launch_bounds__(256, 1) convg_kernel(ConvGArgs a) {
   using G = ConvG<KS>;
+  if (a.skip != nullptr && a.skip[1] != 0.f) return;
   extern __shared__ __align__(16) float smem[];
   float* sIn = smem;                                   // [ICC][ROWS][PITCH]
   float* sW = smem + G::ICC * G::ROWS * G::PITCH;      // [ICC][KS*KS][32]
@@ -243,7 +245,8 @@ __global__ void lstm_fwd_kernel(const float* __restrict__ G, const float* __rest
 __global__ void lstm_bwd_kernel(const float* __restrict__ dh, float dh_const, const float* __restrict__ dc, float dc_const,
                                 const float* __restrict__ gates, const float* __restrict__ c_prev,
                                 const float* __restrict__ c_cur, float* delta, float* dc_prev, float* delta_sum,
-                                int first, int B, int P) {
+                                int first, int B, int P, const float* skip = nullptr) {
+  if (skip != nullptr && skip[1] != 0.f) return;
   const size_t n = (size_t)B * LC * P;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const int pix = (int)(e % P), c = (int)((e / P) % LC), b = (int)(e / ((size_t)P * LC));
@@ -472,6 +475,9 @@ static int convlstm_penalty_t(const LstmDev& d, cudaStream_t st) {
 }
 
 template <int KS>
+static int convlstm_grad_tail(const LstmDev& d, cudaStream_t st);
+
+template <int KS>
 static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
   const int P = d.H * d.W, taps = KS * KS;
   const size_t S = (size_t)d.B * LC * P;
@@ -498,6 +504,59 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
     }
   }
   // input path, once: dWx = xt (star) sum delta; db = sum; d xt = sum delta *^T Wx; conv0
+  return convlstm_grad_tail<KS>(d, st);
+}
+
+// ---- recurrent back-propagation (models/convlstm.py:9-54 `dummyhgru`, :124-135) ----------------------------
+// Neumann series on the LAST step's Jacobian J = d h_T / d h_{T-1} (c_{T-1} held fixed):
+//   g_0 = v_0 = dL/dh_T;  v_k = J^T v_{k-1};  g_k = g_{k-1} + v_k;   stop (keeping g_{k-1}) when |g_k| > 1,
+//   |v_k| > |v_{k-1}| or |v_k| < 1e-9, or after num_iter terms.  Parameter gradients = one cell-step backward
+//   with dh_T := g.  The stop test is data dependent; instead of a host round trip per term the state lives on
+//   the device (state[0] = |v_{k-1}|, state[1] = terminated, state[2] = accepted terms) and every kernel of a
+//   term returns immediately once state[1] is set, so the call never synchronises.
+constexpr int RBP_CTAS = 148 * 2;
+__global__ void __launch_bounds__(256) rbp_sumsq_kernel(const float* __restrict__ v, const float* __restrict__ g, size_t n,
+                                                        double* part, const float* state) {
+  if (state != nullptr && state[1] != 0.f) return;
+  double sv = 0, sg = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = v[i], b = g ? g[i] + a : a;
+    sv += (double)a * a;
+    sg += (double)b * b;
+  }
+  __shared__ double s0[256], s1[256];
+  s0[threadIdx.x] = sv; s1[threadIdx.x] = sg;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { s0[threadIdx.x] += s0[threadIdx.x + s]; s1[threadIdx.x] += s1[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = s0[0]; part[2 * blockIdx.x + 1] = s1[0]; }
+}
+__global__ void rbp_decide_kernel(const double* __restrict__ part, int nPart, float* state, int init) {
+  if (threadIdx.x != 0 || (!init && state[1] != 0.f)) return;
+  double sv = 0, sg = 0;
+  for (int i = 0; i < nPart; ++i) { sv += part[2 * i]; sg += part[2 * i + 1]; }
+  const float normv = (float)sqrt(sv), normg = (float)sqrt(sg);
+  if (init) { state[0] = normv; state[1] = 0.f; state[2] = 0.f; return; }     // normsv[0] = |grad| (:31-34)
+  if (normg > 1.0f || normv > state[0] || normv < 1e-9f) state[1] = 1.f;      // :42-46 (g stays g_prev)
+  else { state[0] = normv; state[2] += 1.f; }
+}
+__global__ void rbp_commit_kernel(float* g, float* v_prev, const float* __restrict__ v_new, size_t n, const float* state) {
+  if (state[1] != 0.f) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = v_new[i];
+    g[i] += v;
+    v_prev[i] = v;
+  }
+}
+
+// input path (time-invariant terms), conv0 and the fold into the flat gradient vector: shared by BPTT and RBP
+template <int KS>
+static int convlstm_grad_tail(const LstmDev& d, cudaStream_t st) {
+  const int P = d.H * d.W, taps = KS * KS;
+  const size_t S = (size_t)d.B * LC * P;
+  int rc;
   WgradGArgs wx{d.xt, d.delta_sum, d.slots_x, d.B, d.H, d.W, LC, LG, d.groups, 0};
   if ((rc = launch_wgradg<KS>(wx, st))) return rc;
   chan_sum_kernel<<<LG, 512, 0, st>>>(d.delta_sum, d.bx_grad, d.B, LG, P);
@@ -520,6 +579,37 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
   return PTK_OK;
 }
 
+template <int KS>
+static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t st) {
+  const int P = d.H * d.W, taps = KS * KS, T = d.T;
+  const size_t S = (size_t)d.B * LC * P;
+  int rc;
+  if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 1, d.whD, (size_t)LG * taps * 32, st))) return rc;
+  if ((rc = launch_prepg(d.wx, 4, LC, LC, taps, 1, d.wxD, (size_t)LG * taps * 32, st))) return rc;
+  // head: d out -> dh_T (= grad of dummyhgru.backward), d bn / conv6.  v_prev lives in d.dc, v_new in d.dh.
+  head_bwd_kernel<<<LC, 512, 0, st>>>(d.h_at(T), d.head_stats, d.bn_w, d.bn_b, d.w6, d.dout, d.dc, d.head_grads, d.B, P);
+  PTK_LAUNCH_OK("head_bwd_kernel");
+  PTK_CUDA_OK(cudaMemcpyAsync(d.rbp_g, d.dc, S * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  rbp_sumsq_kernel<<<RBP_CTAS, 256, 0, st>>>(d.dc, nullptr, S, d.rbp_part, nullptr);
+  rbp_decide_kernel<<<1, 32, 0, st>>>(d.rbp_part, RBP_CTAS, d.rbp_state, 1);
+  for (int ii = 0; ii < num_iter; ++ii) {
+    lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(d.dc, 0.f, nullptr, 0.f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
+                                             nullptr, nullptr, 0, d.B, P, d.rbp_state);
+    ConvGArgs c{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0, d.rbp_state};
+    if ((rc = launch_convg<KS>(c, st))) return rc;
+    rbp_sumsq_kernel<<<RBP_CTAS, 256, 0, st>>>(d.dh, d.rbp_g, S, d.rbp_part, d.rbp_state);
+    rbp_decide_kernel<<<1, 32, 0, st>>>(d.rbp_part, RBP_CTAS, d.rbp_state, 0);
+    rbp_commit_kernel<<<148 * 4, 256, 0, st>>>(d.rbp_g, d.dc, d.dh, S, d.rbp_state);
+  }
+  PTK_LAUNCH_OK("rbp neumann series");
+  // one cell-step backward with dh_T := g (dc_T = 0): deltas of the last step only
+  lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(d.rbp_g, 0.f, nullptr, 0.f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
+                                           nullptr, d.delta_sum, 1, d.B, P);
+  WgradGArgs w{d.h_at(T - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, 0};
+  if ((rc = launch_wgradg<KS>(w, st))) return rc;
+  return convlstm_grad_tail<KS>(d, st);
+}
+
 int run_convlstm_forward(const LstmDev& d, cudaStream_t st) {
   return d.KS == 15 ? convlstm_forward_t<15>(d, st) : convlstm_forward_t<7>(d, st);
 }
@@ -528,6 +618,9 @@ int run_convlstm_penalty(const LstmDev& d, cudaStream_t st) {
 }
 int run_convlstm_backward(const LstmDev& d, cudaStream_t st) {
   return d.KS == 15 ? convlstm_backward_t<15>(d, st) : convlstm_backward_t<7>(d, st);
+}
+int run_convlstm_backward_rbp(const LstmDev& d, int num_iter, cudaStream_t st) {
+  return d.KS == 15 ? convlstm_backward_rbp_t<15>(d, num_iter, st) : convlstm_backward_rbp_t<7>(d, num_iter, st);
 }
 
 }  // namespace ptk

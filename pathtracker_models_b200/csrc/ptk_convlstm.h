@@ -24,6 +24,8 @@ struct LstmDev {
   // scratch
   float *G, *delta, *delta_sum, *dh, *dc;
   float *slots_h, *slots_x, *slots_0, *bx_grad, *b0_grad, *head_grads;
+  float *rbp_g, *rbp_state;             // RBP: Neumann sum g [B,25,P]; state {|v_prev|, terminated, accepted terms}
+  double* rbp_part;                     // [RBP_CTAS][2] partial sums of squares
   // I/O
   float* out;                           // [B,2,H,W]
   const float* dout;
@@ -39,5 +41,6 @@ struct LstmDev {
 int run_convlstm_forward(const LstmDev& d, cudaStream_t st);
 int run_convlstm_penalty(const LstmDev& d, cudaStream_t st);
 int run_convlstm_backward(const LstmDev& d, cudaStream_t st);
+int run_convlstm_backward_rbp(const LstmDev& d, int num_iter, cudaStream_t st);
 
 }  // namespace ptk

@@ -51,3 +51,39 @@ def test_convlstm_eval_mode_and_determinism():
         o2, states, l2 = m(x, 0, 0, tgt, torch.nn.CrossEntropyLoss(), testmode=True)
     assert pen.shape == (1,) and states == [] and torch.equal(o1, o2)
     assert rel_err(o1, case["output"]) < REL_TOL
+
+
+@pytest.mark.parametrize("name", ["convlstm_k7_rbp", "convlstm_k7_rbp_trunc"])
+def test_convlstm_rbp_grads_vs_reference(name):
+    """recurrent back-propagation: CUDA Neumann series vs the reference's own outputs."""
+    import os
+    import numpy as np
+    from oracle import convlstm_oracle as CO
+    from pathtracker_models_b200 import convlstm
+    from pathtracker_models_b200.convlstm import _ConvLSTMFunction
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case(name)
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    num_iter = int(z["num_iter"])
+    B, T, H, W = case["shape"]
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method='rbp', num_iter=num_iter)
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    loss.backward()
+    assert rel_err(out, case["output"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
+    p64 = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
+    _, _, g64, terms = CO.rbp_grads(case["x"], p64, T, case["target"], num_iter)
+    assert int(_ConvLSTMFunction.last_rbp_terms.item()) == terms
+    bad = []
+    for n, p in m.named_parameters():
+        e = rel_err(p.grad, case["grads"][n])
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+    # testmode of the rbp branch returns the T+1 hidden states (models/convlstm.py:127-135)
+    m.eval()
+    with torch.no_grad():
+        o2, states, _ = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss(), testmode=True)
+    assert len(states) == T + 1 and states[0].abs().max().item() == 0.0 and states[-1].shape == (B, 25, H, W)

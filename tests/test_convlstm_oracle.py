@@ -21,3 +21,22 @@ def test_convlstm_oracle_matches_reference_fp64(name):
         v = prs.normal(0, 1, (4, g.size))
         assert np.allclose(v @ g, case["proj"][n], rtol=1e-8, atol=1e-12 * max(1.0, case["gmax"][n])), n
         assert abs(np.abs(g).max() - case["gmax"][n]) <= 1e-9 * case["gmax"][n], n
+
+
+@pytest.mark.parametrize("name", ["convlstm_k7_rbp", "convlstm_k7_rbp_trunc"])
+def test_rbp_oracle_matches_reference_fp64(name):
+    """grad_method='rbp' (dummyhgru Neumann series, models/convlstm.py:9-54,124-135): fixture = the reference itself."""
+    import torch
+    from oracle import convlstm_oracle as CO
+    import numpy as _np
+    import os
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case(name)
+    z = _np.load(os.path.join(GOLDEN, name + ".npz"))
+    num_iter, calls = int(z["num_iter"]), int(z["rbp_grad_calls"])
+    p = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
+    out, loss, grads, terms = CO.rbp_grads(case["x"], p, case["shape"][1], case["target"], num_iter)
+    assert rel_err(out, case["output"]) < 1e-10 and abs(loss - case["loss"]) < 1e-10
+    assert terms in (calls, calls - 1) and terms <= num_iter     # the reference tried `calls` terms (the last may be rejected)
+    for n, g in case["grads"].items():
+        assert rel_err(grads[n], g) < (2e-7 if g.numel() > 4096 else 1e-9), n
