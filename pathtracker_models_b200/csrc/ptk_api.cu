@@ -63,7 +63,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   const size_t S = state_elems(dm);
   const int pw = pw_grid(dm->B, dm->H, dm->W);
   float* w = cv.take<float>(4 * (size_t)C * C * TAPS);
-  float* gt = cv.take<float>(6 * C * C);
+  float* gt = cv.take<float>(3 * 6 * C * C);   // gateT, gateTF, gateF
   float* Ge = cv.take<float>(S);
   float* big = cv.take<float>(14 * S);   // inference ring (9S) or backward scratch (14S)
   float* ring_stats = cv.take<float>(4 * C);
@@ -100,7 +100,11 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
     }
     d->w_inh_f = w; d->w_inh_d = w + (size_t)C * C * TAPS;
     d->w_exc_f = w + 2 * (size_t)C * C * TAPS; d->w_exc_d = w + 3 * (size_t)C * C * TAPS;
-    for (int i = 0; i < 6; ++i) d->gateT[i] = gt + i * C * C;
+    for (int i = 0; i < 6; ++i) {
+      d->gateT[i] = gt + i * C * C;
+      d->gateTF[i] = gt + (6 + i) * C * C;
+      d->gateF[i] = gt + (12 + i) * C * C;
+    }
   }
   return (cv.off + 255) & ~(size_t)255;
 }

@@ -30,6 +30,8 @@ struct IntDev {
   const float *Wp, *bp, *alpha, *mu, *gamma, *kappa;
   const float* gate[6];    // [out][in], a_w a_u i_w i_u e_w e_u
   const float* gateT[6];   // [in][out]
+  const float* gateTF[6];  // gateT in mma B-fragment order (ptk_pw.cuh), tensor-core modes
+  const float* gateF[6];   // gate ([out][in], the k-by-n matrix of the transposed products) in B-fragment order
   const float* gate_b[6];
   const float *bn_w[2], *bn_b[2];
   const float *Wr, *br, *Wt, *bt, *Wd, *bd;

@@ -22,6 +22,10 @@
 #include "ptk_profile.h"
 #include "ptk_pw.cuh"
 
+#ifndef PTK_BWD_MMA
+#define PTK_BWD_MMA 0
+#endif
+
 namespace ptk {
 
 constexpr int TILE_F = C * TP;
@@ -253,10 +257,15 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   BwdCIn cur;
   float xin[3][4];
   // prologue on parameters, forward statistics and the (read-only) clip: overlaps the previous kernel's tail (PDL)
-  cta_fill_async(sWiw, d.gate[2], C * C);
-  cta_fill_async(sWiu, d.gate[3], C * C);
-  cta_fill_async(sWew, d.gate[4], C * C);
-  cta_fill_async(sWeu, d.gate[5], C * C);
+  // The mma.sync gate products (ptk_pw.cuh) pay in the forward kernels (-14 %) but not here: with 4-6 products per
+  // tile the legacy HMMA tf32 pipe is as busy as the FMA pipe was (measured +4 % on the two backward kernels), so
+  // the backward keeps the register-tiled FFMA products.  Flip PTK_BWD_MMA to re-measure.
+  constexpr bool MMA = PTK_BWD_MMA && (ACT & ACT_FAST) != 0;
+  const float* const* gsrc = MMA ? d.gateF : d.gate;
+  cta_fill_async(sWiw, gsrc[2], C * C);
+  cta_fill_async(sWiu, gsrc[3], C * C);
+  cta_fill_async(sWew, gsrc[4], C * C);
+  cta_fill_async(sWeu, gsrc[5], C * C);
   cta_fill_async(sWp, d.Wp, C * 3);
   cta_fill_async(sbp, d.bp, C);
   cta_fill_async(sAl, d.alpha, C);
@@ -311,15 +320,31 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
       cp_async_wait<0>();
       __syncwarp();
       float acc[4][8];
-      acc_fill(acc, nullptr, L);
-      warp_gemm(acc, sGe, sWew, L);
-      acc_to_global(d.dS, base, P, L, acc);
+      if (MMA) {
+        Frag f;
+        frag_zero(f);
+        warp_mma_gemm(f, sGe, sWew);
+        acc_fill(acc, nullptr, L);
+        acc_to_global(d.dS, base, P, L, acc);          // zero, then the product in fragment layout
+        __syncwarp();
+        frag_add_to_global(d.dS, (size_t)b * C * P + pix_base, P, f);
+        frag_zero(f);
+        warp_mma_gemm(f, sGe, sWeu);
+        __syncwarp();
+        frag_to_tile(sGe, f);                           // ge is dead once both products have read it
+        __syncwarp();
+      } else {
+        acc_fill(acc, nullptr, L);
+        warp_gemm(acc, sGe, sWew, L);
+        acc_to_global(d.dS, base, P, L, acc);
+      }
 #pragma unroll
       for (int o = 0; o < 8; ++o) {
         const float4 g1 = ld4(d.gI + base + (size_t)(L.oc0 + o) * P), g2 = ld4(d.cgI + base + (size_t)(L.oc0 + o) * P);
         acc[0][o] = g1.x + g2.x; acc[1][o] = g1.y + g2.y; acc[2][o] = g1.z + g2.z; acc[3][o] = g1.w + g2.w;
       }
-      warp_gemm(acc, sGe, sWeu, L);
+      if (MMA) acc_add_tile(acc, sGe, L);
+      else warp_gemm(acc, sGe, sWeu, L);
       acc_to_global(d.dGe, base, P, L, acc);
       acc_fill(acc, nullptr, L);
       acc_to_global(d.gI, base, P, L, acc);   // the step ignores its inhibition input: dI for step t-1 is zero
@@ -383,17 +408,42 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
     cp_async_wait<0>();
     __syncwarp();
     float acc[4][8];
-    acc_from_global(acc, d.dX, base, P, L);
-    warp_gemm(acc, sGi, sWiw, L);      // dX = z + Wi_w^T gi
-    acc_to_global(d.dX, base, P, L, acc);
-    acc_from_global(acc, d.dS, base, P, L);
-    warp_gemm(acc, sGi, sWiu, L);      // dS += Wi_u^T gi
-    warp_gemm(acc, sGe, sWew, L);      //     + We_w^T ge
-    if (CELL == PTK_CELL_INT) acc_to_global(d.gI, base, P, L, acc);   // (b10) InT: dI += dS
-    else acc_to_global(d.dS, base, P, L, acc);                         //       hGRU: dA += dS (in bwd_d)
-    acc_fill(acc, nullptr, L);
-    warp_gemm(acc, sGe, sWeu, L);      // dGe = We_u^T ge
-    acc_to_global(d.dGe, base, P, L, acc);
+    if (MMA) {
+      Frag f;                            // one accumulator set at a time (two would spill)
+      frag_zero(f);
+      warp_mma_gemm(f, sGi, sWiw);       // dX = z + Wi_w^T gi: added to the parked z in fragment layout
+      frag_add_to_global(d.dX, (size_t)b * C * P + pix_base, P, f);
+      frag_zero(f);
+      warp_mma_gemm(f, sGi, sWiu);       // dS += Wi_u^T gi + We_w^T ge   (the gi tile is dead after this)
+      warp_mma_gemm(f, sGe, sWew);
+      __syncwarp();
+      frag_to_tile(sGi, f);
+      __syncwarp();
+      acc_from_global(acc, d.dS, base, P, L);
+      acc_add_tile(acc, sGi, L);
+      if (CELL == PTK_CELL_INT) acc_to_global(d.gI, base, P, L, acc);   // (b10) InT: dI += dS
+      else acc_to_global(d.dS, base, P, L, acc);                         //       hGRU: dA += dS (in bwd_d)
+      frag_zero(f);
+      warp_mma_gemm(f, sGe, sWeu);       // dGe = We_u^T ge
+      __syncwarp();
+      frag_to_tile(sGe, f);
+      __syncwarp();
+      acc_fill(acc, nullptr, L);
+      acc_add_tile(acc, sGe, L);
+      acc_to_global(d.dGe, base, P, L, acc);
+    } else {
+      acc_from_global(acc, d.dX, base, P, L);
+      warp_gemm(acc, sGi, sWiw, L);      // dX = z + Wi_w^T gi
+      acc_to_global(d.dX, base, P, L, acc);
+      acc_from_global(acc, d.dS, base, P, L);
+      warp_gemm(acc, sGi, sWiu, L);      // dS += Wi_u^T gi
+      warp_gemm(acc, sGe, sWew, L);      //     + We_w^T ge
+      if (CELL == PTK_CELL_INT) acc_to_global(d.gI, base, P, L, acc);   // (b10) InT: dI += dS
+      else acc_to_global(d.dS, base, P, L, acc);                         //       hGRU: dA += dS (in bwd_d)
+      acc_fill(acc, nullptr, L);
+      warp_gemm(acc, sGe, sWeu, L);      // dGe = We_u^T ge
+      acc_to_global(d.dGe, base, P, L, acc);
+    }
     __syncwarp();
   }
   if (CELL == CELL_NOINH) return;      // no alpha / mu / BatchNorm0 in this variant
@@ -439,8 +489,13 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   BwdDIn cur;
   float xin[3][4];
   // prologue on parameters, forward statistics and the (read-only) clip: overlaps the previous kernel's tail (PDL)
-  cta_fill_async(sWaw, d.gate[0], C * C);
-  cta_fill_async(sWau, d.gate[1], C * C);
+  // The mma.sync gate products (ptk_pw.cuh) pay in the forward kernels (-14 %) but not here: with 4-6 products per
+  // tile the legacy HMMA tf32 pipe is as busy as the FMA pipe was (measured +4 % on the two backward kernels), so
+  // the backward keeps the register-tiled FFMA products.  Flip PTK_BWD_MMA to re-measure.
+  constexpr bool MMA = PTK_BWD_MMA && (ACT & ACT_FAST) != 0;
+  const float* const* gsrc = MMA ? d.gateF : d.gate;
+  cta_fill_async(sWaw, gsrc[0], C * C);
+  cta_fill_async(sWau, gsrc[1], C * C);
   cta_fill_async(sWp, d.Wp, C * 3);
   cta_fill_async(sbp, d.bp, C);
   if (fuse) bwd_a_fill_const(d, t - 1, sKa, sGa, sW1, sB1, sM1, sR1);
@@ -502,14 +557,30 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
       tile_st(sA, L, o, oa);
     }
     __syncwarp();
-    float acc[4][8];
-    acc_from_global(acc, d.gE, base, P, L);
-    warp_gemm(acc, sA, sWau, L);     // dE += Wa_u^T a   (= dE' of step t-1)
-    if (fuse) acc_to_tile(sB, L, acc);
-    acc_from_global(acc, d.dX, base, P, L);
-    warp_gemm(acc, sA, sWaw, L);     // dX += Wa_w^T a
-    __syncwarp();
-    acc_to_tile(sA, L, acc);         // park dX; each thread re-reads only its own patch
+    if (MMA) {
+      Frag f;                          // one accumulator set at a time
+      if (fuse) {
+        frag_zero(f);
+        warp_mma_gemm(f, sA, sWau);    // dE += Wa_u^T a   (= dE' of step t-1), parked in the free tile
+        frag_to_tile(sB, f);
+      }
+      frag_zero(f);
+      warp_mma_gemm(f, sA, sWaw);      // dX += Wa_w^T a
+      __syncwarp();
+      frag_to_tile(sA, f);             // park dX
+      __syncwarp();
+      if (fuse) tile_add_global(sB, d.gE, base, P, L);
+      tile_add_global(sA, d.dX, base, P, L);
+    } else {
+      float acc[4][8];
+      acc_from_global(acc, d.gE, base, P, L);
+      warp_gemm(acc, sA, sWau, L);     // dE += Wa_u^T a   (= dE' of step t-1)
+      if (fuse) acc_to_tile(sB, L, acc);
+      acc_from_global(acc, d.dX, base, P, L);
+      warp_gemm(acc, sA, sWaw, L);     // dX += Wa_w^T a
+      __syncwarp();
+      acc_to_tile(sA, L, acc);         // park dX; each thread re-reads only its own patch
+    }
     BwdAIn acur, anxt;
     if (fuse) bwd_a_load(d, t - 1, 0, base + (size_t)L.oc0 * P, acur);   // in flight during the stem loop below
     float dxs[3][4];
@@ -602,16 +673,6 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 //     ~2^-21 relative error per product (same idea as the split-bf16 convolutions).  The [c][GSP] tile
 //     layout (GSP = 68 = 4 mod 32) makes every fragment load a conflict-free LDS.32.
 constexpr int GPX = 64, GSP = GPX + 4, GT_F = C * GSP;
-
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;           // truncation: x - hi is exact and |lo| < 2^-10 |x|
-  lo = __float_as_uint(x - __uint_as_float(hi));   // the MMA reads only the tf32 bits of lo (error ~2^-20 |x|)
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 
 template <int CELL, bool MMA>
 __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {

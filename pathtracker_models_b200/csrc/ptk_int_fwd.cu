@@ -42,12 +42,23 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
   const int P = d.H * d.W, pix = pix_base + L.pxo;
   stem_to_tile<ACT>(sX, sWp, sbp, xin, L);
   __syncwarp();
+  constexpr bool MMA = (ACT & ACT_FAST) != 0;   // tensor-core modes: weights are in B-fragment order, bias added at read
   float acc[4][8];
-  acc_fill(acc, sba, L);
-  warp_gemm(acc, sX, sWaw, L);
-  warp_gemm(acc, sE, sWau, L);
-  __syncwarp();
-  acc_to_tile(sX, L, acc);          // park the pre-activations; only this thread re-reads its patch
+  if (MMA) {
+    Frag f;
+    frag_zero(f);
+    warp_mma_gemm(f, sX, sWaw);
+    warp_mma_gemm(f, sE, sWau);
+    __syncwarp();
+    frag_to_tile(sX, f);
+    __syncwarp();
+  } else {
+    acc_fill(acc, sba, L);
+    warp_gemm(acc, sX, sWaw, L);
+    warp_gemm(acc, sE, sWau, L);
+    __syncwarp();
+    acc_to_tile(sX, L, acc);          // park the pre-activations; only this thread re-reads its patch
+  }
   float* Aout = d.A_at(t) + (size_t)b * d.a_bstride + pix;
   float* Geout = d.Ge + (size_t)b * C * P + pix;
   float* Iout = d.I_at(t + 1) + (size_t)b * C * P + pix;
@@ -56,8 +67,9 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
     float e[4], a[4], ge[4];
     tile_ld(sE, L, o, e);
     tile_ld(sX, L, o, a);
+    const float bias = MMA ? sba[L.oc0 + o] : 0.f;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) { a[p] = sigm<ACT>(a[p]); ge[p] = a[p] * e[p]; }
+    for (int p = 0; p < 4; ++p) { a[p] = sigm<ACT>(a[p] + bias); ge[p] = a[p] * e[p]; }
     st4(Aout + (size_t)(L.oc0 + o) * P, a);
     st4(Geout + (size_t)(L.oc0 + o) * P, ge);
     if (NOINH) {
@@ -67,9 +79,21 @@ __device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, in
   }
   if (NOINH) {
     __syncwarp();
-    acc_fill(acc, sbe, L);
-    warp_gemm(acc, sE, sWew, L);
-    warp_gemm(acc, sX, sWeu, L);
+    if (MMA) {
+      Frag f;
+      frag_zero(f);
+      warp_mma_gemm(f, sE, sWew);
+      warp_mma_gemm(f, sX, sWeu);
+      __syncwarp();
+      frag_to_tile(sX, f);          // Ge (in sX) is dead now
+      __syncwarp();
+      acc_fill(acc, sbe, L);
+      acc_add_tile(acc, sX, L);
+    } else {
+      acc_fill(acc, sbe, L);
+      warp_gemm(acc, sE, sWew, L);
+      warp_gemm(acc, sX, sWeu, L);
+    }
     float* Gx = d.Gex_at(t) + (size_t)b * C * P + pix;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -90,9 +114,10 @@ __global__ void __launch_bounds__(128, 4) int_pre_kernel(IntDev d, int t) {
   float* sWeu = sWew + (NOINH ? C * C : 0);
   float* tiles = sWeu + (NOINH ? C * C : 0);
   __shared__ float sWp[C * 3], sbp[C], sba[C], sbe[C];
-  cta_fill(sWaw, d.gateT[0], C * C);
-  cta_fill(sWau, d.gateT[1], C * C);
-  if (NOINH) { cta_fill(sWew, d.gateT[4], C * C); cta_fill(sWeu, d.gateT[5], C * C); }
+  const float* const* gsrc = (ACT & ACT_FAST) ? d.gateTF : d.gateT;   // B-fragment order for the mma products
+  cta_fill(sWaw, gsrc[0], C * C);
+  cta_fill(sWau, gsrc[1], C * C);
+  if (NOINH) { cta_fill(sWew, gsrc[4], C * C); cta_fill(sWeu, gsrc[5], C * C); }
   cta_fill(sWp, d.Wp, C * 3);
   cta_fill(sbp, d.bp, C);
   if (threadIdx.x < C) {
@@ -145,10 +170,11 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   int wt = blockIdx.x * 4 + warp;
   float xin[3][4];
   // prologue on parameters and the (read-only) input clip only: overlaps the previous kernel's tail (PDL)
-  cta_fill_async(sWiw, d.gateT[2], C * C);
-  cta_fill_async(sWiu, d.gateT[3], C * C);
-  cta_fill_async(sWew, d.gateT[4], C * C);
-  cta_fill_async(sWeu, d.gateT[5], C * C);
+  const float* const* gsrc = (ACT & ACT_FAST) ? d.gateTF : d.gateT;   // B-fragment order for the mma products
+  cta_fill_async(sWiw, gsrc[2], C * C);
+  cta_fill_async(sWiu, gsrc[3], C * C);
+  cta_fill_async(sWew, gsrc[4], C * C);
+  cta_fill_async(sWeu, gsrc[5], C * C);
   cta_fill_async(sWp, d.Wp, C * 3);
   cta_fill_async(sbp, d.bp, C);
   cta_fill_async(sAl, d.alpha, C);
@@ -194,11 +220,24 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
       cp_async_wait<0>();
       __syncwarp();
     }
+    constexpr bool MMA = (ACT & ACT_FAST) != 0;
     float acc[4][8];
     // excitation gate (eq. 9) first: G_e = sigmoid(We_w S + We_u Ge + b), written straight to the checkpoint
-    acc_fill(acc, sbe, L);
-    warp_gemm(acc, sS, sWew, L);
-    warp_gemm(acc, sGX, sWeu, L);
+    if (MMA) {
+      Frag f;
+      frag_zero(f);
+      warp_mma_gemm(f, sS, sWew);
+      warp_mma_gemm(f, sGX, sWeu);
+      __syncwarp();
+      frag_to_tile(sGX, f);          // the Ge tile is dead once both products have read it
+      __syncwarp();
+      acc_fill(acc, sbe, L);
+      acc_add_tile(acc, sGX, L);
+    } else {
+      acc_fill(acc, sbe, L);
+      warp_gemm(acc, sS, sWew, L);
+      warp_gemm(acc, sGX, sWeu, L);
+    }
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
       float gx[4];
@@ -212,11 +251,21 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
     stem_to_tile<ACT>(sGX, sWp, sbp, xin, L);     // the Ge tile is free now: X takes its place
     __syncwarp();
     // inhibition gate pre-activation (eq. 7), parked in the S tile (S is re-read from global below)
-    acc_fill(acc, sbi, L);
-    warp_gemm(acc, sGX, sWiw, L);
-    warp_gemm(acc, sS, sWiu, L);
-    __syncwarp();
-    acc_to_tile(sS, L, acc);
+    if (MMA) {
+      Frag f;
+      frag_zero(f);
+      warp_mma_gemm(f, sGX, sWiw);
+      warp_mma_gemm(f, sS, sWiu);
+      __syncwarp();
+      frag_to_tile(sS, f);           // bias is added where the tile is read
+      __syncwarp();
+    } else {
+      acc_fill(acc, sbi, L);
+      warp_gemm(acc, sGX, sWiw, L);
+      warp_gemm(acc, sS, sWiu, L);
+      __syncwarp();
+      acc_to_tile(sS, L, acc);
+    }
 #pragma unroll 1
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
@@ -234,9 +283,10 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
       } else {
         I[0] = cur.i.x; I[1] = cur.i.y; I[2] = cur.i.z; I[3] = cur.i.w;
       }
+      const float gbias = MMA ? sbi[c] : 0.f;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        gi[p] = sigm<ACT>(gi[p]);
+        gi[p] = sigm<ACT>(gi[p] + gbias);
         const float U = fmaf(y0[p], sScale[c], sShift[c]);
         const float Pp = U * fmaf(sAl[c], S[p], sMu[c]);
         const float Q = actf<ACT>(Pp);
@@ -280,9 +330,10 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
   PostIn cur;
   float xin[3][4];
   // prologue on parameters and the (read-only) input clip only: overlaps the previous kernel's tail (PDL)
-  cta_fill_async(sWaw, d.gateT[0], C * C);
-  cta_fill_async(sWau, d.gateT[1], C * C);
-  if (NOINH) { cta_fill_async(sWew, d.gateT[4], C * C); cta_fill_async(sWeu, d.gateT[5], C * C); }
+  const float* const* gsrc = (ACT & ACT_FAST) ? d.gateTF : d.gateT;   // B-fragment order for the mma products
+  cta_fill_async(sWaw, gsrc[0], C * C);
+  cta_fill_async(sWau, gsrc[1], C * C);
+  if (NOINH) { cta_fill_async(sWew, gsrc[4], C * C); cta_fill_async(sWeu, gsrc[5], C * C); }
   cta_fill_async(sWp, d.Wp, C * 3);
   cta_fill_async(sbp, d.bp, C);
   cta_fill_async(sKa, d.kappa, C);
@@ -417,11 +468,18 @@ __global__ void prep_weights_kernel(const float* __restrict__ w /*[oc][ic][49]*/
   if (wf) wf[(ic * TAPS + tap) * C + oc] = v;
   if (wd) wd[(oc * TAPS + (TAPS - 1 - tap)) * C + ic] = v;   // conv_transpose2d(dY, w, padding=3)
 }
+// gateT = [in][out]; gateT + 6*1024: the same matrix in mma B-fragment order (ptk_pw.cuh); gateT + 12*1024: the
+// [out][in] matrix (k = out, n = in: the transposed products of the backward kernels) in B-fragment order.
 __global__ void prep_gates_kernel(IntGateSrc g, float* gateT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 6 * C * C) return;
   const int gi = i / (C * C), o = (i / C) % C, in = i % C;
   gateT[gi * C * C + in * C + o] = g.w[gi][o * C + in];
+  // fragment-order element r of matrix gi: (kt, nt, lane, j) -> k = kt*8 + (lane&3) + 4j, n = nt*8 + (lane>>2)
+  const int r = i % (C * C), j = r & 1, lane = (r >> 1) & 31, nt = (r >> 6) & 3, kt = r >> 8;
+  const int k = kt * 8 + (lane & 3) + 4 * j, n = nt * 8 + (lane >> 2);
+  gateT[(6 + gi) * C * C + r] = g.w[gi][n * C + k];    // gateT[k][n] = w[out = n][in = k]
+  gateT[(12 + gi) * C * C + r] = g.w[gi][k * C + n];   // gate[k = out][n = in]
 }
 
 // ---- host ----------------------------------------------------------------------------------

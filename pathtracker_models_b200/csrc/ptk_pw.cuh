@@ -43,6 +43,71 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[4][8], const float* __res
   }
 }
 
+// ---- tensor-core variant of the gate products (tensor-core modes only) -----------------------------------------
+// out[px][n] += sum_k tile[k][px] * W[k][n] on mma.sync.m16n8k8 tf32 with the operands split x = hi + lo in
+// registers (mask + subtract) and three products hi*hi + hi*lo + lo*hi: ~2^-20 relative error per product, the
+// same idea as the split-bf16 convolutions.  W sits in shared memory in B-fragment order (prep_gates_kernel):
+//   WF[((kt*4 + nt)*32 + lane)*2 + j] = W[kt*8 + (lane&3) + 4j][nt*8 + (lane>>2)].
+// The accumulators come out in MMA fragment layout; frag_to_tile writes them to a [c][TP] tile (conflict-free),
+// from which every thread re-reads its own 4 px x 8 ch patch.  4x fewer issue slots than the FFMA product.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;           // truncation: x - hi is exact and |lo| < 2^-10 |x|
+  lo = __float_as_uint(x - __uint_as_float(hi));   // the MMA reads only the tf32 bits of lo (error ~2^-20 |x|)
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+struct Frag { float c[2][4][4]; };   // [m-tile: 16 px][n-tile: 8 ch][4]
+__device__ __forceinline__ void frag_zero(Frag& f) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f.c[m][n][e] = 0.f;
+}
+__device__ __forceinline__ void warp_mma_gemm(Frag& f, const float* __restrict__ tile, const float* __restrict__ sWF) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float* a = tile + (kt * 8 + t) * TP + m * 16 + g;
+      split_tf32(a[0], ah[m][0], al[m][0]);
+      split_tf32(a[8], ah[m][1], al[m][1]);
+      split_tf32(a[4 * TP], ah[m][2], al[m][2]);
+      split_tf32(a[4 * TP + 8], ah[m][3], al[m][3]);
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const float2 b = *reinterpret_cast<const float2*>(sWF + ((kt * 4 + n) * 32 + lane) * 2);
+      uint32_t bh[2], bl[2];
+      split_tf32(b.x, bh[0], bl[0]);
+      split_tf32(b.y, bh[1], bl[1]);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma_tf32(f.c[m][n], al[m], bh);
+        mma_tf32(f.c[m][n], ah[m], bl);
+        mma_tf32(f.c[m][n], ah[m], bh);
+      }
+    }
+  }
+}
+// fragment layout -> [c][TP] tile; callers bracket it with __syncwarp()
+__device__ __forceinline__ void frag_to_tile(float* tile, const Frag& f) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        tile[(n * 8 + 2 * t + (e & 1)) * TP + m * 16 + g + 8 * (e >> 1)] = f.c[m][n][e];
+}
+
 // async copy of a [32 ch][32 px] tile of a [B,C,P] tensor into the warp's shared tile
 __device__ __forceinline__ void warp_tile_load_async(float* tile, const float* __restrict__ src, size_t bstride,
                                                      int b, int pix_base, int P) {
@@ -130,6 +195,40 @@ __device__ __forceinline__ void acc_to_global(float* dst, size_t base, int P, co
   for (int o = 0; o < 8; ++o) {
     const float v[4] = {acc[0][o], acc[1][o], acc[2][o], acc[3][o]};
     st4(dst + base + (size_t)(L.oc0 + o) * P, v);
+  }
+}
+
+// [B,C,P] global tile (base = b*C*P + first pixel of the warp tile) += fragment, in fragment layout: every
+// instruction touches 4 channels x 8 consecutive pixels (full 32-byte sectors).  Used where a second
+// accumulator set would not fit in registers next to the one still being formed.
+__device__ __forceinline__ void frag_add_to_global(float* dst, size_t tile_base, int P, const Frag& f) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float* q = dst + tile_base + (size_t)(n * 8 + 2 * t + (e & 1)) * P + m * 16 + g + 8 * (e >> 1);
+        *q += f.c[m][n][e];
+      }
+}
+// acc += the thread's patch of a tile
+__device__ __forceinline__ void acc_add_tile(float (&acc)[4][8], const float* tile, const Lane& L) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float4 t = ld4(tile + (L.oc0 + o) * TP + L.pxo);
+    acc[0][o] += t.x; acc[1][o] += t.y; acc[2][o] += t.z; acc[3][o] += t.w;
+  }
+}
+// tile patch += [B,C,P] global patch (each thread its own patch)
+__device__ __forceinline__ void tile_add_global(float* tile, const float* src, size_t base, int P, const Lane& L) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    const float4 a = ld4(src + base + (size_t)(L.oc0 + o) * P);
+    float* tp = tile + (L.oc0 + o) * TP + L.pxo;
+    const float4 t = ld4(tp);
+    *reinterpret_cast<float4*>(tp) = make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
   }
 }
 
