@@ -306,7 +306,7 @@ def run_b200(args):
                                      "instrumented vs %.2f ms/step plain)" % (steps, ms_prof / steps, ms_total / steps)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores, sample = cpu_reference_seq_per_s(steps=2, warmup=1)
+            v, sec, cores, sample = cpu_reference_seq_per_s(steps=16, warmup=1)     # ~10-15 s of host work
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
