@@ -237,3 +237,36 @@ def test_device_prefetcher_copies_every_batch():
         assert x.is_cuda and torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
         n += 1
     assert n == 4
+
+
+def test_programmatic_dependent_launch_changes_no_bits(tmp_path):
+    """the PDL chain (ptk_common.cuh) must be pure scheduling: the same step with the launch attribute disabled
+    (PTK_NO_PDL=1, read once per process) is bit-identical; a missing griddepcontrol.wait would show up here."""
+    import os
+    import subprocess
+    import sys
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from tests.golden_util import load_case
+from pathtracker_models_b200 import InT
+case = load_case("int_tile")
+m = InT.InT(dimensions=32, timesteps=8, kernel_size=7); m.load_state_dict(case["sd"]); m = m.cuda()
+x = case["x"].float().cuda(); y = case["y"].float().cuda()
+outs = []
+for _ in range(3):
+    m.zero_grad(set_to_none=True)
+    out, _ = m(x)
+    torch.nn.functional.binary_cross_entropy_with_logits(out, y).backward()
+    outs.append(torch.cat([out.reshape(-1)] + [p.grad.reshape(-1) for p in m.parameters() if p.grad is not None]).cpu())
+assert all(torch.equal(outs[0], o) for o in outs[1:])
+torch.save(outs[0], sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("pdl", {}), ("nopdl", {"PTK_NO_PDL": "1"})):
+        f = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ); e.update(env)
+        r = subprocess.run([sys.executable, "-c", script, f], env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = torch.load(f)
+    assert torch.equal(res["pdl"], res["nopdl"])
