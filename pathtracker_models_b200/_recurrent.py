@@ -80,6 +80,15 @@ class _CellParams(nn.Module):
         raise RuntimeError("the cell is executed inside the fused CUDA time loop; call the model, not the cell")
 
 
+def _attr_by_path(module, path):
+    obj = module
+    for part in path.split("."):
+        obj = obj[int(part)] if part.isdigit() else getattr(obj, part, None)
+        if obj is None:
+            return None
+    return obj
+
+
 class _RecurrentModel(nn.Module):
     """stem + cell + readout container; forward = one call into the CUDA library."""
 
@@ -109,13 +118,15 @@ class _RecurrentModel(nn.Module):
 
     def flat_parameters(self):
         """the 30 live parameters, concatenated in the C ABI's canonical order (differentiable)."""
-        mods = dict(self.named_parameters())
+        # looked up by attribute path, not named_parameters(): nn.DataParallel replicas (mainclean.py:132-134) hold
+        # their broadcast copies as plain tensor attributes and report no parameters at all
         parts = []
         for n in PARAM_ORDER:
-            if n in mods:
-                parts.append(mods[n].reshape(-1))
+            t = _attr_by_path(self, n)
+            if t is not None:
+                parts.append(t.reshape(-1))
             else:   # InT(no_inh=True) has no w_inh (models/InT.py:91-93): the slot stays, filled with zeros
-                ref = mods["unit1.w_exc"]
+                ref = _attr_by_path(self, "unit1.w_exc")
                 parts.append(torch.zeros(ref.numel(), dtype=ref.dtype, device=ref.device))
         return torch.cat(parts)
 

@@ -123,7 +123,13 @@ class ConvLSTM(nn.Module):
         init.constant_(self.conv6.bias, math.log((1 - 0.01) / 0.01))
 
     def flat_parameters(self):
-        return torch.cat([p.reshape(-1) for p in self.parameters()])   # registration order == C ABI order
+        # registration order == C ABI order; by attribute (not parameters()) so that nn.DataParallel replicas work
+        ts = [self.conv0.weight, self.conv0.bias]
+        for g in "ifco":
+            wx, wh = getattr(self.unit1, "Wx" + g), getattr(self.unit1, "Wh" + g)
+            ts += [wx.weight, wx.bias, wh.weight]
+        ts += [self.bn.weight, self.bn.bias, self.conv6.weight, self.conv6.bias]
+        return torch.cat([t.reshape(-1) for t in ts])
 
     def forward(self, x, epoch, itr, target, criterion, testmode=False):
         if not x.is_cuda:

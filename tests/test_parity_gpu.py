@@ -270,3 +270,30 @@ torch.save(outs[0], sys.argv[1])
         assert r.returncode == 0, r.stderr[-2000:]
         res[tag] = torch.load(f)
     assert torch.equal(res["pdl"], res["nopdl"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (nn.DataParallel, mainclean.py:132-134)")
+def test_nn_dataparallel_two_devices_matches_per_replica_runs():
+    """the reference's own multi-GPU mode: replicas called concurrently from Python threads, BatchNorm statistics
+    per replica, gradients summed onto device 0 (SURVEY 8b threading / 8e)."""
+    case = load_case("int_small")
+    m = _model(case, "int")
+    x = torch.cat([case["x"].float(), case["x"].float().flip(0)], 0).cuda()       # batch 2B -> B per device
+    y = torch.cat([case["y"].float(), case["y"].float().flip(0)], 0).cuda()
+    B = x.shape[0] // 2
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    out, pen = dp(x)
+    assert out.shape == (2 * B, 1) and pen.shape == (2,)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+    g_dp = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    outs = []
+    for h in range(2):       # the same halves on one device, each weighted 1/2 in the full-batch mean
+        o, _ = m(x[h * B:(h + 1) * B])
+        (0.5 * torch.nn.functional.binary_cross_entropy_with_logits(o, y[h * B:(h + 1) * B])).backward()
+        outs.append(o.detach())
+    assert rel_err(out, torch.cat(outs, 0)) < 1e-6
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_err(g_dp[n], p.grad) < 1e-5, n
