@@ -207,9 +207,24 @@ def run_b200(args):
 
     from pathtracker_models_b200.data import DevicePrefetcher
 
-    def e2e_run(n):     # every step's clip goes host -> device inside the loop (one batch in flight on a copy stream)
-        for x, y in DevicePrefetcher(((hx[i % nbuf], hy[i % nbuf]) for i in range(n)), dev):
-            step(x.permute(0, 4, 1, 2, 3), y).item()
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_run(n):
+        """every step: its clip goes host -> device (one batch in flight on a copy stream) and its loss comes back to
+        the host.  The loss is copied asynchronously into pinned memory and READ one step later (how a training loop
+        logs it), so the device never idles on the host; the last value is read after the loop."""
+        seen = []
+        for i, (x, y) in enumerate(DevicePrefetcher(((hx[j % nbuf], hy[j % nbuf]) for j in range(n)), dev)):
+            loss = step(x.permute(0, 4, 1, 2, 3), y)
+            loss_host[i & 1:(i & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                seen.append(float(loss_host[(i - 1) & 1]))
+        loss_ev[(n - 1) & 1].synchronize()
+        seen.append(float(loss_host[(n - 1) & 1]))
+        assert len(seen) == n and all(v == v for v in seen)
 
     e2e_run(2)
     barrier()
