@@ -955,7 +955,6 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const int grid = d.pw_ctas;
   const int grid_c = grid;
   const bool tc = (d.conv_mode != PTK_CONV_FP32);
-  const int nWT = d.B * P / WPX;
   const int grid_a = grid;
   PTK_CUDA_OK(cudaMemsetAsync(d.acc, 0, (size_t)PW_EW_CTAS * ACC_N * sizeof(float), st));
   if (CELL == CELL_NOINH) {   // buffers the skipped inhibition branch would have written

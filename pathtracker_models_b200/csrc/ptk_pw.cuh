@@ -26,11 +26,8 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[4][8], const float* __res
                                           const float* __restrict__ sW, const Lane& L) {
   const float* tp = tile + L.pxo;
   const float* wp = sW + L.oc0;
-#ifndef PTK_GEMM_IC
-#define PTK_GEMM_IC C
-#endif
 #pragma unroll 8
-  for (int ic = 0; ic < PTK_GEMM_IC; ++ic) {
+  for (int ic = 0; ic < C; ++ic) {
     const float4 v = *reinterpret_cast<const float4*>(tp + ic * TP);
     const float4 w0 = *reinterpret_cast<const float4*>(wp + ic * C);
     const float4 w1 = *reinterpret_cast<const float4*>(wp + ic * C + 4);
