@@ -137,6 +137,12 @@ class _RecurrentModel(nn.Module):
         flat = self.flat_parameters()
         B = x.shape[0]
         if testmode:   # models/InT.py:230-233,244: (output, states [B,T,1,H,W], gates [B,T,C,H,W])
+            if torch.is_grad_enabled() and (x.requires_grad or flat.requires_grad):
+                # the logits stay differentiable (saliency maps: imgs.requires_grad = True; model_step(test=True);
+                # score.backward(); imgs.grad -- viz_model_att.py:189-196); states / gates are plain outputs
+                from .functional import _IntFunction
+                logits, gates, states = _IntFunction.apply(x, flat, cfg, True)
+                return logits.view(B, 1), states, gates
             with torch.no_grad():
                 logits, _, gates, states = int_forward_raw(x, flat, cfg, want_saved=False, testmode=True)
             return logits.view(B, 1), states, gates

@@ -75,17 +75,28 @@ class _IntFunction(torch.autograd.Function):
     """logits = InT/FFhGRU time loop (x, flat parameters); backward = hand-written BPTT kernels."""
 
     @staticmethod
-    def forward(ctx, x, flat, cfg):
+    def forward(ctx, x, flat, cfg, testmode=False):
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        logits, saved, _, _ = int_forward_raw(x, flat, cfg, want_saved=need)
+        logits, saved, gates, states = int_forward_raw(x, flat, cfg, want_saved=need, testmode=testmode)
+        if testmode and saved is not None:
+            # testmode writes the attention gates straight into the [B,T,C,H,W] output instead of the checkpoint
+            # buffer; the reverse loop reads them from the checkpoint layout [T][B,C,H,W] (ptk_api.cu:bind_saved:
+            # ckI, ckE (T+1 each), Y0, Y1, A, ...), so mirror them there (saliency path, viz_model_att.py:189-196)
+            B, _, T, H, W = x.shape
+            S = B * cfg.C * H * W
+            a_off = (2 * (T + 1) + 2 * T) * S
+            saved.view(torch.float32)[a_off:a_off + T * S].view(T, B, cfg.C, H, W).copy_(gates.permute(1, 0, 2, 3, 4))
         ctx.cfg = cfg
         ctx.saved_buf = saved
         ctx.save_for_backward(x, flat)
-        return logits
+        if not testmode:
+            return logits
+        ctx.mark_non_differentiable(gates, states)
+        return logits, gates, states
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dlogits):
+    def backward(ctx, dlogits, *_unused):
         x, flat = ctx.saved_tensors
         cfg = ctx.cfg
         L = _lib.lib()
@@ -101,7 +112,7 @@ class _IntFunction(torch.autograd.Function):
                                     _ptr(dlogits), _ptr(dflat), _ptr(dx), _ptr(ws), ws_bytes, stream)
             _lib.check(rc, "ptk_int_backward")
         ctx.saved_buf = None
-        return dx, dflat, None
+        return dx, dflat, None, None
 
 
 def int_apply(x, flat, cfg):

@@ -297,3 +297,21 @@ def test_nn_dataparallel_two_devices_matches_per_replica_runs():
     for n, p in m.named_parameters():
         if p.grad is not None:
             assert rel_err(g_dp[n], p.grad) < 1e-5, n
+
+
+def test_saliency_through_testmode_forward():
+    """viz_model_att.py:189-196: imgs.requires_grad = True; output, states, gates = model(imgs, testmode=True);
+    score(output).backward(); imgs.grad -- the testmode logits must stay differentiable."""
+    case = load_case("int_small")
+    m = _model(case, "int")
+    x1 = case["x"].float().cuda().requires_grad_(True)
+    out1, states, gates = m(x1, testmode=True)
+    assert not states.requires_grad and not gates.requires_grad
+    torch.nn.functional.mse_loss(out1.flatten(), torch.zeros_like(out1.flatten())).backward()
+    x2 = case["x"].float().cuda().requires_grad_(True)
+    out2, _ = m(x2)
+    torch.nn.functional.mse_loss(out2.flatten(), torch.zeros_like(out2.flatten())).backward()
+    assert torch.equal(out1, out2)
+    assert x1.grad is not None and float(x1.grad.abs().max()) > 0
+    assert rel_err(x1.grad, x2.grad) < 1e-6
+    assert rel_err(gates, case["extra"]["tm_gates"]) < REL_TOL
