@@ -127,6 +127,15 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // forward checkpoints a backward kernel is about to read out of HBM while the previous kernel drains.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 bool pdl_enabled();   // PTK_NO_PDL=1 disables the attribute (A/B measurements)
+// Every kernel of the time loop asks for the maximum shared-memory carve-out, including the ones that use none
+// (bn_apply): a kernel-to-kernel change of the L1/shared split forces the SMs to drain and reconfigure.
+template <typename F>
+inline cudaError_t ptk_func_smem(F* kern, int dyn_bytes) {
+  cudaError_t e = cudaSuccess;
+  if (dyn_bytes > 0) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

@@ -350,10 +350,10 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
   if (a.mode == PTK_CONV_BF16) {
-    PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    PTK_CUDA_OK(ptk_func_smem(conv7_tc_kernel<true>, TC_SMEM));
     PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc_kernel<true>, grid, dim3(256), TC_SMEM, st, a));
   } else {
-    PTK_CUDA_OK(cudaFuncSetAttribute(conv7_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    PTK_CUDA_OK(ptk_func_smem(conv7_tc_kernel<false>, TC_SMEM));
     PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc_kernel<false>, grid, dim3(256), TC_SMEM, st, a));
   }
   PTK_LAUNCH_OK("conv7_tc_kernel");

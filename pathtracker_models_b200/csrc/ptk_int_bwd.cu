@@ -966,19 +966,20 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     PTK_CUDA_OK(cudaMemsetAsync(d.wacc_inh, 0, (tc ? wgrad_tc_acc_floats(d.B, d.H, d.W) : (size_t)4 * WGRAD_GROUPS * TAPS * 256) * sizeof(float), st));
   }
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_c_kernel<CELL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_C));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_bwd_d_kernel<CELL, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_BWD_D));
-  PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
-  PTK_CUDA_OK(cudaFuncSetAttribute(gate_wgrad_kernel<CELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GATE));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_c_kernel<CELL, ACT>, (int)SM_BWD_C));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
+  PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, true>, (int)SM_GATE));
+  PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, false>, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+  PTK_CUDA_OK(ptk_func_smem(int_readout_bwd_kernel, (int)smr));
   {
     ProfileScope ps(PTK_PROF_MISC, st);
     int_readout_bwd_kernel<<<d.B, 256, smr, st>>>(d, d.E_at(d.T));
   }
   PTK_LAUNCH_OK("int_readout_bwd_kernel");
   const int ew_blocks = 148 * 4;
+  PTK_CUDA_OK(ptk_func_smem(bn_apply_kernel, 0));
   for (int t = d.T - 1; t >= 0; --t) {
     const int first = (t == d.T - 1);
     int rc;

@@ -499,10 +499,10 @@ template <int ACT, bool NOINH>
 static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   const int grid = pw_grid(d.B, d.H, d.W);
   const size_t sm_pre = NOINH ? SM_PRE_NI : SM_PRE;
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_pre_kernel<ACT, NOINH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pre));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_post_kernel<ACT, NOINH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pre));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_mid_kernel<PTK_CELL_INT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MID));
-  PTK_CUDA_OK(cudaFuncSetAttribute(int_mid_kernel<PTK_CELL_HGRU, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MID));
+  PTK_CUDA_OK(ptk_func_smem(int_pre_kernel<ACT, NOINH>, (int)sm_pre));
+  PTK_CUDA_OK(ptk_func_smem(int_post_kernel<ACT, NOINH>, (int)sm_pre));
+  PTK_CUDA_OK(ptk_func_smem(int_mid_kernel<PTK_CELL_INT, ACT>, (int)SM_MID));
+  PTK_CUDA_OK(ptk_func_smem(int_mid_kernel<PTK_CELL_HGRU, ACT>, (int)SM_MID));
   {
     ProfileScope ps(PTK_PROF_POINT_FWD, st);
     int_pre_kernel<ACT, NOINH><<<grid, 128, sm_pre, st>>>(d, 0);

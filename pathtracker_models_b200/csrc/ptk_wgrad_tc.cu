@@ -262,10 +262,10 @@ size_t wgrad_tc_acc_floats(int B, int H, int W) { return (size_t)B * (H / WT_TH)
 int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st) {
   dim3 grid(a.W / WT_TW, a.H / WT_TH, a.B);
   if (a.mode == PTK_CONV_BF16) {
-    PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    PTK_CUDA_OK(ptk_func_smem(wgrad7_tc_kernel<true>, WT_SMEM));
     PTK_CUDA_OK(launch_pdl(true, wgrad7_tc_kernel<true>, grid, dim3(256), WT_SMEM, st, a));
   } else {
-    PTK_CUDA_OK(cudaFuncSetAttribute(wgrad7_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM));
+    PTK_CUDA_OK(ptk_func_smem(wgrad7_tc_kernel<false>, WT_SMEM));
     PTK_CUDA_OK(launch_pdl(true, wgrad7_tc_kernel<false>, grid, dim3(256), WT_SMEM, st, a));
   }
   PTK_LAUNCH_OK("wgrad7_tc_kernel");
