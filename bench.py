@@ -147,6 +147,8 @@ def run_b200(args):
     torch.manual_seed(0)
     if args.model == "convlstm":
         return run_convlstm(args, dev, world, rank)
+    if args.model == "gru":
+        return run_gru(args, dev, world, rank)
     ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
     model = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev)
     model.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
@@ -372,6 +374,46 @@ def run_convlstm(args, dev, world, rank):
                                    "note": "strict-fp32 CUDA-core path; recurrent-conv FLOPs only"}}), flush=True)
 
 
+def run_gru(args, dev, world, rank):
+    """kys.GRU (`--model gru`, utils/engine.py:147-153: 64 channels, 7x7) on the headline clip shape.  Secondary line:
+    first version of this family, strict-fp32 CUDA-core convolutions."""
+    import torch
+    import torch.nn.functional as F
+    from pathtracker_models_b200 import _lib, kys, synth_pathtracker
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    B, T, HW = args.batch, args.frames, args.size
+    torch.manual_seed(0)
+    m = kys.GRU(dimensions=64, timesteps=T, kernel_size=7).to(dev)
+    x, y = synth_pathtracker(B, T, HW, HW, n_distractors=DIST, speed=SPEED, device=dev)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        out, _ = m(x)
+        loss = F.binary_cross_entropy_with_logits(out, y)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    flop = 3 * 2.0 * B * HW * HW * 49 * (128 * 128 + 128 * 64) * T     # fwd + dgrad + wgrad of the two cell convolutions
+    print(json.dumps({"metric": "train seq/s (fwd+bwd) kys.GRU", "value": B * steps / (ms / 1e3), "unit": UNIT,
+                      "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "kys.GRU %d frames %dx%d, batch %d" % (T, HW, HW, B)},
+                      "gpu_launches": _lib.launch_count() - l0,
+                      "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
+                                   "note": "strict-fp32 CUDA-core path; cell-convolution FLOPs only"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,7 +422,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm"], help="non-headline configs (BASELINE configs[2..3])")
+    ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm", "gru"], help="non-headline configs (BASELINE configs[2..3])")
     ap.add_argument("--frames", type=int, default=T)
     ap.add_argument("--size", type=int, default=HW)
     ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],

@@ -227,8 +227,65 @@ def run_convlstm_case(name, filt, B, T, H, W, seed, store_full, grad_method='bpt
     print(name, "loss", res["loss"], "penalty max", res["penalty"].max(), "worst fp32-vs-fp64", worst)
 
 
+def run_gru_case(name, B, T, H, W, seed):
+    """kys.GRU (utils/engine.py:147-153: dimensions = 64, kernel 7).  Weights are the reference's own default init under
+    torch.manual_seed(seed): the mirror module must reproduce them bit for bit, so only the seed is stored; gradients
+    of the three 64x128x7x7 banks are pinned through seeded random projections."""
+    from models import kys
+    rs = np.random.RandomState(seed)
+    x_np = rs.rand(B, 3, T, H, W)
+    y_np = (rs.rand(B, 1) > 0.5).astype(np.float64)
+    res = {"x_seed": seed, "shape": np.array([B, T, H, W])}
+    grads = {}
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        torch.set_default_dtype(torch.float32)
+        torch.manual_seed(seed)
+        m = kys.GRU(dimensions=64, timesteps=T, kernel_size=7)
+        if tag == "f64":
+            res["init_sums"] = np.array([v.double().sum().item() for v in m.state_dict().values()])
+            res["init_keys"] = np.array(list(m.state_dict().keys()))
+        m = m.to(dt)
+        x = torch.from_numpy(x_np).to(dt)
+        y = torch.from_numpy(y_np).to(dt)
+        out, pen = m(x)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+        loss.backward()
+        grads[tag] = {n: prm.grad.detach().double() for n, prm in m.named_parameters() if prm.grad is not None}
+        grads[tag]["__logits__"] = out.detach().double()
+        if tag == "f64":
+            res["logits"] = out.detach().numpy()
+            res["loss"] = np.array(loss.item())
+            with torch.no_grad():
+                o2, states, gates = m(x, testmode=True)
+            res["tm_states"] = states.numpy().astype(np.float32)
+            res["tm_gates_sum"] = np.array(gates.double().sum().item())
+            res["tm_gates_last"] = gates[:, -1, :4].numpy().astype(np.float32)
+            prs = np.random.RandomState(seed + 2)
+            for n, gr in grads[tag].items():
+                if n.startswith("__"):
+                    continue
+                if gr.numel() <= 4096:
+                    res["grad/" + n] = gr.numpy()
+                else:
+                    v = prs.normal(0, 1, (4, gr.numel()))
+                    res["proj/" + n] = v @ gr.numpy().ravel()
+                    res["gmax/" + n] = np.array(gr.abs().max().item())
+    for n, g64 in grads["f64"].items():
+        e = (grads["f32"][n] - g64).abs().max().item() / max(g64.abs().max().item(), 1e-300)
+        res["f32err/" + n] = np.array(e)
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **res)
+    worst = max((float(v), k) for k, v in res.items() if k.startswith("f32err/"))
+    print(name, "loss", res["loss"], "worst fp32-vs-fp64", worst)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "convlstm":
+    if len(sys.argv) > 1 and sys.argv[1] == "gru":
+        load_reference()
+        torch.Tensor.cuda = lambda s, *a, **k: s
+        run_gru_case("gru_small", 2, 3, 32, 32, seed=51)
+        run_gru_case("gru_b3", 3, 2, 16, 64, seed=52)
+    elif len(sys.argv) > 1 and sys.argv[1] == "convlstm":
         load_reference()
         run_convlstm_case("convlstm_k7_small", 7, 2, 3, 32, 32, seed=31, store_full=True)
         run_convlstm_case("convlstm_k15_small", 15, 2, 3, 32, 32, seed=32, store_full=False)

@@ -19,7 +19,8 @@ EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_sa
            "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes",
            "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
            "ptk_convlstm_forward", "ptk_convlstm_backward", "ptk_debug_tc_stamps", "ptk_debug_wt_stamps",
-           "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp")
+           "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp",
+           "ptk_gru_param_offsets", "ptk_gru_saved_bytes", "ptk_gru_workspace_bytes", "ptk_gru_forward", "ptk_gru_backward")
 
 
 class PtkDims(ctypes.Structure):
@@ -29,6 +30,10 @@ class PtkDims(ctypes.Structure):
 
 class PtkLstmDims(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K")]
+
+
+class PtkGruDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "C", "K")]
 
 
 class PtkError(RuntimeError):
@@ -89,6 +94,17 @@ def lib():
                                 ctypes.c_float, ctypes.c_int64, i32, vp]
     L.ptk_convlstm_backward_rbp.restype = ctypes.c_int
     L.ptk_convlstm_backward_rbp.argtypes = [ldp, vp, vp, vp, vp, i32, vp, vp, vp, sz, vp]
+    gdp = ctypes.POINTER(PtkGruDims)
+    L.ptk_gru_param_offsets.restype = ctypes.c_int
+    L.ptk_gru_param_offsets.argtypes = [gdp, i64p]
+    L.ptk_gru_saved_bytes.restype = sz
+    L.ptk_gru_saved_bytes.argtypes = [gdp]
+    L.ptk_gru_workspace_bytes.restype = sz
+    L.ptk_gru_workspace_bytes.argtypes = [gdp]
+    L.ptk_gru_forward.restype = ctypes.c_int
+    L.ptk_gru_forward.argtypes = [gdp, vp, i64p, vp, vp, vp, vp, sz, vp]
+    L.ptk_gru_backward.restype = ctypes.c_int
+    L.ptk_gru_backward.argtypes = [gdp, vp, i64p, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_profile_start.restype = None
     L.ptk_profile_start.argtypes = []
     L.ptk_profile_stop.restype = ctypes.c_int

@@ -4,6 +4,7 @@
 
 #include "ptk_common.cuh"
 #include "ptk_convlstm.h"
+#include "ptk_gru.h"
 #include "ptk_int.h"
 
 #include <stdlib.h>
@@ -425,6 +426,120 @@ int ptk_convlstm_backward_rbp(const PtkLstmDims* dm, const float* x, const float
   if ((rc = run_convlstm_backward_rbp(d, num_iter, st))) return rc;
   if (terms_out) PTK_CUDA_OK(cudaMemcpyAsync(terms_out, d.rbp_state + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
   return PTK_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// ConvGRU (models/kys.py)
+static int gru_check(const PtkGruDims* d, const char* who) {
+  if (!d) { set_error("%s: dims is NULL", who); return PTK_EINVAL; }
+  if (d->C != GC || d->K != 7) {
+    set_error("%s: only dimensions=64, kernel_size=7 are built (utils/engine.py:147-153 passes exactly these); got C=%d K=%d",
+              who, d->C, d->K);
+    return PTK_EUNSUPPORTED;
+  }
+  if (d->B < 1 || d->T < 1 || d->H < 16 || d->W < 32 || d->H % 16 || d->W % 32) {
+    set_error("%s: unsupported shape B=%d T=%d H=%d W=%d (need B,T >= 1, H %% 16 == 0, W %% 32 == 0)", who, d->B, d->T, d->H, d->W);
+    return PTK_EINVAL;
+  }
+  return PTK_OK;
+}
+static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, size_t* saved_bytes) {
+  const size_t P = (size_t)dm->H * dm->W, S = (size_t)dm->B * GC * P, taps = 49;
+  const int groups = 7;
+  Carver sv(saved);     // layout relied upon by pathtracker_models_b200/kys.py (testmode dumps): h, r, u, n
+  float* hs = sv.take<float>((size_t)(dm->T + 1) * S);
+  float* rs = sv.take<float>((size_t)dm->T * S);
+  float* us = sv.take<float>((size_t)dm->T * S);
+  float* ns = sv.take<float>((size_t)dm->T * S);
+  if (saved_bytes) *saved_bytes = (sv.off + 255) & ~(size_t)255;
+  Carver cv(ws);
+  float* wruT = cv.take<float>(4 * 2 * GC * taps * 32);
+  float* wnT = cv.take<float>(2 * 2 * GC * taps * 32);
+  float* wruD = cv.take<float>(4 * 2 * GC * taps * 32);
+  float* wnD = cv.take<float>(4 * GC * taps * 32);
+  float* bru = cv.take<float>(2 * GC);
+  float* Z = cv.take<float>(2 * S);
+  float* Z2 = cv.take<float>(2 * S);
+  float* RU = cv.take<float>(2 * S);
+  float* dZ = cv.take<float>(2 * S);
+  float* dRUsum = cv.take<float>(2 * S);
+  float* Nb = cv.take<float>(S);
+  float* dh = cv.take<float>(S);
+  float* dhp = cv.take<float>(S);
+  float* dXb = cv.take<float>(S);
+  float* dNsum = cv.take<float>(S);
+  float* slots_ru = cv.take<float>((size_t)groups * 2 * GC * 2 * GC * taps);
+  float* slots_n = cv.take<float>((size_t)groups * GC * 2 * GC * taps);
+  float* stem_acc = cv.take<float>(4 * GC);
+  float* bias_grad = cv.take<float>(3 * GC);
+  if (d) {
+    d->groups = groups;
+    d->hs = hs; d->rs = rs; d->us = us; d->ns = ns;
+    d->wruT = wruT; d->wnT = wnT; d->wruD = wruD; d->wnD = wnD; d->bru = bru;
+    d->Z = Z; d->Z2 = Z2; d->RU = RU; d->dZ = dZ; d->dRUsum = dRUsum; d->Nb = Nb; d->dh = dh; d->dhp = dhp; d->dXb = dXb;
+    d->dNsum = dNsum; d->slots_ru = slots_ru; d->slots_n = slots_n; d->stem_acc = stem_acc; d->bias_grad = bias_grad;
+  }
+  return (cv.off + 255) & ~(size_t)255;
+}
+static void gru_offsets(int64_t* o) {   // preproc.{w,b}, conv_reset.{w,b}, conv_update.{w,b}, conv_state_new.{w,b}, total
+  const int64_t nw = (int64_t)GC * 2 * GC * 49;
+  const int64_t sizes[8] = {GC * 3, GC, nw, GC, nw, GC, nw, GC};
+  int64_t a = 0;
+  for (int i = 0; i < 8; ++i) { o[i] = a; a += sizes[i]; }
+  o[8] = a;
+}
+static int gru_bind(GruDev* d, const PtkGruDims* dm, const float* x, const int64_t* xs, const float* params, void* saved,
+                    void* ws) {
+  memset(d, 0, sizeof(*d));
+  d->B = dm->B; d->T = dm->T; d->H = dm->H; d->W = dm->W;
+  d->fv.x = x; d->fv.sb = xs[0]; d->fv.sc = xs[1]; d->fv.st = xs[2]; d->fv.sy = xs[3]; d->fv.sx = xs[4];
+  int64_t o[9];
+  gru_offsets(o);
+  d->Wp = params + o[0]; d->bp = params + o[1]; d->wr = params + o[2]; d->br = params + o[3];
+  d->wu = params + o[4]; d->bu = params + o[5]; d->wn = params + o[6]; d->bnw = params + o[7];
+  d->off_wp = o[0]; d->off_bp = o[1]; d->off_wr = o[2]; d->off_br = o[3]; d->off_wu = o[4]; d->off_bu = o[5];
+  d->off_wn = o[6]; d->off_bn = o[7];
+  gru_carve(dm, saved, ws, d, nullptr);
+  return PTK_OK;
+}
+
+int ptk_gru_param_offsets(const PtkGruDims* d, int64_t* offsets) {
+  if (!d || !offsets) { set_error("ptk_gru_param_offsets: NULL argument"); return PTK_EINVAL; }
+  if (int rc = gru_check(d, "ptk_gru_param_offsets")) return rc;
+  gru_offsets(offsets);
+  return PTK_OK;
+}
+size_t ptk_gru_saved_bytes(const PtkGruDims* d) {
+  if (gru_check(d, "ptk_gru_saved_bytes")) return 0;
+  size_t sb = 0;
+  gru_carve(d, nullptr, nullptr, nullptr, &sb);
+  return sb;
+}
+size_t ptk_gru_workspace_bytes(const PtkGruDims* d) {
+  if (gru_check(d, "ptk_gru_workspace_bytes")) return 0;
+  return gru_carve(d, nullptr, nullptr, nullptr, nullptr);
+}
+int ptk_gru_forward(const PtkGruDims* dm, const float* x, const int64_t x_strides[5], const float* params, float* h_last,
+                    void* saved, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = gru_check(dm, "ptk_gru_forward");
+  if (rc) return rc;
+  if (!x || !x_strides || !params || !h_last || !saved || !workspace) { set_error("ptk_gru_forward: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_gru_workspace_bytes(dm)) { set_error("ptk_gru_forward: workspace too small"); return PTK_ENOMEM; }
+  GruDev d;
+  if ((rc = gru_bind(&d, dm, x, x_strides, params, saved, workspace))) return rc;
+  d.hT = h_last;
+  return run_gru_forward(d, (cudaStream_t)stream);
+}
+int ptk_gru_backward(const PtkGruDims* dm, const float* x, const int64_t x_strides[5], const float* params, const void* saved,
+                     const float* dh_last, float* dparams, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = gru_check(dm, "ptk_gru_backward");
+  if (rc) return rc;
+  if (!x || !x_strides || !params || !saved || !dh_last || !dparams || !workspace) { set_error("ptk_gru_backward: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_gru_workspace_bytes(dm)) { set_error("ptk_gru_backward: workspace too small"); return PTK_ENOMEM; }
+  GruDev d;
+  if ((rc = gru_bind(&d, dm, x, x_strides, params, const_cast<void*>(saved), workspace))) return rc;
+  d.dhT = dh_last; d.dparams = dparams; d.dx = dx;
+  return run_gru_backward(d, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,236 @@
+// ConvGRU baseline (models/kys.py; `--model gru`, utils/engine.py:147-153) on the GPU: first version, strict fp32.
+//
+//   forward  (GRU.forward :104-135, ConvGRUCell.forward :36-48)
+//       X_t = softplus(preproc(x_t))                                   (:106-108; never materialised for all t)
+//       for t: [r|u] = sigmoid([Wr|Wu] * cat(X_t, h) + b)               (:37-40, one stacked 128 -> 128 convolution)
+//              n     = tanh(Wn * cat(X_t, r h) + b)                     (:42-43)
+//              h     = (1 - u) h + u n                                  (:45)
+//   backward (autograd of the above): per step two transposed convolutions and two weight-gradient kernels.
+//   The readout head (:127-133) is outside the time loop and stays with the caller.
+// Convolutions: the generic direct kernels of ptk_convg.cuh (shared with the ConvLSTM path).
+#include "ptk_convg.cuh"
+#include "ptk_gru.h"
+
+namespace ptk {
+
+#define GRU_FOR_EACH(e, n) for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (n); e += (size_t)gridDim.x * blockDim.x)
+
+__device__ __forceinline__ float gru_stem_pre(const GruDev& d, int b, int c, int frame, int pix) {
+  const int y = pix / d.W, x = pix - y * d.W;
+  return fmaf(__ldg(d.Wp + c * 3 + 2), d.fv.at(b, 2, frame, y, x),
+              fmaf(__ldg(d.Wp + c * 3 + 1), d.fv.at(b, 1, frame, y, x),
+                   fmaf(__ldg(d.Wp + c * 3), d.fv.at(b, 0, frame, y, x), __ldg(d.bp + c))));
+}
+
+// Z = cat(X_t, h_{t-1}),  Z2[:, :64] = X_t      (step t = 1..T reads frame t-1)
+__global__ void gru_stem_cat_kernel(GruDev d, int t, int with_rh) {
+  const int P = d.H * d.W;
+  const float* hp = d.h_at(t - 1);
+  GRU_FOR_EACH(e, d.S()) {
+    const int pix = (int)(e % P), c = (int)((e / P) % GC), b = (int)(e / ((size_t)P * GC));
+    const float X = softplus_precise(gru_stem_pre(d, b, c, t - 1, pix));
+    const size_t z = ((size_t)b * 2 * GC + c) * P + pix;
+    d.Z[z] = X;
+    d.Z2[z] = X;
+    const float h = hp[e];
+    d.Z[z + (size_t)GC * P] = h;
+    if (with_rh) d.Z2[z + (size_t)GC * P] = d.r_at(t)[e] * h;       // backward: rebuild cat(X_t, r h) from the saved gate
+  }
+}
+__global__ void gru_gate_kernel(GruDev d, int t) {
+  const int P = d.H * d.W;
+  const float* hp = d.h_at(t - 1);
+  GRU_FOR_EACH(e, d.S()) {
+    const int pix = (int)(e % P), c = (int)((e / P) % GC), b = (int)(e / ((size_t)P * GC));
+    const size_t z = ((size_t)b * 2 * GC + c) * P + pix;
+    const float r = sigmoid_precise(d.RU[z]), u = sigmoid_precise(d.RU[z + (size_t)GC * P]);
+    d.r_at(t)[e] = r;
+    d.u_at(t)[e] = u;
+    d.Z2[z + (size_t)GC * P] = r * hp[e];
+  }
+}
+__global__ void gru_update_kernel(GruDev d, int t) {
+  const float* hp = d.h_at(t - 1);
+  float* ho = d.h_at(t);
+  GRU_FOR_EACH(e, d.S()) {
+    const float n = tanh_precise(d.Nb[e]), u = d.u_at(t)[e];
+    d.n_at(t)[e] = n;
+    ho[e] = (1.0f - u) * hp[e] + u * n;
+  }
+}
+
+// ---- backward -------------------------------------------------------------------------------------------------
+// from dh_t: dN (into Nb), the update half of dRU, dh_{t-1} partial
+__global__ void gru_bwd1_kernel(GruDev d, int t, int first) {
+  const int P = d.H * d.W;
+  const float* hp = d.h_at(t - 1);
+  GRU_FOR_EACH(e, d.S()) {
+    const int pix = (int)(e % P), c = (int)((e / P) % GC), b = (int)(e / ((size_t)P * GC));
+    const size_t z = ((size_t)b * 2 * GC + c) * P + pix;
+    const float dh = d.dh[e], u = d.u_at(t)[e], n = d.n_at(t)[e];
+    const float dN = dh * u * (1.0f - n * n);
+    d.Nb[e] = dN;
+    d.dNsum[e] = first ? dN : d.dNsum[e] + dN;
+    const float dU = dh * (n - hp[e]) * u * (1.0f - u);
+    d.RU[z + (size_t)GC * P] = dU;
+    d.dRUsum[z + (size_t)GC * P] = first ? dU : d.dRUsum[z + (size_t)GC * P] + dU;
+    d.dhp[e] = dh * (1.0f - u);
+  }
+}
+// from dZ2 = dN *^T Wn: dX partial, the reset half of dRU, dh_{t-1} += d(r h) r
+__global__ void gru_bwd2_kernel(GruDev d, int t, int first) {
+  const int P = d.H * d.W;
+  const float* hp = d.h_at(t - 1);
+  GRU_FOR_EACH(e, d.S()) {
+    const int pix = (int)(e % P), c = (int)((e / P) % GC), b = (int)(e / ((size_t)P * GC));
+    const size_t z = ((size_t)b * 2 * GC + c) * P + pix;
+    d.dXb[e] = d.dZ[z];
+    const float drh = d.dZ[z + (size_t)GC * P], r = d.r_at(t)[e];
+    d.dhp[e] += drh * r;
+    const float dR = drh * hp[e] * r * (1.0f - r);
+    d.RU[z] = dR;
+    d.dRUsum[z] = first ? dR : d.dRUsum[z] + dR;
+  }
+}
+// from dZ = dRU *^T [Wr|Wu]: dh_{t-1} complete, d(stem pre-activation) into dXb
+__global__ void gru_bwd3_kernel(GruDev d, int t) {
+  const int P = d.H * d.W;
+  GRU_FOR_EACH(e, d.S()) {
+    const int pix = (int)(e % P), c = (int)((e / P) % GC), b = (int)(e / ((size_t)P * GC));
+    const size_t z = ((size_t)b * 2 * GC + c) * P + pix;
+    d.dh[e] = d.dhp[e] + d.dZ[z + (size_t)GC * P];
+    const float pre = gru_stem_pre(d, b, c, t - 1, pix);
+    const float dX = d.dXb[e] + d.dZ[z];
+    d.dXb[e] = dX * (pre > 20.0f ? 1.0f : sigmoid_precise(pre));      // softplus' (threshold 20, models/kys.py:102)
+  }
+}
+// stem parameter gradients of one step: one CTA per channel, fixed order => deterministic
+__global__ void __launch_bounds__(512) gru_stem_grad_kernel(GruDev d, int t, int first) {
+  __shared__ double sh[16];
+  const int c = blockIdx.x, P = d.H * d.W;
+  const size_t N = (size_t)d.B * P;
+  double s[4] = {0, 0, 0, 0};
+  for (size_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const int b = (int)(i / P), pix = (int)(i % P), y = pix / d.W, x = pix - y * d.W;
+    const float g = d.dXb[((size_t)b * GC + c) * P + pix];
+    s[0] += g;
+    s[1] += (double)g * d.fv.at(b, 0, t - 1, y, x);
+    s[2] += (double)g * d.fv.at(b, 1, t - 1, y, x);
+    s[3] += (double)g * d.fv.at(b, 2, t - 1, y, x);
+  }
+  for (int k = 0; k < 4; ++k) {
+    const double tot = block_sum_d(s[k], sh);
+    if (threadIdx.x == 0) d.stem_acc[c * 4 + k] = first ? (float)tot : d.stem_acc[c * 4 + k] + (float)tot;
+    __syncthreads();
+  }
+}
+// optional d loss / d x of the stem (contiguous [B,3,T,H,W])
+__global__ void gru_dx_kernel(GruDev d, int t) {
+  const int P = d.H * d.W;
+  const size_t n = (size_t)d.B * 3 * P;
+  GRU_FOR_EACH(e, n) {
+    const int pix = (int)(e % P), i = (int)((e / P) % 3), b = (int)(e / ((size_t)P * 3));
+    float s = 0.f;
+    for (int c = 0; c < GC; ++c) s = fmaf(__ldg(d.Wp + c * 3 + i), d.dXb[((size_t)b * GC + c) * P + pix], s);
+    d.dx[(((size_t)b * 3 + i) * d.T + (t - 1)) * P + pix] = s;
+  }
+}
+__global__ void gru_stem_out_kernel(GruDev d) {      // stem_acc [64][4] -> dparams (preproc.weight [64][3], preproc.bias [64])
+  const int c = threadIdx.x;
+  if (c >= GC) return;
+  d.dparams[d.off_bp + c] = d.stem_acc[c * 4];
+  for (int i = 0; i < 3; ++i) d.dparams[d.off_wp + c * 3 + i] = d.stem_acc[c * 4 + 1 + i];
+}
+
+static int gru_prep(const GruDev& d, bool transposed, cudaStream_t st) {
+  const int taps = 49;
+  int rc;
+  const float* ru[2] = {d.wr, d.wu};
+  const float* nn[1] = {d.wn};
+  if ((rc = launch_prepg(ru, 2, GC, 2 * GC, taps, 0, d.wruT, (size_t)4 * 2 * GC * taps * 32, st))) return rc;
+  if ((rc = launch_prepg(nn, 1, GC, 2 * GC, taps, 0, d.wnT, (size_t)2 * 2 * GC * taps * 32, st))) return rc;
+  if (transposed) {
+    if ((rc = launch_prepg(ru, 2, GC, 2 * GC, taps, 1, d.wruD, (size_t)4 * 2 * GC * taps * 32, st))) return rc;
+    if ((rc = launch_prepg(nn, 1, GC, 2 * GC, taps, 1, d.wnD, (size_t)4 * GC * taps * 32, st))) return rc;
+  }
+  PTK_CUDA_OK(cudaMemcpyAsync(d.bru, d.br, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PTK_CUDA_OK(cudaMemcpyAsync(d.bru + GC, d.bu, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PTK_OK;
+}
+
+int run_gru_forward(const GruDev& d, cudaStream_t st) {
+  int rc;
+  if ((rc = gru_prep(d, false, st))) return rc;
+  PTK_CUDA_OK(cudaMemsetAsync(d.h_at(0), 0, d.S() * sizeof(float), st));
+  const int grid = 148 * 8;
+  for (int t = 1; t <= d.T; ++t) {
+    {
+      ProfileScope ps(PTK_PROF_POINT_FWD, st);
+      gru_stem_cat_kernel<<<grid, 256, 0, st>>>(d, t, 0);
+    }
+    ConvGArgs cru{d.Z, d.wruT, d.bru, nullptr, d.RU, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
+    if ((rc = launch_convg<7>(cru, st))) return rc;
+    {
+      ProfileScope ps(PTK_PROF_POINT_FWD, st);
+      gru_gate_kernel<<<grid, 256, 0, st>>>(d, t);
+    }
+    ConvGArgs cn{d.Z2, d.wnT, d.bnw, nullptr, d.Nb, d.B, d.H, d.W, 2 * GC, GC, 0};
+    if ((rc = launch_convg<7>(cn, st))) return rc;
+    {
+      ProfileScope ps(PTK_PROF_POINT_FWD, st);
+      gru_update_kernel<<<grid, 256, 0, st>>>(d, t);
+    }
+    PTK_LAUNCH_OK("gru step");
+  }
+  PTK_CUDA_OK(cudaMemcpyAsync(d.hT, d.h_at(d.T), d.S() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PTK_OK;
+}
+
+int run_gru_backward(const GruDev& d, cudaStream_t st) {
+  int rc;
+  const int taps = 49, grid = 148 * 8, P = d.H * d.W;
+  if ((rc = gru_prep(d, true, st))) return rc;
+  PTK_CUDA_OK(cudaMemcpyAsync(d.dh, d.dhT, d.S() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  for (int t = d.T; t >= 1; --t) {
+    const int first = (t == d.T);
+    {
+      ProfileScope ps(PTK_PROF_POINT_BWD, st, 2);
+      gru_bwd1_kernel<<<grid, 256, 0, st>>>(d, t, first);
+      gru_stem_cat_kernel<<<grid, 256, 0, st>>>(d, t, 1);            // Z = cat(X_t, h_{t-1}), Z2 = cat(X_t, r h)
+    }
+    WgradGArgs wn{d.Z2, d.Nb, d.slots_n, d.B, d.H, d.W, 2 * GC, GC, d.groups, !first};
+    if ((rc = launch_wgradg<7>(wn, st))) return rc;
+    ConvGArgs cn{d.Nb, d.wnD, nullptr, nullptr, d.dZ, d.B, d.H, d.W, GC, 2 * GC, 0};
+    if ((rc = launch_convg<7>(cn, st))) return rc;
+    {
+      ProfileScope ps(PTK_PROF_POINT_BWD, st);
+      gru_bwd2_kernel<<<grid, 256, 0, st>>>(d, t, first);
+    }
+    WgradGArgs wru{d.Z, d.RU, d.slots_ru, d.B, d.H, d.W, 2 * GC, 2 * GC, d.groups, !first};
+    if ((rc = launch_wgradg<7>(wru, st))) return rc;
+    ConvGArgs cru{d.RU, d.wruD, nullptr, nullptr, d.dZ, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
+    if ((rc = launch_convg<7>(cru, st))) return rc;
+    {
+      ProfileScope ps(PTK_PROF_POINT_BWD, st, 2);
+      gru_bwd3_kernel<<<grid, 256, 0, st>>>(d, t);
+      gru_stem_grad_kernel<<<GC, 512, 0, st>>>(d, t, first);
+    }
+    if (d.dx) gru_dx_kernel<<<grid, 256, 0, st>>>(d, t);
+    PTK_LAUNCH_OK("gru backward step");
+  }
+  // biases: sums over (t, b, y, x) of the gate pre-activation gradients; weights: fold the per-group slots
+  chan_sum_kernel<<<GC, 512, 0, st>>>(d.dNsum, d.bias_grad, d.B, GC, P);
+  chan_sum_kernel<<<2 * GC, 512, 0, st>>>(d.dRUsum, d.bias_grad + GC, d.B, 2 * GC, P);
+  fold_slots_kernel<<<(2 * GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_ru, d.groups, 2 * GC, 2 * GC, taps,
+                                                                         d.dparams + d.off_wr, d.off_wu - d.off_wr, GC);
+  fold_slots_kernel<<<(GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_n, d.groups, GC, 2 * GC, taps,
+                                                                     d.dparams + d.off_wn, 0, GC);
+  PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_bn, d.bias_grad, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_br, d.bias_grad + GC, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_bu, d.bias_grad + 2 * GC, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  gru_stem_out_kernel<<<1, GC, 0, st>>>(d);
+  PTK_LAUNCH_OK("gru fold");
+  return PTK_OK;
+}
+
+}  // namespace ptk

@@ -1,0 +1,41 @@
+// Device-side view of one ConvGRU problem instance (models/kys.py, `--model gru`).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "ptk_common.cuh"
+
+namespace ptk {
+
+constexpr int GC = 64;   // hidden / stem channels (utils/engine.py:149: dimensions * 2)
+
+struct GruDev {
+  int B, T, H, W, groups;
+  FrameView fv;                                   // x [B,3,T,H,W], arbitrary strides
+  // parameters (views into the flat vector): preproc.{w [64,3], b}, conv_reset / conv_update / conv_state_new {w [64,128,7,7], b}
+  const float *Wp, *bp, *wr, *br, *wu, *bu, *wn, *bnw;
+  long long off_wp, off_bp, off_wr, off_br, off_wu, off_bu, off_wn, off_bn;
+  // re-laid-out weight banks and the gathered [br|bu] bias (workspace)
+  float *wruT, *wnT, *wruD, *wnD, *bru;
+  // checkpoints (saved): h [T+1][B,64,P]; reset / update gates and the candidate [T][B,64,P]
+  float *hs, *rs, *us, *ns;
+  // scratch
+  float *Z, *Z2, *RU, *Nb, *dZ, *dh, *dhp, *dXb, *dNsum, *dRUsum;
+  float *slots_ru, *slots_n, *stem_acc, *bias_grad;
+  // I/O
+  float* hT;            // [B,64,H,W]
+  const float* dhT;
+  float* dparams;
+  float* dx;            // optional [B,3,T,H,W] contiguous
+
+  __host__ __device__ size_t S() const { return (size_t)B * GC * H * W; }
+  __host__ __device__ float* h_at(int t) const { return hs + (size_t)t * S(); }            // t = 0..T
+  __host__ __device__ float* r_at(int t) const { return rs + (size_t)(t - 1) * S(); }      // t = 1..T
+  __host__ __device__ float* u_at(int t) const { return us + (size_t)(t - 1) * S(); }
+  __host__ __device__ float* n_at(int t) const { return ns + (size_t)(t - 1) * S(); }
+};
+
+int run_gru_forward(const GruDev& d, cudaStream_t st);
+int run_gru_backward(const GruDev& d, cudaStream_t st);
+
+}  // namespace ptk

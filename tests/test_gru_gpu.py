@@ -1,0 +1,73 @@
+"""GPU parity of the ConvGRU path (models/kys.py, `--model gru`) through the C ABI, against fixtures produced by the
+reference and the fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import NOISE_MULT, REL_TOL, rel_err
+from tests.test_gru_oracle import load_gru_case, mirror_model
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["gru_small", "gru_b3"])
+def test_gru_logits_and_all_grads_vs_reference(name):
+    from oracle import gru_oracle as GO
+    case = load_gru_case(name)
+    m = mirror_model(case).cuda()
+    x, y = case["x"].float().cuda(), case["y"].float().cuda()
+    out, pen = m(x)
+    assert out.shape == (case["shape"][0], 1) and pen.shape == (1,)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+    assert rel_err(out, case["logits"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
+    # fp64 oracle gradients (the oracle itself is pinned to the reference on the CPU suite)
+    p = {k: v.detach().double().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    torch.nn.functional.binary_cross_entropy_with_logits(GO.forward(case["x"], p), case["y"]).backward()
+    bad = []
+    for n, prm in m.named_parameters():
+        if p[n].grad is None:
+            assert prm.grad is None, n          # the unused BatchNorm3d (models/kys.py:80)
+            continue
+        e = rel_err(prm.grad, p[n].grad)
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+    for n, g in case["grads"].items():          # and directly against the reference's own small tensors
+        assert rel_err(dict(m.named_parameters())[n].grad, g) < max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0)), n
+
+
+def test_gru_testmode_input_gradient_and_determinism():
+    case = load_gru_case("gru_small")
+    m = mirror_model(case).cuda()
+    x = case["x"].float().cuda().requires_grad_(True)
+    out, states, gates = m(x, testmode=True)
+    B, T, H, W = case["shape"]
+    assert states.shape == (B, T, 1, H, W) and gates.shape == (B, T, 64, H, W)
+    assert rel_err(states, torch.from_numpy(case["z"]["tm_states"])) < REL_TOL
+    assert abs(gates.double().sum().item() - float(case["z"]["tm_gates_sum"])) < 1e-5 * abs(float(case["z"]["tm_gates_sum"]))
+    assert rel_err(gates[:, -1, :4], torch.from_numpy(case["z"]["tm_gates_last"])) < REL_TOL
+    out.sum().backward()
+    g1 = x.grad.clone()
+    # fp64 oracle input gradient
+    from oracle import gru_oracle as GO
+    p = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    x64 = case["x"].clone().requires_grad_(True)
+    GO.forward(x64, p).sum().backward()
+    assert rel_err(g1, x64.grad) < 5e-4
+    x2 = case["x"].float().cuda().requires_grad_(True)
+    out2, _ = m(x2)
+    out2.sum().backward()
+    assert torch.equal(out, out2) and torch.equal(g1, x2.grad)      # bit-exact reruns
+
+
+def test_gru_errors_are_loud():
+    from pathtracker_models_b200 import _lib, kys
+    with pytest.raises(NotImplementedError):
+        kys.GRU(dimensions=32, timesteps=4, kernel_size=7)
+    m = kys.GRU(dimensions=64, timesteps=4, kernel_size=7)
+    with pytest.raises(_lib.PtkError):
+        m(torch.rand(1, 3, 2, 32, 32))                    # CPU tensor: no fallback
+    with pytest.raises(_lib.PtkError):
+        m.cuda()(torch.rand(1, 3, 2, 20, 32, device="cuda"))   # H % 16 != 0
