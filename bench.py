@@ -149,6 +149,8 @@ def run_b200(args):
         return run_convlstm(args, dev, world, rank)
     if args.model == "gru":
         return run_gru(args, dev, world, rank)
+    if args.eval:
+        return run_eval(args, dev, world, rank)
     ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
     model = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev)
     model.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
@@ -414,6 +416,36 @@ def run_gru(args, dev, world, rank):
                                    "note": "strict-fp32 CUDA-core path; cell-convolution FLOPs only"}}), flush=True)
 
 
+def run_eval(args, dev, world, rank):
+    """forward-only (inference) throughput: model.eval(), no_grad -- BASELINE configs[2] asks for it at 128 frames 64x64."""
+    import torch
+    from pathtracker_models_b200 import InT, _lib, ffhgru_hierarchy, synth_pathtracker
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    B, T, HW = args.batch, args.frames, args.size
+    torch.manual_seed(0)
+    ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
+    m = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev).eval()
+    m.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
+    x, _ = synth_pathtracker(B, T, HW, HW, n_distractors=DIST, speed=SPEED, device=dev)
+    with torch.no_grad():
+        for _ in range(warmup):
+            m(x)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            m(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"metric": "eval seq/s (fwd only)", "value": B * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                      "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "bf16" if args.conv_mode == "bf16" else "f32", "data": "synthetic",
+                      "config": {"workload": "%s %d frames %dx%d, batch %d, forward only" % (args.model, T, HW, HW, B),
+                                 "conv_mode": args.conv_mode}, "gpu_launches": _lib.launch_count() - l0}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -423,6 +455,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm", "gru"], help="non-headline configs (BASELINE configs[2..3])")
+    ap.add_argument("--eval", action="store_true", help="forward-only throughput (secondary line)")
     ap.add_argument("--frames", type=int, default=T)
     ap.add_argument("--size", type=int, default=HW)
     ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
