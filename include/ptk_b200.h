@@ -171,6 +171,8 @@ typedef struct PtkGruDims {
   int32_t B, T, H, W;
   int32_t C;           /* 64  */
   int32_t K;           /* 7   */
+  int32_t conv_mode;   /* PTK_CONV_FP32: generic CUDA-core convolutions; PTK_CONV_BF16X3 / PTK_CONV_BF16: the 128->128 and
+                        * 128->64 convolutions run as 32x32-channel blocks on the tcgen05 kernels of the InT path      */
 } PtkGruDims;
 PTK_API int ptk_gru_param_offsets(const PtkGruDims* d, int64_t* offsets);
 PTK_API size_t ptk_gru_saved_bytes(const PtkGruDims* d);

@@ -33,7 +33,7 @@ class PtkLstmDims(ctypes.Structure):
 
 
 class PtkGruDims(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "C", "K")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "C", "K", "conv_mode")]
 
 
 class PtkError(RuntimeError):

@@ -441,6 +441,10 @@ static int gru_check(const PtkGruDims* d, const char* who) {
     set_error("%s: unsupported shape B=%d T=%d H=%d W=%d (need B,T >= 1, H %% 16 == 0, W %% 32 == 0)", who, d->B, d->T, d->H, d->W);
     return PTK_EINVAL;
   }
+  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3 && d->conv_mode != PTK_CONV_BF16) {
+    set_error("%s: unknown conv_mode %d", who, d->conv_mode);
+    return PTK_EINVAL;
+  }
   return PTK_OK;
 }
 static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, size_t* saved_bytes) {
@@ -472,8 +476,17 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
   float* slots_n = cv.take<float>((size_t)groups * GC * 2 * GC * taps);
   float* stem_acc = cv.take<float>(4 * GC);
   float* bias_grad = cv.take<float>(3 * GC);
+  uint8_t *wtcF = nullptr, *wtcD = nullptr;
+  float* wacc_tc = nullptr;
+  const size_t wacc_pair = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
+  if (dm->conv_mode != PTK_CONV_FP32) {
+    wtcF = cv.take<uint8_t>((size_t)24 * 4 * C * C * TAPS);      // bf16 hi + lo per pair = 4 bytes per weight
+    wtcD = cv.take<uint8_t>((size_t)24 * 4 * C * C * TAPS);
+    wacc_tc = cv.take<float>(24 * wacc_pair);
+  }
   if (d) {
-    d->groups = groups;
+    d->groups = groups; d->conv_mode = dm->conv_mode;
+    d->wtcF = wtcF; d->wtcD = wtcD; d->wacc_tc = wacc_tc; d->wacc_pair = wacc_pair;
     d->hs = hs; d->rs = rs; d->us = us; d->ns = ns;
     d->wruT = wruT; d->wnT = wnT; d->wruD = wruD; d->wnD = wnD; d->bru = bru;
     d->Z = Z; d->Z2 = Z2; d->RU = RU; d->dZ = dZ; d->dRUsum = dRUsum; d->Nb = Nb; d->dh = dh; d->dhp = dhp; d->dXb = dXb;

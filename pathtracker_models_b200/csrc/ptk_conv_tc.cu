@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform => uniform branches / registers
   const int x0 = blockIdx.x * TC_TW, y0 = blockIdx.y * TC_TH, b = blockIdx.z;
   const int H = a.H, W = a.W;
+  const size_t in_bs = a.in_bs ? (size_t)a.in_bs : (size_t)C * H * W, out_bs = a.out_bs ? (size_t)a.out_bs : (size_t)C * H * W;
 
   TC_STAMP(0);
   const int dbg_cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
       pp[r] = -1; qq[r] = q;
       if (it < NIT && gy >= 0 && gy < H) {
         pp[r] = row * TC_WP + 3 + 4 * g;
-        const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
+        const float* src = a.in + (size_t)b * in_bs + ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
       }
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
       const int c = hc < 3 ? hc : (TC_TW + hc);          // padded columns 0..2 and 35..37
       const int gy = y0 + r - 3, gx = x0 + c - 3;
       if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
-      const float* src = a.in + ((size_t)(b * C + q * 8) * H + gy) * W + gx;
+      const float* src = a.in + (size_t)b * in_bs + ((size_t)(q * 8) * H + gy) * W + gx;
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
           dstp[1] = m2;
         }
       }
-      float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)(b * C + c) * H + y0 + row) * W + x0 + hx);
+      float4* dst = reinterpret_cast<float4*>(a.out + (size_t)b * out_bs + ((size_t)c * H + y0 + row) * W + x0 + hx);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float4 t = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
@@ -330,11 +331,11 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
 // weights fp32 [oc][ic][49] -> bf16 hi/lo in the staged layout (tc_woff): per kernel row, per tap group,
 // [Wh | Wl] blocks of [chunk = k/8][row = (tap in group, n)][k%8].
 //   forward: n = oc, k = ic, tap as is;  dgrad (conv_transpose): n = ic, k = oc, tap -> 48 - tap.
-__global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat16* wf, __nv_bfloat16* wd) {
+__global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat16* wf, __nv_bfloat16* wd, int oc_stride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * C * TAPS) return;
   const int oc = i / (C * TAPS), ic = (i / TAPS) % C, tap = i % TAPS, ky = tap / KS, kx = tap - ky * KS;
-  const float v = w[i];
+  const float v = w[(size_t)oc * oc_stride + ic * TAPS + tap];
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
   if (wf) {
@@ -370,9 +371,9 @@ int read_tc_debug(long long* out) {
   return PTK_OK;
 }
 
-int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st) {
+int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride) {
   const int n = C * C * TAPS;
-  prep_weights_tc_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
+  prep_weights_tc_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, oc_stride ? oc_stride : C * TAPS);
   PTK_LAUNCH_OK("prep_weights_tc_kernel");
   return PTK_OK;
 }

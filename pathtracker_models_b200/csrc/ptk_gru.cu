@@ -10,6 +10,7 @@
 // Convolutions: the generic direct kernels of ptk_convg.cuh (shared with the ConvLSTM path).
 #include "ptk_convg.cuh"
 #include "ptk_gru.h"
+#include "ptk_kernels.h"
 
 namespace ptk {
 
@@ -37,23 +38,26 @@ __global__ void gru_stem_cat_kernel(GruDev d, int t, int with_rh) {
     if (with_rh) d.Z2[z + (size_t)GC * P] = d.r_at(t)[e] * h;       // backward: rebuild cat(X_t, r h) from the saved gate
   }
 }
-__global__ void gru_gate_kernel(GruDev d, int t) {
+__global__ void gru_gate_kernel(GruDev d, int t, int add_bias) {
   const int P = d.H * d.W;
   const float* hp = d.h_at(t - 1);
   GRU_FOR_EACH(e, d.S()) {
     const int pix = (int)(e % P), c = (int)((e / P) % GC), b = (int)(e / ((size_t)P * GC));
     const size_t z = ((size_t)b * 2 * GC + c) * P + pix;
-    const float r = sigmoid_precise(d.RU[z]), u = sigmoid_precise(d.RU[z + (size_t)GC * P]);
+    const float br = add_bias ? __ldg(d.br + c) : 0.f, bu = add_bias ? __ldg(d.bu + c) : 0.f;
+    const float r = sigmoid_precise(d.RU[z] + br), u = sigmoid_precise(d.RU[z + (size_t)GC * P] + bu);
     d.r_at(t)[e] = r;
     d.u_at(t)[e] = u;
     d.Z2[z + (size_t)GC * P] = r * hp[e];
   }
 }
-__global__ void gru_update_kernel(GruDev d, int t) {
+__global__ void gru_update_kernel(GruDev d, int t, int add_bias) {
+  const int P = d.H * d.W;
   const float* hp = d.h_at(t - 1);
   float* ho = d.h_at(t);
   GRU_FOR_EACH(e, d.S()) {
-    const float n = tanh_precise(d.Nb[e]), u = d.u_at(t)[e];
+    const float bn = add_bias ? __ldg(d.bnw + (int)((e / P) % GC)) : 0.f;
+    const float n = tanh_precise(d.Nb[e] + bn), u = d.u_at(t)[e];
     d.n_at(t)[e] = n;
     ho[e] = (1.0f - u) * hp[e] + u * n;
   }
@@ -142,6 +146,68 @@ __global__ void gru_stem_out_kernel(GruDev d) {      // stem_acc [64][4] -> dpar
   for (int i = 0; i < 3; ++i) d.dparams[d.off_wp + c * 3 + i] = d.stem_acc[c * 4 + 1 + i];
 }
 
+// ---- tensor-core modes: the wide convolutions as 32 x 32-channel blocks on the tcgen05 kernels of the InT path ----
+// [reset|update]: out blocks j = 0..3 (j < 2 reset rows, j >= 2 update rows), in blocks i = 0..3, pair = j*4 + i;
+// candidate: out blocks j = 0..1, pair = 16 + j*4 + i.  Each block convolution addresses its 32 channels inside the
+// wider [B,Cw,H,W] tensors through the per-sample strides of ConvArgs / WgradArgs; biases are added by the gate kernels.
+constexpr size_t GRU_WTC_PAIR = (size_t)4 * C * C * TAPS;      // bytes: bf16 hi + lo
+static const float* gru_wblock(const GruDev& d, int pair) {
+  const int j = (pair & 15) >> 2, i = pair & 3;
+  const float* w = pair >= 16 ? d.wn : (j < 2 ? d.wr : d.wu);
+  const int jj = pair >= 16 ? j : (j & 1);
+  return w + (size_t)(jj * 32) * (2 * GC * TAPS) + (size_t)i * 32 * TAPS;
+}
+static int gru_prep_tc(const GruDev& d, cudaStream_t st) {
+  for (int pair = 0; pair < 24; ++pair) {
+    int rc = launch_prep_weights_tc(gru_wblock(d, pair), d.wtcF + pair * GRU_WTC_PAIR, d.wtcD + pair * GRU_WTC_PAIR, st,
+                                    2 * GC * TAPS);
+    if (rc) return rc;
+  }
+  return PTK_OK;
+}
+// out[B, nOut*32, .] = conv(in[B, nIn*32, .]) (transpose = 0) or its data gradient (transpose = 1: in has nOut blocks)
+static int gru_conv_tc(const GruDev& d, const float* in, float* out, int pair0, int nOut, int nIn, int transpose, cudaStream_t st) {
+  const size_t P = (size_t)d.H * d.W;
+  const int nSrc = transpose ? nOut : nIn, nDst = transpose ? nIn : nOut;
+  for (int o = 0; o < nDst; ++o)
+    for (int s = 0; s < nSrc; ++s) {
+      const int pair = pair0 + (transpose ? s * 4 + o : o * 4 + s);
+      ConvArgs a{in + (size_t)s * 32 * P, reinterpret_cast<const float*>((transpose ? d.wtcD : d.wtcF) + pair * GRU_WTC_PAIR),
+                 out + (size_t)o * 32 * P, d.B, d.H, d.W, s > 0, nullptr, nullptr, nullptr, d.conv_mode, 0,
+                 (long long)(nSrc * 32 * P), (long long)(nDst * 32 * P)};
+      int rc;
+      { ProfileScope ps(transpose ? PTK_PROF_CONV_DGRAD : PTK_PROF_CONV_FWD, st); rc = launch_conv7(a, st); }
+      if (rc) return rc;
+    }
+  return PTK_OK;
+}
+static int gru_wgrad_tc(const GruDev& d, const float* in, const float* dy, int pair0, int nOut, int first, cudaStream_t st) {
+  const size_t P = (size_t)d.H * d.W;
+  for (int j = 0; j < nOut; ++j)
+    for (int i = 0; i < 4; ++i) {
+      WgradArgs w{in + (size_t)i * 32 * P, dy + (size_t)j * 32 * P, d.wacc_tc + (size_t)(pair0 + j * 4 + i) * d.wacc_pair,
+                  d.B, d.H, d.W, first, d.conv_mode, (long long)(4 * 32 * P), (long long)(nOut * 32 * P)};
+      int rc;
+      { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7_tc(w, st); }
+      if (rc) return rc;
+    }
+  return PTK_OK;
+}
+// fold the per-CTA slots of all 24 pairs (fp64, fixed order) into conv_reset / conv_update / conv_state_new .weight
+__global__ void gru_fold_tc_kernel(GruDev d, int nCta) {
+  const size_t n = (size_t)3 * GC * 2 * GC * TAPS;
+  GRU_FOR_EACH(e, n) {
+    const int tap = (int)(e % TAPS), ic = (int)((e / TAPS) % (2 * GC)), oc = (int)((e / ((size_t)TAPS * 2 * GC)) % GC);
+    const int which = (int)(e / ((size_t)TAPS * 2 * GC * GC));              // 0 reset, 1 update, 2 candidate
+    const int j = (which == 1 ? 2 : 0) + (oc >> 5), pair = (which == 2 ? 16 : 0) + j * 4 + (ic >> 5);
+    const float* wa = d.wacc_tc + (size_t)pair * d.wacc_pair + (size_t)tap * C * C + (oc & 31) * C + (ic & 31);
+    double s = 0;
+    for (int g = 0; g < nCta; ++g) s += (double)wa[(size_t)g * TAPS * C * C];
+    const long long off = which == 0 ? d.off_wr : (which == 1 ? d.off_wu : d.off_wn);
+    d.dparams[off + ((size_t)oc * 2 * GC + ic) * TAPS + tap] = (float)s;
+  }
+}
+
 static int gru_prep(const GruDev& d, bool transposed, cudaStream_t st) {
   const int taps = 49;
   int rc;
@@ -160,7 +226,8 @@ static int gru_prep(const GruDev& d, bool transposed, cudaStream_t st) {
 
 int run_gru_forward(const GruDev& d, cudaStream_t st) {
   int rc;
-  if ((rc = gru_prep(d, false, st))) return rc;
+  const bool tc = d.conv_mode != PTK_CONV_FP32;
+  if ((rc = tc ? gru_prep_tc(d, st) : gru_prep(d, false, st))) return rc;
   PTK_CUDA_OK(cudaMemsetAsync(d.h_at(0), 0, d.S() * sizeof(float), st));
   const int grid = 148 * 8;
   for (int t = 1; t <= d.T; ++t) {
@@ -168,17 +235,25 @@ int run_gru_forward(const GruDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_FWD, st);
       gru_stem_cat_kernel<<<grid, 256, 0, st>>>(d, t, 0);
     }
-    ConvGArgs cru{d.Z, d.wruT, d.bru, nullptr, d.RU, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
-    if ((rc = launch_convg<7>(cru, st))) return rc;
-    {
-      ProfileScope ps(PTK_PROF_POINT_FWD, st);
-      gru_gate_kernel<<<grid, 256, 0, st>>>(d, t);
+    if (tc) {
+      if ((rc = gru_conv_tc(d, d.Z, d.RU, 0, 4, 4, 0, st))) return rc;
+    } else {
+      ConvGArgs cru{d.Z, d.wruT, d.bru, nullptr, d.RU, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
+      if ((rc = launch_convg<7>(cru, st))) return rc;
     }
-    ConvGArgs cn{d.Z2, d.wnT, d.bnw, nullptr, d.Nb, d.B, d.H, d.W, 2 * GC, GC, 0};
-    if ((rc = launch_convg<7>(cn, st))) return rc;
     {
       ProfileScope ps(PTK_PROF_POINT_FWD, st);
-      gru_update_kernel<<<grid, 256, 0, st>>>(d, t);
+      gru_gate_kernel<<<grid, 256, 0, st>>>(d, t, tc);
+    }
+    if (tc) {
+      if ((rc = gru_conv_tc(d, d.Z2, d.Nb, 16, 2, 4, 0, st))) return rc;
+    } else {
+      ConvGArgs cn{d.Z2, d.wnT, d.bnw, nullptr, d.Nb, d.B, d.H, d.W, 2 * GC, GC, 0};
+      if ((rc = launch_convg<7>(cn, st))) return rc;
+    }
+    {
+      ProfileScope ps(PTK_PROF_POINT_FWD, st);
+      gru_update_kernel<<<grid, 256, 0, st>>>(d, t, tc);
     }
     PTK_LAUNCH_OK("gru step");
   }
@@ -189,7 +264,8 @@ int run_gru_forward(const GruDev& d, cudaStream_t st) {
 int run_gru_backward(const GruDev& d, cudaStream_t st) {
   int rc;
   const int taps = 49, grid = 148 * 8, P = d.H * d.W;
-  if ((rc = gru_prep(d, true, st))) return rc;
+  const bool tc = d.conv_mode != PTK_CONV_FP32;
+  if ((rc = tc ? gru_prep_tc(d, st) : gru_prep(d, true, st))) return rc;
   PTK_CUDA_OK(cudaMemcpyAsync(d.dh, d.dhT, d.S() * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int t = d.T; t >= 1; --t) {
     const int first = (t == d.T);
@@ -198,18 +274,28 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
       gru_bwd1_kernel<<<grid, 256, 0, st>>>(d, t, first);
       gru_stem_cat_kernel<<<grid, 256, 0, st>>>(d, t, 1);            // Z = cat(X_t, h_{t-1}), Z2 = cat(X_t, r h)
     }
-    WgradGArgs wn{d.Z2, d.Nb, d.slots_n, d.B, d.H, d.W, 2 * GC, GC, d.groups, !first};
-    if ((rc = launch_wgradg<7>(wn, st))) return rc;
-    ConvGArgs cn{d.Nb, d.wnD, nullptr, nullptr, d.dZ, d.B, d.H, d.W, GC, 2 * GC, 0};
-    if ((rc = launch_convg<7>(cn, st))) return rc;
+    if (tc) {
+      if ((rc = gru_wgrad_tc(d, d.Z2, d.Nb, 16, 2, first, st))) return rc;
+      if ((rc = gru_conv_tc(d, d.Nb, d.dZ, 16, 2, 4, 1, st))) return rc;
+    } else {
+      WgradGArgs wn{d.Z2, d.Nb, d.slots_n, d.B, d.H, d.W, 2 * GC, GC, d.groups, !first};
+      if ((rc = launch_wgradg<7>(wn, st))) return rc;
+      ConvGArgs cn{d.Nb, d.wnD, nullptr, nullptr, d.dZ, d.B, d.H, d.W, GC, 2 * GC, 0};
+      if ((rc = launch_convg<7>(cn, st))) return rc;
+    }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       gru_bwd2_kernel<<<grid, 256, 0, st>>>(d, t, first);
     }
-    WgradGArgs wru{d.Z, d.RU, d.slots_ru, d.B, d.H, d.W, 2 * GC, 2 * GC, d.groups, !first};
-    if ((rc = launch_wgradg<7>(wru, st))) return rc;
-    ConvGArgs cru{d.RU, d.wruD, nullptr, nullptr, d.dZ, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
-    if ((rc = launch_convg<7>(cru, st))) return rc;
+    if (tc) {
+      if ((rc = gru_wgrad_tc(d, d.Z, d.RU, 0, 4, first, st))) return rc;
+      if ((rc = gru_conv_tc(d, d.RU, d.dZ, 0, 4, 4, 1, st))) return rc;
+    } else {
+      WgradGArgs wru{d.Z, d.RU, d.slots_ru, d.B, d.H, d.W, 2 * GC, 2 * GC, d.groups, !first};
+      if ((rc = launch_wgradg<7>(wru, st))) return rc;
+      ConvGArgs cru{d.RU, d.wruD, nullptr, nullptr, d.dZ, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
+      if ((rc = launch_convg<7>(cru, st))) return rc;
+    }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st, 2);
       gru_bwd3_kernel<<<grid, 256, 0, st>>>(d, t);
@@ -221,10 +307,14 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
   // biases: sums over (t, b, y, x) of the gate pre-activation gradients; weights: fold the per-group slots
   chan_sum_kernel<<<GC, 512, 0, st>>>(d.dNsum, d.bias_grad, d.B, GC, P);
   chan_sum_kernel<<<2 * GC, 512, 0, st>>>(d.dRUsum, d.bias_grad + GC, d.B, 2 * GC, P);
-  fold_slots_kernel<<<(2 * GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_ru, d.groups, 2 * GC, 2 * GC, taps,
-                                                                         d.dparams + d.off_wr, d.off_wu - d.off_wr, GC);
-  fold_slots_kernel<<<(GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_n, d.groups, GC, 2 * GC, taps,
-                                                                     d.dparams + d.off_wn, 0, GC);
+  if (tc) {
+    gru_fold_tc_kernel<<<148 * 8, 256, 0, st>>>(d, conv_num_ctas(d.B, d.H, d.W));
+  } else {
+    fold_slots_kernel<<<(2 * GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_ru, d.groups, 2 * GC, 2 * GC, taps,
+                                                                           d.dparams + d.off_wr, d.off_wu - d.off_wr, GC);
+    fold_slots_kernel<<<(GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_n, d.groups, GC, 2 * GC, taps,
+                                                                       d.dparams + d.off_wn, 0, GC);
+  }
   PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_bn, d.bias_grad, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_br, d.bias_grad + GC, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_bu, d.bias_grad + 2 * GC, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -10,7 +10,7 @@ namespace ptk {
 constexpr int GC = 64;   // hidden / stem channels (utils/engine.py:149: dimensions * 2)
 
 struct GruDev {
-  int B, T, H, W, groups;
+  int B, T, H, W, groups, conv_mode;
   FrameView fv;                                   // x [B,3,T,H,W], arbitrary strides
   // parameters (views into the flat vector): preproc.{w [64,3], b}, conv_reset / conv_update / conv_state_new {w [64,128,7,7], b}
   const float *Wp, *bp, *wr, *br, *wu, *bu, *wn, *bnw;
@@ -22,6 +22,11 @@ struct GruDev {
   // scratch
   float *Z, *Z2, *RU, *Nb, *dZ, *dh, *dhp, *dXb, *dNsum, *dRUsum;
   float *slots_ru, *slots_n, *stem_acc, *bias_grad;
+  // tensor-core modes: 24 (out-block, in-block) pairs of 32x32 channels -- 16 for [reset|update] (pair = j*4 + i), 8 for
+  // the candidate (16 + j*4 + i): bf16 hi/lo tap streams (forward / transposed) and per-CTA weight-gradient slots
+  uint8_t *wtcF, *wtcD;
+  float* wacc_tc;
+  size_t wacc_pair;      // floats per pair
   // I/O
   float* hT;            // [B,64,H,W]
   const float* dhT;

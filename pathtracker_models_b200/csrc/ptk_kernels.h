@@ -16,6 +16,8 @@ struct ConvArgs {
   float* stats_out;    // [2][32] mean, rstd
   int mode;            // PTK_CONV_FP32: wT is fp32 [ic][tap][oc]; PTK_CONV_BF16X3: wT is the bf16 hi/lo tap stream
   int pdl = 0;         // launched inside the time loop: programmatic dependent launch allowed (ptk_common.cuh)
+  long long in_bs = 0, out_bs = 0;   // tensor-core path: elements between samples (0 = 32*H*W); lets a 32-channel block
+                                     // of a wider [B,Cw,H,W] tensor be convolved in place (ConvGRU, ptk_gru.cu)
 };
 
 struct WgradArgs {
@@ -25,13 +27,14 @@ struct WgradArgs {
   int B, H, W;
   int first;           // overwrite instead of accumulate
   int mode;            // PTK_CONV_BF16: single pass (hi parts only)
+  long long in_bs = 0, dy_bs = 0;    // elements between samples (0 = 32*H*W), as in ConvArgs
 };
 
 int conv_num_ctas(int B, int H, int W);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st);
-int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st);
+int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride = 0);   // 0 = 32*49 (dense)
 int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st);   // wacc: [nCTA][49][32 oc][32 ic]
 size_t wgrad_tc_acc_floats(int B, int H, int W);
 int read_tc_debug(long long* out);

@@ -46,7 +46,7 @@ __host__ __device__ constexpr uint32_t wt_idesc() {
 // rows [r0, r0+nrows) of the tile map to image rows gy0 + r; columns: 32 interior (+3 halo each side when
 // `halo` and the neighbour exists).  `col0` = padded column of image column x0.
 __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_bytes, const float* __restrict__ src,
-                                         int b, int gy0, int nrows, int x0, int H, int W, int col0, bool halo, int pitch) {
+                                         size_t bs, int b, int gy0, int nrows, int x0, int H, int W, int col0, bool halo, int pitch) {
   const int tid = threadIdx.x;
   // two items per round: 16 LDG.128 in flight per thread before the first conversion (L2-latency bound)
   const int nit = 4 * nrows * (WT_TW / 4);
@@ -61,7 +61,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
       pp[r] = -1; qq[r] = q;
       if (it < nit && gy >= 0 && gy < H) {
         pp[r] = row * pitch + col0 + 4 * g;
-        const float* p0 = src + ((size_t)(b * C + q * 8) * H + gy) * W + x0 + 4 * g;
+        const float* p0 = src + (size_t)b * bs + ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(p0 + (size_t)e * H * W);
       }
@@ -92,7 +92,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
       const int c = hc < 3 ? hc : (WT_TW + hc);
       const int gy = gy0 + r, gx = x0 + c - 3;
       if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
-      const float* p0 = src + ((size_t)(b * C + q * 8) * H + gy) * W + gx;
+      const float* p0 = src + (size_t)b * bs + ((size_t)(q * 8) * H + gy) * W + gx;
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform => uniform branches / registers
   const int x0 = blockIdx.x * WT_TW, y0 = blockIdx.y * WT_TH, b = blockIdx.z;
   const int H = a.H, W = a.W;
+  const size_t in_bs = a.in_bs ? (size_t)a.in_bs : (size_t)C * H * W, dy_bs = a.dy_bs ? (size_t)a.dy_bs : (size_t)C * H * W;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 
   WT_STAMP(0, 0);
@@ -143,16 +144,16 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   // the In operand is usually a forward checkpoint (I_{t+1}): pull the tile's lines HBM -> L2 before the wait
   for (int it = tid; it < C * WT_ROWS; it += 256) {
     const int ch = it / WT_ROWS, gy = y0 - 3 + (it - ch * WT_ROWS);
-    if (gy >= 0 && gy < H) prefetch_l2(a.in + ((size_t)(b * C + ch) * H + gy) * W + x0);
+    if (gy >= 0 && gy < H) prefetch_l2(a.in + (size_t)b * in_bs + ((size_t)ch * H + gy) * W + x0);
   }
   __syncthreads();
   pdl_wait();                 // the prologue above touched only shared memory / TMEM (ptk_common.cuh, PDL)
   pdl_launch_dependents();
   WT_STAMP(1, 0);
   // dY tile: 16 rows, interior columns only (pad columns stay zero => contribute nothing)
-  wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, b, y0, WT_TH, x0, H, W, 0, false, WT_TW);
+  wt_stage(sDY, sDY + 4 * WT_DY_PLANE, WT_DY_PLANE, a.dy, dy_bs, b, y0, WT_TH, x0, H, W, 0, false, WT_TW);
   // In tile: 22 rows with the 3-pixel halo, interior at padded column 3
-  wt_stage(sIN, sIN + 4 * WT_IN_PLANE, WT_IN_PLANE, a.in, b, y0 - 3, WT_ROWS, x0, H, W, 3, true, WT_WP);
+  wt_stage(sIN, sIN + 4 * WT_IN_PLANE, WT_IN_PLANE, a.in, in_bs, b, y0 - 3, WT_ROWS, x0, H, W, 3, true, WT_WP);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

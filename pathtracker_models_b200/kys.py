@@ -105,6 +105,8 @@ class GRU(nn.Module):
         torch.nn.init.zeros_(self.target_conv.bias)
         self.readout_dense = nn.Linear(1, 1)
         self.nl = F.softplus
+        # cell convolutions: 3-pass split-bf16 tcgen05 blocks (default) or strict-fp32 CUDA cores; same parity gate
+        self.conv_mode = _lib.PTK_CONV_BF16X3
 
     def flat_parameters(self):
         """the 8 tensors of the stem and the cell, in the C ABI's order (by attribute: works on DataParallel replicas)."""
@@ -120,7 +122,7 @@ class GRU(nn.Module):
             raise ValueError(f"expected x of shape [B,3,T,H,W], got {tuple(x.shape)}")
         x = x.float()
         B, _, T, H, W = x.shape
-        dims = _lib.PtkGruDims(B, T, H, W, self.hgru_size, self.unit1.kernel_size)
+        dims = _lib.PtkGruDims(B, T, H, W, self.hgru_size, self.unit1.kernel_size, int(self.conv_mode))
         hT, hs, rs = _GruFunction.apply(x, self.flat_parameters(), dims, bool(testmode))
         # readout (models/kys.py:127-133), kept in PyTorch: negligible work, outside the time loop
         output = torch.cat([self.readout_conv(hT), x[:, 2, 0][:, None]], 1)

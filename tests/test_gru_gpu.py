@@ -10,11 +10,15 @@ from tests.test_gru_oracle import load_gru_case, mirror_model
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("name", ["gru_small", "gru_b3"])
-def test_gru_logits_and_all_grads_vs_reference(name):
+def test_gru_logits_and_all_grads_vs_reference(name, conv_mode):
+    """both precisions: 32x32-channel blocks on the tcgen05 kernels (default) and the generic strict-fp32 kernels"""
     from oracle import gru_oracle as GO
+    from pathtracker_models_b200 import _lib
     case = load_gru_case(name)
     m = mirror_model(case).cuda()
+    m.conv_mode = _lib.PTK_CONV_BF16X3 if conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
     x, y = case["x"].float().cuda(), case["y"].float().cuda()
     out, pen = m(x)
     assert out.shape == (case["shape"][0], 1) and pen.shape == (1,)
