@@ -173,7 +173,7 @@ static int gru_conv_tc(const GruDev& d, const float* in, float* out, int pair0, 
     for (int s = 0; s < nSrc; ++s) {
       const int pair = pair0 + (transpose ? s * 4 + o : o * 4 + s);
       ConvArgs a{in + (size_t)s * 32 * P, reinterpret_cast<const float*>((transpose ? d.wtcD : d.wtcF) + pair * GRU_WTC_PAIR),
-                 out + (size_t)o * 32 * P, d.B, d.H, d.W, s > 0, nullptr, nullptr, nullptr, d.conv_mode, 0,
+                 out + (size_t)o * 32 * P, d.B, d.H, d.W, s > 0, nullptr, nullptr, nullptr, d.conv_mode, 1 /* PDL chain */,
                  (long long)(nSrc * 32 * P), (long long)(nDst * 32 * P)};
       int rc;
       { ProfileScope ps(transpose ? PTK_PROF_CONV_DGRAD : PTK_PROF_CONV_FWD, st); rc = launch_conv7(a, st); }
