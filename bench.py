@@ -33,7 +33,7 @@ CONV_FLOP_PER_LAUNCH = 2 * B_PER_GPU * HW * HW * C * C * K * K  # one 7x7 conv o
 FP32_FFMA_PEAK_TFLOPS = 74.4   # nominal 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the headline shape, from the
 # committed `ncu --set full` captures (profiles/r1e_tc_kernels_full.txt, profiles/r1a_conv7_ffma_full.txt)
-NCU_TRAFFIC_BYTES = {"bf16x3": 8.657e6, "fp32": 8.623e6}
+NCU_TRAFFIC_BYTES = {"bf16x3": 8.650e6, "fp32": 8.623e6}   # dram read + write per conv launch, profiles/r1i_kernels_full.txt
 
 
 def load_peaks():
@@ -309,7 +309,7 @@ def run_b200(args):
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tensor_peak) if achieved else None,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.conv_mode) if (args.model, T, HW, B) == ("int", 64, 32, 64) else None,
-                         "traffic_unit": "bytes/launch (ncu --set full, profiles/r1e_tc_kernels_full.txt); algorithmic: 16.8 MB "
+                         "traffic_unit": "bytes/launch (ncu --set full, profiles/r1i_kernels_full.txt); algorithmic: 16.8 MB "
                                          "(8.4 MB in + 8.4 MB out, the output stays in L2)",
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % src,
                          "launch_ms": conv_avg_ms, "launches_timed": conv_n, "flop_per_launch": conv_flop,
