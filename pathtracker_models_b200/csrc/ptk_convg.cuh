@@ -140,8 +140,11 @@ template <int KS>
 __global__ void __launch_bounds__(32 * KS, 2) wgradg_kernel(WgradGArgs a) {
   using G = ConvG<KS>;
   extern __shared__ __align__(16) float smem[];
-  float* sDY = smem;                          // [32][16*32]
-  float* sIn = smem + 32 * GTH * GTW;         // [ROWS][PITCH]
+  // per-oc pitch 16*32 + 4 floats: the 32 lanes of a warp read 32 different oc rows at the same pixel, and an
+  // unpadded 2 KB pitch put all of them in one bank group (32-way conflict on the two LDS.128 per inner iteration)
+  constexpr int DYP = GTH * GTW + 4;
+  float* sDY = smem;                          // [32][DYP]
+  float* sIn = smem + 32 * DYP;               // [ROWS][PITCH]
   const int tid = threadIdx.x, NT = 32 * KS;
   const int oc_l = tid % 32, ky = tid / 32;
   const int ocBlocks = (a.Cout + 31) / 32;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(32 * KS, 2) wgradg_kernel(WgradGArgs a) {
     for (int i = tid; i < 32 * GTH * (GTW / 4); i += NT) {
       const int o = i / (GTH * GTW / 4), r = (i / (GTW / 4)) % GTH, q = i % (GTW / 4);
       const int oc = ob * 32 + o;
-      cp_async16_zfill(sDY + (o * GTH + r) * GTW + 4 * q,
+      cp_async16_zfill(sDY + o * DYP + r * GTW + 4 * q,
                        a.dy + ((size_t)(b * a.Cout + (oc < a.Cout ? oc : 0)) * H + y0 + r) * W + x0 + 4 * q, oc < a.Cout);
     }
     for (int i = tid; i < G::ROWS * (GTW + 2 * G::PAD); i += NT) {
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(32 * KS, 2) wgradg_kernel(WgradGArgs a) {
       for (int xc = 0; xc < GTW / 8; ++xc) {
         float dy[8], in[G::NLD];
         {
-          const float4* p = reinterpret_cast<const float4*>(sDY + (oc_l * GTH + y) * GTW + xc * 8);
+          const float4* p = reinterpret_cast<const float4*>(sDY + oc_l * DYP + y * GTW + xc * 8);
           const float4 v0 = p[0], v1 = p[1];
           dy[0] = v0.x; dy[1] = v0.y; dy[2] = v0.z; dy[3] = v0.w; dy[4] = v1.x; dy[5] = v1.y; dy[6] = v1.z; dy[7] = v1.w;
         }
@@ -257,7 +260,7 @@ static int launch_convg(const ConvGArgs& a, cudaStream_t st) {
 template <int KS>
 static int launch_wgradg(const WgradGArgs& a, cudaStream_t st) {
   using G = ConvG<KS>;
-  const size_t sm = (size_t)(32 * GTH * GTW + G::ROWS * G::PITCH) * sizeof(float);
+  const size_t sm = (size_t)(32 * (GTH * GTW + 4) + G::ROWS * G::PITCH) * sizeof(float);
   PTK_CUDA_OK(cudaFuncSetAttribute(wgradg_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid(((a.Cout + 31) / 32) * a.Cin, a.groups);
   ProfileScope ps(PTK_PROF_WGRAD, st);
