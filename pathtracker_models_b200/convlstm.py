@@ -139,7 +139,8 @@ class ConvLSTM(nn.Module):
             raise ValueError(f"expected x of shape [B,1,H,W], got {tuple(x.shape)}")
         dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size)
         rbp = self.grad_method == 'rbp'
-        output, pen, states = _ConvLSTMFunction.apply(x.float(), self.flat_parameters(), dims, bool(self.training),
+        from .parallel import flat_gradient_hook
+        output, pen, states = _ConvLSTMFunction.apply(x.float(), flat_gradient_hook(self, self.flat_parameters()), dims, bool(self.training),
                                                       int(self.num_iter) if rbp else None, bool(rbp and testmode))
         loss = criterion(output, target)                                # convlstm.py:148
         if testmode:                                                     # the bptt branch never fills `states`

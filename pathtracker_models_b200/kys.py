@@ -115,6 +115,10 @@ class GRU(nn.Module):
               u.conv_update.bias, u.conv_state_new.weight, u.conv_state_new.bias]
         return torch.cat([t.reshape(-1) for t in ts])
 
+    def dp_extra_parameters(self):
+        """parameters outside the flat vector (the PyTorch-side head): averaged by their own hooks under data parallelism"""
+        return [p for m in (self.readout_conv, self.target_conv, self.readout_dense) for p in m.parameters()]
+
     def forward(self, x, testmode=False):
         if not x.is_cuda:
             raise _lib.PtkError("pathtracker_models_b200 runs on CUDA (sm_100a) only; there is no CPU path")
@@ -123,7 +127,8 @@ class GRU(nn.Module):
         x = x.float()
         B, _, T, H, W = x.shape
         dims = _lib.PtkGruDims(B, T, H, W, self.hgru_size, self.unit1.kernel_size, int(self.conv_mode))
-        hT, hs, rs = _GruFunction.apply(x, self.flat_parameters(), dims, bool(testmode))
+        from .parallel import flat_gradient_hook
+        hT, hs, rs = _GruFunction.apply(x, flat_gradient_hook(self, self.flat_parameters()), dims, bool(testmode))
         # readout (models/kys.py:127-133), kept in PyTorch: negligible work, outside the time loop
         output = torch.cat([self.readout_conv(hT), x[:, 2, 0][:, None]], 1)
         output = self.target_conv(output)

@@ -24,7 +24,7 @@ def average_flat_gradient_(flat_grad, group=None):
 
 
 def attach_data_parallel(model, group=None):
-    """make `model` (InT / FFhGRU mirror) average its flat gradient across `group` during backward.
+    """make `model` (any mirror module of this package) average its flat gradient across `group` during backward.
 
     The hook fires on the flat parameter vector right after the reverse-time kernels have been
     enqueued, i.e. before autograd scatters the bucket back into the 30 parameter tensors, so the
@@ -33,7 +33,18 @@ def attach_data_parallel(model, group=None):
         raise RuntimeError("torch.distributed is not initialised")
     model._dp_group = group
     model._dp_enabled = True
+    # parameters that do not travel in the flat vector (the PyTorch-side readout head of kys.GRU) get their own hook
+    for p in getattr(model, "dp_extra_parameters", lambda: [])():
+        p.register_hook(lambda g, _grp=group: average_flat_gradient_(g.contiguous(), _grp))
     return model
+
+
+def flat_gradient_hook(model, flat):
+    """called by the mirror modules' forward on their flat parameter vector (ConvLSTM, kys.GRU; InT has it inline)"""
+    if getattr(model, "_dp_enabled", False) and flat.requires_grad:
+        group = model._dp_group
+        flat.register_hook(lambda g: average_flat_gradient_(g.contiguous(), group))
+    return flat
 
 
 def broadcast_parameters(model, src=0, group=None):

@@ -75,3 +75,30 @@ def test_gru_errors_are_loud():
         m(torch.rand(1, 3, 2, 32, 32))                    # CPU tensor: no fallback
     with pytest.raises(_lib.PtkError):
         m.cuda()(torch.rand(1, 3, 2, 20, 32, device="cuda"))   # H % 16 != 0
+
+
+def test_data_parallel_hooks_on_gru_and_convlstm_world1(tmp_path):
+    """attach_data_parallel on the other families: with a 1-rank group the averaged gradients must equal the plain ones"""
+    import torch.distributed as dist
+    from pathtracker_models_b200.parallel import attach_data_parallel, broadcast_parameters
+    case = load_gru_case("gru_small")
+    m = mirror_model(case).cuda()
+    x, y = case["x"].float().cuda(), case["y"].float().cuda()
+    out, _ = m(x)
+    torch.nn.functional.binary_cross_entropy_with_logits(out, y).backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="file://" + str(tmp_path / "pg"), rank=0, world_size=1)
+    try:
+        broadcast_parameters(m)
+        attach_data_parallel(m)
+        out2, _ = m(x)
+        torch.nn.functional.binary_cross_entropy_with_logits(out2, y).backward()
+        for n, p in m.named_parameters():
+            if p.grad is not None:
+                assert torch.equal(p.grad, ref[n]), n
+    finally:
+        if created:
+            dist.destroy_process_group()
