@@ -109,8 +109,8 @@ class _RecurrentModel(nn.Module):
         # 7x7 convolutions: 3-pass split-bf16 tcgen05 tiles (default) or strict-fp32 CUDA cores; both pass the
         # same parity gate against the fp64 reference (tests/test_parity_gpu.py)
         self.conv_mode = _lib.PTK_CONV_BF16X3
-        if grad_method != "bptt":
-            raise NotImplementedError("only grad_method='bptt' is implemented (utils/engine.py always passes it)")
+        # grad_method / jacobian_penalty are stored and otherwise ignored, exactly as the reference does
+        # (models/InT.py:189-190: InT.forward has no rbp branch and returns a constant penalty, :242-245)
 
     def _config(self):
         return IntConfig(C=self.hgru_size, K=self.unit1.kernel_size, cell=self._cell_code, act=_act_code(self.nl),
