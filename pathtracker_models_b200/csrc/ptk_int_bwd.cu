@@ -25,6 +25,9 @@
 #ifndef PTK_BWD_MMA
 #define PTK_BWD_MMA 0
 #endif
+#ifndef PTK_BWD_D_MMA
+#define PTK_BWD_D_MMA 1
+#endif
 
 namespace ptk {
 
@@ -489,10 +492,9 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   BwdDIn cur;
   float xin[3][4];
   // prologue on parameters, forward statistics and the (read-only) clip: overlaps the previous kernel's tail (PDL)
-  // The mma.sync gate products (ptk_pw.cuh) pay in the forward kernels (-14 %) but not here: with 4-6 products per
-  // tile the legacy HMMA tf32 pipe is as busy as the FMA pipe was (measured +4 % on the two backward kernels), so
-  // the backward keeps the register-tiled FFMA products.  Flip PTK_BWD_MMA to re-measure.
-  constexpr bool MMA = PTK_BWD_MMA && (ACT & ACT_FAST) != 0;
+  // two products per tile, one accumulator set at a time: here the mma.sync path pays (measured -3 % on this kernel),
+  // unlike in int_bwd_c with its 4-6 products (see there).  PTK_BWD_D_MMA=0 restores the FFMA products.
+  constexpr bool MMA = PTK_BWD_D_MMA && (ACT & ACT_FAST) != 0;
   const float* const* gsrc = MMA ? d.gateF : d.gate;
   cta_fill_async(sWaw, gsrc[0], C * C);
   cta_fill_async(sWau, gsrc[1], C * C);
