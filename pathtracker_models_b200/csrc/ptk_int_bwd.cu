@@ -260,12 +260,14 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   BwdCIn cur;
   float xin[3][4];
   // prologue on parameters, forward statistics and the (read-only) clip: overlaps the previous kernel's tail (PDL)
-  // The mma.sync gate products (ptk_pw.cuh) pay in the forward kernels (-14 %) but not here: with 4-6 products per
-  // tile the legacy HMMA tf32 pipe is as busy as the FMA pipe was (measured +4 % on the two backward kernels), so
-  // the backward keeps the register-tiled FFMA products.  Flip PTK_BWD_MMA to re-measure.
+  // The mma.sync gate products (ptk_pw.cuh) pay in the forward kernels (-14 %) and in int_bwd_d (-3 %) but not here:
+  // all-mma was slower (two live accumulator sets spill, the legacy HMMA tf32 pipe is as busy as the FMA pipe was)
+  // and the hybrid below (one FFMA + three mma products) measured exactly equal to four FFMA products, so this
+  // kernel keeps the register-tiled FFMA products.  -DPTK_BWD_MMA=1 selects the hybrid to re-measure.
   constexpr bool MMA = PTK_BWD_MMA && (ACT & ACT_FAST) != 0;
   const float* const* gsrc = MMA ? d.gateF : d.gate;
-  cta_fill_async(sWiw, gsrc[2], C * C);
+  cta_fill_async(sWiw, d.gate[2], C * C);      // always the plain [out][in] layout: its product stays on the FMA pipe
+  const float* sWiw_ffma = sWiw;
   cta_fill_async(sWiu, gsrc[3], C * C);
   cta_fill_async(sWew, gsrc[4], C * C);
   cta_fill_async(sWeu, gsrc[5], C * C);
@@ -412,10 +414,12 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
     __syncwarp();
     float acc[4][8];
     if (MMA) {
-      Frag f;                            // one accumulator set at a time (two would spill)
-      frag_zero(f);
-      warp_mma_gemm(f, sGi, sWiw);       // dX = z + Wi_w^T gi: added to the parked z in fragment layout
-      frag_add_to_global(d.dX, (size_t)b * C * P + pix_base, P, f);
+      // hybrid: the product whose result must be added to the parked z stays on the FMA pipe (its accumulators
+      // start from global memory in patch layout); the other three run on mma.sync, one accumulator set at a time
+      acc_from_global(acc, d.dX, base, P, L);
+      warp_gemm(acc, sGi, sWiw_ffma, L);  // dX = z + Wi_w^T gi
+      acc_to_global(d.dX, base, P, L, acc);
+      Frag f;
       frag_zero(f);
       warp_mma_gemm(f, sGi, sWiu);       // dS += Wi_u^T gi + We_w^T ge   (the gi tile is dead after this)
       warp_mma_gemm(f, sGe, sWew);
