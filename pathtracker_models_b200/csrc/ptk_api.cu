@@ -272,6 +272,7 @@ int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transp
 PTK_API int ptk_debug_tc_stamps(long long* out) { return read_tc_debug(out); }
 PTK_API int ptk_debug_wt_stamps(long long* out) { return read_wt_debug(out); }
 PTK_API int ptk_debug_tc_times(unsigned long long* out, int n) { return read_tc_times(out, n); }
+PTK_API int ptk_debug_pw_stamps(unsigned long long* out) { return read_pw_stamps(out); }
 
 size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
   if (B < 1 || H < 16 || W < 32 || H % 16 || W % 32) return 0;

@@ -31,6 +31,7 @@ struct WgradArgs {
 };
 
 int conv_num_ctas(int B, int H, int W);
+int read_pw_stamps(unsigned long long* out);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st);
