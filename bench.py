@@ -413,7 +413,7 @@ def run_gru(args, dev, world, rank):
                       "config": {"workload": "kys.GRU %d frames %dx%d, batch %d" % (T, HW, HW, B)},
                       "gpu_launches": _lib.launch_count() - l0,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                   "note": "strict-fp32 CUDA-core path; cell-convolution FLOPs only"}}), flush=True)
+                                   "note": "cell-convolution FLOPs only (32x32-channel blocks on the tcgen05 conv kernels unless --conv-mode fp32)"}}), flush=True)
 
 
 def run_eval(args, dev, world, rank):

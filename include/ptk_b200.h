@@ -161,12 +161,13 @@ PTK_API int ptk_convlstm_backward_rbp(const PtkLstmDims* d, const float* x, cons
                                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- ConvGRU baseline (models/kys.py; `--model gru`, utils/engine.py:147-153: dimensions = 64, kernel 7) ----------
- * Flat parameter vector: preproc.{weight[64,3,1,1,1],bias}, unit1.conv_reset.{weight[64,128,7,7],bias},
- * unit1.conv_update.{weight,bias}, unit1.conv_state_new.{weight,bias}; ptk_gru_param_offsets fills 9 entries.
- * ptk_gru_forward = stem (:106-108) + the T ConvGRUCell steps (:36-48, :117-125) -> h_last [B,64,H,W]; the readout
- * head (:127-133) stays with the caller.  saved (always required) holds h_t (T+1), reset gates, update gates and
- * candidates (T each) as [.][B,64,H,W] blocks in that order: the testmode dumps are read from it.
- * ptk_gru_backward: dh_last -> dparams (flat, overwritten) and optionally dx [B,3,T,H,W] contiguous. */
+ * Flat parameter vector (14 tensors): preproc.{weight[64,3,1,1,1],bias}, unit1.conv_reset.{weight[64,128,7,7],bias},
+ * unit1.conv_update.{weight,bias}, unit1.conv_state_new.{weight,bias}, readout_conv.{weight[1,64,1,1],bias},
+ * target_conv.{weight[1,2,5,5],bias}, readout_dense.{weight[1,1],bias}; ptk_gru_param_offsets fills 15 entries.
+ * ptk_gru_forward = GRU.forward (:104-135): stem, the T ConvGRUCell steps (:36-48) and the readout -> logits [B].
+ * saved (always required) holds h_t (T+1), reset gates, update gates and candidates (T each) as [.][B,64,H,W] blocks
+ * in that order: the testmode dumps are read from it.
+ * ptk_gru_backward: dlogits [B] -> dparams (flat, overwritten) and optionally dx [B,3,T,H,W] contiguous. */
 typedef struct PtkGruDims {
   int32_t B, T, H, W;
   int32_t C;           /* 64  */
@@ -178,9 +179,9 @@ PTK_API int ptk_gru_param_offsets(const PtkGruDims* d, int64_t* offsets);
 PTK_API size_t ptk_gru_saved_bytes(const PtkGruDims* d);
 PTK_API size_t ptk_gru_workspace_bytes(const PtkGruDims* d);
 PTK_API int ptk_gru_forward(const PtkGruDims* d, const float* x, const int64_t x_strides[5], const float* params,
-                            float* h_last, void* saved, void* workspace, size_t workspace_bytes, void* stream);
+                            float* logits, void* saved, void* workspace, size_t workspace_bytes, void* stream);
 PTK_API int ptk_gru_backward(const PtkGruDims* d, const float* x, const int64_t x_strides[5], const float* params,
-                             const void* saved, const float* dh_last, float* dparams, float* dx, void* workspace,
+                             const void* saved, const float* dlogits, float* dparams, float* dx, void* workspace,
                              size_t workspace_bytes, void* stream);
 
 /* One horizontal-connection convolution on its own (test / measurement entry; the time loop calls the

@@ -477,6 +477,8 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
   float* slots_n = cv.take<float>((size_t)groups * GC * 2 * GC * taps);
   float* stem_acc = cv.take<float>(4 * GC);
   float* bias_grad = cv.take<float>(3 * GC);
+  float* head_part = cv.take<float>((size_t)dm->B * GRU_HEAD_N);
+  float* dgoal = cv.take<float>((size_t)dm->B * P);
   uint8_t *wtcF = nullptr, *wtcD = nullptr;
   float* wacc_tc = nullptr;
   const size_t wacc_pair = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
@@ -486,7 +488,7 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
     wacc_tc = cv.take<float>(24 * wacc_pair);
   }
   if (d) {
-    d->groups = groups; d->conv_mode = dm->conv_mode;
+    d->groups = groups; d->conv_mode = dm->conv_mode; d->head_part = head_part; d->dgoal = dgoal;
     d->wtcF = wtcF; d->wtcD = wtcD; d->wacc_tc = wacc_tc; d->wacc_pair = wacc_pair;
     d->hs = hs; d->rs = rs; d->us = us; d->ns = ns;
     d->wruT = wruT; d->wnT = wnT; d->wruD = wruD; d->wnD = wnD; d->bru = bru;
@@ -495,24 +497,27 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
   }
   return (cv.off + 255) & ~(size_t)255;
 }
-static void gru_offsets(int64_t* o) {   // preproc.{w,b}, conv_reset.{w,b}, conv_update.{w,b}, conv_state_new.{w,b}, total
+static void gru_offsets(int64_t* o) {   // preproc.{w,b}, conv_reset.{w,b}, conv_update.{w,b}, conv_state_new.{w,b},
+                                        // readout_conv.{w,b}, target_conv.{w,b}, readout_dense.{w,b}, total
   const int64_t nw = (int64_t)GC * 2 * GC * 49;
-  const int64_t sizes[8] = {GC * 3, GC, nw, GC, nw, GC, nw, GC};
+  const int64_t sizes[14] = {GC * 3, GC, nw, GC, nw, GC, nw, GC, GC, 1, 50, 1, 1, 1};
   int64_t a = 0;
-  for (int i = 0; i < 8; ++i) { o[i] = a; a += sizes[i]; }
-  o[8] = a;
+  for (int i = 0; i < 14; ++i) { o[i] = a; a += sizes[i]; }
+  o[14] = a;
 }
 static int gru_bind(GruDev* d, const PtkGruDims* dm, const float* x, const int64_t* xs, const float* params, void* saved,
                     void* ws) {
   memset(d, 0, sizeof(*d));
   d->B = dm->B; d->T = dm->T; d->H = dm->H; d->W = dm->W;
   d->fv.x = x; d->fv.sb = xs[0]; d->fv.sc = xs[1]; d->fv.st = xs[2]; d->fv.sy = xs[3]; d->fv.sx = xs[4];
-  int64_t o[9];
+  int64_t o[15];
   gru_offsets(o);
   d->Wp = params + o[0]; d->bp = params + o[1]; d->wr = params + o[2]; d->br = params + o[3];
   d->wu = params + o[4]; d->bu = params + o[5]; d->wn = params + o[6]; d->bnw = params + o[7];
   d->off_wp = o[0]; d->off_bp = o[1]; d->off_wr = o[2]; d->off_br = o[3]; d->off_wu = o[4]; d->off_bu = o[5];
   d->off_wn = o[6]; d->off_bn = o[7];
+  d->hWr = params + o[8]; d->hbr = params + o[9]; d->hWt = params + o[10]; d->hbt = params + o[11];
+  d->hWd = params + o[12]; d->hbd = params + o[13]; d->off_head = o[8];
   gru_carve(dm, saved, ws, d, nullptr);
   return PTK_OK;
 }
@@ -533,26 +538,26 @@ size_t ptk_gru_workspace_bytes(const PtkGruDims* d) {
   if (gru_check(d, "ptk_gru_workspace_bytes")) return 0;
   return gru_carve(d, nullptr, nullptr, nullptr, nullptr);
 }
-int ptk_gru_forward(const PtkGruDims* dm, const float* x, const int64_t x_strides[5], const float* params, float* h_last,
+int ptk_gru_forward(const PtkGruDims* dm, const float* x, const int64_t x_strides[5], const float* params, float* logits,
                     void* saved, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = gru_check(dm, "ptk_gru_forward");
   if (rc) return rc;
-  if (!x || !x_strides || !params || !h_last || !saved || !workspace) { set_error("ptk_gru_forward: NULL argument"); return PTK_EINVAL; }
+  if (!x || !x_strides || !params || !logits || !saved || !workspace) { set_error("ptk_gru_forward: NULL argument"); return PTK_EINVAL; }
   if (workspace_bytes < ptk_gru_workspace_bytes(dm)) { set_error("ptk_gru_forward: workspace too small"); return PTK_ENOMEM; }
   GruDev d;
   if ((rc = gru_bind(&d, dm, x, x_strides, params, saved, workspace))) return rc;
-  d.hT = h_last;
+  d.logits = logits;
   return run_gru_forward(d, (cudaStream_t)stream);
 }
 int ptk_gru_backward(const PtkGruDims* dm, const float* x, const int64_t x_strides[5], const float* params, const void* saved,
-                     const float* dh_last, float* dparams, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
+                     const float* dlogits, float* dparams, float* dx, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = gru_check(dm, "ptk_gru_backward");
   if (rc) return rc;
-  if (!x || !x_strides || !params || !saved || !dh_last || !dparams || !workspace) { set_error("ptk_gru_backward: NULL argument"); return PTK_EINVAL; }
+  if (!x || !x_strides || !params || !saved || !dlogits || !dparams || !workspace) { set_error("ptk_gru_backward: NULL argument"); return PTK_EINVAL; }
   if (workspace_bytes < ptk_gru_workspace_bytes(dm)) { set_error("ptk_gru_backward: workspace too small"); return PTK_ENOMEM; }
   GruDev d;
   if ((rc = gru_bind(&d, dm, x, x_strides, params, const_cast<void*>(saved), workspace))) return rc;
-  d.dhT = dh_last; d.dparams = dparams; d.dx = dx;
+  d.dlogits = dlogits; d.dparams = dparams; d.dx = dx;
   return run_gru_backward(d, (cudaStream_t)stream);
 }
 

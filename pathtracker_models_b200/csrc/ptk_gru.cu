@@ -136,6 +136,7 @@ __global__ void gru_dx_kernel(GruDev d, int t) {
     const int pix = (int)(e % P), i = (int)((e / P) % 3), b = (int)(e / ((size_t)P * 3));
     float s = 0.f;
     for (int c = 0; c < GC; ++c) s = fmaf(__ldg(d.Wp + c * 3 + i), d.dXb[((size_t)b * GC + c) * P + pix], s);
+    if (t == 1 && i == 2) s += d.dgoal[(size_t)b * P + pix];     // x[:,2,0] also feeds the readout (models/kys.py:127)
     d.dx[(((size_t)b * 3 + i) * d.T + (t - 1)) * P + pix] = s;
   }
 }
@@ -144,6 +145,132 @@ __global__ void gru_stem_out_kernel(GruDev d) {      // stem_acc [64][4] -> dpar
   if (c >= GC) return;
   d.dparams[d.off_bp + c] = d.stem_acc[c * 4];
   for (int i = 0; i < 3; ++i) d.dparams[d.off_wp + c * 3 + i] = d.stem_acc[c * 4 + 1 + i];
+}
+
+// ---- readout head (models/kys.py:127-133): r = readout_conv(h_T); cat with the goal channel x[:,2,0]; 5x5 conv (pad 2);
+//      global mean; Linear(1,1).  One CTA per sample (same scheme as the InT readout, 64 channels).
+__device__ __forceinline__ void gru_head_maps(const GruDev& d, int b, float* sR, float* sG, float* sWt, float* sWr) {
+  const int H = d.H, W = d.W, P = H * W, Wp2 = W + 4, Hp2 = H + 4, tid = threadIdx.x;
+  const float* hT = d.h_at(d.T);
+  if (tid < 50) sWt[tid] = __ldg(d.hWt + tid);
+  if (tid < GC) sWr[tid] = __ldg(d.hWr + tid);
+  for (int i = tid; i < 2 * Hp2 * Wp2; i += 256) sR[i] = 0.f;      // sR and sG are contiguous
+  __syncthreads();
+  const float br = __ldg(d.hbr);
+  for (int pix = tid; pix < P; pix += 256) {
+    float r = br;
+#pragma unroll 8
+    for (int c = 0; c < GC; ++c) r = fmaf(sWr[c], hT[((size_t)b * GC + c) * P + pix], r);
+    const int y = pix / W, x = pix % W;
+    sR[(y + 2) * Wp2 + x + 2] = r;
+    sG[(y + 2) * Wp2 + x + 2] = d.fv.at(b, 2, 0, y, x);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ float gru_head_conv_sum(const GruDev& d, const float* sR, const float* sG, const float* sWt) {
+  const int W = d.W, P = d.H * d.W, Wp2 = W + 4;
+  float s = 0.f;
+  for (int pix = threadIdx.x; pix < P; pix += 256) {
+    const int y = pix / W, x = pix % W;
+    float o = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        o = fmaf(sWt[ky * 5 + kx], sR[(y + ky) * Wp2 + x + kx], o);
+        o = fmaf(sWt[25 + ky * 5 + kx], sG[(y + ky) * Wp2 + x + kx], o);
+      }
+    s += o;
+  }
+  return s;
+}
+__device__ __forceinline__ float gru_block_sum(float v, float* sRed) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sRed[i];
+  return tot;
+}
+__global__ void __launch_bounds__(256) gru_readout_kernel(GruDev d) {
+  extern __shared__ float sm[];
+  const int P = d.H * d.W;
+  float* sR = sm;
+  float* sG = sm + (d.H + 4) * (d.W + 4);
+  __shared__ float sWt[50], sWr[GC], sRed[8];
+  const int b = blockIdx.x;
+  gru_head_maps(d, b, sR, sG, sWt, sWr);
+  const float tot = gru_block_sum(gru_head_conv_sum(d, sR, sG, sWt), sRed);
+  if (threadIdx.x == 0) d.logits[b] = fmaf(__ldg(d.hWd), tot / (float)P + __ldg(d.hbt), __ldg(d.hbd));
+}
+// reverse of the head: dlogits -> d h_T (into d.dh), per-sample head gradients, d x[:,2,0]
+__global__ void __launch_bounds__(256) gru_readout_bwd_kernel(GruDev d) {
+  extern __shared__ float sm[];
+  const int H = d.H, W = d.W, P = H * W, Wp2 = W + 4, Hp2 = H + 4;
+  float* sR = sm;
+  float* sG = sm + Hp2 * Wp2;
+  float* sDr = sG + Hp2 * Wp2;    // [P]
+  __shared__ float sWt[50], sWr[GC], sRed[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* hT = d.h_at(d.T);
+  gru_head_maps(d, b, sR, sG, sWt, sWr);
+  const float pooled = gru_block_sum(gru_head_conv_sum(d, sR, sG, sWt), sRed) / (float)P + __ldg(d.hbt);
+  const float dl = d.dlogits[b];
+  const float dpool = dl * __ldg(d.hWd);
+  const float dov = dpool / (float)P;                      // d(5x5 conv output), constant over the image
+  float* hd = d.head_part + (size_t)b * GRU_HEAD_N;        // order: dWr[64], dbr, dWt[50], dbt, dWd, dbd
+  if (tid == 0) {
+    hd[GC + 1 + 50] = dpool;        // d target_conv.bias
+    hd[GC + 1 + 51] = dl * pooled;  // d readout_dense.weight
+    hd[GC + 1 + 52] = dl;           // d readout_dense.bias
+  }
+  for (int w = 0; w < 50; ++w) {    // d target_conv.weight: window sums of the padded maps
+    const int ch = w / 25, ky = (w % 25) / 5, kx = w % 5;
+    const float* srcm = ch ? sG : sR;
+    float v = 0.f;
+    for (int pix = tid; pix < P; pix += 256) v += srcm[(pix / W + ky) * Wp2 + pix % W + kx];
+    v = gru_block_sum(v, sRed);
+    if (tid == 0) hd[GC + 1 + w] = dov * v;
+  }
+  float sbr = 0.f;
+  for (int pix = tid; pix < P; pix += 256) {
+    const int y = pix / W, x = pix % W;
+    float wsum = 0.f, gsum = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int yy = y - ky + 2, xx = x - kx + 2;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) { wsum += sWt[ky * 5 + kx]; gsum += sWt[25 + ky * 5 + kx]; }
+      }
+    const float dr = dov * wsum;
+    d.dgoal[(size_t)b * P + pix] = dov * gsum;             // d x[b,2,0,y,x] via torch.cat(..., x[:,2,0]) (kys.py:127)
+    sDr[pix] = dr;
+    sbr += dr;
+  }
+  sbr = gru_block_sum(sbr, sRed);
+  if (tid == 0) hd[GC] = sbr;                              // d readout_conv.bias
+  __syncthreads();
+  for (int c = 0; c < GC; ++c) {                           // d h_T = Wr dr; d readout_conv.weight[c] = sum dr h_T[c]
+    float v = 0.f;
+    for (int pix = tid; pix < P; pix += 256) {
+      const size_t idx = ((size_t)b * GC + c) * P + pix;
+      v = fmaf(sDr[pix], hT[idx], v);
+      d.dh[idx] = sWr[c] * sDr[pix];
+    }
+    v = gru_block_sum(v, sRed);
+    if (tid == 0) hd[c] = v;
+  }
+}
+__global__ void gru_head_fold_kernel(GruDev d) {     // per-sample head gradients -> dparams (fp64, fixed order)
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= GRU_HEAD_N) return;
+  double s = 0;
+  for (int b = 0; b < d.B; ++b) s += (double)d.head_part[(size_t)b * GRU_HEAD_N + j];
+  d.dparams[d.off_head + j] = (float)s;
 }
 
 // ---- tensor-core modes: the wide convolutions as 32 x 32-channel blocks on the tcgen05 kernels of the InT path ----
@@ -257,7 +384,10 @@ int run_gru_forward(const GruDev& d, cudaStream_t st) {
     }
     PTK_LAUNCH_OK("gru step");
   }
-  PTK_CUDA_OK(cudaMemcpyAsync(d.hT, d.h_at(d.T), d.S() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const size_t smr = (size_t)2 * (d.H + 4) * (d.W + 4) * sizeof(float);
+  PTK_CUDA_OK(cudaFuncSetAttribute(gru_readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+  gru_readout_kernel<<<d.B, 256, smr, st>>>(d);
+  PTK_LAUNCH_OK("gru_readout_kernel");
   return PTK_OK;
 }
 
@@ -266,7 +396,12 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
   const int taps = 49, grid = 148 * 8, P = d.H * d.W;
   const bool tc = d.conv_mode != PTK_CONV_FP32;
   if ((rc = tc ? gru_prep_tc(d, st) : gru_prep(d, true, st))) return rc;
-  PTK_CUDA_OK(cudaMemcpyAsync(d.dh, d.dhT, d.S() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  {
+    const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
+    PTK_CUDA_OK(cudaFuncSetAttribute(gru_readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+    gru_readout_bwd_kernel<<<d.B, 256, smr, st>>>(d);       // dlogits -> d.dh (= dL/dh_T), head gradients, d goal channel
+    PTK_LAUNCH_OK("gru_readout_bwd_kernel");
+  }
   for (int t = d.T; t >= 1; --t) {
     const int first = (t == d.T);
     {
@@ -319,6 +454,7 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
   PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_br, d.bias_grad + GC, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_bu, d.bias_grad + 2 * GC, GC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   gru_stem_out_kernel<<<1, GC, 0, st>>>(d);
+  gru_head_fold_kernel<<<1, 128, 0, st>>>(d);
   PTK_LAUNCH_OK("gru fold");
   return PTK_OK;
 }

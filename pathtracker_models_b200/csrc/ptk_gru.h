@@ -8,6 +8,7 @@
 namespace ptk {
 
 constexpr int GC = 64;   // hidden / stem channels (utils/engine.py:149: dimensions * 2)
+constexpr int GRU_HEAD_N = GC + 1 + 50 + 1 + 1 + 1;   // dWr, dbr, dWt, dbt, dWd, dbd (flat-vector order)
 
 struct GruDev {
   int B, T, H, W, groups, conv_mode;
@@ -15,6 +16,9 @@ struct GruDev {
   // parameters (views into the flat vector): preproc.{w [64,3], b}, conv_reset / conv_update / conv_state_new {w [64,128,7,7], b}
   const float *Wp, *bp, *wr, *br, *wu, *bu, *wn, *bnw;
   long long off_wp, off_bp, off_wr, off_br, off_wu, off_bu, off_wn, off_bn;
+  // readout head (models/kys.py:127-133): readout_conv [1,64,1,1], target_conv [1,2,5,5], readout_dense [1,1]
+  const float *hWr, *hbr, *hWt, *hbt, *hWd, *hbd;
+  long long off_head;      // the six head tensors are contiguous in the flat vector: 64, 1, 50, 1, 1, 1
   // re-laid-out weight banks and the gathered [br|bu] bias (workspace)
   float *wruT, *wnT, *wruD, *wnD, *bru;
   // checkpoints (saved): h [T+1][B,64,P]; reset / update gates and the candidate [T][B,64,P]
@@ -28,8 +32,9 @@ struct GruDev {
   float* wacc_tc;
   size_t wacc_pair;      // floats per pair
   // I/O
-  float* hT;            // [B,64,H,W]
-  const float* dhT;
+  float* logits;        // [B]
+  const float* dlogits; // [B]
+  float *head_part, *dgoal;   // [B][GRU_HEAD_N] per-sample head gradients; [B,P] d x[:,2,0] through the goal channel
   float* dparams;
   float* dx;            // optional [B,3,T,H,W] contiguous
 

@@ -2,9 +2,9 @@
 same constructors, parameter names, state_dict order and init RNG order; `forward(x[, testmode])` ->
 `(logits [B,1], jv_penalty [1])` / `(logits, states [B,T,1,H,W], gates [B,T,C,H,W])`.
 
-The stem and the T ConvGRU steps (forward and BPTT) run in libptk_b200 (ptk_gru_forward / ptk_gru_backward, first
-version: strict-fp32 CUDA-core convolutions shared with the ConvLSTM path).  The readout head (1x1 conv, 5x5 conv,
-global mean, Linear: ~0.3 MFLOP per sample, outside the time loop) stays in PyTorch for now."""
+The whole of GRU.forward (:104-135) -- stem, the T ConvGRU steps and the readout head (1x1 conv, cat with the goal
+channel, 5x5 conv, global mean, Linear) -- forward and BPTT runs in libptk_b200 (ptk_gru_forward / ptk_gru_backward);
+all 14 parameter tensors travel in one flat vector."""
 import ctypes
 
 import torch
@@ -36,7 +36,7 @@ class ConvGRUCell(nn.Module):
 
 
 class _GruFunction(torch.autograd.Function):
-    """h_T (and the per-step checkpoints) = stem + ConvGRU time loop; backward = hand-written BPTT."""
+    """logits (and the per-step checkpoints) = stem + ConvGRU time loop + readout; backward = hand-written BPTT."""
 
     @staticmethod
     def forward(ctx, x, flat, dims, want_dumps):
@@ -51,9 +51,9 @@ class _GruFunction(torch.autograd.Function):
                 _lib.check(1, "ptk_gru_workspace_bytes")
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             saved = torch.empty(sv_bytes, dtype=torch.uint8, device=x.device)
-            hT = torch.empty(B, C, H, W, dtype=torch.float32, device=x.device)
+            logits = torch.empty(B, 1, dtype=torch.float32, device=x.device)
             stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-            rc = L.ptk_gru_forward(ctypes.byref(dims), _ptr(x), _strides(x), _ptr(flat), _ptr(hT), _ptr(saved), _ptr(ws),
+            rc = L.ptk_gru_forward(ctypes.byref(dims), _ptr(x), _strides(x), _ptr(flat), _ptr(logits), _ptr(saved), _ptr(ws),
                                    ws_bytes, stream)
             _lib.check(rc, "ptk_gru_forward")
         ctx.dims, ctx.saved_buf = dims, saved
@@ -66,11 +66,11 @@ class _GruFunction(torch.autograd.Function):
         else:
             hs = rs = torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(hs, rs)
-        return hT, hs, rs
+        return logits, hs, rs
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dhT, _dhs, _drs):
+    def backward(ctx, dlogits, _dhs, _drs):
         x, flat = ctx.saved_tensors
         L = _lib.lib()
         dims = ctx.dims
@@ -79,9 +79,9 @@ class _GruFunction(torch.autograd.Function):
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             dflat = torch.empty_like(flat)
             dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
-            dhT = dhT.contiguous().float()
+            dlogits = dlogits.contiguous().float()
             stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-            rc = L.ptk_gru_backward(ctypes.byref(dims), _ptr(x), _strides(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dhT),
+            rc = L.ptk_gru_backward(ctypes.byref(dims), _ptr(x), _strides(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dlogits),
                                     _ptr(dflat), _ptr(dx), _ptr(ws), ws_bytes, stream)
             _lib.check(rc, "ptk_gru_backward")
         ctx.saved_buf = None
@@ -109,15 +109,13 @@ class GRU(nn.Module):
         self.conv_mode = _lib.PTK_CONV_BF16X3
 
     def flat_parameters(self):
-        """the 8 tensors of the stem and the cell, in the C ABI's order (by attribute: works on DataParallel replicas)."""
+        """the 14 tensors of stem, cell and head in the C ABI's order (by attribute: works on DataParallel replicas)."""
         u = self.unit1
         ts = [self.preproc.weight, self.preproc.bias, u.conv_reset.weight, u.conv_reset.bias, u.conv_update.weight,
-              u.conv_update.bias, u.conv_state_new.weight, u.conv_state_new.bias]
+              u.conv_update.bias, u.conv_state_new.weight, u.conv_state_new.bias, self.readout_conv.weight,
+              self.readout_conv.bias, self.target_conv.weight, self.target_conv.bias, self.readout_dense.weight,
+              self.readout_dense.bias]
         return torch.cat([t.reshape(-1) for t in ts])
-
-    def dp_extra_parameters(self):
-        """parameters outside the flat vector (the PyTorch-side head): averaged by their own hooks under data parallelism"""
-        return [p for m in (self.readout_conv, self.target_conv, self.readout_dense) for p in m.parameters()]
 
     def forward(self, x, testmode=False):
         if not x.is_cuda:
@@ -128,12 +126,7 @@ class GRU(nn.Module):
         B, _, T, H, W = x.shape
         dims = _lib.PtkGruDims(B, T, H, W, self.hgru_size, self.unit1.kernel_size, int(self.conv_mode))
         from .parallel import flat_gradient_hook
-        hT, hs, rs = _GruFunction.apply(x, flat_gradient_hook(self, self.flat_parameters()), dims, bool(testmode))
-        # readout (models/kys.py:127-133), kept in PyTorch: negligible work, outside the time loop
-        output = torch.cat([self.readout_conv(hT), x[:, 2, 0][:, None]], 1)
-        output = self.target_conv(output)
-        output = F.avg_pool2d(output, kernel_size=output.size()[2:]).reshape(B, -1)
-        output = self.readout_dense(output)
+        output, hs, rs = _GruFunction.apply(x, flat_gradient_hook(self, self.flat_parameters()), dims, bool(testmode))
         if testmode:
             with torch.no_grad():
                 states = self.readout_conv(hs.reshape(B * T, self.hgru_size, H, W)).view(B, T, 1, H, W)

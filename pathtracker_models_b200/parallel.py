@@ -33,7 +33,7 @@ def attach_data_parallel(model, group=None):
         raise RuntimeError("torch.distributed is not initialised")
     model._dp_group = group
     model._dp_enabled = True
-    # parameters that do not travel in the flat vector (the PyTorch-side readout head of kys.GRU) get their own hook
+    # parameters a mirror module keeps outside its flat vector (none today) would get their own hook
     for p in getattr(model, "dp_extra_parameters", lambda: [])():
         p.register_hook(lambda g, _grp=group: average_flat_gradient_(g.contiguous(), _grp))
     return model

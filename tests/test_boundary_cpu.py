@@ -111,3 +111,23 @@ def test_device_prefetcher_preserves_order_and_count():
     for i, (x, y) in enumerate(got):
         assert float(x[0, 0]) == i and float(y[0]) == i
     assert list(DevicePrefetcher(iter([]), "cpu")) == []
+
+
+def test_gru_flat_layout_covers_all_fourteen_tensors():
+    """ptk_gru_param_offsets (include/ptk_b200.h) vs kys.GRU.flat_parameters: stem, cell and readout head in one vector"""
+    import ctypes
+    from pathtracker_models_b200 import _lib, kys
+    m = kys.GRU(dimensions=64, timesteps=4, kernel_size=7)
+    off = (ctypes.c_int64 * 15)()
+    dims = _lib.PtkGruDims(2, 4, 32, 32, 64, 7, _lib.PTK_CONV_FP32)
+    _lib.check(_lib.lib().ptk_gru_param_offsets(ctypes.byref(dims), off), "ptk_gru_param_offsets")
+    u = m.unit1
+    ts = [m.preproc.weight, m.preproc.bias, u.conv_reset.weight, u.conv_reset.bias, u.conv_update.weight, u.conv_update.bias,
+          u.conv_state_new.weight, u.conv_state_new.bias, m.readout_conv.weight, m.readout_conv.bias, m.target_conv.weight,
+          m.target_conv.bias, m.readout_dense.weight, m.readout_dense.bias]
+    assert [off[i + 1] - off[i] for i in range(14)] == [t.numel() for t in ts]
+    flat = m.flat_parameters()
+    assert flat.numel() == off[14]
+    assert torch.equal(flat[off[10]:off[11]], m.target_conv.weight.detach().reshape(-1))
+    # every trainable tensor except the reference's unused BatchNorm3d (models/kys.py:80) travels in the flat vector
+    assert sum(p.numel() for n, p in m.named_parameters() if not n.startswith("bn.")) == off[14]
