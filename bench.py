@@ -344,6 +344,7 @@ def run_convlstm(args, dev, world, rank):
     gabor = torch.from_numpy(rs.normal(0, 0.3, (25, 1, 7, 7)).astype(np.float32))   # the .npy is not on the GPU box
     torch.manual_seed(0)
     m = convlstm.ConvLSTM(timesteps=T, filt_size=15, gabor=gabor).to(dev).train()
+    m.conv_mode = _lib.PTK_CONV_FP32 if args.conv_mode == "fp32" else _lib.PTK_CONV_BF16X3
     clips, y = synth_pathtracker(B, 2, HW, HW, device=dev)
     x = clips[:, 0:1, 0].contiguous()                                               # [B,1,H,W] static image
     tgt = (clips[:, 2, 0] > 0).long()
@@ -373,7 +374,9 @@ def run_convlstm(args, dev, world, rank):
                       "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T, B, HW, HW)},
                       "gpu_launches": _lib.launch_count() - l0,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                   "note": "strict-fp32 CUDA-core path; recurrent-conv FLOPs only"}}), flush=True)
+                                   "note": "recurrent-conv FLOPs only; conv_mode %s (bf16x3: forward / transposed convolution on "
+                                           "tcgen05, weight gradient on CUDA cores)" % ("fp32" if args.conv_mode == "fp32" else "bf16x3")}}),
+          flush=True)
 
 
 def run_gru(args, dev, world, rank):

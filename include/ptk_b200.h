@@ -137,6 +137,9 @@ PTK_API int ptk_adam_step(int64_t n, float* params, float* grads, float* exp_avg
 typedef struct PtkLstmDims {
   int32_t B, T, H, W;  /* x is [B,1,H,W]; T = timesteps (models/convlstm.py:138 loops self.timesteps) */
   int32_t K;           /* filt_size: 15 (default, models/convlstm.py:95) or 7                         */
+  int32_t conv_mode;   /* PTK_CONV_FP32: every convolution in strict fp32 on CUDA cores; PTK_CONV_BF16X3: the recurrent
+                        * convolution of h and its transpose (the two per-step convolutions of the time loops) as
+                        * 3-pass split-bf16 tcgen05 implicit GEMMs, same parity gate                    */
 } PtkLstmDims;
 PTK_API int ptk_convlstm_param_offsets(const PtkLstmDims* d, int64_t* offsets);
 PTK_API size_t ptk_convlstm_saved_bytes(const PtkLstmDims* d);

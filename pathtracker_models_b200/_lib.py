@@ -29,7 +29,7 @@ class PtkDims(ctypes.Structure):
 
 
 class PtkLstmDims(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K", "conv_mode")]
 
 
 class PtkGruDims(ctypes.Structure):

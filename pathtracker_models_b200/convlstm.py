@@ -121,6 +121,9 @@ class ConvLSTM(nn.Module):
         self.conv6 = nn.Conv2d(25, 2, kernel_size=1)
         init.xavier_normal_(self.conv6.weight)
         init.constant_(self.conv6.bias, math.log((1 - 0.01) / 0.01))
+        # the two per-step convolutions of the time loops (h -> gates and its transpose): 3-pass split-bf16 tcgen05
+        # implicit GEMMs (default) or strict-fp32 CUDA cores; same parity gate (tests/test_convlstm_gpu.py)
+        self.conv_mode = _lib.PTK_CONV_BF16X3
 
     def flat_parameters(self):
         # registration order == C ABI order; by attribute (not parameters()) so that nn.DataParallel replicas work
@@ -137,7 +140,7 @@ class ConvLSTM(nn.Module):
         B, ch, H, W = x.shape
         if ch != 1:
             raise ValueError(f"expected x of shape [B,1,H,W], got {tuple(x.shape)}")
-        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size)
+        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size, int(self.conv_mode))
         rbp = self.grad_method == 'rbp'
         from .parallel import flat_gradient_hook
         output, pen, states = _ConvLSTMFunction.apply(x.float(), flat_gradient_hook(self, self.flat_parameters()), dims, bool(self.training),

@@ -290,6 +290,10 @@ size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
 static int lstm_check(const PtkLstmDims* d, const char* who) {
   if (!d) { set_error("%s: dims is NULL", who); return PTK_EINVAL; }
   if (d->K != 7 && d->K != 15) { set_error("%s: filt_size %d not built (7 and 15 are)", who, d->K); return PTK_EUNSUPPORTED; }
+  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3) {
+    set_error("%s: conv_mode %d not built for the ConvLSTM (fp32 and bf16x3 are)", who, d->conv_mode);
+    return PTK_EUNSUPPORTED;
+  }
   if (d->B < 1 || d->T < 1 || d->H < 16 || d->W < 32 || d->H % 16 || d->W % 32) {
     set_error("%s: unsupported shape B=%d T=%d H=%d W=%d", who, d->B, d->T, d->H, d->W);
     return PTK_EINVAL;
@@ -342,7 +346,13 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   float* rbp_g = cv.take<float>(S);
   float* rbp_state = cv.take<float>(64);
   double* rbp_part = cv.take<double>(2 * 148 * 2);
+  uint8_t *whF_tc = nullptr, *whD_tc = nullptr;
+  if (dm->conv_mode != PTK_CONV_FP32) {
+    whF_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(0) : convk_tc_weight_bytes<7>(0));
+    whD_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));
+  }
   if (d) {
+    d->whF_tc = whF_tc; d->whD_tc = whD_tc; d->conv_mode = dm->conv_mode;
     d->rbp_g = rbp_g; d->rbp_state = rbp_state; d->rbp_part = rbp_part;
     d->groups = groups;
     d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;

@@ -18,6 +18,7 @@
 #include "ptk_common.cuh"
 #include "ptk_convg.cuh"
 #include "ptk_convlstm.h"
+#include "ptk_kernels.h"
 #include "ptk_profile.h"
 
 namespace ptk {
@@ -152,6 +153,21 @@ __global__ void __launch_bounds__(512) head_bwd_kernel(const float* __restrict__
     dh[idx] = gw * rstd * (dhn - m1 - xh * m2);   // BatchNorm backward with batch statistics
   }
 }
+// the two per-step convolutions of the time loops: h -> stacked gate pre-activations and its transpose.
+// conv_mode bf16x3: tcgen05 implicit GEMM (ptk_convk_tc.cu); fp32: the generic direct kernel.
+template <int KS>
+static int recurrent_conv(const LstmDev& d, const ConvGArgs& g, bool transposed, cudaStream_t st) {
+  if (d.conv_mode == PTK_CONV_FP32) return launch_convg<KS>(g, st);
+  ConvKArgs k{g.in, transposed ? d.whD_tc : d.whF_tc, g.bias, g.addend, g.out, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, g.skip};
+  ProfileScope ps(transposed ? PTK_PROF_CONV_DGRAD : PTK_PROF_CONV_FWD, st);
+  return launch_convk_tc<KS>(k, transposed ? 1 : 0, st);
+}
+template <int KS>
+static int recurrent_prep(const LstmDev& d, bool transposed, cudaStream_t st) {
+  if (d.conv_mode == PTK_CONV_FP32) return PTK_OK;
+  return launch_prep_weights_k<KS>(d.wh, transposed ? 1 : 0, transposed ? d.whD_tc : d.whF_tc, st);
+}
+
 template <int KS>
 static int convlstm_forward_t(const LstmDev& d, cudaStream_t st) {
   const int P = d.H * d.W, taps = KS * KS;
@@ -162,6 +178,7 @@ static int convlstm_forward_t(const LstmDev& d, cudaStream_t st) {
   if ((rc = launch_prepg(w0, 1, LC, 1, 49, 0, d.w0T, (size_t)49 * 32, st))) return rc;
   if ((rc = launch_prepg(d.wx, 4, LC, LC, taps, 0, d.wxT, (size_t)4 * LC * taps * 32, st))) return rc;
   if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 0, d.whT, (size_t)4 * LC * taps * 32, st))) return rc;
+  if ((rc = recurrent_prep<KS>(d, false, st))) return rc;
   ConvGArgs c0{d.x, d.w0T, d.b0, nullptr, d.u, d.B, d.H, d.W, 1, LC, 0};
   if ((rc = launch_convg<7>(c0, st))) return rc;
   square_kernel<<<148 * 4, 256, 0, st>>>(d.u, d.xt, S);
@@ -171,7 +188,7 @@ static int convlstm_forward_t(const LstmDev& d, cudaStream_t st) {
   PTK_CUDA_OK(cudaMemsetAsync(d.c_at(0), 0, S * sizeof(float), st));
   for (int t = 1; t <= d.T; ++t) {
     ConvGArgs ch{d.h_at(t - 1), d.whT, nullptr, d.Xg, d.G, d.B, d.H, d.W, LC, LG, 0};
-    if ((rc = launch_convg<KS>(ch, st))) return rc;
+    if ((rc = recurrent_conv<KS>(d, ch, false, st))) return rc;
     ProfileScope ps(PTK_PROF_POINT_FWD, st);
     lstm_fwd_kernel<<<148 * 4, 256, 0, st>>>(d.G, d.c_at(t - 1), d.gates_at(t), d.c_at(t), d.h_at(t), d.B, P);
     PTK_LAUNCH_OK("lstm_fwd_kernel");
@@ -189,17 +206,18 @@ static int convlstm_penalty_t(const LstmDev& d, cudaStream_t st) {
   const int P = d.H * d.W, taps = KS * KS;
   int rc;
   if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 1, d.whD, (size_t)LG * taps * 32, st))) return rc;
+  if ((rc = recurrent_prep<KS>(d, true, st))) return rc;
   const int T = d.T;
   // seed dh = 1, dc = 0  -> jh
   lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(nullptr, 1.0f, nullptr, 0.0f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
                                            nullptr, nullptr, 0, d.B, P);
   ConvGArgs c1{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0};
-  if ((rc = launch_convg<KS>(c1, st))) return rc;
+  if ((rc = recurrent_conv<KS>(d, c1, true, st))) return rc;
   // seed dh = 0, dc = 1  -> v = d c_T / d h_{T-1}
   lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(nullptr, 0.0f, nullptr, 1.0f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
                                            nullptr, nullptr, 0, d.B, P);
   ConvGArgs c2{d.delta, d.whD, nullptr, nullptr, d.dc, d.B, d.H, d.W, LG, LC, 0};
-  if ((rc = launch_convg<KS>(c2, st))) return rc;
+  if ((rc = recurrent_conv<KS>(d, c2, true, st))) return rc;
   penalty_kernel<<<148 * 4, 256, 0, st>>>(d.dh, d.dc, d.gates_at(T), T >= 2 ? d.gates_at(T - 1) : nullptr,
                                           d.c_at(T - 1), d.penalty, d.B, P);
   PTK_LAUNCH_OK("penalty_kernel");
@@ -215,6 +233,7 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
   const size_t S = (size_t)d.B * LC * P;
   int rc;
   if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 1, d.whD, (size_t)LG * taps * 32, st))) return rc;
+  if ((rc = recurrent_prep<KS>(d, true, st))) return rc;
   if ((rc = launch_prepg(d.wx, 4, LC, LC, taps, 1, d.wxD, (size_t)LG * taps * 32, st))) return rc;
   // head: d out -> dh_T, d bn / conv6
   head_bwd_kernel<<<LC, 512, 0, st>>>(d.h_at(d.T), d.head_stats, d.bn_w, d.bn_b, d.w6, d.dout, d.dh, d.head_grads, d.B, P);
@@ -232,7 +251,7 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
     if ((rc = launch_wgradg<KS>(w, st))) return rc;
     if (t > 1) {
       ConvGArgs c{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0};
-      if ((rc = launch_convg<KS>(c, st))) return rc;
+      if ((rc = recurrent_conv<KS>(d, c, true, st))) return rc;
     }
   }
   // input path, once: dWx = xt (star) sum delta; db = sum; d xt = sum delta *^T Wx; conv0
@@ -317,6 +336,7 @@ static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t 
   const size_t S = (size_t)d.B * LC * P;
   int rc;
   if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 1, d.whD, (size_t)LG * taps * 32, st))) return rc;
+  if ((rc = recurrent_prep<KS>(d, true, st))) return rc;
   if ((rc = launch_prepg(d.wx, 4, LC, LC, taps, 1, d.wxD, (size_t)LG * taps * 32, st))) return rc;
   // head: d out -> dh_T (= grad of dummyhgru.backward), d bn / conv6.  v_prev lives in d.dc, v_new in d.dh.
   head_bwd_kernel<<<LC, 512, 0, st>>>(d.h_at(T), d.head_stats, d.bn_w, d.bn_b, d.w6, d.dout, d.dc, d.head_grads, d.B, P);
@@ -328,7 +348,7 @@ static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t 
     lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(d.dc, 0.f, nullptr, 0.f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
                                              nullptr, nullptr, 0, d.B, P, d.rbp_state);
     ConvGArgs c{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0, d.rbp_state};
-    if ((rc = launch_convg<KS>(c, st))) return rc;
+    if ((rc = recurrent_conv<KS>(d, c, true, st))) return rc;
     rbp_sumsq_kernel<<<RBP_CTAS, 256, 0, st>>>(d.dh, d.rbp_g, S, d.rbp_part, d.rbp_state);
     rbp_decide_kernel<<<1, 32, 0, st>>>(d.rbp_part, RBP_CTAS, d.rbp_state, 0);
     rbp_commit_kernel<<<148 * 4, 256, 0, st>>>(d.rbp_g, d.dc, d.dh, S, d.rbp_state);

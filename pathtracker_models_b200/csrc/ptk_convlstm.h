@@ -6,7 +6,8 @@
 namespace ptk {
 
 struct LstmDev {
-  int B, T, H, W, KS, groups;
+  int B, T, H, W, KS, groups, conv_mode;
+  void *whF_tc, *whD_tc;                // tensor-core weight streams of the recurrent convolution / its transpose
   const float* x;                       // [B,1,H,W]
   // parameters (views into the flat vector)
   const float *w0, *b0;                 // conv0 [25,1,7,7], [25]

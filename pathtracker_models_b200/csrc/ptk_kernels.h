@@ -30,6 +30,20 @@ struct WgradArgs {
   long long in_bs = 0, dy_bs = 0;    // elements between samples (0 = 32*H*W), as in ConvArgs
 };
 
+// wide recurrent convolutions on tcgen05 (ptk_convk_tc.cu; ConvLSTM): fp32 NCHW in / out, prepared bf16 hi/lo weight stream
+struct ConvKArgs {
+  const float* in;      // [B, Cin, H, W]
+  const void* wT;       // launch_prep_weights_k stream
+  const float* bias;    // [Cout] or null
+  const float* addend;  // [B, Cout, H, W] or null
+  float* out;           // [B, Cout, H, W]
+  int B, H, W, Cin, Cout, accumulate;
+  const float* skip = nullptr;   // RBP device state: skip[1] != 0 => do nothing
+};
+template <int KSZ> size_t convk_tc_weight_bytes(int transposed);
+template <int KSZ> int launch_prep_weights_k(const float* const* w, int transposed, void* dst, cudaStream_t st);
+template <int KSZ> int launch_convk_tc(const ConvKArgs& a, int transposed, cudaStream_t st);
+
 int conv_num_ctas(int B, int H, int W);
 int read_pw_stamps(unsigned long long* out);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);

@@ -8,10 +8,16 @@ from tests.golden_util import NOISE_MULT, REL_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _run(case):
+def _mode(conv_mode):
+    from pathtracker_models_b200 import _lib
+    return _lib.PTK_CONV_BF16X3 if conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
+
+
+def _run(case, conv_mode="bf16x3"):
     from pathtracker_models_b200 import convlstm
     B, T, H, W = case["shape"]
     m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"])
+    m.conv_mode = _mode(conv_mode)
     m.load_state_dict(case["sd"])
     m = m.cuda().train()
     out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
@@ -19,10 +25,12 @@ def _run(case):
     return m, out, pen, loss
 
 
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("name", ["convlstm_k7_small", "convlstm_k15_small", "convlstm_k15_b3"])
-def test_convlstm_output_penalty_and_grads(name):
+def test_convlstm_output_penalty_and_grads(name, conv_mode):
+    """both precisions of the per-step convolutions: tcgen05 split-bf16 (default) and strict fp32 on CUDA cores"""
     case = load_convlstm_case(name)
-    m, out, pen, loss = _run(case)
+    m, out, pen, loss = _run(case, conv_mode)
     B, T, H, W = case["shape"]
     assert out.shape == (B, 2, H, W) and pen.shape == (B, 25, H, W)
     assert rel_err(out, case["output"]) < REL_TOL
@@ -53,8 +61,9 @@ def test_convlstm_eval_mode_and_determinism():
     assert rel_err(o1, case["output"]) < REL_TOL
 
 
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
 @pytest.mark.parametrize("name", ["convlstm_k7_rbp", "convlstm_k7_rbp_trunc"])
-def test_convlstm_rbp_grads_vs_reference(name):
+def test_convlstm_rbp_grads_vs_reference(name, conv_mode):
     """recurrent back-propagation: CUDA Neumann series vs the reference's own outputs."""
     import os
     import numpy as np
@@ -67,6 +76,7 @@ def test_convlstm_rbp_grads_vs_reference(name):
     num_iter = int(z["num_iter"])
     B, T, H, W = case["shape"]
     m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method='rbp', num_iter=num_iter)
+    m.conv_mode = _mode(conv_mode)
     m.load_state_dict(case["sd"])
     m = m.cuda().train()
     out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
