@@ -347,12 +347,14 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   float* rbp_state = cv.take<float>(64);
   double* rbp_part = cv.take<double>(2 * 148 * 2);
   uint8_t *whF_tc = nullptr, *whD_tc = nullptr;
+  float* slots_h_tc = nullptr;
   if (dm->conv_mode != PTK_CONV_FP32) {
+    slots_h_tc = cv.take<float>(wgradk_tc_slot_floats(dm->K));
     whF_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(0) : convk_tc_weight_bytes<7>(0));
     whD_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));
   }
   if (d) {
-    d->whF_tc = whF_tc; d->whD_tc = whD_tc; d->conv_mode = dm->conv_mode;
+    d->whF_tc = whF_tc; d->whD_tc = whD_tc; d->conv_mode = dm->conv_mode; d->slots_h_tc = slots_h_tc;
     d->rbp_g = rbp_g; d->rbp_state = rbp_state; d->rbp_part = rbp_part;
     d->groups = groups;
     d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;

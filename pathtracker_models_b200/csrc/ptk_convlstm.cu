@@ -163,6 +163,13 @@ static int recurrent_conv(const LstmDev& d, const ConvGArgs& g, bool transposed,
   return launch_convk_tc<KS>(k, transposed ? 1 : 0, st);
 }
 template <int KS>
+static int recurrent_wgrad(const LstmDev& d, const WgradGArgs& g, cudaStream_t st) {
+  if (d.conv_mode == PTK_CONV_FP32) return launch_wgradg<KS>(g, st);
+  WgradKArgs k{g.in, g.dy, d.slots_h_tc, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, nullptr};
+  ProfileScope ps(PTK_PROF_WGRAD, st);
+  return launch_wgradk_tc<KS>(k, st);
+}
+template <int KS>
 static int recurrent_prep(const LstmDev& d, bool transposed, cudaStream_t st) {
   if (d.conv_mode == PTK_CONV_FP32) return PTK_OK;
   return launch_prep_weights_k<KS>(d.wh, transposed ? 1 : 0, transposed ? d.whD_tc : d.whF_tc, st);
@@ -248,7 +255,7 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
       PTK_LAUNCH_OK("lstm_bwd_kernel");
     }
     WgradGArgs w{d.h_at(t - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, !first};
-    if ((rc = launch_wgradg<KS>(w, st))) return rc;
+    if ((rc = recurrent_wgrad<KS>(d, w, st))) return rc;
     if (t > 1) {
       ConvGArgs c{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0};
       if ((rc = recurrent_conv<KS>(d, c, true, st))) return rc;
@@ -321,7 +328,9 @@ static int convlstm_grad_tail(const LstmDev& d, cudaStream_t st) {
   const long long per_gate = (long long)LC * LC * taps + LC + (long long)LC * LC * taps;   // Wx.w, Wx.b, Wh.w
   fold_slots_kernel<<<(LC * 49 + 255) / 256, 256, 0, st>>>(d.slots_0, d.groups, LC, 1, 49, d.dparams + d.off_w0, 0, LC);
   fold_slots_kernel<<<(LG * LC * taps + 255) / 256, 256, 0, st>>>(d.slots_x, d.groups, LG, LC, taps, d.dparams + d.off_wx, per_gate, LC);
-  fold_slots_kernel<<<(LG * LC * taps + 255) / 256, 256, 0, st>>>(d.slots_h, d.groups, LG, LC, taps, d.dparams + d.off_wh, per_gate, LC);
+  if (d.conv_mode == PTK_CONV_FP32)
+    fold_slots_kernel<<<(LG * LC * taps + 255) / 256, 256, 0, st>>>(d.slots_h, d.groups, LG, LC, taps, d.dparams + d.off_wh, per_gate, LC);
+  else if ((rc = launch_fold_wgradk(d.slots_h_tc, KS, 4, LC, LC, d.dparams + d.off_wh, per_gate, st))) return rc;
   PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_b0, d.b0_grad, LC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   for (int k = 0; k < 4; ++k)
     PTK_CUDA_OK(cudaMemcpyAsync(d.dparams + d.off_bx + k * per_gate, d.bx_grad + k * LC, LC * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -358,7 +367,7 @@ static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t 
   lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(d.rbp_g, 0.f, nullptr, 0.f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
                                            nullptr, d.delta_sum, 1, d.B, P);
   WgradGArgs w{d.h_at(T - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, 0};
-  if ((rc = launch_wgradg<KS>(w, st))) return rc;
+  if ((rc = recurrent_wgrad<KS>(d, w, st))) return rc;
   return convlstm_grad_tail<KS>(d, st);
 }
 

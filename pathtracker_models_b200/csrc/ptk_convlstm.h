@@ -7,6 +7,7 @@ namespace ptk {
 
 struct LstmDev {
   int B, T, H, W, KS, groups, conv_mode;
+  float* slots_h_tc;                    // tensor-core weight-gradient slots of Wh (ptk_wgradk_tc.cu)
   void *whF_tc, *whD_tc;                // tensor-core weight streams of the recurrent convolution / its transpose
   const float* x;                       // [B,1,H,W]
   // parameters (views into the flat vector)

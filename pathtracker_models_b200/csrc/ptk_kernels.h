@@ -44,6 +44,19 @@ template <int KSZ> size_t convk_tc_weight_bytes(int transposed);
 template <int KSZ> int launch_prep_weights_k(const float* const* w, int transposed, void* dst, cudaStream_t st);
 template <int KSZ> int launch_convk_tc(const ConvKArgs& a, int transposed, cudaStream_t st);
 
+// weight gradient of the same convolution on tcgen05 (ptk_wgradk_tc.cu): slots [groups][KS*KS][128][32], folded at the end
+struct WgradKArgs {
+  const float* in;      // [B, Cin <= 32, H, W]
+  const float* dy;      // [B, Cout <= 128, H, W]
+  float* slots;         // wgradk_tc_slot_floats(KS) floats
+  int B, H, W, Cin, Cout, accumulate;
+  const float* skip = nullptr;
+};
+int wgradk_tc_groups(int ks);
+size_t wgradk_tc_slot_floats(int ks);
+template <int KSZ> int launch_wgradk_tc(const WgradKArgs& a, cudaStream_t st);
+int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, float* dst0, long long stride_between, cudaStream_t st);
+
 int conv_num_ctas(int B, int H, int W);
 int read_pw_stamps(unsigned long long* out);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);

@@ -1,0 +1,236 @@
+// Tensor-core weight gradient of the ConvLSTM's recurrent convolution (tcgen05 / TMEM):
+//
+//   dWh[n = gate*25 + oc][ic][ky][kx] += sum_{b,y,x} delta[b,n,y,x] * h[b,ic,y+ky-P,x+kx-P]      (autograd of models/convlstm.py:84-87)
+//
+// GEMM per tap: D[m = n (128 >= 100)][ic (32 >= 25)] = sum_{k = pixel} delta[k][m] * h[k + shift(tap)][ic]; pixels are the
+// K axis, both operands MN-major views of channel-chunk planar tiles ([8-channel plane][pixel][8 ch], ptk_wgrad_tc.cu).
+// The gradient of one tap is a 128 x 32 fp32 block = 32 TMEM columns, so one kernel ROW (KS taps) fits in TMEM and the
+// whole gradient (KS rows) does not.  Hence the work split: a CTA owns ONE kernel row ky and a strided share of the
+// pixel tiles (4 rows x 32 columns of one sample), keeps its KS accumulators in TMEM across all of its tiles and writes
+// them once at the end (read-add-write of its private slot: deterministic, no atomics).  For a fixed ky the h tile needs
+// no row halo (4 rows shifted by ky - P), so a tile's operands are small (88 KB) and double-buffered: warps 2-7 stage
+// tile i+1 (fp32 -> bf16 hi/lo split) while warp 1 issues the MMAs of tile i.
+//   per (tap, 16-pixel K-step): three M = 128, N = 32 instructions  dh*hh + dh*hl + dl*hh  (3-pass split, as everywhere).
+#include <cuda_bf16.h>
+
+#include "ptk_common.cuh"
+#include "ptk_kernels.h"
+#include "ptk_tc.cuh"
+
+namespace ptk {
+
+template <int KS_>
+struct WgK {
+  static constexpr int KSZ = KS_, PAD = KS_ / 2;
+  static constexpr int TH = 4, TW = 32, KPIX = TH * TW, KSTEPS = KPIX / 16;
+  static constexpr int WP = TW + KSZ - 1;                     // padded pitch of the h tile
+  static constexpr int DY_PLANE = KPIX * 16 + 16;             // +16 B: the planes of one K row start in different bank groups
+  static constexpr int IN_NPIX = TH * WP;
+  static constexpr int IN_PLANE = IN_NPIX * 16 + 16;
+  static constexpr int DY_BYTES = 32 * DY_PLANE;              // 16 hi planes (128 channels) + 16 lo planes
+  static constexpr int IN_BYTES = 8 * IN_PLANE;               // 4 hi + 4 lo planes
+  static constexpr int BUF = DY_BYTES + IN_BYTES;
+  static constexpr int SMEM = 2 * BUF + 128;
+  static constexpr int TCOLS = KSZ * 32 <= 256 ? 256 : 512;
+  static_assert(KSZ * 32 <= 512, "one kernel row of accumulators must fit in TMEM");
+  static_assert(BUF % 16 == 0 && SMEM <= 232448, "shared memory");
+};
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both MN-major, M = 128, N = 32
+__host__ __device__ constexpr uint32_t wgk_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <class K>
+__global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
+  if (a.skip != nullptr && a.skip[1] != 0.f) return;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * K::BUF);
+  uint64_t* full = bars;           // [2] tile staged (192 arrivals)
+  uint64_t* empty = bars + 2;      // [2] MMAs of the tile retired (tcgen05.commit)
+  uint64_t* accum_bar = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int ky = blockIdx.y, R = gridDim.x, r0 = blockIdx.x;
+  const int H = a.H, W = a.W, tilesX = W / K::TW, tilesY = H / K::TH, nTiles = a.B * tilesX * tilesY;
+  const size_t HW = (size_t)H * W;
+  const int myTiles = r0 < nTiles ? (nTiles - r0 + R - 1) / R : 0;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 192); mbar_init(&full[1], 192);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(K::TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < 2 * K::BUF / 16; i += 256) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 1) {
+    // ---- MMA issuer ----------------------------------------------------------------------------------------
+    constexpr uint32_t IDESC = wgk_idesc();
+    for (int i = 0; i < myTiles; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&full[buf], (uint32_t)((i >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sDY = smem_u32(smem_raw + buf * K::BUF), sIN = sDY + K::DY_BYTES;
+      // MN-major no-swizzle descriptors: LBO = 128 B between 8-pixel K groups, SBO = plane stride between 8-channel groups
+      const uint64_t dAh = umma_desc(sDY, 128, K::DY_PLANE), dAl = umma_desc(sDY + 16 * K::DY_PLANE, 128, K::DY_PLANE);
+      const uint64_t dBh = umma_desc(sIN, 128, K::IN_PLANE), dBl = umma_desc(sIN + 4 * K::IN_PLANE, 128, K::IN_PLANE);
+#pragma unroll 1
+      for (int kx = 0; kx < K::KSZ; ++kx) {
+        const uint32_t dcol = tmem_base + (uint32_t)(kx * 32);
+#pragma unroll 2
+        for (int ks = 0; ks < K::KSTEPS; ++ks) {
+          // K-step = 16 consecutive pixels of one tile row: delta compact (pitch 32), h padded (pitch WP) shifted by kx
+          const uint32_t ao = (uint32_t)(ks * 16), bo = (uint32_t)((ks >> 1) * K::WP + (ks & 1) * 16 + kx);
+          if (elect_one()) {
+            umma_bf16(dcol, dAh + ao, dBh + bo, IDESC, (i | ks) ? 1u : 0u);
+            umma_bf16(dcol, dAh + ao, dBl + bo, IDESC, 1u);
+            umma_bf16(dcol, dAl + ao, dBh + bo, IDESC, 1u);
+          }
+        }
+      }
+      __syncwarp();
+      if (elect_one()) umma_commit(&empty[buf]);
+    }
+    __syncwarp();
+    if (elect_one()) umma_commit(accum_bar);
+  } else if (warp >= 2) {
+    // ---- staging warps ----------------------------------------------------------------------------------------
+    const int stid = tid - 64;
+    for (int i = 0; i < myTiles; ++i) {
+      const int buf = i & 1;
+      if (i >= 2) mbar_wait(&empty[buf], (uint32_t)(((i >> 1) - 1) & 1));
+      const int tile = r0 + i * R;
+      const int b = tile / (tilesX * tilesY), trem = tile - b * (tilesX * tilesY), y0 = (trem / tilesX) * K::TH, x0 = (trem % tilesX) * K::TW;
+      uint8_t* sDY = smem_raw + buf * K::BUF;
+      uint8_t* sIN = sDY + K::DY_BYTES;
+      // delta tile: planes 0..ceil(Cout/8)-1, 4 rows x 8 four-pixel groups; channels >= Cout are zero
+      const float* dyb = a.dy + (size_t)b * a.Cout * HW;
+      const int nplanes = (a.Cout + 7) / 8;
+      for (int it = stid; it < nplanes * K::TH * 8; it += 192) {
+        const int q = it / (K::TH * 8), rem = it - q * (K::TH * 8), row = rem >> 3, g = rem & 7;
+        float4 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q * 8 + e < a.Cout) v[e] = *reinterpret_cast<const float4*>(dyb + (size_t)(q * 8 + e) * HW + (size_t)(y0 + row) * W + x0 + 4 * g);
+        }
+        const int p = row * K::TW + 4 * g;
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(reinterpret_cast<const float*>(&v[2 * e])[px], h0, l0);
+            split_bf16(reinterpret_cast<const float*>(&v[2 * e + 1])[px], h1, l1);
+            hi[e] = pack_bf16x2(h0, h1);
+            lo[e] = pack_bf16x2(l0, l1);
+          }
+          *reinterpret_cast<uint4*>(sDY + q * K::DY_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sDY + (16 + q) * K::DY_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      // h tile: 4 rows shifted by ky - PAD, WP columns (x0 - PAD ...), 4 planes; zero outside the image / beyond Cin
+      const float* inb = a.in + (size_t)b * a.Cin * HW;
+      for (int it = stid; it < 4 * K::TH * K::WP; it += 192) {
+        const int q = it / (K::TH * K::WP), rem = it - q * (K::TH * K::WP), row = rem / K::WP, c = rem - row * K::WP;
+        const int gy = y0 + row + ky - K::PAD, gx = x0 + c - K::PAD;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float v0 = 0.f, v1 = 0.f;
+          if (ok && q * 8 + 2 * e < a.Cin) v0 = inb[(size_t)(q * 8 + 2 * e) * HW + (size_t)gy * W + gx];
+          if (ok && q * 8 + 2 * e + 1 < a.Cin) v1 = inb[(size_t)(q * 8 + 2 * e + 1) * HW + (size_t)gy * W + gx];
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v0, h0, l0);
+          split_bf16(v1, h1, l1);
+          hi[e] = pack_bf16x2(h0, h1);
+          lo[e] = pack_bf16x2(l0, l1);
+        }
+        const int p = row * K::WP + c;
+        *reinterpret_cast<uint4*>(sIN + q * K::IN_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sIN + (4 + q) * K::IN_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&full[buf]);
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue: the CTA's KS accumulators -> its slot [r0][ky*KS + kx][128][32] ----------------------------------
+  if (myTiles > 0) {
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quad = warp & 3, par = warp >> 2;
+    float* slot = a.slots + ((size_t)r0 * K::KSZ * K::KSZ + (size_t)ky * K::KSZ) * 4096 + (size_t)(quad * 32 + lane) * 32;
+#pragma unroll 1
+    for (int kx = par; kx < K::KSZ; kx += 2) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kx * 32), v);
+      float4* dst = reinterpret_cast<float4*>(slot + (size_t)kx * 4096);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 t = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (a.accumulate) { const float4 p = dst[i]; t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w; }
+        dst[i] = t;
+      }
+    }
+  } else if (!a.accumulate) {   // a CTA without tiles still owns a slot: define it
+    float* slot = a.slots + ((size_t)r0 * K::KSZ * K::KSZ + (size_t)ky * K::KSZ) * 4096;
+    for (int i = tid; i < K::KSZ * 4096; i += 256) slot[i] = 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(K::TCOLS));
+}
+
+// slots [R][taps][128][32] -> the `nbank` stacked [ocb][icb][taps] tensors inside dparams (double-precision fold, fixed order)
+__global__ void fold_wgradk_kernel(const float* __restrict__ slots, int R, int taps, int nbank, int ocb, int icb, float* dst0,
+                                   long long stride_between) {
+  const int total = nbank * ocb * icb * taps;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int tap = i % taps, ic = (i / taps) % icb, n = i / (taps * icb);
+  double s = 0;
+  for (int r = 0; r < R; ++r) s += slots[(((size_t)r * taps + tap) * 128 + n) * 32 + ic];
+  dst0[(size_t)(n / ocb) * stride_between + ((size_t)(n % ocb) * icb + ic) * taps + tap] = (float)s;
+}
+
+int wgradk_tc_groups(int ks) { return 148 / ks; }
+size_t wgradk_tc_slot_floats(int ks) { return (size_t)wgradk_tc_groups(ks) * ks * ks * 4096; }
+
+template <int KSZ>
+int launch_wgradk_tc(const WgradKArgs& a, cudaStream_t st) {
+  using K = WgK<KSZ>;
+  if (a.H % K::TH || a.W % K::TW || a.Cin > 32 || a.Cout > 128) {
+    set_error("wgradk_tc: unsupported problem H=%d W=%d Cin=%d Cout=%d", a.H, a.W, a.Cin, a.Cout);
+    return PTK_EINVAL;
+  }
+  PTK_CUDA_OK(ptk_func_smem(wgradk_tc_kernel<K>, K::SMEM));
+  wgradk_tc_kernel<K><<<dim3(wgradk_tc_groups(KSZ), KSZ), 256, K::SMEM, st>>>(a);
+  PTK_LAUNCH_OK("wgradk_tc_kernel");
+  return PTK_OK;
+}
+template int launch_wgradk_tc<7>(const WgradKArgs&, cudaStream_t);
+template int launch_wgradk_tc<15>(const WgradKArgs&, cudaStream_t);
+
+int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, float* dst0, long long stride_between, cudaStream_t st) {
+  const int total = nbank * ocb * icb * ks * ks;
+  fold_wgradk_kernel<<<(total + 255) / 256, 256, 0, st>>>(slots, wgradk_tc_groups(ks), ks * ks, nbank, ocb, icb, dst0, stride_between);
+  PTK_LAUNCH_OK("fold_wgradk_kernel");
+  return PTK_OK;
+}
+
+}  // namespace ptk
