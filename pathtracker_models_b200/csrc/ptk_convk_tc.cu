@@ -19,6 +19,7 @@
 //   * weights stream through a cp.async.bulk + mbarrier ring in "units" (one B operand: NT rows x 32 k, hi then lo);
 //     warp 0 = producer, warp 1 = MMA issuer (one elected lane), warps 2-7 = staging; all 8 warps run the epilogue.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "ptk_common.cuh"
 #include "ptk_kernels.h"
@@ -44,7 +45,8 @@ struct ConvK {
   static constexpr int STAGE = G * UNIT_BYTES;
   static constexpr int NST = (STAGE * 6 + A_BYTES + 512 <= 232448) ? 6 : ((STAGE * 4 + A_BYTES + 512 <= 232448) ? 4 : 3);
   static constexpr int SMEM = A_BYTES + NST * STAGE + 256;
-  static constexpr int DCOLS = MT * NT;
+  static constexpr int DSTRIDE = (NT + 31) & ~31;           // TMEM columns between M-tiles: accumulators start on 32-column boundaries
+  static constexpr int DCOLS = MT * DSTRIDE;
   static constexpr int TCOLS = DCOLS <= 128 ? 128 : (DCOLS <= 256 ? 256 : 512);
   static constexpr int SP = MT * 128 + 4;                   // pitch (floats) of the realignment tile
   static_assert(KSZ % NSTACK == 0, "taps per row must split into whole stacks");
@@ -52,7 +54,7 @@ struct ConvK {
   static_assert(NT % 16 == 0 && NT <= 256, "UMMA N constraint for M = 128");
   static_assert(DCOLS <= 512, "TMEM columns");
   static_assert(SMEM <= 232448, "shared memory");
-  static_assert(NSTACK == 1 || 32 * SP * 4 <= A_BYTES, "realignment tile must fit in the operand image");
+  static_assert(32 * SP * 4 <= A_BYTES, "epilogue tile must fit in the operand image");
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -151,8 +153,8 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
               const uint32_t aL = aLoW + ((aLo + (uint32_t)(2 * s) * K::PLANE) >> 4) + po;
               const uint32_t kadv = (uint32_t)(s * ((2 * K::NT * 16) >> 4));
               const uint64_t dBh = ((uint64_t)bHiW << 32) | (bH + kadv), dBl = ((uint64_t)bHiW << 32) | (bL + kadv);
-              const uint32_t dcol = tmem_base + (uint32_t)(j * K::NT);
-              if (elect_one()) {
+              const uint32_t dcol = tmem_base + (uint32_t)(j * K::DSTRIDE);
+              if (a.dbg != 2 && elect_one()) {
                 umma_bf16(dcol, ((uint64_t)aHiW << 32) | aH, dBh, IDESC, (first_unit && s == 0) ? 0u : 1u);
                 umma_bf16(dcol, ((uint64_t)aHiW << 32) | aH, dBl, IDESC, 1u);
                 umma_bf16(dcol, ((uint64_t)aHiW << 32) | aL, dBh, IDESC, 1u);
@@ -234,63 +236,48 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
   const int quad = warp & 3, jpar = warp >> 2;
   float* outb = a.out + (size_t)b * a.Cout * HW;
   const float* addb = a.addend ? a.addend + (size_t)b * a.Cout * HW : nullptr;
-  if (K::NSTACK == 1) {
-    // direct: lane = padded pixel m; for a fixed channel the 32 lanes of a warp write one row segment
-#pragma unroll 1
-    for (int j = jpar; j < K::MT; j += 2) {
-      const int m = j * 128 + quad * 32 + lane, row = m / K::WP, col = m - row * K::WP;
-      const bool ok = row < K::TH && col < K::TW;
-      const size_t pix = (size_t)(y0 + row) * W + x0 + col;
-#pragma unroll 1
-      for (int cb = 0; cb < K::NT / 16; ++cb) {
-        if (cb * 16 >= a.Cout) break;   // warp-uniform
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * K::NT + cb * 16), v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = cb * 16 + i;
-          if (ok && n < a.Cout) {
-            float r = v[i];
-            if (a.bias) r += a.bias[n];
-            if (addb) r += addb[(size_t)n * HW + pix];
-            if (a.accumulate) r += outb[(size_t)n * HW + pix];
-            outb[(size_t)n * HW + pix] = r;
-          }
-        }
-      }
-    }
-  } else {
-    // stacked taps: out[m] = D0[m] + D1[m+1] + D2[m+2]; three phases through a [32][SP] tile in the dead operand image
+  // TMEM -> [channel][padded pixel] tile in the (dead) operand image -> coalesced 16-byte global accesses, CH channels per
+  // pass.  Stacked taps (NSTACK = 3) are realigned on the way: out[m] = D0[m] + D1[m+1] + D2[m+2], one phase per block.
+  // (A first version stored straight from the TMEM registers, one 4-byte element per lane and channel: 108 us per CTA.)
+  {
     float* sS = reinterpret_cast<float*>(sA);
-    constexpr int NCH = K::NT / K::NSTACK;   // 32
+    constexpr int NCH = K::NT / K::NSTACK;
+    constexpr int CH = (NCH > 32 && K::A_BYTES >= 64 * K::SP * 4) ? 64 : 32;
 #pragma unroll 1
-    for (int dl = 0; dl < K::NSTACK; ++dl) {
+    for (int c0 = 0; c0 < a.Cout && a.dbg != 1; c0 += CH) {
 #pragma unroll 1
-      for (int j = jpar; j < K::MT; j += 2) {
-        const int m = j * 128 + quad * 32 + lane - dl;
+      for (int dl = 0; dl < K::NSTACK; ++dl) {
 #pragma unroll 1
-        for (int cb = 0; cb < NCH / 16; ++cb) {
-          float v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * K::NT + dl * NCH + cb * 16), v);
-          if (m >= 0) {
+        for (int j = jpar; j < K::MT; j += 2) {
+          const int m = j * 128 + quad * 32 + lane - dl;
+#pragma unroll 1
+          for (int cb = 0; cb < CH / 16; ++cb) {
+            if (c0 + cb * 16 >= NCH) break;   // warp-uniform
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * K::DSTRIDE + dl * NCH + c0 + cb * 16), v);
+            if (m >= 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float* p = sS + (cb * 16 + i) * K::SP + m;
-              *p = dl ? (*p + v[i]) : v[i];
+              for (int i = 0; i < 16; ++i) {
+                float* p = sS + (cb * 16 + i) * K::SP + m;
+                *p = dl ? (*p + v[i]) : v[i];
+              }
             }
           }
         }
+        __syncthreads();
+      }
+      const int nc = min(CH, a.Cout - c0);
+      for (int it = tid; it < nc * K::TH * (K::TW / 4); it += 256) {
+        const int n = it / (K::TH * (K::TW / 4)), rem = it - n * (K::TH * (K::TW / 4)), row = rem / (K::TW / 4), g = rem % (K::TW / 4);
+        const float* src = sS + n * K::SP + row * K::WP + 4 * g;
+        float4 r = make_float4(src[0], src[1], src[2], src[3]);
+        const size_t off = (size_t)(c0 + n) * HW + (size_t)(y0 + row) * W + x0 + 4 * g;
+        if (addb) { const float4 t = __ldg(reinterpret_cast<const float4*>(addb + off)); r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+        if (a.accumulate) { const float4 t = *reinterpret_cast<const float4*>(outb + off); r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w; }
+        if (a.bias) { const float t = __ldg(a.bias + c0 + n); r.x += t; r.y += t; r.z += t; r.w += t; }
+        *reinterpret_cast<float4*>(outb + off) = r;
       }
       __syncthreads();
-    }
-    for (int it = tid; it < a.Cout * K::TH * K::TW; it += 256) {
-      const int n = it / (K::TH * K::TW), rem = it - n * (K::TH * K::TW), row = rem / K::TW, col = rem % K::TW;
-      const size_t pix = (size_t)(y0 + row) * W + x0 + col;
-      float r = sS[n * K::SP + row * K::WP + col];
-      if (a.bias) r += a.bias[n];
-      if (addb) r += addb[(size_t)n * HW + pix];
-      if (a.accumulate) r += outb[(size_t)n * HW + pix];
-      outb[(size_t)n * HW + pix] = r;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -361,15 +348,29 @@ template int launch_prep_weights_k<15>(const float* const*, int, void*, cudaStre
 
 // forward: Cin <= 32 (25), Cout <= 112 (100);  transposed: Cin <= 128 (100), Cout <= 32 (25)
 template <int KSZ>
-int launch_convk_tc(const ConvKArgs& a, int transposed, cudaStream_t st) {
+int launch_convk_tc(const ConvKArgs& a_in, int transposed, cudaStream_t st) {
+  ConvKArgs a = a_in;
+  static const int exp_d = getenv("PTK_CONVK_DBG") ? atoi(getenv("PTK_CONVK_DBG")) : 0;
+  a.dbg = exp_d;
   using F = ConvK<KSZ, 112, 1>;
   using D = ConvK<KSZ, (KSZ % 3 == 0) ? 96 : 32, (KSZ % 3 == 0) ? 3 : 1>;
   if (a.H % 8 || a.W % 32) { set_error("convk_tc: H %% 8 / W %% 32 violated (%d x %d)", a.H, a.W); return PTK_EINVAL; }
   dim3 grid(a.W / 32, a.H / 8, a.B);
   if (!transposed) {
     if (a.Cin > 32 || a.Cout > F::NT) { set_error("convk_tc forward: %d -> %d channels unsupported", a.Cin, a.Cout); return PTK_EINVAL; }
+    static const int exp_n = getenv("PTK_CONVK_EXP") ? atoi(getenv("PTK_CONVK_EXP")) : 0;   // timing experiments only (wrong results)
+    if (KSZ == 15 && exp_n == 96) {
+      using X = ConvK<15, 96, 1>;
+      PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<X>, X::SMEM));
+      convk_tc_kernel<X><<<grid, 256, X::SMEM, st>>>(a);
+    } else if (KSZ == 15 && exp_n == 128) {
+      using X = ConvK<15, 128, 1>;
+      PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<X>, X::SMEM));
+      convk_tc_kernel<X><<<grid, 256, X::SMEM, st>>>(a);
+    } else {
     PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<F>, F::SMEM));
     convk_tc_kernel<F><<<grid, 256, F::SMEM, st>>>(a);
+    }
   } else {
     if (a.Cin > 128 || a.Cout > D::NT / D::NSTACK) { set_error("convk_tc transposed: %d -> %d channels unsupported", a.Cin, a.Cout); return PTK_EINVAL; }
     PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<D>, D::SMEM));

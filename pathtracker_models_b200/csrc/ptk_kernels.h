@@ -39,6 +39,7 @@ struct ConvKArgs {
   float* out;           // [B, Cout, H, W]
   int B, H, W, Cin, Cout, accumulate;
   const float* skip = nullptr;   // RBP device state: skip[1] != 0 => do nothing
+  int dbg = 0;                   // timing experiments (PTK_CONVK_EXP): 1 = no epilogue stores, 2 = no MMAs
 };
 template <int KSZ> size_t convk_tc_weight_bytes(int transposed);
 template <int KSZ> int launch_prep_weights_k(const float* const* w, int transposed, void* dst, cudaStream_t st);

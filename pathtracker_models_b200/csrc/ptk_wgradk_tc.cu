@@ -10,7 +10,10 @@
 // them once at the end (read-add-write of its private slot: deterministic, no atomics).  For a fixed ky the h tile needs
 // no row halo (4 rows shifted by ky - P), so a tile's operands are small (88 KB) and double-buffered: warps 2-7 stage
 // tile i+1 (fp32 -> bf16 hi/lo split) while warp 1 issues the MMAs of tile i.
-//   per (tap, 16-pixel K-step): three M = 128, N = 32 instructions  dh*hh + dh*hl + dl*hh  (3-pass split, as everywhere).
+//   per (tap PAIR, 16-pixel K-step): three M = 128, N = 64 instructions  dh*hh + dh*hl + dl*hh  (3-pass split, as
+//   everywhere).  N = 64 = [tap kx | tap kx+1]: the h tile is stored twice, the second copy shifted by one pixel, so that
+//   the second 32 columns of the B operand are the neighbouring tap (an M = 128, N = 32 instruction is bound by the 4 KB
+//   A read; the pair costs 6 KB instead of 2 x 5 KB).
 #include <cuda_bf16.h>
 
 #include "ptk_common.cuh"
@@ -25,20 +28,21 @@ struct WgK {
   static constexpr int TH = 4, TW = 32, KPIX = TH * TW, KSTEPS = KPIX / 16;
   static constexpr int WP = TW + KSZ - 1;                     // padded pitch of the h tile
   static constexpr int DY_PLANE = KPIX * 16 + 16;             // +16 B: the planes of one K row start in different bank groups
-  static constexpr int IN_NPIX = TH * WP;
+  static constexpr int IN_NPIX = TH * WP + 2;                 // +2: the odd partner tap of the last pair reads one pixel further
   static constexpr int IN_PLANE = IN_NPIX * 16 + 16;
   static constexpr int DY_BYTES = 32 * DY_PLANE;              // 16 hi planes (128 channels) + 16 lo planes
-  static constexpr int IN_BYTES = 8 * IN_PLANE;               // 4 hi + 4 lo planes
+  static constexpr int IN_BYTES = 16 * IN_PLANE;              // [hh | hh shifted by one pixel | hl | hl shifted], 4 planes each
   static constexpr int BUF = DY_BYTES + IN_BYTES;
   static constexpr int SMEM = 2 * BUF + 128;
-  static constexpr int TCOLS = KSZ * 32 <= 256 ? 256 : 512;
-  static_assert(KSZ * 32 <= 512, "one kernel row of accumulators must fit in TMEM");
+  static constexpr int NPAIR = (KSZ + 1) / 2;                 // taps are processed in horizontally adjacent pairs (N = 64)
+  static constexpr int TCOLS = NPAIR * 64 <= 256 ? 256 : 512;
+  static_assert(NPAIR * 64 <= 512, "one kernel row of accumulators must fit in TMEM");
   static_assert(BUF % 16 == 0 && SMEM <= 232448, "shared memory");
 };
 
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both MN-major, M = 128, N = 32
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both MN-major, M = 128, N = 64
 __host__ __device__ constexpr uint32_t wgk_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 template <class K>
@@ -84,14 +88,15 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
       const uint32_t sDY = smem_u32(smem_raw + buf * K::BUF), sIN = sDY + K::DY_BYTES;
       // MN-major no-swizzle descriptors: LBO = 128 B between 8-pixel K groups, SBO = plane stride between 8-channel groups
       const uint64_t dAh = umma_desc(sDY, 128, K::DY_PLANE), dAl = umma_desc(sDY + 16 * K::DY_PLANE, 128, K::DY_PLANE);
-      const uint64_t dBh = umma_desc(sIN, 128, K::IN_PLANE), dBl = umma_desc(sIN + 4 * K::IN_PLANE, 128, K::IN_PLANE);
+      // B = 8 planes from hh (resp. hl) on: columns 0-31 = tap kx, columns 32-63 = the shifted copy = tap kx + 1
+      const uint64_t dBh = umma_desc(sIN, 128, K::IN_PLANE), dBl = umma_desc(sIN + 8 * K::IN_PLANE, 128, K::IN_PLANE);
 #pragma unroll 1
-      for (int kx = 0; kx < K::KSZ; ++kx) {
-        const uint32_t dcol = tmem_base + (uint32_t)(kx * 32);
+      for (int pr = 0; pr < K::NPAIR; ++pr) {
+        const uint32_t dcol = tmem_base + (uint32_t)(pr * 64);
 #pragma unroll 2
         for (int ks = 0; ks < K::KSTEPS; ++ks) {
           // K-step = 16 consecutive pixels of one tile row: delta compact (pitch 32), h padded (pitch WP) shifted by kx
-          const uint32_t ao = (uint32_t)(ks * 16), bo = (uint32_t)((ks >> 1) * K::WP + (ks & 1) * 16 + kx);
+          const uint32_t ao = (uint32_t)(ks * 16), bo = (uint32_t)((ks >> 1) * K::WP + (ks & 1) * 16 + 2 * pr);
           if (elect_one()) {
             umma_bf16(dcol, dAh + ao, dBh + bo, IDESC, (i | ks) ? 1u : 0u);
             umma_bf16(dcol, dAh + ao, dBl + bo, IDESC, 1u);
@@ -114,37 +119,73 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
       const int b = tile / (tilesX * tilesY), trem = tile - b * (tilesX * tilesY), y0 = (trem / tilesX) * K::TH, x0 = (trem % tilesX) * K::TW;
       uint8_t* sDY = smem_raw + buf * K::BUF;
       uint8_t* sIN = sDY + K::DY_BYTES;
-      // delta tile: planes 0..ceil(Cout/8)-1, 4 rows x 8 four-pixel groups; channels >= Cout are zero
+      // one list of 16-byte-vector items: delta (planes 0..ceil(Cout/8)-1, 4 rows x 8 four-pixel groups; channels >= Cout
+      // zero) followed by the interior of the h tile (4 planes; rows shifted by ky - PAD; zero outside the image / beyond
+      // Cin).  Two items per pass: 16 LDG.128 in flight per thread before the first conversion (L2-latency bound).
       const float* dyb = a.dy + (size_t)b * a.Cout * HW;
-      const int nplanes = (a.Cout + 7) / 8;
-      for (int it = stid; it < nplanes * K::TH * 8; it += 192) {
-        const int q = it / (K::TH * 8), rem = it - q * (K::TH * 8), row = rem >> 3, g = rem & 7;
-        float4 v[8];
+      const float* inb = a.in + (size_t)b * a.Cin * HW;
+      const int nDY = ((a.Cout + 7) / 8) * K::TH * 8, nIt = nDY + 4 * K::TH * 8;
+      for (int it0 = stid; it0 < nIt; it0 += 384) {
+        float4 v[2][8];
+        int dst[2];                       // byte offset of the item's first pixel inside its first plane, -1 = no item
+        bool isin[2];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q * 8 + e < a.Cout) v[e] = *reinterpret_cast<const float4*>(dyb + (size_t)(q * 8 + e) * HW + (size_t)(y0 + row) * W + x0 + 4 * g);
-        }
-        const int p = row * K::TW + 4 * g;
+        for (int r = 0; r < 2; ++r) {
+          const int it = it0 + 192 * r;
+          dst[r] = -1; isin[r] = false;
 #pragma unroll
-        for (int px = 0; px < 4; ++px) {
-          uint32_t hi[4], lo[4];
+          for (int e = 0; e < 8; ++e) v[r][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it < nDY) {
+            const int q = it / (K::TH * 8), rem = it - q * (K::TH * 8), row = rem >> 3, g = rem & 7;
+            dst[r] = q * K::DY_PLANE + (row * K::TW + 4 * g) * 16;
+            const float* src = dyb + (size_t)(q * 8) * HW + (size_t)(y0 + row) * W + x0 + 4 * g;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(reinterpret_cast<const float*>(&v[2 * e])[px], h0, l0);
-            split_bf16(reinterpret_cast<const float*>(&v[2 * e + 1])[px], h1, l1);
-            hi[e] = pack_bf16x2(h0, h1);
-            lo[e] = pack_bf16x2(l0, l1);
+            for (int e = 0; e < 8; ++e)
+              if (q * 8 + e < a.Cout) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * HW);
+          } else if (it < nIt) {
+            const int j = it - nDY, q = j / (K::TH * 8), rem = j - q * (K::TH * 8), row = rem >> 3, g = rem & 7;
+            const int gy = y0 + row + ky - K::PAD;
+            isin[r] = true;
+            dst[r] = q * K::IN_PLANE + (row * K::WP + K::PAD + 4 * g) * 16;
+            if (gy >= 0 && gy < H) {
+              const float* src = inb + (size_t)(q * 8) * HW + (size_t)gy * W + x0 + 4 * g;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (q * 8 + e < a.Cin) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * HW);
+            }
           }
-          *reinterpret_cast<uint4*>(sDY + q * K::DY_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(sDY + (16 + q) * K::DY_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (dst[r] < 0) continue;
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(reinterpret_cast<const float*>(&v[r][2 * e])[px], h0, l0);
+              split_bf16(reinterpret_cast<const float*>(&v[r][2 * e + 1])[px], h1, l1);
+              hi[e] = pack_bf16x2(h0, h1);
+              lo[e] = pack_bf16x2(l0, l1);
+            }
+            const uint4 uh = make_uint4(hi[0], hi[1], hi[2], hi[3]), ul = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (!isin[r]) {
+              *reinterpret_cast<uint4*>(sDY + dst[r] + px * 16) = uh;
+              *reinterpret_cast<uint4*>(sDY + 16 * K::DY_PLANE + dst[r] + px * 16) = ul;
+            } else {     // plane sets: hh, hh shifted (pixel p lands at p - 1; PAD >= 1 so p >= 1), hl, hl shifted
+              *reinterpret_cast<uint4*>(sIN + dst[r] + px * 16) = uh;
+              *reinterpret_cast<uint4*>(sIN + 4 * K::IN_PLANE + dst[r] + px * 16 - 16) = uh;
+              *reinterpret_cast<uint4*>(sIN + 8 * K::IN_PLANE + dst[r] + px * 16) = ul;
+              *reinterpret_cast<uint4*>(sIN + 12 * K::IN_PLANE + dst[r] + px * 16 - 16) = ul;
+            }
+          }
         }
       }
-      // h tile: 4 rows shifted by ky - PAD, WP columns (x0 - PAD ...), 4 planes; zero outside the image / beyond Cin
-      const float* inb = a.in + (size_t)b * a.Cin * HW;
-      for (int it = stid; it < 4 * K::TH * K::WP; it += 192) {
-        const int q = it / (K::TH * K::WP), rem = it - q * (K::TH * K::WP), row = rem / K::WP, c = rem - row * K::WP;
+      // halo columns of the h tile (always outside the image when W == 32)
+      for (int it = stid; it < 4 * K::TH * 2 * K::PAD; it += 192) {
+        const int q = it / (K::TH * 2 * K::PAD), rem = it - q * (K::TH * 2 * K::PAD), row = rem / (2 * K::PAD), hc = rem - row * (2 * K::PAD);
+        const int c = hc < K::PAD ? hc : (K::TW + hc);
         const int gy = y0 + row + ky - K::PAD, gx = x0 + c - K::PAD;
         const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
         uint32_t hi[4], lo[4];
@@ -160,8 +201,13 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
           lo[e] = pack_bf16x2(l0, l1);
         }
         const int p = row * K::WP + c;
-        *reinterpret_cast<uint4*>(sIN + q * K::IN_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(sIN + (4 + q) * K::IN_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        const uint4 uh = make_uint4(hi[0], hi[1], hi[2], hi[3]), ul = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(sIN + q * K::IN_PLANE + p * 16) = uh;
+        *reinterpret_cast<uint4*>(sIN + 8 * K::IN_PLANE + q * K::IN_PLANE + p * 16) = ul;
+        if (p >= 1) {
+          *reinterpret_cast<uint4*>(sIN + (4 + q) * K::IN_PLANE + (p - 1) * 16) = uh;
+          *reinterpret_cast<uint4*>(sIN + (12 + q) * K::IN_PLANE + (p - 1) * 16) = ul;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&full[buf]);
