@@ -346,15 +346,19 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   float* rbp_g = cv.take<float>(S);
   float* rbp_state = cv.take<float>(64);
   double* rbp_part = cv.take<double>(2 * 148 * 2);
-  uint8_t *whF_tc = nullptr, *whD_tc = nullptr;
-  float* slots_h_tc = nullptr;
+  uint8_t *whF_tc = nullptr, *whD_tc = nullptr, *wxF_tc = nullptr, *wxD_tc = nullptr;
+  float *slots_h_tc = nullptr, *slots_x_tc = nullptr;
   if (dm->conv_mode != PTK_CONV_FP32) {
     slots_h_tc = cv.take<float>(wgradk_tc_slot_floats(dm->K));
+    slots_x_tc = cv.take<float>(wgradk_tc_slot_floats(dm->K));
+    wxF_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(0) : convk_tc_weight_bytes<7>(0));
+    wxD_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));
     whF_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(0) : convk_tc_weight_bytes<7>(0));
     whD_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));
   }
   if (d) {
     d->whF_tc = whF_tc; d->whD_tc = whD_tc; d->conv_mode = dm->conv_mode; d->slots_h_tc = slots_h_tc;
+    d->slots_x_tc = slots_x_tc; d->wxF_tc = wxF_tc; d->wxD_tc = wxD_tc;
     d->rbp_g = rbp_g; d->rbp_state = rbp_state; d->rbp_part = rbp_part;
     d->groups = groups;
     d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
           for (int j = 0; j < K::MT; ++j) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
+              if (kb * 32 + s * 16 >= a.Cin) continue;   // all-zero K-step (channels 112-127 of the 100-channel transpose)
               const uint32_t po = poff + (uint32_t)(j * 128);
               const uint32_t aH = aLoW + ((aHi + (uint32_t)(2 * s) * K::PLANE) >> 4) + po;
               const uint32_t aL = aLoW + ((aLo + (uint32_t)(2 * s) * K::PLANE) >> 4) + po;

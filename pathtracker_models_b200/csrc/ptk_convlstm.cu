@@ -153,26 +153,36 @@ __global__ void __launch_bounds__(512) head_bwd_kernel(const float* __restrict__
     dh[idx] = gw * rstd * (dhn - m1 - xh * m2);   // BatchNorm backward with batch statistics
   }
 }
-// the two per-step convolutions of the time loops: h -> stacked gate pre-activations and its transpose.
-// conv_mode bf16x3: tcgen05 implicit GEMM (ptk_convk_tc.cu); fp32: the generic direct kernel.
+// the wide convolutions (25 -> 100 stacked gates, its transpose, its weight gradient) of the recurrent path (Wh: every
+// step of the time loops) and of the hoisted input path (Wx: once per sequence).
+// conv_mode bf16x3: tcgen05 implicit GEMMs (ptk_convk_tc.cu, ptk_wgradk_tc.cu); fp32: the generic direct kernels.
 template <int KS>
-static int recurrent_conv(const LstmDev& d, const ConvGArgs& g, bool transposed, cudaStream_t st) {
+static int wide_conv(const LstmDev& d, const ConvGArgs& g, bool transposed, bool xpath, cudaStream_t st) {
   if (d.conv_mode == PTK_CONV_FP32) return launch_convg<KS>(g, st);
-  ConvKArgs k{g.in, transposed ? d.whD_tc : d.whF_tc, g.bias, g.addend, g.out, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, g.skip};
+  const void* w = xpath ? (transposed ? d.wxD_tc : d.wxF_tc) : (transposed ? d.whD_tc : d.whF_tc);
+  ConvKArgs k{g.in, w, g.bias, g.addend, g.out, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, g.skip};
   ProfileScope ps(transposed ? PTK_PROF_CONV_DGRAD : PTK_PROF_CONV_FWD, st);
   return launch_convk_tc<KS>(k, transposed ? 1 : 0, st);
 }
 template <int KS>
-static int recurrent_wgrad(const LstmDev& d, const WgradGArgs& g, cudaStream_t st) {
+static int recurrent_conv(const LstmDev& d, const ConvGArgs& g, bool transposed, cudaStream_t st) {
+  return wide_conv<KS>(d, g, transposed, false, st);
+}
+template <int KS>
+static int wide_wgrad(const LstmDev& d, const WgradGArgs& g, bool xpath, cudaStream_t st) {
   if (d.conv_mode == PTK_CONV_FP32) return launch_wgradg<KS>(g, st);
-  WgradKArgs k{g.in, g.dy, d.slots_h_tc, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, nullptr};
+  WgradKArgs k{g.in, g.dy, xpath ? d.slots_x_tc : d.slots_h_tc, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, nullptr};
   ProfileScope ps(PTK_PROF_WGRAD, st);
   return launch_wgradk_tc<KS>(k, st);
 }
 template <int KS>
-static int recurrent_prep(const LstmDev& d, bool transposed, cudaStream_t st) {
+static int recurrent_wgrad(const LstmDev& d, const WgradGArgs& g, cudaStream_t st) { return wide_wgrad<KS>(d, g, false, st); }
+template <int KS>
+static int recurrent_prep(const LstmDev& d, bool transposed, cudaStream_t st) {   // both banks
   if (d.conv_mode == PTK_CONV_FP32) return PTK_OK;
-  return launch_prep_weights_k<KS>(d.wh, transposed ? 1 : 0, transposed ? d.whD_tc : d.whF_tc, st);
+  int rc = launch_prep_weights_k<KS>(d.wh, transposed ? 1 : 0, transposed ? d.whD_tc : d.whF_tc, st);
+  if (rc) return rc;
+  return launch_prep_weights_k<KS>(d.wx, transposed ? 1 : 0, transposed ? d.wxD_tc : d.wxF_tc, st);
 }
 
 template <int KS>
@@ -190,6 +200,8 @@ static int convlstm_forward_t(const LstmDev& d, cudaStream_t st) {
   if ((rc = launch_convg<7>(c0, st))) return rc;
   square_kernel<<<148 * 4, 256, 0, st>>>(d.u, d.xt, S);
   ConvGArgs cx{d.xt, d.wxT, d.bx, nullptr, d.Xg, d.B, d.H, d.W, LC, LG, 0};
+  // the hoisted input term stays in strict fp32: xt = u^2 is all-positive and large, so the 16 mantissa bits of the
+  // hi/lo split are not enough against the cancellation in Wx * xt (measured: output error 1.5e-4 of max vs 6e-7)
   if ((rc = launch_convg<KS>(cx, st))) return rc;
   PTK_CUDA_OK(cudaMemsetAsync(d.h_at(0), 0, S * sizeof(float), st));
   PTK_CUDA_OK(cudaMemsetAsync(d.c_at(0), 0, S * sizeof(float), st));
@@ -316,10 +328,10 @@ static int convlstm_grad_tail(const LstmDev& d, cudaStream_t st) {
   const size_t S = (size_t)d.B * LC * P;
   int rc;
   WgradGArgs wx{d.xt, d.delta_sum, d.slots_x, d.B, d.H, d.W, LC, LG, d.groups, 0};
-  if ((rc = launch_wgradg<KS>(wx, st))) return rc;
+  if ((rc = wide_wgrad<KS>(d, wx, true, st))) return rc;
   chan_sum_kernel<<<LG, 512, 0, st>>>(d.delta_sum, d.bx_grad, d.B, LG, P);
   ConvGArgs cx{d.delta_sum, d.wxD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0};   // dh reused as d xt
-  if ((rc = launch_convg<KS>(cx, st))) return rc;
+  if ((rc = wide_conv<KS>(d, cx, true, true, st))) return rc;
   dsquare_kernel<<<148 * 4, 256, 0, st>>>(d.u, d.dh, S);                                 // d u = 2 u d xt
   WgradGArgs w0{d.x, d.dh, d.slots_0, d.B, d.H, d.W, 1, LC, d.groups, 0};
   if ((rc = launch_wgradg<7>(w0, st))) return rc;
@@ -327,7 +339,9 @@ static int convlstm_grad_tail(const LstmDev& d, cudaStream_t st) {
   // fold everything into the flat gradient vector (layout: ptk_convlstm_param_offsets)
   const long long per_gate = (long long)LC * LC * taps + LC + (long long)LC * LC * taps;   // Wx.w, Wx.b, Wh.w
   fold_slots_kernel<<<(LC * 49 + 255) / 256, 256, 0, st>>>(d.slots_0, d.groups, LC, 1, 49, d.dparams + d.off_w0, 0, LC);
-  fold_slots_kernel<<<(LG * LC * taps + 255) / 256, 256, 0, st>>>(d.slots_x, d.groups, LG, LC, taps, d.dparams + d.off_wx, per_gate, LC);
+  if (d.conv_mode == PTK_CONV_FP32)
+    fold_slots_kernel<<<(LG * LC * taps + 255) / 256, 256, 0, st>>>(d.slots_x, d.groups, LG, LC, taps, d.dparams + d.off_wx, per_gate, LC);
+  else if ((rc = launch_fold_wgradk(d.slots_x_tc, KS, 4, LC, LC, d.dparams + d.off_wx, per_gate, st))) return rc;
   if (d.conv_mode == PTK_CONV_FP32)
     fold_slots_kernel<<<(LG * LC * taps + 255) / 256, 256, 0, st>>>(d.slots_h, d.groups, LG, LC, taps, d.dparams + d.off_wh, per_gate, LC);
   else if ((rc = launch_fold_wgradk(d.slots_h_tc, KS, 4, LC, LC, d.dparams + d.off_wh, per_gate, st))) return rc;

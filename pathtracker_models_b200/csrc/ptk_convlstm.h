@@ -7,8 +7,8 @@ namespace ptk {
 
 struct LstmDev {
   int B, T, H, W, KS, groups, conv_mode;
-  float* slots_h_tc;                    // tensor-core weight-gradient slots of Wh (ptk_wgradk_tc.cu)
-  void *whF_tc, *whD_tc;                // tensor-core weight streams of the recurrent convolution / its transpose
+  float *slots_h_tc, *slots_x_tc;       // tensor-core weight-gradient slots of Wh / Wx (ptk_wgradk_tc.cu)
+  void *whF_tc, *whD_tc, *wxF_tc, *wxD_tc;   // [0] = Wh, [1] = Wx streams                // tensor-core weight streams of the recurrent convolution / its transpose
   const float* x;                       // [B,1,H,W]
   // parameters (views into the flat vector)
   const float *w0, *b0;                 // conv0 [25,1,7,7], [25]
