@@ -374,8 +374,8 @@ def run_convlstm(args, dev, world, rank):
                       "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T, B, HW, HW)},
                       "gpu_launches": _lib.launch_count() - l0,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                   "note": "recurrent-conv FLOPs only; conv_mode %s (bf16x3: forward / transposed convolution on "
-                                           "tcgen05, weight gradient on CUDA cores)" % ("fp32" if args.conv_mode == "fp32" else "bf16x3")}}),
+                                   "note": "recurrent-conv FLOPs only; conv_mode %s (bf16x3: forward / transposed convolution and "
+                                           "weight gradient on tcgen05, 3-pass split-bf16)" % ("fp32" if args.conv_mode == "fp32" else "bf16x3")}}),
           flush=True)
 
 
