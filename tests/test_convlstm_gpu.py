@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from tests.convlstm_util import load_convlstm_case, oracle_run
+from tests.convlstm_util import convlstm_shapes, load_convlstm_case, oracle_run
 from tests.golden_util import NOISE_MULT, REL_TOL, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -97,3 +97,32 @@ def test_convlstm_rbp_grads_vs_reference(name, conv_mode):
     with torch.no_grad():
         o2, states, _ = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss(), testmode=True)
     assert len(states) == T + 1 and states[0].abs().max().item() == 0.0 and states[-1].shape == (B, 25, H, W)
+
+
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("filt,H,W", [(15, 32, 64), (7, 64, 64)])
+def test_convlstm_wide_frames_vs_fp64_oracle(filt, H, W, conv_mode):
+    """frames wider / taller than one 32-column tile: the halo columns and rows of the convolution tiles carry real
+    neighbours (the 32x32 fixtures only ever see zero padding there).  Checked against the fp64 oracle, which the CPU
+    suite pins to the reference's own outputs."""
+    import numpy as np
+    from oracle.gen_golden import convlstm_weights
+    from pathtracker_models_b200 import convlstm
+    base = load_convlstm_case("convlstm_k7_small")
+    B, T = 2, 3
+    rs = np.random.RandomState(77)
+    like = {k: torch.zeros(s) for k, s in convlstm_shapes(filt).items()}
+    like["conv0.weight"] = base["gabor"].reshape(25, 1, 7, 7).clone()
+    case = dict(x=torch.from_numpy(rs.rand(B, 1, H, W)), target=torch.from_numpy((rs.rand(B, H, W) > 0.5).astype(np.int64)),
+                sd=convlstm_weights(like, 5), filt=filt, shape=(B, T, H, W))
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=filt, gabor=base["gabor"])
+    m.conv_mode = _mode(conv_mode)
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    loss.backward()
+    o64, l64, p64, g64 = oracle_run(case)
+    assert rel_err(out, o64) < REL_TOL and abs(loss.item() - l64) < 1e-5
+    assert rel_err(pen, p64) < 4 * REL_TOL          # the penalty is a clamp of a Jacobian product: compare loosely
+    bad = [(n, rel_err(p.grad, g64[n])) for n, p in m.named_parameters() if not rel_err(p.grad, g64[n]) <= 2 * REL_TOL]
+    assert not bad, bad
