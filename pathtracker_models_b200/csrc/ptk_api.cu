@@ -498,12 +498,21 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
   uint8_t *wtcF = nullptr, *wtcD = nullptr;
   float* wacc_tc = nullptr;
   const size_t wacc_pair = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
-  if (dm->conv_mode != PTK_CONV_FP32) {
+  uint8_t *wk_ruF = nullptr, *wk_ruD = nullptr, *wk_nF = nullptr, *wk_nD = nullptr;
+  float* slots_k = nullptr;
+  if (dm->conv_mode == PTK_CONV_BF16) {      // single-pass mode: 32x32-channel blocks on the InT kernels
     wtcF = cv.take<uint8_t>((size_t)24 * 4 * C * C * TAPS);      // bf16 hi + lo per pair = 4 bytes per weight
     wtcD = cv.take<uint8_t>((size_t)24 * 4 * C * C * TAPS);
     wacc_tc = cv.take<float>(24 * wacc_pair);
+  } else if (dm->conv_mode == PTK_CONV_BF16X3) {
+    wk_ruF = cv.take<uint8_t>(convk_tc_stream_bytes(7, 128, 4));
+    wk_ruD = cv.take<uint8_t>(convk_tc_stream_bytes(7, 128, 4));
+    wk_nF = cv.take<uint8_t>(convk_tc_stream_bytes(7, 64, 4));
+    wk_nD = cv.take<uint8_t>(convk_tc_stream_bytes(7, 128, 2));
+    slots_k = cv.take<float>(8 * wgradk_tc_slot_floats(7));
   }
   if (d) {
+    d->wk_ruF = wk_ruF; d->wk_ruD = wk_ruD; d->wk_nF = wk_nF; d->wk_nD = wk_nD; d->slots_k = slots_k;
     d->groups = groups; d->conv_mode = dm->conv_mode; d->head_part = head_part; d->dgoal = dgoal;
     d->wtcF = wtcF; d->wtcD = wtcD; d->wacc_tc = wacc_tc; d->wacc_pair = wacc_pair;
     d->hs = hs; d->rs = rs; d->us = us; d->ns = ns;

@@ -41,7 +41,7 @@ struct ConvK {
   static constexpr int UPR = KSZ / NSTACK;                  // units per kernel row
   static constexpr int UNITS = KSZ * UPR;
   static constexpr int UNIT_BYTES = 2 * 4 * NT * 16;        // [Wh: 4 chunks x NT rows x 16 B][Wl: same]
-  static constexpr int G = (UNIT_BYTES >= 12288) ? 1 : UPR; // units per ring stage
+  static constexpr int G = (UPR * UNIT_BYTES <= 32768) ? UPR : 1;   // units per ring stage (a whole kernel row if it is small)
   static constexpr int STAGE = G * UNIT_BYTES;
   static constexpr int NST = (STAGE * 6 + A_BYTES + 512 <= 232448) ? 6 : ((STAGE * 4 + A_BYTES + 512 <= 232448) ? 4 : 3);
   static constexpr int SMEM = A_BYTES + NST * STAGE + 256;
@@ -319,6 +319,30 @@ __global__ void prep_weights_k_kernel(PrepKArgs p) {
     p.dst[e] = lo ? l : h;
   }
 }
+
+// generic entry points (ConvGRU, ptk_gru.cu): dense [B,Cin,H,W] -> [B,Cout,H,W], one tap per instruction, N = NT >= Cout
+size_t convk_tc_stream_bytes(int ks, int nt, int nblk) { return (size_t)nblk * ks * ks * 2 * 4 * nt * 16; }
+int launch_prep_weights_k_generic(const float* const* w, int nbank, int ocb, int icb, int ks, int nt, int nblk, int transposed,
+                                  void* dst, cudaStream_t st) {
+  PrepKArgs p;
+  for (int i = 0; i < 4; ++i) p.w[i] = i < nbank ? w[i] : nullptr;
+  p.nbank = nbank; p.ocb = ocb; p.icb = icb; p.ks = ks; p.nt = nt; p.nstack = 1; p.nblk = nblk; p.transposed = transposed;
+  p.dst = (__nv_bfloat16*)dst;
+  prep_weights_k_kernel<<<148 * 4, 256, 0, st>>>(p);
+  PTK_LAUNCH_OK("prep_weights_k_kernel");
+  return PTK_OK;
+}
+template <int KSZ, int NT>
+int launch_convk_tc_n(const ConvKArgs& a, cudaStream_t st) {
+  using X = ConvK<KSZ, NT, 1>;
+  if (a.H % 8 || a.W % 32 || a.Cout > NT) { set_error("convk_tc_n: unsupported problem H=%d W=%d Cout=%d", a.H, a.W, a.Cout); return PTK_EINVAL; }
+  PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<X>, X::SMEM));
+  convk_tc_kernel<X><<<dim3(a.W / 32, a.H / 8, a.B), 256, X::SMEM, st>>>(a);
+  PTK_LAUNCH_OK("convk_tc_kernel");
+  return PTK_OK;
+}
+template int launch_convk_tc_n<7, 128>(const ConvKArgs&, cudaStream_t);
+template int launch_convk_tc_n<7, 64>(const ConvKArgs&, cudaStream_t);
 
 template <int KSZ>
 size_t convk_tc_weight_bytes(int transposed) {

@@ -335,6 +335,49 @@ __global__ void gru_fold_tc_kernel(GruDev d, int nCta) {
   }
 }
 
+// ---- bf16x3 mode: the wide convolutions as single launches of the ConvLSTM's tcgen05 kernels --------------------------
+// forward [r|u]: N = 128 stacked output channels, the 128 input channels walked in four 32-channel blocks (accumulators
+// stay in TMEM); candidate: N = 64; transposes: N = 128; weight gradients: one launch per 32-channel input block
+// (dY = 128 resp. 64 channels on the M axis), slots folded at the end.  Biases are added by the gate kernels.
+static int gru_prep_wide(const GruDev& d, bool transposed, cudaStream_t st) {
+  const float* ru[2] = {d.wr, d.wu};
+  const float* nn[1] = {d.wn};
+  int rc;
+  if ((rc = launch_prep_weights_k_generic(ru, 2, GC, 2 * GC, 7, 128, 4, 0, d.wk_ruF, st))) return rc;
+  if ((rc = launch_prep_weights_k_generic(nn, 1, GC, 2 * GC, 7, 64, 4, 0, d.wk_nF, st))) return rc;
+  if (transposed) {
+    if ((rc = launch_prep_weights_k_generic(ru, 2, GC, 2 * GC, 7, 128, 4, 1, d.wk_ruD, st))) return rc;
+    if ((rc = launch_prep_weights_k_generic(nn, 1, GC, 2 * GC, 7, 128, 2, 1, d.wk_nD, st))) return rc;
+  }
+  return PTK_OK;
+}
+template <int NT>
+static int gru_conv_wide(const GruDev& d, const float* in, const void* w, float* out, int Cin, int Cout, bool transposed, cudaStream_t st) {
+  ConvKArgs k{in, w, nullptr, nullptr, out, d.B, d.H, d.W, Cin, Cout, 0, nullptr};
+  ProfileScope ps(transposed ? PTK_PROF_CONV_DGRAD : PTK_PROF_CONV_FWD, st);
+  return launch_convk_tc_n<7, NT>(k, st);
+}
+static int gru_wgrad_wide(const GruDev& d, const float* in, const float* dy, int Cout, int slot0, int first, cudaStream_t st) {
+  const size_t P = (size_t)d.H * d.W, SF = wgradk_tc_slot_floats(7);
+  for (int i = 0; i < 4; ++i) {
+    WgradKArgs k{in + (size_t)i * 32 * P, dy, d.slots_k + (size_t)(slot0 + i) * SF, d.B, d.H, d.W, 32, Cout, !first, nullptr,
+                 (long long)(2 * GC * P)};
+    int rc;
+    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgradk_tc<7>(k, st); }
+    if (rc) return rc;
+  }
+  return PTK_OK;
+}
+static int gru_fold_wide(const GruDev& d, cudaStream_t st) {
+  const size_t SF = wgradk_tc_slot_floats(7);
+  int rc;
+  for (int i = 0; i < 4; ++i) {
+    if ((rc = launch_fold_wgradk(d.slots_k + (size_t)i * SF, 7, 2, GC, 32, d.dparams + d.off_wr, d.off_wu - d.off_wr, st, i * 32, 2 * GC))) return rc;
+    if ((rc = launch_fold_wgradk(d.slots_k + (size_t)(4 + i) * SF, 7, 1, GC, 32, d.dparams + d.off_wn, 0, st, i * 32, 2 * GC))) return rc;
+  }
+  return PTK_OK;
+}
+
 static int gru_prep(const GruDev& d, bool transposed, cudaStream_t st) {
   const int taps = 49;
   int rc;
@@ -353,8 +396,8 @@ static int gru_prep(const GruDev& d, bool transposed, cudaStream_t st) {
 
 int run_gru_forward(const GruDev& d, cudaStream_t st) {
   int rc;
-  const bool tc = d.conv_mode != PTK_CONV_FP32;
-  if ((rc = tc ? gru_prep_tc(d, st) : gru_prep(d, false, st))) return rc;
+  const bool tc = d.conv_mode != PTK_CONV_FP32, wide = d.conv_mode == PTK_CONV_BF16X3;
+  if ((rc = wide ? gru_prep_wide(d, false, st) : (tc ? gru_prep_tc(d, st) : gru_prep(d, false, st)))) return rc;
   PTK_CUDA_OK(cudaMemsetAsync(d.h_at(0), 0, d.S() * sizeof(float), st));
   const int grid = 148 * 8;
   for (int t = 1; t <= d.T; ++t) {
@@ -362,7 +405,9 @@ int run_gru_forward(const GruDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_FWD, st);
       gru_stem_cat_kernel<<<grid, 256, 0, st>>>(d, t, 0);
     }
-    if (tc) {
+    if (wide) {
+      if ((rc = gru_conv_wide<128>(d, d.Z, d.wk_ruF, d.RU, 2 * GC, 2 * GC, false, st))) return rc;
+    } else if (tc) {
       if ((rc = gru_conv_tc(d, d.Z, d.RU, 0, 4, 4, 0, st))) return rc;
     } else {
       ConvGArgs cru{d.Z, d.wruT, d.bru, nullptr, d.RU, d.B, d.H, d.W, 2 * GC, 2 * GC, 0};
@@ -372,7 +417,9 @@ int run_gru_forward(const GruDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_FWD, st);
       gru_gate_kernel<<<grid, 256, 0, st>>>(d, t, tc);
     }
-    if (tc) {
+    if (wide) {
+      if ((rc = gru_conv_wide<64>(d, d.Z2, d.wk_nF, d.Nb, 2 * GC, GC, false, st))) return rc;
+    } else if (tc) {
       if ((rc = gru_conv_tc(d, d.Z2, d.Nb, 16, 2, 4, 0, st))) return rc;
     } else {
       ConvGArgs cn{d.Z2, d.wnT, d.bnw, nullptr, d.Nb, d.B, d.H, d.W, 2 * GC, GC, 0};
@@ -394,8 +441,8 @@ int run_gru_forward(const GruDev& d, cudaStream_t st) {
 int run_gru_backward(const GruDev& d, cudaStream_t st) {
   int rc;
   const int taps = 49, grid = 148 * 8, P = d.H * d.W;
-  const bool tc = d.conv_mode != PTK_CONV_FP32;
-  if ((rc = tc ? gru_prep_tc(d, st) : gru_prep(d, true, st))) return rc;
+  const bool tc = d.conv_mode != PTK_CONV_FP32, wide = d.conv_mode == PTK_CONV_BF16X3;
+  if ((rc = wide ? gru_prep_wide(d, true, st) : (tc ? gru_prep_tc(d, st) : gru_prep(d, true, st)))) return rc;
   {
     const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
     PTK_CUDA_OK(cudaFuncSetAttribute(gru_readout_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
@@ -409,7 +456,10 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
       gru_bwd1_kernel<<<grid, 256, 0, st>>>(d, t, first);
       gru_stem_cat_kernel<<<grid, 256, 0, st>>>(d, t, 1);            // Z = cat(X_t, h_{t-1}), Z2 = cat(X_t, r h)
     }
-    if (tc) {
+    if (wide) {
+      if ((rc = gru_wgrad_wide(d, d.Z2, d.Nb, GC, 4, first, st))) return rc;
+      if ((rc = gru_conv_wide<128>(d, d.Nb, d.wk_nD, d.dZ, GC, 2 * GC, true, st))) return rc;
+    } else if (tc) {
       if ((rc = gru_wgrad_tc(d, d.Z2, d.Nb, 16, 2, first, st))) return rc;
       if ((rc = gru_conv_tc(d, d.Nb, d.dZ, 16, 2, 4, 1, st))) return rc;
     } else {
@@ -422,7 +472,10 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       gru_bwd2_kernel<<<grid, 256, 0, st>>>(d, t, first);
     }
-    if (tc) {
+    if (wide) {
+      if ((rc = gru_wgrad_wide(d, d.Z, d.RU, 2 * GC, 0, first, st))) return rc;
+      if ((rc = gru_conv_wide<128>(d, d.RU, d.wk_ruD, d.dZ, 2 * GC, 2 * GC, true, st))) return rc;
+    } else if (tc) {
       if ((rc = gru_wgrad_tc(d, d.Z, d.RU, 0, 4, first, st))) return rc;
       if ((rc = gru_conv_tc(d, d.RU, d.dZ, 0, 4, 4, 1, st))) return rc;
     } else {
@@ -442,7 +495,9 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
   // biases: sums over (t, b, y, x) of the gate pre-activation gradients; weights: fold the per-group slots
   chan_sum_kernel<<<GC, 512, 0, st>>>(d.dNsum, d.bias_grad, d.B, GC, P);
   chan_sum_kernel<<<2 * GC, 512, 0, st>>>(d.dRUsum, d.bias_grad + GC, d.B, 2 * GC, P);
-  if (tc) {
+  if (wide) {
+    if ((rc = gru_fold_wide(d, st))) return rc;
+  } else if (tc) {
     gru_fold_tc_kernel<<<148 * 8, 256, 0, st>>>(d, conv_num_ctas(d.B, d.H, d.W));
   } else {
     fold_slots_kernel<<<(2 * GC * 2 * GC * taps + 255) / 256, 256, 0, st>>>(d.slots_ru, d.groups, 2 * GC, 2 * GC, taps,

@@ -44,6 +44,10 @@ struct ConvKArgs {
 template <int KSZ> size_t convk_tc_weight_bytes(int transposed);
 template <int KSZ> int launch_prep_weights_k(const float* const* w, int transposed, void* dst, cudaStream_t st);
 template <int KSZ> int launch_convk_tc(const ConvKArgs& a, int transposed, cudaStream_t st);
+size_t convk_tc_stream_bytes(int ks, int nt, int nblk);
+int launch_prep_weights_k_generic(const float* const* w, int nbank, int ocb, int icb, int ks, int nt, int nblk, int transposed,
+                                  void* dst, cudaStream_t st);
+template <int KSZ, int NT> int launch_convk_tc_n(const ConvKArgs& a, cudaStream_t st);
 
 // weight gradient of the same convolution on tcgen05 (ptk_wgradk_tc.cu): slots [groups][KS*KS][128][32], folded at the end
 struct WgradKArgs {
@@ -52,11 +56,13 @@ struct WgradKArgs {
   float* slots;         // wgradk_tc_slot_floats(KS) floats
   int B, H, W, Cin, Cout, accumulate;
   const float* skip = nullptr;
+  long long in_bs = 0;  // elements between samples of `in` (0 = Cin*H*W): a 32-channel block of a wider tensor
 };
 int wgradk_tc_groups(int ks);
 size_t wgradk_tc_slot_floats(int ks);
 template <int KSZ> int launch_wgradk_tc(const WgradKArgs& a, cudaStream_t st);
-int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, float* dst0, long long stride_between, cudaStream_t st);
+int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, float* dst0, long long stride_between, cudaStream_t st,
+                       int ic0 = 0, int ic_total = 0);
 
 int conv_num_ctas(int B, int H, int W);
 int read_pw_stamps(unsigned long long* out);

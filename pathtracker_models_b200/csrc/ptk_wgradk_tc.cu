@@ -22,6 +22,9 @@
 
 namespace ptk {
 
+constexpr int WGK_NSTAGE_THREADS = 224;   // warps 0, 2-7 stage; warp 1 issues the MMAs
+constexpr int WGK_NITEM = 3;              // 16-byte-vector items per staging pass: 24 LDG.128 in flight per thread
+
 template <int KS_>
 struct WgK {
   static constexpr int KSZ = KS_, PAD = KS_ / 2;
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
   if (a.skip != nullptr && a.skip[1] != 0.f) return;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * K::BUF);
-  uint64_t* full = bars;           // [2] tile staged (192 arrivals)
+  uint64_t* full = bars;           // [2] tile staged (one arrival per staging thread)
   uint64_t* empty = bars + 2;      // [2] MMAs of the tile retired (tcgen05.commit)
   uint64_t* accum_bar = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
   const int myTiles = r0 < nTiles ? (nTiles - r0 + R - 1) / R : 0;
 
   if (tid == 0) {
-    mbar_init(&full[0], 192); mbar_init(&full[1], 192);
+    mbar_init(&full[0], WGK_NSTAGE_THREADS); mbar_init(&full[1], WGK_NSTAGE_THREADS);
     mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -109,9 +112,9 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
     }
     __syncwarp();
     if (elect_one()) umma_commit(accum_bar);
-  } else if (warp >= 2) {
-    // ---- staging warps ----------------------------------------------------------------------------------------
-    const int stid = tid - 64;
+  } else {
+    // ---- staging warps (0, 2-7) -------------------------------------------------------------------------------
+    const int stid = warp == 0 ? lane : tid - 32;
     for (int i = 0; i < myTiles; ++i) {
       const int buf = i & 1;
       if (i >= 2) mbar_wait(&empty[buf], (uint32_t)(((i >> 1) - 1) & 1));
@@ -121,17 +124,17 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
       uint8_t* sIN = sDY + K::DY_BYTES;
       // one list of 16-byte-vector items: delta (planes 0..ceil(Cout/8)-1, 4 rows x 8 four-pixel groups; channels >= Cout
       // zero) followed by the interior of the h tile (4 planes; rows shifted by ky - PAD; zero outside the image / beyond
-      // Cin).  Two items per pass: 16 LDG.128 in flight per thread before the first conversion (L2-latency bound).
+      // Cin).  WGK_NITEM items per pass, all loads requested before the first conversion (L2-latency bound).
       const float* dyb = a.dy + (size_t)b * a.Cout * HW;
-      const float* inb = a.in + (size_t)b * a.Cin * HW;
+      const float* inb = a.in + (size_t)b * (a.in_bs ? (size_t)a.in_bs : (size_t)a.Cin * HW);
       const int nDY = ((a.Cout + 7) / 8) * K::TH * 8, nIt = nDY + 4 * K::TH * 8;
-      for (int it0 = stid; it0 < nIt; it0 += 384) {
-        float4 v[2][8];
-        int dst[2];                       // byte offset of the item's first pixel inside its first plane, -1 = no item
-        bool isin[2];
+      for (int it0 = stid; it0 < nIt; it0 += WGK_NITEM * WGK_NSTAGE_THREADS) {
+        float4 v[WGK_NITEM][8];
+        int dst[WGK_NITEM];               // byte offset of the item's first pixel inside its first plane, -1 = no item
+        bool isin[WGK_NITEM];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int it = it0 + 192 * r;
+        for (int r = 0; r < WGK_NITEM; ++r) {
+          const int it = it0 + WGK_NSTAGE_THREADS * r;
           dst[r] = -1; isin[r] = false;
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[r][e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
           }
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < WGK_NITEM; ++r) {
           if (dst[r] < 0) continue;
 #pragma unroll
           for (int px = 0; px < 4; ++px) {
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
         }
       }
       // halo columns of the h tile (always outside the image when W == 32)
-      for (int it = stid; it < 4 * K::TH * 2 * K::PAD; it += 192) {
+      for (int it = stid; it < 4 * K::TH * 2 * K::PAD; it += WGK_NSTAGE_THREADS) {
         const int q = it / (K::TH * 2 * K::PAD), rem = it - q * (K::TH * 2 * K::PAD), row = rem / (2 * K::PAD), hc = rem - row * (2 * K::PAD);
         const int c = hc < K::PAD ? hc : (K::TW + hc);
         const int gy = y0 + row + ky - K::PAD, gx = x0 + c - K::PAD;
@@ -243,15 +246,16 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
 }
 
 // slots [R][taps][128][32] -> the `nbank` stacked [ocb][icb][taps] tensors inside dparams (double-precision fold, fixed order)
+// icb = input channels covered by these slots (<= 32), placed at ic0 inside tensors with ic_total input channels
 __global__ void fold_wgradk_kernel(const float* __restrict__ slots, int R, int taps, int nbank, int ocb, int icb, float* dst0,
-                                   long long stride_between) {
+                                   long long stride_between, int ic0, int ic_total) {
   const int total = nbank * ocb * icb * taps;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int tap = i % taps, ic = (i / taps) % icb, n = i / (taps * icb);
   double s = 0;
   for (int r = 0; r < R; ++r) s += slots[(((size_t)r * taps + tap) * 128 + n) * 32 + ic];
-  dst0[(size_t)(n / ocb) * stride_between + ((size_t)(n % ocb) * icb + ic) * taps + tap] = (float)s;
+  dst0[(size_t)(n / ocb) * stride_between + ((size_t)(n % ocb) * ic_total + ic0 + ic) * taps + tap] = (float)s;
 }
 
 int wgradk_tc_groups(int ks) { return 148 / ks; }
@@ -272,9 +276,11 @@ int launch_wgradk_tc(const WgradKArgs& a, cudaStream_t st) {
 template int launch_wgradk_tc<7>(const WgradKArgs&, cudaStream_t);
 template int launch_wgradk_tc<15>(const WgradKArgs&, cudaStream_t);
 
-int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, float* dst0, long long stride_between, cudaStream_t st) {
+int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, float* dst0, long long stride_between, cudaStream_t st,
+                       int ic0, int ic_total) {
   const int total = nbank * ocb * icb * ks * ks;
-  fold_wgradk_kernel<<<(total + 255) / 256, 256, 0, st>>>(slots, wgradk_tc_groups(ks), ks * ks, nbank, ocb, icb, dst0, stride_between);
+  fold_wgradk_kernel<<<(total + 255) / 256, 256, 0, st>>>(slots, wgradk_tc_groups(ks), ks * ks, nbank, ocb, icb, dst0, stride_between,
+                                                          ic0, ic_total ? ic_total : icb);
   PTK_LAUNCH_OK("fold_wgradk_kernel");
   return PTK_OK;
 }
