@@ -22,6 +22,14 @@
 
 namespace ptk {
 
+// two floats -> packed bf16 hi pair and lo pair (hi + lo ~= v to 16 mantissa bits) with the paired conversions
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);      // .x = v0 in the low half
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 constexpr int WGK_NSTAGE_THREADS = 224;   // warps 0, 2-7 stage; warp 1 issues the MMAs
 constexpr int WGK_NITEM = 3;              // 16-byte-vector items per staging pass: 24 LDG.128 in flight per thread
 
@@ -127,7 +135,10 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
       // Cin).  WGK_NITEM items per pass, all loads requested before the first conversion (L2-latency bound).
       const float* dyb = a.dy + (size_t)b * a.Cout * HW;
       const float* inb = a.in + (size_t)b * (a.in_bs ? (size_t)a.in_bs : (size_t)a.Cin * HW);
-      const int nDY = ((a.Cout + 7) / 8) * K::TH * 8, nIt = nDY + 4 * K::TH * 8;
+      // item -> (plane group of 4, row) x lane; inside a warp the lane picks (plane q = 4*group + lane%4, 4-pixel group g):
+      // the 8 lanes of a quarter warp then hit 8 different 16-byte bank groups with their STS.128 (plane strides are
+      // 16 resp. 48 mod 128 bytes, the two g of a quarter warp are 64 bytes apart) and still read whole 32-byte sectors.
+      const int nDY = ((a.Cout + 31) / 32) * K::TH * 32, nIt = nDY + K::TH * 32;
       for (int it0 = stid; it0 < nIt; it0 += WGK_NITEM * WGK_NSTAGE_THREADS) {
         float4 v[WGK_NITEM][8];
         int dst[WGK_NITEM];               // byte offset of the item's first pixel inside its first plane, -1 = no item
@@ -138,15 +149,16 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
           dst[r] = -1; isin[r] = false;
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[r][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int l5 = it & 31, g = ((l5 >> 3) << 1) | ((l5 >> 2) & 1);
           if (it < nDY) {
-            const int q = it / (K::TH * 8), rem = it - q * (K::TH * 8), row = rem >> 3, g = rem & 7;
-            dst[r] = q * K::DY_PLANE + (row * K::TW + 4 * g) * 16;
+            const int grp = it >> 5, row = grp % K::TH, q = (grp / K::TH) * 4 + (l5 & 3);
+            if (q * 8 < a.Cout) dst[r] = q * K::DY_PLANE + (row * K::TW + 4 * g) * 16;   // planes past Cout stay zero
             const float* src = dyb + (size_t)(q * 8) * HW + (size_t)(y0 + row) * W + x0 + 4 * g;
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               if (q * 8 + e < a.Cout) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * HW);
           } else if (it < nIt) {
-            const int j = it - nDY, q = j / (K::TH * 8), rem = j - q * (K::TH * 8), row = rem >> 3, g = rem & 7;
+            const int row = (it - nDY) >> 5, q = l5 & 3;
             const int gy = y0 + row + ky - K::PAD;
             isin[r] = true;
             dst[r] = q * K::IN_PLANE + (row * K::WP + K::PAD + 4 * g) * 16;
@@ -165,13 +177,8 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
           for (int px = 0; px < 4; ++px) {
             uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(reinterpret_cast<const float*>(&v[r][2 * e])[px], h0, l0);
-              split_bf16(reinterpret_cast<const float*>(&v[r][2 * e + 1])[px], h1, l1);
-              hi[e] = pack_bf16x2(h0, h1);
-              lo[e] = pack_bf16x2(l0, l1);
-            }
+            for (int e = 0; e < 4; ++e)
+              split_bf16x2(reinterpret_cast<const float*>(&v[r][2 * e])[px], reinterpret_cast<const float*>(&v[r][2 * e + 1])[px], hi[e], lo[e]);
             const uint4 uh = make_uint4(hi[0], hi[1], hi[2], hi[3]), ul = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             if (!isin[r]) {
               *reinterpret_cast<uint4*>(sDY + dst[r] + px * 16) = uh;
@@ -197,11 +204,7 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
           float v0 = 0.f, v1 = 0.f;
           if (ok && q * 8 + 2 * e < a.Cin) v0 = inb[(size_t)(q * 8 + 2 * e) * HW + (size_t)gy * W + gx];
           if (ok && q * 8 + 2 * e + 1 < a.Cin) v1 = inb[(size_t)(q * 8 + 2 * e + 1) * HW + (size_t)gy * W + gx];
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v0, h0, l0);
-          split_bf16(v1, h1, l1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(l0, l1);
+          split_bf16x2(v0, v1, hi[e], lo[e]);
         }
         const int p = row * K::WP + c;
         const uint4 uh = make_uint4(hi[0], hi[1], hi[2], hi[3]), ul = make_uint4(lo[0], lo[1], lo[2], lo[3]);
