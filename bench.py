@@ -374,6 +374,9 @@ def run_convlstm(args, dev, world, rank):
                       "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T, B, HW, HW)},
                       "gpu_launches": _lib.launch_count() - l0,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
+                                   "peak": load_peaks()[0], "frac": flop * steps / (ms / 1e3) / 1e12 / load_peaks()[0],
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); the 3-pass split issues 3x "
+                                                  "the algorithmic MACs, so the fp32-parity ceiling is 1/3 of it" % load_peaks()[2],
                                    "note": "recurrent-conv FLOPs only; conv_mode %s (bf16x3: forward / transposed convolution and "
                                            "weight gradient on tcgen05, 3-pass split-bf16)" % ("fp32" if args.conv_mode == "fp32" else "bf16x3")}}),
           flush=True)
