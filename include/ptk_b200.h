@@ -192,6 +192,14 @@ PTK_API int ptk_gru_backward(const PtkGruDims* d, const float* x, const int64_t 
  * or conv_transpose2d(in, weight, padding=3) (transpose=1, its data gradient).  in/out [B,32,H,W],
  * weight [32,32,7,7] as stored by torch; stats optional [2][32] out: batch mean and 1/sqrt(var+1e-3)
  * of the convolution result (the BatchNorm that follows it). */
+/* One wide operator of the ConvLSTM time loops on its own, on the tcgen05 kernels (test / measurement entry; the time
+ * loops call the same launchers).  weights: the four recurrent banks Wh{i,f,c,o} (models/convlstm.py:66-79) contiguous,
+ * [4][25][25][K][K].  op 0: out [B,100,H,W] = stacked conv(in [B,25,H,W]) (+ aux [B,100,H,W] if given);
+ * op 1: out [B,25,H,W] = transposed conv(in [B,100,H,W]);  op 2: out [4][25][25][K][K] = weight gradient for
+ * in = h [B,25,H,W], aux = dY [B,100,H,W]. */
+PTK_API size_t ptk_lstm_wide_op_workspace_bytes(int32_t K);
+PTK_API int ptk_lstm_wide_op(int32_t B, int32_t H, int32_t W, int32_t K, int32_t op, const float* in, const float* aux,
+                             const float* weights, float* out, void* workspace, size_t workspace_bytes, void* stream);
 PTK_API size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W);
 PTK_API int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transpose, int32_t accumulate,
                       const float* in, const float* weight, float* out, float* stats, void* workspace,

@@ -20,6 +20,7 @@ EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_sa
            "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
            "ptk_convlstm_forward", "ptk_convlstm_backward", "ptk_debug_tc_stamps", "ptk_debug_wt_stamps", "ptk_debug_pw_stamps", "ptk_debug_tc_times",
            "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp",
+           "ptk_lstm_wide_op", "ptk_lstm_wide_op_workspace_bytes",
            "ptk_gru_param_offsets", "ptk_gru_saved_bytes", "ptk_gru_workspace_bytes", "ptk_gru_forward", "ptk_gru_backward")
 
 
@@ -94,6 +95,10 @@ def lib():
                                 ctypes.c_float, ctypes.c_int64, i32, vp]
     L.ptk_convlstm_backward_rbp.restype = ctypes.c_int
     L.ptk_convlstm_backward_rbp.argtypes = [ldp, vp, vp, vp, vp, i32, vp, vp, vp, sz, vp]
+    L.ptk_lstm_wide_op_workspace_bytes.restype = sz
+    L.ptk_lstm_wide_op_workspace_bytes.argtypes = [i32]
+    L.ptk_lstm_wide_op.restype = ctypes.c_int
+    L.ptk_lstm_wide_op.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     gdp = ctypes.POINTER(PtkGruDims)
     L.ptk_gru_param_offsets.restype = ctypes.c_int
     L.ptk_gru_param_offsets.argtypes = [gdp, i64p]

@@ -274,6 +274,36 @@ PTK_API int ptk_debug_wt_stamps(long long* out) { return read_wt_debug(out); }
 PTK_API int ptk_debug_tc_times(unsigned long long* out, int n) { return read_tc_times(out, n); }
 PTK_API int ptk_debug_pw_stamps(unsigned long long* out) { return read_pw_stamps(out); }
 
+size_t ptk_lstm_wide_op_workspace_bytes(int32_t K) {
+  if (K != 7 && K != 15) return 0;
+  Carver cv(nullptr);
+  cv.take<uint8_t>(K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));   // >= the forward stream
+  cv.take<float>(wgradk_tc_slot_floats(K));
+  return (cv.off + 255) & ~(size_t)255;
+}
+int ptk_lstm_wide_op(int32_t B, int32_t H, int32_t W, int32_t K, int32_t op, const float* in, const float* aux,
+                     const float* weights, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (K != 7 && K != 15) { set_error("ptk_lstm_wide_op: filt_size %d not built (7 and 15 are)", K); return PTK_EUNSUPPORTED; }
+  if (B < 1 || H < 8 || W < 32 || H % 8 || W % 32 || op < 0 || op > 2) { set_error("ptk_lstm_wide_op: unsupported B=%d H=%d W=%d op=%d", B, H, W, op); return PTK_EINVAL; }
+  if (!in || !weights || !out || !workspace || (op == 2 && !aux)) { set_error("ptk_lstm_wide_op: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_lstm_wide_op_workspace_bytes(K)) { set_error("ptk_lstm_wide_op: workspace too small"); return PTK_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(workspace);
+  uint8_t* wstream = cv.take<uint8_t>(K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));
+  float* slots = cv.take<float>(wgradk_tc_slot_floats(K));
+  const size_t per = (size_t)25 * 25 * K * K;
+  const float* banks[4] = {weights, weights + per, weights + 2 * per, weights + 3 * per};
+  int rc;
+  if (op == 2) {
+    WgradKArgs w{in, aux, slots, B, H, W, 25, 100, 0, nullptr};
+    if ((rc = K == 15 ? launch_wgradk_tc<15>(w, st) : launch_wgradk_tc<7>(w, st))) return rc;
+    return launch_fold_wgradk(slots, K, 4, 25, 25, out, (long long)per, st);
+  }
+  if ((rc = K == 15 ? launch_prep_weights_k<15>(banks, op, wstream, st) : launch_prep_weights_k<7>(banks, op, wstream, st))) return rc;
+  ConvKArgs k{in, wstream, nullptr, op == 0 ? aux : nullptr, out, B, H, W, op == 0 ? 25 : 100, op == 0 ? 100 : 25, 0, nullptr};
+  return K == 15 ? launch_convk_tc<15>(k, op, st) : launch_convk_tc<7>(k, op, st);
+}
+
 size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
   if (B < 1 || H < 16 || W < 32 || H % 16 || W % 32) return 0;
   Carver cv(nullptr);

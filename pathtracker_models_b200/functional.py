@@ -149,3 +149,26 @@ def conv7(x, weight, conv_mode=_lib.PTK_CONV_FP32, transpose=False, out=None, wa
                          _ptr(stats), _ptr(ws), nbytes, stream)
         _lib.check(rc, "ptk_conv7")
     return (out, stats) if want_stats else out
+
+
+def lstm_wide_op(op, x, weights, aux=None):
+    """one wide operator of the ConvLSTM time loops on the tcgen05 kernels (ptk_lstm_wide_op; test / measurement entry).
+    weights [4,25,25,K,K] (Wh of the gates i,f,c,o).  op 'conv': x [B,25,H,W] (+ aux [B,100,H,W]) -> [B,100,H,W];
+    'transpose': x [B,100,H,W] -> [B,25,H,W]; 'wgrad': x = h [B,25,H,W], aux = dY [B,100,H,W] -> [4,25,25,K,K]."""
+    L = _lib.lib()
+    code = {"conv": 0, "transpose": 1, "wgrad": 2}[op]
+    B, _, H, W = x.shape
+    K = weights.shape[-1]
+    x, weights = x.contiguous().float(), weights.contiguous().float()
+    aux = aux.contiguous().float() if aux is not None else None
+    with torch.cuda.device(x.device):
+        shape = {0: (B, 100, H, W), 1: (B, 25, H, W), 2: tuple(weights.shape)}[code]
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+        nbytes = L.ptk_lstm_wide_op_workspace_bytes(K)
+        if nbytes == 0:
+            _lib.check(1, "ptk_lstm_wide_op_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        rc = L.ptk_lstm_wide_op(B, H, W, K, code, _ptr(x), _ptr(aux), _ptr(weights), _ptr(out), _ptr(ws), nbytes, stream)
+        _lib.check(rc, "ptk_lstm_wide_op")
+    return out

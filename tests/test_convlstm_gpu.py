@@ -126,3 +126,26 @@ def test_convlstm_wide_frames_vs_fp64_oracle(filt, H, W, conv_mode):
     assert rel_err(pen, p64) < 4 * REL_TOL          # the penalty is a clamp of a Jacobian product: compare loosely
     bad = [(n, rel_err(p.grad, g64[n])) for n, p in m.named_parameters() if not rel_err(p.grad, g64[n]) <= 2 * REL_TOL]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("K,B,H,W", [(15, 64, 32, 32), (7, 64, 32, 32), (15, 3, 16, 64), (7, 1, 64, 32), (15, 1, 8, 32)])
+def test_wide_operators_alone_vs_torch_fp64(K, B, H, W):
+    """the three tcgen05 operators of the time loops on their own (through ptk_lstm_wide_op) against torch fp64
+    convolutions, at BASELINE's full batch and at ragged shapes (B = 1: fewer tiles than weight-gradient CTAs)."""
+    import torch.nn.functional as F
+    from pathtracker_models_b200.functional import lstm_wide_op
+    g = torch.Generator().manual_seed(K * 1000 + B)
+    w = torch.randn(4, 25, 25, K, K, generator=g, dtype=torch.float64) / (25 * K * K) ** 0.5
+    h = (torch.rand(B, 25, H, W, generator=g, dtype=torch.float64) * 2 - 1)
+    dy = torch.randn(B, 100, H, W, generator=g, dtype=torch.float64)
+    add = torch.randn(B, 100, H, W, generator=g, dtype=torch.float64)
+    w32, h32, dy32, add32 = (t.float() for t in (w, h, dy, add))        # the fp64 reference sees the fp32-rounded inputs
+    w64, h64, dy64, add64 = (t.double().requires_grad_(t is not add32) for t in (w32, h32, dy32, add32))
+    ws = w64.reshape(100, 25, K, K)
+    ref = F.conv2d(h64, ws, padding=K // 2) + add64
+    got = lstm_wide_op("conv", h32.cuda(), w32.cuda(), add32.cuda())
+    tol = 5e-5      # the 3-pass bf16 split carries 16-17 mantissa bits per operand; measured 1e-5 ... 3e-5 of max here
+    assert rel_err(got, ref.detach()) < tol
+    (F.conv2d(h64, ws, padding=K // 2) * dy64.detach()).sum().backward()
+    assert rel_err(lstm_wide_op("transpose", dy32.cuda(), w32.cuda()), h64.grad) < tol
+    assert rel_err(lstm_wide_op("wgrad", h32.cuda(), w32.cuda(), dy32.cuda()), w64.grad) < tol
