@@ -378,9 +378,11 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   double* rbp_part = cv.take<double>(2 * 148 * 2);
   uint8_t *whF_tc = nullptr, *whD_tc = nullptr, *wxF_tc = nullptr, *wxD_tc = nullptr;
   float *slots_h_tc = nullptr, *slots_x_tc = nullptr;
+  uint8_t* dyc_tc = nullptr;
   if (dm->conv_mode != PTK_CONV_FP32) {
     slots_h_tc = cv.take<float>(wgradk_tc_slot_floats(dm->K));
     slots_x_tc = cv.take<float>(wgradk_tc_slot_floats(dm->K));
+    dyc_tc = cv.take<uint8_t>(wgradk_tc_dyc_bytes(dm->B, dm->H, dm->W));
     wxF_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(0) : convk_tc_weight_bytes<7>(0));
     wxD_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(1) : convk_tc_weight_bytes<7>(1));
     whF_tc = cv.take<uint8_t>(dm->K == 15 ? convk_tc_weight_bytes<15>(0) : convk_tc_weight_bytes<7>(0));
@@ -388,7 +390,7 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   }
   if (d) {
     d->whF_tc = whF_tc; d->whD_tc = whD_tc; d->conv_mode = dm->conv_mode; d->slots_h_tc = slots_h_tc;
-    d->slots_x_tc = slots_x_tc; d->wxF_tc = wxF_tc; d->wxD_tc = wxD_tc;
+    d->slots_x_tc = slots_x_tc; d->wxF_tc = wxF_tc; d->wxD_tc = wxD_tc; d->dyc_tc = dyc_tc;
     d->rbp_g = rbp_g; d->rbp_state = rbp_state; d->rbp_part = rbp_part;
     d->groups = groups;
     d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;
@@ -530,6 +532,7 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
   const size_t wacc_pair = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
   uint8_t *wk_ruF = nullptr, *wk_ruD = nullptr, *wk_nF = nullptr, *wk_nD = nullptr;
   float* slots_k = nullptr;
+  uint8_t* dyc_k = nullptr;
   if (dm->conv_mode == PTK_CONV_BF16) {      // single-pass mode: 32x32-channel blocks on the InT kernels
     wtcF = cv.take<uint8_t>((size_t)24 * 4 * C * C * TAPS);      // bf16 hi + lo per pair = 4 bytes per weight
     wtcD = cv.take<uint8_t>((size_t)24 * 4 * C * C * TAPS);
@@ -540,9 +543,10 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
     wk_nF = cv.take<uint8_t>(convk_tc_stream_bytes(7, 64, 4));
     wk_nD = cv.take<uint8_t>(convk_tc_stream_bytes(7, 128, 2));
     slots_k = cv.take<float>(8 * wgradk_tc_slot_floats(7));
+    dyc_k = cv.take<uint8_t>(wgradk_tc_dyc_bytes(dm->B, dm->H, dm->W));
   }
   if (d) {
-    d->wk_ruF = wk_ruF; d->wk_ruD = wk_ruD; d->wk_nF = wk_nF; d->wk_nD = wk_nD; d->slots_k = slots_k;
+    d->wk_ruF = wk_ruF; d->wk_ruD = wk_ruD; d->wk_nF = wk_nF; d->wk_nD = wk_nD; d->slots_k = slots_k; d->dyc_k = dyc_k;
     d->groups = groups; d->conv_mode = dm->conv_mode; d->head_part = head_part; d->dgoal = dgoal;
     d->wtcF = wtcF; d->wtcD = wtcD; d->wacc_tc = wacc_tc; d->wacc_pair = wacc_pair;
     d->hs = hs; d->rs = rs; d->us = us; d->ns = ns;

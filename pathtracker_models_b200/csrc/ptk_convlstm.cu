@@ -171,7 +171,10 @@ static int recurrent_conv(const LstmDev& d, const ConvGArgs& g, bool transposed,
 template <int KS>
 static int wide_wgrad(const LstmDev& d, const WgradGArgs& g, bool xpath, cudaStream_t st) {
   if (d.conv_mode == PTK_CONV_FP32) return launch_wgradg<KS>(g, st);
-  WgradKArgs k{g.in, g.dy, xpath ? d.slots_x_tc : d.slots_h_tc, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, nullptr};
+  // the KS kernel-row CTAs all read the same delta tiles: split them into bf16 hi/lo once, fetch by bulk copy
+  int rc = launch_wgradk_prep_dy(g.dy, g.B, g.H, g.W, g.Cout, d.dyc_tc, nullptr, st);
+  if (rc) return rc;
+  WgradKArgs k{g.in, g.dy, xpath ? d.slots_x_tc : d.slots_h_tc, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, nullptr, 0, d.dyc_tc};
   ProfileScope ps(PTK_PROF_WGRAD, st);
   return launch_wgradk_tc<KS>(k, st);
 }

@@ -7,6 +7,7 @@ namespace ptk {
 
 struct LstmDev {
   int B, T, H, W, KS, groups, conv_mode;
+  void* dyc_tc;                         // delta of the step, pre-split per tile for the weight-gradient CTAs (wgradk_prep_dy)
   float *slots_h_tc, *slots_x_tc;       // tensor-core weight-gradient slots of Wh / Wx (ptk_wgradk_tc.cu)
   void *whF_tc, *whD_tc, *wxF_tc, *wxD_tc;   // [0] = Wh, [1] = Wx streams                // tensor-core weight streams of the recurrent convolution / its transpose
   const float* x;                       // [B,1,H,W]

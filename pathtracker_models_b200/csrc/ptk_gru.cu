@@ -359,9 +359,11 @@ static int gru_conv_wide(const GruDev& d, const float* in, const void* w, float*
 }
 static int gru_wgrad_wide(const GruDev& d, const float* in, const float* dy, int Cout, int slot0, int first, cudaStream_t st) {
   const size_t P = (size_t)d.H * d.W, SF = wgradk_tc_slot_floats(7);
+  int rc0 = launch_wgradk_prep_dy(dy, d.B, d.H, d.W, Cout, d.dyc_k, nullptr, st);   // read by 4 input blocks x 7 kernel rows
+  if (rc0) return rc0;
   for (int i = 0; i < 4; ++i) {
     WgradKArgs k{in + (size_t)i * 32 * P, dy, d.slots_k + (size_t)(slot0 + i) * SF, d.B, d.H, d.W, 32, Cout, !first, nullptr,
-                 (long long)(2 * GC * P)};
+                 (long long)(2 * GC * P), d.dyc_k};
     int rc;
     { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgradk_tc<7>(k, st); }
     if (rc) return rc;

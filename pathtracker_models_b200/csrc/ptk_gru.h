@@ -30,6 +30,7 @@ struct GruDev {
   // the candidate (16 + j*4 + i): bf16 hi/lo tap streams (forward / transposed) and per-CTA weight-gradient slots
   // bf16x3 mode: wide tcgen05 kernels shared with the ConvLSTM (ptk_convk_tc.cu / ptk_wgradk_tc.cu)
   uint8_t *wk_ruF, *wk_ruD, *wk_nF, *wk_nD;   // weight streams: [reset|update] 128 -> 128 and candidate 128 -> 64, forward / transposed
+  void* dyc_k;                                // gate-gradient tiles pre-split for the weight-gradient CTAs (wgradk_prep_dy)
   float* slots_k;                             // 8 x wgradk_tc_slot_floats(7): input-channel blocks 0-3 of [r|u], then of the candidate
   uint8_t *wtcF, *wtcD;
   float* wacc_tc;

@@ -57,7 +57,12 @@ struct WgradKArgs {
   int B, H, W, Cin, Cout, accumulate;
   const float* skip = nullptr;
   long long in_bs = 0;  // elements between samples of `in` (0 = Cin*H*W): a 32-channel block of a wider tensor
+  const void* dyc = nullptr;   // dy already split and laid out per tile by launch_wgradk_prep_dy (then `dy` is not read)
 };
+// dy [B,Cout,H,W] fp32 -> per 4x32-pixel tile the kernel's shared-memory image (bf16 hi/lo planes): the weight-gradient
+// CTAs of all kernel rows (and input blocks) then fetch a tile with ONE bulk copy instead of converting it again each
+size_t wgradk_tc_dyc_bytes(int B, int H, int W);
+int launch_wgradk_prep_dy(const float* dy, int B, int H, int W, int Cout, void* dyc, const float* skip, cudaStream_t st);
 int wgradk_tc_groups(int ks);
 size_t wgradk_tc_slot_floats(int ks);
 template <int KSZ> int launch_wgradk_tc(const WgradKArgs& a, cudaStream_t st);

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
   const int myTiles = r0 < nTiles ? (nTiles - r0 + R - 1) / R : 0;
 
   if (tid == 0) {
-    mbar_init(&full[0], WGK_NSTAGE_THREADS); mbar_init(&full[1], WGK_NSTAGE_THREADS);
+    const int nfull = WGK_NSTAGE_THREADS + (a.dyc ? 1 : 0);   // + the expect_tx arrival of the bulk copy
+    mbar_init(&full[0], nfull); mbar_init(&full[1], nfull);
     mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < 2 * K::BUF / 16; i += 256) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the bulk copies (async proxy) overwrite these bytes
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -139,7 +141,11 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
       // the 8 lanes of a quarter warp then hit 8 different 16-byte bank groups with their STS.128 (plane strides are
       // 16 resp. 48 mod 128 bytes, the two g of a quarter warp are 64 bytes apart) and still read whole 32-byte sectors.
       const int nDY = ((a.Cout + 31) / 32) * K::TH * 32, nIt = nDY + K::TH * 32;
-      for (int it0 = stid; it0 < nIt; it0 += WGK_NITEM * WGK_NSTAGE_THREADS) {
+      if (a.dyc != nullptr && stid == 0) {    // pre-split delta tile: one bulk copy, completes on the same barrier
+        mbar_expect_tx(&full[buf], K::DY_BYTES);
+        bulk_g2s(sDY, reinterpret_cast<const uint8_t*>(a.dyc) + (size_t)tile * K::DY_BYTES, K::DY_BYTES, &full[buf]);
+      }
+      for (int it0 = (a.dyc ? nDY : 0) + stid; it0 < nIt; it0 += WGK_NITEM * WGK_NSTAGE_THREADS) {
         float4 v[WGK_NITEM][8];
         int dst[WGK_NITEM];               // byte offset of the item's first pixel inside its first plane, -1 = no item
         bool isin[WGK_NITEM];
@@ -259,6 +265,44 @@ __global__ void fold_wgradk_kernel(const float* __restrict__ slots, int R, int t
   double s = 0;
   for (int r = 0; r < R; ++r) s += slots[(((size_t)r * taps + tap) * 128 + n) * 32 + ic];
   dst0[(size_t)(n / ocb) * stride_between + ((size_t)(n % ocb) * ic_total + ic0 + ic) * taps + tap] = (float)s;
+}
+
+// fp32 [B,Cout,H,W] -> per tile [32 planes][128 px][8 ch] bf16 (hi planes 0-15, lo planes 16-31, WgK::DY_PLANE pitch)
+__global__ void wgradk_prep_dy_kernel(const float* __restrict__ dy, int B, int H, int W, int Cout, uint8_t* dst, const float* skip) {
+  if (skip != nullptr && skip[1] != 0.f) return;
+  using K = WgK<7>;     // the delta-tile layout does not depend on the kernel size
+  const int tilesX = W / K::TW, tilesY = H / K::TH, nTiles = B * tilesX * tilesY;
+  const size_t HW = (size_t)H * W, total = (size_t)nTiles * 4 * K::TH * 32;     // items: (tile, plane group, row, lane)
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int l5 = (int)(e & 31), g = ((l5 >> 3) << 1) | ((l5 >> 2) & 1);
+    const int grp = (int)((e >> 5) % (4 * K::TH)), tile = (int)(e / (4 * K::TH * 32));
+    const int row = grp % K::TH, q = (grp / K::TH) * 4 + (l5 & 3);
+    const int b = tile / (tilesX * tilesY), trem = tile - b * (tilesX * tilesY), y0 = (trem / tilesX) * K::TH, x0 = (trem % tilesX) * K::TW;
+    float4 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q * 8 + c < Cout) v[c] = *reinterpret_cast<const float4*>(dy + ((size_t)b * Cout + q * 8 + c) * HW + (size_t)(y0 + row) * W + x0 + 4 * g);
+    }
+    uint8_t* o = dst + (size_t)tile * K::DY_BYTES + (size_t)q * K::DY_PLANE + (size_t)(row * K::TW + 4 * g) * 16;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        split_bf16x2(reinterpret_cast<const float*>(&v[2 * c])[px], reinterpret_cast<const float*>(&v[2 * c + 1])[px], hi[c], lo[c]);
+      *reinterpret_cast<uint4*>(o + px * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(o + 16 * K::DY_PLANE + px * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+size_t wgradk_tc_dyc_bytes(int B, int H, int W) { return (size_t)B * (H / 4) * (W / 32) * WgK<7>::DY_BYTES; }
+int launch_wgradk_prep_dy(const float* dy, int B, int H, int W, int Cout, void* dyc, const float* skip, cudaStream_t st) {
+  static_assert(WgK<7>::DY_BYTES == WgK<15>::DY_BYTES && WgK<7>::DY_PLANE == WgK<15>::DY_PLANE, "one delta-tile layout");
+  if (H % 4 || W % 32 || Cout > 128) { set_error("wgradk_prep_dy: unsupported H=%d W=%d Cout=%d", H, W, Cout); return PTK_EINVAL; }
+  wgradk_prep_dy_kernel<<<148 * 8, 256, 0, st>>>(dy, B, H, W, Cout, (uint8_t*)dyc, skip);
+  PTK_LAUNCH_OK("wgradk_prep_dy_kernel");
+  return PTK_OK;
 }
 
 int wgradk_tc_groups(int ks) { return 148 / ks; }
