@@ -523,7 +523,7 @@ static size_t gru_carve(const PtkGruDims* dm, void* saved, void* ws, GruDev* d, 
   float* dNsum = cv.take<float>(S);
   float* slots_ru = cv.take<float>((size_t)groups * 2 * GC * 2 * GC * taps);
   float* slots_n = cv.take<float>((size_t)groups * GC * 2 * GC * taps);
-  float* stem_acc = cv.take<float>(4 * GC);
+  float* stem_acc = cv.take<float>(GRU_STEM_SPLIT * 4 * GC);
   float* bias_grad = cv.take<float>(3 * GC);
   float* head_part = cv.take<float>((size_t)dm->B * GRU_HEAD_N);
   float* dgoal = cv.take<float>((size_t)dm->B * P);

@@ -27,9 +27,10 @@
 
 namespace ptk {
 
-template <int KS_, int NT_, int NSTACK_>
+template <int KS_, int NT_, int NSTACK_, int NBUF_ = 1>
 struct ConvK {
   static constexpr int KSZ = KS_, NT = NT_, NSTACK = NSTACK_;
+  static constexpr int NBUF = NBUF_;   // operand images: 2 = the next 32-channel block is staged while this one is multiplied
   static constexpr int PAD = KSZ / 2;
   static constexpr int TH = 8, TW = 32;
   static constexpr int WP = TW + KSZ - 1;                   // padded row pitch (pixels)
@@ -43,8 +44,8 @@ struct ConvK {
   static constexpr int UNIT_BYTES = 2 * 4 * NT * 16;        // [Wh: 4 chunks x NT rows x 16 B][Wl: same]
   static constexpr int G = (UPR * UNIT_BYTES <= 32768) ? UPR : 1;   // units per ring stage (a whole kernel row if it is small)
   static constexpr int STAGE = G * UNIT_BYTES;
-  static constexpr int NST = (STAGE * 6 + A_BYTES + 512 <= 232448) ? 6 : ((STAGE * 4 + A_BYTES + 512 <= 232448) ? 4 : 3);
-  static constexpr int SMEM = A_BYTES + NST * STAGE + 256;
+  static constexpr int NST = (STAGE * 6 + NBUF * A_BYTES + 512 <= 232448) ? 6 : ((STAGE * 4 + NBUF * A_BYTES + 512 <= 232448) ? 4 : 3);
+  static constexpr int SMEM = NBUF * A_BYTES + NST * STAGE + 256;
   static constexpr int DSTRIDE = (NT + 31) & ~31;           // TMEM columns between M-tiles: accumulators start on 32-column boundaries
   static constexpr int DCOLS = MT * DSTRIDE;
   static constexpr int TCOLS = DCOLS <= 128 ? 128 : (DCOLS <= 256 ? 256 : 512);
@@ -75,14 +76,14 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
   if (a.skip != nullptr && a.skip[1] != 0.f) return;   // RBP: the Neumann series has terminated (uniform for the grid)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sA = smem_raw;
-  uint8_t* sWr = smem_raw + K::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::A_BYTES + K::NST * K::STAGE);
+  uint8_t* sWr = smem_raw + K::NBUF * K::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + K::NBUF * K::A_BYTES + K::NST * K::STAGE);
   uint64_t* full = bars;                 // [NST]
   uint64_t* empty = bars + K::NST;       // [NST]
-  uint64_t* a_full = bars + 2 * K::NST;  // operand image of block kb staged (192 arrivals)
-  uint64_t* a_free = a_full + 1;         // MMAs of block kb have retired (tcgen05.commit)
-  uint64_t* accum_bar = a_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 3);
+  uint64_t* a_full = bars + 2 * K::NST;  // [2] operand image of block kb staged (192 arrivals)
+  uint64_t* a_free = a_full + 2;         // [2] MMAs of block kb have retired (tcgen05.commit)
+  uint64_t* accum_bar = a_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 5);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -93,8 +94,8 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
 
   if (tid == 0) {
     for (int i = 0; i < K::NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_full, 192);
-    mbar_init(a_free, 1);
+    mbar_init(&a_full[0], 192); mbar_init(&a_full[1], 192);
+    mbar_init(&a_free[0], 1); mbar_init(&a_free[1], 1);
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(K::TCOLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < K::A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < K::NBUF * K::A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
     }
   } else if (warp == 1) {
     // ---- MMA issuer ----------------------------------------------------------------------------------------
-    const uint32_t aHi = smem_u32(sA), aLo = aHi + 4 * K::PLANE, wBase = smem_u32(sWr);
+    const uint32_t aBase = smem_u32(sA), wBase = smem_u32(sWr);
     const uint64_t dA0 = umma_desc(0, K::PLANE, 128);
     const uint64_t dB0 = umma_desc(0, K::NT * 16, 128);
     const uint32_t aHiW = (uint32_t)(dA0 >> 32), aLoW = (uint32_t)dA0;
@@ -130,8 +131,10 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
     constexpr uint32_t IDESC = umma_idesc(K::NT);
     int s_glob = 0;
     for (int kb = 0; kb < nblk; ++kb) {
-      mbar_wait(a_full, (uint32_t)(kb & 1));
+      const int ab = kb % K::NBUF;
+      mbar_wait(&a_full[ab], (uint32_t)((kb / K::NBUF) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t aHi = aBase + (uint32_t)ab * K::A_BYTES, aLo = aHi + 4 * K::PLANE;
       for (int sb = 0; sb < K::UNITS / K::G; ++sb, ++s_glob) {
         const int st = s_glob % K::NST, round = s_glob / K::NST;
         mbar_wait(&full[st], (uint32_t)(round & 1));
@@ -167,13 +170,16 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
         if (elect_one()) umma_commit(&empty[st]);
       }
       __syncwarp();
-      if (elect_one()) umma_commit(kb + 1 < nblk ? a_free : accum_bar);
+      if (kb + 1 == nblk) { if (elect_one()) umma_commit(accum_bar); }
+      else if (kb + K::NBUF < nblk) { if (elect_one()) umma_commit(&a_free[ab]); }
     }
   } else {
     // ---- staging warps: fp32 NCHW -> bf16 hi/lo channel-chunk planar, one 32-channel block at a time ---------
     const int stid = tid - 64;
     for (int kb = 0; kb < nblk; ++kb) {
-      if (kb > 0) mbar_wait(a_free, (uint32_t)((kb - 1) & 1));
+      const int ab = kb % K::NBUF;
+      if (kb >= K::NBUF) mbar_wait(&a_free[ab], (uint32_t)((kb / K::NBUF - 1) & 1));
+      uint8_t* sA = smem_raw + ab * K::A_BYTES;      // shadows the CTA-wide pointer: this block's image
       const float* inb = a.in + (size_t)b * a.Cin * HW;
       // interior columns: item = (chunk, row, 4-pixel group); 8 channel loads of 16 B -> 4 pixels
       for (int it = stid; it < 4 * K::ROWS * (K::TW / 4); it += 192) {
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
         *reinterpret_cast<uint4*>(sA + 4 * K::PLANE + q * K::PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-      mbar_arrive(a_full);
+      mbar_arrive(&a_full[ab]);
     }
   }
   __syncwarp();
@@ -334,7 +340,7 @@ int launch_prep_weights_k_generic(const float* const* w, int nbank, int ocb, int
 }
 template <int KSZ, int NT>
 int launch_convk_tc_n(const ConvKArgs& a, cudaStream_t st) {
-  using X = ConvK<KSZ, NT, 1>;
+  using X = ConvK<KSZ, NT, 1, 2>;    // 7x7: two operand images fit, re-staging overlaps the MMAs
   if (a.H % 8 || a.W % 32 || a.Cout > NT) { set_error("convk_tc_n: unsupported problem H=%d W=%d Cout=%d", a.H, a.W, a.Cout); return PTK_EINVAL; }
   PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<X>, X::SMEM));
   convk_tc_kernel<X><<<dim3(a.W / 32, a.H / 8, a.B), 256, X::SMEM, st>>>(a);

@@ -108,13 +108,16 @@ __global__ void gru_bwd3_kernel(GruDev d, int t) {
     d.dXb[e] = dX * (pre > 20.0f ? 1.0f : sigmoid_precise(pre));      // softplus' (threshold 20, models/kys.py:102)
   }
 }
-// stem parameter gradients of one step: one CTA per channel, fixed order => deterministic
+// stem parameter gradients of one step: GRU_STEM_SPLIT CTAs per channel (64 CTAs left most of the GPU idle for
+// 150 us per step), each owning a fixed slice of (b, pixel) and its own accumulator => deterministic
 __global__ void __launch_bounds__(512) gru_stem_grad_kernel(GruDev d, int t, int first) {
   __shared__ double sh[16];
-  const int c = blockIdx.x, P = d.H * d.W;
-  const size_t N = (size_t)d.B * P;
+  const int c = blockIdx.x / GRU_STEM_SPLIT, part = blockIdx.x % GRU_STEM_SPLIT, P = d.H * d.W;
+  const size_t Nall = (size_t)d.B * P, per = (Nall + GRU_STEM_SPLIT - 1) / GRU_STEM_SPLIT;
+  const size_t i0 = (size_t)part * per, N = i0 + per < Nall ? i0 + per : Nall;
+  float* acc = d.stem_acc + (size_t)part * 4 * GC;
   double s[4] = {0, 0, 0, 0};
-  for (size_t i = threadIdx.x; i < N; i += blockDim.x) {
+  for (size_t i = i0 + threadIdx.x; i < N; i += blockDim.x) {
     const int b = (int)(i / P), pix = (int)(i % P), y = pix / d.W, x = pix - y * d.W;
     const float g = d.dXb[((size_t)b * GC + c) * P + pix];
     s[0] += g;
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(512) gru_stem_grad_kernel(GruDev d, int t, int
   }
   for (int k = 0; k < 4; ++k) {
     const double tot = block_sum_d(s[k], sh);
-    if (threadIdx.x == 0) d.stem_acc[c * 4 + k] = first ? (float)tot : d.stem_acc[c * 4 + k] + (float)tot;
+    if (threadIdx.x == 0) acc[c * 4 + k] = first ? (float)tot : acc[c * 4 + k] + (float)tot;
     __syncthreads();
   }
 }
@@ -143,8 +146,11 @@ __global__ void gru_dx_kernel(GruDev d, int t) {
 __global__ void gru_stem_out_kernel(GruDev d) {      // stem_acc [64][4] -> dparams (preproc.weight [64][3], preproc.bias [64])
   const int c = threadIdx.x;
   if (c >= GC) return;
-  d.dparams[d.off_bp + c] = d.stem_acc[c * 4];
-  for (int i = 0; i < 3; ++i) d.dparams[d.off_wp + c * 3 + i] = d.stem_acc[c * 4 + 1 + i];
+  double s[4] = {0, 0, 0, 0};
+  for (int part = 0; part < GRU_STEM_SPLIT; ++part)
+    for (int k = 0; k < 4; ++k) s[k] += (double)d.stem_acc[(size_t)part * 4 * GC + c * 4 + k];
+  d.dparams[d.off_bp + c] = (float)s[0];
+  for (int i = 0; i < 3; ++i) d.dparams[d.off_wp + c * 3 + i] = (float)s[1 + i];
 }
 
 // ---- readout head (models/kys.py:127-133): r = readout_conv(h_T); cat with the goal channel x[:,2,0]; 5x5 conv (pad 2);
@@ -489,7 +495,7 @@ int run_gru_backward(const GruDev& d, cudaStream_t st) {
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st, 2);
       gru_bwd3_kernel<<<grid, 256, 0, st>>>(d, t);
-      gru_stem_grad_kernel<<<GC, 512, 0, st>>>(d, t, first);
+      gru_stem_grad_kernel<<<GC * GRU_STEM_SPLIT, 512, 0, st>>>(d, t, first);
     }
     if (d.dx) gru_dx_kernel<<<grid, 256, 0, st>>>(d, t);
     PTK_LAUNCH_OK("gru backward step");

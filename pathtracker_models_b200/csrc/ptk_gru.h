@@ -8,6 +8,7 @@
 namespace ptk {
 
 constexpr int GC = 64;   // hidden / stem channels (utils/engine.py:149: dimensions * 2)
+constexpr int GRU_STEM_SPLIT = 4;   // CTAs per channel in gru_stem_grad_kernel (partials folded in fixed order at the end)
 constexpr int GRU_HEAD_N = GC + 1 + 50 + 1 + 1 + 1;   // dWr, dbr, dWt, dbt, dWd, dbd (flat-vector order)
 
 struct GruDev {
