@@ -392,6 +392,7 @@ def run_gru(args, dev, world, rank):
     B, T, HW = args.batch, args.frames, args.size
     torch.manual_seed(0)
     m = kys.GRU(dimensions=64, timesteps=T, kernel_size=7).to(dev)
+    m.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
     x, y = synth_pathtracker(B, T, HW, HW, n_distractors=DIST, speed=SPEED, device=dev)
 
     def step():
@@ -419,7 +420,11 @@ def run_gru(args, dev, world, rank):
                       "config": {"workload": "kys.GRU %d frames %dx%d, batch %d" % (T, HW, HW, B)},
                       "gpu_launches": _lib.launch_count() - l0,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                   "note": "cell-convolution FLOPs only (32x32-channel blocks on the tcgen05 conv kernels unless --conv-mode fp32)"}}), flush=True)
+                                   "peak": load_peaks()[0], "frac": flop * steps / (ms / 1e3) / 1e12 / load_peaks()[0],
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); fp32-parity ceiling = 1/3 of it "
+                                                  "(3-pass split-bf16)" % load_peaks()[2],
+                                   "note": "cell-convolution FLOPs only; conv_mode %s (bf16x3: wide tcgen05 kernels shared with the "
+                                           "ConvLSTM)" % args.conv_mode}}), flush=True)
 
 
 def run_eval(args, dev, world, rank):

@@ -381,7 +381,7 @@ template int launch_prep_weights_k<15>(const float* const*, int, void*, cudaStre
 template <int KSZ>
 int launch_convk_tc(const ConvKArgs& a_in, int transposed, cudaStream_t st) {
   ConvKArgs a = a_in;
-  static const int exp_d = getenv("PTK_CONVK_DBG") ? atoi(getenv("PTK_CONVK_DBG")) : 0;
+  static const int exp_d = getenv("PTK_CONVK_DBG") ? atoi(getenv("PTK_CONVK_DBG")) : 0;   // phase timing: 1 = no epilogue, 2 = no MMAs
   a.dbg = exp_d;
   using F = ConvK<KSZ, 112, 1>;
   using D = ConvK<KSZ, (KSZ % 3 == 0) ? 96 : 32, (KSZ % 3 == 0) ? 3 : 1>;
@@ -389,19 +389,8 @@ int launch_convk_tc(const ConvKArgs& a_in, int transposed, cudaStream_t st) {
   dim3 grid(a.W / 32, a.H / 8, a.B);
   if (!transposed) {
     if (a.Cin > 32 || a.Cout > F::NT) { set_error("convk_tc forward: %d -> %d channels unsupported", a.Cin, a.Cout); return PTK_EINVAL; }
-    static const int exp_n = getenv("PTK_CONVK_EXP") ? atoi(getenv("PTK_CONVK_EXP")) : 0;   // timing experiments only (wrong results)
-    if (KSZ == 15 && exp_n == 96) {
-      using X = ConvK<15, 96, 1>;
-      PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<X>, X::SMEM));
-      convk_tc_kernel<X><<<grid, 256, X::SMEM, st>>>(a);
-    } else if (KSZ == 15 && exp_n == 128) {
-      using X = ConvK<15, 128, 1>;
-      PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<X>, X::SMEM));
-      convk_tc_kernel<X><<<grid, 256, X::SMEM, st>>>(a);
-    } else {
     PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<F>, F::SMEM));
     convk_tc_kernel<F><<<grid, 256, F::SMEM, st>>>(a);
-    }
   } else {
     if (a.Cin > 128 || a.Cout > D::NT / D::NSTACK) { set_error("convk_tc transposed: %d -> %d channels unsupported", a.Cin, a.Cout); return PTK_EINVAL; }
     PTK_CUDA_OK(ptk_func_smem(convk_tc_kernel<D>, D::SMEM));
