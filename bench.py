@@ -106,6 +106,50 @@ def cpu_reference_seq_per_s(steps, warmup, batch=8):
         f"InT fwd+bwd, batch {batch} (of 64), T={T}, {HW}x{HW}, fp32, {len(times)} timed passes after {warmup} warm-up"
 
 
+def gpu_eager_reference(args):
+    """SURVEY 8(d) "honest beat-this bar": the reference's OPERATOR SEQUENCE (oracle/int_eager.py: F.conv2d, F.batch_norm,
+    one ATen kernel per point-wise operator, autograd tape) run by PyTorch eager on cuda:0 at the full headline shape,
+    TF32 off (fp32 parity class) and on.  Extra information only: `--impl reference` without --ref-device stays the CPU arm."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import int_eager
+    from oracle import int_oracle as O
+    from pathtracker_models_b200 import InT, synth_pathtracker
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = InT.InT(dimensions=C, timesteps=T, kernel_size=K)
+    p = {k: v.to(dev).requires_grad_(True) for k, v in O.unpack(m.state_dict(), dtype=torch.float32).items()}
+    batches = [synth_pathtracker(args.batch, T, HW, HW, n_distractors=DIST, first_index=i * args.batch, device=dev)
+               for i in range(2)]
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(warmup + steps):
+            if i == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            x, y = batches[i % 2]
+            F.binary_cross_entropy_with_logits(int_eager.forward(x, p), y).backward()
+            for v in p.values():
+                v.grad = None
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["tf32_on" if tf32 else "tf32_off"] = {"value": args.batch / (ms / 1e3), "ms_per_step": ms}
+    print(json.dumps({"impl": "reference-gpu-eager", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": steps,
+                      "warmup": warmup, "value": out["tf32_off"]["value"], "ms_per_step": out["tf32_off"]["ms_per_step"],
+                      "tf32_on": out["tf32_on"], "tf32_off": out["tf32_off"], "dtype": "f32", "data": "synthetic",
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                      "config": {"workload": "InT 64 frames 32x32, 14 distractors, batch %d/GPU (BASELINE configs[1])" % args.batch,
+                                 "note": "oracle/int_eager.py = the reference's operator sequence in PyTorch eager on the same B200; "
+                                         "not the product path, not the driver's reference arm"}}), flush=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -463,6 +507,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cuda = additionally time the reference's operator sequence in PyTorch eager on the GPU")
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm", "gru"], help="non-headline configs (BASELINE configs[2..3])")
@@ -472,7 +518,9 @@ def main():
     ap.add_argument("--conv-mode", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="7x7 convolutions: strict-fp32 FFMA, or 3-pass split-bf16 tcgen05 (both parity-gated)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.ref_device == "cuda":
+        gpu_eager_reference(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

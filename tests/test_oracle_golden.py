@@ -64,3 +64,20 @@ def test_oracle_cfg1_logits():
     with torch.no_grad():
         logits, _ = O.forward(case["x"], p, keep=False)
     assert rel_err(logits, case["logits"]) < 1e-10
+
+
+@pytest.mark.parametrize("name,variant", [("int_small", "int"), ("int_tile", "int"), ("hgru_small", "hgru")])
+def test_library_operator_restatement_matches_reference_fp64(name, variant):
+    """oracle/int_eager.py (the reference's operator sequence, timed by `bench.py --impl reference --ref-device cuda`)
+    against the fixtures produced by the reference itself: logits and every parameter gradient."""
+    from oracle import int_eager
+    case = load_case(name)
+    p = O.unpack(case["sd"])
+    for v in p.values():
+        v.requires_grad_(True)
+    logits = int_eager.forward(case["x"], p, variant)
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, case["y"]).backward()
+    g = O.grad_to_state_keys({k: v.grad for k, v in p.items() if v.grad is not None}, case["sd"])
+    assert rel_err(logits.detach(), case["logits"]) < 1e-10
+    for n, g_ref in case["grads"].items():
+        assert rel_err(g[n], g_ref) < (2e-7 if g_ref.numel() > 4096 else 1e-9), n
