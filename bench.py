@@ -75,6 +75,20 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def _host_cores():
+    """physical cores this process may run on (what torch picks by itself when OMP_NUM_THREADS is unset)."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or avail
+    except Exception:  # noqa: BLE001
+        phys = avail
+    return max(1, min(avail, phys))
+
+
 def cpu_reference_seq_per_s(steps, warmup, batch=8):
     """the reference algorithm on the host cores: oracle port (torch CPU ops + autograd), fp32,
     fwd + BCE + bwd on a bounded sample of the headline workload (batch `batch` instead of 64)."""
@@ -83,6 +97,7 @@ def cpu_reference_seq_per_s(steps, warmup, batch=8):
     from oracle import int_oracle as O
     from oracle.synth_oracle import synth
     from pathtracker_models_b200 import InT
+    torch.set_num_threads(_host_cores())   # torchrun exports OMP_NUM_THREADS=1: the CPU arm still gets every core
     torch.manual_seed(0)
     m = InT.InT(dimensions=C, timesteps=T, kernel_size=K)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
