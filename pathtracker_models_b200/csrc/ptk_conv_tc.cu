@@ -36,7 +36,7 @@ constexpr int TC_WP = TC_TW + 6;                       // 38: padded row pitch (
 constexpr int TC_ROWS = TC_TH + 6;                     // 22 input rows
 constexpr int TC_MT = 5;                               // M-tiles: 5*128 = 640 >= 16*38 = 608
 constexpr int TC_NPIX = 880;                           // >= 640 + 6*38 + 6 = 874 pixels incl. slack
-constexpr int TC_PLANE = TC_NPIX * 16;                 // bytes per channel-chunk plane
+constexpr int TC_PLANE = TC_NPIX * 16 + 16;            // bytes per channel-chunk plane; +16 so the 4 chunks of one pixel hit 4 different bank groups
 constexpr int TC_A_BYTES = 2 * 4 * TC_PLANE;           // hi + lo, 4 chunks
 constexpr int TC_WTAP = 4 * 64 * 16;                   // bytes of one tap's weights: 4 chunks x (32 hi + 32 lo rows) x 8 bf16
 constexpr int TC_STAGE = KS * TC_WTAP;                 // one ring stage = one kernel row (7 taps, 28 KB)
@@ -113,8 +113,11 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
     int pp[NR], qq[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
+      // a quarter warp = (2 adjacent pixel groups) x (4 chunks): its eight 16-byte stores land 64*g1 + 16*q bytes apart
+      // modulo the 128-byte bank period, i.e. conflict-free (one row per chunk-plane per quarter warp was 4-way conflicted);
+      // a warp covers one whole input row of all 32 channels, so the loads are still full 128-byte lines.
       const int it = tid + 256 * r;
-      const int q = it / (TC_ROWS * (TC_TW / 4)), rem = it - q * (TC_ROWS * (TC_TW / 4)), row = rem / (TC_TW / 4), g = rem % (TC_TW / 4);
+      const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
       const int gy = y0 + row - 3;
       pp[r] = -1; qq[r] = q;
       if (it < NIT && gy >= 0 && gy < H) {

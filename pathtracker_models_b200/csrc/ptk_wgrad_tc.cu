@@ -56,7 +56,9 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int it = it0 + 256 * r;
-      const int q = it / (nrows * (WT_TW / 4)), rem = it - q * (nrows * (WT_TW / 4)), row = rem / (WT_TW / 4), g = rem % (WT_TW / 4);
+      // quarter warp = (2 adjacent pixel groups) x (4 chunk planes, 16 B apart modulo the bank period): conflict-free
+      // 16-byte stores (see conv7_tc_kernel); a warp covers one tile row of all 32 channels
+      const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
       const int gy = gy0 + row;
       pp[r] = -1; qq[r] = q;
       if (it < nit && gy >= 0 && gy < H) {
