@@ -294,5 +294,21 @@ if __name__ == "__main__":
         load_reference()
         run_convlstm_case("convlstm_k7_rbp", 7, 2, 4, 32, 32, seed=41, store_full=True, grad_method='rbp', num_iter=50)
         run_convlstm_case("convlstm_k7_rbp_trunc", 7, 2, 3, 32, 32, seed=42, store_full=True, grad_method='rbp', num_iter=2)
+    elif len(sys.argv) > 1 and sys.argv[1] == "long":
+        # the horizons the benchmark is quoted on (BASELINE.json configs[1]-[4]): T = 64 at 32x32, T = 128 at 64x64,
+        # ConvLSTM timesteps = 64 (models/convlstm.py:138), kys.GRU T = 64.  Minutes of CPU time each.
+        which = sys.argv[2:] or ["int", "hgru", "int128", "convlstm", "gru"]
+        RInT, RH = load_reference()
+        if "int" in which:
+            run_case("int_t64", lambda: RInT.InT(dimensions=32, timesteps=64, kernel_size=7), 8, 64, 32, 32, seed=61, wseed=23)
+        if "hgru" in which:
+            run_case("hgru_t64", lambda: RH.FFhGRU(dimensions=32, timesteps=64, kernel_size=7), 8, 64, 32, 32, seed=62, wseed=24)
+        if "int128" in which:
+            run_case("int_t128_64px", lambda: RInT.InT(dimensions=32, timesteps=128, kernel_size=7), 2, 128, 64, 64,
+                     seed=63, wseed=25)
+        if "convlstm" in which:
+            run_convlstm_case("convlstm_k15_t64", 15, 2, 64, 32, 32, seed=64, store_full=False)
+        if "gru" in which:
+            run_gru_case("gru_t64", 2, 64, 32, 32, seed=65)
     else:
         main()

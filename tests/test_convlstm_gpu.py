@@ -46,6 +46,39 @@ def test_convlstm_output_penalty_and_grads(name, conv_mode):
     assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
 
 
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
+def test_convlstm_long_horizon_k15_t64_vs_reference(conv_mode):
+    """BASELINE configs[4] at its own horizon: filt 15, timesteps = 64 (models/convlstm.py:138), B = 2, train mode (penalty
+    branch).  Fixture = the reference in fp64 (output, loss, penalty, every gradient through seeded projections); the
+    per-tensor gradient check uses the fp64 oracle evaluated with torch on the GPU, itself held to those projections."""
+    import numpy as np
+    from oracle import convlstm_oracle as CO
+    case = load_convlstm_case("convlstm_k15_t64")
+    m, out, pen, loss = _run(case, conv_mode)
+    B, T, H, W = case["shape"]
+    assert T == 64 and out.shape == (B, 2, H, W)
+    assert rel_err(out, case["output"]) < REL_TOL
+    assert abs(loss.item() - case["loss"]) < 1e-5
+    assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))
+    p = {k: v.cuda().requires_grad_(True) for k, v in CO.unpack(case["sd"]).items()}
+    o64, _ = CO.forward(case["x"].cuda(), p, T)
+    torch.nn.functional.cross_entropy(o64, case["target"].cuda()).backward()
+    g64 = {CO.STATE_KEYS[k]: v.grad for k, v in p.items()}
+    assert rel_err(o64, case["output"]) < 1e-9
+    prs = np.random.RandomState(case["proj_seed"])
+    for n in case["proj"]:                                  # the checker against the reference's own gradients
+        g = g64[n].cpu().numpy().ravel()
+        v = prs.normal(0, 1, (4, g.size))
+        assert np.allclose(v @ g, case["proj"][n], rtol=1e-7, atol=1e-11 * max(1.0, case["gmax"][n])), n
+    bad = []
+    for n, prm in m.named_parameters():
+        e = rel_err(prm.grad, g64[n])
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+
+
 def test_convlstm_eval_mode_and_determinism():
     from pathtracker_models_b200 import convlstm
     case = load_convlstm_case("convlstm_k7_small")

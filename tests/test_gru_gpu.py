@@ -42,6 +42,46 @@ def test_gru_logits_and_all_grads_vs_reference(name, conv_mode):
         assert rel_err(dict(m.named_parameters())[n].grad, g) < max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0)), n
 
 
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
+def test_gru_long_horizon_t64_vs_reference(conv_mode):
+    """T = 64 (the horizon `bench.py --model gru` is quoted on), B = 2.  Fixture: the reference in fp64 (logits, loss, the
+    small gradients in full, the three 7x7 banks through seeded projections).  The per-tensor check of the big banks uses the
+    fp64 oracle evaluated with torch on the GPU, after that evaluation has itself been held to the fixture."""
+    from oracle import gru_oracle as GO
+    from pathtracker_models_b200 import _lib
+    case = load_gru_case("gru_t64")
+    m = mirror_model(case).cuda()
+    m.conv_mode = _lib.PTK_CONV_BF16X3 if conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
+    x, y = case["x"].float().cuda(), case["y"].float().cuda()
+    out, _ = m(x)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+    assert rel_err(out, case["logits"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
+    p = {k: v.detach().double().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    lo = GO.forward(case["x"].cuda(), p)
+    torch.nn.functional.binary_cross_entropy_with_logits(lo, case["y"].cuda()).backward()
+    assert rel_err(lo, case["logits"]) < 1e-9                       # the checker against the reference's own output
+    prs = np.random.RandomState(case["seed"] + 2)
+    for n, prm in p.items():
+        if prm.grad is None:
+            continue
+        if n in case["grads"]:
+            assert rel_err(prm.grad, case["grads"][n]) < 1e-8, n
+        else:
+            g = prm.grad.cpu().numpy().ravel()
+            v = prs.normal(0, 1, (4, g.size))
+            assert np.allclose(v @ g, case["proj"][n], rtol=1e-7, atol=1e-11 * max(1.0, case["gmax"][n])), n
+    bad = []
+    for n, prm in m.named_parameters():
+        if p[n].grad is None:
+            continue
+        e = rel_err(prm.grad, p[n].grad)
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+
+
 def test_gru_testmode_input_gradient_and_determinism():
     case = load_gru_case("gru_small")
     m = mirror_model(case).cuda()

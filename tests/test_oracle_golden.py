@@ -47,6 +47,21 @@ def test_oracle_manual_backward_matches_reference_fp64(name, variant, act):
         assert rel_err(g[n], g_ref) < (2e-7 if big else 1e-9), n
 
 
+# the horizons the benchmark is quoted on (BASELINE.json configs[1]-[3]): T = 64 at 32x32 (B = 8), hGRU likewise,
+# T = 128 at 64x64 (B = 2).  Fixtures = the unmodified reference in fp64 (oracle/gen_golden.py long).
+LONG_CASES = [("int_t64", "int"), ("hgru_t64", "hgru"), ("int_t128_64px", "int")]
+
+
+@pytest.mark.parametrize("name,variant", LONG_CASES)
+def test_oracle_long_horizon_matches_reference_fp64(name, variant):
+    case = load_case(name)
+    logits, loss, g = _autograd(case, variant, "softplus", False)
+    assert rel_err(logits, case["logits"]) < 1e-10
+    assert abs(loss - case["loss"]) < 1e-10
+    for n, g_ref in case["grads"].items():
+        assert rel_err(g[n], g_ref) < (2e-7 if g_ref.numel() > 4096 else 1e-8), n
+
+
 def test_oracle_testmode_outputs():
     for name, variant in (("int_small", "int"), ("hgru_small", "hgru")):
         case = load_case(name)
