@@ -213,11 +213,6 @@ PTK_API int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_
 PTK_API void ptk_profile_start(void);
 PTK_API int ptk_profile_stop(double* ms, long long* count);
 PTK_API long long ptk_launch_count(void);
-/* tuning aids: in-kernel cycle stamps of CTA 0 of the last tcgen05 conv / weight-gradient launch */
-PTK_API int ptk_debug_tc_stamps(long long* out);
-PTK_API int ptk_debug_wt_stamps(long long* out);
-PTK_API int ptk_debug_tc_times(unsigned long long* out, int n_ctas);   /* per conv CTA: start, MMAs done, end (globaltimer ns) */
-PTK_API int ptk_debug_pw_stamps(unsigned long long* out4);   /* globaltimer at entry / after the PDL wait of int_post_kernel's CTA 0 */
 
 #ifdef __cplusplus
 }

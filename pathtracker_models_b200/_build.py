@@ -32,11 +32,15 @@ def build(force=False, verbose=False):
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("PTK_DEBUG_STAMPS") == "1":     # tuning build (tools/step_stamps.py, gap_probe.py, ...): never shipped
+        flags.append("-DPTK_DEBUG_STAMPS=1")
+        force = True
     jobs = []
     for s in SOURCES:
         src, obj = os.path.join(CSRC, s), os.path.join(objdir, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else []))
+            jobs.append([nvcc, *flags, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else []))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

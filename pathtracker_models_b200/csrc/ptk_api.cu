@@ -36,6 +36,12 @@ static int check_dims(const PtkDims* d, const char* who) {
               d->T, d->H, d->W);
     return PTK_EINVAL;
   }
+  // the readout kernels keep two zero-padded maps (+ one plain map in backward) of a whole frame in shared memory
+  if (((size_t)2 * (d->H + 4) * (d->W + 4) + (size_t)d->H * d->W) * sizeof(float) > (size_t)227 * 1024) {
+    set_error("%s: frame %dx%d too large: the readout tile (2 (H+4)(W+4) + H W floats) exceeds the 227 KB of shared memory per CTA",
+              who, d->H, d->W);
+    return PTK_EUNSUPPORTED;
+  }
   if (d->cell != PTK_CELL_INT && d->cell != PTK_CELL_HGRU) { set_error("%s: bad cell %d", who, d->cell); return PTK_EINVAL; }
   if (d->act != PTK_ACT_SOFTPLUS && d->act != PTK_ACT_TANH) { set_error("%s: bad act %d", who, d->act); return PTK_EINVAL; }
   if (d->no_inh && d->cell != PTK_CELL_INT) { set_error("%s: no_inh exists for the InT cell only (models/InT.py:167)", who); return PTK_EINVAL; }
@@ -269,10 +275,12 @@ int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transp
   return launch_conv7(a, st);
 }
 
+#if PTK_DEBUG_STAMPS   // tuning builds only (tools/): not declared in include/ptk_b200.h, not in the shipped library
 PTK_API int ptk_debug_tc_stamps(long long* out) { return read_tc_debug(out); }
 PTK_API int ptk_debug_wt_stamps(long long* out) { return read_wt_debug(out); }
 PTK_API int ptk_debug_tc_times(unsigned long long* out, int n) { return read_tc_times(out, n); }
 PTK_API int ptk_debug_pw_stamps(unsigned long long* out) { return read_pw_stamps(out); }
+#endif
 
 size_t ptk_lstm_wide_op_workspace_bytes(int32_t K) {
   if (K != 7 && K != 15) return 0;

@@ -42,8 +42,11 @@ void set_error(const char* fmt, ...);
 static __device__ __noinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
 static __device__ __noinline__ float softplus_precise(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 static __device__ __noinline__ float tanh_precise(float x) { return tanhf(x); }
-// MUFU-based variants (ex2.approx / lg2.approx / rcp.approx, ~2 ulp): used by the split-bf16 tensor-core
-// mode, whose convolutions are already ~1e-5 accurate; same parity gate (tests/test_parity_gpu.py).
+// MUFU-based variants (ex2.approx / lg2.approx / rcp.approx): used by the split-bf16 tensor-core mode, whose
+// convolutions are already ~1e-5 accurate; same parity gate (tests/test_parity_gpu.py).  Accuracy: sigmoid ~2 ulp.
+// softplus_fast is accurate in ABSOLUTE terms only (~6e-8): for x < -10 the sum 1 + e^x rounds in fp32, so the
+// RELATIVE error of the tiny result grows to 1e-3 and reaches 100 % below x ~ -16 (the result flushes to 0 where the
+// exact value is < 1.2e-7).  Every use adds the result to O(1) quantities, so absolute accuracy is what the gate needs.
 static __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 static __device__ __forceinline__ float softplus_fast(float x) {
   return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x)));   // = log(1 + e^x), no overflow, threshold-free

@@ -52,10 +52,19 @@ __host__ __device__ constexpr size_t tc_woff(int ky, int kx, int n, int k, bool 
 constexpr int TC_NST = 3;                              // weight ring stages
 constexpr int TC_SMEM = TC_A_BYTES + TC_NST * TC_STAGE + 256;
 
+// Tuning instrumentation (tools/step_stamps.py, gap_probe.py, conv_cta_times.py): compiled in only with -DPTK_DEBUG_STAMPS=1
+// (PTK_DEBUG_STAMPS=1 python -m pathtracker_models_b200._build --force); the shipped library carries none of it.
+#if PTK_DEBUG_STAMPS
+constexpr int TC_TIMES_MAX = 1024;
 __device__ long long g_tc_dbg[8];
-__device__ unsigned long long g_tc_times[1024][3];   // per CTA: start, mma-done, end (globaltimer ns)
+__device__ unsigned long long g_tc_times[TC_TIMES_MAX][3];   // per CTA: start, mma-done, end (globaltimer ns)
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TC_STAMP(i) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == 64) g_tc_dbg[i] = clock64(); } while (0)
+#define TC_TIME(cta, i) do { if (threadIdx.x == 64 && (cta) < TC_TIMES_MAX) g_tc_times[cta][i] = gtimer(); } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#define TC_TIME(cta, i) do { } while (0)
+#endif
 
 template <bool SINGLE>
 __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
@@ -77,8 +86,10 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   const size_t in_bs = a.in_bs ? (size_t)a.in_bs : (size_t)C * H * W, out_bs = a.out_bs ? (size_t)a.out_bs : (size_t)C * H * W;
 
   TC_STAMP(0);
+#if PTK_DEBUG_STAMPS
   const int dbg_cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][0] = gtimer();
+#endif
+  TC_TIME(dbg_cta, 0);
   // ---- one-time setup: barriers, TMEM, zero the operand image ------------------------------------
   if (tid == 0) {
     for (int i = 0; i < TC_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
   // ---- epilogue -----------------------------------------------------------------------------------
   mbar_wait(accum_bar, 0);
   TC_STAMP(3);
-  if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][1] = gtimer();
+  TC_TIME(dbg_cta, 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int quad = warp & 3, jpar = warp >> 2;   // warps 0-3: tiles 0,2,4; warps 4-7: tiles 1,3
   const int nCta = gridDim.x * gridDim.y * gridDim.z;
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
     if (stats) conv_stats_fold(a, nCta, TC_TH * TC_TW, sFin, &sIsLast);
   }
   TC_STAMP(4);
-  if (threadIdx.x == 64 && dbg_cta < 1024) g_tc_times[dbg_cta][2] = gtimer();
+  TC_TIME(dbg_cta, 2);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
@@ -364,7 +375,9 @@ int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
   return PTK_OK;
 }
 
+#if PTK_DEBUG_STAMPS
 int read_tc_times(unsigned long long* out, int n) {
+  if (n < 0 || n > TC_TIMES_MAX) { set_error("ptk_debug_tc_times: n = %d outside [0, %d]", n, TC_TIMES_MAX); return PTK_EINVAL; }
   PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_tc_times, sizeof(unsigned long long) * 3 * n));
   return PTK_OK;
 }
@@ -373,6 +386,7 @@ int read_tc_debug(long long* out) {
   PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_tc_dbg, sizeof(long long) * 8));
   return PTK_OK;
 }
+#endif
 
 int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride) {
   const int n = C * C * TAPS;

@@ -310,10 +310,15 @@ __device__ __forceinline__ void post_load(const float* Y1, const float* I2, cons
                                           size_t idx, PostIn& r) {
   r.y1 = ld4(Y1 + idx); r.i2 = ld4(I2 + idx); r.e = ld4(Et + idx); r.gx = ld4(Gx + idx);
 }
-__device__ unsigned long long g_pw_stamp[4];   // debug: globaltimer at entry / after the PDL wait of int_post_kernel's CTA 0
+#if PTK_DEBUG_STAMPS   // tuning instrumentation, not in the shipped library (see ptk_conv_tc.cu)
+__device__ unsigned long long g_pw_stamp[4];   // globaltimer at entry / after the PDL wait of int_post_kernel's CTA 0
+#define PW_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_pw_stamp[i])); } while (0)
+#else
+#define PW_STAMP(i) do { } while (0)
+#endif
 template <int ACT, bool NOINH>
 __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int has_next) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_pw_stamp[0]));
+  PW_STAMP(0);
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;
   float* sWau = sWaw + C * C;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
     frame_px(d.fv, b, t + 1, pix, d.W, xin);
   }
   pdl_wait();
-  if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_pw_stamp[1]));
+  PW_STAMP(1);
   pdl_launch_dependents();
   if (wt < nWT) {    // first tile: operands of channel 0
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
@@ -534,6 +539,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
     PTK_LAUNCH_OK("int_post_kernel");
   }
   const size_t sm = (size_t)2 * (d.H + 4) * (d.W + 4) * sizeof(float);
+  PTK_CUDA_OK(ptk_func_smem(int_readout_kernel, (int)sm));   // above the 48 KB default from 64x96 frames on
   {
     ProfileScope ps(PTK_PROF_MISC, st);
     int_readout_kernel<<<d.B, 256, sm, st>>>(d, d.E_at(d.T), d.logits);
@@ -547,10 +553,12 @@ static int run_forward_ni(const IntDev& d, int cell, cudaStream_t st) {
   return cell == CELL_NOINH ? run_forward_act<ACT, true>(d, cell, st) : run_forward_act<ACT, false>(d, cell, st);
 }
 
+#if PTK_DEBUG_STAMPS
 int read_pw_stamps(unsigned long long* out) {
   PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_pw_stamp, sizeof(unsigned long long) * 4));
   return PTK_OK;
 }
+#endif
 
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st) {
   const bool fast = (d.conv_mode != PTK_CONV_FP32);

@@ -70,15 +70,17 @@ int launch_fold_wgradk(const float* slots, int ks, int nbank, int ocb, int icb, 
                        int ic0 = 0, int ic_total = 0);
 
 int conv_num_ctas(int B, int H, int W);
-int read_pw_stamps(unsigned long long* out);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st);
 int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride = 0);   // 0 = 32*49 (dense)
 int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st);   // wacc: [nCTA][49][32 oc][32 ic]
 size_t wgrad_tc_acc_floats(int B, int H, int W);
+#if PTK_DEBUG_STAMPS   // tuning builds only (-DPTK_DEBUG_STAMPS=1): in-kernel cycle / globaltimer stamps
+int read_pw_stamps(unsigned long long* out);
 int read_tc_debug(long long* out);
 int read_wt_debug(long long* out);
-int read_tc_times(unsigned long long* out, int n);   // cycle stamps of CTA 0 of the last conv7_tc_kernel (tuning aid)
+int read_tc_times(unsigned long long* out, int n);
+#endif
 
 }  // namespace ptk

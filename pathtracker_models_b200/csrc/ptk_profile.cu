@@ -1,6 +1,7 @@
 // Optional in-library kernel timing + launch counting (used by bench.py, off by default).
 // When enabled, every kernel-class launch is bracketed by cudaEvents recorded on the launching
 // stream; ptk_profile_stop() synchronises those events and returns per-class totals.
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -10,8 +11,8 @@
 namespace ptk {
 
 static std::mutex g_mu;
-static bool g_on = false;
-static long long g_launches = 0;
+static std::atomic<bool> g_on{false};
+static std::atomic<long long> g_launches{0};   // the non-profiling path takes no lock
 struct Span { cudaEvent_t a, b; int kind; };
 static std::vector<Span> g_spans;
 static std::vector<cudaEvent_t> g_pool;
@@ -24,9 +25,10 @@ static cudaEvent_t get_event() {
 }
 
 ProfileScope::ProfileScope(int kind, cudaStream_t st, int n_launches) : idx_(-1), st_(st) {
+  g_launches.fetch_add(n_launches, std::memory_order_relaxed);
+  if (!g_on.load(std::memory_order_acquire)) return;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_launches += n_launches;
-  if (!g_on) return;
+  if (!g_on.load(std::memory_order_relaxed)) return;
   Span s{get_event(), get_event(), kind};
   cudaEventRecord(s.a, st);
   g_spans.push_back(s);
@@ -71,9 +73,6 @@ PTK_API int ptk_profile_stop(double* ms, long long* count) {
   return n;
 }
 
-PTK_API long long ptk_launch_count(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  return g_launches;
-}
+PTK_API long long ptk_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

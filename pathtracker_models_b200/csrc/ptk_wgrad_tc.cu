@@ -111,8 +111,12 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
   }
 }
 
+#if PTK_DEBUG_STAMPS   // tuning instrumentation, not in the shipped library (see ptk_conv_tc.cu)
 __device__ long long g_wt_dbg[8];
 #define WT_STAMP(i, t) do { if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && threadIdx.x == (t)) g_wt_dbg[i] = clock64(); } while (0)
+#else
+#define WT_STAMP(i, t) do { } while (0)
+#endif
 
 template <bool SINGLE>
 __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
@@ -255,10 +259,12 @@ __global__ void __launch_bounds__(256, 1) wgrad7_tc_kernel(WgradArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
 }
 
+#if PTK_DEBUG_STAMPS
 int read_wt_debug(long long* out) {
   PTK_CUDA_OK(cudaMemcpyFromSymbol(out, g_wt_dbg, sizeof(long long) * 8));
   return PTK_OK;
 }
+#endif
 
 size_t wgrad_tc_acc_floats(int B, int H, int W) { return (size_t)B * (H / WT_TH) * (W / WT_TW) * TAPS * C * C; }
 

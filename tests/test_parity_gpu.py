@@ -214,6 +214,8 @@ def test_errors_are_loud():
         m(torch.rand(2, 3, 4, 32, 32))                         # CPU tensor: no fallback
     with pytest.raises(_lib.PtkError):
         InT.InT(dimensions=32, timesteps=4, kernel_size=15).cuda()(torch.rand(1, 3, 2, 32, 32, device="cuda"))
+    with pytest.raises(_lib.PtkError, match="readout tile"):
+        m(torch.rand(1, 3, 1, 160, 160, device="cuda"))         # frame larger than the readout kernels' shared-memory tile
     d = _lib.PtkDims(1, 1, 32, 32, 32, 7, 0, 0, 0, 0)
     L = _lib.lib()
     rc = L.ptk_int_forward(ctypes.byref(d), None, None, None, None, None, None, None, None, 0, None)
@@ -337,7 +339,7 @@ def test_saliency_through_testmode_forward():
 
 
 @pytest.mark.parametrize("kind,B,T,H,W", [("int", 1, 1, 16, 32), ("int", 5, 2, 16, 64), ("hgru", 3, 3, 48, 32),
-                                           ("int", 2, 2, 64, 64), ("int", 96, 1, 32, 32)])
+                                           ("int", 2, 2, 64, 64), ("int", 96, 1, 32, 32), ("int", 1, 2, 96, 96)])
 def test_edge_shapes_vs_fp64_oracle(kind, B, T, H, W):
     """minimum tile (16x32), single sample / single frame, odd batch, non-square frames, a batch larger than the SM
     count: CUDA path vs the fp64 oracle on the same seeded inputs (the oracle is pinned to the reference on CPU).
