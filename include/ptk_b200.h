@@ -88,7 +88,10 @@ PTK_API int ptk_int_param_offsets(const PtkDims* d, int64_t* offsets);
  * pre-BatchNorm conv outputs, the three gates (A, G_i, G_e) and the 4*C batch statistics.  This replaces
  * the autograd tape of models/InT.py:223-235 (21 state-sized tensors/step in the reference). */
 PTK_API size_t ptk_int_saved_bytes(const PtkDims* d);
-PTK_API size_t ptk_int_workspace_bytes(const PtkDims* d);
+PTK_API size_t ptk_int_workspace_bytes(const PtkDims* d);            /* scratch of ptk_int_forward */
+/* scratch of ptk_int_backward: the forward scratch plus, in the tensor-core modes, every step's dY0 / dY1 / Ge
+ * ([T][B,C,H,W] each) for the 7x7 weight gradients, which are taken in one launch after the reverse loop */
+PTK_API size_t ptk_int_backward_workspace_bytes(const PtkDims* d);
 
 /* Forward of InT.forward / FFhGRU.forward (models/InT.py:210-245,
  * models/ffhgru_hierarchy.py:211-276): stem Conv3d(3->C)+nl, T cell steps (rCell.forward
@@ -204,6 +207,14 @@ PTK_API size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W);
 PTK_API int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transpose, int32_t accumulate,
                       const float* in, const float* weight, float* out, float* stats, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* The 7x7 weight gradient on its own (test / measurement entry), summed over T (input, output-gradient) pairs:
+ *   dweight[oc][ic][ky][kx] = sum_t sum_{b,y,x} dy[t][b,oc,y,x] * in[t][b,ic,y+ky-3,x+kx-3]
+ * i.e. the gradient autograd accumulates into w_inh / w_exc through F.conv2d(..., padding=3) (models/InT.py:161,172) over
+ * the time loop.  in, dy: [T][B,32,H,W] contiguous.  Tensor-core modes only (ptk_wgrad_ts.cu). */
+PTK_API size_t ptk_wgrad7_workspace_bytes(int32_t T, int32_t B, int32_t H, int32_t W);
+PTK_API int ptk_wgrad7(int32_t T, int32_t B, int32_t H, int32_t W, int32_t conv_mode, const float* in, const float* dy,
+                       float* dweight, void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* Measurement hooks (used by bench.py; off by default, no effect on results).
  * ptk_profile_start(): from now on every kernel-class launch is bracketed by cudaEvents on its stream.

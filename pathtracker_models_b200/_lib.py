@@ -15,7 +15,7 @@ PTK_CONV_FP32, PTK_CONV_BF16X3, PTK_CONV_BF16 = 0, 1, 2
 PTK_INT_NPARAM = 30
 
 EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_saved_bytes",
-           "ptk_int_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker",
+           "ptk_int_workspace_bytes", "ptk_int_backward_workspace_bytes", "ptk_wgrad7", "ptk_wgrad7_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker",
            "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes",
            "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
            "ptk_convlstm_forward", "ptk_convlstm_backward",
@@ -67,6 +67,12 @@ def lib():
     L.ptk_int_saved_bytes.argtypes = [dp]
     L.ptk_int_workspace_bytes.restype = sz
     L.ptk_int_workspace_bytes.argtypes = [dp]
+    L.ptk_int_backward_workspace_bytes.restype = sz
+    L.ptk_int_backward_workspace_bytes.argtypes = [dp]
+    L.ptk_wgrad7_workspace_bytes.restype = sz
+    L.ptk_wgrad7_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.ptk_wgrad7.restype = ctypes.c_int
+    L.ptk_wgrad7.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     L.ptk_int_forward.restype = ctypes.c_int
     L.ptk_int_forward.argtypes = [dp, vp, i64p, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_int_backward.restype = ctypes.c_int

@@ -65,7 +65,7 @@ struct Carver {
 static size_t state_elems(const PtkDims* d) { return (size_t)d->B * C * d->H * d->W; }
 
 // carve the workspace into the IntDev scratch pointers; returns bytes needed
-static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
+static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_bwd) {
   Carver cv(ws);
   const size_t S = state_elems(dm);
   const int pw = pw_grid(dm->B, dm->H, dm->W);
@@ -84,9 +84,12 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);
   float* dgoal = cv.take<float>(S / C);
   size_t wacc_n = (size_t)4 * WGRAD_GROUPS * TAPS * 256;
-  if (dm->conv_mode != PTK_CONV_FP32) wacc_n = wgrad_tc_acc_floats(dm->B, dm->H, dm->W);
+  if (dm->conv_mode != PTK_CONV_FP32) wacc_n = wgrad_ts_acc_floats(dm->T, dm->B, dm->H, dm->W);
   float* wacc_exc = cv.take<float>(wacc_n);
   float* wacc_inh = cv.take<float>(wacc_n);
+  // tensor-core modes, backward only: every step's dY0, dY1 and Ge stay live for the deferred weight gradient
+  const bool defer = dm->conv_mode != PTK_CONV_FP32 && with_bwd;
+  float* dys = cv.take<float>(defer ? 3 * (size_t)dm->T * S : 0);
   if (d) {
     d->Ge = Ge;
     d->bn_part = bn_part; d->counter = counter; d->pw_ctas = pw;
@@ -98,6 +101,8 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d) {
     d->dX = big + 5 * S; d->dS = big + 6 * S; d->giS = big + 7 * S; d->aS = big + 8 * S; d->Xs = big + 9 * S;
     d->cgI = big + 10 * S; d->cGe = big + 11 * S;
     d->GeB[0] = Ge; d->GeB[1] = big + 12 * S; d->gebB[0] = d->geb; d->gebB[1] = big + 13 * S;
+    d->dy_tstride = defer ? S : 0;
+    d->dYs[0] = dys; d->dYs[1] = dys + (defer ? (size_t)dm->T * S : 0); d->GeT = dys + (defer ? 2 * (size_t)dm->T * S : 0);
     // inference ring view of `big` (only used when saved == NULL)
     if (d->ck_ring) {
       d->ckI = big; d->ckE = big + 2 * S; d->ck_stride = S;
@@ -186,7 +191,11 @@ size_t ptk_int_saved_bytes(const PtkDims* d) {
 
 size_t ptk_int_workspace_bytes(const PtkDims* d) {
   if (check_dims(d, "ptk_int_workspace_bytes")) return 0;
-  return carve_workspace(d, nullptr, nullptr);
+  return carve_workspace(d, nullptr, nullptr, false);
+}
+size_t ptk_int_backward_workspace_bytes(const PtkDims* d) {
+  if (check_dims(d, "ptk_int_backward_workspace_bytes")) return 0;
+  return carve_workspace(d, nullptr, nullptr, true);
 }
 
 int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5], const float* params,
@@ -207,7 +216,7 @@ int ptk_int_forward(const PtkDims* dm, const float* x, const int64_t x_strides[5
   bind_params(&d, params);
   d.ck_ring = (saved == nullptr);
   if (saved) bind_saved(&d, dm, saved);
-  carve_workspace(dm, workspace, &d);
+  carve_workspace(dm, workspace, &d, false);
   const size_t S = state_elems(dm);
   if (gates) {   // testmode: the attention gate of every step goes straight into the [B,T,C,H,W] output
     d.A = gates; d.a_tstride = (long long)C * d.H * d.W; d.a_bstride = (long long)d.T * C * d.H * d.W;
@@ -230,8 +239,9 @@ int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[
     set_error("ptk_int_backward: NULL argument (forward must have been given a `saved` buffer)");
     return PTK_EINVAL;
   }
-  if (workspace_bytes < ptk_int_workspace_bytes(dm)) {
-    set_error("ptk_int_backward: workspace too small (%zu < %zu)", workspace_bytes, ptk_int_workspace_bytes(dm));
+  if (workspace_bytes < ptk_int_backward_workspace_bytes(dm)) {
+    set_error("ptk_int_backward: workspace too small (%zu < %zu = ptk_int_backward_workspace_bytes)", workspace_bytes,
+              ptk_int_backward_workspace_bytes(dm));
     return PTK_ENOMEM;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -241,7 +251,7 @@ int ptk_int_backward(const PtkDims* dm, const float* x, const int64_t x_strides[
   d.fv = FrameView{x, x_strides[0], x_strides[1], x_strides[2], x_strides[3], x_strides[4]};
   bind_params(&d, params);
   bind_saved(&d, dm, const_cast<void*>(saved));
-  carve_workspace(dm, workspace, &d);
+  carve_workspace(dm, workspace, &d, true);
   d.dlogits = dlogits; d.dparams = dparams; d.dx = dx;
   PTK_CUDA_OK(cudaMemsetAsync(d.counter, 0, 4 * sizeof(unsigned), st));
   if ((rc = prep(&d, params, st))) return rc;   // the workspace may have been reused since forward
@@ -310,6 +320,25 @@ int ptk_lstm_wide_op(int32_t B, int32_t H, int32_t W, int32_t K, int32_t op, con
   if ((rc = K == 15 ? launch_prep_weights_k<15>(banks, op, wstream, st) : launch_prep_weights_k<7>(banks, op, wstream, st))) return rc;
   ConvKArgs k{in, wstream, nullptr, op == 0 ? aux : nullptr, out, B, H, W, op == 0 ? 25 : 100, op == 0 ? 100 : 25, 0, nullptr};
   return K == 15 ? launch_convk_tc<15>(k, op, st) : launch_convk_tc<7>(k, op, st);
+}
+
+size_t ptk_wgrad7_workspace_bytes(int32_t T, int32_t B, int32_t H, int32_t W) {
+  if (T < 1 || B < 1 || H < 16 || W < 32 || H % 16 || W % 32) return 0;
+  return (wgrad_ts_acc_floats(T, B, H, W) * sizeof(float) + 255) & ~(size_t)255;
+}
+int ptk_wgrad7(int32_t T, int32_t B, int32_t H, int32_t W, int32_t conv_mode, const float* in, const float* dy,
+               float* dweight, void* workspace, size_t workspace_bytes, void* stream) {
+  PtkDims dm = {B, T, H, W, C, KS, 0, 0, 0, conv_mode};
+  int rc = check_dims(&dm, "ptk_wgrad7");
+  if (rc) return rc;
+  if (conv_mode == PTK_CONV_FP32) { set_error("ptk_wgrad7: tensor-core modes only (bf16x3, bf16)"); return PTK_EUNSUPPORTED; }
+  if (!in || !dy || !dweight || !workspace) { set_error("ptk_wgrad7: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_wgrad7_workspace_bytes(T, B, H, W)) { set_error("ptk_wgrad7: workspace too small"); return PTK_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long S = (long long)B * C * H * W;
+  WgradTsArgs a{in, S, dy, S, (float*)workspace, T, B, H, W, conv_mode, 0};
+  if ((rc = launch_wgrad7_ts(a, st))) return rc;
+  return launch_wgrad_ts_fold((const float*)workspace, wgrad_ts_ctas(T, B, H, W), dweight, st);
 }
 
 size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {

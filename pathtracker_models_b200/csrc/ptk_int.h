@@ -55,6 +55,10 @@ struct IntDev {
   float *GeB[2], *gebB[2]; // per-step-parity copies of Ge and geb (the fused bwd_d(t)+bwd_a(t-1) kernel writes step t-1's
                            // while gate_wgrad(t) still reads step t's)
   float *cgI, *cGe;        // data-gradient outputs of the two transposed convolutions (added by the consumers)
+  // tensor-core modes: the 7x7 weight gradients are taken once, after the reverse loop, over ALL steps
+  // (ptk_wgrad_ts.cu), so every step's dY0 / dY1 and Ge are kept: [T][B,C,P] each (dy_tstride = B*C*P, else 0)
+  float *dYs[2], *GeT;
+  size_t dy_tstride;
   int pw_ctas;             // grid of the backward point-wise kernels (fixed => deterministic slots)
   float* acc;              // [pw_ctas][ACC_N]
   float* gacc;             // [GATE_CTAS][GACC_N]
@@ -78,6 +82,9 @@ struct IntDev {
   __host__ __device__ float* Gi_at(int t) const { return Gi + y_stride * yslot(t); }
   __host__ __device__ float* Gex_at(int t) const { return Gex + y_stride * yslot(t); }
   __host__ __device__ float* A_at(int t) const { return A + (size_t)t * a_tstride; }
+  // gradient wrt the pre-BatchNorm conv output of BatchNorm `bn` at step t (dV / dU before bn_apply, dY after)
+  __host__ __device__ float* dAct_at(int t, int bn) const { return dy_tstride ? dYs[bn] + dy_tstride * t : dAct; }
+  __host__ __device__ float* GeB_at(int t) const { return dy_tstride ? GeT + dy_tstride * t : GeB[t & 1]; }
 };
 
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st);

@@ -137,8 +137,8 @@ __device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, size_t idx
   st4(d.gE + idx, oGE);
   st4(d.gI + idx, oGI);
   st4(d.gebB[t & 1] + idx, oGeb);
-  st4(d.dAct + idx, oDv);
-  st4(d.GeB[t & 1] + idx, oGe);
+  st4(d.dAct_at(t, 1) + idx, oDv);
+  st4(d.GeB_at(t) + idx, oGe);
 }
 __device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* sKa, float* sGa, float* sW1, float* sB1,
                                                  float* sM1, float* sR1) {
@@ -208,17 +208,18 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __
   const int P = d.H * d.W;
   const size_t n4 = (size_t)d.B * C * P / 4;
   const float* st = d.stat(t, bn);
+  float* dA = d.dAct_at(t, bn);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4 / P) % C);
     const float mean = st[c], rstd = st[C + c];
     const float k = __ldg(d.bn_w[bn] + c) * rstd, m = d.bn_tot[c], n = d.bn_tot[C + c];
-    float4 g = reinterpret_cast<float4*>(d.dAct)[i];
+    float4 g = reinterpret_cast<float4*>(dA)[i];
     const float4 y = reinterpret_cast<const float4*>(Y)[i];
     g.x = k * (g.x - m - (y.x - mean) * rstd * n);
     g.y = k * (g.y - m - (y.y - mean) * rstd * n);
     g.z = k * (g.z - m - (y.z - mean) * rstd * n);
     g.w = k * (g.w - m - (y.w - mean) * rstd * n);
-    reinterpret_cast<float4*>(d.dAct)[i] = g;
+    reinterpret_cast<float4*>(dA)[i] = g;
   }
 }
 
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   const float* At = d.A_at(t);
   const float* Y0 = d.Y0_at(t);
   const float* Git = d.Gi_at(t);
+  float* dU_out = d.dAct_at(t, 0);
   int wt = blockIdx.x * 4 + warp;
   BwdCIn cur;
   float xin[3][4];
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
         part[2] += dU;                         // -> sum dU
         part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
       }
-      st4(d.dAct + idx, oDu);
+      st4(dU_out + idx, oDu);
       st4(d.giS + idx, oGi);
       st4(d.Xs + idx, X);
       st4(d.dX + idx, oZ);        // parked: completed by the transposed products below
@@ -687,7 +689,7 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
   pdl_launch_dependents();
   const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
   const float* src[7] = {d.gebB[t & 1], d.giS, d.aS,
-                         (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB[t & 1], d.Xs, d.E_at(t)};
+                         (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB_at(t), d.Xs, d.E_at(t)};
   auto issue = [&](int tile, int buf) {
     const int b = tile / tpi, pix_base = (tile - b * tpi) * GPX;
     float* dstb = dsm + (size_t)buf * 7 * GT_F;
@@ -969,7 +971,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     PTK_CUDA_OK(cudaMemsetAsync(d.dX, 0, Sb, st));
     PTK_CUDA_OK(cudaMemsetAsync(d.giS, 0, Sb, st));
     PTK_CUDA_OK(cudaMemsetAsync(d.bn_acc, 0, 4 * C * sizeof(double), st));
-    PTK_CUDA_OK(cudaMemsetAsync(d.wacc_inh, 0, (tc ? wgrad_tc_acc_floats(d.B, d.H, d.W) : (size_t)4 * WGRAD_GROUPS * TAPS * 256) * sizeof(float), st));
+    PTK_CUDA_OK(cudaMemsetAsync(d.wacc_inh, 0, (tc ? wgrad_ts_acc_floats(d.T, d.B, d.H, d.W) : (size_t)4 * WGRAD_GROUPS * TAPS * 256) * sizeof(float), st));
   }
   const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
   PTK_CUDA_OK(ptk_func_smem(int_bwd_c_kernel<CELL, ACT>, (int)SM_BWD_C));
@@ -999,12 +1001,14 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       PTK_CUDA_OK(launch_pdl(true, bn_apply_kernel, dim3(ew_blocks), dim3(256), 0, st, d, (const float*)d.Y1_at(t), t, 1));
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c1{d.dAct, d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+    ConvArgs c1{d.dAct_at(t, 1), d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
-    WgradArgs w1{d.I_at(t + 1), d.dAct, d.wacc_exc, d.B, d.H, d.W, first, d.conv_mode};
-    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w1, st) : launch_wgrad7(w1, WGRAD_GROUPS, st); }
-    if (rc) return rc;
+    if (!tc) {   // strict fp32: per-step CUDA-core weight gradient (the tensor-core modes defer it, see below)
+      WgradArgs w1{d.I_at(t + 1), d.dAct_at(t, 1), d.wacc_exc, d.B, d.H, d.W, first, d.conv_mode};
+      { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w1, WGRAD_GROUPS, st); }
+      if (rc) return rc;
+    }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       PTK_CUDA_OK(launch_pdl(true, int_bwd_c_kernel<CELL, ACT>, dim3(grid_c), dim3(128), SM_BWD_C, st, d, t, first));
@@ -1016,12 +1020,14 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
         PTK_CUDA_OK(launch_pdl(true, bn_apply_kernel, dim3(ew_blocks), dim3(256), 0, st, d, (const float*)d.Y0_at(t), t, 0));
       }
       PTK_LAUNCH_OK("bn_apply_kernel");
-      ConvArgs c0{d.dAct, d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+      ConvArgs c0{d.dAct_at(t, 0), d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
       { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
-      WgradArgs w0{d.GeB[t & 1], d.dAct, d.wacc_inh, d.B, d.H, d.W, first, d.conv_mode};
-      { ProfileScope ps(PTK_PROF_WGRAD, st); rc = tc ? launch_wgrad7_tc(w0, st) : launch_wgrad7(w0, WGRAD_GROUPS, st); }
-      if (rc) return rc;
+      if (!tc) {
+        WgradArgs w0{d.GeB_at(t), d.dAct_at(t, 0), d.wacc_inh, d.B, d.H, d.W, first, d.conv_mode};
+        { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7(w0, WGRAD_GROUPS, st); }
+        if (rc) return rc;
+      }
     }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
@@ -1036,9 +1042,22 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     PTK_LAUNCH_OK("gate_wgrad_kernel");
   }
+  if (tc) {
+    // the two 7x7 weight gradients, each ONE launch over all T steps: dW_exc = sum_t I_{t+1} (star) dY1_t,
+    // dW_inh = sum_t Ge_t (star) dY0_t (accumulators stay in TMEM for the whole kernel, ptk_wgrad_ts.cu)
+    int rc;
+    WgradTsArgs w1{d.I_at(1), (long long)d.ck_stride, d.dYs[1], (long long)d.dy_tstride, d.wacc_exc, d.T, d.B, d.H, d.W, d.conv_mode, 1};
+    { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7_ts(w1, st); }
+    if (rc) return rc;
+    if (CELL != CELL_NOINH) {
+      WgradTsArgs w0{d.GeT, (long long)d.dy_tstride, d.dYs[0], (long long)d.dy_tstride, d.wacc_inh, d.T, d.B, d.H, d.W, d.conv_mode, 1};
+      { ProfileScope ps(PTK_PROF_WGRAD, st); rc = launch_wgrad7_ts(w0, st); }
+      if (rc) return rc;
+    }
+  }
   FinalizeArgs f;
   f.pw_ctas = PW_EW_CTAS; f.gate_ctas = gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
-  f.wgrad_tc = tc ? conv_num_ctas(d.B, d.H, d.W) : 0;
+  f.wgrad_tc = tc ? wgrad_ts_ctas(d.T, d.B, d.H, d.W) : 0;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
   {

@@ -30,6 +30,23 @@ struct WgradArgs {
   long long in_bs = 0, dy_bs = 0;    // elements between samples (0 = 32*H*W), as in ConvArgs
 };
 
+// weight gradient of the 7x7 convolutions summed over a whole sequence in ONE launch (ptk_wgrad_ts.cu): accumulators
+// resident in TMEM, A operand (dY) fed from TMEM, persistent CTAs; slots [ctas][49][32 oc][32 ic] written once
+struct WgradTsArgs {
+  const float* in;      // conv inputs  [T][B,32,H,W] (time stride in_ts elements)
+  long long in_ts;
+  const float* dy;      // gradients wrt the conv outputs [T][B,32,H,W] (time stride dy_ts elements)
+  long long dy_ts;
+  float* wacc;          // wgrad_ts_acc_floats() floats
+  int T, B, H, W;
+  int mode;             // PTK_CONV_BF16: single pass (hi parts only)
+  int pdl = 0;
+};
+int wgrad_ts_ctas(int T, int B, int H, int W);
+size_t wgrad_ts_acc_floats(int T, int B, int H, int W);
+int launch_wgrad7_ts(const WgradTsArgs& a, cudaStream_t st);
+int launch_wgrad_ts_fold(const float* wacc, int nslots, float* dw, cudaStream_t st);
+
 // wide recurrent convolutions on tcgen05 (ptk_convk_tc.cu; ConvLSTM): fp32 NCHW in / out, prepared bf16 hi/lo weight stream
 struct ConvKArgs {
   const float* in;      // [B, Cin, H, W]

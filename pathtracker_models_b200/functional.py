@@ -39,8 +39,8 @@ def _check_inputs(x, flat):
         raise _lib.PtkError("parameters and input are on different devices")
 
 
-def _buffers(L, dims, device, want_saved):
-    ws_bytes = L.ptk_int_workspace_bytes(ctypes.byref(dims))
+def _buffers(L, dims, device, want_saved, backward=False):
+    ws_bytes = (L.ptk_int_backward_workspace_bytes if backward else L.ptk_int_workspace_bytes)(ctypes.byref(dims))
     if ws_bytes == 0:
         _lib.check(1, "ptk_int_workspace_bytes")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
@@ -104,7 +104,7 @@ class _IntFunction(torch.autograd.Function):
         flat = flat.contiguous()
         dlogits = dlogits.contiguous().float()
         with torch.cuda.device(x.device):
-            ws, ws_bytes, _ = _buffers(L, dims, x.device, False)
+            ws, ws_bytes, _ = _buffers(L, dims, x.device, False, backward=True)
             dflat = torch.empty_like(flat)
             dx = torch.empty(x.shape, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[0] else None
             stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
@@ -149,6 +149,24 @@ def conv7(x, weight, conv_mode=_lib.PTK_CONV_FP32, transpose=False, out=None, wa
                          _ptr(stats), _ptr(ws), nbytes, stream)
         _lib.check(rc, "ptk_conv7")
     return (out, stats) if want_stats else out
+
+
+def wgrad7(inp, dy, conv_mode=_lib.PTK_CONV_BF16X3):
+    """the 7x7 weight gradient summed over T (input, output-gradient) pairs through ptk_wgrad7 (test / measurement
+    entry).  inp, dy: [T,B,32,H,W] -> dW [32,32,7,7]."""
+    L = _lib.lib()
+    T, B, Cc, H, W = inp.shape
+    inp, dy = inp.contiguous().float(), dy.contiguous().float()
+    with torch.cuda.device(inp.device):
+        out = torch.empty(Cc, Cc, 7, 7, dtype=torch.float32, device=inp.device)
+        nbytes = L.ptk_wgrad7_workspace_bytes(T, B, H, W)
+        if nbytes == 0:
+            _lib.check(1, "ptk_wgrad7_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=inp.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(inp.device).cuda_stream)
+        rc = L.ptk_wgrad7(T, B, H, W, conv_mode, _ptr(inp), _ptr(dy), _ptr(out), _ptr(ws), nbytes, stream)
+        _lib.check(rc, "ptk_wgrad7")
+    return out
 
 
 def lstm_wide_op(op, x, weights, aux=None):

@@ -250,6 +250,29 @@ def test_conv7_operator_vs_torch(mode, shape):
     assert torch.equal(y, y2)                       # deterministic
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("shape", [(1, 1, 16, 32), (3, 3, 16, 64), (2, 2, 64, 64), (5, 7, 32, 32), (2, 64, 32, 32)])
+def test_wgrad7_operator_vs_torch(mode, shape):
+    """ptk_wgrad7 (ptk_wgrad_ts.cu: the 7x7 weight gradient summed over a whole sequence in one launch, accumulators and
+    the dY operand in TMEM) against torch autograd in fp64: single tile, ragged batch, frames wider / taller than a tile
+    (real halo columns), more work items than CTAs.  mode 1 = 3-pass split-bf16 (fp32-parity), 2 = single-pass bf16."""
+    import torch.nn.functional as F
+    from pathtracker_models_b200.functional import wgrad7
+    T, B, H, W = shape
+    g = torch.Generator().manual_seed(T * 100 + B + mode)
+    inp = torch.randn(T, B, 32, H, W, generator=g) * torch.rand(1, 1, 32, 1, 1, generator=g) * 2
+    dy = torch.randn(T, B, 32, H, W, generator=g) * 0.1
+    w = torch.zeros(32, 32, 7, 7, dtype=torch.float64, device="cuda", requires_grad=True)
+    tot = sum((F.conv2d(inp[t].double().cuda(), w, padding=3) * dy[t].double().cuda()).sum() for t in range(T))
+    tot.backward()
+    got = wgrad7(inp.cuda(), dy.cuda(), conv_mode=mode)
+    e = rel_err(got, w.grad)
+    assert e < (3e-5 if mode == 1 else 2e-2), e
+    if mode == 2:
+        assert e > 1e-5                                         # really the single-pass mode
+    assert torch.equal(got, wgrad7(inp.cuda(), dy.cuda(), conv_mode=mode))      # deterministic
+
+
 def test_device_prefetcher_copies_every_batch():
     from pathtracker_models_b200.data import DevicePrefetcher
     host = [(torch.randn(4, 8).pin_memory(), torch.randn(4, 1).pin_memory()) for _ in range(4)]
