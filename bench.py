@@ -9,7 +9,11 @@ synthetic 64-frame 32x32 PathTracker, 14 distractors, batch 64 per GPU (BASELINE
 One JSON line on stdout (rank 0).  A "step" = one forward + backward pass over one batch of 64 clips
 per GPU; the optimizer step is excluded (SURVEY 8d).  `value` = clips/s with inputs resident in HBM;
 `e2e` = the same through the nn.Module API from pinned HOST buffers (H2D inside the timed region,
-loss read back to the host every step).
+loss read back to the host every step).  At N = 1 the line also carries
+  `parity`         one un-timed check of loss + every gradient of the CUDA path against the CPU port on the
+                   cpu_baseline sample (same weights, same clips),
+  `other_configs`  BASELINE.json configs[2]-[4] (InT 128 frames 64x64; FFhGRU fp32-parity and bf16; ConvLSTM),
+                   each with value / ms_per_step / e2e / roofline / cpu_baseline, short runs (--no-extra skips them).
 """
 import argparse
 import json
@@ -21,19 +25,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "train seq/s (fwd+bwd) InT 64-frame PathTracker"
 UNIT = "seq/s"
 B_PER_GPU, T, HW, DIST, SPEED = 64, 64, 32, 14, 1
 C, K = 32, 7
-# algorithmic FLOPs (1 MAC = 2 FLOP; recompute not counted)
-FWD_FLOP_PER_SEQ = T * HW * HW * (2 * (2 * C * C * K * K) + 6 * (2 * C * C) + 2 * 3 * C) + HW * HW * (2 * C + 100)
-BWD_FLOP_PER_SEQ = 2 * T * HW * HW * (2 * (2 * C * C * K * K) + 6 * (2 * C * C)) + T * HW * HW * 6 * C + 2 * HW * HW * (2 * C + 100)
-FLOP_PER_SEQ = FWD_FLOP_PER_SEQ + BWD_FLOP_PER_SEQ          # 41.902 GFLOP
-CONV_FLOP_PER_LAUNCH = 2 * B_PER_GPU * HW * HW * C * C * K * K  # one 7x7 conv over the per-GPU batch: 6.58 GFLOP
 FP32_FFMA_PEAK_TFLOPS = 74.4   # nominal 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the headline shape, from the
-# committed `ncu --set full` captures (profiles/r1e_tc_kernels_full.txt, profiles/r1a_conv7_ffma_full.txt)
-NCU_TRAFFIC_BYTES = {"bf16x3": 8.650e6, "fp32": 8.623e6}   # dram read + write per conv launch, profiles/r1i_kernels_full.txt
+# committed `ncu --set full` capture named in NCU_TRAFFIC_SOURCE (bench.py cannot run ncu on itself)
+NCU_TRAFFIC_BYTES = {"bf16x3": 8.650e6, "fp32": 8.623e6}
+NCU_TRAFFIC_SOURCE = "profiles/r1k_kernels_full.txt"
+
+
+def int_flop_per_seq(T_, HW_):
+    """algorithmic FLOPs of one InT / FFhGRU sequence, fwd + bwd (1 MAC = 2 FLOP; recompute not counted)"""
+    px = HW_ * HW_
+    fwd = T_ * px * (2 * (2 * C * C * K * K) + 6 * (2 * C * C) + 2 * 3 * C) + px * (2 * C + 100)
+    bwd = 2 * T_ * px * (2 * (2 * C * C * K * K) + 6 * (2 * C * C)) + T_ * px * 6 * C + 2 * px * (2 * C + 100)
+    return fwd + bwd
+
+
+def metric_name(model, frames, eval_only=False):
+    fam = {"int": "InT", "hgru": "FFhGRU", "convlstm": "ConvLSTM", "gru": "kys.GRU"}[model]
+    if eval_only:
+        return "eval seq/s (fwd only) %s %d-frame PathTracker" % (fam, frames)
+    return "train seq/s (fwd+bwd) %s %d-frame PathTracker" % (fam, frames)
 
 
 def load_peaks():
@@ -89,28 +103,66 @@ def _host_cores():
     return max(1, min(avail, phys))
 
 
-def cpu_reference_seq_per_s(steps, warmup, batch=8):
-    """the reference algorithm on the host cores: oracle port (torch CPU ops + autograd), fp32,
-    fwd + BCE + bwd on a bounded sample of the headline workload (batch `batch` instead of 64)."""
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference ALGORITHM on the host cores.  /root/reference is Python and absent on the GPU box, so this is
+# the oracle port (oracle/int_oracle.py: torch CPU ops + autograd, fp32; 1x1 gates as einsum), `kind: "port"`.
+def cpu_port_int(steps, warmup, batch=8, frames=T, size=HW, variant="int", keep_last=False):
+    """fwd + BCE + bwd of the InT / FFhGRU restatement on a bounded sample of the workload (batch `batch`).
+    returns (seq/s, s/pass, threads, sample description[, loss, grads by state_dict key])"""
     import torch
     import torch.nn.functional as F
     from oracle import int_oracle as O
     from oracle.synth_oracle import synth
-    from pathtracker_models_b200 import InT
+    from pathtracker_models_b200 import InT, ffhgru_hierarchy
     torch.set_num_threads(_host_cores())   # torchrun exports OMP_NUM_THREADS=1: the CPU arm still gets every core
     torch.manual_seed(0)
-    m = InT.InT(dimensions=C, timesteps=T, kernel_size=K)
+    ctor = InT.InT if variant == "int" else ffhgru_hierarchy.FFhGRU
+    m = ctor(dimensions=C, timesteps=frames, kernel_size=K)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     p = O.unpack(sd, dtype=torch.float32)
     for v in p.values():
         v.requires_grad_(True)
-    xn, yn = synth(1234, 0, batch, T, HW, HW, DIST, SPEED)
+    xn, yn = synth(1234, 0, batch, frames, size, size, DIST, SPEED)
     x, y = torch.from_numpy(xn), torch.from_numpy(yn).view(batch, 1)
+    times, last = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        logits, _ = O.forward(x, p, variant, keep=False)
+        loss = F.binary_cross_entropy_with_logits(logits, y)
+        loss.backward()
+        if keep_last and i == warmup + steps - 1:
+            last = (loss.item(), O.grad_to_state_keys({k: v.grad.clone() for k, v in p.items() if v.grad is not None}, sd))
+        for v in p.values():
+            v.grad = None
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    desc = "%s fwd+bwd, batch %d, T=%d, %dx%d, fp32, %d timed passes after %d warm-up" % (
+        "InT" if variant == "int" else "FFhGRU", batch, frames, size, size, len(times), warmup)
+    res = (batch * len(times) / tot, tot / len(times), torch.get_num_threads(), desc)
+    return res + last if keep_last else res
+
+
+def cpu_port_convlstm(steps, warmup, batch, frames, size, gabor):
+    import torch
+    import torch.nn.functional as F
+    from oracle import convlstm_oracle as CO
+    from pathtracker_models_b200 import convlstm
+    torch.set_num_threads(_host_cores())
+    torch.manual_seed(0)
+    m = convlstm.ConvLSTM(timesteps=frames, filt_size=15, gabor=gabor)
+    p = CO.unpack(m.state_dict(), dtype=torch.float32)
+    for v in p.values():
+        v.requires_grad_(True)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(batch, 1, size, size, generator=g)
+    tgt = (torch.rand(batch, size, size, generator=g) > 0.5).long()
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        logits, _ = O.forward(x, p, keep=False)
-        F.binary_cross_entropy_with_logits(logits, y).backward()
+        out, _ = CO.forward(x, p, frames)
+        F.cross_entropy(out, tgt).backward()
         for v in p.values():
             v.grad = None
         dt = time.perf_counter() - t0
@@ -118,7 +170,8 @@ def cpu_reference_seq_per_s(steps, warmup, batch=8):
             times.append(dt)
     tot = sum(times)
     return batch * len(times) / tot, tot / len(times), torch.get_num_threads(), \
-        f"InT fwd+bwd, batch {batch} (of 64), T={T}, {HW}x{HW}, fp32, {len(times)} timed passes after {warmup} warm-up"
+        "ConvLSTM filt 15 fwd+bwd (input-path convolutions hoisted, no penalty branch), batch %d, timesteps=%d, %dx%d, fp32, " \
+        "%d timed passes after %d warm-up" % (batch, frames, size, size, len(times), warmup)
 
 
 def gpu_eager_reference(args):
@@ -156,7 +209,7 @@ def gpu_eager_reference(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         out["tf32_on" if tf32 else "tf32_off"] = {"value": args.batch / (ms / 1e3), "ms_per_step": ms}
-    print(json.dumps({"impl": "reference-gpu-eager", "metric": METRIC, "unit": UNIT, "n_gpus": 1, "steps": steps,
+    print(json.dumps({"impl": "reference-gpu-eager", "metric": metric_name("int", T), "unit": UNIT, "n_gpus": 1, "steps": steps,
                       "warmup": warmup, "value": out["tf32_off"]["value"], "ms_per_step": out["tf32_off"]["ms_per_step"],
                       "tf32_on": out["tf32_on"], "tf32_off": out["tf32_off"], "dtype": "f32", "data": "synthetic",
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
@@ -170,23 +223,225 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    v, sec, cores, sample = cpu_reference_seq_per_s(steps, warmup)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    v, sec, cores, sample = cpu_port_int(steps, warmup)
+    line = {"impl": "reference", "metric": metric_name("int", T), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "InT 64 frames 32x32, 14 distractors, batch 64/GPU (BASELINE configs[1])",
-                       "note": "CPU arm: each step is a bounded sample (batch 8) of that workload on the host cores"},
+                       "note": "CPU arm: the reference ALGORITHM as restated in oracle/int_oracle.py (torch CPU ops + autograd; the "
+                               "reference itself is Python and is not on the GPU box); each step is a bounded sample (batch 8 of "
+                               "64) of that workload on the host cores"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+class Timer:
+    """device timing of K steps on the current stream, max over ranks"""
+
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(self, fn, n):
+        import torch
+        import torch.distributed as dist
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        fn(n)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+
+def make_e2e_runner(step, host_batches, dev, to_device_view=None):
+    """every step: its inputs go pinned host -> device (one batch in flight on a copy stream) and its loss comes back to
+    the host.  The loss is copied asynchronously into pinned memory and READ one step later (how a training loop logs
+    it), so the device never idles on the host; the last value is read after the loop."""
+    import torch
+    from pathtracker_models_b200.data import DevicePrefetcher
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    nb = len(host_batches)
+
+    def e2e_run(n):
+        seen = []
+        for i, batch in enumerate(DevicePrefetcher((host_batches[j % nb] for j in range(n)), dev)):
+            if to_device_view is not None:
+                batch = to_device_view(batch)
+            loss = step(*batch)
+            loss_host[i & 1:(i & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                seen.append(float(loss_host[(i - 1) & 1]))
+        loss_ev[(n - 1) & 1].synchronize()
+        seen.append(float(loss_host[(n - 1) & 1]))
+        assert len(seen) == n and all(v == v for v in seen)
+
+    return e2e_run
+
+
+def measure(step, batches, host_batches, steps, warmup, timer, per_step_units, to_device_view=None):
+    """resident-input throughput + end-to-end throughput of `step` (same K steps each); returns a dict"""
+    from pathtracker_models_b200 import _lib
+    nb = len(batches)
+    for i in range(warmup):
+        step(*batches[i % nb])
+    l0 = _lib.launch_count()
+    ms = timer.run(lambda n: [step(*batches[i % nb]) for i in range(n)], steps)
+    launches = _lib.launch_count() - l0
+    e2e_run = make_e2e_runner(step, host_batches, timer.dev, to_device_view)
+    e2e_run(2)
+    ms2 = timer.run(e2e_run, steps)
+    h2d = int(sum(t.numel() * t.element_size() for t in host_batches[0]))
+    return {"value": timer.world * per_step_units * steps / (ms / 1e3), "ms_per_step": ms / steps, "gpu_launches": launches,
+            "e2e": {"value": timer.world * per_step_units * steps / (ms2 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4}}
+
+
+def int_batches(B, T_, HW_, rank, world, dev, nbuf):
+    from pathtracker_models_b200 import synth_pathtracker
+    from pathtracker_models_b200.parallel import shard_first_index
+    batches = [synth_pathtracker(B, T_, HW_, HW_, n_distractors=DIST, speed=SPEED, seed=1234,
+                                 first_index=shard_first_index(i, rank, world, B), device=dev) for i in range(nbuf)]
+    # host clips: pinned float32 with channels_last_3d strides, as utils/engine.py:222-243 hands them over
+    host = [(b[0].permute(0, 2, 3, 4, 1).contiguous().cpu().pin_memory(), b[1].cpu().pin_memory()) for b in batches]
+    return batches, host
+
+
+def parity_vs_cpu_port(model, dev):
+    """one un-timed pass of the CUDA path on the cpu_baseline sample (batch 8, same seed-0 weights, same clips) against
+    the CPU port: loss and every parameter gradient.  Also times the port (this IS the cpu_baseline leg)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle.synth_oracle import synth
+    v, sec, cores, sample, loss_cpu, g_cpu = cpu_port_int(steps=12, warmup=1, keep_last=True)
+    xn, yn = synth(1234, 0, 8, T, HW, HW, DIST, SPEED)
+    x, y = torch.from_numpy(xn).to(dev), torch.from_numpy(yn).view(8, 1).to(dev)
+    model.zero_grad(set_to_none=True)
+    out, _ = model(x)
+    loss = F.binary_cross_entropy_with_logits(out, y)
+    loss.backward()
+    worst, worst_name = 0.0, None
+    for n, p in model.named_parameters():
+        if p.grad is None or n not in g_cpu:
+            continue
+        ref = g_cpu[n].double()
+        e = (p.grad.double().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-300)
+        if e > worst:
+            worst, worst_name = e, n
+    model.zero_grad(set_to_none=True)
+    parity = {"sample": "batch 8, T=64, 32x32 (the cpu_baseline sample), seed-0 weights", "checker": "CPU port, fp32 (oracle/int_oracle.py)",
+              "loss_abs_err": abs(loss.item() - loss_cpu), "grad_rel_err_max": worst, "grad_worst_tensor": worst_name,
+              "note": "max|a-b|/max|b| per tensor; both sides are fp32 here, the fp64-arbitrated gate lives in tests/ (T=64 and "
+                      "T=128 fixtures generated by the reference itself)"}
+    return parity, {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+
+def run_other_configs(args, dev, timer, tensor_peak, peak_src):
+    """BASELINE.json configs[2]-[4] at N = 1: short runs, same measurement rules as the headline."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from pathtracker_models_b200 import InT, _lib, convlstm, ffhgru_hierarchy
+    steps, warmup = 4, 3
+    out = []
+
+    def roof(value, flop_per_unit, third):
+        tf = value * flop_per_unit / 1e12
+        r = {"bound": "tensor", "achieved": tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tf / tensor_peak,
+             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peak_src, "traffic": None,
+             "note": "whole step, algorithmic FLOPs / step time"}
+        if third:
+            r["frac_of_third_peak"] = 3 * tf / tensor_peak
+            r["note"] += "; 3-pass split-bf16: fp32-parity ceiling = 1/3 of the bf16 peak"
+        return r
+
+    def int_like(tag, ctor, B, T_, HW_, mode, baseline_cfg, cpu_batch):
+        torch.manual_seed(0)
+        model = ctor(dimensions=C, timesteps=T_, kernel_size=K).to(dev)
+        model.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "bf16": _lib.PTK_CONV_BF16}[mode]
+        batches, host = int_batches(B, T_, HW_, 0, 1, dev, 2)
+
+        def step(x, y):
+            model.zero_grad(set_to_none=True)
+            o, _ = model(x)
+            loss = F.binary_cross_entropy_with_logits(o, y)
+            loss.backward()
+            return loss
+
+        r = measure(step, batches, host, steps, warmup, timer, B, lambda b: (b[0].permute(0, 4, 1, 2, 3), b[1]))
+        fam = "int" if ctor is InT.InT else "hgru"
+        r.update({"metric": metric_name(fam, T_), "unit": UNIT, "steps": steps, "warmup": warmup,
+                  "dtype": "bf16" if mode == "bf16" else "f32",
+                  "config": {"workload": "%s %d frames %dx%d, 14 distractors, batch %d/GPU (%s)" % (
+                      "InT" if fam == "int" else "FFhGRU", T_, HW_, HW_, B, baseline_cfg), "conv_mode": mode},
+                  "roofline": roof(r["value"], int_flop_per_seq(T_, HW_), mode == "bf16x3")})
+        if cpu_batch and not args.no_cpu_baseline:
+            v, sec, cores, sample = cpu_port_int(steps=2, warmup=1, batch=cpu_batch, frames=T_, size=HW_, variant=fam)
+            r["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        del model, batches, host
+        torch.cuda.empty_cache()
+        return r
+
+    out.append(int_like("cfg3", InT.InT, 16, 128, 64, "bf16x3", "BASELINE configs[2]", 1))
+    out.append(int_like("cfg4", ffhgru_hierarchy.FFhGRU, B_PER_GPU, T, HW, "bf16x3", "BASELINE configs[3], fp32-parity variant", 4))
+    out.append(int_like("cfg4b", ffhgru_hierarchy.FFhGRU, B_PER_GPU, T, HW, "bf16", "BASELINE configs[3], bf16 variant: single-pass "
+                        "bf16 MMAs, not fp32-parity", 0))
+    out.append(int_like("cfg2b", InT.InT, B_PER_GPU, T, HW, "bf16", "BASELINE configs[1] shape, bf16 variant: single-pass bf16 MMAs, "
+                        "not fp32-parity", 0))
+
+    # ConvLSTM (BASELINE configs[4]): timesteps = 64, filt 15, x [64,1,32,32], CrossEntropy, train mode (penalty branch runs)
+    gpath = os.path.join(ROOT, "tests", "golden", "convlstm_k7_small.npz")
+    gabor = torch.from_numpy(np.load(gpath)["gabor"]).float()       # the reference's utils/gabor_serre.npy, kept as a fixture
+    torch.manual_seed(0)
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=15, gabor=gabor).to(dev).train()
+    m.conv_mode = _lib.PTK_CONV_BF16X3
+    g = torch.Generator().manual_seed(1)
+    host = [(torch.rand(B_PER_GPU, 1, HW, HW, generator=g).pin_memory(),
+             (torch.rand(B_PER_GPU, HW, HW, generator=g) > 0.5).long().pin_memory()) for _ in range(2)]
+    batches = [(h[0].to(dev), h[1].to(dev)) for h in host]
+    crit = torch.nn.CrossEntropyLoss()
+
+    def lstm_step(x, tgt):
+        m.zero_grad(set_to_none=True)
+        o, pen, loss = m(x, 0, 0, tgt, crit)
+        loss.backward()
+        return loss
+
+    r = measure(lstm_step, batches, host, steps, warmup, timer, B_PER_GPU)
+    flop = 3 * 2.0 * HW * HW * 100 * 25 * 225 * T          # fwd + dgrad + wgrad of the recurrent convolution, per sequence
+    r.update({"metric": metric_name("convlstm", T), "unit": UNIT, "steps": steps, "warmup": warmup, "dtype": "f32",
+              "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d], train mode incl. the Jacobian-penalty branch "
+                                     "(BASELINE configs[4])" % (T, B_PER_GPU, HW, HW), "conv_mode": "bf16x3",
+                         "gabor": "reference bank (tests/golden fixture)"},
+              "roofline": roof(r["value"], flop, True)})
+    r["roofline"]["note"] += "; recurrent-convolution FLOPs only"
+    if not args.no_cpu_baseline:
+        v, sec, cores, sample = cpu_port_convlstm(steps=1, warmup=0, batch=1, frames=T, size=HW, gabor=gabor)
+        r["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    out.append(r)
+    return out
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import torch.nn.functional as F
-    from pathtracker_models_b200 import InT, _lib, ffhgru_hierarchy, synth_pathtracker
-    from pathtracker_models_b200.parallel import attach_data_parallel, broadcast_parameters, shard_first_index
+    from pathtracker_models_b200 import InT, _lib, ffhgru_hierarchy
+    from pathtracker_models_b200.parallel import attach_data_parallel, broadcast_parameters
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,10 +453,9 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    B, T, HW = args.batch, args.frames, args.size      # defaults = the headline workload
-    flop_per_seq = (T * HW * HW * (2 * (2 * C * C * K * K) + 6 * (2 * C * C) + 2 * 3 * C) + HW * HW * (2 * C + 100)
-                    + 2 * T * HW * HW * (2 * (2 * C * C * K * K) + 6 * (2 * C * C)) + T * HW * HW * 6 * C
-                    + 2 * HW * HW * (2 * C + 100))
+    B, T_, HW_ = args.batch, args.frames, args.size      # defaults = the headline workload
+    flop_per_seq = int_flop_per_seq(T_, HW_)
+    timer = Timer(dev, world)
 
     torch.manual_seed(0)
     if args.model == "convlstm":
@@ -211,16 +465,15 @@ def run_b200(args):
     if args.eval:
         return run_eval(args, dev, world, rank)
     ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
-    model = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev)
+    model = ctor(dimensions=C, timesteps=T_, kernel_size=K).to(dev)
     model.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
     if world > 1:
         broadcast_parameters(model)
         attach_data_parallel(model)
 
-    # resident inputs: a few different batches (per-step working set -- 2.2 GB of checkpoints -- exceeds L2)
+    # resident inputs: a few different batches (per-step working set -- GBs of checkpoints -- exceeds L2)
     nbuf = 4
-    batches = [synth_pathtracker(B, T, HW, HW, n_distractors=DIST, speed=SPEED, seed=1234,
-                                 first_index=shard_first_index(i, rank, world, B), device=dev) for i in range(nbuf)]
+    batches, host = int_batches(B, T_, HW_, rank, world, dev, nbuf)
 
     def step(x, y):
         model.zero_grad(set_to_none=True)
@@ -229,79 +482,32 @@ def run_b200(args):
         loss.backward()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for i in range(warmup):
         step(*batches[i % nbuf])
-    barrier()
+    timer.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-
-    def timed_region(profile):
-        launches0 = _lib.launch_count()
-        if profile:
-            _lib.profile_start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            step(*batches[i % nbuf])
-        e1.record()
-        barrier()
-        prof = _lib.profile_stop() if profile else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), _lib.launch_count() - launches0, prof
-
-    # pass 1: the headline number, nothing but the K steps between the two events
-    ms_total, launches, _ = timed_region(profile=False)
-    value = world * B * steps / (ms_total / 1e3)
+    # pass 1 (+ the end-to-end pass): the headline numbers, nothing but the K steps between the two events
+    main = measure(step, batches, host, steps, 0, timer, B, lambda b: (b[0].permute(0, 4, 1, 2, 3), b[1]))
     # pass 2: the same K steps with every kernel-class launch bracketed by CUDA events on its stream
     # (event records between kernels cost a few percent, so this pass only feeds the roofline block)
-    ms_prof, _, prof = timed_region(profile=True)
-
-    # ---- end to end: pinned host float32 clips (channels_last_3d strides, as utils/engine.py:222-243) -> H2D
-    # inside the timed region, loss read back each step
-    hx = [b[0].permute(0, 2, 3, 4, 1).contiguous().cpu().pin_memory() for b in batches]
-    hy = [b[1].cpu().pin_memory() for b in batches]
-
-    from pathtracker_models_b200.data import DevicePrefetcher
-
-    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
-    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def e2e_run(n):
-        """every step: its clip goes host -> device (one batch in flight on a copy stream) and its loss comes back to
-        the host.  The loss is copied asynchronously into pinned memory and READ one step later (how a training loop
-        logs it), so the device never idles on the host; the last value is read after the loop."""
-        seen = []
-        for i, (x, y) in enumerate(DevicePrefetcher(((hx[j % nbuf], hy[j % nbuf]) for j in range(n)), dev)):
-            loss = step(x.permute(0, 4, 1, 2, 3), y)
-            loss_host[i & 1:(i & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)
-            loss_ev[i & 1].record()
-            if i > 0:
-                loss_ev[(i - 1) & 1].synchronize()
-                seen.append(float(loss_host[(i - 1) & 1]))
-        loss_ev[(n - 1) & 1].synchronize()
-        seen.append(float(loss_host[(n - 1) & 1]))
-        assert len(seen) == n and all(v == v for v in seen)
-
-    e2e_run(2)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    e2e_run(steps)
-    f1.record()
-    barrier()
+    _lib.profile_start()
+    ms_prof = timer.run(lambda n: [step(*batches[i % nbuf]) for i in range(n)], steps)
+    prof = _lib.profile_stop()
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+
+    grad_check = None
     if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * steps / (ms2.item() / 1e3)
+        # once per run: every rank must hold the same averaged gradient after the all-reduce (cross-rank checksum)
+        step(*batches[0])
+        flat = torch.cat([p.grad.reshape(-1).double() for p in model.parameters() if p.grad is not None])
+        cs = torch.stack([flat.sum(), flat.abs().sum()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        grad_check = {"checksum_sum": cs[0].item(), "checksum_abs": cs[1].item(),
+                      "max_rank_spread": (hi - lo).abs().max().item(), "identical_on_all_ranks": bool(torch.equal(lo, hi))}
 
     # ---- the step either side of the path, reported separately (SURVEY 8d: "optimizer step excluded and reported
     # separately"): loss + metrics kernel and fused Adam + zero_grad vs torch.optim.Adam on the same gradients
@@ -344,51 +550,77 @@ def run_b200(args):
 
     if rank == 0:
         tensor_peak, hbm_peak, src = load_peaks()
+        headline = (args.model, T_, HW_, B) == ("int", 64, 32, 64)
         conv_ms, conv_n = prof["conv_fwd"][0] + prof["conv_dgrad"][0], prof["conv_fwd"][1] + prof["conv_dgrad"][1]
-        conv_flop = 2 * B * HW * HW * C * C * K * K
+        conv_flop = 2 * B * HW_ * HW_ * C * C * K * K
         conv_avg_ms = conv_ms / max(conv_n, 1)
         achieved = conv_flop / (conv_avg_ms * 1e-3) / 1e12 if conv_n else None
         shares = {k: round(v[0] / ms_prof, 4) for k, v in prof.items()}
+        value = main["value"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": metric_name(args.model, T_), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.conv_mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "%s %d frames %dx%d, 14 distractors, batch %d/GPU%s" % (
-                           "InT" if args.model == "int" else "FFhGRU", T, HW, HW, B,
-                           " (BASELINE configs[1])" if (args.model, T, HW, B) == ("int", 64, 32, 64) else ""),
+                           "InT" if args.model == "int" else "FFhGRU", T_, HW_, HW_, B, " (BASELINE configs[1])" if headline else ""),
                        "global_batch": B * world, "parallelism": "dp%d" % world, "conv_mode": args.conv_mode,
                        "l2": "no flush: per-step working set (GBs of checkpoints per GPU) exceeds the 126 MB L2; "
                              "%d distinct input batches rotate" % nbuf},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 4),
-                    "d2h_bytes_per_step": 4},
-            "gpu_launches": launches,
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
             "optimizer": optimizer_block,
             "clocks": sampler.result(),
             "roofline": {"bound": "tensor", "kernel": ("conv7_ffma_kernel" if args.conv_mode == "fp32" else "conv7_tc_kernel") + " (fwd + dgrad launches)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tensor_peak) if achieved else None,
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.conv_mode) if (args.model, T, HW, B) == ("int", 64, 32, 64) else None,
-                         "traffic_unit": "bytes/launch (ncu --set full, profiles/r1i_kernels_full.txt); algorithmic: 16.8 MB "
-                                         "(8.4 MB in + 8.4 MB out, the output stays in L2)",
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.conv_mode) if headline else None,
+                         "traffic_unit": "bytes/launch (dram read + write, ncu --set full, %s); algorithmic: 16.8 MB "
+                                         "(8.4 MB in + 8.4 MB out, the output stays in L2)" % NCU_TRAFFIC_SOURCE,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % src,
                          "launch_ms": conv_avg_ms, "launches_timed": conv_n, "flop_per_launch": conv_flop,
                          "frac_of_fp32_ffma_nominal": (achieved / FP32_FFMA_PEAK_TFLOPS) if achieved else None,
                          "note": ("3-pass split-bf16 tcgen05 conv: issues 3x the algorithmic MACs, so the fp32-parity ceiling "
                                   "is 1/3 of the bf16 peak (frac_of_third_peak)" if args.conv_mode == "bf16x3" else
-                                  "strict-fp32 CUDA-core conv: its own pipe peaks at 74.4 TFLOP/s nominal"),
+                                  "strict-fp32 CUDA-core conv: its own pipe peaks at 74.4 TFLOP/s nominal" if args.conv_mode == "fp32"
+                                  else "single-pass bf16 conv"),
                          "frac_of_third_peak": (3 * achieved / tensor_peak) if achieved else None,
                          "step_tflops": value / world * flop_per_seq / 1e12,
                          "step_frac_of_tensor_peak": value / world * flop_per_seq / 1e12 / tensor_peak,
                          "kernel_time_share": shares,
                          "measured": "second pass of the same %d steps with per-kernel CUDA events (%.2f ms/step "
-                                     "instrumented vs %.2f ms/step plain)" % (steps, ms_prof / steps, ms_total / steps)},
+                                     "instrumented vs %.2f ms/step plain)" % (steps, ms_prof / steps, main["ms_per_step"])},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            v, sec, cores, sample = cpu_reference_seq_per_s(steps=16, warmup=1)     # ~10-15 s of host work
+        if grad_check is not None:
+            line["multi_gpu_gradient_check"] = grad_check
+        if world == 1 and not args.no_cpu_baseline and headline:
+            line["parity"], line["cpu_baseline"] = parity_vs_cpu_port(model, dev)     # ~15 s of host work
+        elif world == 1 and not args.no_cpu_baseline:
+            v, sec, cores, sample = cpu_port_int(steps=4, warmup=1, batch=max(1, min(8, 2048 // (HW_ * HW_ // 16))),
+                                                 frames=T_, size=HW_, variant=args.model)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and headline and not args.no_extra:
+            del batches, host
+            torch.cuda.empty_cache()
+            line["other_configs"] = run_other_configs(args, dev, timer, tensor_peak, src)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _simple_run(step, steps, warmup):
+    import torch
+    from pathtracker_models_b200 import _lib
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), _lib.launch_count() - l0
 
 
 def run_convlstm(args, dev, world, rank):
@@ -398,13 +630,12 @@ def run_convlstm(args, dev, world, rank):
     import torch
     from pathtracker_models_b200 import _lib, convlstm, synth_pathtracker
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    B, T, HW = args.batch, args.frames, args.size
-    rs = np.random.RandomState(0)
-    gabor = torch.from_numpy(rs.normal(0, 0.3, (25, 1, 7, 7)).astype(np.float32))   # the .npy is not on the GPU box
+    B, T_, HW_ = args.batch, args.frames, args.size
+    gabor = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "convlstm_k7_small.npz"))["gabor"]).float()
     torch.manual_seed(0)
-    m = convlstm.ConvLSTM(timesteps=T, filt_size=15, gabor=gabor).to(dev).train()
+    m = convlstm.ConvLSTM(timesteps=T_, filt_size=15, gabor=gabor).to(dev).train()
     m.conv_mode = _lib.PTK_CONV_FP32 if args.conv_mode == "fp32" else _lib.PTK_CONV_BF16X3
-    clips, y = synth_pathtracker(B, 2, HW, HW, device=dev)
+    clips, y = synth_pathtracker(B, 2, HW_, HW_, device=dev)
     x = clips[:, 0:1, 0].contiguous()                                               # [B,1,H,W] static image
     tgt = (clips[:, 2, 0] > 0).long()
     crit = torch.nn.CrossEntropyLoss()
@@ -415,44 +646,33 @@ def run_convlstm(args, dev, world, rank):
         loss.backward()
         return loss
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    flop = 3 * 2.0 * B * HW * HW * 100 * 25 * 225 * T          # fwd + dgrad + wgrad of the recurrent conv
-    print(json.dumps({"metric": "train seq/s (fwd+bwd) ConvLSTM", "value": B * steps / (ms / 1e3), "unit": UNIT,
+    ms, launches = _simple_run(step, steps, warmup)
+    flop = 3 * 2.0 * B * HW_ * HW_ * 100 * 25 * 225 * T_          # fwd + dgrad + wgrad of the recurrent conv
+    peak, _, src = load_peaks()
+    print(json.dumps({"metric": metric_name("convlstm", T_), "value": B * steps / (ms / 1e3), "unit": UNIT,
                       "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T, B, HW, HW)},
-                      "gpu_launches": _lib.launch_count() - l0,
+                      "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T_, B, HW_, HW_),
+                                 "conv_mode": "fp32" if args.conv_mode == "fp32" else "bf16x3"},
+                      "gpu_launches": launches,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                   "peak": load_peaks()[0], "frac": flop * steps / (ms / 1e3) / 1e12 / load_peaks()[0],
+                                   "peak": peak, "frac": flop * steps / (ms / 1e3) / 1e12 / peak,
                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); the 3-pass split issues 3x "
-                                                  "the algorithmic MACs, so the fp32-parity ceiling is 1/3 of it" % load_peaks()[2],
-                                   "note": "recurrent-conv FLOPs only; conv_mode %s (bf16x3: forward / transposed convolution and "
-                                           "weight gradient on tcgen05, 3-pass split-bf16)" % ("fp32" if args.conv_mode == "fp32" else "bf16x3")}}),
-          flush=True)
+                                                  "the algorithmic MACs, so the fp32-parity ceiling is 1/3 of it" % src,
+                                   "note": "recurrent-conv FLOPs only"}}), flush=True)
 
 
 def run_gru(args, dev, world, rank):
-    """kys.GRU (`--model gru`, utils/engine.py:147-153: 64 channels, 7x7) on the headline clip shape.  Secondary line:
-    first version of this family, strict-fp32 CUDA-core convolutions."""
+    """kys.GRU (`--model gru`, utils/engine.py:147-153: 64 channels, 7x7) on the headline clip shape.  Secondary line."""
     import torch
     import torch.nn.functional as F
     from pathtracker_models_b200 import _lib, kys, synth_pathtracker
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    B, T, HW = args.batch, args.frames, args.size
+    B, T_, HW_ = args.batch, args.frames, args.size
     torch.manual_seed(0)
-    m = kys.GRU(dimensions=64, timesteps=T, kernel_size=7).to(dev)
+    m = kys.GRU(dimensions=64, timesteps=T_, kernel_size=7).to(dev)
     m.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
-    x, y = synth_pathtracker(B, T, HW, HW, n_distractors=DIST, speed=SPEED, device=dev)
+    x, y = synth_pathtracker(B, T_, HW_, HW_, n_distractors=DIST, speed=SPEED, device=dev)
 
     def step():
         m.zero_grad(set_to_none=True)
@@ -461,29 +681,19 @@ def run_gru(args, dev, world, rank):
         loss.backward()
         return loss
 
-    for _ in range(warmup):
-        step()
-    torch.cuda.synchronize()
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    flop = 3 * 2.0 * B * HW * HW * 49 * (128 * 128 + 128 * 64) * T     # fwd + dgrad + wgrad of the two cell convolutions
-    print(json.dumps({"metric": "train seq/s (fwd+bwd) kys.GRU", "value": B * steps / (ms / 1e3), "unit": UNIT,
+    ms, launches = _simple_run(step, steps, warmup)
+    flop = 3 * 2.0 * B * HW_ * HW_ * 49 * (128 * 128 + 128 * 64) * T_     # fwd + dgrad + wgrad of the two cell convolutions
+    peak, _, src = load_peaks()
+    print(json.dumps({"metric": metric_name("gru", T_), "value": B * steps / (ms / 1e3), "unit": UNIT,
                       "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "kys.GRU %d frames %dx%d, batch %d" % (T, HW, HW, B)},
-                      "gpu_launches": _lib.launch_count() - l0,
+                      "config": {"workload": "kys.GRU %d frames %dx%d, batch %d" % (T_, HW_, HW_, B), "conv_mode": args.conv_mode},
+                      "gpu_launches": launches,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
-                                   "peak": load_peaks()[0], "frac": flop * steps / (ms / 1e3) / 1e12 / load_peaks()[0],
+                                   "peak": peak, "frac": flop * steps / (ms / 1e3) / 1e12 / peak,
                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); fp32-parity ceiling = 1/3 of it "
-                                                  "(3-pass split-bf16)" % load_peaks()[2],
-                                   "note": "cell-convolution FLOPs only; conv_mode %s (bf16x3: wide tcgen05 kernels shared with the "
-                                           "ConvLSTM)" % args.conv_mode}}), flush=True)
+                                                  "(3-pass split-bf16)" % src,
+                                   "note": "cell-convolution FLOPs only"}}), flush=True)
 
 
 def run_eval(args, dev, world, rank):
@@ -491,29 +701,19 @@ def run_eval(args, dev, world, rank):
     import torch
     from pathtracker_models_b200 import InT, _lib, ffhgru_hierarchy, synth_pathtracker
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    B, T, HW = args.batch, args.frames, args.size
+    B, T_, HW_ = args.batch, args.frames, args.size
     torch.manual_seed(0)
     ctor = InT.InT if args.model == "int" else ffhgru_hierarchy.FFhGRU
-    m = ctor(dimensions=C, timesteps=T, kernel_size=K).to(dev).eval()
+    m = ctor(dimensions=C, timesteps=T_, kernel_size=K).to(dev).eval()
     m.conv_mode = {"bf16x3": _lib.PTK_CONV_BF16X3, "fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}[args.conv_mode]
-    x, _ = synth_pathtracker(B, T, HW, HW, n_distractors=DIST, speed=SPEED, device=dev)
+    x, _ = synth_pathtracker(B, T_, HW_, HW_, n_distractors=DIST, speed=SPEED, device=dev)
     with torch.no_grad():
-        for _ in range(warmup):
-            m(x)
-        torch.cuda.synchronize()
-        l0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            m(x)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print(json.dumps({"metric": "eval seq/s (fwd only)", "value": B * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+        ms, launches = _simple_run(lambda: m(x), steps, warmup)
+    print(json.dumps({"metric": metric_name(args.model, T_, eval_only=True), "value": B * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                       "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "bf16" if args.conv_mode == "bf16" else "f32", "data": "synthetic",
-                      "config": {"workload": "%s %d frames %dx%d, batch %d, forward only" % (args.model, T, HW, HW, B),
-                                 "conv_mode": args.conv_mode}, "gpu_launches": _lib.launch_count() - l0}), flush=True)
+                      "config": {"workload": "%s %d frames %dx%d, batch %d, forward only" % (args.model, T_, HW_, HW_, B),
+                                 "conv_mode": args.conv_mode}, "gpu_launches": launches}), flush=True)
 
 
 def main():
@@ -526,7 +726,8 @@ def main():
                     help="with --impl reference: cuda = additionally time the reference's operator sequence in PyTorch eager on the GPU")
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm", "gru"], help="non-headline configs (BASELINE configs[2..3])")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_configs block (BASELINE configs[2]-[4]) of the default run")
+    ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm", "gru"], help="non-headline configs (BASELINE configs[2..4])")
     ap.add_argument("--eval", action="store_true", help="forward-only throughput (secondary line)")
     ap.add_argument("--frames", type=int, default=T)
     ap.add_argument("--size", type=int, default=HW)

@@ -18,8 +18,11 @@ def average_flat_gradient_(flat_grad, group=None):
     world = dist.get_world_size(group)
     if world == 1:
         return flat_grad
-    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
-    flat_grad.div_(world)
+    if flat_grad.is_cuda and dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG, group=group)      # one NCCL kernel, the mean is taken in it
+    else:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)      # gloo (CPU tests) has no AVG
+        flat_grad.div_(world)
     return flat_grad
 
 
