@@ -106,7 +106,7 @@ def _host_cores():
 # --------------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference ALGORITHM on the host cores.  /root/reference is Python and absent on the GPU box, so this is
 # the oracle port (oracle/int_oracle.py: torch CPU ops + autograd, fp32; 1x1 gates as einsum), `kind: "port"`.
-def cpu_port_int(steps, warmup, batch=8, frames=T, size=HW, variant="int", keep_last=False):
+def cpu_port_int(steps, warmup, batch=8, frames=T, size=HW, variant="int", keep_last=False, fp64=False):
     """fwd + BCE + bwd of the InT / FFhGRU restatement on a bounded sample of the workload (batch `batch`).
     returns (seq/s, s/pass, threads, sample description[, loss, grads by state_dict key])"""
     import torch
@@ -119,11 +119,12 @@ def cpu_port_int(steps, warmup, batch=8, frames=T, size=HW, variant="int", keep_
     ctor = InT.InT if variant == "int" else ffhgru_hierarchy.FFhGRU
     m = ctor(dimensions=C, timesteps=frames, kernel_size=K)
     sd = {k: v.detach() for k, v in m.state_dict().items()}
-    p = O.unpack(sd, dtype=torch.float32)
+    dt_ = torch.float64 if fp64 else torch.float32
+    p = O.unpack(sd, dtype=dt_)
     for v in p.values():
         v.requires_grad_(True)
     xn, yn = synth(1234, 0, batch, frames, size, size, DIST, SPEED)
-    x, y = torch.from_numpy(xn), torch.from_numpy(yn).view(batch, 1)
+    x, y = torch.from_numpy(xn).to(dt_), torch.from_numpy(yn).view(batch, 1).to(dt_)
     times, last = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -327,26 +328,33 @@ def parity_vs_cpu_port(model, dev):
     import torch
     import torch.nn.functional as F
     from oracle.synth_oracle import synth
-    v, sec, cores, sample, loss_cpu, g_cpu = cpu_port_int(steps=12, warmup=1, keep_last=True)
+    v, sec, cores, sample, loss32, g32 = cpu_port_int(steps=12, warmup=1, keep_last=True)
+    _, _, _, _, loss_cpu, g_cpu = cpu_port_int(steps=1, warmup=0, keep_last=True, fp64=True)      # the arbiter
     xn, yn = synth(1234, 0, 8, T, HW, HW, DIST, SPEED)
     x, y = torch.from_numpy(xn).to(dev), torch.from_numpy(yn).view(8, 1).to(dev)
     model.zero_grad(set_to_none=True)
     out, _ = model(x)
     loss = F.binary_cross_entropy_with_logits(out, y)
     loss.backward()
-    worst, worst_name = 0.0, None
+    rel = lambda a, b: (a.double().cpu() - b.double()).abs().max().item() / max(b.double().abs().max().item(), 1e-300)
+    worst, worst_name, worst_ratio, ratio_name = 0.0, None, 0.0, None
     for n, p in model.named_parameters():
-        if p.grad is None or n not in g_cpu:
+        if p.grad is None or n not in g_cpu or float(g_cpu[n].abs().max()) == 0.0:
             continue
-        ref = g_cpu[n].double()
-        e = (p.grad.double().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-300)
+        e, noise = rel(p.grad, g_cpu[n]), rel(g32[n], g_cpu[n])
         if e > worst:
             worst, worst_name = e, n
+        r = e / max(1e-4, 4 * noise)
+        if r > worst_ratio:
+            worst_ratio, ratio_name = r, n
     model.zero_grad(set_to_none=True)
-    parity = {"sample": "batch 8, T=64, 32x32 (the cpu_baseline sample), seed-0 weights", "checker": "CPU port, fp32 (oracle/int_oracle.py)",
-              "loss_abs_err": abs(loss.item() - loss_cpu), "grad_rel_err_max": worst, "grad_worst_tensor": worst_name,
-              "note": "max|a-b|/max|b| per tensor; both sides are fp32 here, the fp64-arbitrated gate lives in tests/ (T=64 and "
-                      "T=128 fixtures generated by the reference itself)"}
+    parity = {"sample": "batch 8, T=64, 32x32 (the cpu_baseline sample), seed-0 default-init weights",
+              "checker": "CPU port in fp64 (oracle/int_oracle.py); the fp32 port run gives the fp32 noise floor per tensor",
+              "loss_abs_err": abs(loss.item() - loss_cpu), "loss_abs_err_fp32_port": abs(loss32 - loss_cpu),
+              "grad_rel_err_max": worst, "grad_worst_tensor": worst_name,
+              "worst_fraction_of_allowed": worst_ratio, "tightest_tensor": ratio_name, "pass": bool(worst_ratio <= 1.0),
+              "rule": "per tensor max|a-b|/max|b| vs fp64 <= max(1e-4, 4 x the fp32 port's own error) (SURVEY 8c); the same gate "
+                      "runs in tests/ on T=64 / T=128 fixtures generated by the reference itself"}
     return parity, {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
 

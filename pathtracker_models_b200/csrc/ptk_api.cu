@@ -9,6 +9,15 @@
 
 #include <stdlib.h>
 namespace ptk {
+bool conv_v2_enabled() {
+  static const bool on = [] { const char* e = getenv("PTK_CONV_V1"); return !(e && e[0] == '1'); }();
+  return on;
+}
+// floats per prepared 7x7 weight bank and direction: fp32 re-layout, or the larger of the two bf16 hi/lo streams
+static size_t wbank_floats() {
+  const size_t a = (size_t)C * C * TAPS, b = (conv7_tc2_weight_bytes() + 3) / 4;
+  return a > b ? a : b;
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("PTK_NO_PDL"); return !(e && e[0] == '1'); }();
   return on;
@@ -69,7 +78,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
   Carver cv(ws);
   const size_t S = state_elems(dm);
   const int pw = pw_grid(dm->B, dm->H, dm->W);
-  float* w = cv.take<float>(4 * (size_t)C * C * TAPS);
+  float* w = cv.take<float>(4 * wbank_floats());
   float* gt = cv.take<float>(3 * 6 * C * C);   // gateT, gateTF, gateF
   float* Ge = cv.take<float>(S);
   float* big = cv.take<float>(14 * S);   // inference ring (9S) or backward scratch (14S)
@@ -110,8 +119,8 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
       d->A = big + 8 * S; d->a_tstride = 0; d->a_bstride = (long long)C * dm->H * dm->W;
       d->stats = ring_stats;
     }
-    d->w_inh_f = w; d->w_inh_d = w + (size_t)C * C * TAPS;
-    d->w_exc_f = w + 2 * (size_t)C * C * TAPS; d->w_exc_d = w + 3 * (size_t)C * C * TAPS;
+    d->w_inh_f = w; d->w_inh_d = w + wbank_floats();
+    d->w_exc_f = w + 2 * wbank_floats(); d->w_exc_d = w + 3 * wbank_floats();
     for (int i = 0; i < 6; ++i) {
       d->gateT[i] = gt + i * C * C;
       d->gateTF[i] = gt + (6 + i) * C * C;
@@ -156,10 +165,13 @@ static int prep(IntDev* d, const float* params, cudaStream_t st) {
   const float* w_inh = params + po.o[PTK_P_W_INH];
   const float* w_exc = params + po.o[PTK_P_W_EXC];
   if (d->conv_mode != PTK_CONV_FP32) {
-    // the four 200,704-byte banks hold the bf16 hi/lo tap streams instead of fp32 re-layouts
-    int rc = launch_prep_weights_tc(w_inh, (void*)d->w_inh_f, (void*)d->w_inh_d, st);
+    // the four banks hold the bf16 hi/lo tap streams instead of fp32 re-layouts
+    const bool v2 = conv_v2_enabled();
+    int rc = v2 ? launch_prep_weights_tc2(w_inh, (void*)d->w_inh_f, (void*)d->w_inh_d, st)
+                : launch_prep_weights_tc(w_inh, (void*)d->w_inh_f, (void*)d->w_inh_d, st);
     if (rc) return rc;
-    if ((rc = launch_prep_weights_tc(w_exc, (void*)d->w_exc_f, (void*)d->w_exc_d, st))) return rc;
+    if ((rc = v2 ? launch_prep_weights_tc2(w_exc, (void*)d->w_exc_f, (void*)d->w_exc_d, st)
+                 : launch_prep_weights_tc(w_exc, (void*)d->w_exc_f, (void*)d->w_exc_d, st))) return rc;
     return run_prep_weights(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, g, (float*)d->gateT[0], st);
   }
   return run_prep_weights(w_inh, w_exc, (float*)d->w_inh_f, (float*)d->w_inh_d, (float*)d->w_exc_f,
@@ -270,18 +282,20 @@ int ptk_conv7(int32_t B, int32_t H, int32_t W, int32_t conv_mode, int32_t transp
   if (workspace_bytes < need) { set_error("ptk_conv7: workspace too small (%zu < %zu)", workspace_bytes, need); return PTK_ENOMEM; }
   cudaStream_t st = (cudaStream_t)stream;
   Carver cv(workspace);
-  float* wf = cv.take<float>((size_t)C * C * TAPS);
-  float* wd = cv.take<float>((size_t)C * C * TAPS);
+  float* wf = cv.take<float>(wbank_floats());
+  float* wd = cv.take<float>(wbank_floats());
   float* part = cv.take<float>((size_t)conv_num_ctas(B, H, W) * C * 2);
   unsigned* counter = cv.take<unsigned>(4);
   PTK_CUDA_OK(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned), st));
-  if (conv_mode != PTK_CONV_FP32) rc = launch_prep_weights_tc(weight, wf, wd, st);
+  const bool v2 = conv_mode != PTK_CONV_FP32 && conv_v2_enabled();
+  if (conv_mode != PTK_CONV_FP32) rc = v2 ? launch_prep_weights_tc2(weight, wf, wd, st) : launch_prep_weights_tc(weight, wf, wd, st);
   else {
     IntGateSrc g = {};
     rc = run_prep_weights(weight, nullptr, wf, wd, nullptr, nullptr, g, nullptr, st);
   }
   if (rc) return rc;
   ConvArgs a{in, transpose ? wd : wf, out, B, H, W, accumulate, stats ? part : nullptr, counter, stats, conv_mode};
+  a.v2 = v2;
   return launch_conv7(a, st);
 }
 
@@ -344,8 +358,8 @@ int ptk_wgrad7(int32_t T, int32_t B, int32_t H, int32_t W, int32_t conv_mode, co
 size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
   if (B < 1 || H < 16 || W < 32 || H % 16 || W % 32) return 0;
   Carver cv(nullptr);
-  cv.take<float>((size_t)C * C * TAPS);
-  cv.take<float>((size_t)C * C * TAPS);
+  cv.take<float>(wbank_floats());
+  cv.take<float>(wbank_floats());
   cv.take<float>((size_t)conv_num_ctas(B, H, W) * C * 2);
   cv.take<unsigned>(4);
   return (cv.off + 255) & ~(size_t)255;

@@ -363,6 +363,7 @@ __global__ void prep_weights_tc_kernel(const float* __restrict__ w, __nv_bfloat1
 }
 
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st) {
+  if (a.v2) return launch_conv7_tc2(a, st);
   dim3 grid(a.W / TC_TW, a.H / TC_TH, a.B);
   if (a.mode == PTK_CONV_BF16) {
     PTK_CUDA_OK(ptk_func_smem(conv7_tc_kernel<true>, TC_SMEM));

@@ -1,0 +1,360 @@
+// Tensor-core horizontal-connection convolution, second generation: weights are the A operand, pixels the B operand.
+//
+//   Y[b, oc, y, x] = sum_{tap, ic} In[b, ic, y+ky-3, x+kx-3] * W[oc, ic, tap]      (models/InT.py:161,172; dgrad = flipped W)
+//
+// What changed against ptk_conv_tc.cu (pixels as A with M = 128, three taps stacked along N = 96) and why:
+//  * that kernel's MMA loop ran at the shared-memory operand floor (7 KB of operands per 48 tensor-pipe cycles: 68 cycles
+//    per instruction measured, tensor pipe 42 % active), then drained all of TMEM in a serial epilogue.
+//  * here an instruction is M = 128 = 4 horizontally adjacent taps x 32 output channels (A = weights, 4 KB, K-major) times
+//    N = 240 or 160 padded pixels (B = the SAME zero-padded bf16 image as before, addressed at start pixel
+//    chunk + ky*38 + 4*kxg): 11.5 KB of operands per 120 tensor-pipe cycles = 96 B/clk, under the ~105-128 B/clk the
+//    shared memory delivers, so the loop is bound by the tensor pipe.  3-pass split as before (Wh*Ih + Wh*Il + Wl*Ih).
+//  * the 16x38 padded output tile is produced in three row chunks (6, 6, 4 rows) whose accumulators alternate between two
+//    240-column TMEM buffers: four epilogue warps drain chunk c while the MMA warp issues chunk c+1.
+//  * D[(dl, oc)][n] holds tap kx = 4*kxg + dl's contribution to output pixel n - dl: the realignment is a column offset of
+//    the tcgen05.ld, the sum over the four lane quadrants goes through a small shared-memory tile, and because lanes are
+//    output CHANNELS the result is already row-major NCHW: coalesced stores, per-channel BatchNorm partial statistics in
+//    registers.
+//  * price: the weight stream (14 stages of 16 KB) passes once per chunk, 3 x 224 KB per CTA, through a 4-stage
+//    cp.async.bulk ring.
+#include <cuda_bf16.h>
+
+#include "ptk_common.cuh"
+#include "ptk_conv_stats.cuh"
+#include "ptk_kernels.h"
+#include "ptk_tc.cuh"
+
+namespace ptk {
+
+constexpr int T2_TH = 16, T2_TW = 32;
+constexpr int T2_WP = T2_TW + 6;                       // 38: padded row pitch (pixels)
+constexpr int T2_ROWS = T2_TH + 6;                     // 22 input rows
+constexpr int T2_NPIX = 880;                           // pixels of the operand image incl. slack (last read: 456 + 232 + 160 = 848)
+constexpr int T2_PLANE = T2_NPIX * 16 + 16;            // bytes per channel-chunk plane (+16: the 4 chunks of a pixel hit 4 bank groups)
+constexpr int T2_A_BYTES = 2 * 4 * T2_PLANE;           // hi + lo, 4 chunks
+constexpr int T2_NG = 2 * KS;                          // tap groups (ky, kxg): kx = 4*kxg + dl, dl = 0..3 (kx = 7 is a zero dummy)
+constexpr int T2_WTILE = 2 * 128 * 16;                 // one A operand: [2 k-chunks][128 rows = (dl, n)][8 bf16]
+constexpr int T2_STAGE = 4 * T2_WTILE;                 // ic half 0: Wh, Wl; ic half 1: Wh, Wl  = 16 KB
+constexpr int T2_NST = 4;                              // weight ring stages
+constexpr int T2_NCH = 3;                              // row chunks of the output tile
+constexpr int T2_DBUF = 240;                           // TMEM columns per accumulator buffer
+constexpr int T2_PP = 36;                              // row pitch (floats) of the quadrant-sum tile
+constexpr int T2_PART = 4 * C * T2_PP * 4;             // [4 quadrants][32 oc][32 px (+4)] floats
+constexpr int T2_SMEM = T2_A_BYTES + T2_NST * T2_STAGE + 2 * T2_PART + 256;
+
+__host__ __device__ constexpr int t2_chunk_start(int c) { return c * 6 * T2_WP; }                    // 0, 228, 456
+__host__ __device__ constexpr int t2_chunk_n(int c) { return c < 2 ? 240 : 160; }                    // >= outputs + 3
+__host__ __device__ constexpr int t2_chunk_blocks(int c) { return c < 2 ? 7 : 5; }                   // 32-pixel output blocks
+
+// byte offset of weight element (tap (ky, kx), row n, k) in the staged stream
+__host__ __device__ constexpr size_t t2_woff(int ky, int kx, int n, int k, bool lo) {
+  return (size_t)(ky * 2 + (kx >> 2)) * T2_STAGE + (size_t)(k >> 4) * (2 * T2_WTILE) + (lo ? T2_WTILE : 0) +
+         (size_t)((k >> 3) & 1) * (128 * 16) + (size_t)((kx & 3) * 32 + n) * 16 + (size_t)(k & 7) * 2;
+}
+
+template <bool SINGLE>
+__global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* sA = smem_raw;                                   // [hi|lo][4 chunks][880 px][16 B]
+  uint8_t* sWr = smem_raw + T2_A_BYTES;                     // weight ring
+  float* sPart = reinterpret_cast<float*>(smem_raw + T2_A_BYTES + T2_NST * T2_STAGE);   // [2][4][32][36]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + T2_A_BYTES + T2_NST * T2_STAGE + 2 * T2_PART);
+  uint64_t* full = bars;                                    // [T2_NST]
+  uint64_t* empty = bars + T2_NST;                          // [T2_NST]
+  uint64_t* dFull = bars + 2 * T2_NST;                      // [2] accumulator buffer complete
+  uint64_t* dEmpty = dFull + 2;                             // [2] accumulator buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dEmpty + 2);
+  __shared__ double sFin[8][C][3];
+  __shared__ int sIsLast;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  const int x0 = blockIdx.x * T2_TW, y0 = blockIdx.y * T2_TH, b = blockIdx.z;
+  const int H = a.H, W = a.W;
+  const size_t in_bs = a.in_bs ? (size_t)a.in_bs : (size_t)C * H * W, out_bs = a.out_bs ? (size_t)a.out_bs : (size_t)C * H * W;
+  constexpr int NSTG = T2_NCH * T2_NG;                      // 42 weight stages per CTA
+
+  // ---- one-time setup: barriers, TMEM, zero the operand image ------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < T2_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&dFull[0], 1); mbar_init(&dFull[1], 1);
+    mbar_init(&dEmpty[0], 4); mbar_init(&dEmpty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < T2_A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // weights do not depend on the input tile: start streaming right away
+  if (tid == 0) {
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wT);
+    for (int i = 0; i < T2_NST; ++i) {
+      mbar_expect_tx(&full[i], T2_STAGE);
+      bulk_g2s(sWr + i * T2_STAGE, wsrc + (size_t)i * T2_STAGE, T2_STAGE, &full[i]);
+    }
+  }
+  // everything above touched only shared memory, TMEM and the prepared weights (written >= 2 kernels ago)
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // ---- stage the input tile: fp32 NCHW -> bf16 hi/lo, channel-chunk planar (same image as ptk_conv_tc.cu) -------
+  {
+    constexpr int NIT = 4 * T2_ROWS * (T2_TW / 4), NR = (NIT + 255) / 256;
+    float4 v[NR][8];
+    int pp[NR], qq[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int it = tid + 256 * r;
+      const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
+      const int gy = y0 + row - 3;
+      pp[r] = -1; qq[r] = q;
+      if (it < NIT && gy >= 0 && gy < H) {
+        pp[r] = row * T2_WP + 3 + 4 * g;
+        const float* src = a.in + (size_t)b * in_bs + ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      if (pp[r] < 0) continue;
+      const int p = pp[r], q = qq[r];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = reinterpret_cast<const float*>(&v[r][2 * e])[px], v1 = reinterpret_cast<const float*>(&v[r][2 * e + 1])[px];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          hi[e] = pack_bf16x2(h0, h1);
+          lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        }
+        *reinterpret_cast<uint4*>(sA + q * T2_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sA + 4 * T2_PLANE + q * T2_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+  if (W > T2_TW) {   // halo columns (only inside the image when W > 32)
+    for (int it = tid; it < 4 * T2_ROWS * 6; it += 256) {
+      const int q = it / (T2_ROWS * 6), rem = it - q * (T2_ROWS * 6), r = rem / 6, hc = rem % 6;
+      const int c = hc < 3 ? hc : (T2_TW + hc);          // padded columns 0..2 and 35..37
+      const int gy = y0 + r - 3, gx = x0 + c - 3;
+      if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
+      const float* src = a.in + (size_t)b * in_bs + ((size_t)(q * 8) * H + gy) * W + gx;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        hi[e] = pack_bf16x2(h0, h1);
+        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+      }
+      const int p = r * T2_WP + c;
+      *reinterpret_cast<uint4*>(sA + q * T2_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sA + 4 * T2_PLANE + q * T2_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const bool stats = (a.part != nullptr);
+
+  if (warp == 0) {
+    // ---- weight producer: refill a ring slot as soon as the MMAs that read it have retired --------------------
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wT);
+      for (int i = T2_NST; i < NSTG; ++i) {
+        const int st = i % T2_NST, round = i / T2_NST;
+        mbar_wait(&empty[st], (uint32_t)((round - 1) & 1));
+        mbar_expect_tx(&full[st], T2_STAGE);
+        bulk_g2s(sWr + st * T2_STAGE, wsrc + (size_t)(i % T2_NG) * T2_STAGE, T2_STAGE, &full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer -------------------------------------------------------------------------------------------
+    const uint32_t bHiA = smem_u32(sA), bLoA = bHiA + 4 * T2_PLANE, wBase = smem_u32(sWr);
+    const uint64_t dB0 = umma_desc(0, T2_PLANE, 128);          // pixels: K-major, LBO = next 8-channel plane, SBO = next 8 pixels
+    const uint64_t dW0 = umma_desc(0, 128 * 16, 128);          // weights: K-major, LBO = next k-chunk (128 rows x 16 B), SBO = next 8 rows
+    const uint32_t bHiW = (uint32_t)(dB0 >> 32), bLoW = (uint32_t)dB0;
+    const uint32_t wHiW = (uint32_t)(dW0 >> 32), wLoW = (uint32_t)dW0;
+    uint32_t bH[2], bL[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      bH[s] = bLoW + ((bHiA + (uint32_t)(2 * s) * T2_PLANE) >> 4);
+      bL[s] = bLoW + ((bLoA + (uint32_t)(2 * s) * T2_PLANE) >> 4);
+    }
+    int i = 0;
+#pragma unroll 1
+    for (int c = 0; c < T2_NCH; ++c) {
+      const int buf = c & 1;
+      if (c >= 2) {                                            // the buffer's previous chunk must have been drained
+        mbar_wait(&dEmpty[buf], 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const uint32_t idesc = umma_idesc(t2_chunk_n(c));
+      const uint32_t dcol = tmem_base + (uint32_t)(buf * T2_DBUF);
+#pragma unroll 1
+      for (int g = 0; g < T2_NG; ++g, ++i) {
+        const int st = i % T2_NST, round = i / T2_NST;
+        mbar_wait(&full[st], (uint32_t)(round & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t po = (uint32_t)(t2_chunk_start(c) + (g >> 1) * T2_WP + 4 * (g & 1));     // 16-byte units == pixels
+        const uint32_t wS = wLoW + ((wBase + (uint32_t)st * T2_STAGE) >> 4);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const uint64_t dWh = ((uint64_t)wHiW << 32) | (wS + (uint32_t)((s * 2 * T2_WTILE) >> 4));
+          const uint64_t dWl = ((uint64_t)wHiW << 32) | (wS + (uint32_t)((s * 2 * T2_WTILE + T2_WTILE) >> 4));
+          const uint64_t dIh = ((uint64_t)bHiW << 32) | (bH[s] + po), dIl = ((uint64_t)bHiW << 32) | (bL[s] + po);
+          if (elect_one()) {
+            umma_bf16(dcol, dWh, dIh, idesc, (g | s) ? 1u : 0u);
+            if (!SINGLE) {   // PTK_CONV_BF16 keeps Wh*Ih only
+              umma_bf16(dcol, dWh, dIl, idesc, 1u);
+              umma_bf16(dcol, dWl, dIh, idesc, 1u);
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) umma_commit(&empty[st]);   // frees this ring slot once the MMAs above have read it
+      }
+      __syncwarp();
+      if (elect_one()) umma_commit(&dFull[buf]);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---- epilogue warps: quadrant dl = warp - 4 holds tap kx = 4*kxg + dl's share; out[oc][m] = sum_dl D[dl][oc][m + dl] ----
+    const int dl = warp - 4, et = tid - 128;
+    const int oc = et >> 2, jq = et & 3;              // sum phase: channel, 8-pixel slice of a 32-pixel block
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    float sK = 0.f, s1 = 0.f, s2 = 0.f;               // shifted sums of this thread's outputs: sum (v - K), sum (v - K)^2
+    int sn = 0;
+    float* outc = a.out + (size_t)b * out_bs + (size_t)oc * H * W;
+    int blk = 0;
+#pragma unroll 1
+    for (int c = 0; c < T2_NCH; ++c) {
+      const int buf = c & 1;
+      mbar_wait(&dFull[buf], (uint32_t)((c >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int nb = t2_chunk_blocks(c);
+#pragma unroll 1
+      for (int kb = 0; kb < nb; ++kb, ++blk) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(dl * 32) << 16) + (uint32_t)(buf * T2_DBUF + kb * 32 + dl), v);   // lane = oc
+        float* pw = sPart + (size_t)(blk & 1) * (T2_PART / 4) + (size_t)(dl * C + lane) * T2_PP;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(pw + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        if (kb == nb - 1) {                             // this warp is done with the TMEM buffer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&dEmpty[buf]);
+        }
+        named_bar_sync(1, 128);
+        const float* pr = sPart + (size_t)(blk & 1) * (T2_PART / 4) + (size_t)oc * T2_PP + 8 * jq;
+        float o[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 p0 = *reinterpret_cast<const float4*>(pr + 4 * h), p1 = *reinterpret_cast<const float4*>(pr + C * T2_PP + 4 * h);
+          const float4 p2 = *reinterpret_cast<const float4*>(pr + 2 * C * T2_PP + 4 * h), p3 = *reinterpret_cast<const float4*>(pr + 3 * C * T2_PP + 4 * h);
+          o[4 * h + 0] = (p0.x + p1.x) + (p2.x + p3.x);
+          o[4 * h + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+          o[4 * h + 2] = (p0.z + p1.z) + (p2.z + p3.z);
+          o[4 * h + 3] = (p0.w + p1.w) + (p2.w + p3.w);
+        }
+        const int m0 = t2_chunk_start(c) + kb * 32 + 8 * jq;      // padded output pixel of o[0]
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int m = m0 + 2 * u, r = m / T2_WP, col = m - r * T2_WP;       // col is even: both pixels share a row
+          if (r < T2_TH && col < T2_TW) {
+            float2 t = make_float2(o[2 * u], o[2 * u + 1]);
+            float2* dst = reinterpret_cast<float2*>(outc + (size_t)(y0 + r) * W + x0 + col);
+            if (a.accumulate) { const float2 p = *dst; t.x += p.x; t.y += p.y; }
+            *dst = t;
+            if (stats) {
+              if (sn == 0) sK = o[2 * u];
+              const float d0 = o[2 * u] - sK, d1 = o[2 * u + 1] - sK;
+              s1 += d0 + d1;
+              s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+              sn += 2;
+            }
+          }
+        }
+      }
+    }
+    if (stats) {
+      // per-thread (n, mean, M2) -> Chan merge over the 4 threads of a channel -> per-CTA partial (mean, M2) of 16x32 outputs
+      float n = (float)sn, mean = sn ? sK + s1 / n : 0.f, m2 = sn ? fmaxf(s2 - s1 * s1 / n, 0.f) : 0.f;
+#pragma unroll
+      for (int off = 1; off <= 2; off <<= 1) {
+        const float n2 = __shfl_xor_sync(0xffffffffu, n, off), mean2 = __shfl_xor_sync(0xffffffffu, mean, off);
+        const float m22 = __shfl_xor_sync(0xffffffffu, m2, off);
+        const float nt = n + n2, dlt = mean2 - mean;
+        if (nt > 0.f) {
+          m2 = m2 + m22 + dlt * dlt * (n * n2 / nt);
+          mean = mean + dlt * (n2 / nt);
+        }
+        n = nt;
+      }
+      if (jq == 0) {
+        float* dstp = a.part + ((size_t)cta * C + oc) * 2;
+        dstp[0] = mean;
+        dstp[1] = m2;
+      }
+    }
+  }
+  if (stats) conv_stats_fold(a, gridDim.x * gridDim.y * gridDim.z, T2_TH * T2_TW, sFin, &sIsLast);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+}
+
+// weights fp32 [oc][ic][49] -> bf16 hi/lo in the staged layout (t2_woff); the dummy tap kx = 7 is written as zeros.
+//   forward: n = oc, k = ic, tap as is;  dgrad (conv_transpose): n = ic, k = oc, tap -> 48 - tap.
+__global__ void prep_weights_tc2_kernel(const float* __restrict__ w, __nv_bfloat16* wf, __nv_bfloat16* wd, int oc_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * C * KS * 8) return;
+  const int oc = i / (C * KS * 8), ic = (i / (KS * 8)) % C, ky = (i / 8) % KS, kx = i % 8;
+  const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+  if (kx == KS) {
+    if (wf) { wf[t2_woff(ky, kx, oc, ic, false) / 2] = z; wf[t2_woff(ky, kx, oc, ic, true) / 2] = z; }
+    if (wd) { wd[t2_woff(ky, kx, ic, oc, false) / 2] = z; wd[t2_woff(ky, kx, ic, oc, true) / 2] = z; }
+    return;
+  }
+  const float v = w[(size_t)oc * oc_stride + ic * TAPS + ky * KS + kx];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  if (wf) {
+    wf[t2_woff(ky, kx, oc, ic, false) / 2] = h;
+    wf[t2_woff(ky, kx, oc, ic, true) / 2] = l;
+  }
+  if (wd) {
+    wd[t2_woff(KS - 1 - ky, KS - 1 - kx, ic, oc, false) / 2] = h;
+    wd[t2_woff(KS - 1 - ky, KS - 1 - kx, ic, oc, true) / 2] = l;
+  }
+}
+
+size_t conv7_tc2_weight_bytes() { return (size_t)T2_NG * T2_STAGE; }
+
+int launch_conv7_tc2(const ConvArgs& a, cudaStream_t st) {
+  dim3 grid(a.W / T2_TW, a.H / T2_TH, a.B);
+  if (a.mode == PTK_CONV_BF16) {
+    PTK_CUDA_OK(ptk_func_smem(conv7_tc2_kernel<true>, T2_SMEM));
+    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc2_kernel<true>, grid, dim3(256), T2_SMEM, st, a));
+  } else {
+    PTK_CUDA_OK(ptk_func_smem(conv7_tc2_kernel<false>, T2_SMEM));
+    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc2_kernel<false>, grid, dim3(256), T2_SMEM, st, a));
+  }
+  PTK_LAUNCH_OK("conv7_tc2_kernel");
+  return PTK_OK;
+}
+
+int launch_prep_weights_tc2(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride) {
+  const int n = C * C * KS * 8;
+  prep_weights_tc2_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, oc_stride ? oc_stride : C * TAPS);
+  PTK_LAUNCH_OK("prep_weights_tc2_kernel");
+  return PTK_OK;
+}
+
+}  // namespace ptk

@@ -1002,6 +1002,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     PTK_LAUNCH_OK("bn_apply_kernel");
     ConvArgs c1{d.dAct_at(t, 1), d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+    c1.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     if (!tc) {   // strict fp32: per-step CUDA-core weight gradient (the tensor-core modes defer it, see below)
@@ -1021,6 +1022,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       }
       PTK_LAUNCH_OK("bn_apply_kernel");
       ConvArgs c0{d.dAct_at(t, 0), d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+    c0.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
       { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
       if (!tc) {

@@ -520,6 +520,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
     int rc;
     if (!NOINH) {
       ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode, 1};
+    c0.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
       { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
       {
@@ -530,6 +531,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
       PTK_LAUNCH_OK("int_mid_kernel");
     }
     ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1), d.conv_mode, 1};
+    c1.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     {

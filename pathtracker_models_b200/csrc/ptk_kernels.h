@@ -18,6 +18,7 @@ struct ConvArgs {
   int pdl = 0;         // launched inside the time loop: programmatic dependent launch allowed (ptk_common.cuh)
   long long in_bs = 0, out_bs = 0;   // tensor-core path: elements between samples (0 = 32*H*W); lets a 32-channel block
                                      // of a wider [B,Cw,H,W] tensor be convolved in place (ConvGRU, ptk_gru.cu)
+  int v2 = 0;          // tensor-core path: wT is the ptk_conv_tc2.cu weight stream (launch_prep_weights_tc2) -> conv7_tc2_kernel
 };
 
 struct WgradArgs {
@@ -90,6 +91,11 @@ int conv_num_ctas(int B, int H, int W);
 int launch_conv7(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad7(const WgradArgs& a, int groups, cudaStream_t st);
 int launch_conv7_tc(const ConvArgs& a, cudaStream_t st);
+// second-generation tensor-core convolution (ptk_conv_tc2.cu: weights as the A operand, chunked double-buffered epilogue)
+bool conv_v2_enabled();            // PTK_CONV_V1=1 selects the first-generation kernel (A/B measurements)
+size_t conv7_tc2_weight_bytes();   // per weight bank and direction
+int launch_conv7_tc2(const ConvArgs& a, cudaStream_t st);
+int launch_prep_weights_tc2(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride = 0);
 int launch_prep_weights_tc(const float* w, void* wf, void* wd, cudaStream_t st, int oc_stride = 0);   // 0 = 32*49 (dense)
 int launch_wgrad7_tc(const WgradArgs& a, cudaStream_t st);   // wacc: [nCTA][49][32 oc][32 ic]
 size_t wgrad_tc_acc_floats(int B, int H, int W);
