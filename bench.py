@@ -517,6 +517,12 @@ def run_b200(args):
         grad_check = {"checksum_sum": cs[0].item(), "checksum_abs": cs[1].item(),
                       "max_rank_spread": (hi - lo).abs().max().item(), "identical_on_all_ranks": bool(torch.equal(lo, hi))}
 
+    headline = (args.model, T_, HW_, B) == ("int", 64, 32, 64)
+    parity = cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and headline:
+        # BEFORE the optimizer timing below touches the weights: the CPU port rebuilds the same seed-0 model
+        parity, cpu_base = parity_vs_cpu_port(model, dev)     # ~15 s of host work
+
     # ---- the step either side of the path, reported separately ("optimizer step excluded and reported
     # separately"): loss + metrics kernel and fused Adam + zero_grad vs torch.optim.Adam on the same gradients
     from pathtracker_models_b200.optim import FusedAdam, bce_with_logits_and_scores
@@ -558,7 +564,6 @@ def run_b200(args):
 
     if rank == 0:
         tensor_peak, hbm_peak, src = load_peaks()
-        headline = (args.model, T_, HW_, B) == ("int", 64, 32, 64)
         conv_ms, conv_n = prof["conv_fwd"][0] + prof["conv_dgrad"][0], prof["conv_fwd"][1] + prof["conv_dgrad"][1]
         conv_flop = 2 * B * HW_ * HW_ * C * C * K * K
         conv_avg_ms = conv_ms / max(conv_n, 1)
@@ -600,8 +605,8 @@ def run_b200(args):
         }
         if grad_check is not None:
             line["multi_gpu_gradient_check"] = grad_check
-        if world == 1 and not args.no_cpu_baseline and headline:
-            line["parity"], line["cpu_baseline"] = parity_vs_cpu_port(model, dev)     # ~15 s of host work
+        if parity is not None:
+            line["parity"], line["cpu_baseline"] = parity, cpu_base
         elif world == 1 and not args.no_cpu_baseline:
             v, sec, cores, sample = cpu_port_int(steps=4, warmup=1, batch=max(1, min(8, 2048 // (HW_ * HW_ // 16))),
                                                  frames=T_, size=HW_, variant=args.model)

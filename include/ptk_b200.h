@@ -143,6 +143,10 @@ typedef struct PtkLstmDims {
   int32_t conv_mode;   /* PTK_CONV_FP32: every convolution in strict fp32 on CUDA cores; PTK_CONV_BF16X3: the recurrent
                         * convolution of h and its transpose (the two per-step convolutions of the time loops) as
                         * 3-pass split-bf16 tcgen05 implicit GEMMs, same parity gate                    */
+  int32_t ckpt_ring;   /* 0: forward keeps h_t, c_t, gates_t of EVERY step (BPTT needs them all).
+                        * 1: constant-memory checkpoints for recurrent back-propagation (models/convlstm.py:124-135 runs the
+                        *    first T-1 steps under no_grad): two-slot rings, so only steps T-1 and T survive;
+                        *    ptk_convlstm_saved_bytes no longer grows with T.  ptk_convlstm_backward then refuses. */
 } PtkLstmDims;
 PTK_API int ptk_convlstm_param_offsets(const PtkLstmDims* d, int64_t* offsets);
 PTK_API size_t ptk_convlstm_saved_bytes(const PtkLstmDims* d);
@@ -161,7 +165,8 @@ PTK_API int ptk_convlstm_backward(const PtkLstmDims* d, const float* x, const fl
  * :124-135): Neumann series g = sum_k (J^T)^k dL/dh_T on the last step's Jacobian, truncated after num_iter
  * terms or by the reference's norm tests (|g| > 1, |v_k| > |v_{k-1}|, |v_k| < 1e-9); parameter gradients = one
  * cell-step backward with dh_T := g.  The stop test runs on the device (no synchronisation); terms_out
- * (optional, device, 1 float) receives the number of accepted terms.  Same forward / saved buffer as BPTT. */
+ * (optional, device, 1 float) receives the number of accepted terms.  Reads only the last two steps of the
+ * checkpoints: works with ckpt_ring = 1 (O(1) memory) as well as with the full BPTT buffer. */
 PTK_API int ptk_convlstm_backward_rbp(const PtkLstmDims* d, const float* x, const float* params, const void* saved,
                                       const float* doutput, int32_t num_iter, float* dparams, float* terms_out,
                                       void* workspace, size_t workspace_bytes, void* stream);

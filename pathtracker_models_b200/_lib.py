@@ -30,7 +30,7 @@ class PtkDims(ctypes.Structure):
 
 
 class PtkLstmDims(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K", "conv_mode")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K", "conv_mode", "ckpt_ring")]
 
 
 class PtkGruDims(ctypes.Structure):

@@ -140,8 +140,10 @@ class ConvLSTM(nn.Module):
         B, ch, H, W = x.shape
         if ch != 1:
             raise ValueError(f"expected x of shape [B,1,H,W], got {tuple(x.shape)}")
-        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size, int(self.conv_mode))
         rbp = self.grad_method == 'rbp'
+        # recurrent back-propagation reads only the last two steps: constant-memory checkpoint ring (models/convlstm.py:124-135
+        # runs the first T-1 steps under no_grad for exactly that reason); testmode returns every hidden state, so it keeps them
+        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size, int(self.conv_mode), int(rbp and not testmode))
         from .parallel import flat_gradient_hook
         output, pen, states = _ConvLSTMFunction.apply(x.float(), flat_gradient_hook(self, self.flat_parameters()), dims, bool(self.training),
                                                       int(self.num_iter) if rbp else None, bool(rbp and testmode))

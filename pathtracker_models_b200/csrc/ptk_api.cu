@@ -398,9 +398,10 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   const size_t P = (size_t)dm->H * dm->W, S = (size_t)dm->B * 25 * P, SG = 4 * S, taps = (size_t)dm->K * dm->K;
   const int groups = 7;   // (4 oc-blocks x 25 ic) x 7 = 700 CTAs: 5 per SM at most vs 4.73 on average (wave quantisation)
   Carver sv(saved);
-  float* hs = sv.take<float>((size_t)(dm->T + 1) * S);
-  float* cs = sv.take<float>((size_t)(dm->T + 1) * S);
-  float* gates = sv.take<float>((size_t)dm->T * SG);
+  const bool ring = dm->ckpt_ring != 0;
+  float* hs = sv.take<float>((size_t)(ring ? 2 : dm->T + 1) * S);
+  float* cs = sv.take<float>((size_t)(ring ? 2 : dm->T + 1) * S);
+  float* gates = sv.take<float>((size_t)(ring ? 2 : dm->T) * SG);
   float* u = sv.take<float>(S);
   float* xt = sv.take<float>(S);
   float* hstats = sv.take<float>(64);
@@ -455,6 +456,7 @@ static int lstm_bind(LstmDev* d, const PtkLstmDims* dm, const float* x, const fl
                      cudaStream_t st) {
   memset(d, 0, sizeof(*d));
   d->B = dm->B; d->T = dm->T; d->H = dm->H; d->W = dm->W; d->KS = dm->K;
+  d->ring = dm->ckpt_ring != 0;
   d->x = x;
   int64_t o[20];
   lstm_offsets(dm->K, o);
@@ -503,6 +505,7 @@ int ptk_convlstm_backward(const PtkLstmDims* dm, const float* x, const float* pa
   int rc = lstm_check(dm, "ptk_convlstm_backward");
   if (rc) return rc;
   if (!x || !params || !saved || !doutput || !dparams || !workspace) { set_error("ptk_convlstm_backward: NULL argument"); return PTK_EINVAL; }
+  if (dm->ckpt_ring) { set_error("ptk_convlstm_backward: BPTT needs the checkpoints of every step; the forward ran with ckpt_ring = 1"); return PTK_EINVAL; }
   if (workspace_bytes < ptk_convlstm_workspace_bytes(dm)) { set_error("ptk_convlstm_backward: workspace too small"); return PTK_ENOMEM; }
   cudaStream_t st = (cudaStream_t)stream;
   LstmDev d;

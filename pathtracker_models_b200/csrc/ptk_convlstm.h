@@ -7,6 +7,7 @@ namespace ptk {
 
 struct LstmDev {
   int B, T, H, W, KS, groups, conv_mode;
+  int ring;                             // checkpoints are two-slot rings (recurrent back-propagation: only steps T-1, T are read)
   void* dyc_tc;                         // delta of the step, pre-split per tile for the weight-gradient CTAs (wgradk_prep_dy)
   float *slots_h_tc, *slots_x_tc;       // tensor-core weight-gradient slots of Wh / Wx (ptk_wgradk_tc.cu)
   void *whF_tc, *whD_tc, *wxF_tc, *wxD_tc;   // [0] = Wh, [1] = Wx streams                // tensor-core weight streams of the recurrent convolution / its transpose
@@ -20,8 +21,8 @@ struct LstmDev {
   // re-laid-out weight banks (workspace)
   float *w0T, *wxT, *whT, *whD, *wxD;
   // checkpoints
-  float *hs, *cs;                       // [T+1][B,25,P]
-  float* gates;                         // [T][B,100,P] post-activation (i,f,g,o)
+  float *hs, *cs;                       // [T+1][B,25,P]   (ring: [2])
+  float* gates;                         // [T][B,100,P] post-activation (i,f,g,o)   (ring: [2])
   float *u, *xt, *Xg;                   // conv0 output, its square, hoisted input terms
   float* head_stats;                    // [2][25]
   // scratch
@@ -36,9 +37,9 @@ struct LstmDev {
   float* dparams;
   long long off_w0, off_b0, off_wx, off_bx, off_wh, off_head;
 
-  __host__ __device__ float* h_at(int t) const { return hs + (size_t)t * B * 25 * H * W; }
-  __host__ __device__ float* c_at(int t) const { return cs + (size_t)t * B * 25 * H * W; }
-  __host__ __device__ float* gates_at(int t) const { return gates + (size_t)(t - 1) * B * 100 * H * W; }   // t = 1..T
+  __host__ __device__ float* h_at(int t) const { return hs + (size_t)(ring ? (t & 1) : t) * B * 25 * H * W; }
+  __host__ __device__ float* c_at(int t) const { return cs + (size_t)(ring ? (t & 1) : t) * B * 25 * H * W; }
+  __host__ __device__ float* gates_at(int t) const { return gates + (size_t)(ring ? (t & 1) : t - 1) * B * 100 * H * W; }   // t = 1..T
 };
 
 int run_convlstm_forward(const LstmDev& d, cudaStream_t st);

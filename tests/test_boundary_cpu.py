@@ -24,6 +24,18 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().ptk_version() == 100
 
 
+def test_rbp_checkpoints_are_constant_memory():
+    """recurrent back-propagation (models/convlstm.py:124-135) keeps no per-step state: with ckpt_ring = 1 the checkpoint
+    buffer of the ConvLSTM does not grow with the number of time steps; the BPTT buffer does."""
+    from pathtracker_models_b200 import _lib
+    L = _lib.lib()
+    sb = lambda T, ring: L.ptk_convlstm_saved_bytes(ctypes.byref(_lib.PtkLstmDims(8, T, 32, 32, 15, 1, ring)))
+    assert sb(4, 1) == sb(64, 1) == sb(1000, 1) > 0
+    assert sb(64, 0) > 10 * sb(64, 1)
+    per_step = (25 + 25 + 100) * 8 * 32 * 32 * 4            # h_t, c_t, gates_t
+    assert sb(65, 0) - sb(64, 0) == per_step
+
+
 def test_param_layout_matches_module():
     from pathtracker_models_b200 import InT, _lib
     from pathtracker_models_b200._recurrent import PARAM_ORDER
