@@ -98,7 +98,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
   float* wacc_inh = cv.take<float>(wacc_n);
   // tensor-core modes, backward only: every step's dY0, dY1 and Ge stay live for the deferred weight gradient
   const bool defer = dm->conv_mode != PTK_CONV_FP32 && with_bwd;
-  float* dys = cv.take<float>(defer ? 3 * (size_t)dm->T * S : 0);
+  float* dys = cv.take<float>(defer ? 7 * (size_t)dm->T * S : 0);
   if (d) {
     d->Ge = Ge;
     d->bn_part = bn_part; d->counter = counter; d->pw_ctas = pw;
@@ -111,7 +111,9 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
     d->cgI = big + 10 * S; d->cGe = big + 11 * S;
     d->GeB[0] = Ge; d->GeB[1] = big + 12 * S; d->gebB[0] = d->geb; d->gebB[1] = big + 13 * S;
     d->dy_tstride = defer ? S : 0;
-    d->dYs[0] = dys; d->dYs[1] = dys + (defer ? (size_t)dm->T * S : 0); d->GeT = dys + (defer ? 2 * (size_t)dm->T * S : 0);
+    const size_t TS = defer ? (size_t)dm->T * S : 0;
+    d->dYs[0] = dys; d->dYs[1] = dys + TS; d->GeT = dys + 2 * TS;
+    d->gebT = dys + 3 * TS; d->giT = dys + 4 * TS; d->aT = dys + 5 * TS; d->XT = dys + 6 * TS;
     // inference ring view of `big` (only used when saved == NULL)
     if (d->ck_ring) {
       d->ckI = big; d->ckE = big + 2 * S; d->ck_stride = S;

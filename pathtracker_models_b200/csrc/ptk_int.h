@@ -58,6 +58,7 @@ struct IntDev {
   // tensor-core modes: the 7x7 weight gradients are taken once, after the reverse loop, over ALL steps
   // (ptk_wgrad_ts.cu), so every step's dY0 / dY1 and Ge are kept: [T][B,C,P] each (dy_tstride = B*C*P, else 0)
   float *dYs[2], *GeT;
+  float *gebT, *giT, *aT, *XT;   // likewise the operands of the six gate weight gradients (one launch over all steps at the end)
   size_t dy_tstride;
   int pw_ctas;             // grid of the backward point-wise kernels (fixed => deterministic slots)
   float* acc;              // [pw_ctas][ACC_N]
@@ -85,6 +86,10 @@ struct IntDev {
   // gradient wrt the pre-BatchNorm conv output of BatchNorm `bn` at step t (dV / dU before bn_apply, dY after)
   __host__ __device__ float* dAct_at(int t, int bn) const { return dy_tstride ? dYs[bn] + dy_tstride * t : dAct; }
   __host__ __device__ float* GeB_at(int t) const { return dy_tstride ? GeT + dy_tstride * t : GeB[t & 1]; }
+  __host__ __device__ float* geb_at(int t) const { return dy_tstride ? gebT + dy_tstride * t : gebB[t & 1]; }
+  __host__ __device__ float* gi_at(int t) const { return dy_tstride ? giT + dy_tstride * t : giS; }
+  __host__ __device__ float* a_at(int t) const { return dy_tstride ? aT + dy_tstride * t : aS; }
+  __host__ __device__ float* X_at(int t) const { return dy_tstride ? XT + dy_tstride * t : Xs; }
 };
 
 int run_int_forward(const IntDev& d, int cell, int act, cudaStream_t st);

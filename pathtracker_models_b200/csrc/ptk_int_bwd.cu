@@ -136,7 +136,7 @@ __device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, size_t idx
   }
   st4(d.gE + idx, oGE);
   st4(d.gI + idx, oGI);
-  st4(d.gebB[t & 1] + idx, oGeb);
+  st4(d.geb_at(t) + idx, oGeb);
   st4(d.dAct_at(t, 1) + idx, oDv);
   st4(d.GeB_at(t) + idx, oGe);
 }
@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   const float* Y0 = d.Y0_at(t);
   const float* Git = d.Gi_at(t);
   float* dU_out = d.dAct_at(t, 0);
+  float* gi_out = d.gi_at(t);
+  float* X_out = d.X_at(t);
   int wt = blockIdx.x * 4 + warp;
   BwdCIn cur;
   float xin[3][4];
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   pdl_launch_dependents();
   if (wt < nWT) {     // first tile's operands
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
-    warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(sGe, d.geb_at(t), (size_t)C * P, b, pix_base, P);
     if (CELL != CELL_NOINH) bwd_c_load<CELL>(d, It, At, Y0, Git, (size_t)b * C * P + pix_base + L.pxo + (size_t)L.oc0 * P, cur);
   }
   cp_async_commit();
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
     if (!firstTile) {
-      warp_tile_load_async(sGe, d.gebB[t & 1], (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(sGe, d.geb_at(t), (size_t)C * P, b, pix_base, P);
       cp_async_commit();
       if (CELL != CELL_NOINH) bwd_c_load<CELL>(d, It, At, Y0, Git, base + (size_t)L.oc0 * P, cur);
       frame_px(d.fv, b, t, pix, d.W, xin);
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
         stem_pre(sWp, sbp, L.oc0 + o, xin, X);
 #pragma unroll
         for (int p = 0; p < 4; ++p) X[p] = actf<ACT>(X[p]);
-        st4(d.Xs + base + (size_t)(L.oc0 + o) * P, X);
+        st4(d.X_at(t) + base + (size_t)(L.oc0 + o) * P, X);
       }
       cp_async_wait<0>();
       __syncwarp();
@@ -403,8 +405,8 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
         part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
       }
       st4(dU_out + idx, oDu);
-      st4(d.giS + idx, oGi);
-      st4(d.Xs + idx, X);
+      st4(gi_out + idx, oGi);
+      st4(X_out + idx, X);
       st4(d.dX + idx, oZ);        // parked: completed by the transposed products below
       st4(d.dS + idx, oDs);
       tile_st(sGi, L, o, oGi);
@@ -494,6 +496,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   const float* Et = d.E_at(t);
   const float* At = d.A_at(t);
+  float* a_out = d.a_at(t);
   int wt = blockIdx.x * 4 + warp;
   BwdDIn cur;
   float xin[3][4];
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
         ode[p] = fmaf(dGe[p], A[p], gE[p]) + (CELL == CELL_NOINH ? dS[p] : 0.0f);
       }
       if (o < 7) cur = nxt;
-      st4(d.aS + idx, oa);
+      st4(a_out + idx, oa);
       st4(d.gE + idx, ode);          // parked: completed by the transposed product below
       tile_st(sA, L, o, oa);
     }
@@ -682,16 +685,19 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 //     layout (GSP = 68 = 4 mod 32) makes every fragment load a conflict-free LDS.32.
 constexpr int GPX = 64, GSP = GPX + 4, GT_F = C * GSP;
 
+// The kernel covers steps t0 .. t0 + nT - 1: one step per launch in the strict-fp32 mode, ALL steps in one launch after the
+// reverse loop in the tensor-core modes (the operands of every step are kept, IntDev::geb_at ...), persistent CTAs.
 template <int CELL, bool MMA>
-__global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int first) {
+__global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, int nT, int first) {
   extern __shared__ __align__(16) float dsm[];
   pdl_wait();
   pdl_launch_dependents();
-  const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, nTiles = d.B * tpi;
-  const float* src[7] = {d.gebB[t & 1], d.giS, d.aS,
-                         (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB_at(t), d.Xs, d.E_at(t)};
+  const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, perT = d.B * tpi, nTiles = nT * perT;
   auto issue = [&](int tile, int buf) {
-    const int b = tile / tpi, pix_base = (tile - b * tpi) * GPX;
+    const int t = t0 + tile / perT, tile_t = tile % perT;
+    const float* src[7] = {d.geb_at(t), d.gi_at(t), d.a_at(t),
+                           (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB_at(t), d.X_at(t), d.E_at(t)};
+    const int b = tile_t / tpi, pix_base = (tile_t - b * tpi) * GPX;
     float* dstb = dsm + (size_t)buf * 7 * GT_F;
     for (int q = tid; q < 7 * C * (GPX / 4); q += 384) {
       const int k = q / (C * (GPX / 4)), r = q - k * (C * (GPX / 4)), c = r / (GPX / 4), part = r % (GPX / 4);
@@ -702,16 +708,27 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
   const int half = (tid >> 5) & 1, fg = (tid & 31) >> 2, ft = tid & 3;   // MMA fragment coordinates
   const int gsel = m >> 1;                       // 0: ge, 1: gi, 2: a
   const int vsel = (m == 0 || m == 3) ? 3 : (m == 1 ? 4 : (m == 5 ? 6 : 5));   // S, Ge, X, S, X, E
-  float acc[4][4];
+  // two-level sums: `acc` / `bsum` hold the current time step, `tot` / `btot` all finished ones (one long fp32 chain
+  // over 64 steps x 7 tiles lost ~1e-4 on the hGRU gate gradients at T = 64; per-step partial sums do not)
+  float acc[4][4], tot[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float bsum = 0.f;
-  int buf = 0;
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
+  float bsum = 0.f, btot = 0.f;
+  int buf = 0, t_cur = (int)blockIdx.x / perT;
   if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
   cp_async_commit();
   for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    if (tile / perT != t_cur) {       // a new time step starts: retire the finished one
+      t_cur = tile / perT;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+      btot += bsum;
+      bsum = 0.f;
+    }
     const int nxt = tile + gridDim.x;
     if (nxt < nTiles) issue(nxt, buf ^ 1);
     cp_async_commit();
@@ -768,6 +785,11 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t, int
     buf ^= 1;
   }
   cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += tot[i][j];
+  bsum += btot;
   float* ga = d.gacc + (size_t)blockIdx.x * GACC_N;
   if (MMA) {
 #pragma unroll
@@ -969,11 +991,12 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     const size_t Sb = (size_t)d.B * C * P * sizeof(float);
     PTK_CUDA_OK(cudaMemsetAsync(d.cGe, 0, Sb, st));
     PTK_CUDA_OK(cudaMemsetAsync(d.dX, 0, Sb, st));
-    PTK_CUDA_OK(cudaMemsetAsync(d.giS, 0, Sb, st));
+    PTK_CUDA_OK(cudaMemsetAsync(d.gi_at(0), 0, d.dy_tstride ? Sb * d.T : Sb, st));
     PTK_CUDA_OK(cudaMemsetAsync(d.bn_acc, 0, 4 * C * sizeof(double), st));
     PTK_CUDA_OK(cudaMemsetAsync(d.wacc_inh, 0, (tc ? wgrad_ts_acc_floats(d.T, d.B, d.H, d.W) : (size_t)4 * WGRAD_GROUPS * TAPS * 256) * sizeof(float), st));
   }
-  const int gate_grid = (d.B * P / GPX) < GATE_CTAS ? (d.B * P / GPX) : GATE_CTAS;
+  const long long gate_tiles = (long long)(d.B * P / GPX) * (tc ? d.T : 1);
+  const int gate_grid = gate_tiles < GATE_CTAS ? (int)gate_tiles : GATE_CTAS;
   PTK_CUDA_OK(ptk_func_smem(int_bwd_c_kernel<CELL, ACT>, (int)SM_BWD_C));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
@@ -1037,11 +1060,15 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
     }
     PTK_LAUNCH_OK("int_bwd_d_kernel");
-    {
+    if (!tc) {
       ProfileScope ps(PTK_PROF_GATE_WGRAD, st);
-      if (tc) PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, true>, dim3(gate_grid), dim3(384), SM_GATE, st, d, t, first));
-      else PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, false>, dim3(gate_grid), dim3(384), SM_GATE, st, d, t, first));
+      PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, false>, dim3(gate_grid), dim3(384), SM_GATE, st, d, t, 1, first));
+      PTK_LAUNCH_OK("gate_wgrad_kernel");
     }
+  }
+  if (tc) {   // the six gate weight gradients of ALL steps in one launch
+    ProfileScope ps(PTK_PROF_GATE_WGRAD, st);
+    PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, true>, dim3(gate_grid), dim3(384), SM_GATE, st, d, 0, d.T, 1));
     PTK_LAUNCH_OK("gate_wgrad_kernel");
   }
   if (tc) {
