@@ -138,7 +138,7 @@ __device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, size_t idx
   st4(d.gI + idx, oGI);
   st4(d.geb_at(t) + idx, oGeb);
   st4(d.dAct_at(t, 1) + idx, oDv);
-  st4(d.GeB_at(t) + idx, oGe);
+  st4s(d.GeB_at(t) + idx, oGe, d.dy_tstride != 0);
 }
 __device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* sKa, float* sGa, float* sW1, float* sB1,
                                                  float* sM1, float* sR1) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
         stem_pre(sWp, sbp, L.oc0 + o, xin, X);
 #pragma unroll
         for (int p = 0; p < 4; ++p) X[p] = actf<ACT>(X[p]);
-        st4(d.X_at(t) + base + (size_t)(L.oc0 + o) * P, X);
+        st4s(d.X_at(t) + base + (size_t)(L.oc0 + o) * P, X, d.dy_tstride != 0);
       }
       cp_async_wait<0>();
       __syncwarp();
@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
         part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
       }
       st4(dU_out + idx, oDu);
-      st4(gi_out + idx, oGi);
-      st4(X_out + idx, X);
+      st4s(gi_out + idx, oGi, d.dy_tstride != 0);
+      st4s(X_out + idx, X, d.dy_tstride != 0);
       st4(d.dX + idx, oZ);        // parked: completed by the transposed products below
       st4(d.dS + idx, oDs);
       tile_st(sGi, L, o, oGi);
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
         ode[p] = fmaf(dGe[p], A[p], gE[p]) + (CELL == CELL_NOINH ? dS[p] : 0.0f);
       }
       if (o < 7) cur = nxt;
-      st4(a_out + idx, oa);
+      st4s(a_out + idx, oa, d.dy_tstride != 0);
       st4(d.gE + idx, ode);          // parked: completed by the transposed product below
       tile_st(sA, L, o, oa);
     }
@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 //     ~2^-21 relative error per product (same idea as the split-bf16 convolutions).  The [c][GSP] tile
 //     layout (GSP = 68 = 4 mod 32) makes every fragment load a conflict-free LDS.32.
 constexpr int GPX = 64, GSP = GPX + 4, GT_F = C * GSP;
+constexpr int GNST = 3;   // cp.async stages: the all-steps launch streams its 7 operand tensors from HBM, two tiles in flight
 
 // The kernel covers steps t0 .. t0 + nT - 1: one step per launch in the strict-fp32 mode, ALL steps in one launch after the
 // reverse loop in the tensor-core modes (the operands of every step are kept, IntDev::geb_at ...), persistent CTAs.
@@ -717,8 +718,11 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
     for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
   float bsum = 0.f, btot = 0.f;
   int buf = 0, t_cur = (int)blockIdx.x / perT;
-  if ((int)blockIdx.x < nTiles) issue(blockIdx.x, 0);
-  cp_async_commit();
+#pragma unroll
+  for (int s = 0; s < GNST - 1; ++s) {
+    if ((int)(blockIdx.x + s * gridDim.x) < nTiles) issue(blockIdx.x + s * gridDim.x, s);
+    cp_async_commit();
+  }
   for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     if (tile / perT != t_cur) {       // a new time step starts: retire the finished one
       t_cur = tile / perT;
@@ -729,10 +733,10 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
       btot += bsum;
       bsum = 0.f;
     }
-    const int nxt = tile + gridDim.x;
-    if (nxt < nTiles) issue(nxt, buf ^ 1);
+    const int nxt = tile + (GNST - 1) * gridDim.x;
+    if (nxt < nTiles) issue(nxt, (buf + GNST - 1) % GNST);
     cp_async_commit();
-    cp_async_wait<1>();
+    cp_async_wait<GNST - 1>();
     __syncthreads();
     const float* base = dsm + (size_t)buf * 7 * GT_F;
     if (MMA) {
@@ -782,7 +786,7 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
       }
     }
     __syncthreads();
-    buf ^= 1;
+    buf = (buf + 1) % GNST;
   }
   cp_async_wait<0>();
 #pragma unroll
@@ -977,7 +981,7 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
 // ---- host ----------------------------------------------------------------------------------
 static constexpr size_t SM_BWD_C = (size_t)(4 * C * C + 4 * 2 * TILE_F) * sizeof(float);
 static constexpr size_t SM_BWD_D = (size_t)(2 * C * C + 4 * 2 * TILE_F) * sizeof(float);
-static constexpr size_t SM_GATE = (size_t)(2 * 7 * GT_F) * sizeof(float);
+static constexpr size_t SM_GATE = (size_t)(GNST * 7 * GT_F) * sizeof(float);
 
 template <int CELL, int ACT>
 static int run_backward_t(const IntDev& d, cudaStream_t st) {

@@ -125,6 +125,12 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
+// streaming store (st.global.cs, evict-first in L2): for tensors nobody reads again inside the reverse loop (the per-step
+// operand stores of the deferred weight-gradient launches), so that they do not push the step's working set out of L2
+__device__ __forceinline__ void st4s(float* p, const float (&v)[4], bool stream) {
+  if (stream) __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  else st4(p, v);
+}
 __device__ __forceinline__ void ld4v(const float* p, float (&v)[4]) {
   const float4 t = ld4(p);
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
