@@ -183,8 +183,12 @@ typedef struct PtkGruDims {
   int32_t B, T, H, W;
   int32_t C;           /* 64  */
   int32_t K;           /* 7   */
-  int32_t conv_mode;   /* PTK_CONV_FP32: generic CUDA-core convolutions; PTK_CONV_BF16X3 / PTK_CONV_BF16: the 128->128 and
-                        * 128->64 convolutions run as 32x32-channel blocks on the tcgen05 kernels of the InT path      */
+  int32_t conv_mode;   /* PTK_CONV_FP32: generic strict-fp32 CUDA-core convolutions (ptk_convg.cuh).
+                        * PTK_CONV_BF16X3 (default): the stacked 128->128 [r|u] convolution, the 128->64 candidate
+                        *   convolution, their transposes and weight gradients on the wide tcgen05 kernels shared with the
+                        *   ConvLSTM (ptk_convk_tc.cu, ptk_wgradk_tc.cu), 3-pass split-bf16, same parity gate.
+                        * PTK_CONV_BF16: single-pass bf16 as 32x32-channel block launches on the first-generation InT
+                        *   kernels (ptk_conv_tc.cu, ptk_wgrad_tc.cu); not an fp32-parity mode                          */
 } PtkGruDims;
 PTK_API int ptk_gru_param_offsets(const PtkGruDims* d, int64_t* offsets);
 PTK_API size_t ptk_gru_saved_bytes(const PtkGruDims* d);
