@@ -111,6 +111,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
     d->cgI = big + 10 * S; d->cGe = big + 11 * S;
     d->GeB[0] = Ge; d->GeB[1] = big + 12 * S; d->gebB[0] = d->geb; d->gebB[1] = big + 13 * S;
     d->dy_tstride = defer ? S : 0;
+    d->bn_fused = defer && conv_v2_enabled();
     const size_t TS = defer ? (size_t)dm->T * S : 0;
     d->dYs[0] = dys; d->dYs[1] = dys + TS; d->GeT = dys + 2 * TS;
     d->gebT = dys + 3 * TS; d->giT = dys + 4 * TS; d->aT = dys + 5 * TS; d->XT = dys + 6 * TS;

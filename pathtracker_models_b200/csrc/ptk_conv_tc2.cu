@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
   uint64_t* dEmpty = dFull + 2;                             // [2] accumulator buffer drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dEmpty + 2);
   __shared__ double sFin[8][C][3];
+  __shared__ float4 sBN[C];                                 // fused BatchNorm backward: k, mean(dV), mean, rstd * mean(dV*xhat)
   __shared__ int sIsLast;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -95,32 +96,76 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
       bulk_g2s(sWr + i * T2_STAGE, wsrc + (size_t)i * T2_STAGE, T2_STAGE, &full[i]);
     }
   }
+  if (a.bn_y != nullptr) {   // the saved conv output is a forward checkpoint: pull the tile's lines HBM -> L2 before the wait
+    for (int it = tid; it < C * T2_ROWS; it += 256) {
+      const int ch = it / T2_ROWS, gy = y0 - 3 + (it - ch * T2_ROWS);
+      if (gy >= 0 && gy < H) prefetch_l2(a.bn_y + (size_t)b * C * H * W + ((size_t)ch * H + gy) * W + x0);
+    }
+  }
   // everything above touched only shared memory, TMEM and the prepared weights (written >= 2 kernels ago)
   pdl_wait();
   pdl_launch_dependents();
 
   // ---- stage the input tile: fp32 NCHW -> bf16 hi/lo, channel-chunk planar (same image as ptk_conv_tc.cu) -------
+  // With bn_y set the tile is dV and the BatchNorm backward (b3 / b9) is applied on the way: per channel
+  //   dY = k * (dV - m - (Y - mean) * rn),  k = w*rstd, m = mean(dV), rn = rstd * mean(dV*xhat)
+  const bool bnf = (a.bn_y != nullptr);
+  if (bnf) {
+    if (tid < C) {
+      const float rstd = a.bn_stat[C + tid];
+      sBN[tid] = make_float4(__ldg(a.bn_w + tid) * rstd, a.bn_tot[tid], a.bn_stat[tid], rstd * a.bn_tot[C + tid]);
+    }
+    __syncthreads();
+  }
   {
     constexpr int NIT = 4 * T2_ROWS * (T2_TW / 4), NR = (NIT + 255) / 256;
     float4 v[NR][8];
     int pp[NR], qq[NR];
+    size_t off[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int it = tid + 256 * r;
       const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
       const int gy = y0 + row - 3;
-      pp[r] = -1; qq[r] = q;
+      pp[r] = -1; qq[r] = q; off[r] = 0;
       if (it < NIT && gy >= 0 && gy < H) {
         pp[r] = row * T2_WP + 3 + 4 * g;
-        const float* src = a.in + (size_t)b * in_bs + ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
+        off[r] = ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
+        const float* src = a.in + (size_t)b * in_bs + off[r];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
       }
     }
+    float4 yv[2][8];
+    if (bnf && pp[0] >= 0) {
+      const float* ys = a.bn_y + (size_t)b * C * H * W + off[0];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[0][e] = *reinterpret_cast<const float4*>(ys + (size_t)e * H * W);
+    }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
+      if (bnf && r + 1 < NR && pp[r + 1] >= 0) {     // the next item's Y in flight while this one is converted
+        const float* ys = a.bn_y + (size_t)b * C * H * W + off[r + 1];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[(r + 1) & 1][e] = *reinterpret_cast<const float4*>(ys + (size_t)e * H * W);
+      }
       if (pp[r] < 0) continue;
       const int p = pp[r], q = qq[r];
+      if (bnf) {
+        const int row = (tid + 256 * r) >> 5;
+        const bool own = row >= 3 && row < 3 + T2_TH;            // interior rows: this CTA owns their dY
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 cst = sBN[q * 8 + e], y = yv[r & 1][e];
+          float4 t = v[r][e];
+          t.x = cst.x * (t.x - cst.y - (y.x - cst.z) * cst.w);
+          t.y = cst.x * (t.y - cst.y - (y.y - cst.z) * cst.w);
+          t.z = cst.x * (t.z - cst.y - (y.z - cst.z) * cst.w);
+          t.w = cst.x * (t.w - cst.y - (y.w - cst.z) * cst.w);
+          v[r][e] = t;
+          if (own) *reinterpret_cast<float4*>(a.bn_out + (size_t)b * C * H * W + off[r] + (size_t)e * H * W) = t;
+        }
+      }
 #pragma unroll
       for (int px = 0; px < 4; ++px) {
         uint32_t hi[4], lo[4];
@@ -142,11 +187,18 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
       const int c = hc < 3 ? hc : (T2_TW + hc);          // padded columns 0..2 and 35..37
       const int gy = y0 + r - 3, gx = x0 + c - 3;
       if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;
-      const float* src = a.in + (size_t)b * in_bs + ((size_t)(q * 8) * H + gy) * W + gx;
+      const size_t o = ((size_t)(q * 8) * H + gy) * W + gx;
+      const float* src = a.in + (size_t)b * in_bs + o;
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
+        float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
+        if (bnf) {
+          const float* ys = a.bn_y + (size_t)b * C * H * W + o;
+          const float4 c0 = sBN[q * 8 + 2 * e], c1 = sBN[q * 8 + 2 * e + 1];
+          v0 = c0.x * (v0 - c0.y - (ys[(size_t)(2 * e) * H * W] - c0.z) * c0.w);
+          v1 = c1.x * (v1 - c1.y - (ys[(size_t)(2 * e + 1) * H * W] - c1.z) * c1.w);
+        }
         const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
         hi[e] = pack_bf16x2(h0, h1);
         lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));

@@ -60,6 +60,8 @@ struct IntDev {
   float *dYs[2], *GeT;
   float *gebT, *giT, *aT, *XT;   // likewise the operands of the six gate weight gradients (one launch over all steps at the end)
   size_t dy_tstride;
+  int bn_fused;            // the BatchNorm backward (b3 / b9) runs inside the data-gradient convolution's operand staging
+                           // (conv7_tc2): bwd_a / bwd_c write dV / dU to the scratch `dAct`, the convolution writes dY per step
   int pw_ctas;             // grid of the backward point-wise kernels (fixed => deterministic slots)
   float* acc;              // [pw_ctas][ACC_N]
   float* gacc;             // [GATE_CTAS][GACC_N]
@@ -85,6 +87,7 @@ struct IntDev {
   __host__ __device__ float* A_at(int t) const { return A + (size_t)t * a_tstride; }
   // gradient wrt the pre-BatchNorm conv output of BatchNorm `bn` at step t (dV / dU before bn_apply, dY after)
   __host__ __device__ float* dAct_at(int t, int bn) const { return dy_tstride ? dYs[bn] + dy_tstride * t : dAct; }
+  __host__ __device__ float* dV_at(int t, int bn) const { return bn_fused ? dAct : dAct_at(t, bn); }
   __host__ __device__ float* GeB_at(int t) const { return dy_tstride ? GeT + dy_tstride * t : GeB[t & 1]; }
   __host__ __device__ float* geb_at(int t) const { return dy_tstride ? gebT + dy_tstride * t : gebB[t & 1]; }
   __host__ __device__ float* gi_at(int t) const { return dy_tstride ? giT + dy_tstride * t : giS; }

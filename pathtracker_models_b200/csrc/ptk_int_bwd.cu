@@ -137,7 +137,7 @@ __device__ __forceinline__ void bwd_a_channel(const IntDev& d, int t, size_t idx
   st4(d.gE + idx, oGE);
   st4(d.gI + idx, oGI);
   st4(d.geb_at(t) + idx, oGeb);
-  st4(d.dAct_at(t, 1) + idx, oDv);
+  st4(d.dV_at(t, 1) + idx, oDv);
   st4s(d.GeB_at(t) + idx, oGe, d.dy_tstride != 0);
 }
 __device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* sKa, float* sGa, float* sW1, float* sB1,
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
   const float* At = d.A_at(t);
   const float* Y0 = d.Y0_at(t);
   const float* Git = d.Gi_at(t);
-  float* dU_out = d.dAct_at(t, 0);
+  float* dU_out = d.dV_at(t, 0);
   float* gi_out = d.gi_at(t);
   float* X_out = d.X_at(t);
   int wt = blockIdx.x * 4 + warp;
@@ -1023,12 +1023,15 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       int_bwd_a_kernel<ACT><<<grid_a, 128, 0, st>>>(d, t, first);
       PTK_LAUNCH_OK("int_bwd_a_kernel");
     }
-    {
+    if (!d.bn_fused) {
       ProfileScope ps(PTK_PROF_BN_APPLY, st);
       PTK_CUDA_OK(launch_pdl(true, bn_apply_kernel, dim3(ew_blocks), dim3(256), 0, st, d, (const float*)d.Y1_at(t), t, 1));
+      PTK_LAUNCH_OK("bn_apply_kernel");
     }
-    PTK_LAUNCH_OK("bn_apply_kernel");
-    ConvArgs c1{d.dAct_at(t, 1), d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+    ConvArgs c1{d.dV_at(t, 1), d.w_exc_d, d.cgI, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+    if (d.bn_fused) {   // (b3) inside the convolution's staging; dY1 of this step lands in its per-step store
+      c1.bn_y = d.Y1_at(t); c1.bn_stat = d.stat(t, 1); c1.bn_tot = d.bn_tot; c1.bn_w = d.bn_w[1]; c1.bn_out = d.dAct_at(t, 1);
+    }
     c1.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
     { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
@@ -1043,12 +1046,15 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     PTK_LAUNCH_OK("int_bwd_c_kernel");
     if (CELL != CELL_NOINH) {
-      {
+      if (!d.bn_fused) {
         ProfileScope ps(PTK_PROF_BN_APPLY, st);
         PTK_CUDA_OK(launch_pdl(true, bn_apply_kernel, dim3(ew_blocks), dim3(256), 0, st, d, (const float*)d.Y0_at(t), t, 0));
+        PTK_LAUNCH_OK("bn_apply_kernel");
       }
-      PTK_LAUNCH_OK("bn_apply_kernel");
-      ConvArgs c0{d.dAct_at(t, 0), d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+      ConvArgs c0{d.dV_at(t, 0), d.w_inh_d, d.cGe, d.B, d.H, d.W, 0, nullptr, nullptr, nullptr, d.conv_mode, 1};
+      if (d.bn_fused) {   // (b9)
+        c0.bn_y = d.Y0_at(t); c0.bn_stat = d.stat(t, 0); c0.bn_tot = d.bn_tot; c0.bn_w = d.bn_w[0]; c0.bn_out = d.dAct_at(t, 0);
+      }
     c0.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
       { ProfileScope ps(PTK_PROF_CONV_DGRAD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;

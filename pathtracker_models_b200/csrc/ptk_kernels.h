@@ -19,6 +19,15 @@ struct ConvArgs {
   long long in_bs = 0, out_bs = 0;   // tensor-core path: elements between samples (0 = 32*H*W); lets a 32-channel block
                                      // of a wider [B,Cw,H,W] tensor be convolved in place (ConvGRU, ptk_gru.cu)
   int v2 = 0;          // tensor-core path: wT is the ptk_conv_tc2.cu weight stream (launch_prep_weights_tc2) -> conv7_tc2_kernel
+  // conv7_tc2 only: BatchNorm backward fused into the operand staging (the data-gradient convolutions of the reverse loop).
+  // `in` then holds dV, the gradient wrt the BatchNorm OUTPUT; the kernel forms
+  //   dY = w*rstd * (dV - mean(dV) - xhat * mean(dV*xhat)),  xhat = (Y - mean) * rstd        (eqs b3 / b9)
+  // on the fly, convolves dY and writes the interior rows of dY to bn_out (read later by the deferred weight gradient).
+  const float* bn_y = nullptr;      // saved conv output Y of the forward step [B,32,H,W]; non-null enables the fusion
+  const float* bn_stat = nullptr;   // forward statistics: mean[32], rstd[32]
+  const float* bn_tot = nullptr;    // backward sums of this step: mean(dV)[32], mean(dV*xhat)[32]
+  const float* bn_w = nullptr;      // BatchNorm weight [32]
+  float* bn_out = nullptr;          // dY [B,32,H,W]; must not alias `in`
 };
 
 struct WgradArgs {
