@@ -31,8 +31,8 @@ C, K = 32, 7
 FP32_FFMA_PEAK_TFLOPS = 74.4   # nominal 148 SM x 128 lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the headline shape, from the
 # committed `ncu --set full` capture named in NCU_TRAFFIC_SOURCE (bench.py cannot run ncu on itself)
-NCU_TRAFFIC_BYTES = {"bf16x3": 8.650e6, "fp32": 8.623e6}
-NCU_TRAFFIC_SOURCE = "profiles/r1k_kernels_full.txt"
+NCU_TRAFFIC_BYTES = {"bf16x3": 8.665e6, "fp32": 8.623e6}
+NCU_TRAFFIC_SOURCE = "profiles/r2i_kernels_full.txt (conv7_tc2_kernel; fp32: profiles/r1a_conv7_ffma_full.txt)"
 
 
 def int_flop_per_seq(T_, HW_):
@@ -564,9 +564,13 @@ def run_b200(args):
 
     if rank == 0:
         tensor_peak, hbm_peak, src = load_peaks()
-        conv_ms, conv_n = prof["conv_fwd"][0] + prof["conv_dgrad"][0], prof["conv_fwd"][1] + prof["conv_dgrad"][1]
+        # the dominant kernel = the 7x7 convolution.  Its FORWARD launches are pure convolution (+ BatchNorm partial statistics);
+        # the data-gradient launches of the tensor-core modes also carry the fused BatchNorm backward (a second operand stream and
+        # the dY write-back), so they are reported beside it (dgrad_launch_ms) instead of being averaged into the roofline figure
+        conv_ms, conv_n = prof["conv_fwd"][0], prof["conv_fwd"][1]
         conv_flop = 2 * B * HW_ * HW_ * C * C * K * K
         conv_avg_ms = conv_ms / max(conv_n, 1)
+        dgrad_avg_ms = prof["conv_dgrad"][0] / max(prof["conv_dgrad"][1], 1)
         achieved = conv_flop / (conv_avg_ms * 1e-3) / 1e12 if conv_n else None
         shares = {k: round(v[0] / ms_prof, 4) for k, v in prof.items()}
         value = main["value"]
@@ -583,7 +587,7 @@ def run_b200(args):
             "gpu_launches": main["gpu_launches"],
             "optimizer": optimizer_block,
             "clocks": sampler.result(),
-            "roofline": {"bound": "tensor", "kernel": ("conv7_ffma_kernel" if args.conv_mode == "fp32" else "conv7_tc_kernel") + " (fwd + dgrad launches)",
+            "roofline": {"bound": "tensor", "kernel": ("conv7_ffma_kernel" if args.conv_mode == "fp32" else "conv7_tc2_kernel") + " (forward launches)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": (achieved / tensor_peak) if achieved else None,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.conv_mode) if headline else None,
@@ -591,6 +595,7 @@ def run_b200(args):
                                          "(8.4 MB in + 8.4 MB out, the output stays in L2)" % NCU_TRAFFIC_SOURCE,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % src,
                          "launch_ms": conv_avg_ms, "launches_timed": conv_n, "flop_per_launch": conv_flop,
+                         "dgrad_launch_ms": dgrad_avg_ms,
                          "frac_of_fp32_ffma_nominal": (achieved / FP32_FFMA_PEAK_TFLOPS) if achieved else None,
                          "note": ("3-pass split-bf16 tcgen05 conv: issues 3x the algorithmic MACs, so the fp32-parity ceiling "
                                   "is 1/3 of the bf16 peak (frac_of_third_peak)" if args.conv_mode == "bf16x3" else
