@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
   uint64_t* empty = bars + T2_NST;                          // [T2_NST]
   uint64_t* dFull = bars + 2 * T2_NST;                      // [2] accumulator buffer complete
   uint64_t* dEmpty = dFull + 2;                             // [2] accumulator buffer drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dEmpty + 2);
+  uint64_t* stA = dEmpty + 2;                               // operand image: input rows 0-11 (+ halo columns) staged
+  uint64_t* stB = stA + 1;                                  // input rows 12-21 staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stB + 1);
   __shared__ double sFin[8][C][3];
   __shared__ float4 sBN[C];                                 // fused BatchNorm backward: k, mean(dV), mean, rstd * mean(dV*xhat)
   __shared__ int sIsLast;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     for (int i = 0; i < T2_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&dFull[0], 1); mbar_init(&dFull[1], 1);
     mbar_init(&dEmpty[0], 4); mbar_init(&dEmpty[1], 4);
+    mbar_init(stA, 256); mbar_init(stB, 192);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -87,7 +90,10 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < T2_A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
   // weights do not depend on the input tile: start streaming right away
   if (tid == 0) {
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wT);
@@ -117,18 +123,24 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     }
     __syncthreads();
   }
-  {
-    constexpr int NIT = 4 * T2_ROWS * (T2_TW / 4), NR = (NIT + 255) / 256;
+  // Two phases, so that the MMA warp can start the first row chunk (input rows 0-11) while rows 12-21 are still being staged:
+  //   phase A: rows 0-11 (items 0..383), all 256 threads, + the halo columns  -> mbarrier stA
+  //   phase B: rows 12-21 (items 384..703), warps 2-7 only (warps 0 / 1 go to their producer / MMA roles) -> mbarrier stB
+  // one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels; a thread's items are requested before the
+  // first conversion (the tile is L2-latency bound).
+  auto stage_items = [&](int first, int stride, int limit) {
+    constexpr int NR = 2;
     float4 v[NR][8];
-    int pp[NR], qq[NR];
+    int pp[NR], qq[NR], rw[NR];
     size_t off[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const int it = tid + 256 * r;
+      // a quarter warp = (2 adjacent pixel groups) x (4 chunks): conflict-free 16-byte stores; a warp covers one whole input row
+      const int it = first + stride * r;
       const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
       const int gy = y0 + row - 3;
-      pp[r] = -1; qq[r] = q; off[r] = 0;
-      if (it < NIT && gy >= 0 && gy < H) {
+      pp[r] = -1; qq[r] = q; off[r] = 0; rw[r] = row;
+      if (it < limit && gy >= 0 && gy < H) {
         pp[r] = row * T2_WP + 3 + 4 * g;
         off[r] = ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
         const float* src = a.in + (size_t)b * in_bs + off[r];
@@ -152,8 +164,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
       if (pp[r] < 0) continue;
       const int p = pp[r], q = qq[r];
       if (bnf) {
-        const int row = (tid + 256 * r) >> 5;
-        const bool own = row >= 3 && row < 3 + T2_TH;            // interior rows: this CTA owns their dY
+        const bool own = rw[r] >= 3 && rw[r] < 3 + T2_TH;        // interior rows: this CTA owns their dY
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float4 cst = sBN[q * 8 + e], y = yv[r & 1][e];
@@ -180,7 +191,9 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
         *reinterpret_cast<uint4*>(sA + 4 * T2_PLANE + q * T2_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
-  }
+  };
+  constexpr int NIT_A = 4 * 12 * (T2_TW / 4), NIT = 4 * T2_ROWS * (T2_TW / 4);      // 384, 704
+  stage_items(tid, 256, NIT_A);
   if (W > T2_TW) {   // halo columns (only inside the image when W > 32)
     for (int it = tid; it < 4 * T2_ROWS * 6; it += 256) {
       const int q = it / (T2_ROWS * 6), rem = it - q * (T2_ROWS * 6), r = rem / 6, hc = rem % 6;
@@ -209,10 +222,12 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  mbar_arrive(stA);
+  if (warp >= 2) {
+    stage_items(NIT_A + tid - 64, 192, NIT);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(stB);
+  }
   const bool stats = (a.part != nullptr);
 
   if (warp == 0) {
@@ -243,6 +258,8 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
 #pragma unroll 1
     for (int c = 0; c < T2_NCH; ++c) {
       const int buf = c & 1;
+      mbar_wait(c == 0 ? stA : stB, 0u);                      // chunk 0 reads input rows 0-11, chunks 1 / 2 rows 6-21
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (c >= 2) {                                            // the buffer's previous chunk must have been drained
         mbar_wait(&dEmpty[buf], 0u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
