@@ -18,6 +18,8 @@
 // Point-wise kernels use the warp-tile scheme of ptk_pw.cuh.  Sums over pixels live in registers
 // across a persistent CTA's tiles and are accumulated per CTA slot in global memory (read-add-write
 // by the owning CTA only => deterministic); `finalize` folds the slots in double precision.
+#include <stdlib.h>
+
 #include "ptk_int.h"
 #include "ptk_profile.h"
 #include "ptk_pw.cuh"
@@ -153,20 +155,34 @@ __device__ __forceinline__ void bwd_a_fill_const(const IntDev& d, int t, float* 
   }
 }
 
-// stand-alone (b1)-(b2) kernel: only used for the last time step (the others are fused into bwd_d).
+// stand-alone (b1)-(b2) kernel.  Round 1 ran it only for the last time step and fused the other steps into the tail of
+// int_bwd_d_kernel (dE' stays on chip); that fusion pushed int_bwd_d to 40-55 spilled words per thread at its 128-register
+// budget (as many local as global load instructions, ncu r2i) and measured 4 % SLOWER per training step than this extra launch.
 template <int ACT>
 __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int first) {
   __shared__ __align__(16) float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C];
   __shared__ __align__(16) float sPart[4 * 4 * C], sTot[4 * C];
   __shared__ int sIsLast;
+  // prologue on parameters, forward statistics and forward checkpoints only: overlaps the previous kernel's tail (PDL)
   bwd_a_fill_const(d, t, sKa, sGa, sW1, sB1, sM1, sR1);
   cp_async_commit();
   for (int i = threadIdx.x; i < 4 * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  if (blockIdx.x * 4 + warp < nWT) {
+    const int wt0 = blockIdx.x * 4 + warp, b0 = wt0 / tpi;
+    const size_t tb = (size_t)b0 * C * P + (wt0 - b0 * tpi) * WPX;
+    warp_tile_prefetch(d.E_at(t), tb, P);
+    warp_tile_prefetch(d.A_at(t), tb, P);
+    warp_tile_prefetch(d.I_at(t + 1), tb, P);
+    warp_tile_prefetch(d.Y1_at(t), tb, P);
+    warp_tile_prefetch(d.Gex_at(t), tb, P);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
   cp_async_wait<0>();
   __syncthreads();
   const BwdAConst k{sKa, sGa, sW1, sB1, sM1, sR1};
-  const Lane L;
-  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   float* sPw = sPart + warp * 4 * C;
   for (int wt = blockIdx.x * 4 + warp; wt < nWT; wt += gridDim.x * 4) {
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
@@ -481,7 +497,7 @@ __device__ __forceinline__ void bwd_d_load(const IntDev& d, const float* At, con
 // (b10)-(b12): complete dGe, dE partial (gE), A_t, E_t, dX, [dS], x_t.
 // writes gE <- dE (for step t-1), a (scratch for gate_wgrad), stem parameter sums, optional dx.
 // When t > 0 the kernel continues with (b1)-(b2) of step t-1 on the same patch (dE stays on chip).
-template <int CELL, int ACT, bool DX>   // DX: also form d(loss)/d(clip) (viz_model_att.py:189-196); training does not need it
+template <int CELL, int ACT, bool DX, bool FUSE = true>   // DX: also form d(loss)/d(clip) (viz_model_att.py:189-196); training does not need it
 __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int first) {
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;              // [out][in]
@@ -491,7 +507,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
   __shared__ __align__(16) float sPart[4 * 4 * C], sTot[4 * C];
   __shared__ __align__(16) float sKa[C], sGa[C], sW1[C], sB1[C], sM1[C], sR1[C], sPartA[4 * 4 * C], sTotA[4 * C];
   __shared__ int sIsLast;
-  const bool fuse = (t > 0);
+  const bool fuse = FUSE && (t > 0);
   const Lane L;
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   const float* Et = d.E_at(t);
@@ -570,10 +586,11 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
     __syncwarp();
     if (MMA) {
       Frag f;                          // one accumulator set at a time
-      if (fuse) {
+      if (t > 0) {
         frag_zero(f);
-        warp_mma_gemm(f, sA, sWau);    // dE += Wa_u^T a   (= dE' of step t-1), parked in the free tile
-        frag_to_tile(sB, f);
+        warp_mma_gemm(f, sA, sWau);    // dE += Wa_u^T a   (= dE' of step t-1)
+        if (fuse) frag_to_tile(sB, f);                                          // parked in the free tile for the fused tail
+        else frag_add_to_global(d.gE, (size_t)b * C * P + pix_base, P, f);      // or completed in place for int_bwd_a_kernel(t-1)
       }
       frag_zero(f);
       warp_mma_gemm(f, sA, sWaw);      // dX += Wa_w^T a
@@ -587,6 +604,7 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
       acc_from_global(acc, d.gE, base, P, L);
       warp_gemm(acc, sA, sWau, L);     // dE += Wa_u^T a   (= dE' of step t-1)
       if (fuse) acc_to_tile(sB, L, acc);
+      else if (t > 0) acc_to_global(d.gE, base, P, L, acc);
       acc_from_global(acc, d.dX, base, P, L);
       warp_gemm(acc, sA, sWaw, L);     // dX += Wa_w^T a
       __syncwarp();
@@ -1004,6 +1022,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   PTK_CUDA_OK(ptk_func_smem(int_bwd_c_kernel<CELL, ACT>, (int)SM_BWD_C));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false, false>, (int)SM_BWD_D));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, true>, (int)SM_GATE));
   PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, false>, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
@@ -1018,9 +1038,12 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   for (int t = d.T - 1; t >= 0; --t) {
     const int first = (t == d.T - 1);
     int rc;
-    if (first) {   // later steps: (b1)-(b2) run as the tail of the previous iteration's bwd_d kernel
+    // (b1)-(b2) as a launch of their own (default), or fused into the tail of the previous iteration's int_bwd_d_kernel
+    // (PTK_BWD_FUSE_A=1: the round-1 structure, kept for A/B runs)
+    static const bool unfuse = [] { const char* e = getenv("PTK_BWD_FUSE_A"); return !(e && e[0] == '1'); }();
+    if (first || unfuse) {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      int_bwd_a_kernel<ACT><<<grid_a, 128, 0, st>>>(d, t, first);
+      PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_kernel<ACT>, dim3(grid_a), dim3(128), 0, st, d, t, first));
       PTK_LAUNCH_OK("int_bwd_a_kernel");
     }
     if (!d.bn_fused) {
@@ -1066,8 +1089,10 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
-      else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
+      if (d.dx != nullptr && unfuse) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
+      else if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true, true>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
+      else if (unfuse) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, false, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
+      else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, false, true>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
     }
     PTK_LAUNCH_OK("int_bwd_d_kernel");
     if (!tc) {
