@@ -691,6 +691,194 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// (b10)-(b12) with the tile's operands STAGED in shared memory (InT cell, tensor-core modes, un-fused (b1)-(b2)).
+// int_bwd_d_kernel walks a tile channel by channel with a one-channel register prefetch: at B = 64 every warp owns exactly
+// one tile, so that kernel's duration is the length of ONE tile's dependent chain of global loads (8 round trips + the
+// accumulate passes).  Here a warp requests all five operand tiles of its tile at once (cp.async, 23 KB in flight per warp,
+// no registers held), computes from shared memory, adds the Wa_u^T product into the parked dE tile in shared memory
+// (instead of a parked global write + a fragment-layout global read-add-write) and fetches dX for the stem while the two
+// gate products run.  One 7-warp CTA per SM: 2 048 tiles / (148 x 7) = 1.98, i.e. two full rounds.
+constexpr int BDS_NW = 7, BDS_NT = 5;
+static constexpr size_t SM_BWD_DS = (size_t)(2 * C * C + BDS_NW * BDS_NT * TILE_F) * sizeof(float);
+
+__device__ __forceinline__ void frag_add_to_tile(float* tile, const Frag& f) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        tile[(n * 8 + 2 * t + (e & 1)) * TP + m * 16 + g + 8 * (e >> 1)] += f.c[m][n][e];
+}
+
+template <int ACT, bool DX>
+__global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev d, int t, int first) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWaw = dsm;              // [out][in], mma B-fragment order
+  float* sWau = sWaw + C * C;
+  float* tiles = sWau + C * C;
+  __shared__ __align__(16) float sWp[C * 3], sbp[C];
+  __shared__ __align__(16) float sPart[BDS_NW * 4 * C], sTot[4 * C];
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* Et = d.E_at(t);
+  const float* At = d.A_at(t);
+  float* a_out = d.a_at(t);
+  float* tA = tiles + (size_t)warp * BDS_NT * TILE_F;   // A_t -> a = dA A (1 - A) -> parked Wa_w^T a
+  float* tE = tA + TILE_F;                              // E_t -> dX of this step
+  float* tG = tE + TILE_F;                              // dGe (point-wise part)
+  float* tC = tG + TILE_F;                              // dY0 *7^T W_inh (b9)
+  float* tg = tC + TILE_F;                              // dE partial -> dE' of step t-1
+  int wt = blockIdx.x * BDS_NW + warp;
+  float xin[3][4];
+  // prologue on parameters, the (read-only) clip and forward checkpoints: overlaps the previous kernel's tail (PDL)
+  cta_fill_async(sWaw, d.gateF[0], C * C);
+  cta_fill_async(sWau, d.gateF[1], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  for (int i = threadIdx.x; i < BDS_NW * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+    warp_tile_load_async(tA, At, (size_t)d.a_bstride, b, pix_base, P);
+    warp_tile_load_async(tE, Et, (size_t)C * P, b, pix_base, P);
+  }
+  cp_async_commit();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async(tG, d.dGe, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(tC, d.cGe, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(tg, d.gE, (size_t)C * P, b, pix_base, P);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  float* sPw = sPart + warp * 4 * C;   // [0] d bp, [1..3] d Wp[:, i]
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * BDS_NW, firstTile = false) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    if (!firstTile) {
+      warp_tile_load_async(tA, At, (size_t)d.a_bstride, b, pix_base, P);
+      warp_tile_load_async(tE, Et, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tG, d.dGe, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tC, d.cGe, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tg, d.gE, (size_t)C * P, b, pix_base, P);
+      cp_async_commit();
+      frame_px(d.fv, b, t, pix, d.W, xin);
+      cp_async_wait<0>();
+      __syncwarp();
+    }
+#pragma unroll 2
+    for (int o = 0; o < 8; ++o) {
+      const size_t idx = base + (size_t)(L.oc0 + o) * P;
+      float A[4], E[4], gE[4], dg[4], cg[4], oa[4], ode[4];
+      tile_ld(tA, L, o, A);
+      tile_ld(tE, L, o, E);
+      tile_ld(tG, L, o, dg);
+      tile_ld(tC, L, o, cg);
+      tile_ld(tg, L, o, gE);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float dGe = dg[p] + cg[p];               // + dY0 *7^T W_inh (b9)
+        const float dA = dGe * E[p];
+        oa[p] = dA * A[p] * (1.0f - A[p]);
+        ode[p] = fmaf(dGe, A[p], gE[p]);
+      }
+      st4s(a_out + idx, oa, d.dy_tstride != 0);
+      tile_st(tA, L, o, oa);
+      tile_st(tg, L, o, ode);          // parked: completed by the transposed product below
+    }
+    __syncwarp();
+    warp_tile_load_async(tE, d.dX, (size_t)C * P, b, pix_base, P);    // E_t is dead: dX arrives while the gate products run
+    cp_async_commit();
+    {
+      Frag f;                          // one accumulator set at a time
+      if (t > 0) {
+        frag_zero(f);
+        warp_mma_gemm(f, tA, sWau);    // dE += Wa_u^T a   (= dE' of step t-1)
+        frag_add_to_tile(tg, f);
+      }
+      frag_zero(f);
+      warp_mma_gemm(f, tA, sWaw);      // dX += Wa_w^T a
+      __syncwarp();
+      frag_to_tile(tA, f);             // park the product; the stem loop adds the dX tile
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+    float dxs[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) dxs[i][p] = 0.f;
+#pragma unroll 2
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
+      float pre[4], dxa[4], dxb[4], part[4] = {0.f, 0.f, 0.f, 0.f};
+      if (t > 0) {                     // dE' of step t-1, read by int_bwd_a_kernel(t-1)
+        float ge[4];
+        tile_ld(tg, L, o, ge);
+        st4(d.gE + base + (size_t)c * P, ge);
+      }
+      stem_pre(sWp, sbp, c, xin, pre);
+      tile_ld(tA, L, o, dxa);
+      tile_ld(tE, L, o, dxb);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float dp = (dxa[p] + dxb[p]) * dactf<ACT>(pre[p]);
+        part[0] += dp;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          part[1 + i] = fmaf(dp, xin[i][p], part[1 + i]);
+          if (DX) dxs[i][p] = fmaf(sWp[c * 3 + i], dp, dxs[i][p]);
+        }
+      }
+      part_add<4>(sPw, c, L, part);
+    }
+    if (DX) {   // contiguous [B,3,T,H,W]
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          dxs[i][p] += __shfl_xor_sync(0xffffffffu, dxs[i][p], 8);
+          dxs[i][p] += __shfl_xor_sync(0xffffffffu, dxs[i][p], 16);
+        }
+      if (L.og == 0) {
+        const size_t plane = (size_t)d.T * P;
+        float* o = d.dx + (size_t)b * 3 * plane + (size_t)t * P + pix;
+        if (t == 0) {
+          float g[4];
+          ld4v(d.dgoal + (size_t)b * P + pix, g);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) dxs[2][p] += g[p];
+        }
+        st4(o, dxs[0]);
+        st4(o + plane, dxs[1]);
+        st4(o + 2 * plane, dxs[2]);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < BDS_NW; ++w) s += sPart[w * 4 * C + i];
+    sTot[i] = s;
+  }
+  __syncthreads();
+  float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    acc_store(acc + ACC_BP + c, sTot[c], first);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc_store(acc + ACC_WP + c * 3 + i, sTot[(1 + i) * C + c], first);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gate weight / bias gradients of one step: six 32x32 outer-product sums over all pixels
 //   dWe_w += ge (x) S, dWe_u += ge (x) Ge, dWi_w += gi (x) X, dWi_u += gi (x) S, dWa_w += a (x) X,
 //   dWa_u += a (x) E;  d(bias) += sum ge / gi / a.
@@ -1024,6 +1212,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true, false>, (int)SM_BWD_D));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<ACT, true>, (int)SM_BWD_DS));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<ACT, false>, (int)SM_BWD_DS));
   PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, true>, (int)SM_GATE));
   PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, false>, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
@@ -1089,6 +1279,14 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
+      static const bool staged_on = [] { const char* e = getenv("PTK_BWD_D_STAGED"); return !(e && e[0] == '0'); }();
+      constexpr bool can_stage = CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
+      if (can_stage && unfuse && staged_on) {   // operands staged in shared memory, one 7-warp CTA per SM
+        const int nWT = d.B * P / WPX, sg = (nWT + BDS_NW - 1) / BDS_NW;
+        const dim3 g2(sg < 148 ? sg : 148);
+        if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_staged_kernel<ACT, true>, g2, dim3(32 * BDS_NW), SM_BWD_DS, st, d, t, first));
+        else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_staged_kernel<ACT, false>, g2, dim3(32 * BDS_NW), SM_BWD_DS, st, d, t, first));
+      } else
       if (d.dx != nullptr && unfuse) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
       else if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true, true>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
       else if (unfuse) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, false, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
