@@ -484,6 +484,241 @@ __global__ void __launch_bounds__(128, 4) int_bwd_c_kernel(IntDev d, int t, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// (b5)-(b8) with the tile's operands STAGED in shared memory (InT cell, tensor-core modes): see int_bwd_d_staged_kernel.
+// All six operand tiles of a warp's tile are requested at once (cp.async); z and dS are parked in the tiles they replace
+// instead of in global memory, the four transposed gate products run on mma.sync one accumulator set at a time and are added
+// into those tiles in shared memory, and dX / dI / dGe leave once, in patch layout.  One 7-warp CTA per SM.
+__device__ __forceinline__ void frag_add_to_tile(float* tile, const Frag& f) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        tile[(n * 8 + 2 * t + (e & 1)) * TP + m * 16 + g + 8 * (e >> 1)] += f.c[m][n][e];
+}
+
+constexpr int BCS_NW = 7, BCS_NT = 6;
+static constexpr size_t SM_BWD_CS = (size_t)(4 * C * C + BCS_NW * BCS_NT * TILE_F) * sizeof(float);
+
+// bn_sums_fold for CTAs of more than 128 threads (only the first 128 take part in the load phase)
+__device__ __forceinline__ void bn_sums_fold_wide(const IntDev& d, int bn, const float* sPart /*[2][32]*/, int first,
+                                                  int* sIsLast, float* sScratch /* >= 2 KB, 8-byte aligned, free */) {
+  const int k = threadIdx.x, nCta = gridDim.x;
+  if (k < 2 * C) d.bn_sums[(size_t)blockIdx.x * 2 * C + k] = sPart[k];
+  __threadfence();
+  __syncthreads();
+  if (k == 0) *sIsLast = (atomicAdd(d.counter, 1u) == (unsigned)(nCta - 1));
+  __syncthreads();
+  if (*sIsLast) {
+    __threadfence();
+    double* sD = reinterpret_cast<double*>(sScratch);   // [4 warps][64]
+    if (k < 128) {
+      const int q = k & 15, g = k >> 4;
+      double s[4] = {0, 0, 0, 0};
+      const float4* src = reinterpret_cast<const float4*>(d.bn_sums) + q;
+      int i = g;
+      for (; i + 8 * 15 < nCta; i += 8 * 16) {
+        float4 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __ldcg(src + (size_t)(i + 8 * j) * (2 * C / 4));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { s[0] += (double)v[j].x; s[1] += (double)v[j].y; s[2] += (double)v[j].z; s[3] += (double)v[j].w; }
+      }
+      for (; i < nCta; i += 8) {
+        const float4 v = __ldcg(src + (size_t)i * (2 * C / 4));
+        s[0] += (double)v.x; s[1] += (double)v.y; s[2] += (double)v.z; s[3] += (double)v.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);   // rows g and g^1
+      if ((k & 31) < 16) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sD[(k >> 5) * 2 * C + 4 * q + e] = s[e];
+      }
+    }
+    __syncthreads();
+    if (k < 2 * C) {
+      const double tt = (sD[k] + sD[2 * C + k]) + (sD[4 * C + k] + sD[6 * C + k]);
+      const double N = (double)d.B * d.H * d.W;
+      d.bn_tot[k] = (float)(tt / N);
+      double* a = d.bn_acc + (size_t)bn * 2 * C + k;
+      *a = first ? tt : (*a + tt);
+    }
+    if (k == 0) *d.counter = 0u;
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev d, int t, int first) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWiw = dsm;              // [out][in] = [k][n] of the transposed products, mma B-fragment order
+  float* sWiu = sWiw + C * C;
+  float* sWew = sWiu + C * C;
+  float* sWeu = sWew + C * C;
+  float* tiles = sWeu + C * C;
+  __shared__ __align__(16) float sWp[C * 3], sbp[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
+  __shared__ __align__(16) float sPart[BCS_NW * 4 * C], sTot[4 * C];
+  __shared__ int sIsLast;
+  const Lane L;
+  const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* It = d.I_at(t);
+  const float* Y0 = d.Y0_at(t);
+  const float* Git = d.Gi_at(t);
+  float* dU_out = d.dV_at(t, 0);
+  float* gi_out = d.gi_at(t);
+  float* X_out = d.X_at(t);
+  float* tgI = tiles + (size_t)warp * BCS_NT * TILE_F;   // dI' partial -> dS parked -> dI (+ dS) of step t
+  float* tcg = tgI + TILE_F;                             // dY1 *7^T W_exc (b4) -> z parked -> dX
+  float* tI = tcg + TILE_F;                              // I_t -> dGe
+  float* tY = tI + TILE_F;                               // Y0_t
+  float* tG = tY + TILE_F;                               // G_i -> gi
+  float* tge = tG + TILE_F;                              // ge
+  int wt = blockIdx.x * BCS_NW + warp;
+  float xin[3][4];
+  // prologue on parameters, forward statistics, the (read-only) clip and forward checkpoints: overlaps the previous kernel (PDL)
+  cta_fill_async(sWiw, d.gateF[2], C * C);
+  cta_fill_async(sWiu, d.gateF[3], C * C);
+  cta_fill_async(sWew, d.gateF[4], C * C);
+  cta_fill_async(sWeu, d.gateF[5], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  cta_fill_async(sAl, d.alpha, C);
+  cta_fill_async(sMu, d.mu, C);
+  cta_fill_async(sW0, d.bn_w[0], C);
+  cta_fill_async(sB0, d.bn_b[0], C);
+  for (int i = threadIdx.x; i < BCS_NW * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  if (threadIdx.x < C) {
+    const float* st = d.stat(t, 0);
+    sM0[threadIdx.x] = st[threadIdx.x];
+    sR0[threadIdx.x] = st[C + threadIdx.x];
+  }
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+    warp_tile_load_async(tI, It, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(tY, Y0, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(tG, Git, (size_t)C * P, b, pix_base, P);
+  }
+  cp_async_commit();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async(tgI, d.gI, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(tcg, d.cgI, (size_t)C * P, b, pix_base, P);
+    warp_tile_load_async(tge, d.geb_at(t), (size_t)C * P, b, pix_base, P);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  float* sPw = sPart + warp * 4 * C;
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * BCS_NW, firstTile = false) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    if (!firstTile) {
+      warp_tile_load_async(tI, It, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tY, Y0, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tG, Git, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tgI, d.gI, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tcg, d.cgI, (size_t)C * P, b, pix_base, P);
+      warp_tile_load_async(tge, d.geb_at(t), (size_t)C * P, b, pix_base, P);
+      cp_async_commit();
+      frame_px(d.fv, b, t, pix, d.W, xin);
+      cp_async_wait<0>();
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int o = 0; o < 8; ++o) {
+      const int c = L.oc0 + o;
+      const size_t idx = base + (size_t)c * P;
+      float gi_[4], cg[4], I[4], y0[4], G[4], X[4], oDu[4], oGi[4], oZ[4], oDs[4];
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+      tile_ld(tgI, L, o, gi_);
+      tile_ld(tcg, L, o, cg);
+      tile_ld(tI, L, o, I);
+      tile_ld(tY, L, o, y0);
+      tile_ld(tG, L, o, G);
+      stem_pre(sWp, sbp, c, xin, X);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float gIn = gi_[p] + cg[p];
+        X[p] = actf<ACT>(X[p]);
+        const float xh = (y0[p] - sM0[c]) * sR0[c];
+        const float U = fmaf(sW0[c], xh, sB0[c]);
+        const float aSm = fmaf(sAl[c], I[p], sMu[c]);          // InT: S = I
+        const float Pp = U * aSm;
+        const float Q = actf<ACT>(Pp);
+        const float d1 = X[p] - Q;
+        const float Ihat = actf<ACT>(d1);
+        const float dGi = gIn * (Ihat - I[p]);
+        const float oDI = gIn * (1.0f - G[p]);
+        const float zz = gIn * G[p] * dactf<ACT>(d1);
+        oGi[p] = dGi * G[p] * (1.0f - G[p]);
+        const float dP = -zz * dactf<ACT>(Pp);
+        const float dPU = dP * U;
+        const float dU = dP * aSm;
+        oDu[p] = dU;
+        oZ[p] = zz;
+        oDs[p] = dPU * sAl[c] + oDI;                          // InT: dI + dS lands in gI
+        part[0] = fmaf(dPU, I[p], part[0]);   // -> d alpha
+        part[1] += dPU;                        // -> d mu
+        part[2] += dU;                         // -> sum dU
+        part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
+      }
+      st4(dU_out + idx, oDu);
+      st4s(gi_out + idx, oGi, d.dy_tstride != 0);
+      st4s(X_out + idx, X, d.dy_tstride != 0);
+      tile_st(tG, L, o, oGi);
+      tile_st(tcg, L, o, oZ);         // parked: completed by the transposed products below
+      tile_st(tgI, L, o, oDs);
+      part_add<4>(sPw, c, L, part);
+    }
+    __syncwarp();
+    {
+      Frag f;                          // one accumulator set at a time
+      frag_zero(f);
+      warp_mma_gemm(f, tG, sWiw);      // dX = z + Wi_w^T gi
+      frag_add_to_tile(tcg, f);
+      frag_zero(f);
+      warp_mma_gemm(f, tG, sWiu);      // dI += dS + Wi_u^T gi + We_w^T ge
+      warp_mma_gemm(f, tge, sWew);
+      frag_add_to_tile(tgI, f);
+      frag_zero(f);
+      warp_mma_gemm(f, tge, sWeu);     // dGe = We_u^T ge
+      frag_to_tile(tI, f);             // I_t is dead
+    }
+    __syncwarp();
+#pragma unroll 2
+    for (int o = 0; o < 8; ++o) {
+      const size_t idx = base + (size_t)(L.oc0 + o) * P;
+      float v[4];
+      tile_ld(tcg, L, o, v);
+      st4(d.dX + idx, v);
+      tile_ld(tgI, L, o, v);
+      st4(d.gI + idx, v);
+      tile_ld(tI, L, o, v);
+      st4(d.dGe + idx, v);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < BCS_NW; ++w) sacc += sPart[w * 4 * C + i];
+    sTot[i] = sacc;
+  }
+  __syncthreads();
+  float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
+  if (threadIdx.x < C) {
+    acc_store(acc + ACC_ALPHA + threadIdx.x, sTot[threadIdx.x], first);
+    acc_store(acc + ACC_MU + threadIdx.x, sTot[C + threadIdx.x], first);
+  }
+  bn_sums_fold_wide(d, 0, sTot + 2 * C, first, &sIsLast, sPart);
+}
+
+// ------------------------------------------------------------------------------------------------
 struct BwdDIn { float4 a, dge, cg, e, ge, ds; };   // one channel of the patch, prefetched one channel ahead
 template <int CELL>
 __device__ __forceinline__ void bwd_d_load(const IntDev& d, const float* At, const float* Et, size_t idx, BwdDIn& r) {
@@ -700,17 +935,6 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 // gate products run.  One 7-warp CTA per SM: 2 048 tiles / (148 x 7) = 1.98, i.e. two full rounds.
 constexpr int BDS_NW = 7, BDS_NT = 5;
 static constexpr size_t SM_BWD_DS = (size_t)(2 * C * C + BDS_NW * BDS_NT * TILE_F) * sizeof(float);
-
-__device__ __forceinline__ void frag_add_to_tile(float* tile, const Frag& f) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int m = 0; m < 2; ++m)
-#pragma unroll
-    for (int n = 0; n < 4; ++n)
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        tile[(n * 8 + 2 * t + (e & 1)) * TP + m * 16 + g + 8 * (e >> 1)] += f.c[m][n][e];
-}
 
 template <int ACT, bool DX>
 __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev d, int t, int first) {
@@ -1208,6 +1432,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const long long gate_tiles = (long long)(d.B * P / GPX) * (tc ? d.T : 1);
   const int gate_grid = gate_tiles < GATE_CTAS ? (int)gate_tiles : GATE_CTAS;
   PTK_CUDA_OK(ptk_func_smem(int_bwd_c_kernel<CELL, ACT>, (int)SM_BWD_C));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_c_staged_kernel<ACT>, (int)SM_BWD_CS));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false, false>, (int)SM_BWD_D));
@@ -1255,7 +1480,13 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      PTK_CUDA_OK(launch_pdl(true, int_bwd_c_kernel<CELL, ACT>, dim3(grid_c), dim3(128), SM_BWD_C, st, d, t, first));
+      static const bool c_staged_on = [] { const char* e = getenv("PTK_BWD_C_STAGED"); return !(e && e[0] == '0'); }();
+      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on) {   // operands staged in shared memory, one 7-warp CTA per SM
+        const int nWT = d.B * P / WPX, sg = (nWT + BCS_NW - 1) / BCS_NW;
+        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_staged_kernel<ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * BCS_NW), SM_BWD_CS, st, d, t, first));
+      } else {
+        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_kernel<CELL, ACT>, dim3(grid_c), dim3(128), SM_BWD_C, st, d, t, first));
+      }
     }
     PTK_LAUNCH_OK("int_bwd_c_kernel");
     if (CELL != CELL_NOINH) {
