@@ -87,7 +87,8 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
   unsigned* counter = cv.take<unsigned>(4);
   float* acc = cv.take<float>((size_t)PW_EW_CTAS * ACC_N);
   float* gacc = cv.take<float>((size_t)GATE_CTAS * GACC_N);
-  float* bn_sums = cv.take<float>((size_t)PW_EW_CTAS * 2 * C);
+  const size_t bn_sums_n = (size_t)PW_EW_CTAS * 2 * C > (size_t)dm->B * C * 4 ? (size_t)PW_EW_CTAS * 2 * C : (size_t)dm->B * C * 4;
+  float* bn_sums = cv.take<float>(bn_sums_n);   // per-CTA partials of the warp-tile kernels, or [B*C][4] row sums of int_bwd_a_stream_kernel
   float* bn_tot = cv.take<float>(2 * C);
   double* bn_acc = cv.take<double>(4 * C);
   float* head = cv.take<float>((size_t)dm->B * HEAD_N);

@@ -211,6 +211,114 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
   bn_sums_fold(d, 1, sTot + 2 * C, first, &sIsLast, sPart);
 }
 
+// (b1)-(b2) as a plain streaming kernel: one CTA per (sample, channel) row, one float4 per thread and iteration, seven
+// independent 16-byte loads in flight per thread (the warp-tile version above walks 8 channels per thread with a one-channel
+// prefetch: 29 us per launch for 92 MB; this one is bound by the memory system).  Per-row partial sums go to `bn_sums`
+// ([B*C][4]); the last CTA folds them per channel in double, in a fixed order (deterministic): BatchNorm-backward means,
+// d(bn weight / bias), and the step's d(kappa), d(gamma) (accumulated in accumulator slot 0).
+template <int ACT>
+__global__ void __launch_bounds__(256, 4) int_bwd_a_stream_kernel(IntDev d, int t, int first) {
+  __shared__ float sRed[8][4];
+  __shared__ int sIsLast;
+  const int tid = threadIdx.x, P = d.H * d.W, n4 = P / 4;
+  const int b = blockIdx.x / C, c = blockIdx.x - b * C;
+  const size_t row = ((size_t)b * C + c) * P;
+  const float4* E4 = reinterpret_cast<const float4*>(d.E_at(t) + row);
+  const float4* A4 = reinterpret_cast<const float4*>(d.A_at(t) + (size_t)b * d.a_bstride + (size_t)c * P);
+  const float4* I4 = reinterpret_cast<const float4*>(d.I_at(t + 1) + row);
+  const float4* Y4 = reinterpret_cast<const float4*>(d.Y1_at(t) + row);
+  const float4* G4 = reinterpret_cast<const float4*>(d.Gex_at(t) + row);
+  // prologue on parameters, forward statistics and forward checkpoints only (PDL)
+  const float Ka = __ldg(d.kappa + c), Ga = __ldg(d.gamma + c), W1 = __ldg(d.bn_w[1] + c), B1 = __ldg(d.bn_b[1] + c);
+  const float M1 = d.stat(t, 1)[c], R1 = d.stat(t, 1)[C + c];
+  if ((tid & 7) == 0 && tid < n4) {
+    prefetch_l2(E4 + tid); prefetch_l2(A4 + tid); prefetch_l2(I4 + tid); prefetch_l2(Y4 + tid); prefetch_l2(G4 + tid);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  float4* gE4 = reinterpret_cast<float4*>(d.gE + row);
+  float4* gI4 = reinterpret_cast<float4*>(d.gI + row);
+  float4* geb4 = reinterpret_cast<float4*>(d.geb_at(t) + row);
+  float4* dV4 = reinterpret_cast<float4*>(d.dV_at(t, 1) + row);
+  float4* Ge4 = reinterpret_cast<float4*>(d.GeB_at(t) + row);
+  const bool stream = d.dy_tstride != 0;
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = tid; i < n4; i += 256) {
+    const float4 e4 = E4[i], a4 = A4[i], i4 = I4[i], y4 = Y4[i], g4 = G4[i], ge4 = gE4[i];
+    const float4 gi4 = first ? make_float4(0.f, 0.f, 0.f, 0.f) : gI4[i];
+    const float e[4] = {e4.x, e4.y, e4.z, e4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w}, i2[4] = {i4.x, i4.y, i4.z, i4.w};
+    const float y1[4] = {y4.x, y4.y, y4.z, y4.w}, gx[4] = {g4.x, g4.y, g4.z, g4.w}, gEn[4] = {ge4.x, ge4.y, ge4.z, ge4.w};
+    const float gi_in[4] = {gi4.x, gi4.y, gi4.z, gi4.w};
+    float oGe[4], oGE[4], oGI[4], oGeb[4], oDv[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float xh = (y1[p] - M1) * R1;
+      const float V = fmaf(W1, xh, B1);
+      const float kIg = fmaf(Ka, i2[p], Ga);
+      const float R = V * kIg;
+      const float Ehat = actf<ACT>(R);
+      const float dGx = gEn[p] * (Ehat - e[p]);
+      oGE[p] = gEn[p] * (1.0f - gx[p]);
+      const float dR = gEn[p] * gx[p] * dactf<ACT>(R);
+      const float dV = dR * kIg;
+      const float dRV = dR * V;
+      oGI[p] = fmaf(dRV, Ka, gi_in[p]);
+      oGeb[p] = dGx * gx[p] * (1.0f - gx[p]);
+      oDv[p] = dV;
+      oGe[p] = a[p] * e[p];
+      part[0] = fmaf(dRV, i2[p], part[0]);   // -> d kappa
+      part[1] += dRV;                         // -> d gamma
+      part[2] += dV;                          // -> sum dV
+      part[3] = fmaf(dV, xh, part[3]);        // -> sum dV * xhat
+    }
+    gE4[i] = make_float4(oGE[0], oGE[1], oGE[2], oGE[3]);
+    gI4[i] = make_float4(oGI[0], oGI[1], oGI[2], oGI[3]);
+    geb4[i] = make_float4(oGeb[0], oGeb[1], oGeb[2], oGeb[3]);
+    dV4[i] = make_float4(oDv[0], oDv[1], oDv[2], oDv[3]);
+    if (stream) __stcs(Ge4 + i, make_float4(oGe[0], oGe[1], oGe[2], oGe[3]));
+    else Ge4[i] = make_float4(oGe[0], oGe[1], oGe[2], oGe[3]);
+  }
+  // row sums in a fixed order: lanes (xor tree), then the 8 warps
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) part[q] += __shfl_xor_sync(0xffffffffu, part[q], m);
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sRed[tid >> 5][q] = part[q];
+  }
+  __syncthreads();
+  if (tid < 4) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sacc += sRed[w][tid];
+    d.bn_sums[(size_t)blockIdx.x * 4 + tid] = sacc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sIsLast = (atomicAdd(d.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (sIsLast) {
+    __threadfence();
+    if (tid < 4 * C) {
+      const int q = tid >> 5, cc = tid & 31;
+      double sacc = 0;
+      for (int bb = 0; bb < d.B; ++bb) sacc += (double)__ldcg(d.bn_sums + ((size_t)bb * C + cc) * 4 + q);
+      const double N = (double)d.B * P;
+      if (q == 0) acc_store(d.acc + ACC_KAPPA + cc, (float)sacc, first);
+      else if (q == 1) acc_store(d.acc + ACC_GAMMA + cc, (float)sacc, first);
+      else {
+        const int k2 = (q - 2) * C + cc;          // [0, C): sum dV -> d(bn bias); [C, 2C): sum dV*xhat -> d(bn weight)
+        d.bn_tot[k2] = (float)(sacc / N);
+        double* ap = d.bn_acc + (size_t)1 * 2 * C + k2;
+        *ap = first ? sacc : (*ap + sacc);
+      }
+    }
+    if (tid == 0) *d.counter = 0u;
+  }
+}
+
 // (b3)/(b9): dAct <- w*rstd*(dAct - mean(dAct) - xhat*mean(dAct*xhat)), xhat from the saved conv output.
 __global__ void __launch_bounds__(256) bn_apply_kernel(IntDev d, const float* __restrict__ Y, int t, int bn) {
   {   // the saved conv output is a forward checkpoint: pull this thread's lines HBM -> L2 while the previous kernel drains
@@ -1458,7 +1566,11 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     static const bool unfuse = [] { const char* e = getenv("PTK_BWD_FUSE_A"); return !(e && e[0] == '1'); }();
     if (first || unfuse) {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
-      PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_kernel<ACT>, dim3(grid_a), dim3(128), 0, st, d, t, first));
+      static const bool a_stream = [] { const char* e = getenv("PTK_BWD_A_STREAM"); return !(e && e[0] == '0'); }();
+      // the streaming kernel keeps the step's d(kappa), d(gamma) in accumulator slot 0, the warp-tile kernel one partial per
+      // CTA slot: one or the other for ALL steps of a call (a_stream && unfuse), never mixed
+      if (a_stream && unfuse) PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_stream_kernel<ACT>, dim3(d.B * C), dim3(256), 0, st, d, t, first));
+      else PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_kernel<ACT>, dim3(grid_a), dim3(128), 0, st, d, t, first));
       PTK_LAUNCH_OK("int_bwd_a_kernel");
     }
     if (!d.bn_fused) {
