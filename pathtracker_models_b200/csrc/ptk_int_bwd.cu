@@ -216,33 +216,43 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
 // prefetch: 29 us per launch for 92 MB; this one is bound by the memory system).  Per-row partial sums go to `bn_sums`
 // ([B*C][4]); the last CTA folds them per channel in double, in a fixed order (deterministic): BatchNorm-backward means,
 // d(bn weight / bias), and the step's d(kappa), d(gamma) (accumulated in accumulator slot 0).
+constexpr int BAS_R = 4;   // sample rows per CTA: 512 CTAs at B = 64, all resident at once (4 per SM)
 template <int ACT>
 __global__ void __launch_bounds__(256, 4) int_bwd_a_stream_kernel(IntDev d, int t, int first) {
   __shared__ float sRed[8][4];
   __shared__ int sIsLast;
   const int tid = threadIdx.x, P = d.H * d.W, n4 = P / 4;
-  const int b = blockIdx.x / C, c = blockIdx.x - b * C;
+  const int bg = blockIdx.x / C, c = blockIdx.x - bg * C;      // CTA = channel c of samples bg*BAS_R .. +BAS_R-1
+  // prologue on parameters, forward statistics and forward checkpoints only (PDL)
+  const float Ka = __ldg(d.kappa + c), Ga = __ldg(d.gamma + c), W1 = __ldg(d.bn_w[1] + c), B1 = __ldg(d.bn_b[1] + c);
+  const float M1 = d.stat(t, 1)[c], R1 = d.stat(t, 1)[C + c];
+  for (int r = 0; r < BAS_R; ++r) {
+    const int b = bg * BAS_R + r;
+    if (b < d.B && (tid & 7) == 0 && tid < n4) {
+      const size_t row = ((size_t)b * C + c) * P + 4 * tid;
+      prefetch_l2(d.E_at(t) + row); prefetch_l2(d.A_at(t) + (size_t)b * d.a_bstride + (size_t)c * P + 4 * tid);
+      prefetch_l2(d.I_at(t + 1) + row); prefetch_l2(d.Y1_at(t) + row); prefetch_l2(d.Gex_at(t) + row);
+    }
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+  const bool stream = d.dy_tstride != 0;
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int r = 0; r < BAS_R; ++r) {
+  const int b = bg * BAS_R + r;
+  if (b >= d.B) break;
   const size_t row = ((size_t)b * C + c) * P;
   const float4* E4 = reinterpret_cast<const float4*>(d.E_at(t) + row);
   const float4* A4 = reinterpret_cast<const float4*>(d.A_at(t) + (size_t)b * d.a_bstride + (size_t)c * P);
   const float4* I4 = reinterpret_cast<const float4*>(d.I_at(t + 1) + row);
   const float4* Y4 = reinterpret_cast<const float4*>(d.Y1_at(t) + row);
   const float4* G4 = reinterpret_cast<const float4*>(d.Gex_at(t) + row);
-  // prologue on parameters, forward statistics and forward checkpoints only (PDL)
-  const float Ka = __ldg(d.kappa + c), Ga = __ldg(d.gamma + c), W1 = __ldg(d.bn_w[1] + c), B1 = __ldg(d.bn_b[1] + c);
-  const float M1 = d.stat(t, 1)[c], R1 = d.stat(t, 1)[C + c];
-  if ((tid & 7) == 0 && tid < n4) {
-    prefetch_l2(E4 + tid); prefetch_l2(A4 + tid); prefetch_l2(I4 + tid); prefetch_l2(Y4 + tid); prefetch_l2(G4 + tid);
-  }
-  pdl_wait();
-  pdl_launch_dependents();
   float4* gE4 = reinterpret_cast<float4*>(d.gE + row);
   float4* gI4 = reinterpret_cast<float4*>(d.gI + row);
   float4* geb4 = reinterpret_cast<float4*>(d.geb_at(t) + row);
   float4* dV4 = reinterpret_cast<float4*>(d.dV_at(t, 1) + row);
   float4* Ge4 = reinterpret_cast<float4*>(d.GeB_at(t) + row);
-  const bool stream = d.dy_tstride != 0;
-  float part[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = tid; i < n4; i += 256) {
     const float4 e4 = E4[i], a4 = A4[i], i4 = I4[i], y4 = Y4[i], g4 = G4[i], ge4 = gE4[i];
     const float4 gi4 = first ? make_float4(0.f, 0.f, 0.f, 0.f) : gI4[i];
@@ -278,7 +288,8 @@ __global__ void __launch_bounds__(256, 4) int_bwd_a_stream_kernel(IntDev d, int 
     if (stream) __stcs(Ge4 + i, make_float4(oGe[0], oGe[1], oGe[2], oGe[3]));
     else Ge4[i] = make_float4(oGe[0], oGe[1], oGe[2], oGe[3]);
   }
-  // row sums in a fixed order: lanes (xor tree), then the 8 warps
+  }
+  // sums of the CTA's rows in a fixed order: lanes (xor tree), then the 8 warps
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -304,7 +315,8 @@ __global__ void __launch_bounds__(256, 4) int_bwd_a_stream_kernel(IntDev d, int 
     if (tid < 4 * C) {
       const int q = tid >> 5, cc = tid & 31;
       double sacc = 0;
-      for (int bb = 0; bb < d.B; ++bb) sacc += (double)__ldcg(d.bn_sums + ((size_t)bb * C + cc) * 4 + q);
+      const int ng = (int)gridDim.x / C;
+      for (int bb = 0; bb < ng; ++bb) sacc += (double)__ldcg(d.bn_sums + ((size_t)bb * C + cc) * 4 + q);
       const double N = (double)d.B * P;
       if (q == 0) acc_store(d.acc + ACC_KAPPA + cc, (float)sacc, first);
       else if (q == 1) acc_store(d.acc + ACC_GAMMA + cc, (float)sacc, first);
@@ -1569,7 +1581,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool a_stream = [] { const char* e = getenv("PTK_BWD_A_STREAM"); return !(e && e[0] == '0'); }();
       // the streaming kernel keeps the step's d(kappa), d(gamma) in accumulator slot 0, the warp-tile kernel one partial per
       // CTA slot: one or the other for ALL steps of a call (a_stream && unfuse), never mixed
-      if (a_stream && unfuse) PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_stream_kernel<ACT>, dim3(d.B * C), dim3(256), 0, st, d, t, first));
+      if (a_stream && unfuse) PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_stream_kernel<ACT>, dim3(((d.B + BAS_R - 1) / BAS_R) * C), dim3(256), 0, st, d, t, first));
       else PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_kernel<ACT>, dim3(grid_a), dim3(128), 0, st, d, t, first));
       PTK_LAUNCH_OK("int_bwd_a_kernel");
     }
