@@ -23,6 +23,7 @@
 #include "ptk_int.h"
 #include "ptk_profile.h"
 #include "ptk_pw.cuh"
+#include "ptk_tc.cuh"
 
 #ifndef PTK_BWD_MMA
 #define PTK_BWD_MMA 0
@@ -1241,18 +1242,29 @@ constexpr int GNST = 3;   // cp.async stages: the all-steps launch streams its 7
 template <int CELL, bool MMA>
 __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, int nT, int first) {
   extern __shared__ __align__(16) float dsm[];
+  __shared__ __align__(8) uint64_t sFull[GNST];      // one mbarrier per stage: 7 x 32 bulk copies of 256 B each
+  const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, perT = d.B * tpi, nTiles = nT * perT;
+  if (tid == 0) {
+    for (int i = 0; i < GNST; ++i) mbar_init(&sFull[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   pdl_wait();
   pdl_launch_dependents();
-  const int tid = threadIdx.x, P = d.H * d.W, tpi = P / GPX, perT = d.B * tpi, nTiles = nT * perT;
+  // a tile = 64 pixels x 32 channels of the 7 operand tensors; row (tensor k, channel c) is 256 contiguous bytes in global
+  // memory: warp k < 7 issues tensor k's 32 rows as cp.async.bulk copies (lane = channel).  (The first version issued 3 808
+  // 16-byte cp.async per tile with a dynamically indexed pointer table in local memory: the kernel was bound by that
+  // address arithmetic, not by HBM.)
   auto issue = [&](int tile, int buf) {
     const int t = t0 + tile / perT, tile_t = tile % perT;
-    const float* src[7] = {d.geb_at(t), d.gi_at(t), d.a_at(t),
-                           (CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)), d.GeB_at(t), d.X_at(t), d.E_at(t)};
     const int b = tile_t / tpi, pix_base = (tile_t - b * tpi) * GPX;
-    float* dstb = dsm + (size_t)buf * 7 * GT_F;
-    for (int q = tid; q < 7 * C * (GPX / 4); q += 384) {
-      const int k = q / (C * (GPX / 4)), r = q - k * (C * (GPX / 4)), c = r / (GPX / 4), part = r % (GPX / 4);
-      cp_async16(dstb + k * GT_F + c * GSP + part * 4, src[k] + ((size_t)b * C + c) * P + pix_base + part * 4);
+    const int k = tid >> 5, c = tid & 31;
+    if (tid == 0) mbar_expect_tx(&sFull[buf], 7 * C * GPX * 4);
+    if (k < 7) {
+      const float* sp = k == 0 ? d.geb_at(t) : k == 1 ? d.gi_at(t) : k == 2 ? d.a_at(t)
+                      : k == 3 ? ((CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)))
+                      : k == 4 ? d.GeB_at(t) : k == 5 ? d.X_at(t) : d.E_at(t);
+      bulk_g2s(dsm + (size_t)buf * 7 * GT_F + k * GT_F + c * GSP, sp + ((size_t)b * C + c) * P + pix_base, GPX * 4, &sFull[buf]);
     }
   };
   const int m = tid >> 6, r = tid & 63, ocq = r >> 3, icq = r & 7;   // MMA: m = warp / 2 as well
@@ -1267,13 +1279,11 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
   float bsum = 0.f, btot = 0.f;
-  int buf = 0, t_cur = (int)blockIdx.x / perT;
+  int buf = 0, t_cur = (int)blockIdx.x / perT, it = 0;
 #pragma unroll
-  for (int s = 0; s < GNST - 1; ++s) {
+  for (int s = 0; s < GNST - 1; ++s)
     if ((int)(blockIdx.x + s * gridDim.x) < nTiles) issue(blockIdx.x + s * gridDim.x, s);
-    cp_async_commit();
-  }
-  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
     if (tile / perT != t_cur) {       // a new time step starts: retire the finished one
       t_cur = tile / perT;
 #pragma unroll
@@ -1284,10 +1294,8 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
       bsum = 0.f;
     }
     const int nxt = tile + (GNST - 1) * gridDim.x;
-    if (nxt < nTiles) issue(nxt, (buf + GNST - 1) % GNST);
-    cp_async_commit();
-    cp_async_wait<GNST - 1>();
-    __syncthreads();
+    if (nxt < nTiles) issue(nxt, (buf + GNST - 1) % GNST);      // that stage was released by the barrier ending the previous iteration
+    mbar_wait(&sFull[buf], (uint32_t)((it / GNST) & 1));
     const float* base = dsm + (size_t)buf * 7 * GT_F;
     if (MMA) {
       const float* gA = base + gsel * GT_F + (half * 16 + fg) * GSP + ft;
@@ -1338,7 +1346,6 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
     __syncthreads();
     buf = (buf + 1) % GNST;
   }
-  cp_async_wait<0>();
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
