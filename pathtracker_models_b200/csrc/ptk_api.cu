@@ -86,7 +86,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
   float* bn_part = cv.take<float>((size_t)conv_num_ctas(dm->B, dm->H, dm->W) * C * 2);
   unsigned* counter = cv.take<unsigned>(4);
   float* acc = cv.take<float>((size_t)PW_EW_CTAS * ACC_N);
-  float* gacc = cv.take<float>((size_t)GATE_CTAS * GACC_N);
+  float* gacc = cv.take<float>((size_t)2 * GATE_CTAS * GACC_N);   // tensor-core modes: two slots per CTA (pixel halves)
   const size_t bn_sums_n = (size_t)PW_EW_CTAS * 2 * C > (size_t)dm->B * C * 4 ? (size_t)PW_EW_CTAS * 2 * C : (size_t)dm->B * C * 4;
   float* bn_sums = cv.take<float>(bn_sums_n);   // per-CTA partials of the warp-tile kernels, or [B*C][4] row sums of int_bwd_a_stream_kernel
   float* bn_tot = cv.take<float>(2 * C);

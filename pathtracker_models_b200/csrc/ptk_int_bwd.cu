@@ -1273,9 +1273,14 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
   const int vsel = (m == 0 || m == 3) ? 3 : (m == 1 ? 4 : (m == 5 ? 6 : 5));   // S, Ge, X, S, X, E
   // two-level sums: `acc` / `bsum` hold the current time step, `tot` / `btot` all finished ones (one long fp32 chain
   // over 64 steps x 7 tiles lost ~1e-4 on the hGRU gate gradients at T = 64; per-step partial sums do not)
-  float acc[4][4], tot[4][4];
+  // MMA mapping: warp = (matrix m, pixel half ph); it owns the whole 32 x 32 block of dW_m for 32 of the tile's 64 pixels
+  // (acc[8][4]: m-tile mt = i >> 2, n-tile nt = i & 3), so a tile's operands are split once per (matrix, pixel) instead of
+  // once per (matrix, row half, pixel): 64 instead of 96 splits per lane and tile.  The two pixel halves keep separate slots.
+  // FFMA mapping (strict fp32): acc[4][4] as before (rows ocq + 8 i, columns icq + 8 j).
+  constexpr int NACC = MMA ? 8 : 4;
+  float acc[NACC][4], tot[NACC][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NACC; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
   float bsum = 0.f, btot = 0.f;
@@ -1287,7 +1292,7 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
     if (tile / perT != t_cur) {       // a new time step starts: retire the finished one
       t_cur = tile / perT;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NACC; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
       btot += bsum;
@@ -1298,24 +1303,30 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
     mbar_wait(&sFull[buf], (uint32_t)((it / GNST) & 1));
     const float* base = dsm + (size_t)buf * 7 * GT_F;
     if (MMA) {
-      const float* gA = base + gsel * GT_F + (half * 16 + fg) * GSP + ft;
-      const float* vB = base + vsel * GT_F + fg * GSP + ft;
-      // acc[nt][0..3]: rows fg / fg+8 of the half, columns 8 nt + 2 ft (+1)
+      const float* gA = base + gsel * GT_F + fg * GSP + ft + half * (GPX / 2);      // `half` = pixel half of this warp
+      const float* vB = base + vsel * GT_F + fg * GSP + ft + half * (GPX / 2);
+      // acc[mt*4 + nt][0..3]: rows 16 mt + fg / + 8, columns 8 nt + 2 ft (+1)
 #pragma unroll 2
-      for (int ks = 0; ks < GPX / 8; ++ks) {
-        uint32_t ah[4], al[4];
-        split_tf32(gA[ks * 8], ah[0], al[0]);
-        split_tf32(gA[8 * GSP + ks * 8], ah[1], al[1]);
-        split_tf32(gA[ks * 8 + 4], ah[2], al[2]);
-        split_tf32(gA[8 * GSP + ks * 8 + 4], ah[3], al[3]);
+      for (int ks = 0; ks < GPX / 16; ++ks) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          split_tf32(gA[mt * 16 * GSP + ks * 8], ah[mt][0], al[mt][0]);
+          split_tf32(gA[(mt * 16 + 8) * GSP + ks * 8], ah[mt][1], al[mt][1]);
+          split_tf32(gA[mt * 16 * GSP + ks * 8 + 4], ah[mt][2], al[mt][2]);
+          split_tf32(gA[(mt * 16 + 8) * GSP + ks * 8 + 4], ah[mt][3], al[mt][3]);
+        }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           uint32_t bh[2], bl[2];
           split_tf32(vB[nt * 8 * GSP + ks * 8], bh[0], bl[0]);
           split_tf32(vB[nt * 8 * GSP + ks * 8 + 4], bh[1], bl[1]);
-          mma_tf32(acc[nt], al, bh);
-          mma_tf32(acc[nt], ah, bl);
-          mma_tf32(acc[nt], ah, bh);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            mma_tf32(acc[mt * 4 + nt], al[mt], bh);
+            mma_tf32(acc[mt * 4 + nt], ah[mt], bl);
+            mma_tf32(acc[mt * 4 + nt], ah[mt], bh);
+          }
         }
       }
     } else {
@@ -1347,24 +1358,29 @@ __global__ void __launch_bounds__(384, 1) gate_wgrad_kernel(IntDev d, int t0, in
     buf = (buf + 1) % GNST;
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NACC; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] += tot[i][j];
   bsum += btot;
-  float* ga = d.gacc + (size_t)blockIdx.x * GACC_N;
+  float* ga = d.gacc + (size_t)(MMA ? 2 * blockIdx.x + half : blockIdx.x) * GACC_N;
   if (MMA) {
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int i = 0; i < NACC; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        acc_store(ga + m * 1024 + (half * 16 + fg + 8 * (e >> 1)) * C + nt * 8 + 2 * ft + (e & 1), acc[nt][e], first);
+        acc_store(ga + m * 1024 + ((i >> 2) * 16 + fg + 8 * (e >> 1)) * C + (i & 3) * 8 + 2 * ft + (e & 1), acc[i][e], first);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc_store(ga + m * 1024 + (ocq + 8 * i) * C + icq + 8 * j, acc[i][j], first);
   }
-  if (tid < 3 * C) acc_store(ga + GACC_BE + tid, bsum, first);
+  if (tid < 3 * C) {
+    // bias sums are whole-tile row sums: with the two-slot MMA mapping they live in the CTA's even slot, the odd slot holds zero
+    float* gb = d.gacc + (size_t)(MMA ? 2 * blockIdx.x : blockIdx.x) * GACC_N + GACC_BE + tid;
+    acc_store(gb, bsum, first);
+    if (MMA) gb[GACC_N] = 0.f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1680,7 +1696,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
   }
   FinalizeArgs f;
-  f.pw_ctas = PW_EW_CTAS; f.gate_ctas = gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
+  f.pw_ctas = PW_EW_CTAS; f.gate_ctas = tc ? 2 * gate_grid : gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
   f.wgrad_tc = tc ? wgrad_ts_ctas(d.T, d.B, d.H, d.W) : 0;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
