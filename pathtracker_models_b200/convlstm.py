@@ -46,6 +46,10 @@ def _find_gabor(gabor, gabor_path):
 class _ConvLSTMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False):
+        if ctx.needs_input_grad[0]:
+            # the reference is differentiable w.r.t. the image through autograd; this path has no dx kernel: say so
+            raise NotImplementedError("ConvLSTM: gradient w.r.t. the input image is not implemented (InT / FFhGRU / kys.GRU "
+                                      "provide it); pass x without requires_grad")
         L = _lib.lib()
         B, _, H, W = x.shape
         flat = flat.contiguous()

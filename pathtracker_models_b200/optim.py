@@ -80,6 +80,29 @@ class FusedAdam(torch.optim.Optimizer):
         self._g = torch.zeros_like(self._flat)
         self._steps = [0] * len(ps)
 
+    def add_param_group(self, param_group):
+        if getattr(self, "_flat", None) is not None:
+            raise ValueError("FusedAdam re-homes its parameters into one flat buffer at construction; build a new optimizer "
+                             "instead of adding a parameter group")
+        super().add_param_group(param_group)
+
+    def state_dict(self):
+        """torch.optim.Optimizer.state_dict() plus the fused state (moments and per-parameter step counts), so that a resumed
+        run continues Adam's bias correction instead of silently restarting it."""
+        sd = super().state_dict()
+        sd["fused"] = {"exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone(), "steps": list(self._steps)}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        fused = state_dict.pop("fused", None)
+        super().load_state_dict(state_dict)
+        if fused is not None:
+            if fused["exp_avg"].numel() != self._m.numel() or len(fused["steps"]) != len(self._steps):
+                raise ValueError("FusedAdam.load_state_dict: fused state does not match this optimizer's parameters")
+            self._m.copy_(fused["exp_avg"]); self._v.copy_(fused["exp_avg_sq"])
+            self._steps = [int(v) for v in fused["steps"]]
+
     @torch.no_grad()
     def step(self, closure=None, zero_grad=False):
         """One Adam update; `zero_grad=True` folds `optimizer.zero_grad()` (grads set to None) into it.
@@ -91,8 +114,12 @@ class FusedAdam(torch.optim.Optimizer):
         views = self._g.split(self._sizes)
         srcs, dsts = [], []
         runs, off = [], 0       # [first element, count, step]
+        base = self._flat.data_ptr()
         for i, (p, v) in enumerate(zip(self._ps, views)):
             k = self._sizes[i]
+            if p.data_ptr() != base + 4 * off:
+                raise RuntimeError("FusedAdam: a parameter's storage was re-assigned after construction (p.data = ...); it no "
+                                   "longer lives in the optimizer's flat buffer and would silently stop being updated")
             if p.grad is not None:
                 srcs.append(p.grad.reshape(-1)); dsts.append(v)
                 self._steps[i] += 1

@@ -182,3 +182,13 @@ def test_wide_operators_alone_vs_torch_fp64(K, B, H, W):
     (F.conv2d(h64, ws, padding=K // 2) * dy64.detach()).sum().backward()
     assert rel_err(lstm_wide_op("transpose", dy32.cuda(), w32.cuda()), h64.grad) < tol
     assert rel_err(lstm_wide_op("wgrad", h32.cuda(), w32.cuda(), dy32.cuda()), w64.grad) < tol
+
+
+def test_convlstm_input_gradient_is_refused_loudly():
+    """the reference is differentiable w.r.t. the image; this path has no dx kernel and says so instead of returning None"""
+    from pathtracker_models_b200 import convlstm
+    case = load_convlstm_case("convlstm_k7_small")
+    m = convlstm.ConvLSTM(timesteps=2, filt_size=7, gabor=case["gabor"]).cuda().train()
+    x = case["x"].float().cuda().requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="input image"):
+        m(x, 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())

@@ -91,3 +91,41 @@ def test_fused_adam_vs_torch_adam_and_module_contract():
     out, _ = m(x)
     out.sum().backward()
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.gpu
+def test_fused_adam_state_dict_round_trip_and_guards():
+    """optimizer.state_dict() / load_state_dict() carry the fused moments and step counts (a resumed run must not restart Adam's
+    bias correction); add_param_group after construction and a re-assigned p.data are refused instead of silently ignored."""
+    from pathtracker_models_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(5, 3, device="cuda")), torch.nn.Parameter(torch.randn(7, device="cuda"))]
+    opt = FusedAdam(ps, lr=1e-2)
+    g = torch.Generator().manual_seed(2)
+    grads = [[torch.randn(p.shape, generator=g).cuda() for p in ps] for _ in range(4)]
+    for k in range(2):
+        for p, gr in zip(ps, grads[k]):
+            p.grad = gr.clone()
+        opt.step(zero_grad=True)
+    sd = opt.state_dict()
+    snap = [p.detach().clone() for p in ps]
+    for k in range(2, 4):                      # continue two more steps: the reference trajectory
+        for p, gr in zip(ps, grads[k]):
+            p.grad = gr.clone()
+        opt.step(zero_grad=True)
+    want = [p.detach().clone() for p in ps]
+    ps2 = [torch.nn.Parameter(s.clone()) for s in snap]
+    opt2 = FusedAdam(ps2, lr=1e-2)
+    opt2.load_state_dict(sd)
+    for k in range(2, 4):
+        for p, gr in zip(ps2, grads[k]):
+            p.grad = gr.clone()
+        opt2.step(zero_grad=True)
+    for a, b in zip(ps2, want):
+        assert torch.equal(a.detach(), b)
+    with pytest.raises(ValueError):
+        opt2.add_param_group({"params": [torch.nn.Parameter(torch.zeros(2, device="cuda"))]})
+    ps2[0].data = torch.zeros(5, 3, device="cuda")
+    ps2[0].grad = torch.ones(5, 3, device="cuda")
+    with pytest.raises(RuntimeError, match="re-assigned"):
+        opt2.step()
