@@ -50,6 +50,8 @@ struct IntDev {
   float *states, *logits;
   float* bn_part;
   unsigned* counter;
+  float* bn_part2;         // persistent time-loop kernel (ptk_int_loop.cu): second partial-statistics buffer, barrier counters
+  unsigned* loop_sync;
   // backward scratch
   float *gE, *gI, *geb, *dAct, *dGe, *dX, *dS, *giS, *aS, *Xs;
   float *GeB[2], *gebB[2]; // per-step-parity copies of Ge and geb (the fused bwd_d(t)+bwd_a(t-1) kernel writes step t-1's
@@ -100,5 +102,10 @@ int run_int_backward(const IntDev& d, int cell, int act, cudaStream_t st);
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st);
 int pw_grid(int B, int H, int W);
+// persistent forward time loop (ptk_int_loop.cu): one cooperative kernel for all frames
+bool int_loop_enabled();               // PTK_FWD_LOOP=0 selects the per-phase PDL chain (A/B measurements)
+bool int_loop_fits(int B, int H, int W);
+size_t int_loop_sync_words(int B);
+int run_int_forward_loop(const IntDev& d, int cell, int act, float* part1, unsigned* sync_words, cudaStream_t st);
 
 }  // namespace ptk

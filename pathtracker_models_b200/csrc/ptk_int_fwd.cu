@@ -9,101 +9,12 @@
 // convolutions are register-tiled 32x32x32 products against shared-memory tiles; CTAs are
 // persistent (weights staged once) and warps stride over the tiles.
 #include "ptk_int.h"
+#include "ptk_int_fwd_tiles.cuh"
 #include "ptk_profile.h"
 #include "ptk_pw.cuh"
 
 namespace ptk {
 
-constexpr int TILE_F = C * TP;   // floats per warp tile
-
-// stem of the thread's patch into the X tile (rolled: softplus is ~100 instructions per element)
-template <int ACT>
-__device__ __forceinline__ void stem_to_tile(float* sX, const float* sWp, const float* sbp, const float (&xin)[3][4],
-                                             const Lane& L) {
-#pragma unroll 1
-  for (int o = 0; o < 8; ++o) {
-    float pre[4];
-    stem_pre(sWp, sbp, L.oc0 + o, xin, pre);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) pre[p] = actf<ACT>(pre[p]);
-    tile_st(sX, L, o, pre);
-  }
-}
-
-// eqs (1)-(2) for frame t: A = sigmoid(Wa_w X + Wa_u E + b), Ge = A*E.  sE must hold E_t.
-// NOINH (InT(no_inh=True), models/InT.py:167-168): inhibition := Ge, gated_inhibition := E, so the step's
-// excitation gate G_e = sigmoid(We_w E + We_u Ge + b) (eq. 9) is formed here as well and Ge becomes I_{t+1}.
-template <int ACT, bool NOINH>
-__device__ __forceinline__ void attention_tile(const IntDev& d, int t, int b, int pix_base, float* sX,
-                                               const float* sE, const float* sWaw, const float* sWau,
-                                               const float* sba, const float* sWp, const float* sbp,
-                                               const float* sWew, const float* sWeu, const float* sbe,
-                                               const Lane& L, const float (&xin)[3][4]) {
-  const int P = d.H * d.W, pix = pix_base + L.pxo;
-  stem_to_tile<ACT>(sX, sWp, sbp, xin, L);
-  __syncwarp();
-  constexpr bool MMA = (ACT & ACT_FAST) != 0;   // tensor-core modes: weights are in B-fragment order, bias added at read
-  float acc[4][8];
-  if (MMA) {
-    Frag f;
-    frag_zero(f);
-    warp_mma_gemm(f, sX, sWaw);
-    warp_mma_gemm(f, sE, sWau);
-    __syncwarp();
-    frag_to_tile(sX, f);
-    __syncwarp();
-  } else {
-    acc_fill(acc, sba, L);
-    warp_gemm(acc, sX, sWaw, L);
-    warp_gemm(acc, sE, sWau, L);
-    __syncwarp();
-    acc_to_tile(sX, L, acc);          // park the pre-activations; only this thread re-reads its patch
-  }
-  float* Aout = d.A_at(t) + (size_t)b * d.a_bstride + pix;
-  float* Geout = d.Ge + (size_t)b * C * P + pix;
-  float* Iout = d.I_at(t + 1) + (size_t)b * C * P + pix;
-#pragma unroll 1
-  for (int o = 0; o < 8; ++o) {
-    float e[4], a[4], ge[4];
-    tile_ld(sE, L, o, e);
-    tile_ld(sX, L, o, a);
-    const float bias = MMA ? sba[L.oc0 + o] : 0.f;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) { a[p] = sigm<ACT>(a[p] + bias); ge[p] = a[p] * e[p]; }
-    st4(Aout + (size_t)(L.oc0 + o) * P, a);
-    st4(Geout + (size_t)(L.oc0 + o) * P, ge);
-    if (NOINH) {
-      st4(Iout + (size_t)(L.oc0 + o) * P, ge);
-      tile_st(sX, L, o, ge);
-    }
-  }
-  if (NOINH) {
-    __syncwarp();
-    if (MMA) {
-      Frag f;
-      frag_zero(f);
-      warp_mma_gemm(f, sE, sWew);
-      warp_mma_gemm(f, sX, sWeu);
-      __syncwarp();
-      frag_to_tile(sX, f);          // Ge (in sX) is dead now
-      __syncwarp();
-      acc_fill(acc, sbe, L);
-      acc_add_tile(acc, sX, L);
-    } else {
-      acc_fill(acc, sbe, L);
-      warp_gemm(acc, sE, sWew, L);
-      warp_gemm(acc, sX, sWeu, L);
-    }
-    float* Gx = d.Gex_at(t) + (size_t)b * C * P + pix;
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      float g[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) g[p] = sigm<ACT>(acc[p][o]);
-      st4(Gx + (size_t)(L.oc0 + o) * P, g);
-    }
-  }
-}
 
 template <int ACT, bool NOINH>
 __global__ void __launch_bounds__(128, 4) int_pre_kernel(IntDev d, int t) {
@@ -143,14 +54,6 @@ __global__ void __launch_bounds__(128, 4) int_pre_kernel(IntDev d, int t) {
 }
 
 // eqs (3b)-(9): BatchNorm0 apply, inhibition drive, inhibition gate + blend, excitation gate.
-struct MidIn { float4 s, i, y0; };
-template <int CELL>
-__device__ __forceinline__ void mid_load(const float* Sg, const float* It, const float* Y0, size_t base, int c, int P,
-                                         MidIn& r) {
-  r.s = ld4(Sg + (size_t)c * P);
-  if (CELL != PTK_CELL_INT) r.i = ld4(It + base + (size_t)c * P);
-  r.y0 = ld4(Y0 + base + (size_t)c * P);
-}
 template <int CELL, int ACT>
 __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   extern __shared__ __align__(16) float dsm[];
@@ -207,6 +110,7 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
   }
   cp_async_wait<0>();
   __syncthreads();
+  const MidW mw{sWiw, sWiu, sWew, sWeu, sWp, sbp, sbi, sbe, sAl, sMu, sScale, sShift};
   for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
@@ -220,83 +124,9 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
       cp_async_wait<0>();
       __syncwarp();
     }
-    constexpr bool MMA = (ACT & ACT_FAST) != 0;
-    float acc[4][8];
-    // excitation gate (eq. 9) first: G_e = sigmoid(We_w S + We_u Ge + b), written straight to the checkpoint
-    if (MMA) {
-      Frag f;
-      frag_zero(f);
-      warp_mma_gemm(f, sS, sWew);
-      warp_mma_gemm(f, sGX, sWeu);
-      __syncwarp();
-      frag_to_tile(sGX, f);          // the Ge tile is dead once both products have read it
-      __syncwarp();
-      acc_fill(acc, sbe, L);
-      acc_add_tile(acc, sGX, L);
-    } else {
-      acc_fill(acc, sbe, L);
-      warp_gemm(acc, sS, sWew, L);
-      warp_gemm(acc, sGX, sWeu, L);
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      float gx[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) gx[p] = sigm<ACT>(acc[p][o]);
-      st4(d.Gex_at(t) + base + (size_t)(L.oc0 + o) * P, gx);
-    }
-    __syncwarp();
-    MidIn cur;                                    // channel 0 of the blend loop: in flight during the products below
-    mid_load<CELL>(Sg, It, Y0, base, L.oc0, P, cur);
-    stem_to_tile<ACT>(sGX, sWp, sbp, xin, L);     // the Ge tile is free now: X takes its place
-    __syncwarp();
-    // inhibition gate pre-activation (eq. 7), parked in the S tile (S is re-read from global below)
-    if (MMA) {
-      Frag f;
-      frag_zero(f);
-      warp_mma_gemm(f, sGX, sWiw);
-      warp_mma_gemm(f, sS, sWiu);
-      __syncwarp();
-      frag_to_tile(sS, f);           // bias is added where the tile is read
-      __syncwarp();
-    } else {
-      acc_fill(acc, sbi, L);
-      warp_gemm(acc, sGX, sWiw, L);
-      warp_gemm(acc, sS, sWiu, L);
-      __syncwarp();
-      acc_to_tile(sS, L, acc);
-    }
-#pragma unroll 1
-    for (int o = 0; o < 8; ++o) {
-      const int c = L.oc0 + o;
-      const size_t idx = base + (size_t)c * P;
-      MidIn nxt;
-      if (o < 7) mid_load<CELL>(Sg, It, Y0, base, c + 1, P, nxt);
-      float X[4], gi[4], out[4];
-      tile_ld(sGX, L, o, X);
-      tile_ld(sS, L, o, gi);
-      const float S[4] = {cur.s.x, cur.s.y, cur.s.z, cur.s.w}, y0[4] = {cur.y0.x, cur.y0.y, cur.y0.z, cur.y0.w};
-      float I[4];
-      if (CELL == PTK_CELL_INT) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) I[p] = S[p];
-      } else {
-        I[0] = cur.i.x; I[1] = cur.i.y; I[2] = cur.i.z; I[3] = cur.i.w;
-      }
-      const float gbias = MMA ? sbi[c] : 0.f;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        gi[p] = sigm<ACT>(gi[p] + gbias);
-        const float U = fmaf(y0[p], sScale[c], sShift[c]);
-        const float Pp = U * fmaf(sAl[c], S[p], sMu[c]);
-        const float Q = actf<ACT>(Pp);
-        const float Ihat = actf<ACT>(X[p] - Q);
-        out[p] = (1.0f - gi[p]) * I[p] + gi[p] * Ihat;
-      }
-      st4(d.Gi_at(t) + idx, gi);
-      st4(Iout + idx, out);
-      if (o < 7) cur = nxt;
-    }
+    MidIn cur;
+    mid_tile_head<CELL, ACT>(d, t, base, Sg, sS, sGX, mw, L, xin, cur, It, Y0);
+    mid_tile_tail<CELL, ACT>(d, t, base, Sg, sS, sGX, mw, L, cur, It, Y0, Iout);
     __syncwarp();
   }
 }
@@ -305,11 +135,6 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
 // Latency structure (profiles/r1f_pointwise_full.txt: global-load scoreboard stalls dominated): the first
 // tile's operands are requested before the weight fill, the fill itself is cp.async, and the per-channel
 // loop prefetches the next channel's operands while the current one is computed.
-struct PostIn { float4 y1, i2, e, gx; };
-__device__ __forceinline__ void post_load(const float* Y1, const float* I2, const float* Et, const float* Gx,
-                                          size_t idx, PostIn& r) {
-  r.y1 = ld4(Y1 + idx); r.i2 = ld4(I2 + idx); r.e = ld4(Et + idx); r.gx = ld4(Gx + idx);
-}
 #if PTK_DEBUG_STAMPS   // tuning instrumentation, not in the shipped library (see ptk_conv_tc.cu)
 __device__ unsigned long long g_pw_stamp[4];   // globaltimer at entry / after the PDL wait of int_post_kernel's CTA 0
 #define PW_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_pw_stamp[i])); } while (0)
@@ -330,7 +155,6 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
   const int warp = threadIdx.x >> 5, P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
   const float* Et = d.E_at(t);
   const float* I2 = d.I_at(t + 1);
-  float* Eout = d.E_at(t + 1);
   const float* Y1 = d.Y1_at(t);
   const float* Gx = d.Gex_at(t);
   int wt = blockIdx.x * 4 + warp;
@@ -375,6 +199,7 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
   float* sX = tiles + warp * 2 * TILE_F;
   float* sE = sX + TILE_F;
   const float br = __ldg(d.br);
+  const PostW pw{sWaw, sWau, sWew, sWeu, sWp, sbp, sba, sbe, sKa, sGa, sScale, sShift, sWr};
   for (bool firstTile = true; wt < nWT; wt += gridDim.x * 4, firstTile = false) {
     const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
     const size_t base = (size_t)b * C * P + pix;
@@ -382,38 +207,7 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
       post_load(Y1, I2, Et, Gx, base + (size_t)L.oc0 * P, cur);
       if (has_next) frame_px(d.fv, b, t + 1, pix, d.W, xin);
     }
-    float sread[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int o = 0; o < 8; ++o) {
-      const int c = L.oc0 + o;
-      const size_t idx = base + (size_t)c * P;
-      PostIn nxt;
-      if (o < 7) post_load(Y1, I2, Et, Gx, idx + P, nxt);
-      const float y1[4] = {cur.y1.x, cur.y1.y, cur.y1.z, cur.y1.w}, i2[4] = {cur.i2.x, cur.i2.y, cur.i2.z, cur.i2.w};
-      const float e[4] = {cur.e.x, cur.e.y, cur.e.z, cur.e.w}, gx[4] = {cur.gx.x, cur.gx.y, cur.gx.z, cur.gx.w};
-      float e2[4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float V = fmaf(y1[p], sScale[c], sShift[c]);
-        const float R = V * fmaf(sKa[c], i2[p], sGa[c]);
-        const float Ehat = actf<ACT>(R);
-        e2[p] = (1.0f - gx[p]) * e[p] + gx[p] * Ehat;
-        sread[p] = fmaf(sWr[c], e2[p], sread[p]);
-      }
-      st4(Eout + idx, e2);
-      tile_st(sE, L, o, e2);
-      if (o < 7) cur = nxt;
-    }
-    if (d.states != nullptr) {   // testmode: states.append(readout_conv(excitation)), InT.py:233
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        sread[p] += __shfl_xor_sync(0xffffffffu, sread[p], 8);
-        sread[p] += __shfl_xor_sync(0xffffffffu, sread[p], 16);
-        sread[p] += br;
-      }
-      if (L.og == 0) st4(d.states + ((size_t)b * d.T + t) * P + pix, sread);
-    }
-    if (has_next) attention_tile<ACT, NOINH>(d, t + 1, b, pix_base, sX, sE, sWaw, sWau, sba, sWp, sbp, sWew, sWeu, sbe, L, xin);
+    post_tile<ACT, NOINH>(d, t, has_next, b, pix_base, sX, sE, pw, br, L, xin, cur);
     __syncwarp();
   }
 }
@@ -516,7 +310,15 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
     int_pre_kernel<ACT, NOINH><<<grid, 128, sm_pre, st>>>(d, 0);
   }
   PTK_LAUNCH_OK("int_pre_kernel");
-  for (int t = 0; t < d.T; ++t) {
+  // tensor-core modes, whole grid co-resident: ONE persistent cooperative kernel walks all frames (ptk_int_loop.cu)
+  const bool loop = !NOINH && (ACT & ACT_FAST) && d.conv_mode != PTK_CONV_FP32 && conv_v2_enabled() && int_loop_enabled() &&
+                    int_loop_fits(d.B, d.H, d.W);
+  if (loop) {
+    const int rc = run_int_forward_loop(d, cell, ACT & 1, d.bn_part2, d.loop_sync, st);
+    if (rc) return rc;
+    PTK_LAUNCH_OK("int_loop_kernel");
+  }
+  for (int t = 0; t < d.T && !loop; ++t) {
     int rc;
     if (!NOINH) {
       ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode, 1};
