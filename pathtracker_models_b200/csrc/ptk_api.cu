@@ -18,9 +18,9 @@ static size_t wbank_floats() {
   const size_t a = (size_t)C * C * TAPS, b = (conv7_tc2_weight_bytes() + 3) / 4;
   return a > b ? a : b;
 }
-bool int_loop_enabled() {
-  static const bool on = [] { const char* e = getenv("PTK_FWD_LOOP"); return e && e[0] == '1'; }();
-  return on;
+int int_loop_mode() {
+  static const int mode = [] { const char* e = getenv("PTK_FWD_LOOP"); return e ? atoi(e) : 0; }();
+  return mode;
 }
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("PTK_NO_PDL"); return !(e && e[0] == '1'); }();
@@ -91,6 +91,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
   unsigned* counter = cv.take<unsigned>(4);
   float* bn_part2 = cv.take<float>((size_t)conv_num_ctas(dm->B, dm->H, dm->W) * C * 2);
   unsigned* loop_sync = cv.take<unsigned>(int_loop_sync_words(dm->B));
+  uint8_t* loop_gates = cv.take<uint8_t>(int_loop2_gate_bytes());
   float* acc = cv.take<float>((size_t)PW_EW_CTAS * ACC_N);
   float* gacc = cv.take<float>((size_t)2 * GATE_CTAS * GACC_N);   // tensor-core modes: two slots per CTA (pixel halves)
   const size_t bn_sums_n = (size_t)PW_EW_CTAS * 2 * C > (size_t)dm->B * C * 4 ? (size_t)PW_EW_CTAS * 2 * C : (size_t)dm->B * C * 4;
@@ -109,7 +110,7 @@ static size_t carve_workspace(const PtkDims* dm, void* ws, IntDev* d, bool with_
   if (d) {
     d->Ge = Ge;
     d->bn_part = bn_part; d->counter = counter; d->pw_ctas = pw;
-    d->bn_part2 = bn_part2; d->loop_sync = loop_sync;
+    d->bn_part2 = bn_part2; d->loop_sync = loop_sync; d->loop_gates = loop_gates;
     d->acc = acc; d->gacc = gacc; d->bn_sums = bn_sums; d->bn_tot = bn_tot; d->bn_acc = bn_acc;
     d->head = head; d->dgoal = dgoal;
     d->wacc_exc = wacc_exc; d->wacc_inh = wacc_inh;
@@ -315,6 +316,7 @@ PTK_API int ptk_debug_tc_stamps(long long* out) { return read_tc_debug(out); }
 PTK_API int ptk_debug_wt_stamps(long long* out) { return read_wt_debug(out); }
 PTK_API int ptk_debug_tc_times(unsigned long long* out, int n) { return read_tc_times(out, n); }
 PTK_API int ptk_debug_pw_stamps(unsigned long long* out) { return read_pw_stamps(out); }
+PTK_API int ptk_debug_loop_stamps(long long* out) { return read_loop_stamps(out); }
 #endif
 
 size_t ptk_lstm_wide_op_workspace_bytes(int32_t K) {

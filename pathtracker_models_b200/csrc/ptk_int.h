@@ -52,6 +52,7 @@ struct IntDev {
   unsigned* counter;
   float* bn_part2;         // persistent time-loop kernel (ptk_int_loop.cu): second partial-statistics buffer, barrier counters
   unsigned* loop_sync;
+  uint8_t* loop_gates;     // gate matrices as bf16 hi/lo tcgen05 B operands (ptk_int_loop2.cu)
   // backward scratch
   float *gE, *gI, *geb, *dAct, *dGe, *dX, *dS, *giS, *aS, *Xs;
   float *GeB[2], *gebB[2]; // per-step-parity copies of Ge and geb (the fused bwd_d(t)+bwd_a(t-1) kernel writes step t-1's
@@ -103,9 +104,12 @@ int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st);
 int pw_grid(int B, int H, int W);
 // persistent forward time loop (ptk_int_loop.cu): one cooperative kernel for all frames
-bool int_loop_enabled();               // PTK_FWD_LOOP=0 selects the per-phase PDL chain (A/B measurements)
+int int_loop_mode();                   // PTK_FWD_LOOP: 0 = per-phase PDL chain, 1 = the chain's phases in one cooperative kernel
+                                       // (bit-identical), 2 = second generation (tcgen05 gate products, thread = pixel)
 bool int_loop_fits(int B, int H, int W);
 size_t int_loop_sync_words(int B);
 int run_int_forward_loop(const IntDev& d, int cell, int act, float* part1, unsigned* sync_words, cudaStream_t st);
+size_t int_loop2_gate_bytes();
+int run_int_forward_loop2(const IntDev& d, int cell, int act, float* part1, unsigned* sync_words, uint8_t* gateB, cudaStream_t st);
 
 }  // namespace ptk

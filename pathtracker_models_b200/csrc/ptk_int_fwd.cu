@@ -311,10 +311,11 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
   }
   PTK_LAUNCH_OK("int_pre_kernel");
   // tensor-core modes, whole grid co-resident: ONE persistent cooperative kernel walks all frames (ptk_int_loop.cu)
-  const bool loop = !NOINH && (ACT & ACT_FAST) && d.conv_mode != PTK_CONV_FP32 && conv_v2_enabled() && int_loop_enabled() &&
+  const bool loop = !NOINH && (ACT & ACT_FAST) && d.conv_mode != PTK_CONV_FP32 && conv_v2_enabled() && int_loop_mode() > 0 &&
                     int_loop_fits(d.B, d.H, d.W);
   if (loop) {
-    const int rc = run_int_forward_loop(d, cell, ACT & 1, d.bn_part2, d.loop_sync, st);
+    const int rc = int_loop_mode() == 1 ? run_int_forward_loop(d, cell, ACT & 1, d.bn_part2, d.loop_sync, st)
+                                        : run_int_forward_loop2(d, cell, ACT & 1, d.bn_part2, d.loop_sync, d.loop_gates, st);
     if (rc) return rc;
     PTK_LAUNCH_OK("int_loop_kernel");
   }

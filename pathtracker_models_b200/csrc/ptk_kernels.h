@@ -113,6 +113,7 @@ int read_pw_stamps(unsigned long long* out);
 int read_tc_debug(long long* out);
 int read_wt_debug(long long* out);
 int read_tc_times(unsigned long long* out, int n);
+int read_loop_stamps(long long* out);
 #endif
 
 }  // namespace ptk
