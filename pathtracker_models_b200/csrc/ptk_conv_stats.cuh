@@ -7,7 +7,7 @@ namespace ptk {
 
 // Every CTA has written part[cta][c] = (mean, M2) over its `npix` conv outputs of channel c.
 // The last CTA to arrive folds all partials (Chan et al. parallel variance, in double) into
-// stats_out = mean[32], rstd[32] (biased variance, eps 1e-3: models/InT.py:102).  256 threads.
+// stats_out = mean[32], rstd[32] (biased variance, eps 1e-3: models/InT.py:102).  >= 256 threads (eight warps fold).
 __device__ __forceinline__ void conv_stats_fold(const ConvArgs& a, int nCta, int npix, double (*sFin)[C][3],
                                                 int* sIsLast) {
   const int tid = threadIdx.x;
@@ -18,9 +18,9 @@ __device__ __forceinline__ void conv_stats_fold(const ConvArgs& a, int nCta, int
   if (*sIsLast) {
     __threadfence();
     const int c = tid & 31, g = tid >> 5;
-    // the whole grid waits for this CTA: keep 16 independent loads in flight per thread
+    // the whole grid waits for this CTA: keep 16 independent loads in flight per thread (eight warps; further warps idle)
     double s1 = 0, s2 = 0, s3 = 0;
-    int i = g;
+    int i = g < 8 ? g : nCta;
     for (; i + 8 * 15 < nCta; i += 8 * 16) {
       float2 pm[16];
 #pragma unroll
@@ -34,7 +34,7 @@ __device__ __forceinline__ void conv_stats_fold(const ConvArgs& a, int nCta, int
       s2 += (double)pm.x * pm.x;
       s3 += pm.y;
     }
-    sFin[g][c][0] = s1; sFin[g][c][1] = s2; sFin[g][c][2] = s3;
+    if (g < 8) { sFin[g][c][0] = s1; sFin[g][c][1] = s2; sFin[g][c][2] = s3; }
     __syncthreads();
     if (tid < C) {
       s1 = s2 = s3 = 0;

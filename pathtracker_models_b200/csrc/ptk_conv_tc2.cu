@@ -27,8 +27,10 @@
 
 namespace ptk {
 
+constexpr int T2_THREADS = 384;   // warp 0: weight producer, 1: MMA issuer, 2-3: staging only, 4-11: two epilogue groups; all warps stage
+
 template <bool SINGLE>
-__global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
+__global__ void __launch_bounds__(T2_THREADS, 1) conv7_tc2_kernel(ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* sA = smem_raw;                                   // [hi|lo][4 chunks][880 px][16 B]
   uint8_t* sWr = smem_raw + T2_A_BYTES;                     // weight ring
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
   uint64_t* stB = stA + 1;                                  // input rows 12-21 staged
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stB + 1);
   __shared__ double sFin[8][C][3];
+  __shared__ float sMerge[C * 4];                           // BatchNorm partials of the second epilogue group
   __shared__ float4 sBN[C];                                 // fused BatchNorm backward: k, mean(dV), mean, rstd * mean(dV*xhat)
   __shared__ int sIsLast;
 
@@ -56,15 +59,15 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
   if (tid == 0) {
     for (int i = 0; i < T2_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&dFull[0], 1); mbar_init(&dFull[1], 1);
-    mbar_init(&dEmpty[0], 4); mbar_init(&dEmpty[1], 4);
-    mbar_init(stA, 256); mbar_init(stB, 192);
+    mbar_init(&dEmpty[0], T2_EPI_WARPS); mbar_init(&dEmpty[1], T2_EPI_WARPS);
+    mbar_init(stA, T2_THREADS); mbar_init(stB, T2_THREADS - 64);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < T2_A_BYTES / 16; i += 256) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < T2_A_BYTES / 16; i += T2_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     }
   }
   if (a.bn_y != nullptr) {   // the saved conv output is a forward checkpoint: pull the tile's lines HBM -> L2 before the wait
-    for (int it = tid; it < C * T2_ROWS; it += 256) {
+    for (int it = tid; it < C * T2_ROWS; it += T2_THREADS) {
       const int ch = it / T2_ROWS, gy = y0 - 3 + (it - ch * T2_ROWS);
       if (gy >= 0 && gy < H) prefetch_l2(a.bn_y + (size_t)b * C * H * W + ((size_t)ch * H + gy) * W + x0);
     }
@@ -99,78 +102,57 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     __syncthreads();
   }
   // Two phases, so that the MMA warp can start the first row chunk (input rows 0-11) while rows 12-21 are still being staged:
-  //   phase A: rows 0-11 (items 0..383), all 256 threads, + the halo columns  -> mbarrier stA
-  //   phase B: rows 12-21 (items 384..703), warps 2-7 only (warps 0 / 1 go to their producer / MMA roles) -> mbarrier stB
-  // one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels; a thread's items are requested before the
-  // first conversion (the tile is L2-latency bound).
-  auto stage_items = [&](int first, int stride, int limit) {
-    constexpr int NR = 2;
-    float4 v[NR][8];
-    int pp[NR], qq[NR], rw[NR];
-    size_t off[NR];
+  //   phase A: rows 0-11 (items 0..383), one item per thread, + the halo columns  -> mbarrier stA
+  //   phase B: rows 12-21 (items 384..703), warps 2-11 only (warps 0 / 1 go to their producer / MMA roles) -> mbarrier stB
+  // one item = (chunk, row, 4-pixel group): 8 LDG.128 (one per channel) -> 4 pixels (the tile is L2-latency bound: one item per
+  // thread and phase, 12 warps' worth of loads in flight).
+  auto stage_item = [&](int it, int limit) {
+    // a quarter warp = (2 adjacent pixel groups) x (4 chunks): conflict-free 16-byte stores; a warp covers one whole input row
+    const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
+    const int gy = y0 + row - 3;
+    if (it >= limit || gy < 0 || gy >= H) return;
+    const int p = row * T2_WP + 3 + 4 * g;
+    const size_t off = ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
+    const float* src = a.in + (size_t)b * in_bs + off;
+    float4 v[8];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      // a quarter warp = (2 adjacent pixel groups) x (4 chunks): conflict-free 16-byte stores; a warp covers one whole input row
-      const int it = first + stride * r;
-      const int q = (it >> 1) & 3, row = it >> 5, g = ((it >> 3) & 3) * 2 + (it & 1);
-      const int gy = y0 + row - 3;
-      pp[r] = -1; qq[r] = q; off[r] = 0; rw[r] = row;
-      if (it < limit && gy >= 0 && gy < H) {
-        pp[r] = row * T2_WP + 3 + 4 * g;
-        off[r] = ((size_t)(q * 8) * H + gy) * W + x0 + 4 * g;
-        const float* src = a.in + (size_t)b * in_bs + off[r];
+    for (int e = 0; e < 8; ++e) v[e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
+    if (bnf) {
+      const float* ys = a.bn_y + (size_t)b * C * H * W + off;
+      float4 yv[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[r][e] = *reinterpret_cast<const float4*>(src + (size_t)e * H * W);
+      for (int e = 0; e < 8; ++e) yv[e] = *reinterpret_cast<const float4*>(ys + (size_t)e * H * W);
+      const bool own = row >= 3 && row < 3 + T2_TH;        // interior rows: this CTA owns their dY
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 cst = sBN[q * 8 + e], y = yv[e];
+        float4 t = v[e];
+        t.x = cst.x * (t.x - cst.y - (y.x - cst.z) * cst.w);
+        t.y = cst.x * (t.y - cst.y - (y.y - cst.z) * cst.w);
+        t.z = cst.x * (t.z - cst.y - (y.z - cst.z) * cst.w);
+        t.w = cst.x * (t.w - cst.y - (y.w - cst.z) * cst.w);
+        v[e] = t;
+        if (own) *reinterpret_cast<float4*>(a.bn_out + (size_t)b * C * H * W + off + (size_t)e * H * W) = t;
       }
     }
-    float4 yv[2][8];
-    if (bnf && pp[0] >= 0) {
-      const float* ys = a.bn_y + (size_t)b * C * H * W + off[0];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv[0][e] = *reinterpret_cast<const float4*>(ys + (size_t)e * H * W);
-    }
+    for (int px = 0; px < 4; ++px) {
+      uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      if (bnf && r + 1 < NR && pp[r + 1] >= 0) {     // the next item's Y in flight while this one is converted
-        const float* ys = a.bn_y + (size_t)b * C * H * W + off[r + 1];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) yv[(r + 1) & 1][e] = *reinterpret_cast<const float4*>(ys + (size_t)e * H * W);
+      for (int e = 0; e < 4; ++e) {
+        const float v0 = reinterpret_cast<const float*>(&v[2 * e])[px], v1 = reinterpret_cast<const float*>(&v[2 * e + 1])[px];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        hi[e] = pack_bf16x2(h0, h1);
+        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
       }
-      if (pp[r] < 0) continue;
-      const int p = pp[r], q = qq[r];
-      if (bnf) {
-        const bool own = rw[r] >= 3 && rw[r] < 3 + T2_TH;        // interior rows: this CTA owns their dY
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float4 cst = sBN[q * 8 + e], y = yv[r & 1][e];
-          float4 t = v[r][e];
-          t.x = cst.x * (t.x - cst.y - (y.x - cst.z) * cst.w);
-          t.y = cst.x * (t.y - cst.y - (y.y - cst.z) * cst.w);
-          t.z = cst.x * (t.z - cst.y - (y.z - cst.z) * cst.w);
-          t.w = cst.x * (t.w - cst.y - (y.w - cst.z) * cst.w);
-          v[r][e] = t;
-          if (own) *reinterpret_cast<float4*>(a.bn_out + (size_t)b * C * H * W + off[r] + (size_t)e * H * W) = t;
-        }
-      }
-#pragma unroll
-      for (int px = 0; px < 4; ++px) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v0 = reinterpret_cast<const float*>(&v[r][2 * e])[px], v1 = reinterpret_cast<const float*>(&v[r][2 * e + 1])[px];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
-        }
-        *reinterpret_cast<uint4*>(sA + q * T2_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(sA + 4 * T2_PLANE + q * T2_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
+      *reinterpret_cast<uint4*>(sA + q * T2_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(sA + 4 * T2_PLANE + q * T2_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   };
   constexpr int NIT_A = 4 * 12 * (T2_TW / 4), NIT = 4 * T2_ROWS * (T2_TW / 4);      // 384, 704
-  stage_items(tid, 256, NIT_A);
+  stage_item(tid, NIT_A);
   if (W > T2_TW) {   // halo columns (only inside the image when W > 32)
-    for (int it = tid; it < 4 * T2_ROWS * 6; it += 256) {
+    for (int it = tid; it < 4 * T2_ROWS * 6; it += T2_THREADS) {
       const int q = it / (T2_ROWS * 6), rem = it - q * (T2_ROWS * 6), r = rem / 6, hc = rem % 6;
       const int c = hc < 3 ? hc : (T2_TW + hc);          // padded columns 0..2 and 35..37
       const int gy = y0 + r - 3, gx = x0 + c - 3;
@@ -199,7 +181,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (UMMA)
   mbar_arrive(stA);
   if (warp >= 2) {
-    stage_items(NIT_A + tid - 64, 192, NIT);
+    stage_item(NIT_A + tid - 64, NIT);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(stB);
   }
@@ -269,84 +251,10 @@ __global__ void __launch_bounds__(256, 1) conv7_tc2_kernel(ConvArgs a) {
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ---- epilogue warps: quadrant dl = warp - 4 holds tap kx = 4*kxg + dl's share; out[oc][m] = sum_dl D[dl][oc][m + dl] ----
-    const int dl = warp - 4, et = tid - 128;
-    const int oc = et >> 2, jq = et & 3;              // sum phase: channel, 8-pixel slice of a 32-pixel block
+    // ---- epilogue: two groups of four warps drain alternate 32-pixel blocks (t2_epilogue, ptk_conv_tc2.cuh) --------------------
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    float sK = 0.f, s1 = 0.f, s2 = 0.f;               // shifted sums of this thread's outputs: sum (v - K), sum (v - K)^2
-    int sn = 0;
-    float* outc = a.out + (size_t)b * out_bs + (size_t)oc * H * W;
-    int blk = 0;
-#pragma unroll 1
-    for (int c = 0; c < T2_NCH; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&dFull[buf], (uint32_t)((c >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nb = t2_chunk_blocks(c);
-#pragma unroll 1
-      for (int kb = 0; kb < nb; ++kb, ++blk) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(dl * 32) << 16) + (uint32_t)(buf * T2_DBUF + kb * 32 + dl), v);   // lane = oc
-        float* pw = sPart + (size_t)(blk & 1) * (T2_PART / 4) + (size_t)(dl * C + lane) * T2_PP;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(pw + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        if (kb == nb - 1) {                             // this warp is done with the TMEM buffer
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&dEmpty[buf]);
-        }
-        named_bar_sync(1, 128);
-        const float* pr = sPart + (size_t)(blk & 1) * (T2_PART / 4) + (size_t)oc * T2_PP + 8 * jq;
-        float o[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 p0 = *reinterpret_cast<const float4*>(pr + 4 * h), p1 = *reinterpret_cast<const float4*>(pr + C * T2_PP + 4 * h);
-          const float4 p2 = *reinterpret_cast<const float4*>(pr + 2 * C * T2_PP + 4 * h), p3 = *reinterpret_cast<const float4*>(pr + 3 * C * T2_PP + 4 * h);
-          o[4 * h + 0] = (p0.x + p1.x) + (p2.x + p3.x);
-          o[4 * h + 1] = (p0.y + p1.y) + (p2.y + p3.y);
-          o[4 * h + 2] = (p0.z + p1.z) + (p2.z + p3.z);
-          o[4 * h + 3] = (p0.w + p1.w) + (p2.w + p3.w);
-        }
-        const int m0 = t2_chunk_start(c) + kb * 32 + 8 * jq;      // padded output pixel of o[0]
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int m = m0 + 2 * u, r = m / T2_WP, col = m - r * T2_WP;       // col is even: both pixels share a row
-          if (r < T2_TH && col < T2_TW) {
-            float2 t = make_float2(o[2 * u], o[2 * u + 1]);
-            float2* dst = reinterpret_cast<float2*>(outc + (size_t)(y0 + r) * W + x0 + col);
-            if (a.accumulate) { const float2 p = *dst; t.x += p.x; t.y += p.y; }
-            *dst = t;
-            if (stats) {
-              if (sn == 0) sK = o[2 * u];
-              const float d0 = o[2 * u] - sK, d1 = o[2 * u + 1] - sK;
-              s1 += d0 + d1;
-              s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-              sn += 2;
-            }
-          }
-        }
-      }
-    }
-    if (stats) {
-      // per-thread (n, mean, M2) -> Chan merge over the 4 threads of a channel -> per-CTA partial (mean, M2) of 16x32 outputs
-      float n = (float)sn, mean = sn ? sK + s1 / n : 0.f, m2 = sn ? fmaxf(s2 - s1 * s1 / n, 0.f) : 0.f;
-#pragma unroll
-      for (int off = 1; off <= 2; off <<= 1) {
-        const float n2 = __shfl_xor_sync(0xffffffffu, n, off), mean2 = __shfl_xor_sync(0xffffffffu, mean, off);
-        const float m22 = __shfl_xor_sync(0xffffffffu, m2, off);
-        const float nt = n + n2, dlt = mean2 - mean;
-        if (nt > 0.f) {
-          m2 = m2 + m22 + dlt * dlt * (n * n2 / nt);
-          mean = mean + dlt * (n2 / nt);
-        }
-        n = nt;
-      }
-      if (jq == 0) {
-        float* dstp = a.part + ((size_t)cta * C + oc) * 2;
-        dstp[0] = mean;
-        dstp[1] = m2;
-      }
-    }
+    const T2Epi e{a.out + (size_t)b * out_bs, H, W, x0, y0, a.accumulate, stats ? a.part + (size_t)cta * C * 2 : nullptr};
+    t2_epilogue(e, tmem_base, sPart, sMerge, dFull, dEmpty, 0u, warp - 4, lane);
   }
   if (stats) conv_stats_fold(a, gridDim.x * gridDim.y * gridDim.z, T2_TH * T2_TW, sFin, &sIsLast);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -385,10 +293,10 @@ int launch_conv7_tc2(const ConvArgs& a, cudaStream_t st) {
   dim3 grid(a.W / T2_TW, a.H / T2_TH, a.B);
   if (a.mode == PTK_CONV_BF16) {
     PTK_CUDA_OK(ptk_func_smem(conv7_tc2_kernel<true>, T2_SMEM));
-    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc2_kernel<true>, grid, dim3(256), T2_SMEM, st, a));
+    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc2_kernel<true>, grid, dim3(T2_THREADS), T2_SMEM, st, a));
   } else {
     PTK_CUDA_OK(ptk_func_smem(conv7_tc2_kernel<false>, T2_SMEM));
-    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc2_kernel<false>, grid, dim3(256), T2_SMEM, st, a));
+    PTK_CUDA_OK(launch_pdl(a.pdl != 0, conv7_tc2_kernel<false>, grid, dim3(T2_THREADS), T2_SMEM, st, a));
   }
   PTK_LAUNCH_OK("conv7_tc2_kernel");
   return PTK_OK;

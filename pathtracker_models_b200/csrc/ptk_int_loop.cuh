@@ -117,8 +117,8 @@ __device__ __forceinline__ void loop_fold(const float* part, int nCta, int npix,
 // stA, stB one: the parity a wait has to look for is the one of the stand-alone kernel xor (odd phase count ? kpar : 0).
 template <bool SINGLE>
 __device__ __forceinline__ void loop_conv(const float* __restrict__ in, const uint8_t* __restrict__ wsrc, float* out, float* part,
-                                          int cta, int H, int W, int x0, int y0, int b, uint8_t* smem, uint32_t tmem_base,
-                                          uint32_t kpar, bool own_rows_staged = false) {
+                                          int cta, int H, int W, int x0, int y0, int b, uint8_t* smem, float* sMerge,
+                                          uint32_t tmem_base, uint32_t kpar, bool own_rows_staged = false) {
   uint8_t* sWr = smem + LP_RING;
   uint8_t* sA = smem + LP_IMG;
   float* sPart = reinterpret_cast<float*>(smem + LP_PART);
@@ -269,77 +269,10 @@ __device__ __forceinline__ void loop_conv(const float* __restrict__ in, const ui
       if (elect_one()) umma_commit(&dFull[buf]);
     }
     __syncwarp();
-  } else if (warp >= 4 && warp < 8) {
-    // ---- epilogue warps: quadrant dl = warp - 4; out[oc][m] = sum_dl D[dl][oc][m + dl] -------------------------------
-    const int dl = warp - 4, et = tid - 128;
-    const int oc = et >> 2, jq = et & 3;
-    float sK = 0.f, s1 = 0.f, s2 = 0.f;
-    int sn = 0;
-    float* outc = out + (size_t)b * bs + (size_t)oc * H * W;
-    int blk = 0;
-#pragma unroll 1
-    for (int c = 0; c < T2_NCH; ++c) {
-      const int buf = c & 1;
-      mbar_wait(&dFull[buf], (uint32_t)((c >> 1) & 1) ^ (buf ? p01 : 0u));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nb = t2_chunk_blocks(c);
-#pragma unroll 1
-      for (int kb = 0; kb < nb; ++kb, ++blk) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(dl * 32) << 16) + (uint32_t)(buf * T2_DBUF + kb * 32 + dl), v);   // lane = oc
-        float* pw = sPart + (size_t)(blk & 1) * (T2_PART / 4) + (size_t)(dl * C + lane) * T2_PP;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(pw + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-        if (kb == nb - 1) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&dEmpty[buf]);
-        }
-        named_bar_sync(1, 128);
-        const float* pr = sPart + (size_t)(blk & 1) * (T2_PART / 4) + (size_t)oc * T2_PP + 8 * jq;
-        float o[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 p0 = *reinterpret_cast<const float4*>(pr + 4 * h), p1 = *reinterpret_cast<const float4*>(pr + C * T2_PP + 4 * h);
-          const float4 p2 = *reinterpret_cast<const float4*>(pr + 2 * C * T2_PP + 4 * h), p3 = *reinterpret_cast<const float4*>(pr + 3 * C * T2_PP + 4 * h);
-          o[4 * h + 0] = (p0.x + p1.x) + (p2.x + p3.x);
-          o[4 * h + 1] = (p0.y + p1.y) + (p2.y + p3.y);
-          o[4 * h + 2] = (p0.z + p1.z) + (p2.z + p3.z);
-          o[4 * h + 3] = (p0.w + p1.w) + (p2.w + p3.w);
-        }
-        const int m0 = t2_chunk_start(c) + kb * 32 + 8 * jq;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int m = m0 + 2 * u, r = m / T2_WP, col = m - r * T2_WP;
-          if (r < T2_TH && col < T2_TW) {
-            *reinterpret_cast<float2*>(outc + (size_t)(y0 + r) * W + x0 + col) = make_float2(o[2 * u], o[2 * u + 1]);
-            if (sn == 0) sK = o[2 * u];
-            const float d0 = o[2 * u] - sK, d1 = o[2 * u + 1] - sK;
-            s1 += d0 + d1;
-            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-            sn += 2;
-          }
-        }
-      }
-    }
-    // per-thread (n, mean, M2) -> Chan merge over the 4 threads of a channel -> per-CTA partial (mean, M2) of 16x32 outputs
-    float n = (float)sn, mean = sn ? sK + s1 / n : 0.f, m2 = sn ? fmaxf(s2 - s1 * s1 / n, 0.f) : 0.f;
-#pragma unroll
-    for (int off = 1; off <= 2; off <<= 1) {
-      const float n2 = __shfl_xor_sync(0xffffffffu, n, off), mean2 = __shfl_xor_sync(0xffffffffu, mean, off);
-      const float m22 = __shfl_xor_sync(0xffffffffu, m2, off);
-      const float nt = n + n2, dlt = mean2 - mean;
-      if (nt > 0.f) {
-        m2 = m2 + m22 + dlt * dlt * (n * n2 / nt);
-        mean = mean + dlt * (n2 / nt);
-      }
-      n = nt;
-    }
-    if (jq == 0) {
-      float* dstp = part + ((size_t)cta * C + oc) * 2;
-      dstp[0] = mean;
-      dstp[1] = m2;
-    }
+  } else if (warp >= 4 && warp < 4 + T2_EPI_WARPS) {
+    // ---- epilogue: two groups of four warps drain alternate 32-pixel blocks (t2_epilogue, ptk_conv_tc2.cuh) --------------------
+    const T2Epi e{out + (size_t)b * bs, H, W, x0, y0, 0, part + (size_t)cta * C * 2};
+    t2_epilogue(e, tmem_base, sPart, sMerge, dFull, dEmpty, p01, warp - 4, lane);
   }
   // every asynchronous operation of this convolution has completed once the epilogue warps are through (they waited for the
   // last accumulator commit, which follows every ring commit); the caller's next barrier releases the region to the point-wise view

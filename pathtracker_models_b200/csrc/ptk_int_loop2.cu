@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) int_loop2_kernel(IntDev d, Loop
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_NST + 6);
   uint64_t* gbar = bars + 2 * T2_NST + 8;              // gate MMAs complete
   uint64_t* wbar = gbar + 1;                           // gate matrices landed
-  __shared__ __align__(16) float sWp[C * 3], sbp[C], sbi[C], sbe[C], sba[C], sAl[C], sMu[C], sKa[C], sGa[C], sWr[C], sScale[C], sShift[C];
+  __shared__ __align__(16) float sWp[C * 3], sbp[C], sbi[C], sbe[C], sba[C], sAl[C], sMu[C], sKa[C], sGa[C], sWr[C], sScale[C], sShift[C], sMerge[C * 4];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) int_loop2_kernel(IntDev d, Loop
     uint64_t* dEmpty = dFull + 2;
     for (int i = 0; i < T2_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&dFull[0], 1); mbar_init(&dFull[1], 1);
-    mbar_init(&dEmpty[0], 4); mbar_init(&dEmpty[1], 4);
+    mbar_init(&dEmpty[0], T2_EPI_WARPS); mbar_init(&dEmpty[1], T2_EPI_WARPS);
     mbar_init(dEmpty + 2, LP_THREADS); mbar_init(dEmpty + 3, LP_THREADS - 64);
     mbar_init(gbar, 1); mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) int_loop2_kernel(IntDev d, Loop
   for (int t = 0; t < d.T; ++t) {
     // ================= conv0: Ge_t -> Y0_t ==================================================================================
     loop_conv<SINGLE>(d.Ge, reinterpret_cast<const uint8_t*>(d.w_inh_f), d.Y0_at(t), la.part[0], cta, H, W, x0, y0, b, smem_raw,
-                      tmem_base, 0u, t > 0);
+                      sMerge, tmem_base, 0u, t > 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     LP_STAMP(0);
     cta_arrive(la.gctr);
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) int_loop2_kernel(IntDev d, Loop
     LP_STAMP(6);
     // ================= conv1: I_{t+1} -> Y1_t ==============================================================================
     loop_conv<SINGLE>(d.I_at(t + 1), reinterpret_cast<const uint8_t*>(d.w_exc_f), d.Y1_at(t), la.part[1], cta, H, W, x0, y0, b,
-                      smem_raw, tmem_base, 1u, true);
+                      smem_raw, sMerge, tmem_base, 1u, true);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     LP_STAMP(7);
     cta_arrive(la.gctr);
