@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libptk_b200.so")
-SOURCES = ["ptk_api.cu", "ptk_conv.cu", "ptk_conv_tc.cu", "ptk_conv_tc2.cu", "ptk_wgrad_tc.cu", "ptk_wgrad_ts.cu", "ptk_int_fwd.cu", "ptk_int_loop.cu", "ptk_int_loop2.cu", "ptk_int_bwd.cu", "ptk_synth.cu", "ptk_convlstm.cu", "ptk_profile.cu", "ptk_optim.cu", "ptk_gru.cu", "ptk_convk_tc.cu", "ptk_wgradk_tc.cu"]
+SOURCES = ["ptk_api.cu", "ptk_conv.cu", "ptk_conv_tc.cu", "ptk_conv_tc2.cu", "ptk_wgrad_tc.cu", "ptk_wgrad_ts.cu", "ptk_int_fwd.cu", "ptk_int_loop.cu", "ptk_int_loop2.cu", "ptk_int_bwd.cu", "ptk_gate_wgrad_tc.cu", "ptk_synth.cu", "ptk_convlstm.cu", "ptk_profile.cu", "ptk_optim.cu", "ptk_gru.cu", "ptk_convk_tc.cu", "ptk_wgradk_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

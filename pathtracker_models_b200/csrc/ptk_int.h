@@ -103,6 +103,8 @@ int run_int_backward(const IntDev& d, int cell, int act, cudaStream_t st);
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st);
 int pw_grid(int B, int H, int W);
+// gate weight gradients of all steps on tcgen05 (ptk_gate_wgrad_tc.cu); returns the number of gacc slots written or < 0
+int launch_gate_wgrad_tc(const IntDev& d, int cell, int nT, cudaStream_t st);
 // persistent forward time loop (ptk_int_loop.cu): one cooperative kernel for all frames
 int int_loop_mode();                   // PTK_FWD_LOOP: 0 = per-phase PDL chain, 1 = the chain's phases in one cooperative kernel
                                        // (bit-identical), 2 = second generation (tcgen05 gate products, thread = pixel)

@@ -1677,9 +1677,18 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       PTK_LAUNCH_OK("gate_wgrad_kernel");
     }
   }
+  int gate_slots = gate_grid;
   if (tc) {   // the six gate weight gradients of ALL steps in one launch
     ProfileScope ps(PTK_PROF_GATE_WGRAD, st);
-    PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, true>, dim3(gate_grid), dim3(384), SM_GATE, st, d, 0, d.T, 1));
+    // tcgen05 version (ptk_gate_wgrad_tc.cu: one GEMM per 16 pixels, HBM-bound) or the mma.sync tf32 version (PTK_GATE_WGRAD_TC=0)
+    static const bool gw_tc = [] { const char* e = getenv("PTK_GATE_WGRAD_TC"); return !(e && e[0] == '0'); }();
+    if (gw_tc) {
+      gate_slots = launch_gate_wgrad_tc(d, CELL, d.T, st);
+      if (gate_slots < 0) return PTK_ECUDA;
+    } else {
+      PTK_CUDA_OK(launch_pdl(true, gate_wgrad_kernel<CELL, true>, dim3(gate_grid), dim3(384), SM_GATE, st, d, 0, d.T, 1));
+      gate_slots = 2 * gate_grid;
+    }
     PTK_LAUNCH_OK("gate_wgrad_kernel");
   }
   if (tc) {
@@ -1696,7 +1705,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     }
   }
   FinalizeArgs f;
-  f.pw_ctas = PW_EW_CTAS; f.gate_ctas = tc ? 2 * gate_grid : gate_grid; f.B = d.B; f.wgroups = WGRAD_GROUPS;
+  f.pw_ctas = PW_EW_CTAS; f.gate_ctas = gate_slots; f.B = d.B; f.wgroups = WGRAD_GROUPS;
   f.wgrad_tc = tc ? wgrad_ts_ctas(d.T, d.B, d.H, d.W) : 0;
   const ParamOffsets po = param_offsets(C, KS);
   for (int i = 0; i <= PTK_INT_NPARAM; ++i) f.off[i] = po.o[i];
