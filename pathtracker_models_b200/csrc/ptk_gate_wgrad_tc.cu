@@ -15,6 +15,7 @@
 // Accumulation is two-level, as in the mma.sync version: a TMEM buffer holds one time step's sum, three flush warps retire it into
 // fp32 running totals in registers while the next step accumulates in the second buffer (one long chain over all steps lost 1e-4
 // on the hGRU gate gradients at T = 64).  Persistent CTAs, one per SM; slots folded in fp64 by int_finalize (deterministic).
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "ptk_int.h"
@@ -22,28 +23,45 @@
 
 namespace ptk {
 
-constexpr int GW_THREADS = 384;                 // warp 0: MMA issuer; warps 4-6: flush (TMEM quadrants 0-2); the other 8: producers
-constexpr int GW_PX = 64;                       // pixels per stage
+constexpr int GW_THREADS = 512;                 // warp 0: MMA issuer; warps 4-6: flush (TMEM quadrants 0-2); the other 12: converters
+constexpr int GW_NCONV = 12;
+constexpr int GW_PX = 32;                       // pixels per tile (= per stage)
 constexpr int GW_KC = GW_PX / 8;                // 8-pixel chunks per stage
 constexpr int GW_MA = 128, GW_NB = 144;
-constexpr int GW_PLANE_A = GW_MA * 16 + 16;     // +16: the 8 chunk lanes of a quarter warp hit 8 bank groups
+constexpr int GW_PLANE_A = GW_MA * 16 + 16;     // +16: the chunk lanes of a quarter warp hit different bank groups
 constexpr int GW_PLANE_B = GW_NB * 16 + 16;
-constexpr int GW_LO_A = GW_KC * GW_PLANE_A + 64;     // lo planes follow the hi planes, skewed by 64 B: a hi / lo lane pair of the same chunk
-constexpr int GW_LO_B = GW_KC * GW_PLANE_B + 64;     // then hits different bank groups
+constexpr int GW_SKEW = (64 + 128 - (GW_KC * 16) % 128) % 128;   // lo planes follow the hi planes at an offset = 64 (mod 128): a hi / lo
+constexpr int GW_LO_A = GW_KC * GW_PLANE_A + GW_SKEW;           // lane pair of the same chunk then hits different bank groups
+constexpr int GW_LO_B = GW_KC * GW_PLANE_B + GW_SKEW;
+static_assert(GW_LO_A % 128 == 64 && GW_LO_B % 128 == 64, "bank skew");
 constexpr int GW_A_BYTES = GW_LO_A + GW_KC * GW_PLANE_A + 64;
 constexpr int GW_B_BYTES = GW_LO_B + GW_KC * GW_PLANE_B + 64;
-constexpr int GW_STAGE = GW_A_BYTES + GW_B_BYTES;
-constexpr int GW_NST = 3;
-constexpr int GW_SMEM = GW_NST * GW_STAGE + 256;
+constexpr int GW_OP_STAGE = GW_A_BYTES + GW_B_BYTES;  // one operand stage (bf16 hi/lo chunk planes)
+constexpr int GW_NOP = 2;
+constexpr int GW_RAW_STAGE = 7 * C * GW_PX * 4;       // one raw stage: [7 tensors][32 ch][32 px] fp32, rows of 128 B
+constexpr int GW_NRAW = 5;                            // four tiles in flight while one is converted
+constexpr int GW_OP0 = GW_NRAW * GW_RAW_STAGE;
+constexpr int GW_BARS = GW_OP0 + GW_NOP * GW_OP_STAGE;
+constexpr int GW_SMEM = GW_BARS + 256;
 constexpr int GW_DCOLS = 160;                   // TMEM columns per accumulator buffer (144 used)
 
+// the seven operand tensors as 2-D tensor maps [rows = (t, b, c)][P pixels] (fp32, box = 32 channels x 32 pixels): order ge, gi, a, S, Ge, X, E
+struct GwMaps { CUtensorMap m[7]; };
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int CELL>
-__global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, int nT) {
+__global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, int nT, const __grid_constant__ GwMaps maps) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + GW_NST * GW_STAGE);
-  uint64_t* full = bars;                        // [GW_NST] stage filled (8 producer warps)
-  uint64_t* empty = bars + GW_NST;              // [GW_NST] stage consumed (tcgen05.commit)
-  uint64_t* dFull = bars + 2 * GW_NST;          // [2] a time step's sum is complete
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + GW_BARS);
+  uint64_t* rawFull = bars;                     // [GW_NRAW] raw tile landed (bulk copies, tx count)
+  uint64_t* rawEmpty = rawFull + GW_NRAW;       // [GW_NRAW] ... and converted by all converter warps
+  uint64_t* opFull = rawEmpty + GW_NRAW;        // [GW_NOP] operand stage written (all converter warps)
+  uint64_t* opEmpty = opFull + GW_NOP;          // [GW_NOP] ... and consumed (tcgen05.commit)
+  uint64_t* dFull = opEmpty + GW_NOP;           // [2] a time step's sum is complete
   uint64_t* dEmpty = dFull + 2;                 // [2] ... and has been retired (3 flush warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dEmpty + 2);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -51,7 +69,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
   const int P = d.H * d.W, tpi = P / GW_PX, perT = d.B * tpi, nTiles = nT * perT;
 
   if (tid == 0) {
-    for (int i = 0; i < GW_NST; ++i) { mbar_init(&full[i], 8); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < GW_NRAW; ++i) { mbar_init(&rawFull[i], 1); mbar_init(&rawEmpty[i], GW_NCONV); }
+    for (int i = 0; i < GW_NOP; ++i) { mbar_init(&opFull[i], GW_NCONV); mbar_init(&opEmpty[i], 1); }
     mbar_init(&dFull[0], 1); mbar_init(&dFull[1], 1);
     mbar_init(&dEmpty[0], 3); mbar_init(&dEmpty[1], 3);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -60,12 +79,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // rows the producers never write: A rows 96-127 and B rows 129-143 stay zero, B row 128 is the bias column (ones)
-  for (int i = tid; i < GW_NST * GW_STAGE / 16; i += GW_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
+  // rows the converters never write: A rows 96-127 and B rows 129-143 stay zero, B row 128 is the bias column (ones)
+  for (int i = tid; i < GW_NOP * GW_OP_STAGE / 16; i += GW_THREADS) reinterpret_cast<uint4*>(smem_raw + GW_OP0)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  if (tid < GW_NST * GW_KC) {
+  if (tid < GW_NOP * GW_KC) {
     const int st = tid / GW_KC, kc = tid % GW_KC;
-    *reinterpret_cast<uint4*>(smem_raw + (size_t)st * GW_STAGE + GW_A_BYTES + kc * GW_PLANE_B + 128 * 16) =
+    *reinterpret_cast<uint4*>(smem_raw + GW_OP0 + (size_t)st * GW_OP_STAGE + GW_A_BYTES + kc * GW_PLANE_B + 128 * 16) =
         make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -81,7 +100,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
     const uint64_t dA0 = umma_desc(0, GW_PLANE_A, 128), dB0 = umma_desc(0, GW_PLANE_B, 128);
     const uint32_t aW = (uint32_t)(dA0 >> 32), bW = (uint32_t)(dB0 >> 32);
     const uint32_t idesc = umma_idesc(GW_NB);
-    const uint32_t sbase = smem_u32(smem_raw);
+    const uint32_t sbase = smem_u32(smem_raw + GW_OP0);
     int it = 0, ev = 0, t_cur = -1;
     bool fresh = true;
     for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
@@ -99,10 +118,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
         t_cur = t;
         fresh = true;
       }
-      const int st = it % GW_NST;
-      mbar_wait(&full[st], (uint32_t)((it / GW_NST) & 1));
+      const int st = it % GW_NOP;
+      mbar_wait(&opFull[st], (uint32_t)((it / GW_NOP) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t aH0 = sbase + (uint32_t)st * GW_STAGE, bH0 = aH0 + GW_A_BYTES;
+      const uint32_t aH0 = sbase + (uint32_t)st * GW_OP_STAGE, bH0 = aH0 + GW_A_BYTES;
       const uint32_t dcol = tmem_base + (uint32_t)((ev & 1) * GW_DCOLS);
 #pragma unroll
       for (int ks = 0; ks < GW_PX / 16; ++ks) {
@@ -120,7 +139,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
       }
       fresh = false;
       __syncwarp();
-      if (elect_one()) umma_commit(&empty[st]);
+      if (elect_one()) umma_commit(&opEmpty[st]);
     }
     __syncwarp();
     if (t_cur >= 0 && elect_one()) umma_commit(&dFull[ev & 1]);
@@ -169,64 +188,64 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
     }
     ga[GACC_BE + q * C + lane] = btot;
   } else {
-    // ---- producers: fp32 rows -> bf16 hi/lo chunk planes.  warp-item = (tensor k, 4 channels) = two load instructions of two full
-    // 256-byte rows each (lane = 4 pixels of one row: every 32-byte sector is used whole).  A 16-byte unit of the operand planes is
-    // 8 pixels, so a lane pair exchanges halves: the even lane stores the pair's hi unit, the odd lane the lo unit.
-    const int pw = warp < 4 ? warp - 1 : warp - 4;            // 0..7
-    const int px4 = lane & 15, rsel = lane >> 4, kc = px4 >> 1;
-    const bool odd = (lane & 1) != 0;
-    auto load_tile = [&](float4 (&v)[7][2], int tile) {
-      const int t = tile / perT, tile_t = tile - t * perT;
-      const int b = tile_t / tpi, pix_base = (tile_t - b * tpi) * GW_PX;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int item = pw * 7 + j, k = item >> 3, c0 = (item & 7) * 4 + rsel;
-        const float* sp = k == 0 ? d.geb_at(t) : k == 1 ? d.gi_at(t) : k == 2 ? d.a_at(t)
-                        : k == 3 ? ((CELL == PTK_CELL_INT) ? d.I_at(t) : (CELL == PTK_CELL_HGRU ? d.A_at(t) : d.E_at(t)))
-                        : k == 4 ? d.GeB_at(t) : k == 5 ? d.X_at(t) : d.E_at(t);
-        const float* src = sp + ((size_t)b * C + c0) * P + pix_base + px4 * 4;
-        v[j][0] = __ldcs(reinterpret_cast<const float4*>(src));                      // channel c0
-        v[j][1] = __ldcs(reinterpret_cast<const float4*>(src + (size_t)2 * P));      // channel c0 + 2
+    // ---- loaders + converters.  Raw fp32 tiles arrive by TMA: ONE cp.async.bulk.tensor per operand tensor and tile (a 32-channel x
+    // 32-pixel box of the [rows][P] tensor map), no registers held, four tiles in flight per SM.  (Measured alternatives: LDG-fed
+    // registers hold one tile, 1.25 ms, one load latency per tile; one cp.async.bulk per 128-byte row is bound by the TMA issue rate,
+    // ~20 cycles per copy, 2.07 ms -- as the mma.sync version's 256-byte row copies were.)  Conversion: a warp owns 8 channels of 3 (or 2)
+    // tensors; lane = (channel, 8-pixel chunk): 32 bytes of fp32 in, one hi and one lo 16-byte unit of the operand planes out.
+    const int pw = warp < 4 ? warp - 1 : warp - 4;            // 0..11
+    const int kc = lane & 3, r8 = lane >> 2;                  // 8-pixel chunk of the tile, row inside the warp's 8-row group
+    const int row = (pw & 3) * 8 + r8;                        // converters 0-3: tensors 0, 3, 6; 4-7: tensors 1, 4; 8-11: tensors 2, 5; 8 channels each
+    constexpr int AHEAD = GW_NRAW - 1;                         // tiles in flight; the slot of tile it + AHEAD is the one tile it - 1 used
+    // Every converter warp waits for the slot (= for all warps to be through with tile it - 1), converter 0 issues: keeping the
+    // warps in step was measured faster (1.00 ms) than letting them run ahead of each other (1.05 ms: a warp that is a tile ahead
+    // takes issue slots from the ones the MMA warp is waiting for).
+    auto issue = [&](int tile, int j) {                        // j = sequence number of the tile in this CTA
+      const int slot = j % GW_NRAW;
+      if (j >= GW_NRAW) mbar_wait(&rawEmpty[slot], (uint32_t)(((j / GW_NRAW) - 1) & 1));
+      if (pw == 0 && lane < 7) {                                          // one tensor-map copy per operand tensor: [32 channels][32 pixels]
+        const int t = tile / perT, tile_t = tile - t * perT;
+        const int b = tile_t / tpi, pix_base = (tile_t - b * tpi) * GW_PX;
+        if (lane == 0) mbar_expect_tx(&rawFull[slot], GW_RAW_STAGE);
+        __syncwarp(0x7fu);
+        tma_load_2d(smem_raw + (size_t)slot * GW_RAW_STAGE + lane * (C * GW_PX * 4), &maps.m[lane], pix_base, (t * d.B + b) * C, &rawFull[slot]);
       }
     };
-    auto store_tile = [&](const float4 (&v)[7][2], int it) {
-      const int st = it % GW_NST;
-      if (it >= GW_NST) mbar_wait(&empty[st], (uint32_t)(((it / GW_NST) - 1) & 1));
-      uint8_t* sa = smem_raw + (size_t)st * GW_STAGE;
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int item = pw * 7 + j, k = item >> 3, c0 = (item & 7) * 4 + rsel;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float f[4] = {v[j][h].x, v[j][h].y, v[j][h].z, v[j][h].w};
-          uint32_t hi[2], lo[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * e]), h1 = __float2bfloat16_rn(f[2 * e + 1]);
-            hi[e] = pack_bf16x2(h0, h1);
-            lo[e] = pack_bf16x2(__float2bfloat16_rn(f[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(f[2 * e + 1] - __bfloat162float(h1)));
-          }
-          // even lane: keeps hi, receives the partner's hi;  odd lane: keeps lo, receives the partner's lo
-          const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? hi[0] : lo[0], 1);
-          const uint32_t r1 = __shfl_xor_sync(0xffffffffu, odd ? hi[1] : lo[1], 1);
-          const uint4 unit = odd ? make_uint4(r0, r1, lo[0], lo[1]) : make_uint4(hi[0], hi[1], r0, r1);
-          const int row = c0 + 2 * h;
-          uint8_t* dst = k < 3 ? sa + kc * GW_PLANE_A + (k * 32 + row) * 16 + (odd ? GW_LO_A : 0)
-                               : sa + GW_A_BYTES + kc * GW_PLANE_B + ((k - 3) * 32 + row) * 16 + (odd ? GW_LO_B : 0);
-          *reinterpret_cast<uint4*>(dst) = unit;
-        }
+    const int G = gridDim.x;
+    for (int j = 0; j < AHEAD; ++j)
+      if ((int)blockIdx.x + j * G < nTiles) issue(blockIdx.x + j * G, j);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < nTiles; tile += G, ++it) {
+      if (tile + AHEAD * G < nTiles) issue(tile + AHEAD * G, it + AHEAD);
+      const int slot = it % GW_NRAW, st = it % GW_NOP;
+      mbar_wait(&rawFull[slot], (uint32_t)((it / GW_NRAW) & 1));
+      if (it >= GW_NOP) mbar_wait(&opEmpty[st], (uint32_t)(((it / GW_NOP) - 1) & 1));
+      const uint8_t* raw = smem_raw + (size_t)slot * GW_RAW_STAGE + row * (GW_PX * 4) + kc * 32;
+      uint8_t* sa = smem_raw + GW_OP0 + (size_t)st * GW_OP_STAGE;
+      // lane = (row, 8-pixel chunk): 32 bytes in, one hi and one lo 16-byte unit out; the tensor index is a compile-time constant
+#define GW_CONVERT(K)                                                                                                        \
+      {                                                                                                                      \
+        const float4 a4 = *reinterpret_cast<const float4*>(raw + (K) * (C * GW_PX * 4));                                      \
+        const float4 b4 = *reinterpret_cast<const float4*>(raw + (K) * (C * GW_PX * 4) + 16);                                 \
+        const float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};                                                  \
+        uint32_t hi[4], lo[4];                                                                                               \
+        _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                                      \
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * e]), h1 = __float2bfloat16_rn(f[2 * e + 1]);                     \
+          hi[e] = pack_bf16x2(h0, h1);                                                                                       \
+          lo[e] = pack_bf16x2(__float2bfloat16_rn(f[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(f[2 * e + 1] - __bfloat162float(h1))); \
+        }                                                                                                                    \
+        uint8_t* dst = (K) < 3 ? sa + kc * GW_PLANE_A + ((K) * 32 + row) * 16                                                 \
+                               : sa + GW_A_BYTES + kc * GW_PLANE_B + (((K) - 3) * 32 + row) * 16;                             \
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);                                             \
+        *reinterpret_cast<uint4*>(dst + ((K) < 3 ? GW_LO_A : GW_LO_B)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);             \
       }
+      if (pw < 4) { GW_CONVERT(0) GW_CONVERT(3) GW_CONVERT(6) }
+      else if (pw < 8) { GW_CONVERT(1) GW_CONVERT(4) }
+      else { GW_CONVERT(2) GW_CONVERT(5) }
+#undef GW_CONVERT
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[st]);
-    };
-    // One register set: a second set with the next tile's loads in flight during the conversion was measured SLOWER (1.44 vs 1.25 ms
-    // at the headline shape); the kernel sits at ~3.0 TB/s of operand traffic like its mma.sync predecessor.
-    float4 v0[7][2];
-    int it = 0;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
-      load_tile(v0, tile);
-      store_tile(v0, it);
+      if (lane == 0) { mbar_arrive(&opFull[st]); mbar_arrive(&rawEmpty[slot]); }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -235,17 +254,51 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
 }
 
 // returns the number of accumulator slots written (one per CTA) or a negative error code
+typedef CUresult (*PtkEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PtkEncodeTiled encode_tiled_fn() {
+  static PtkEncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (PtkEncodeTiled)p;
+  }();
+  return fn;
+}
+static bool make_map(CUtensorMap* m, const float* base, long long rows, int P) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)P, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)P * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)GW_PX, (cuuint32_t)C};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 template <int CELL>
-static cudaError_t launch_gw(const IntDev& d, int nT, int grid, cudaStream_t st) {
+static cudaError_t launch_gw(const IntDev& d, int nT, int grid, const GwMaps& maps, cudaStream_t st) {
   cudaError_t e = ptk_func_smem(gate_wgrad_tc_kernel<CELL>, GW_SMEM);
-  if (e == cudaSuccess) e = launch_pdl(true, gate_wgrad_tc_kernel<CELL>, dim3(grid), dim3(GW_THREADS), GW_SMEM, st, d, nT);
+  if (e == cudaSuccess) e = launch_pdl(true, gate_wgrad_tc_kernel<CELL>, dim3(grid), dim3(GW_THREADS), GW_SMEM, st, d, nT, maps);
   return e;
 }
 int launch_gate_wgrad_tc(const IntDev& d, int cell, int nT, cudaStream_t st) {
-  const long long tiles = (long long)nT * d.B * (d.H * d.W / GW_PX);
+  const int P = d.H * d.W;
+  const long long tiles = (long long)nT * d.B * (P / GW_PX);
   const int grid = tiles < GATE_CTAS ? (int)tiles : GATE_CTAS;
-  const cudaError_t e = cell == PTK_CELL_INT ? launch_gw<PTK_CELL_INT>(d, nT, grid, st)
-                      : cell == PTK_CELL_HGRU ? launch_gw<PTK_CELL_HGRU>(d, nT, grid, st) : launch_gw<2>(d, nT, grid, st);
+  if (!encode_tiled_fn()) { set_error("gate_wgrad_tc: cuTensorMapEncodeTiled not available from the driver"); return -1; }
+  if (d.dy_tstride != (size_t)d.B * C * P || d.ck_stride != (size_t)d.B * C * P || (cell == PTK_CELL_HGRU && d.a_tstride != (long long)d.B * C * P)) {
+    set_error("gate_wgrad_tc: per-step operand tensors are not laid out [T][B,C,P]");
+    return -1;
+  }
+  // operand tensors of all steps are contiguous [T (or T+1)][B][C][P]: row (t, b, c) of a [rows][P] matrix
+  const long long rT = (long long)nT * d.B * C, rT1 = (long long)(nT + 1) * d.B * C;
+  const float* S = cell == PTK_CELL_INT ? d.I_at(0) : (cell == PTK_CELL_HGRU ? d.A_at(0) : d.E_at(0));
+  const long long rS = cell == PTK_CELL_HGRU ? rT : rT1;
+  GwMaps maps;
+  const bool ok = make_map(&maps.m[0], d.geb_at(0), rT, P) && make_map(&maps.m[1], d.gi_at(0), rT, P) && make_map(&maps.m[2], d.a_at(0), rT, P) &&
+                  make_map(&maps.m[3], S, rS, P) && make_map(&maps.m[4], d.GeB_at(0), rT, P) && make_map(&maps.m[5], d.X_at(0), rT, P) &&
+                  make_map(&maps.m[6], d.E_at(0), rT1, P);
+  if (!ok) { set_error("gate_wgrad_tc: cuTensorMapEncodeTiled failed"); return -1; }
+  const cudaError_t e = cell == PTK_CELL_INT ? launch_gw<PTK_CELL_INT>(d, nT, grid, maps, st)
+                      : cell == PTK_CELL_HGRU ? launch_gw<PTK_CELL_HGRU>(d, nT, grid, maps, st) : launch_gw<2>(d, nT, grid, maps, st);
   if (e != cudaSuccess) {
     set_error("gate_wgrad_tc_kernel launch failed: %s", cudaGetErrorString(e));
     return -1;

@@ -1,7 +1,7 @@
 # tcgen05 gate weight gradient: parity suite, then A/B of the producer pipelining and the mma.sync version
 TAG=${1:-r3j}
 python -m pytest tests/test_parity_gpu.py -q --timeout 900 -x > gpurun_out/${TAG}_parity.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_parity.log; tail -3 gpurun_out/${TAG}_parity.log
-for V in "PTK_GW_PIPE=1" "PTK_GW_PIPE=0" "PTK_GATE_WGRAD_TC=0"; do
+for V in "PTK_GATE_WGRAD_TC=1" "PTK_GATE_WGRAD_TC=0"; do
   env $V python bench.py --no-extra --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/${TAG}_bench_$V.log 2>&1
   python - "$V" "gpurun_out/${TAG}_bench_$V.log" <<PY
 import json, sys, re
