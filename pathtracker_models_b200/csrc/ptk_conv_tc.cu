@@ -148,9 +148,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float v0 = reinterpret_cast<const float*>(&v[r][2 * e])[px], v1 = reinterpret_cast<const float*>(&v[r][2 * e + 1])[px];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+          split_bf16x2(v0, v1, hi[e], lo[e]);
         }
         *reinterpret_cast<uint4*>(sA + q * TC_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(sA + 4 * TC_PLANE + q * TC_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -169,9 +167,7 @@ __global__ void __launch_bounds__(256, 1) conv7_tc_kernel(ConvArgs a) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float v0 = src[(size_t)(2 * e) * H * W], v1 = src[(size_t)(2 * e + 1) * H * W];
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        split_bf16x2(v0, v1, hi[e], lo[e]);
       }
       const int p = r * TC_WP + c;
       *reinterpret_cast<uint4*>(sA + q * TC_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -199,11 +199,7 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float v0 = reinterpret_cast<const float*>(&v[2 * e])[px], v1 = reinterpret_cast<const float*>(&v[2 * e + 1])[px];
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v0, h0, l0);
-            split_bf16(v1, h1, l1);
-            hi[e] = pack_bf16x2(h0, h1);
-            lo[e] = pack_bf16x2(l0, l1);
+            split_bf16x2(v0, v1, hi[e], lo[e]);
           }
           *reinterpret_cast<uint4*>(sA + q * K::PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sA + 4 * K::PLANE + q * K::PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -221,11 +217,7 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
           float v0 = 0.f, v1 = 0.f;
           if (ok && ch0 + 2 * e < a.Cin) v0 = inb[(size_t)(ch0 + 2 * e) * HW + (size_t)gy * W + gx];
           if (ok && ch0 + 2 * e + 1 < a.Cin) v1 = inb[(size_t)(ch0 + 2 * e + 1) * HW + (size_t)gy * W + gx];
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v0, h0, l0);
-          split_bf16(v1, h1, l1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(l0, l1);
+          split_bf16x2(v0, v1, hi[e], lo[e]);
         }
         const int p = row * K::WP + c;
         *reinterpret_cast<uint4*>(sA + q * K::PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

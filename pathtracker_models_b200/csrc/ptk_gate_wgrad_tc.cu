@@ -37,9 +37,9 @@ static_assert(GW_LO_A % 128 == 64 && GW_LO_B % 128 == 64, "bank skew");
 constexpr int GW_A_BYTES = GW_LO_A + GW_KC * GW_PLANE_A + 64;
 constexpr int GW_B_BYTES = GW_LO_B + GW_KC * GW_PLANE_B + 64;
 constexpr int GW_OP_STAGE = GW_A_BYTES + GW_B_BYTES;  // one operand stage (bf16 hi/lo chunk planes)
-constexpr int GW_NOP = 2;
+constexpr int GW_NOP = 3;
 constexpr int GW_RAW_STAGE = 7 * C * GW_PX * 4;       // one raw stage: [7 tensors][32 ch][32 px] fp32, rows of 128 B
-constexpr int GW_NRAW = 5;                            // four tiles in flight while one is converted
+constexpr int GW_NRAW = 4;                            // four tiles in flight while one is converted
 constexpr int GW_OP0 = GW_NRAW * GW_RAW_STAGE;
 constexpr int GW_BARS = GW_OP0 + GW_NOP * GW_OP_STAGE;
 constexpr int GW_SMEM = GW_BARS + 256;
@@ -230,9 +230,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gate_wgrad_tc_kernel(IntDev d, 
         const float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};                                                  \
         uint32_t hi[4], lo[4];                                                                                               \
         _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                                      \
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * e]), h1 = __float2bfloat16_rn(f[2 * e + 1]);                     \
-          hi[e] = pack_bf16x2(h0, h1);                                                                                       \
-          lo[e] = pack_bf16x2(__float2bfloat16_rn(f[2 * e] - __bfloat162float(h0)), __float2bfloat16_rn(f[2 * e + 1] - __bfloat162float(h1))); \
+          split_bf16x2(f[2 * e], f[2 * e + 1], hi[e], lo[e]); \
         }                                                                                                                    \
         uint8_t* dst = (K) < 3 ? sa + kc * GW_PLANE_A + ((K) * 32 + row) * 16                                                 \
                                : sa + GW_A_BYTES + kc * GW_PLANE_B + (((K) - 3) * 32 + row) * 16;                             \

@@ -165,9 +165,7 @@ __device__ __forceinline__ void loop_conv(const float* __restrict__ in, const ui
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float v0 = reinterpret_cast<const float*>(&v[2 * e])[px], v1 = reinterpret_cast<const float*>(&v[2 * e + 1])[px];
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        split_bf16x2(v0, v1, hi[e], lo[e]);
       }
       *reinterpret_cast<uint4*>(sA + q * T2_PLANE + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(sA + 4 * T2_PLANE + q * T2_PLANE + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -187,9 +185,7 @@ __device__ __forceinline__ void loop_conv(const float* __restrict__ in, const ui
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float v0 = __ldcg(src + (size_t)(2 * e) * H * W), v1 = __ldcg(src + (size_t)(2 * e + 1) * H * W);
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        split_bf16x2(v0, v1, hi[e], lo[e]);
       }
       const int p = r * T2_WP + c;
       *reinterpret_cast<uint4*>(sA + q * T2_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

@@ -65,9 +65,7 @@ __device__ __forceinline__ void stage_px(uint8_t* img, const float (&v)[32], int
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float v0 = v[q * 8 + 2 * e], v1 = v[q * 8 + 2 * e + 1];
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-      hi[e] = pack_bf16x2(h0, h1);
-      lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+      split_bf16x2(v0, v1, hi[e], lo[e]);
     }
     *reinterpret_cast<uint4*>(img + q * G_PLANE + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(img + (4 + q) * G_PLANE + p * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -79,9 +77,7 @@ __device__ __forceinline__ void stage_px_conv(uint8_t* sA, const float (&v)[8], 
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float v0 = v[2 * e], v1 = v[2 * e + 1];
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-    hi[e] = pack_bf16x2(h0, h1);
-    lo[e] = pack_bf16x2(__float2bfloat16_rn(v0 - __bfloat162float(h0)), __float2bfloat16_rn(v1 - __bfloat162float(h1)));
+    split_bf16x2(v0, v1, hi[e], lo[e]);
   }
   *reinterpret_cast<uint4*>(sA + q * T2_PLANE + pc * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(sA + (4 + q) * T2_PLANE + pc * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

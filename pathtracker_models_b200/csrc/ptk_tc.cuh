@@ -83,6 +83,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 }
 
 
+// two floats -> packed bf16x2 hi pair (round to nearest) and lo pair (hi + lo ~= v to 16 mantissa bits), first value in the low half.
+// Compiles to one F2FP.BF16.F32.PACK_AB per pair; the scalar __float2bfloat16_rn is an F2F.BF16.F32 on the 16-lane conversion
+// pipe -- 8x the issue cost per element, which is what bound the operand-staging loops.  Bit-identical results.
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);      // .x = v0 in the low half
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // fp32 -> (hi, lo) bf16 pair with hi + lo ~= v to 16 mantissa bits
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
   h = __float2bfloat16_rn(v);

@@ -77,11 +77,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(reinterpret_cast<const float*>(&v[r][2 * e])[px], h0, l0);
-          split_bf16(reinterpret_cast<const float*>(&v[r][2 * e + 1])[px], h1, l1);
-          hi[e] = pack_bf16x2(h0, h1);
-          lo[e] = pack_bf16x2(l0, l1);
+          split_bf16x2(reinterpret_cast<const float*>(&v[r][2 * e])[px], reinterpret_cast<const float*>(&v[r][2 * e + 1])[px], hi[e], lo[e]);
         }
         *reinterpret_cast<uint4*>(sHi + q * plane_bytes + (p + px) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(sLo + q * plane_bytes + (p + px) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -98,11 +94,7 @@ __device__ __forceinline__ void wt_stage(uint8_t* sHi, uint8_t* sLo, int plane_b
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(p0[(size_t)(2 * e) * H * W], h0, l0);
-        split_bf16(p0[(size_t)(2 * e + 1) * H * W], h1, l1);
-        hi[e] = pack_bf16x2(h0, h1);
-        lo[e] = pack_bf16x2(l0, l1);
+        split_bf16x2(p0[(size_t)(2 * e) * H * W], p0[(size_t)(2 * e + 1) * H * W], hi[e], lo[e]);
       }
       const int p = r * pitch + c;
       *reinterpret_cast<uint4*>(sHi + q * plane_bytes + p * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);

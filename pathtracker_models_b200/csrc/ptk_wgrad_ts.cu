@@ -151,11 +151,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad7_ts_kernel(WgradTsArgs a)
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[2 * e], h0, l0);
-              split_bf16(v[2 * e + 1], h1, l1);
-              hi[e] = pack_bf16x2(h0, h1);
-              lo[e] = pack_bf16x2(l0, l1);
+              split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
             }
             const int slot = inCount % TS_NI;
             if (inCount >= TS_NI) mbar_wait(&inEmpty[slot], (uint32_t)(((inCount / TS_NI) - 1) & 1));
@@ -178,11 +174,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad7_ts_kernel(WgradTsArgs a)
                 const float* ph = inT + ((size_t)(q * 8) * H + gy) * W + gx;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat16 h0, l0, h1, l1;
-                  split_bf16(__ldg(ph + (size_t)(2 * e) * plane), h0, l0);
-                  split_bf16(__ldg(ph + (size_t)(2 * e + 1) * plane), h1, l1);
-                  hh[e] = pack_bf16x2(h0, h1);
-                  ll[e] = pack_bf16x2(l0, l1);
+                  split_bf16x2(__ldg(ph + (size_t)(2 * e) * plane), __ldg(ph + (size_t)(2 * e + 1) * plane), hh[e], ll[e]);
                 }
               }
 #pragma unroll
@@ -212,15 +204,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad7_ts_kernel(WgradTsArgs a)
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[e].x, h0, l0);
-              split_bf16(v[e].y, h1, l1);
-              hi[2 * e] = pack_bf16x2(h0, h1);
-              lo[2 * e] = pack_bf16x2(l0, l1);
-              split_bf16(v[e].z, h0, l0);
-              split_bf16(v[e].w, h1, l1);
-              hi[2 * e + 1] = pack_bf16x2(h0, h1);
-              lo[2 * e + 1] = pack_bf16x2(l0, l1);
+              split_bf16x2(v[e].x, v[e].y, hi[2 * e], lo[2 * e]);
+              split_bf16x2(v[e].z, v[e].w, hi[2 * e + 1], lo[2 * e + 1]);
             }
             const int slot = dseq % TS_ND;
             if (dseq >= TS_ND) mbar_wait(&dyEmpty[slot], (uint32_t)(((dseq / TS_ND) - 1) & 1));

@@ -22,14 +22,6 @@
 
 namespace ptk {
 
-// two floats -> packed bf16 hi pair and lo pair (hi + lo ~= v to 16 mantissa bits) with the paired conversions
-__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);      // .x = v0 in the low half
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 constexpr int WGK_NSTAGE_THREADS = 224;   // warps 0, 2-7 stage; warp 1 issues the MMAs
 constexpr int WGK_NITEM = 3;              // 16-byte-vector items per staging pass: 24 LDG.128 in flight per thread
 
