@@ -171,6 +171,13 @@ PTK_API int ptk_convlstm_backward_rbp(const PtkLstmDims* d, const float* x, cons
                                       const float* doutput, int32_t num_iter, float* dparams, float* terms_out,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* d(loss)/d(x) [B,1,H,W] of the ConvLSTM (the reference is differentiable w.r.t. the image through autograd: x feeds conv0,
+ * models/convlstm.py:118): dx = conv_transpose2d(d(loss)/d(u), conv0.weight, padding = 3).  Call it right after
+ * ptk_convlstm_backward / ptk_convlstm_backward_rbp on the same stream with the SAME workspace, untouched in between:
+ * d(loss)/d(u) is read from where that call left it. */
+PTK_API int ptk_convlstm_input_grad(const PtkLstmDims* d, const float* params, float* dx, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* ---- ConvGRU baseline (models/kys.py; `--model gru`, utils/engine.py:147-153: dimensions = 64, kernel 7) ----------
  * Flat parameter vector (14 tensors): preproc.{weight[64,3,1,1,1],bias}, unit1.conv_reset.{weight[64,128,7,7],bias},
  * unit1.conv_update.{weight,bias}, unit1.conv_state_new.{weight,bias}, readout_conv.{weight[1,64,1,1],bias},

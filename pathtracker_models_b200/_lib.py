@@ -18,7 +18,7 @@ EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_sa
            "ptk_int_workspace_bytes", "ptk_int_backward_workspace_bytes", "ptk_wgrad7", "ptk_wgrad7_workspace_bytes", "ptk_int_forward", "ptk_int_backward", "ptk_synth_pathtracker",
            "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes",
            "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
-           "ptk_convlstm_forward", "ptk_convlstm_backward",
+           "ptk_convlstm_forward", "ptk_convlstm_backward", "ptk_convlstm_input_grad",
            "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp",
            "ptk_lstm_wide_op", "ptk_lstm_wide_op_workspace_bytes",
            "ptk_gru_param_offsets", "ptk_gru_saved_bytes", "ptk_gru_workspace_bytes", "ptk_gru_forward", "ptk_gru_backward")
@@ -94,6 +94,8 @@ def lib():
     L.ptk_convlstm_forward.argtypes = [ldp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_convlstm_backward.restype = ctypes.c_int
     L.ptk_convlstm_backward.argtypes = [ldp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ptk_convlstm_input_grad.restype = ctypes.c_int
+    L.ptk_convlstm_input_grad.argtypes = [ldp, vp, vp, vp, sz, vp]
     L.ptk_bce_scores.restype = ctypes.c_int
     L.ptk_bce_scores.argtypes = [i32, vp, vp, vp, vp, vp]
     L.ptk_adam_step.restype = ctypes.c_int

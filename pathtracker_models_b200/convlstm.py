@@ -46,10 +46,6 @@ def _find_gabor(gabor, gabor_path):
 class _ConvLSTMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False):
-        if ctx.needs_input_grad[0]:
-            # the reference is differentiable w.r.t. the image through autograd; this path has no dx kernel: say so
-            raise NotImplementedError("ConvLSTM: gradient w.r.t. the input image is not implemented (InT / FFhGRU / kys.GRU "
-                                      "provide it); pass x without requires_grad")
         L = _lib.lib()
         B, _, H, W = x.shape
         flat = flat.contiguous()
@@ -101,8 +97,13 @@ class _ConvLSTMFunction(torch.autograd.Function):
                                                  int(ctx.rbp_iters), _ptr(dflat), _ptr(terms), _ptr(ws), ws_bytes, stream)
                 _lib.check(rc, "ptk_convlstm_backward_rbp")
                 _ConvLSTMFunction.last_rbp_terms = terms      # device tensor; read it only when you want the sync
+            dx = None
+            if ctx.needs_input_grad[0]:       # the reference is differentiable w.r.t. the image: dx = conv0^T (d loss / d u)
+                dx = torch.empty_like(x)
+                rc = L.ptk_convlstm_input_grad(ctypes.byref(dims), _ptr(flat), _ptr(dx), _ptr(ws), ws_bytes, stream)
+                _lib.check(rc, "ptk_convlstm_input_grad")
         ctx.saved_buf = None
-        return None, dflat, None, None, None, None
+        return dx, dflat, None, None, None, None
 
 
 class ConvLSTM(nn.Module):

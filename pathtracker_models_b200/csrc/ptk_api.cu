@@ -544,6 +544,22 @@ int ptk_convlstm_backward_rbp(const PtkLstmDims* dm, const float* x, const float
   return PTK_OK;
 }
 
+int ptk_convlstm_input_grad(const PtkLstmDims* dm, const float* params, float* dx, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  int rc = lstm_check(dm, "ptk_convlstm_input_grad");
+  if (rc) return rc;
+  if (!params || !dx || !workspace) { set_error("ptk_convlstm_input_grad: NULL argument"); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_convlstm_workspace_bytes(dm)) { set_error("ptk_convlstm_input_grad: workspace too small"); return PTK_ENOMEM; }
+  LstmDev d;
+  memset(&d, 0, sizeof(d));
+  d.B = dm->B; d.T = dm->T; d.H = dm->H; d.W = dm->W; d.KS = dm->K;
+  int64_t o[20];
+  lstm_offsets(dm->K, o);
+  d.w0 = params + o[0];
+  lstm_carve(dm, nullptr, workspace, &d, nullptr);     // only the workspace view is used: `dh` still holds d(loss)/d(u)
+  return run_convlstm_dx(d, dx, (cudaStream_t)stream);
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 // ConvGRU (models/kys.py)
 static int gru_check(const PtkGruDims* d, const char* who) {

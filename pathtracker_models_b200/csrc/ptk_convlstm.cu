@@ -388,6 +388,43 @@ static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t 
   return convlstm_grad_tail<KS>(d, st);
 }
 
+// d(loss)/d(x): x feeds only conv0 (u = conv0(x), models/convlstm.py:118), so dx = conv_transpose2d(du, conv0.weight, padding = 3)
+// with du = 2 u d(xt) as left in `dh` by convlstm_grad_tail.  One thread per pixel, the 25 x 49 taps in shared memory.
+__global__ void __launch_bounds__(256) lstm_dx_kernel(const float* __restrict__ du, const float* __restrict__ w0, float* __restrict__ dx,
+                                                      int B, int H, int W) {
+  __shared__ float sW[LC * 49];
+  for (int i = threadIdx.x; i < LC * 49; i += blockDim.x) sW[i] = __ldg(w0 + i);
+  __syncthreads();
+  const int P = H * W;
+  const long long n = (long long)B * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / P), pix = (int)(i - (long long)b * P), y = pix / W, x = pix - y * W;
+    float acc = 0.f;
+    for (int c = 0; c < LC; ++c) {
+      const float* dc = du + ((size_t)b * LC + c) * P;
+      const float* wc = sW + c * 49;
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky) {
+        const int yy = y + 3 - ky;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int xx = x + 3 - kx;
+          if (xx >= 0 && xx < W) acc = fmaf(__ldg(dc + (size_t)yy * W + xx), wc[ky * 7 + kx], acc);
+        }
+      }
+    }
+    dx[i] = acc;
+  }
+}
+int run_convlstm_dx(const LstmDev& d, float* dx, cudaStream_t st) {
+  const long long n = (long long)d.B * d.H * d.W;
+  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  lstm_dx_kernel<<<grid, 256, 0, st>>>(d.dh, d.w0, dx, d.B, d.H, d.W);
+  PTK_LAUNCH_OK("lstm_dx_kernel");
+  return PTK_OK;
+}
+
 int run_convlstm_forward(const LstmDev& d, cudaStream_t st) {
   return d.KS == 15 ? convlstm_forward_t<15>(d, st) : convlstm_forward_t<7>(d, st);
 }

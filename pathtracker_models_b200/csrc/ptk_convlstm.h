@@ -45,6 +45,7 @@ struct LstmDev {
 int run_convlstm_forward(const LstmDev& d, cudaStream_t st);
 int run_convlstm_penalty(const LstmDev& d, cudaStream_t st);
 int run_convlstm_backward(const LstmDev& d, cudaStream_t st);
+int run_convlstm_dx(const LstmDev& d, float* dx, cudaStream_t st);
 int run_convlstm_backward_rbp(const LstmDev& d, int num_iter, cudaStream_t st);
 
 }  // namespace ptk

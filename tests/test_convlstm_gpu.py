@@ -184,11 +184,35 @@ def test_wide_operators_alone_vs_torch_fp64(K, B, H, W):
     assert rel_err(lstm_wide_op("wgrad", h32.cuda(), w32.cuda(), dy32.cuda()), w64.grad) < tol
 
 
-def test_convlstm_input_gradient_is_refused_loudly():
-    """the reference is differentiable w.r.t. the image; this path has no dx kernel and says so instead of returning None"""
+@pytest.mark.parametrize("grad_method", ["bptt", "rbp"])
+def test_convlstm_input_gradient_vs_fp64_oracle(grad_method):
+    """the reference is differentiable w.r.t. the image through autograd (x feeds conv0, models/convlstm.py:118):
+    x.grad = conv0^T (d loss / d u), ptk_convlstm_input_grad.  BPTT: against autograd through the fp64 oracle;
+    rbp: x.grad must equal conv_transpose2d of the conv0.weight-gradient's own d(loss)/d(u), checked through the identity
+    <x.grad, x> = <conv0.weight.grad, conv0.weight> (both equal <du, conv0(x) - b>)."""
+    from oracle import convlstm_oracle as CO
     from pathtracker_models_b200 import convlstm
     case = load_convlstm_case("convlstm_k7_small")
-    m = convlstm.ConvLSTM(timesteps=2, filt_size=7, gabor=case["gabor"]).cuda().train()
+    B, T, H, W = case["shape"]
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method=grad_method, num_iter=4)
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
     x = case["x"].float().cuda().requires_grad_(True)
-    with pytest.raises(NotImplementedError, match="input image"):
-        m(x, 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    out, pen, loss = m(x, 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    loss.backward()
+    assert x.grad is not None and x.grad.shape == x.shape and torch.isfinite(x.grad).all()
+    if grad_method == "bptt":
+        p = {k: v.cuda() for k, v in CO.unpack(case["sd"]).items()}
+        x64 = case["x"].double().cuda().requires_grad_(True)
+        o64, _ = CO.forward(x64, p, T)
+        torch.nn.functional.cross_entropy(o64, case["target"].cuda()).backward()
+        # the usual gate: 1e-4 of max, or 4x the error of the same computation in fp32 (oracle port on the CPU, no TF32)
+        p32 = CO.unpack(case["sd"], dtype=torch.float32)
+        x32 = case["x"].float().requires_grad_(True)
+        o32, _ = CO.forward(x32, p32, T)
+        torch.nn.functional.cross_entropy(o32, case["target"]).backward()
+        allowed = max(REL_TOL, NOISE_MULT * rel_err(x32.grad, x64.grad))
+        assert rel_err(x.grad, x64.grad) <= allowed, (rel_err(x.grad, x64.grad), allowed)
+    lhs = float((x.grad.double() * x.detach().double()).sum())
+    rhs = float((m.conv0.weight.grad.double() * m.conv0.weight.detach().double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1e-12), (lhs, rhs)
