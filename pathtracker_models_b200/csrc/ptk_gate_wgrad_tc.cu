@@ -37,9 +37,9 @@ static_assert(GW_LO_A % 128 == 64 && GW_LO_B % 128 == 64, "bank skew");
 constexpr int GW_A_BYTES = GW_LO_A + GW_KC * GW_PLANE_A + 64;
 constexpr int GW_B_BYTES = GW_LO_B + GW_KC * GW_PLANE_B + 64;
 constexpr int GW_OP_STAGE = GW_A_BYTES + GW_B_BYTES;  // one operand stage (bf16 hi/lo chunk planes)
-constexpr int GW_NOP = 3;
+constexpr int GW_NOP = 2;
 constexpr int GW_RAW_STAGE = 7 * C * GW_PX * 4;       // one raw stage: [7 tensors][32 ch][32 px] fp32, rows of 128 B
-constexpr int GW_NRAW = 4;                            // four tiles in flight while one is converted
+constexpr int GW_NRAW = 5;                            // four tiles in flight while one is converted
 constexpr int GW_OP0 = GW_NRAW * GW_RAW_STAGE;
 constexpr int GW_BARS = GW_OP0 + GW_NOP * GW_OP_STAGE;
 constexpr int GW_SMEM = GW_BARS + 256;
