@@ -620,8 +620,10 @@ __device__ __forceinline__ void frag_add_to_tile(float* tile, const Frag& f) {
         tile[(n * 8 + 2 * t + (e & 1)) * TP + m * 16 + g + 8 * (e >> 1)] += f.c[m][n][e];
 }
 
-constexpr int BCS_NW = 7, BCS_NT = 6;
-static constexpr size_t SM_BWD_CS = (size_t)(4 * C * C + BCS_NW * BCS_NT * TILE_F) * sizeof(float);
+// InT: 7 warps x 6 operand tiles.  hGRU (S = A_t, models/ffhgru_hierarchy.py:146-150) needs a seventh tile: 6 warps x 7 tiles.
+template <int CELL> constexpr int bcs_nw() { return CELL == PTK_CELL_HGRU ? 6 : 7; }
+template <int CELL> constexpr int bcs_nt() { return CELL == PTK_CELL_HGRU ? 7 : 6; }
+template <int CELL> constexpr size_t sm_bwd_cs() { return (size_t)(4 * C * C + bcs_nw<CELL>() * bcs_nt<CELL>() * TILE_F) * sizeof(float); }
 
 // bn_sums_fold for CTAs of more than 128 threads (only the first 128 take part in the load phase)
 __device__ __forceinline__ void bn_sums_fold_wide(const IntDev& d, int bn, const float* sPart /*[2][32]*/, int first,
@@ -670,8 +672,9 @@ __device__ __forceinline__ void bn_sums_fold_wide(const IntDev& d, int bn, const
   }
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev d, int t, int first) {
+template <int CELL, int ACT>
+__global__ void __launch_bounds__(32 * bcs_nw<CELL>(), 1) int_bwd_c_staged_kernel(IntDev d, int t, int first) {
+  constexpr int BCS_NW = bcs_nw<CELL>(), BCS_NT = bcs_nt<CELL>();
   extern __shared__ __align__(16) float dsm[];
   float* sWiw = dsm;              // [out][in] = [k][n] of the transposed products, mma B-fragment order
   float* sWiu = sWiw + C * C;
@@ -695,6 +698,7 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
   float* tY = tI + TILE_F;                               // Y0_t
   float* tG = tY + TILE_F;                               // G_i -> gi
   float* tge = tG + TILE_F;                              // ge
+  float* tS = tge + TILE_F;                              // hGRU only: S = A_t
   int wt = blockIdx.x * BCS_NW + warp;
   float xin[3][4];
   // prologue on parameters, forward statistics, the (read-only) clip and forward checkpoints: overlaps the previous kernel (PDL)
@@ -720,6 +724,7 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
     warp_tile_load_async(tI, It, (size_t)C * P, b, pix_base, P);
     warp_tile_load_async(tY, Y0, (size_t)C * P, b, pix_base, P);
     warp_tile_load_async(tG, Git, (size_t)C * P, b, pix_base, P);
+    if (CELL == PTK_CELL_HGRU) warp_tile_load_async(tS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
   }
   cp_async_commit();
   pdl_wait();
@@ -741,6 +746,7 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
       warp_tile_load_async(tI, It, (size_t)C * P, b, pix_base, P);
       warp_tile_load_async(tY, Y0, (size_t)C * P, b, pix_base, P);
       warp_tile_load_async(tG, Git, (size_t)C * P, b, pix_base, P);
+      if (CELL == PTK_CELL_HGRU) warp_tile_load_async(tS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P);
       warp_tile_load_async(tgI, d.gI, (size_t)C * P, b, pix_base, P);
       warp_tile_load_async(tcg, d.cgI, (size_t)C * P, b, pix_base, P);
       warp_tile_load_async(tge, d.geb_at(t), (size_t)C * P, b, pix_base, P);
@@ -753,13 +759,18 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
     for (int o = 0; o < 8; ++o) {
       const int c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float gi_[4], cg[4], I[4], y0[4], G[4], X[4], oDu[4], oGi[4], oZ[4], oDs[4];
+      float gi_[4], cg[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oZ[4], oDs[4], oDI[4];
       float part[4] = {0.f, 0.f, 0.f, 0.f};
       tile_ld(tgI, L, o, gi_);
       tile_ld(tcg, L, o, cg);
       tile_ld(tI, L, o, I);
       tile_ld(tY, L, o, y0);
       tile_ld(tG, L, o, G);
+      if (CELL == PTK_CELL_HGRU) tile_ld(tS, L, o, S);
+      else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) S[p] = I[p];               // InT: S = I
+      }
       stem_pre(sWp, sbp, c, xin, X);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -767,13 +778,13 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
         X[p] = actf<ACT>(X[p]);
         const float xh = (y0[p] - sM0[c]) * sR0[c];
         const float U = fmaf(sW0[c], xh, sB0[c]);
-        const float aSm = fmaf(sAl[c], I[p], sMu[c]);          // InT: S = I
+        const float aSm = fmaf(sAl[c], S[p], sMu[c]);
         const float Pp = U * aSm;
         const float Q = actf<ACT>(Pp);
         const float d1 = X[p] - Q;
         const float Ihat = actf<ACT>(d1);
         const float dGi = gIn * (Ihat - I[p]);
-        const float oDI = gIn * (1.0f - G[p]);
+        oDI[p] = gIn * (1.0f - G[p]);
         const float zz = gIn * G[p] * dactf<ACT>(d1);
         oGi[p] = dGi * G[p] * (1.0f - G[p]);
         const float dP = -zz * dactf<ACT>(Pp);
@@ -781,8 +792,8 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
         const float dU = dP * aSm;
         oDu[p] = dU;
         oZ[p] = zz;
-        oDs[p] = dPU * sAl[c] + oDI;                          // InT: dI + dS lands in gI
-        part[0] = fmaf(dPU, I[p], part[0]);   // -> d alpha
+        oDs[p] = dPU * sAl[c] + (CELL == PTK_CELL_INT ? oDI[p] : 0.0f);   // InT: dI + dS lands in gI
+        part[0] = fmaf(dPU, S[p], part[0]);   // -> d alpha
         part[1] += dPU;                        // -> d mu
         part[2] += dU;                         // -> sum dU
         part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
@@ -793,6 +804,7 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
       tile_st(tG, L, o, oGi);
       tile_st(tcg, L, o, oZ);         // parked: completed by the transposed products below
       tile_st(tgI, L, o, oDs);
+      if (CELL == PTK_CELL_HGRU) st4(d.gI + idx, oDI);        // hGRU: dI of step t-1 is the point-wise part alone
       part_add<4>(sPw, c, L, part);
     }
     __syncwarp();
@@ -817,7 +829,7 @@ __global__ void __launch_bounds__(32 * BCS_NW, 1) int_bwd_c_staged_kernel(IntDev
       tile_ld(tcg, L, o, v);
       st4(d.dX + idx, v);
       tile_ld(tgI, L, o, v);
-      st4(d.gI + idx, v);
+      st4((CELL == PTK_CELL_INT ? d.gI : d.dS) + idx, v);    // (b10) InT: dI += dS;  hGRU: dA += dS (in bwd_d)
       tile_ld(tI, L, o, v);
       st4(d.dGe + idx, v);
     }
@@ -1054,11 +1066,14 @@ __global__ void __launch_bounds__(128, 4) int_bwd_d_kernel(IntDev d, int t, int 
 // no registers held), computes from shared memory, adds the Wa_u^T product into the parked dE tile in shared memory
 // (instead of a parked global write + a fragment-layout global read-add-write) and fetches dX for the stem while the two
 // gate products run.  One 7-warp CTA per SM: 2 048 tiles / (148 x 7) = 1.98, i.e. two full rounds.
-constexpr int BDS_NW = 7, BDS_NT = 5;
-static constexpr size_t SM_BWD_DS = (size_t)(2 * C * C + BDS_NW * BDS_NT * TILE_F) * sizeof(float);
+// hGRU (S = A, models/ffhgru_hierarchy.py:146-150): dS, completed by int_bwd_c, joins dA -- a sixth operand tile.
+constexpr int BDS_NW = 7;
+template <int CELL> constexpr int bds_nt() { return CELL == PTK_CELL_HGRU ? 6 : 5; }
+template <int CELL> constexpr size_t sm_bwd_ds() { return (size_t)(2 * C * C + BDS_NW * bds_nt<CELL>() * TILE_F) * sizeof(float); }
 
-template <int ACT, bool DX>
+template <int CELL, int ACT, bool DX>
 __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev d, int t, int first) {
+  constexpr int BDS_NT = bds_nt<CELL>();
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;              // [out][in], mma B-fragment order
   float* sWau = sWaw + C * C;
@@ -1075,6 +1090,7 @@ __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev
   float* tG = tE + TILE_F;                              // dGe (point-wise part)
   float* tC = tG + TILE_F;                              // dY0 *7^T W_inh (b9)
   float* tg = tC + TILE_F;                              // dE partial -> dE' of step t-1
+  float* tS = tg + TILE_F;                              // hGRU only: dS
   int wt = blockIdx.x * BDS_NW + warp;
   float xin[3][4];
   // prologue on parameters, the (read-only) clip and forward checkpoints: overlaps the previous kernel's tail (PDL)
@@ -1097,6 +1113,7 @@ __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev
     warp_tile_load_async(tG, d.dGe, (size_t)C * P, b, pix_base, P);
     warp_tile_load_async(tC, d.cGe, (size_t)C * P, b, pix_base, P);
     warp_tile_load_async(tg, d.gE, (size_t)C * P, b, pix_base, P);
+    if (CELL == PTK_CELL_HGRU) warp_tile_load_async(tS, d.dS, (size_t)C * P, b, pix_base, P);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -1111,6 +1128,7 @@ __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev
       warp_tile_load_async(tG, d.dGe, (size_t)C * P, b, pix_base, P);
       warp_tile_load_async(tC, d.cGe, (size_t)C * P, b, pix_base, P);
       warp_tile_load_async(tg, d.gE, (size_t)C * P, b, pix_base, P);
+      if (CELL == PTK_CELL_HGRU) warp_tile_load_async(tS, d.dS, (size_t)C * P, b, pix_base, P);
       cp_async_commit();
       frame_px(d.fv, b, t, pix, d.W, xin);
       cp_async_wait<0>();
@@ -1119,16 +1137,17 @@ __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev
 #pragma unroll 2
     for (int o = 0; o < 8; ++o) {
       const size_t idx = base + (size_t)(L.oc0 + o) * P;
-      float A[4], E[4], gE[4], dg[4], cg[4], oa[4], ode[4];
+      float A[4], E[4], gE[4], dg[4], cg[4], oa[4], ode[4], dS[4] = {0.f, 0.f, 0.f, 0.f};
       tile_ld(tA, L, o, A);
       tile_ld(tE, L, o, E);
       tile_ld(tG, L, o, dg);
       tile_ld(tC, L, o, cg);
       tile_ld(tg, L, o, gE);
+      if (CELL == PTK_CELL_HGRU) tile_ld(tS, L, o, dS);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const float dGe = dg[p] + cg[p];               // + dY0 *7^T W_inh (b9)
-        const float dA = dGe * E[p];
+        const float dA = fmaf(dGe, E[p], dS[p]);       // hGRU: S = A, so dS joins dA
         oa[p] = dA * A[p] * (1.0f - A[p]);
         ode[p] = fmaf(dGe, A[p], gE[p]);
       }
@@ -1575,13 +1594,19 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   const long long gate_tiles = (long long)(d.B * P / GPX) * (tc ? d.T : 1);
   const int gate_grid = gate_tiles < GATE_CTAS ? (int)gate_tiles : GATE_CTAS;
   PTK_CUDA_OK(ptk_func_smem(int_bwd_c_kernel<CELL, ACT>, (int)SM_BWD_C));
-  PTK_CUDA_OK(ptk_func_smem(int_bwd_c_staged_kernel<ACT>, (int)SM_BWD_CS));
+  {
+    constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_c_staged_kernel<SC, ACT>, (int)sm_bwd_cs<SC>()));
+  }
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true, false>, (int)SM_BWD_D));
-  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<ACT, true>, (int)SM_BWD_DS));
-  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<ACT, false>, (int)SM_BWD_DS));
+  {
+    constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<SC, ACT, true>, (int)sm_bwd_ds<SC>()));
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<SC, ACT, false>, (int)sm_bwd_ds<SC>()));
+  }
   PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, true>, (int)SM_GATE));
   PTK_CUDA_OK(ptk_func_smem(gate_wgrad_kernel<CELL, false>, (int)SM_GATE));
   const size_t smr = (size_t)(2 * (d.H + 4) * (d.W + 4) + P) * sizeof(float);
@@ -1628,9 +1653,11 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       static const bool c_staged_on = [] { const char* e = getenv("PTK_BWD_C_STAGED"); return !(e && e[0] == '0'); }();
-      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on) {   // operands staged in shared memory, one 7-warp CTA per SM
-        const int nWT = d.B * P / WPX, sg = (nWT + BCS_NW - 1) / BCS_NW;
-        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_staged_kernel<ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * BCS_NW), SM_BWD_CS, st, d, t, first));
+      if ((CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && c_staged_on) {   // operands staged in shared memory, one CTA per SM
+        constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
+        constexpr int NW = bcs_nw<SC>();
+        const int nWT = d.B * P / WPX, sg = (nWT + NW - 1) / NW;
+        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_staged_kernel<SC, ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * NW), sm_bwd_cs<SC>(), st, d, t, first));
       } else {
         PTK_CUDA_OK(launch_pdl(true, int_bwd_c_kernel<CELL, ACT>, dim3(grid_c), dim3(128), SM_BWD_C, st, d, t, first));
       }
@@ -1658,12 +1685,13 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       static const bool staged_on = [] { const char* e = getenv("PTK_BWD_D_STAGED"); return !(e && e[0] == '0'); }();
-      constexpr bool can_stage = CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
+      constexpr bool can_stage = (CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
       if (can_stage && unfuse && staged_on) {   // operands staged in shared memory, one 7-warp CTA per SM
+        constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
         const int nWT = d.B * P / WPX, sg = (nWT + BDS_NW - 1) / BDS_NW;
         const dim3 g2(sg < 148 ? sg : 148);
-        if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_staged_kernel<ACT, true>, g2, dim3(32 * BDS_NW), SM_BWD_DS, st, d, t, first));
-        else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_staged_kernel<ACT, false>, g2, dim3(32 * BDS_NW), SM_BWD_DS, st, d, t, first));
+        if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_staged_kernel<SC, ACT, true>, g2, dim3(32 * BDS_NW), sm_bwd_ds<SC>(), st, d, t, first));
+        else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_staged_kernel<SC, ACT, false>, g2, dim3(32 * BDS_NW), sm_bwd_ds<SC>(), st, d, t, first));
       } else
       if (d.dx != nullptr && unfuse) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true, false>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
       else if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_kernel<CELL, ACT, true, true>, dim3(grid), dim3(128), SM_BWD_D, st, d, t, first));
