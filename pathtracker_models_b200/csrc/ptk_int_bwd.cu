@@ -852,6 +852,248 @@ __global__ void __launch_bounds__(32 * bcs_nw<CELL>(), 1) int_bwd_c_staged_kerne
 }
 
 // ------------------------------------------------------------------------------------------------
+// (b5)-(b8), staged operands, TWO warps per tile (InT cell, tensor-core modes).  int_bwd_c_staged_kernel keeps 7 warps per SM
+// (six 4.6 KB operand tiles per warp fill the shared memory) and each warp walks a long dependent instruction stream: issue
+// slots 29 % busy, 42 us per launch.  Here the two warps of a pair share one tile's operand tiles and split its CHANNELS:
+// warp h takes channels oc0 + 4h .. + 3 of every lane's patch in the element-wise loops and output n-tiles 2h, 2h + 1 of the
+// transposed gate products (all K = 32 input channels are read by both).  Same shared memory, twice the warps in flight.
+__device__ __forceinline__ void pair_sync(int slot) { named_bar_sync(1 + slot, 64); }
+// half of warp_tile_load_async: channels 16 h .. 16 h + 15
+__device__ __forceinline__ void warp_tile_load_async_half(float* tile, const float* __restrict__ src, size_t bstride, int b,
+                                                          int pix_base, int P, int h) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int q = lane + 32 * (4 * h + j), c = q >> 3, part = q & 7;
+    cp_async16(tile + c * TP + part * 4, src + (size_t)b * bstride + (size_t)c * P + pix_base + part * 4);
+  }
+}
+struct Frag2 { float c[2][2][4]; };   // [m-tile][local n-tile][4]: n-tiles n0, n0 + 1
+__device__ __forceinline__ void frag2_zero(Frag2& f) {
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f.c[m][n][e] = 0.f;
+}
+// warp_mma_gemm restricted to output n-tiles n0, n0 + 1 (same products, same order per accumulator)
+__device__ __forceinline__ void warp_mma_gemm_n2(Frag2& f, const float* __restrict__ tile, const float* __restrict__ sWF, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float* a = tile + (kt * 8 + t) * TP + m * 16 + g;
+      split_tf32(a[0], ah[m][0], al[m][0]);
+      split_tf32(a[8], ah[m][1], al[m][1]);
+      split_tf32(a[4 * TP], ah[m][2], al[m][2]);
+      split_tf32(a[4 * TP + 8], ah[m][3], al[m][3]);
+    }
+#pragma unroll
+    for (int nl = 0; nl < 2; ++nl) {
+      const float2 b = *reinterpret_cast<const float2*>(sWF + ((kt * 4 + n0 + nl) * 32 + lane) * 2);
+      uint32_t bh[2], bl[2];
+      split_tf32(b.x, bh[0], bl[0]);
+      split_tf32(b.y, bh[1], bl[1]);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        mma_tf32(f.c[m][nl], al[m], bh);
+        mma_tf32(f.c[m][nl], ah[m], bl);
+        mma_tf32(f.c[m][nl], ah[m], bh);
+      }
+    }
+  }
+}
+template <bool ADD>
+__device__ __forceinline__ void frag2_to_tile(float* tile, const Frag2& f, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int nl = 0; nl < 2; ++nl)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float* q = tile + ((n0 + nl) * 8 + 2 * t + (e & 1)) * TP + m * 16 + g + 8 * (e >> 1);
+        if (ADD) *q += f.c[m][nl][e]; else *q = f.c[m][nl][e];
+      }
+}
+
+constexpr int BCP_NS = 7, BCP_NT = 6, BCP_NW = 2 * BCP_NS;     // tile slots, operand tiles per slot, warps
+static constexpr size_t SM_BWD_CP = (size_t)(4 * C * C + BCP_NS * BCP_NT * TILE_F) * sizeof(float);
+
+template <int ACT>
+__global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d, int t, int first) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWiw = dsm;              // [out][in] = [k][n] of the transposed products, mma B-fragment order
+  float* sWiu = sWiw + C * C;
+  float* sWew = sWiu + C * C;
+  float* sWeu = sWew + C * C;
+  float* tiles = sWeu + C * C;
+  __shared__ __align__(16) float sWp[C * 3], sbp[C], sAl[C], sMu[C], sW0[C], sB0[C], sM0[C], sR0[C];
+  __shared__ __align__(16) float sPart[BCP_NW * 4 * C], sTot[4 * C];
+  __shared__ int sIsLast;
+  const Lane L;
+  const int warp = threadIdx.x >> 5, slot = warp >> 1, h = warp & 1, O0 = 4 * h, N0 = 2 * h;
+  const int P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* It = d.I_at(t);
+  const float* Y0 = d.Y0_at(t);
+  const float* Git = d.Gi_at(t);
+  float* dU_out = d.dV_at(t, 0);
+  float* gi_out = d.gi_at(t);
+  float* X_out = d.X_at(t);
+  float* tgI = tiles + (size_t)slot * BCP_NT * TILE_F;   // dI' partial -> dS parked -> dI (+ dS) of step t
+  float* tcg = tgI + TILE_F;                             // dY1 *7^T W_exc (b4) -> z parked -> dX
+  float* tI = tcg + TILE_F;                              // I_t -> dGe
+  float* tY = tI + TILE_F;                               // Y0_t
+  float* tG = tY + TILE_F;                               // G_i -> gi
+  float* tge = tG + TILE_F;                              // ge
+  int wt = blockIdx.x * BCP_NS + slot;
+  float xin[3][4];
+  // prologue on parameters, forward statistics, the (read-only) clip and forward checkpoints: overlaps the previous kernel (PDL)
+  cta_fill_async(sWiw, d.gateF[2], C * C);
+  cta_fill_async(sWiu, d.gateF[3], C * C);
+  cta_fill_async(sWew, d.gateF[4], C * C);
+  cta_fill_async(sWeu, d.gateF[5], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  cta_fill_async(sAl, d.alpha, C);
+  cta_fill_async(sMu, d.mu, C);
+  cta_fill_async(sW0, d.bn_w[0], C);
+  cta_fill_async(sB0, d.bn_b[0], C);
+  for (int i = threadIdx.x; i < BCP_NW * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  if (threadIdx.x < C) {
+    const float* st = d.stat(t, 0);
+    sM0[threadIdx.x] = st[threadIdx.x];
+    sR0[threadIdx.x] = st[C + threadIdx.x];
+  }
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+    warp_tile_load_async_half(tI, It, (size_t)C * P, b, pix_base, P, h);
+    warp_tile_load_async_half(tY, Y0, (size_t)C * P, b, pix_base, P, h);
+    warp_tile_load_async_half(tG, Git, (size_t)C * P, b, pix_base, P, h);
+  }
+  cp_async_commit();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async_half(tgI, d.gI, (size_t)C * P, b, pix_base, P, h);
+    warp_tile_load_async_half(tcg, d.cgI, (size_t)C * P, b, pix_base, P, h);
+    warp_tile_load_async_half(tge, d.geb_at(t), (size_t)C * P, b, pix_base, P, h);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  float* sPw = sPart + warp * 4 * C;
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * BCP_NS, firstTile = false) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    if (!firstTile) {
+      warp_tile_load_async_half(tI, It, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tY, Y0, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tG, Git, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tgI, d.gI, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tcg, d.cgI, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tge, d.geb_at(t), (size_t)C * P, b, pix_base, P, h);
+      cp_async_commit();
+      frame_px(d.fv, b, t, pix, d.W, xin);
+      cp_async_wait<0>();
+      pair_sync(slot);                 // both halves of every operand tile have landed
+    }
+#pragma unroll 1
+    for (int oo = 0; oo < 4; ++oo) {
+      const int o = O0 + oo, c = L.oc0 + o;
+      const size_t idx = base + (size_t)c * P;
+      float gi_[4], cg[4], I[4], y0[4], G[4], X[4], oDu[4], oGi[4], oZ[4], oDs[4];
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
+      tile_ld(tgI, L, o, gi_);
+      tile_ld(tcg, L, o, cg);
+      tile_ld(tI, L, o, I);
+      tile_ld(tY, L, o, y0);
+      tile_ld(tG, L, o, G);
+      stem_pre(sWp, sbp, c, xin, X);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float gIn = gi_[p] + cg[p];
+        X[p] = actf<ACT>(X[p]);
+        const float xh = (y0[p] - sM0[c]) * sR0[c];
+        const float U = fmaf(sW0[c], xh, sB0[c]);
+        const float aSm = fmaf(sAl[c], I[p], sMu[c]);          // InT: S = I
+        const float Pp = U * aSm;
+        const float Q = actf<ACT>(Pp);
+        const float d1 = X[p] - Q;
+        const float Ihat = actf<ACT>(d1);
+        const float dGi = gIn * (Ihat - I[p]);
+        const float oDI = gIn * (1.0f - G[p]);
+        const float zz = gIn * G[p] * dactf<ACT>(d1);
+        oGi[p] = dGi * G[p] * (1.0f - G[p]);
+        const float dP = -zz * dactf<ACT>(Pp);
+        const float dPU = dP * U;
+        const float dU = dP * aSm;
+        oDu[p] = dU;
+        oZ[p] = zz;
+        oDs[p] = dPU * sAl[c] + oDI;                          // InT: dI + dS lands in gI
+        part[0] = fmaf(dPU, I[p], part[0]);   // -> d alpha
+        part[1] += dPU;                        // -> d mu
+        part[2] += dU;                         // -> sum dU
+        part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
+      }
+      st4(dU_out + idx, oDu);
+      st4s(gi_out + idx, oGi, d.dy_tstride != 0);
+      st4s(X_out + idx, X, d.dy_tstride != 0);
+      tile_st(tG, L, o, oGi);
+      tile_st(tcg, L, o, oZ);         // parked: completed by the transposed products below
+      tile_st(tgI, L, o, oDs);
+      part_add<4>(sPw, c, L, part);
+    }
+    pair_sync(slot);                   // gi, z, dS complete for all 32 channels; I_t dead
+    {
+      Frag2 f;                         // one accumulator set at a time; this warp's output channels 16 h .. 16 h + 15
+      frag2_zero(f);
+      warp_mma_gemm_n2(f, tG, sWiw, N0);     // dX = z + Wi_w^T gi
+      frag2_to_tile<true>(tcg, f, N0);
+      frag2_zero(f);
+      warp_mma_gemm_n2(f, tG, sWiu, N0);     // dI += dS + Wi_u^T gi + We_w^T ge
+      warp_mma_gemm_n2(f, tge, sWew, N0);
+      frag2_to_tile<true>(tgI, f, N0);
+      frag2_zero(f);
+      warp_mma_gemm_n2(f, tge, sWeu, N0);    // dGe = We_u^T ge
+      frag2_to_tile<false>(tI, f, N0);
+    }
+    pair_sync(slot);
+#pragma unroll 2
+    for (int oo = 0; oo < 4; ++oo) {
+      const size_t idx = base + (size_t)(L.oc0 + O0 + oo) * P;
+      float v[4];
+      tile_ld(tcg, L, O0 + oo, v);
+      st4(d.dX + idx, v);
+      tile_ld(tgI, L, O0 + oo, v);
+      st4(d.gI + idx, v);
+      tile_ld(tI, L, O0 + oo, v);
+      st4(d.dGe + idx, v);
+    }
+    pair_sync(slot);                   // the partner is through with the tiles before the next tile's loads land
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < BCP_NW; ++w) sacc += sPart[w * 4 * C + i];
+    sTot[i] = sacc;
+  }
+  __syncthreads();
+  float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
+  if (threadIdx.x < C) {
+    acc_store(acc + ACC_ALPHA + threadIdx.x, sTot[threadIdx.x], first);
+    acc_store(acc + ACC_MU + threadIdx.x, sTot[C + threadIdx.x], first);
+  }
+  bn_sums_fold_wide(d, 0, sTot + 2 * C, first, &sIsLast, sPart);
+}
+
+// ------------------------------------------------------------------------------------------------
 struct BwdDIn { float4 a, dge, cg, e, ge, ds; };   // one channel of the patch, prefetched one channel ahead
 template <int CELL>
 __device__ __forceinline__ void bwd_d_load(const IntDev& d, const float* At, const float* Et, size_t idx, BwdDIn& r) {
@@ -1597,6 +1839,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   {
     constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
     PTK_CUDA_OK(ptk_func_smem(int_bwd_c_staged_kernel<SC, ACT>, (int)sm_bwd_cs<SC>()));
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_c_pair_kernel<ACT>, (int)SM_BWD_CP));
   }
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
@@ -1653,6 +1896,11 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
     {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       static const bool c_staged_on = [] { const char* e = getenv("PTK_BWD_C_STAGED"); return !(e && e[0] == '0'); }();
+      static const bool c_pair_on = [] { const char* e = getenv("PTK_BWD_C_PAIR"); return !(e && e[0] == '0'); }();
+      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on) {   // staged operands, two warps per tile
+        const int nWT = d.B * P / WPX, sg = (nWT + BCP_NS - 1) / BCP_NS;
+        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_pair_kernel<ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * BCP_NW), SM_BWD_CP, st, d, t, first));
+      } else
       if ((CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && c_staged_on) {   // operands staged in shared memory, one CTA per SM
         constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
         constexpr int NW = bcs_nw<SC>();
