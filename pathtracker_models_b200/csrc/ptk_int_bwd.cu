@@ -1485,6 +1485,192 @@ __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev
 }
 
 // ------------------------------------------------------------------------------------------------
+// (b10)-(b12), staged operands, TWO warps per tile (InT cell): the channel split of int_bwd_c_pair_kernel applied to
+// int_bwd_d_staged_kernel.  14 warps per SM on the same shared memory.
+constexpr int BDP_NS = 7, BDP_NT = 5, BDP_NW = 2 * BDP_NS;
+static constexpr size_t SM_BWD_DP = (size_t)(2 * C * C + BDP_NS * BDP_NT * TILE_F) * sizeof(float);
+
+template <int ACT, bool DX>
+__global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d, int t, int first) {
+  extern __shared__ __align__(16) float dsm[];
+  float* sWaw = dsm;              // [out][in], mma B-fragment order
+  float* sWau = sWaw + C * C;
+  float* tiles = sWau + C * C;
+  __shared__ __align__(16) float sWp[C * 3], sbp[C];
+  __shared__ __align__(16) float sPart[BDP_NW * 4 * C], sTot[4 * C];
+  const Lane L;
+  const int warp = threadIdx.x >> 5, slot = warp >> 1, h = warp & 1, O0 = 4 * h, N0 = 2 * h;
+  const int P = d.H * d.W, tpi = P / WPX, nWT = d.B * tpi;
+  const float* Et = d.E_at(t);
+  const float* At = d.A_at(t);
+  float* a_out = d.a_at(t);
+  float* tA = tiles + (size_t)slot * BDP_NT * TILE_F;   // A_t -> a = dA A (1 - A) -> parked Wa_w^T a
+  float* tE = tA + TILE_F;                              // E_t -> dX of this step
+  float* tG = tE + TILE_F;                              // dGe (point-wise part)
+  float* tC = tG + TILE_F;                              // dY0 *7^T W_inh (b9)
+  float* tg = tC + TILE_F;                              // dE partial -> dE' of step t-1
+  int wt = blockIdx.x * BDP_NS + slot;
+  float xin[3][4];
+  cta_fill_async(sWaw, d.gateF[0], C * C);
+  cta_fill_async(sWau, d.gateF[1], C * C);
+  cta_fill_async(sWp, d.Wp, C * 3);
+  cta_fill_async(sbp, d.bp, C);
+  for (int i = threadIdx.x; i < BDP_NW * 4 * C; i += blockDim.x) sPart[i] = 0.f;
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    frame_px(d.fv, b, t, pix_base + L.pxo, d.W, xin);
+    warp_tile_load_async_half(tA, At, (size_t)d.a_bstride, b, pix_base, P, h);
+    warp_tile_load_async_half(tE, Et, (size_t)C * P, b, pix_base, P, h);
+  }
+  cp_async_commit();
+  pdl_wait();
+  pdl_launch_dependents();
+  if (wt < nWT) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX;
+    warp_tile_load_async_half(tG, d.dGe, (size_t)C * P, b, pix_base, P, h);
+    warp_tile_load_async_half(tC, d.cGe, (size_t)C * P, b, pix_base, P, h);
+    warp_tile_load_async_half(tg, d.gE, (size_t)C * P, b, pix_base, P, h);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  float* sPw = sPart + warp * 4 * C;   // [0] d bp, [1..3] d Wp[:, i]
+  for (bool firstTile = true; wt < nWT; wt += gridDim.x * BDP_NS, firstTile = false) {
+    const int b = wt / tpi, pix_base = (wt - b * tpi) * WPX, pix = pix_base + L.pxo;
+    const size_t base = (size_t)b * C * P + pix;
+    if (!firstTile) {
+      warp_tile_load_async_half(tA, At, (size_t)d.a_bstride, b, pix_base, P, h);
+      warp_tile_load_async_half(tE, Et, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tG, d.dGe, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tC, d.cGe, (size_t)C * P, b, pix_base, P, h);
+      warp_tile_load_async_half(tg, d.gE, (size_t)C * P, b, pix_base, P, h);
+      cp_async_commit();
+      frame_px(d.fv, b, t, pix, d.W, xin);
+      cp_async_wait<0>();
+      pair_sync(slot);
+    }
+#pragma unroll 2
+    for (int oo = 0; oo < 4; ++oo) {
+      const int o = O0 + oo;
+      const size_t idx = base + (size_t)(L.oc0 + o) * P;
+      float A[4], E[4], gE[4], dg[4], cg[4], oa[4], ode[4];
+      tile_ld(tA, L, o, A);
+      tile_ld(tE, L, o, E);
+      tile_ld(tG, L, o, dg);
+      tile_ld(tC, L, o, cg);
+      tile_ld(tg, L, o, gE);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float dGe = dg[p] + cg[p];               // + dY0 *7^T W_inh (b9)
+        const float dA = dGe * E[p];
+        oa[p] = dA * A[p] * (1.0f - A[p]);
+        ode[p] = fmaf(dGe, A[p], gE[p]);
+      }
+      st4s(a_out + idx, oa, d.dy_tstride != 0);
+      tile_st(tA, L, o, oa);
+      tile_st(tg, L, o, ode);          // parked: completed by the transposed product below
+    }
+    pair_sync(slot);                   // a complete for all 32 channels; E_t dead
+    warp_tile_load_async_half(tE, d.dX, (size_t)C * P, b, pix_base, P, h);    // dX arrives while the gate products run
+    cp_async_commit();
+    Frag2 fx;
+    {
+      Frag2 f;
+      if (t > 0) {
+        frag2_zero(f);
+        warp_mma_gemm_n2(f, tA, sWau, N0);   // dE += Wa_u^T a   (= dE' of step t-1)
+        frag2_to_tile<true>(tg, f, N0);
+      }
+      frag2_zero(fx);
+      warp_mma_gemm_n2(fx, tA, sWaw, N0);    // dX += Wa_w^T a: parked in tA below, once BOTH warps have read a
+    }
+    cp_async_wait<0>();
+    pair_sync(slot);
+    frag2_to_tile<false>(tA, fx, N0);
+    pair_sync(slot);
+    float dxs[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) dxs[i][p] = 0.f;
+#pragma unroll 2
+    for (int oo = 0; oo < 4; ++oo) {
+      const int o = O0 + oo, c = L.oc0 + o;
+      float pre[4], dxa[4], dxb[4], part[4] = {0.f, 0.f, 0.f, 0.f};
+      if (t > 0) {                     // dE' of step t-1, read by int_bwd_a_kernel(t-1)
+        float ge[4];
+        tile_ld(tg, L, o, ge);
+        st4(d.gE + base + (size_t)c * P, ge);
+      }
+      stem_pre(sWp, sbp, c, xin, pre);
+      tile_ld(tA, L, o, dxa);
+      tile_ld(tE, L, o, dxb);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float dp = (dxa[p] + dxb[p]) * dactf<ACT>(pre[p]);
+        part[0] += dp;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          part[1 + i] = fmaf(dp, xin[i][p], part[1 + i]);
+          if (DX) dxs[i][p] = fmaf(sWp[c * 3 + i], dp, dxs[i][p]);
+        }
+      }
+      part_add<4>(sPw, c, L, part);
+    }
+    if (DX) {   // contiguous [B,3,T,H,W]: the two warps' channel halves meet through the dead dGe tile
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          dxs[i][p] += __shfl_xor_sync(0xffffffffu, dxs[i][p], 8);
+          dxs[i][p] += __shfl_xor_sync(0xffffffffu, dxs[i][p], 16);
+        }
+      if (h == 1 && L.og == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) st4(tG + i * TP + L.pxo, dxs[i]);
+      }
+      pair_sync(slot);
+      if (h == 0 && L.og == 0) {
+        const size_t plane = (size_t)d.T * P;
+        float* o = d.dx + (size_t)b * 3 * plane + (size_t)t * P + pix;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          float v[4];
+          ld4v(tG + i * TP + L.pxo, v);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) dxs[i][p] += v[p];
+        }
+        if (t == 0) {
+          float g[4];
+          ld4v(d.dgoal + (size_t)b * P + pix, g);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) dxs[2][p] += g[p];
+        }
+        st4(o, dxs[0]);
+        st4(o + plane, dxs[1]);
+        st4(o + 2 * plane, dxs[2]);
+      }
+    }
+    pair_sync(slot);                   // the partner is through with the tiles before the next tile's loads land
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < BDP_NW; ++w) s += sPart[w * 4 * C + i];
+    sTot[i] = s;
+  }
+  __syncthreads();
+  float* acc = d.acc + (size_t)blockIdx.x * ACC_N;
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    acc_store(acc + ACC_BP + c, sTot[c], first);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc_store(acc + ACC_WP + c * 3 + i, sTot[(1 + i) * C + c], first);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gate weight / bias gradients of one step: six 32x32 outer-product sums over all pixels
 //   dWe_w += ge (x) S, dWe_u += ge (x) Ge, dWi_w += gi (x) X, dWi_u += gi (x) S, dWa_w += a (x) X,
 //   dWa_u += a (x) E;  d(bias) += sum ge / gi / a.
@@ -1845,6 +2031,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true, false>, (int)SM_BWD_D));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_pair_kernel<ACT, true>, (int)SM_BWD_DP));
+  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_pair_kernel<ACT, false>, (int)SM_BWD_DP));
   {
     constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
     PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<SC, ACT, true>, (int)sm_bwd_ds<SC>()));
@@ -1934,6 +2122,13 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       static const bool staged_on = [] { const char* e = getenv("PTK_BWD_D_STAGED"); return !(e && e[0] == '0'); }();
       constexpr bool can_stage = (CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
+      static const bool d_pair_on = [] { const char* e = getenv("PTK_BWD_D_PAIR"); return !(e && e[0] == '0'); }();
+      if (can_stage && CELL == PTK_CELL_INT && unfuse && staged_on && d_pair_on) {   // staged operands, two warps per tile
+        const int nWT = d.B * P / WPX, sg = (nWT + BDP_NS - 1) / BDP_NS;
+        const dim3 g2(sg < 148 ? sg : 148);
+        if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<ACT, true>, g2, dim3(32 * BDP_NW), SM_BWD_DP, st, d, t, first));
+        else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<ACT, false>, g2, dim3(32 * BDP_NW), SM_BWD_DP, st, d, t, first));
+      } else
       if (can_stage && unfuse && staged_on) {   // operands staged in shared memory, one 7-warp CTA per SM
         constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
         const int nWT = d.B * P / WPX, sg = (nWT + BDS_NW - 1) / BDS_NW;
