@@ -22,6 +22,10 @@ int int_loop_mode() {
   static const int mode = [] { const char* e = getenv("PTK_FWD_LOOP"); return e ? atoi(e) : 0; }();
   return mode;
 }
+bool stats_deferred() {
+  static const bool on = [] { const char* e = getenv("PTK_STATS_DEFER"); return e && e[0] == '1'; }();
+  return on;
+}
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("PTK_NO_PDL"); return !(e && e[0] == '1'); }();
   return on;

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv7_tc2_kernel(ConvArgs a) {
     const T2Epi e{a.out + (size_t)b * out_bs, H, W, x0, y0, a.accumulate, stats ? a.part + (size_t)cta * C * 2 : nullptr};
     t2_epilogue(e, tmem_base, sPart, sMerge, dFull, dEmpty, 0u, warp - 4, lane);
   }
-  if (stats) conv_stats_fold(a, gridDim.x * gridDim.y * gridDim.z, T2_TH * T2_TW, sFin, &sIsLast);
+  if (stats && !a.defer_stats) conv_stats_fold(a, gridDim.x * gridDim.y * gridDim.z, T2_TH * T2_TW, sFin, &sIsLast);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));

@@ -50,6 +50,7 @@ struct IntDev {
   float *states, *logits;
   float* bn_part;
   unsigned* counter;
+  int defer_stats;         // forward chain: the convolutions leave per-CTA BatchNorm partials in bn_part, int_mid / int_post fold them
   float* bn_part2;         // persistent time-loop kernel (ptk_int_loop.cu): second partial-statistics buffer, barrier counters
   unsigned* loop_sync;
   uint8_t* loop_gates;     // gate matrices as bf16 hi/lo tcgen05 B operands (ptk_int_loop2.cu)
@@ -103,6 +104,8 @@ int run_int_backward(const IntDev& d, int cell, int act, cudaStream_t st);
 int run_prep_weights(const float* w_inh, const float* w_exc, float* inh_f, float* inh_d, float* exc_f,
                      float* exc_d, const IntGateSrc& g, float* gateT, cudaStream_t st);
 int pw_grid(int B, int H, int W);
+bool stats_deferred();                 // PTK_STATS_DEFER=1: int_mid / int_post fold the convolutions' BatchNorm partials (default: the
+                                       // convolution's last CTA does; measured equal)
 // gate weight gradients of all steps on tcgen05 (ptk_gate_wgrad_tc.cu); returns the number of gacc slots written or < 0
 int launch_gate_wgrad_tc(const IntDev& d, int cell, int nT, cudaStream_t st);
 // persistent forward time loop (ptk_int_loop.cu): one cooperative kernel for all frames

@@ -8,6 +8,7 @@
 // Warp-tile kernels (ptk_pw.cuh): a warp owns 32 pixels x 32 channels, the six 1x1 gate
 // convolutions are register-tiled 32x32x32 products against shared-memory tiles; CTAs are
 // persistent (weights staged once) and warps stride over the tiles.
+#include "ptk_conv_stats.cuh"
 #include "ptk_int.h"
 #include "ptk_int_fwd_tiles.cuh"
 #include "ptk_profile.h"
@@ -101,7 +102,10 @@ __global__ void __launch_bounds__(128, 4) int_mid_kernel(IntDev d, int t) {
     warp_tile_load_async(sGX, d.Ge, (size_t)C * P, b, pix_base, P);
   }
   cp_async_commit();
-  if (threadIdx.x < C) {
+  if (d.defer_stats) {                // the convolution left per-CTA partials: fold them here (every CTA, same order)
+    consumer_stats_fold(d.bn_part, d.B * (d.H / 16) * (d.W / 32), 16 * 32, d.bn_w[0], d.bn_b[0], sScale, sShift,
+                        blockIdx.x == 0 ? d.stat(t, 0) : nullptr);
+  } else if (threadIdx.x < C) {
     const int c = threadIdx.x;
     const float* st = d.stat(t, 0);   // BN0 of step t: mean, rstd (written by the convolution just before)
     const float sc = __ldg(d.bn_w[0] + c) * st[C + c];
@@ -187,7 +191,10 @@ __global__ void __launch_bounds__(128, 4) int_post_kernel(IntDev d, int t, int h
     const int b = wt / tpi, pix = (wt - b * tpi) * WPX + L.pxo;
     post_load(Y1, I2, Et, Gx, (size_t)b * C * P + pix + (size_t)L.oc0 * P, cur);
   }
-  if (threadIdx.x < C) {
+  if (d.defer_stats) {
+    consumer_stats_fold(d.bn_part, d.B * (d.H / 16) * (d.W / 32), 16 * 32, d.bn_w[1], d.bn_b[1], sScale, sShift,
+                        blockIdx.x == 0 ? d.stat(t, 1) : nullptr);
+  } else if (threadIdx.x < C) {
     const int c = threadIdx.x;
     const float* st = d.stat(t, 1);   // BN1 of step t (written by the convolution just before)
     const float sc = __ldg(d.bn_w[1] + c) * st[C + c];
@@ -298,7 +305,10 @@ constexpr int CELL_NOINH = 2;   // internal: InT(no_inh=True)
 static constexpr size_t SM_PRE_NI = SM_PRE + 2 * C * C * sizeof(float);
 
 template <int ACT, bool NOINH>
-static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
+static int run_forward_act(const IntDev& d_in, int cell, cudaStream_t st) {
+  IntDev d = d_in;
+  // second-generation tensor-core convolutions leave the BatchNorm partials to their consumers (int_mid / int_post)
+  d.defer_stats = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled() && stats_deferred();
   const int grid = pw_grid(d.B, d.H, d.W);
   const size_t sm_pre = NOINH ? SM_PRE_NI : SM_PRE;
   PTK_CUDA_OK(ptk_func_smem(int_pre_kernel<ACT, NOINH>, (int)sm_pre));
@@ -324,6 +334,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
     if (!NOINH) {
       ConvArgs c0{d.Ge, d.w_inh_f, d.Y0_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 0), d.conv_mode, 1};
     c0.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
+      c0.defer_stats = d.defer_stats;
       { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c0, st); }
       if (rc) return rc;
       {
@@ -335,6 +346,7 @@ static int run_forward_act(const IntDev& d, int cell, cudaStream_t st) {
     }
     ConvArgs c1{d.I_at(t + 1), d.w_exc_f, d.Y1_at(t), d.B, d.H, d.W, 0, d.bn_part, d.counter, d.stat(t, 1), d.conv_mode, 1};
     c1.v2 = (d.conv_mode != PTK_CONV_FP32) && conv_v2_enabled();
+    c1.defer_stats = d.defer_stats;
     { ProfileScope ps(PTK_PROF_CONV_FWD, st); rc = launch_conv7(c1, st); }
     if (rc) return rc;
     {

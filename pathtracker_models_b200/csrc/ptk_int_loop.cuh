@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "ptk_conv_stats.cuh"
 #include "ptk_conv_tc2.cuh"
 #include "ptk_int.h"
 #include "ptk_int_fwd_tiles.cuh"

@@ -19,6 +19,8 @@ struct ConvArgs {
   long long in_bs = 0, out_bs = 0;   // tensor-core path: elements between samples (0 = 32*H*W); lets a 32-channel block
                                      // of a wider [B,Cw,H,W] tensor be convolved in place (ConvGRU, ptk_gru.cu)
   int v2 = 0;          // tensor-core path: wT is the ptk_conv_tc2.cu weight stream (launch_prep_weights_tc2) -> conv7_tc2_kernel
+  int defer_stats = 0; // conv7_tc2: write the per-CTA partials only; the CONSUMER kernel folds them (consumer_stats_fold,
+                       // ptk_conv_stats.cuh) -- no fence / atomic hand-shake / last-CTA fold at the end of the convolution
   // conv7_tc2 only: BatchNorm backward fused into the operand staging (the data-gradient convolutions of the reverse loop).
   // `in` then holds dV, the gradient wrt the BatchNorm OUTPUT; the kernel forms
   //   dY = w*rstd * (dV - mean(dV) - xhat * mean(dV*xhat)),  xhat = (Y - mean) * rstd        (eqs b3 / b9)
