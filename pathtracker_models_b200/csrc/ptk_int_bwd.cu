@@ -2086,7 +2086,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool c_staged_on = [] { const char* e = getenv("PTK_BWD_C_STAGED"); return !(e && e[0] == '0'); }();
       static const bool c_pair_on = [] { const char* e = getenv("PTK_BWD_C_PAIR"); return !(e && e[0] == '0'); }();
       // two warps per tile: measured faster at 32x32 (16.56 -> 16.34 ms at B = 64), slower at 64x64 (36.5 -> 38.8 ms at B = 16, T = 128)
-      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on && P <= 1024) {
+      static const bool pair_any = [] { const char* e = getenv("PTK_BWD_PAIR_ANY"); return e && e[0] == '1'; }();   // measurements only
+      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on && (P <= 1024 || pair_any)) {
         const int nWT = d.B * P / WPX, sg = (nWT + BCP_NS - 1) / BCP_NS;
         PTK_CUDA_OK(launch_pdl(true, int_bwd_c_pair_kernel<ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * BCP_NW), SM_BWD_CP, st, d, t, first));
       } else
