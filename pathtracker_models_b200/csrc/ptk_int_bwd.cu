@@ -2085,9 +2085,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       static const bool c_staged_on = [] { const char* e = getenv("PTK_BWD_C_STAGED"); return !(e && e[0] == '0'); }();
       static const bool c_pair_on = [] { const char* e = getenv("PTK_BWD_C_PAIR"); return !(e && e[0] == '0'); }();
-      // two warps per tile: measured faster at 32x32 (16.56 -> 16.34 ms at B = 64), slower at 64x64 (36.5 -> 38.8 ms at B = 16, T = 128)
-      static const bool pair_any = [] { const char* e = getenv("PTK_BWD_PAIR_ANY"); return e && e[0] == '1'; }();   // measurements only
-      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on && (P <= 1024 || pair_any)) {
+      // two warps per tile: measured faster at 32x32 (16.56 -> 16.34 ms at B = 64) and at 64x64 (36.53 -> 36.08 ms at B = 16, T = 128)
+      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on) {
         const int nWT = d.B * P / WPX, sg = (nWT + BCP_NS - 1) / BCP_NS;
         PTK_CUDA_OK(launch_pdl(true, int_bwd_c_pair_kernel<ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * BCP_NW), SM_BWD_CP, st, d, t, first));
       } else
@@ -2125,7 +2124,8 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool staged_on = [] { const char* e = getenv("PTK_BWD_D_STAGED"); return !(e && e[0] == '0'); }();
       constexpr bool can_stage = (CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
       static const bool d_pair_on = [] { const char* e = getenv("PTK_BWD_D_PAIR"); return !(e && e[0] == '0'); }();
-      if (can_stage && CELL == PTK_CELL_INT && unfuse && staged_on && d_pair_on && P <= 1024) {   // staged operands, two warps per tile (32x32 frames)
+      static const bool pair_any_d = [] { const char* e = getenv("PTK_BWD_PAIR_ANY"); return e && e[0] == '1'; }();   // measurements only
+      if (can_stage && CELL == PTK_CELL_INT && unfuse && staged_on && d_pair_on && (P <= 1024 || pair_any_d)) {   // two warps per tile: +0.4 % at 32x32, but 36.5 -> 39.2 ms at 64x64 (B = 16, T = 128): small frames only
         const int nWT = d.B * P / WPX, sg = (nWT + BDP_NS - 1) / BDP_NS;
         const dim3 g2(sg < 148 ? sg : 148);
         if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<ACT, true>, g2, dim3(32 * BDP_NW), SM_BWD_DP, st, d, t, first));
