@@ -217,9 +217,11 @@ __global__ void __launch_bounds__(128, 4) int_bwd_a_kernel(IntDev d, int t, int 
 // prefetch: 29 us per launch for 92 MB; this one is bound by the memory system).  Per-row partial sums go to `bn_sums`
 // ([B*C][4]); the last CTA folds them per channel in double, in a fixed order (deterministic): BatchNorm-backward means,
 // d(bn weight / bias), and the step's d(kappa), d(gamma) (accumulated in accumulator slot 0).
-constexpr int BAS_R = 4;   // sample rows per CTA: 512 CTAs at B = 64, all resident at once (4 per SM)
+// sample rows per CTA: chosen by the host so that the grid is ~512 CTAs of 256 threads, all resident at once (4 per SM):
+// 4 rows at B = 64, 1 row at B = 16 (64x64 frames: a CTA then walks its 16 KB rows in four passes)
+inline int bas_rows(int B) { const int r = B / 16; return r < 1 ? 1 : (r > 4 ? 4 : r); }
 template <int ACT>
-__global__ void __launch_bounds__(256, 4) int_bwd_a_stream_kernel(IntDev d, int t, int first) {
+__global__ void __launch_bounds__(256, 4) int_bwd_a_stream_kernel(IntDev d, int t, int first, int BAS_R) {
   __shared__ float sRed[8][4];
   __shared__ int sIsLast;
   const int tid = threadIdx.x, P = d.H * d.W, n4 = P / 4;
@@ -2060,7 +2062,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool a_stream = [] { const char* e = getenv("PTK_BWD_A_STREAM"); return !(e && e[0] == '0'); }();
       // the streaming kernel keeps the step's d(kappa), d(gamma) in accumulator slot 0, the warp-tile kernel one partial per
       // CTA slot: one or the other for ALL steps of a call (a_stream && unfuse), never mixed
-      if (a_stream && unfuse) PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_stream_kernel<ACT>, dim3(((d.B + BAS_R - 1) / BAS_R) * C), dim3(256), 0, st, d, t, first));
+      if (a_stream && unfuse) PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_stream_kernel<ACT>, dim3(((d.B + bas_rows(d.B) - 1) / bas_rows(d.B)) * C), dim3(256), 0, st, d, t, first, bas_rows(d.B)));
       else PTK_CUDA_OK(launch_pdl(!first, int_bwd_a_kernel<ACT>, dim3(grid_a), dim3(128), 0, st, d, t, first));
       PTK_LAUNCH_OK("int_bwd_a_kernel");
     }
@@ -2124,8 +2126,7 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool staged_on = [] { const char* e = getenv("PTK_BWD_D_STAGED"); return !(e && e[0] == '0'); }();
       constexpr bool can_stage = (CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
       static const bool d_pair_on = [] { const char* e = getenv("PTK_BWD_D_PAIR"); return !(e && e[0] == '0'); }();
-      static const bool pair_any_d = [] { const char* e = getenv("PTK_BWD_PAIR_ANY"); return e && e[0] == '1'; }();   // measurements only
-      if (can_stage && CELL == PTK_CELL_INT && unfuse && staged_on && d_pair_on && (P <= 1024 || pair_any_d)) {   // two warps per tile: +0.4 % at 32x32, but 36.5 -> 39.2 ms at 64x64 (B = 16, T = 128): small frames only
+      if (can_stage && CELL == PTK_CELL_INT && unfuse && staged_on && d_pair_on) {   // staged operands, two warps per tile
         const int nWT = d.B * P / WPX, sg = (nWT + BDP_NS - 1) / BDP_NS;
         const dim3 g2(sg < 148 ? sg : 148);
         if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<ACT, true>, g2, dim3(32 * BDP_NW), SM_BWD_DP, st, d, t, first));
