@@ -922,11 +922,14 @@ __device__ __forceinline__ void frag2_to_tile(float* tile, const Frag2& f, int n
       }
 }
 
-constexpr int BCP_NS = 7, BCP_NT = 6, BCP_NW = 2 * BCP_NS;     // tile slots, operand tiles per slot, warps
-static constexpr size_t SM_BWD_CP = (size_t)(4 * C * C + BCP_NS * BCP_NT * TILE_F) * sizeof(float);
+// tile slots, operand tiles per slot (hGRU: a seventh tile for S = A_t on six slots), warps = 2 per slot
+template <int CELL> constexpr int bcp_ns() { return CELL == PTK_CELL_HGRU ? 6 : 7; }
+template <int CELL> constexpr int bcp_nt() { return CELL == PTK_CELL_HGRU ? 7 : 6; }
+template <int CELL> constexpr size_t sm_bwd_cp() { return (size_t)(4 * C * C + bcp_ns<CELL>() * bcp_nt<CELL>() * TILE_F) * sizeof(float); }
 
-template <int ACT>
-__global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d, int t, int first) {
+template <int CELL, int ACT>
+__global__ void __launch_bounds__(64 * bcp_ns<CELL>(), 1) int_bwd_c_pair_kernel(IntDev d, int t, int first) {
+  constexpr int BCP_NS = bcp_ns<CELL>(), BCP_NT = bcp_nt<CELL>(), BCP_NW = 2 * BCP_NS;
   extern __shared__ __align__(16) float dsm[];
   float* sWiw = dsm;              // [out][in] = [k][n] of the transposed products, mma B-fragment order
   float* sWiu = sWiw + C * C;
@@ -951,6 +954,7 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
   float* tY = tI + TILE_F;                               // Y0_t
   float* tG = tY + TILE_F;                               // G_i -> gi
   float* tge = tG + TILE_F;                              // ge
+  float* tS = tge + TILE_F;                              // hGRU only: S = A_t
   int wt = blockIdx.x * BCP_NS + slot;
   float xin[3][4];
   // prologue on parameters, forward statistics, the (read-only) clip and forward checkpoints: overlaps the previous kernel (PDL)
@@ -976,6 +980,7 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
     warp_tile_load_async_half(tI, It, (size_t)C * P, b, pix_base, P, h);
     warp_tile_load_async_half(tY, Y0, (size_t)C * P, b, pix_base, P, h);
     warp_tile_load_async_half(tG, Git, (size_t)C * P, b, pix_base, P, h);
+    if (CELL == PTK_CELL_HGRU) warp_tile_load_async_half(tS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P, h);
   }
   cp_async_commit();
   pdl_wait();
@@ -997,6 +1002,7 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
       warp_tile_load_async_half(tI, It, (size_t)C * P, b, pix_base, P, h);
       warp_tile_load_async_half(tY, Y0, (size_t)C * P, b, pix_base, P, h);
       warp_tile_load_async_half(tG, Git, (size_t)C * P, b, pix_base, P, h);
+      if (CELL == PTK_CELL_HGRU) warp_tile_load_async_half(tS, d.A_at(t), (size_t)d.a_bstride, b, pix_base, P, h);
       warp_tile_load_async_half(tgI, d.gI, (size_t)C * P, b, pix_base, P, h);
       warp_tile_load_async_half(tcg, d.cgI, (size_t)C * P, b, pix_base, P, h);
       warp_tile_load_async_half(tge, d.geb_at(t), (size_t)C * P, b, pix_base, P, h);
@@ -1009,13 +1015,18 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
     for (int oo = 0; oo < 4; ++oo) {
       const int o = O0 + oo, c = L.oc0 + o;
       const size_t idx = base + (size_t)c * P;
-      float gi_[4], cg[4], I[4], y0[4], G[4], X[4], oDu[4], oGi[4], oZ[4], oDs[4];
+      float gi_[4], cg[4], I[4], S[4], y0[4], G[4], X[4], oDu[4], oGi[4], oZ[4], oDs[4], oDI[4];
       float part[4] = {0.f, 0.f, 0.f, 0.f};
       tile_ld(tgI, L, o, gi_);
       tile_ld(tcg, L, o, cg);
       tile_ld(tI, L, o, I);
       tile_ld(tY, L, o, y0);
       tile_ld(tG, L, o, G);
+      if (CELL == PTK_CELL_HGRU) tile_ld(tS, L, o, S);
+      else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) S[p] = I[p];               // InT: S = I
+      }
       stem_pre(sWp, sbp, c, xin, X);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -1023,13 +1034,13 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
         X[p] = actf<ACT>(X[p]);
         const float xh = (y0[p] - sM0[c]) * sR0[c];
         const float U = fmaf(sW0[c], xh, sB0[c]);
-        const float aSm = fmaf(sAl[c], I[p], sMu[c]);          // InT: S = I
+        const float aSm = fmaf(sAl[c], S[p], sMu[c]);
         const float Pp = U * aSm;
         const float Q = actf<ACT>(Pp);
         const float d1 = X[p] - Q;
         const float Ihat = actf<ACT>(d1);
         const float dGi = gIn * (Ihat - I[p]);
-        const float oDI = gIn * (1.0f - G[p]);
+        oDI[p] = gIn * (1.0f - G[p]);
         const float zz = gIn * G[p] * dactf<ACT>(d1);
         oGi[p] = dGi * G[p] * (1.0f - G[p]);
         const float dP = -zz * dactf<ACT>(Pp);
@@ -1037,8 +1048,8 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
         const float dU = dP * aSm;
         oDu[p] = dU;
         oZ[p] = zz;
-        oDs[p] = dPU * sAl[c] + oDI;                          // InT: dI + dS lands in gI
-        part[0] = fmaf(dPU, I[p], part[0]);   // -> d alpha
+        oDs[p] = dPU * sAl[c] + (CELL == PTK_CELL_INT ? oDI[p] : 0.0f);   // InT: dI + dS lands in gI
+        part[0] = fmaf(dPU, S[p], part[0]);   // -> d alpha
         part[1] += dPU;                        // -> d mu
         part[2] += dU;                         // -> sum dU
         part[3] = fmaf(dU, xh, part[3]);       // -> sum dU * xhat
@@ -1049,6 +1060,7 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
       tile_st(tG, L, o, oGi);
       tile_st(tcg, L, o, oZ);         // parked: completed by the transposed products below
       tile_st(tgI, L, o, oDs);
+      if (CELL == PTK_CELL_HGRU) st4(d.gI + idx, oDI);        // hGRU: dI of step t-1 is the point-wise part alone
       part_add<4>(sPw, c, L, part);
     }
     pair_sync(slot);                   // gi, z, dS complete for all 32 channels; I_t dead
@@ -1073,7 +1085,7 @@ __global__ void __launch_bounds__(32 * BCP_NW, 1) int_bwd_c_pair_kernel(IntDev d
       tile_ld(tcg, L, O0 + oo, v);
       st4(d.dX + idx, v);
       tile_ld(tgI, L, O0 + oo, v);
-      st4(d.gI + idx, v);
+      st4((CELL == PTK_CELL_INT ? d.gI : d.dS) + idx, v);    // (b10) InT: dI += dS;  hGRU: dA += dS (in bwd_d)
       tile_ld(tI, L, O0 + oo, v);
       st4(d.dGe + idx, v);
     }
@@ -1489,11 +1501,13 @@ __global__ void __launch_bounds__(32 * BDS_NW, 1) int_bwd_d_staged_kernel(IntDev
 // ------------------------------------------------------------------------------------------------
 // (b10)-(b12), staged operands, TWO warps per tile (InT cell): the channel split of int_bwd_c_pair_kernel applied to
 // int_bwd_d_staged_kernel.  14 warps per SM on the same shared memory.
-constexpr int BDP_NS = 7, BDP_NT = 5, BDP_NW = 2 * BDP_NS;
-static constexpr size_t SM_BWD_DP = (size_t)(2 * C * C + BDP_NS * BDP_NT * TILE_F) * sizeof(float);
+constexpr int BDP_NS = 7, BDP_NW = 2 * BDP_NS;
+template <int CELL> constexpr int bdp_nt() { return CELL == PTK_CELL_HGRU ? 6 : 5; }     // hGRU: a sixth tile for dS
+template <int CELL> constexpr size_t sm_bwd_dp() { return (size_t)(2 * C * C + BDP_NS * bdp_nt<CELL>() * TILE_F) * sizeof(float); }
 
-template <int ACT, bool DX>
+template <int CELL, int ACT, bool DX>
 __global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d, int t, int first) {
+  constexpr int BDP_NT = bdp_nt<CELL>();
   extern __shared__ __align__(16) float dsm[];
   float* sWaw = dsm;              // [out][in], mma B-fragment order
   float* sWau = sWaw + C * C;
@@ -1511,6 +1525,7 @@ __global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d
   float* tG = tE + TILE_F;                              // dGe (point-wise part)
   float* tC = tG + TILE_F;                              // dY0 *7^T W_inh (b9)
   float* tg = tC + TILE_F;                              // dE partial -> dE' of step t-1
+  float* tS = tg + TILE_F;                              // hGRU only: dS
   int wt = blockIdx.x * BDP_NS + slot;
   float xin[3][4];
   cta_fill_async(sWaw, d.gateF[0], C * C);
@@ -1532,6 +1547,7 @@ __global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d
     warp_tile_load_async_half(tG, d.dGe, (size_t)C * P, b, pix_base, P, h);
     warp_tile_load_async_half(tC, d.cGe, (size_t)C * P, b, pix_base, P, h);
     warp_tile_load_async_half(tg, d.gE, (size_t)C * P, b, pix_base, P, h);
+    if (CELL == PTK_CELL_HGRU) warp_tile_load_async_half(tS, d.dS, (size_t)C * P, b, pix_base, P, h);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -1546,6 +1562,7 @@ __global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d
       warp_tile_load_async_half(tG, d.dGe, (size_t)C * P, b, pix_base, P, h);
       warp_tile_load_async_half(tC, d.cGe, (size_t)C * P, b, pix_base, P, h);
       warp_tile_load_async_half(tg, d.gE, (size_t)C * P, b, pix_base, P, h);
+      if (CELL == PTK_CELL_HGRU) warp_tile_load_async_half(tS, d.dS, (size_t)C * P, b, pix_base, P, h);
       cp_async_commit();
       frame_px(d.fv, b, t, pix, d.W, xin);
       cp_async_wait<0>();
@@ -1555,16 +1572,17 @@ __global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d
     for (int oo = 0; oo < 4; ++oo) {
       const int o = O0 + oo;
       const size_t idx = base + (size_t)(L.oc0 + o) * P;
-      float A[4], E[4], gE[4], dg[4], cg[4], oa[4], ode[4];
+      float A[4], E[4], gE[4], dg[4], cg[4], oa[4], ode[4], dS[4] = {0.f, 0.f, 0.f, 0.f};
       tile_ld(tA, L, o, A);
       tile_ld(tE, L, o, E);
       tile_ld(tG, L, o, dg);
       tile_ld(tC, L, o, cg);
       tile_ld(tg, L, o, gE);
+      if (CELL == PTK_CELL_HGRU) tile_ld(tS, L, o, dS);
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const float dGe = dg[p] + cg[p];               // + dY0 *7^T W_inh (b9)
-        const float dA = dGe * E[p];
+        const float dA = fmaf(dGe, E[p], dS[p]);       // hGRU: S = A, so dS joins dA
         oa[p] = dA * A[p] * (1.0f - A[p]);
         ode[p] = fmaf(dGe, A[p], gE[p]);
       }
@@ -2027,16 +2045,16 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
   {
     constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
     PTK_CUDA_OK(ptk_func_smem(int_bwd_c_staged_kernel<SC, ACT>, (int)sm_bwd_cs<SC>()));
-    PTK_CUDA_OK(ptk_func_smem(int_bwd_c_pair_kernel<ACT>, (int)SM_BWD_CP));
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_c_pair_kernel<SC, ACT>, (int)sm_bwd_cp<SC>()));
   }
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, false, false>, (int)SM_BWD_D));
   PTK_CUDA_OK(ptk_func_smem(int_bwd_d_kernel<CELL, ACT, true, false>, (int)SM_BWD_D));
-  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_pair_kernel<ACT, true>, (int)SM_BWD_DP));
-  PTK_CUDA_OK(ptk_func_smem(int_bwd_d_pair_kernel<ACT, false>, (int)SM_BWD_DP));
   {
     constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_d_pair_kernel<SC, ACT, true>, (int)sm_bwd_dp<SC>()));
+    PTK_CUDA_OK(ptk_func_smem(int_bwd_d_pair_kernel<SC, ACT, false>, (int)sm_bwd_dp<SC>()));
     PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<SC, ACT, true>, (int)sm_bwd_ds<SC>()));
     PTK_CUDA_OK(ptk_func_smem(int_bwd_d_staged_kernel<SC, ACT, false>, (int)sm_bwd_ds<SC>()));
   }
@@ -2088,9 +2106,11 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool c_staged_on = [] { const char* e = getenv("PTK_BWD_C_STAGED"); return !(e && e[0] == '0'); }();
       static const bool c_pair_on = [] { const char* e = getenv("PTK_BWD_C_PAIR"); return !(e && e[0] == '0'); }();
       // two warps per tile: measured faster at 32x32 (16.56 -> 16.34 ms at B = 64) and at 64x64 (36.53 -> 36.08 ms at B = 16, T = 128)
-      if (CELL == PTK_CELL_INT && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on) {
-        const int nWT = d.B * P / WPX, sg = (nWT + BCP_NS - 1) / BCP_NS;
-        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_pair_kernel<ACT>, dim3(sg < 148 ? sg : 148), dim3(32 * BCP_NW), SM_BWD_CP, st, d, t, first));
+      if ((CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && c_staged_on && c_pair_on) {
+        constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
+        constexpr int NS = bcp_ns<SC>();
+        const int nWT = d.B * P / WPX, sg = (nWT + NS - 1) / NS;
+        PTK_CUDA_OK(launch_pdl(true, int_bwd_c_pair_kernel<SC, ACT>, dim3(sg < 148 ? sg : 148), dim3(64 * NS), sm_bwd_cp<SC>(), st, d, t, first));
       } else
       if ((CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && c_staged_on) {   // operands staged in shared memory, one CTA per SM
         constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
@@ -2126,11 +2146,12 @@ static int run_backward_t(const IntDev& d, cudaStream_t st) {
       static const bool staged_on = [] { const char* e = getenv("PTK_BWD_D_STAGED"); return !(e && e[0] == '0'); }();
       constexpr bool can_stage = (CELL == PTK_CELL_INT || CELL == PTK_CELL_HGRU) && (ACT & ACT_FAST) != 0 && PTK_BWD_D_MMA;
       static const bool d_pair_on = [] { const char* e = getenv("PTK_BWD_D_PAIR"); return !(e && e[0] == '0'); }();
-      if (can_stage && CELL == PTK_CELL_INT && unfuse && staged_on && d_pair_on) {   // staged operands, two warps per tile
+      if (can_stage && unfuse && staged_on && d_pair_on) {   // staged operands, two warps per tile
+        constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
         const int nWT = d.B * P / WPX, sg = (nWT + BDP_NS - 1) / BDP_NS;
         const dim3 g2(sg < 148 ? sg : 148);
-        if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<ACT, true>, g2, dim3(32 * BDP_NW), SM_BWD_DP, st, d, t, first));
-        else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<ACT, false>, g2, dim3(32 * BDP_NW), SM_BWD_DP, st, d, t, first));
+        if (d.dx != nullptr) PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<SC, ACT, true>, g2, dim3(32 * BDP_NW), sm_bwd_dp<SC>(), st, d, t, first));
+        else PTK_CUDA_OK(launch_pdl(true, int_bwd_d_pair_kernel<SC, ACT, false>, g2, dim3(32 * BDP_NW), sm_bwd_dp<SC>(), st, d, t, first));
       } else
       if (can_stage && unfuse && staged_on) {   // operands staged in shared memory, one 7-warp CTA per SM
         constexpr int SC = CELL == PTK_CELL_HGRU ? PTK_CELL_HGRU : PTK_CELL_INT;
