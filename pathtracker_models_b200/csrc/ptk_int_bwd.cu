@@ -908,6 +908,43 @@ __device__ __forceinline__ void warp_mma_gemm_n2(Frag2& f, const float* __restri
     }
   }
 }
+// two products with the SAME A operand (tile) against two matrices: the A fragments are loaded and split once.
+// Per accumulator the sequence of mma instructions is the one of two warp_mma_gemm_n2 calls (bit-identical sums).
+template <bool SECOND>
+__device__ __forceinline__ void warp_mma_gemm_n2x2(Frag2& f1, Frag2& f2, const float* __restrict__ tile, const float* __restrict__ sWF1,
+                                                   const float* __restrict__ sWF2, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float* a = tile + (kt * 8 + t) * TP + m * 16 + g;
+      split_tf32(a[0], ah[m][0], al[m][0]);
+      split_tf32(a[8], ah[m][1], al[m][1]);
+      split_tf32(a[4 * TP], ah[m][2], al[m][2]);
+      split_tf32(a[4 * TP + 8], ah[m][3], al[m][3]);
+    }
+#pragma unroll
+    for (int w = 0; w < (SECOND ? 2 : 1); ++w) {
+      const float* sWF = w == 0 ? sWF1 : sWF2;
+#pragma unroll
+      for (int nl = 0; nl < 2; ++nl) {
+        const float2 b = *reinterpret_cast<const float2*>(sWF + ((kt * 4 + n0 + nl) * 32 + lane) * 2);
+        uint32_t bh[2], bl[2];
+        split_tf32(b.x, bh[0], bl[0]);
+        split_tf32(b.y, bh[1], bl[1]);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          float (&c)[4] = w == 0 ? f1.c[m][nl] : f2.c[m][nl];
+          mma_tf32(c, al[m], bh);
+          mma_tf32(c, ah[m], bl);
+          mma_tf32(c, ah[m], bh);
+        }
+      }
+    }
+  }
+}
 template <bool ADD>
 __device__ __forceinline__ void frag2_to_tile(float* tile, const Frag2& f, int n0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -1065,17 +1102,15 @@ __global__ void __launch_bounds__(64 * bcp_ns<CELL>(), 1) int_bwd_c_pair_kernel(
     }
     pair_sync(slot);                   // gi, z, dS complete for all 32 channels; I_t dead
     {
-      Frag2 f;                         // one accumulator set at a time; this warp's output channels 16 h .. 16 h + 15
-      frag2_zero(f);
-      warp_mma_gemm_n2(f, tG, sWiw, N0);     // dX = z + Wi_w^T gi
-      frag2_to_tile<true>(tcg, f, N0);
-      frag2_zero(f);
-      warp_mma_gemm_n2(f, tG, sWiu, N0);     // dI += dS + Wi_u^T gi + We_w^T ge
-      warp_mma_gemm_n2(f, tge, sWew, N0);
-      frag2_to_tile<true>(tgI, f, N0);
-      frag2_zero(f);
-      warp_mma_gemm_n2(f, tge, sWeu, N0);    // dGe = We_u^T ge
-      frag2_to_tile<false>(tI, f, N0);
+      Frag2 f1, f2;                    // this warp's output channels 16 h .. 16 h + 15; each operand tile is split once
+      frag2_zero(f1);
+      frag2_zero(f2);
+      warp_mma_gemm_n2x2<true>(f1, f2, tG, sWiw, sWiu, N0);     // dX = z + Wi_w^T gi;   dI += dS + Wi_u^T gi ...
+      frag2_to_tile<true>(tcg, f1, N0);
+      frag2_zero(f1);
+      warp_mma_gemm_n2x2<true>(f2, f1, tge, sWew, sWeu, N0);    // ... + We_w^T ge;       dGe = We_u^T ge
+      frag2_to_tile<true>(tgI, f2, N0);
+      frag2_to_tile<false>(tI, f1, N0);
     }
     pair_sync(slot);
 #pragma unroll 2
@@ -1596,13 +1631,14 @@ __global__ void __launch_bounds__(32 * BDP_NW, 1) int_bwd_d_pair_kernel(IntDev d
     Frag2 fx;
     {
       Frag2 f;
-      if (t > 0) {
-        frag2_zero(f);
-        warp_mma_gemm_n2(f, tA, sWau, N0);   // dE += Wa_u^T a   (= dE' of step t-1)
-        frag2_to_tile<true>(tg, f, N0);
-      }
+      frag2_zero(f);
       frag2_zero(fx);
-      warp_mma_gemm_n2(fx, tA, sWaw, N0);    // dX += Wa_w^T a: parked in tA below, once BOTH warps have read a
+      if (t > 0) {                           // a is split once for both products
+        warp_mma_gemm_n2x2<true>(f, fx, tA, sWau, sWaw, N0);   // dE += Wa_u^T a (= dE' of step t-1);  dX += Wa_w^T a
+        frag2_to_tile<true>(tg, f, N0);
+      } else {
+        warp_mma_gemm_n2x2<false>(fx, f, tA, sWaw, sWaw, N0);  // dX += Wa_w^T a: parked in tA below, once BOTH warps have read a
+      }
     }
     cp_async_wait<0>();
     pair_sync(slot);
