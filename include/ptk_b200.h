@@ -147,13 +147,18 @@ typedef struct PtkLstmDims {
                         * 1: constant-memory checkpoints for recurrent back-propagation (models/convlstm.py:124-135 runs the
                         *    first T-1 steps under no_grad): two-slot rings, so only steps T-1 and T survive;
                         *    ptk_convlstm_saved_bytes no longer grows with T.  ptk_convlstm_backward then refuses. */
+  int32_t rbp;         /* 1: grad_method='rbp' -- h_{T-1}, c_{T-1} are detached leaves (models/convlstm.py:130-131), so the
+                        *    second product of the Jacobian penalty is f_T alone and the penalty's gradient
+                        *    (ptk_convlstm_backward_penalty) reaches the parameters through the last step only.
+                        * 0: 'bptt' -- they are live graph tensors (:140-142): the product also holds the path
+                        *    c_{T-1} -> h_{T-1} -> gates_T -> c_T and the penalty's gradient runs back through every step. */
 } PtkLstmDims;
 PTK_API int ptk_convlstm_param_offsets(const PtkLstmDims* d, int64_t* offsets);
 PTK_API size_t ptk_convlstm_saved_bytes(const PtkLstmDims* d);
 PTK_API size_t ptk_convlstm_workspace_bytes(const PtkLstmDims* d);
 /* ConvLSTM.forward up to `output = conv6(bn(h_T))` (models/convlstm.py:116-147, bptt branch); the criterion
  * (:148) stays with the caller.  penalty: optional [B,25,H,W] out, the Jacobian penalty of :152-163
- * (training mode, create_graph=False); needs T >= 2.  saved: ptk_convlstm_saved_bytes, always required. */
+ * (training mode; a constant for the caller unless ptk_convlstm_backward_penalty is used); needs T >= 2.  saved: ptk_convlstm_saved_bytes, always required. */
 PTK_API int ptk_convlstm_forward(const PtkLstmDims* d, const float* x, const float* params, float* output,
                                  float* penalty, void* saved, void* workspace, size_t workspace_bytes, void* stream);
 /* BPTT: doutput [B,2,H,W] -> dparams (flat, overwritten). */
@@ -170,6 +175,17 @@ PTK_API int ptk_convlstm_backward(const PtkLstmDims* d, const float* x, const fl
 PTK_API int ptk_convlstm_backward_rbp(const PtkLstmDims* d, const float* x, const float* params, const void* saved,
                                       const float* doutput, int32_t num_iter, float* dparams, float* terms_out,
                                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* jacobian_penalty=True (models/convlstm.py:152-163 with create_graph=True): gradient of
+ *   total = loss + <dpenalty, penalty>      (the training loop uses loss + 10 * penalty.mean(), mainclean.py:192-196)
+ * with the penalty INSIDE the graph, i.e. the double back-propagation autograd performs in the reference, in closed form:
+ * second-order seeds at the gate pre-activations of steps T and T-1, on c_{T-1} and directly on the Wh weight gradient
+ * (two extra forward convolutions, two transposes, two weight-gradient passes), then the unchanged reverse loop.
+ * d->rbp selects the loss gradient: 0 = BPTT (as ptk_convlstm_backward), 1 = recurrent back-propagation (as
+ * ptk_convlstm_backward_rbp; num_iter / terms_out as there, ignored for BPTT).  dpenalty: [B,25,H,W]. */
+PTK_API int ptk_convlstm_backward_penalty(const PtkLstmDims* d, const float* x, const float* params, const void* saved,
+                                          const float* doutput, const float* dpenalty, int32_t num_iter, float* dparams,
+                                          float* terms_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* d(loss)/d(x) [B,1,H,W] of the ConvLSTM (the reference is differentiable w.r.t. the image through autograd: x feeds conv0,
  * models/convlstm.py:118): dx = conv_transpose2d(d(loss)/d(u), conv0.weight, padding = 3).  Call it right after

@@ -78,6 +78,49 @@ def jv_penalty(x, p, timesteps):
     return ((jh - 0.9).clamp(0) ** 2 + (jc - 0.9).clamp(0) ** 2).detach()
 
 
+def jp_total_grads(x, p, timesteps, target, grad_method="bptt", num_iter=50, weight=10.0):
+    """jacobian_penalty=True (models/convlstm.py:152-163 with create_graph=True): gradients of
+    loss + weight * penalty.mean() (mainclean.py:192-196) by double back-propagation.  `p` is keyed like the state_dict,
+    leaf tensors with requires_grad=True.  Returns (output, loss, penalty, grads).
+
+    bptt (:137-144): h_{T-1}, c_{T-1} are live graph tensors, so the penalty's gradient runs back through every step and
+    the second product contains the path c_{T-1} -> h_{T-1} -> gates_T -> c_T.  rbp (:124-135): they are detached leaves,
+    the second product is f_T alone and the penalty reaches the parameters through the last step only; the loss
+    gradient is the Neumann series of `dummyhgru` (rbp_grads)."""
+    u = F.conv2d(x, p["conv0.weight"], p["conv0.bias"], padding=3)
+    xt = u * u
+    pad = (p["unit1.Whi.weight"].shape[-1] - 1) // 2
+    h = torch.zeros_like(xt)
+    c = torch.zeros_like(xt)
+    if grad_method == "rbp":
+        with torch.no_grad():
+            for _ in range(timesteps - 1):
+                h, c = _cell_sd(xt, h, c, p, pad)
+        h2 = h.detach().requires_grad_()
+        c2 = c.detach().requires_grad_()
+    else:
+        for _ in range(timesteps - 1):
+            h, c = _cell_sd(xt, h, c, p, pad)
+        h2, c2 = h, c
+    hT, cT = _cell_sd(xt, h2, c2, p, pad)
+    ones = torch.ones_like(hT)
+    jh = torch.autograd.grad(hT, h2, grad_outputs=ones, retain_graph=True, create_graph=True)[0]
+    jc = torch.autograd.grad(cT, c2, grad_outputs=ones, retain_graph=True, create_graph=True)[0]
+    pen = (jh - 0.9).clamp(0) ** 2 + (jc - 0.9).clamp(0) ** 2
+    keys = list(p)
+    if grad_method == "rbp":
+        out, loss, grads, _ = rbp_grads(x, p, timesteps, target, num_iter)
+        pg = torch.autograd.grad(pen.mean() * weight, [p[k] for k in keys], allow_unused=True)
+        for k, g in zip(keys, pg):
+            if g is not None:
+                grads[k] = g if grads.get(k) is None else grads[k] + g
+        return out, loss, pen.detach(), grads
+    out = F.conv2d(F.batch_norm(hT, None, None, p["bn.weight"], p["bn.bias"], True, 0.0, 1e-3), p["conv6.weight"], p["conv6.bias"])
+    loss = F.cross_entropy(out, target)
+    pg = torch.autograd.grad(loss + pen.mean() * weight, [p[k] for k in keys], allow_unused=True)
+    return out.detach(), loss.item(), pen.detach(), {k: g for k, g in zip(keys, pg)}
+
+
 STATE_KEYS = {"w0": "conv0.weight", "b0": "conv0.bias", "bn_w": "bn.weight", "bn_b": "bn.bias",
               "w6": "conv6.weight", "b6": "conv6.bias"}
 for _k in GATES:

@@ -157,7 +157,9 @@ def convlstm_weights(sd_like, seed):
     return out
 
 
-def run_convlstm_case(name, filt, B, T, H, W, seed, store_full, grad_method='bptt', num_iter=50, wh_scale=1.0):
+def run_convlstm_case(name, filt, B, T, H, W, seed, store_full, grad_method='bptt', num_iter=50, wh_scale=1.0, jacobian_penalty=False):
+    """jacobian_penalty=True: the penalty is built with create_graph=True (models/convlstm.py:157-160) and the training
+    loop back-propagates loss + 10 * penalty.mean() (mainclean.py:192-196); the stored gradients are those of that sum."""
     cwd = os.getcwd()
     os.chdir(REF)                                   # ConvLSTM.__init__ loads 'utils/gabor_serre.npy' (convlstm.py:105)
     from models import convlstm as RC
@@ -177,7 +179,8 @@ def run_convlstm_case(name, filt, B, T, H, W, seed, store_full, grad_method='bpt
     grads = {}
     for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
         torch.set_default_dtype(dt)
-        m = RC.ConvLSTM(timesteps=T, filt_size=filt, grad_method=grad_method, num_iter=num_iter).to(dt)
+        m = RC.ConvLSTM(timesteps=T, filt_size=filt, grad_method=grad_method, num_iter=num_iter,
+                        jacobian_penalty=jacobian_penalty).to(dt)
         m.load_state_dict({k: v.to(dt) for k, v in sd32.items()})
         m.train()
         x = torch.from_numpy(x_np).to(dt)
@@ -189,8 +192,9 @@ def run_convlstm_case(name, filt, B, T, H, W, seed, store_full, grad_method='bpt
             calls[0] += 1
             return real_grad(*a, **k)
         torch.autograd.grad = counting_grad      # dummyhgru.backward calls it once per Neumann term it tries
+        total = loss + pen.mean() * 1e1 if jacobian_penalty else loss      # mainclean.py:192-196
         try:
-            loss.backward()
+            total.backward()
         finally:
             torch.autograd.grad = real_grad
         if tag == "f64":
@@ -294,6 +298,14 @@ if __name__ == "__main__":
         load_reference()
         run_convlstm_case("convlstm_k7_rbp", 7, 2, 4, 32, 32, seed=41, store_full=True, grad_method='rbp', num_iter=50)
         run_convlstm_case("convlstm_k7_rbp_trunc", 7, 2, 3, 32, 32, seed=42, store_full=True, grad_method='rbp', num_iter=2)
+    elif len(sys.argv) > 1 and sys.argv[1] == "convlstm_jp":
+        # jacobian_penalty=True: second-order graph through the last cell step, both gradient methods
+        load_reference()
+        run_convlstm_case("convlstm_k7_jp", 7, 2, 3, 32, 32, seed=71, store_full=True, jacobian_penalty=True)
+        run_convlstm_case("convlstm_k7_jp_t2", 7, 2, 2, 16, 32, seed=72, store_full=True, jacobian_penalty=True)
+        run_convlstm_case("convlstm_k15_jp", 15, 2, 4, 32, 32, seed=73, store_full=False, jacobian_penalty=True)
+        run_convlstm_case("convlstm_k7_rbp_jp", 7, 2, 4, 32, 32, seed=74, store_full=True, grad_method='rbp', num_iter=50,
+                          jacobian_penalty=True)
     elif len(sys.argv) > 1 and sys.argv[1] == "long":
         # the horizons the benchmark is quoted on (BASELINE.json configs[1]-[4]): T = 64 at 32x32, T = 128 at 64x64,
         # ConvLSTM timesteps = 64 (models/convlstm.py:138), kys.GRU T = 64.  Minutes of CPU time each.

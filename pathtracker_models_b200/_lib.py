@@ -19,7 +19,7 @@ EXPORTS = ("ptk_version", "ptk_last_error", "ptk_int_param_offsets", "ptk_int_sa
            "ptk_profile_start", "ptk_profile_stop", "ptk_launch_count", "ptk_conv7", "ptk_conv7_workspace_bytes",
            "ptk_convlstm_param_offsets", "ptk_convlstm_saved_bytes", "ptk_convlstm_workspace_bytes",
            "ptk_convlstm_forward", "ptk_convlstm_backward", "ptk_convlstm_input_grad",
-           "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp",
+           "ptk_bce_scores", "ptk_adam_step", "ptk_convlstm_backward_rbp", "ptk_convlstm_backward_penalty",
            "ptk_lstm_wide_op", "ptk_lstm_wide_op_workspace_bytes",
            "ptk_gru_param_offsets", "ptk_gru_saved_bytes", "ptk_gru_workspace_bytes", "ptk_gru_forward", "ptk_gru_backward")
 
@@ -30,7 +30,7 @@ class PtkDims(ctypes.Structure):
 
 
 class PtkLstmDims(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K", "conv_mode", "ckpt_ring")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "T", "H", "W", "K", "conv_mode", "ckpt_ring", "rbp")]
 
 
 class PtkGruDims(ctypes.Structure):
@@ -94,6 +94,8 @@ def lib():
     L.ptk_convlstm_forward.argtypes = [ldp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.ptk_convlstm_backward.restype = ctypes.c_int
     L.ptk_convlstm_backward.argtypes = [ldp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.ptk_convlstm_backward_penalty.restype = ctypes.c_int
+    L.ptk_convlstm_backward_penalty.argtypes = [ldp, vp, vp, vp, vp, vp, ctypes.c_int32, vp, vp, vp, sz, vp]
     L.ptk_convlstm_input_grad.restype = ctypes.c_int
     L.ptk_convlstm_input_grad.argtypes = [ldp, vp, vp, vp, sz, vp]
     L.ptk_bce_scores.restype = ctypes.c_int

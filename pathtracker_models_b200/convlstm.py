@@ -45,7 +45,7 @@ def _find_gabor(gabor, gabor_path):
 
 class _ConvLSTMFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False):
+    def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False, penalty_in_graph=False):
         L = _lib.lib()
         B, _, H, W = x.shape
         flat = flat.contiguous()
@@ -64,6 +64,7 @@ class _ConvLSTMFunction(torch.autograd.Function):
                                         _ptr(ws), ws_bytes, stream)
             _lib.check(rc, "ptk_convlstm_forward")
         ctx.dims, ctx.saved_buf, ctx.rbp_iters = dims, saved, rbp_iters
+        ctx.penalty_in_graph = bool(penalty_in_graph and want_penalty)
         if want_states:      # testmode of the rbp branch: h_0 .. h_T (models/convlstm.py:127-135); hs is the first saved block
             n = B * 25 * H * W
             states = saved[: (dims.T + 1) * n * 4].view(torch.float32).view(dims.T + 1, B, 25, H, W).clone()
@@ -72,12 +73,15 @@ class _ConvLSTMFunction(torch.autograd.Function):
         ctx.save_for_backward(x, flat)
         if pen is None:
             pen = torch.ones(1, dtype=torch.float32, device=x.device)    # convlstm.py:151 placeholder
-        ctx.mark_non_differentiable(pen, states)
+        if ctx.penalty_in_graph:      # jacobian_penalty=True: the penalty carries a graph (create_graph=True, convlstm.py:157-160)
+            ctx.mark_non_differentiable(states)
+        else:
+            ctx.mark_non_differentiable(pen, states)
         return out, pen, states
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dout, _dpen, _dstates):
+    def backward(ctx, dout, dpen, _dstates):
         x, flat = ctx.saved_tensors
         L = _lib.lib()
         dims = ctx.dims
@@ -87,7 +91,17 @@ class _ConvLSTMFunction(torch.autograd.Function):
             dflat = torch.empty_like(flat)
             dout = dout.contiguous().float()
             stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-            if ctx.rbp_iters is None:
+            if ctx.penalty_in_graph and dpen is not None:
+                # loss + <dpen, penalty>: the penalty's double back-propagation in closed form (ptk_convlstm_backward_penalty)
+                terms = torch.zeros(1, dtype=torch.float32, device=x.device)
+                dpen = dpen.contiguous().float()
+                rc = L.ptk_convlstm_backward_penalty(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
+                                                     _ptr(dpen), int(ctx.rbp_iters or 0), _ptr(dflat), _ptr(terms), _ptr(ws),
+                                                     ws_bytes, stream)
+                _lib.check(rc, "ptk_convlstm_backward_penalty")
+                if ctx.rbp_iters is not None:
+                    _ConvLSTMFunction.last_rbp_terms = terms
+            elif ctx.rbp_iters is None:
                 rc = L.ptk_convlstm_backward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
                                              _ptr(dflat), _ptr(ws), ws_bytes, stream)
                 _lib.check(rc, "ptk_convlstm_backward")
@@ -103,7 +117,7 @@ class _ConvLSTMFunction(torch.autograd.Function):
                 rc = L.ptk_convlstm_input_grad(ctypes.byref(dims), _ptr(flat), _ptr(dx), _ptr(ws), ws_bytes, stream)
                 _lib.check(rc, "ptk_convlstm_input_grad")
         ctx.saved_buf = None
-        return dx, dflat, None, None, None, None
+        return dx, dflat, None, None, None, None, None
 
 
 class ConvLSTM(nn.Module):
@@ -117,8 +131,6 @@ class ConvLSTM(nn.Module):
         self.jacobian_penalty, self.grad_method = jacobian_penalty, grad_method
         if grad_method not in ('bptt', 'rbp'):
             raise ValueError(f"grad_method must be 'bptt' or 'rbp', got {grad_method!r}")   # the reference silently skips the loop
-        if jacobian_penalty:
-            raise NotImplementedError("jacobian_penalty=True needs a second-order graph; only the value is computed")
         self.conv0 = nn.Conv2d(1, 25, kernel_size=7, padding=3)
         self.conv0.weight.data = _find_gabor(gabor, gabor_path).reshape(25, 1, 7, 7).clone()
         self.unit1 = ConvLSTMCell(25, 25, filt_size)
@@ -148,10 +160,12 @@ class ConvLSTM(nn.Module):
         rbp = self.grad_method == 'rbp'
         # recurrent back-propagation reads only the last two steps: constant-memory checkpoint ring (models/convlstm.py:124-135
         # runs the first T-1 steps under no_grad for exactly that reason); testmode returns every hidden state, so it keeps them
-        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size, int(self.conv_mode), int(rbp and not testmode))
+        dims = _lib.PtkLstmDims(B, self.timesteps, H, W, self.unit1.kernel_size, int(self.conv_mode), int(rbp and not testmode),
+                                int(rbp))
         from .parallel import flat_gradient_hook
         output, pen, states = _ConvLSTMFunction.apply(x.float(), flat_gradient_hook(self, self.flat_parameters()), dims, bool(self.training),
-                                                      int(self.num_iter) if rbp else None, bool(rbp and testmode))
+                                                      int(self.num_iter) if rbp else None, bool(rbp and testmode),
+                                                      bool(self.jacobian_penalty))
         loss = criterion(output, target)                                # convlstm.py:148
         if testmode:                                                     # the bptt branch never fills `states`
             return output, (list(states.unbind(0)) if rbp else []), loss

@@ -443,6 +443,9 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
   float* b0g = cv.take<float>(32);
   float* hg = cv.take<float>(128);
   float* rbp_g = cv.take<float>(S);
+  float* jp_rc = cv.take<float>(S);
+  float* jp_eo = cv.take<float>(S);
+  float* jp_dcx = cv.take<float>(S);
   float* rbp_state = cv.take<float>(64);
   double* rbp_part = cv.take<double>(2 * 148 * 2);
   uint8_t *whF_tc = nullptr, *whD_tc = nullptr, *wxF_tc = nullptr, *wxD_tc = nullptr;
@@ -461,6 +464,7 @@ static size_t lstm_carve(const PtkLstmDims* dm, void* saved, void* ws, LstmDev* 
     d->whF_tc = whF_tc; d->whD_tc = whD_tc; d->conv_mode = dm->conv_mode; d->slots_h_tc = slots_h_tc;
     d->slots_x_tc = slots_x_tc; d->wxF_tc = wxF_tc; d->wxD_tc = wxD_tc; d->dyc_tc = dyc_tc;
     d->rbp_g = rbp_g; d->rbp_state = rbp_state; d->rbp_part = rbp_part;
+    d->jp_rc = jp_rc; d->jp_eo = jp_eo; d->jp_dcx = jp_dcx;
     d->groups = groups;
     d->hs = hs; d->cs = cs; d->gates = gates; d->u = u; d->xt = xt; d->head_stats = hstats;
     d->w0T = w0T; d->wxT = wxT; d->whT = whT; d->whD = whD; d->wxD = wxD; d->bx = bx; d->Xg = Xg; d->G = G;
@@ -474,6 +478,7 @@ static int lstm_bind(LstmDev* d, const PtkLstmDims* dm, const float* x, const fl
   memset(d, 0, sizeof(*d));
   d->B = dm->B; d->T = dm->T; d->H = dm->H; d->W = dm->W; d->KS = dm->K;
   d->ring = dm->ckpt_ring != 0;
+  d->detached = dm->rbp != 0;
   d->x = x;
   int64_t o[20];
   lstm_offsets(dm->K, o);
@@ -543,6 +548,26 @@ int ptk_convlstm_backward_rbp(const PtkLstmDims* dm, const float* x, const float
   LstmDev d;
   if ((rc = lstm_bind(&d, dm, x, params, const_cast<void*>(saved), workspace, st))) return rc;
   d.dout = doutput; d.dparams = dparams;
+  if ((rc = run_convlstm_backward_rbp(d, num_iter, st))) return rc;
+  if (terms_out) PTK_CUDA_OK(cudaMemcpyAsync(terms_out, d.rbp_state + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PTK_OK;
+}
+
+int ptk_convlstm_backward_penalty(const PtkLstmDims* dm, const float* x, const float* params, const void* saved,
+                                  const float* doutput, const float* dpenalty, int32_t num_iter, float* dparams, float* terms_out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = lstm_check(dm, "ptk_convlstm_backward_penalty");
+  if (rc) return rc;
+  if (!x || !params || !saved || !doutput || !dpenalty || !dparams || !workspace) { set_error("ptk_convlstm_backward_penalty: NULL argument"); return PTK_EINVAL; }
+  if (dm->T < 2) { set_error("ptk_convlstm_backward_penalty: the Jacobian penalty needs timesteps >= 2 (models/convlstm.py:140-144)"); return PTK_EINVAL; }
+  if (!dm->rbp && dm->ckpt_ring) { set_error("ptk_convlstm_backward_penalty: BPTT needs the checkpoints of every step; the forward ran with ckpt_ring = 1"); return PTK_EINVAL; }
+  if (dm->rbp && num_iter < 0) { set_error("ptk_convlstm_backward_penalty: num_iter %d < 0", num_iter); return PTK_EINVAL; }
+  if (workspace_bytes < ptk_convlstm_workspace_bytes(dm)) { set_error("ptk_convlstm_backward_penalty: workspace too small"); return PTK_ENOMEM; }
+  cudaStream_t st = (cudaStream_t)stream;
+  LstmDev d;
+  if ((rc = lstm_bind(&d, dm, x, params, const_cast<void*>(saved), workspace, st))) return rc;
+  d.dout = doutput; d.dparams = dparams; d.dpen = dpenalty;
+  if (!dm->rbp) return run_convlstm_backward(d, st);
   if ((rc = run_convlstm_backward_rbp(d, num_iter, st))) return rc;
   if (terms_out) PTK_CUDA_OK(cudaMemcpyAsync(terms_out, d.rbp_state + 2, sizeof(float), cudaMemcpyDeviceToDevice, st));
   return PTK_OK;

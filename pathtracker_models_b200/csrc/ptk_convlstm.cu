@@ -88,6 +88,77 @@ __global__ void penalty_kernel(const float* __restrict__ jh, const float* __rest
   }
 }
 
+// ---- the Jacobian penalty INSIDE the graph (jacobian_penalty=True: create_graph=True at models/convlstm.py:157-160) ---------
+// total = loss + <dpen, pen>,  pen = (jh - .9)+^2 + (jc - .9)+^2,  jh = delta^h *^T Wh,  jc = f_T + v m,  v = delta^c *^T Wh,
+// m = o_{T-1} (1 - tanh^2 c_{T-1})  (m = 0 when h_{T-1}, c_{T-1} are detached leaves: grad_method='rbp').
+// delta^h / delta^c are the gate deltas of step T for the seeds (dh, dc) = (1, 0) / (0, 1).  Differentiating once more:
+//   r_h = d total / d jh,  r_c = d total / d jc,  r_v = r_c m;   rho^h = r_h * Wh,  rho^c = r_v * Wh  (forward convolutions);
+//   d Wh += r_h (star) delta^h + r_v (star) delta^c  (the weight-gradient operator with the roles of input / delta as named);
+//   eps = d total / d (gate pre-activations of step T) through delta^h, delta^c and f_T  (jp_eps_kernel), an extra d c_{T-1},
+//   and through m an extra output-gate delta at step T-1 and one more d c_{T-1} term (jp_seed_kernel).
+// These are added to the ordinary deltas of steps T and T-1, so the rest is the unchanged reverse loop.
+// Checked against double back-propagation in fp64 (oracle/convlstm_oracle.py:jp_total_grads) and the reference's own gradients.
+__global__ void jp_seed_kernel(float* jh_rh, float* v_rv, const float* __restrict__ gates_T, const float* __restrict__ gates_Tm1,
+                               const float* __restrict__ c_Tm1, const float* __restrict__ dpen, float* rc_out, float* eo, float* dcx,
+                               int B, int P) {
+  const size_t n = (size_t)B * LC * P;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(e % P), c = (int)((e / P) % LC), b = (int)(e / ((size_t)P * LC));
+    const size_t g0 = ((size_t)b * LG + c) * P + pix, gs = (size_t)LC * P;
+    float m = 0.f, o1 = 0.f, tc1 = 0.f, v = 0.f;
+    if (gates_Tm1) { o1 = gates_Tm1[g0 + 3 * gs]; tc1 = tanhf(c_Tm1[e]); m = o1 * (1.0f - tc1 * tc1); v = v_rv[e]; }
+    const float jc = gates_T[g0 + gs] + v * m;
+    const float w2 = 2.0f * dpen[e];
+    const float rh = w2 * fmaxf(jh_rh[e] - 0.9f, 0.f), rc = w2 * fmaxf(jc - 0.9f, 0.f), kk = rc * v;
+    jh_rh[e] = rh;
+    if (v_rv) v_rv[e] = rc * m;
+    rc_out[e] = rc;
+    eo[e] = kk * (1.0f - tc1 * tc1) * o1 * (1.0f - o1);
+    dcx[e] = kk * o1 * (-2.0f * tc1 * (1.0f - tc1 * tc1));
+  }
+}
+// rho^h (in place -> eps), rho^c (null when detached), r_c;  dcx += the step-T part
+__global__ void jp_eps_kernel(float* rhoH_eps, const float* __restrict__ rhoC, const float* __restrict__ rcv,
+                              const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                              float* dcx, int B, int P) {
+  const size_t n = (size_t)B * LC * P;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(e % P), c = (int)((e / P) % LC), b = (int)(e / ((size_t)P * LC));
+    const size_t g0 = ((size_t)b * LG + c) * P + pix, gs = (size_t)LC * P;
+    const float i = gates[g0], f = gates[g0 + gs], g = gates[g0 + 2 * gs], o = gates[g0 + 3 * gs];
+    const float cp = c_prev[e], s = tanhf(c_cur[e]), D = 1.0f - s * s, kap = o * D;
+    const float ip = i * (1.0f - i), fp = f * (1.0f - f), op = o * (1.0f - o), gp = 1.0f - g * g;
+    const float ipp = ip * (1.0f - 2.0f * i), fpp = fp * (1.0f - 2.0f * f), opp = op * (1.0f - 2.0f * o), gpp = -2.0f * g * gp;
+    const float rHi = rhoH_eps[g0], rHf = rhoH_eps[g0 + gs], rHc = rhoH_eps[g0 + 2 * gs], rHo = rhoH_eps[g0 + 3 * gs];
+    float rCi = 0.f, rCf = 0.f, rCc = 0.f;
+    if (rhoC) { rCi = rhoC[g0]; rCf = rhoC[g0 + gs]; rCc = rhoC[g0 + 2 * gs]; }
+    const float Q = rHi * g * ip + rHf * cp * fp + rHc * i * gp;
+    const float lam = rHo * op * D + Q * o * (-2.0f * s * D);          // d total / d c_T through tanh(c_T)
+    const float ai = rHi * kap + rCi, af = rHf * kap + rCf, ac = rHc * kap + rCc;   // d total / d (delta-without-kappa) per gate
+    rhoH_eps[g0] = lam * g * ip + ai * g * ipp + ac * ip * gp;
+    rhoH_eps[g0 + gs] = lam * cp * fp + af * cp * fpp + rcv[e] * fp;
+    rhoH_eps[g0 + 2 * gs] = lam * i * gp + ai * ip * gp + ac * i * gpp;
+    rhoH_eps[g0 + 3 * gs] = rHo * s * opp + Q * D * op;
+    dcx[e] += lam * f + af * fp;
+  }
+}
+// delta[:, gate_lo : gate_lo + n_gates] += extra (same for delta_sum);  dc += dcx
+__global__ void lstm_add_kernel(float* delta, float* delta_sum, const float* __restrict__ extra, int gate_lo, int n_gates,
+                                float* dc, const float* __restrict__ dcx, int B, int P) {
+  const size_t n = (size_t)B * LC * P;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(e % P), c = (int)((e / P) % LC), b = (int)(e / ((size_t)P * LC));
+    const size_t g0 = ((size_t)b * LG + c) * P + pix, gs = (size_t)LC * P;
+    const size_t x0 = ((size_t)b * n_gates * LC + c) * P + pix;
+    for (int k = 0; k < n_gates; ++k) {
+      const float x = extra[x0 + k * gs];
+      delta[g0 + (gate_lo + k) * gs] += x;
+      delta_sum[g0 + (gate_lo + k) * gs] += x;
+    }
+    if (dc) dc[e] += dcx[e];
+  }
+}
+
 // ---- head: BatchNorm (batch statistics) + 1x1 conv 25 -> 2, forward and backward; one CTA per channel ----------
 __global__ void __launch_bounds__(512) head_stats_kernel(const float* __restrict__ h, float* stats, int B, int P) {
   __shared__ double sh[16];
@@ -240,9 +311,48 @@ static int convlstm_penalty_t(const LstmDev& d, cudaStream_t st) {
                                            nullptr, nullptr, 0, d.B, P);
   ConvGArgs c2{d.delta, d.whD, nullptr, nullptr, d.dc, d.B, d.H, d.W, LG, LC, 0};
   if ((rc = recurrent_conv<KS>(d, c2, true, st))) return rc;
-  penalty_kernel<<<148 * 4, 256, 0, st>>>(d.dh, d.dc, d.gates_at(T), T >= 2 ? d.gates_at(T - 1) : nullptr,
+  penalty_kernel<<<148 * 4, 256, 0, st>>>(d.dh, d.dc, d.gates_at(T), (T >= 2 && !d.detached) ? d.gates_at(T - 1) : nullptr,
                                           d.c_at(T - 1), d.penalty, d.B, P);
   PTK_LAUNCH_OK("penalty_kernel");
+  return PTK_OK;
+}
+
+// second-order seeds of the Jacobian penalty (see jp_seed_kernel): leaves eps (4 gates) in d.G, the extra d c_{T-1} in
+// d.jp_dcx, the step T-1 output-gate term in d.jp_eo and the direct d Wh terms in the weight-gradient slots (overwritten:
+// every later recurrent weight gradient must accumulate).  Uses d.dh, d.dc, d.delta, d.Xg as scratch: call it first.
+template <int KS>
+static int convlstm_penalty_seed(const LstmDev& d, cudaStream_t st) {
+  const int P = d.H * d.W, taps = KS * KS, T = d.T;
+  const bool tail = !d.detached && T >= 2;      // the path c_{T-1} -> h_{T-1} -> gates_T -> c_T exists in the graph
+  int rc;
+  if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 0, d.whT, (size_t)4 * LC * taps * 32, st))) return rc;
+  if ((rc = recurrent_prep<KS>(d, false, st))) return rc;
+  lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(nullptr, 1.0f, nullptr, 0.0f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
+                                           nullptr, nullptr, 0, d.B, P);
+  ConvGArgs c1{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0};
+  if ((rc = recurrent_conv<KS>(d, c1, true, st))) return rc;                       // jh
+  if (tail) {
+    lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(nullptr, 0.0f, nullptr, 1.0f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.Xg,
+                                             nullptr, nullptr, 0, d.B, P);
+    ConvGArgs c2{d.Xg, d.whD, nullptr, nullptr, d.dc, d.B, d.H, d.W, LG, LC, 0};
+    if ((rc = recurrent_conv<KS>(d, c2, true, st))) return rc;                     // v
+  }
+  jp_seed_kernel<<<148 * 4, 256, 0, st>>>(d.dh, tail ? d.dc : nullptr, d.gates_at(T), tail ? d.gates_at(T - 1) : nullptr,
+                                          d.c_at(T - 1), d.dpen, d.jp_rc, d.jp_eo, d.jp_dcx, d.B, P);
+  PTK_LAUNCH_OK("jp_seed_kernel");
+  WgradGArgs w1{d.dh, d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, 0};
+  if ((rc = recurrent_wgrad<KS>(d, w1, st))) return rc;                            // r_h (star) delta^h
+  ConvGArgs f1{d.dh, d.whT, nullptr, nullptr, d.G, d.B, d.H, d.W, LC, LG, 0};
+  if ((rc = recurrent_conv<KS>(d, f1, false, st))) return rc;                      // rho^h
+  if (tail) {
+    WgradGArgs w2{d.dc, d.Xg, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, 1};
+    if ((rc = recurrent_wgrad<KS>(d, w2, st))) return rc;                          // r_v (star) delta^c
+    ConvGArgs f2{d.dc, d.whT, nullptr, nullptr, d.delta, d.B, d.H, d.W, LC, LG, 0};
+    if ((rc = recurrent_conv<KS>(d, f2, false, st))) return rc;                    // rho^c
+  }
+  jp_eps_kernel<<<148 * 4, 256, 0, st>>>(d.G, tail ? d.delta : nullptr, d.jp_rc, d.gates_at(T), d.c_at(T - 1), d.c_at(T),
+                                         d.jp_dcx, d.B, P);
+  PTK_LAUNCH_OK("jp_eps_kernel");
   return PTK_OK;
 }
 
@@ -257,6 +367,8 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
   if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 1, d.whD, (size_t)LG * taps * 32, st))) return rc;
   if ((rc = recurrent_prep<KS>(d, true, st))) return rc;
   if ((rc = launch_prepg(d.wx, 4, LC, LC, taps, 1, d.wxD, (size_t)LG * taps * 32, st))) return rc;
+  const bool jp = d.dpen != nullptr;      // the penalty is part of the graph: its second-order seeds join steps T and T-1
+  if (jp && (rc = convlstm_penalty_seed<KS>(d, st))) return rc;
   // head: d out -> dh_T, d bn / conv6
   head_bwd_kernel<<<LC, 512, 0, st>>>(d.h_at(d.T), d.head_stats, d.bn_w, d.bn_b, d.w6, d.dout, d.dh, d.head_grads, d.B, P);
   PTK_LAUNCH_OK("head_bwd_kernel");
@@ -267,9 +379,11 @@ static int convlstm_backward_t(const LstmDev& d, cudaStream_t st) {
       ProfileScope ps(PTK_PROF_POINT_BWD, st);
       lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(d.dh, 0.f, d.dc, 0.f, d.gates_at(t), d.c_at(t - 1), d.c_at(t), d.delta, d.dc,
                                                d.delta_sum, first, d.B, P);
+      if (jp && first) lstm_add_kernel<<<148 * 4, 256, 0, st>>>(d.delta, d.delta_sum, d.G, 0, 4, d.dc, d.jp_dcx, d.B, P);
+      if (jp && t == d.T - 1) lstm_add_kernel<<<148 * 4, 256, 0, st>>>(d.delta, d.delta_sum, d.jp_eo, 3, 1, nullptr, nullptr, d.B, P);
       PTK_LAUNCH_OK("lstm_bwd_kernel");
     }
-    WgradGArgs w{d.h_at(t - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, !first};
+    WgradGArgs w{d.h_at(t - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, jp || !first};
     if ((rc = recurrent_wgrad<KS>(d, w, st))) return rc;
     if (t > 1) {
       ConvGArgs c{d.delta, d.whD, nullptr, nullptr, d.dh, d.B, d.H, d.W, LG, LC, 0};
@@ -364,6 +478,8 @@ static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t 
   if ((rc = launch_prepg(d.wh, 4, LC, LC, taps, 1, d.whD, (size_t)LG * taps * 32, st))) return rc;
   if ((rc = recurrent_prep<KS>(d, true, st))) return rc;
   if ((rc = launch_prepg(d.wx, 4, LC, LC, taps, 1, d.wxD, (size_t)LG * taps * 32, st))) return rc;
+  const bool jp = d.dpen != nullptr;      // penalty in the graph: one-step seeds (the leaves h_{T-1}, c_{T-1} are detached)
+  if (jp && (rc = convlstm_penalty_seed<KS>(d, st))) return rc;
   // head: d out -> dh_T (= grad of dummyhgru.backward), d bn / conv6.  v_prev lives in d.dc, v_new in d.dh.
   head_bwd_kernel<<<LC, 512, 0, st>>>(d.h_at(T), d.head_stats, d.bn_w, d.bn_b, d.w6, d.dout, d.dc, d.head_grads, d.B, P);
   PTK_LAUNCH_OK("head_bwd_kernel");
@@ -383,7 +499,8 @@ static int convlstm_backward_rbp_t(const LstmDev& d, int num_iter, cudaStream_t 
   // one cell-step backward with dh_T := g (dc_T = 0): deltas of the last step only
   lstm_bwd_kernel<<<148 * 4, 256, 0, st>>>(d.rbp_g, 0.f, nullptr, 0.f, d.gates_at(T), d.c_at(T - 1), d.c_at(T), d.delta,
                                            nullptr, d.delta_sum, 1, d.B, P);
-  WgradGArgs w{d.h_at(T - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, 0};
+  if (jp) lstm_add_kernel<<<148 * 4, 256, 0, st>>>(d.delta, d.delta_sum, d.G, 0, 4, nullptr, nullptr, d.B, P);
+  WgradGArgs w{d.h_at(T - 1), d.delta, d.slots_h, d.B, d.H, d.W, LC, LG, d.groups, jp ? 1 : 0};
   if ((rc = recurrent_wgrad<KS>(d, w, st))) return rc;
   return convlstm_grad_tail<KS>(d, st);
 }

@@ -28,6 +28,9 @@ struct LstmDev {
   // scratch
   float *G, *delta, *delta_sum, *dh, *dc;
   float *slots_h, *slots_x, *slots_0, *bx_grad, *b0_grad, *head_grads;
+  float *jp_rc, *jp_eo, *jp_dcx;        // Jacobian penalty in the graph: d/d jc, the step T-1 output-gate term, the extra d c_{T-1}
+  const float* dpen;                    // d(total)/d(penalty) [B,25,H,W] (null: the penalty is a constant, create_graph=False)
+  int detached;                         // grad_method='rbp': h_{T-1}, c_{T-1} are detached leaves (models/convlstm.py:130-131)
   float *rbp_g, *rbp_state;             // RBP: Neumann sum g [B,25,P]; state {|v_prev|, terminated, accepted terms}
   double* rbp_part;                     // [RBP_CTAS][2] partial sums of squares
   // I/O

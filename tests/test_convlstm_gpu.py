@@ -216,3 +216,72 @@ def test_convlstm_input_gradient_vs_fp64_oracle(grad_method):
     lhs = float((x.grad.double() * x.detach().double()).sum())
     rhs = float((m.conv0.weight.grad.double() * m.conv0.weight.detach().double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs), 1e-12), (lhs, rhs)
+
+
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("name", ["convlstm_k7_jp", "convlstm_k7_jp_t2", "convlstm_k15_jp", "convlstm_k7_rbp_jp"])
+def test_convlstm_jacobian_penalty_in_graph_vs_reference(name, conv_mode):
+    """jacobian_penalty=True (create_graph=True, models/convlstm.py:157-160): the training loop back-propagates
+    loss + 10 * penalty.mean() (mainclean.py:192-196).  The CUDA path takes the penalty's double back-propagation in closed
+    form (ptk_convlstm_backward_penalty); fixtures = the reference's own gradients of that sum, both gradient methods."""
+    import os
+    import numpy as np
+    from oracle import convlstm_oracle as CO
+    from pathtracker_models_b200 import convlstm
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case(name)
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    method = "rbp" if "rbp" in name else "bptt"
+    B, T, H, W = case["shape"]
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method=method,
+                          num_iter=int(z["num_iter"]), jacobian_penalty=True)
+    m.conv_mode = _mode(conv_mode)
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    assert pen.requires_grad
+    (loss + pen.mean() * 1e1).backward()
+    assert rel_err(out, case["output"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
+    assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))
+    # checker: the fp64 double back-propagation oracle on the GPU, itself pinned to the reference on the CPU suite
+    p64 = {k: v.double().cuda().requires_grad_(True) for k, v in case["sd"].items()}
+    _, _, _, g64 = CO.jp_total_grads(case["x"].cuda(), p64, T, case["target"].cuda(), grad_method=method, num_iter=int(z["num_iter"]))
+    for n, g in case["grads"].items():
+        assert rel_err(g64[n], g) < (2e-7 if g.numel() > 4096 else 1e-9), n
+    bad = []
+    for n, prm in m.named_parameters():
+        e = rel_err(prm.grad, g64[n])
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
+    # the penalty alone (no loss term) and the loss alone both go through the same entry point
+    m.zero_grad()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    loss.backward()
+    m2 = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method=method, num_iter=int(z["num_iter"]))
+    m2.conv_mode = _mode(conv_mode)
+    m2.load_state_dict(case["sd"])
+    m2 = m2.cuda().train()
+    _, pen2, loss2 = m2(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    assert not pen2.requires_grad and torch.equal(pen2, pen.detach())
+    loss2.backward()
+    for (n, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
+        assert rel_err(a.grad, b.grad) < 1e-6, n     # d pen = 0: the seeds vanish, the reverse loop is the ordinary one
+
+
+@pytest.mark.parametrize("name", ["convlstm_k7_rbp", "convlstm_k7_rbp_trunc"])
+def test_convlstm_rbp_penalty_value_vs_reference(name):
+    """grad_method='rbp': h_{T-1}, c_{T-1} are detached leaves (models/convlstm.py:130-131), so the second product is f_T alone"""
+    import os
+    import numpy as np
+    from pathtracker_models_b200 import convlstm
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case(name)
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, T, H, W = case["shape"]
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method='rbp', num_iter=int(z["num_iter"]))
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
+    _, pen, _ = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))

@@ -40,3 +40,35 @@ def test_rbp_oracle_matches_reference_fp64(name):
     assert terms in (calls, calls - 1) and terms <= num_iter     # the reference tried `calls` terms (the last may be rejected)
     for n, g in case["grads"].items():
         assert rel_err(grads[n], g) < (2e-7 if g.numel() > 4096 else 1e-9), n
+
+
+@pytest.mark.parametrize("name", ["convlstm_k7_jp", "convlstm_k7_jp_t2", "convlstm_k15_jp", "convlstm_k7_rbp_jp"])
+def test_jacobian_penalty_in_graph_oracle_matches_reference_fp64(name):
+    """jacobian_penalty=True (create_graph=True, models/convlstm.py:157-160): gradients of loss + 10 * penalty.mean()
+    (mainclean.py:192-196).  Fixture = the reference itself in fp64, both gradient methods."""
+    import os
+    import numpy as _np
+    from oracle import convlstm_oracle as CO
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case(name)
+    z = _np.load(os.path.join(GOLDEN, name + ".npz"))
+    method = "rbp" if "rbp" in name else "bptt"
+    p = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
+    out, loss, pen, grads = CO.jp_total_grads(case["x"], p, case["shape"][1], case["target"], grad_method=method,
+                                              num_iter=int(z["num_iter"]))
+    assert rel_err(out, case["output"]) < 1e-10 and abs(loss - case["loss"]) < 1e-10
+    assert rel_err(pen, case["penalty"]) < 1e-9
+    for n, g in case["grads"].items():
+        assert rel_err(grads[n], g) < (2e-7 if g.numel() > 4096 else 1e-9), n
+    prs = _np.random.RandomState(case["proj_seed"])
+    for n in case["proj"]:
+        g = grads[n].detach().numpy().ravel()
+        v = prs.normal(0, 1, (4, g.size))
+        assert _np.allclose(v @ g, case["proj"][n], rtol=1e-8, atol=1e-12 * max(1.0, case["gmax"][n])), n
+    if case["grads"]:      # the penalty term must matter in the fixture: the loss-only gradient is measurably different
+        if method == "bptt":
+            _, _, _, g0 = oracle_run(case)
+        else:
+            p0 = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
+            _, _, g0, _ = CO.rbp_grads(case["x"], p0, case["shape"][1], case["target"], int(z["num_iter"]))
+        assert max(rel_err(g0[n], g) for n, g in case["grads"].items() if "unit1.Wh" in n) > 1e-3
