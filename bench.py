@@ -32,7 +32,7 @@ FP32_FFMA_PEAK_TFLOPS = 74.4   # nominal 148 SM x 128 lanes x 2 x 1.965 GHz (not
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the headline shape, from the
 # committed `ncu --set full` capture named in NCU_TRAFFIC_SOURCE (bench.py cannot run ncu on itself)
 NCU_TRAFFIC_BYTES = {"bf16x3": 8.665e6, "fp32": 8.623e6}
-NCU_TRAFFIC_SOURCE = "profiles/r3z_kernels_full.txt (conv7_tc2_kernel forward launch, final build: 8.67 MB; fp32: profiles/r1a_conv7_ffma_full.txt)"
+NCU_TRAFFIC_SOURCE = "profiles/r5z_kernels_full.txt (conv7_tc2_kernel forward launch, final build: 8.67 MB; fp32: profiles/r1a_conv7_ffma_full.txt)"
 
 
 def int_flop_per_seq(T_, HW_):

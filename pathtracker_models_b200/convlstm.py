@@ -45,7 +45,7 @@ def _find_gabor(gabor, gabor_path):
 
 class _ConvLSTMFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False, penalty_in_graph=False):
+    def forward(ctx, x, flat, dims, want_penalty, rbp_iters=None, want_states=False, penalty_in_graph=False, owner=None):
         L = _lib.lib()
         B, _, H, W = x.shape
         flat = flat.contiguous()
@@ -65,6 +65,7 @@ class _ConvLSTMFunction(torch.autograd.Function):
             _lib.check(rc, "ptk_convlstm_forward")
         ctx.dims, ctx.saved_buf, ctx.rbp_iters = dims, saved, rbp_iters
         ctx.penalty_in_graph = bool(penalty_in_graph and want_penalty)
+        ctx.owner = owner            # the module instance that receives `last_rbp_terms` (per module, not process-wide)
         if want_states:      # testmode of the rbp branch: h_0 .. h_T (models/convlstm.py:127-135); hs is the first saved block
             n = B * 25 * H * W
             states = saved[: (dims.T + 1) * n * 4].view(torch.float32).view(dims.T + 1, B, 25, H, W).clone()
@@ -99,8 +100,8 @@ class _ConvLSTMFunction(torch.autograd.Function):
                                                      _ptr(dpen), int(ctx.rbp_iters or 0), _ptr(dflat), _ptr(terms), _ptr(ws),
                                                      ws_bytes, stream)
                 _lib.check(rc, "ptk_convlstm_backward_penalty")
-                if ctx.rbp_iters is not None:
-                    _ConvLSTMFunction.last_rbp_terms = terms
+                if ctx.rbp_iters is not None and ctx.owner is not None:
+                    ctx.owner.last_rbp_terms = terms
             elif ctx.rbp_iters is None:
                 rc = L.ptk_convlstm_backward(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
                                              _ptr(dflat), _ptr(ws), ws_bytes, stream)
@@ -110,14 +111,15 @@ class _ConvLSTMFunction(torch.autograd.Function):
                 rc = L.ptk_convlstm_backward_rbp(ctypes.byref(dims), _ptr(x), _ptr(flat), _ptr(ctx.saved_buf), _ptr(dout),
                                                  int(ctx.rbp_iters), _ptr(dflat), _ptr(terms), _ptr(ws), ws_bytes, stream)
                 _lib.check(rc, "ptk_convlstm_backward_rbp")
-                _ConvLSTMFunction.last_rbp_terms = terms      # device tensor; read it only when you want the sync
+                if ctx.owner is not None:
+                    ctx.owner.last_rbp_terms = terms          # device tensor; read it only when you want the sync
             dx = None
             if ctx.needs_input_grad[0]:       # the reference is differentiable w.r.t. the image: dx = conv0^T (d loss / d u)
                 dx = torch.empty_like(x)
                 rc = L.ptk_convlstm_input_grad(ctypes.byref(dims), _ptr(flat), _ptr(dx), _ptr(ws), ws_bytes, stream)
                 _lib.check(rc, "ptk_convlstm_input_grad")
         ctx.saved_buf = None
-        return dx, dflat, None, None, None, None, None
+        return dx, dflat, None, None, None, None, None, None
 
 
 class ConvLSTM(nn.Module):
@@ -141,6 +143,7 @@ class ConvLSTM(nn.Module):
         # the two per-step convolutions of the time loops (h -> gates and its transpose): 3-pass split-bf16 tcgen05
         # implicit GEMMs (default) or strict-fp32 CUDA cores; same parity gate (tests/test_convlstm_gpu.py)
         self.conv_mode = _lib.PTK_CONV_BF16X3
+        self.last_rbp_terms = None      # rbp: accepted Neumann terms of the latest backward (device tensor, 1 float)
 
     def flat_parameters(self):
         # registration order == C ABI order; by attribute (not parameters()) so that nn.DataParallel replicas work
@@ -165,7 +168,7 @@ class ConvLSTM(nn.Module):
         from .parallel import flat_gradient_hook
         output, pen, states = _ConvLSTMFunction.apply(x.float(), flat_gradient_hook(self, self.flat_parameters()), dims, bool(self.training),
                                                       int(self.num_iter) if rbp else None, bool(rbp and testmode),
-                                                      bool(self.jacobian_penalty))
+                                                      bool(self.jacobian_penalty), self)
         loss = criterion(output, target)                                # convlstm.py:148
         if testmode:                                                     # the bptt branch never fills `states`
             return output, (list(states.unbind(0)) if rbp else []), loss

@@ -102,7 +102,6 @@ def test_convlstm_rbp_grads_vs_reference(name, conv_mode):
     import numpy as np
     from oracle import convlstm_oracle as CO
     from pathtracker_models_b200 import convlstm
-    from pathtracker_models_b200.convlstm import _ConvLSTMFunction
     from tests.golden_util import GOLDEN
     case = load_convlstm_case(name)
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -117,7 +116,7 @@ def test_convlstm_rbp_grads_vs_reference(name, conv_mode):
     assert rel_err(out, case["output"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
     p64 = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
     _, _, g64, terms = CO.rbp_grads(case["x"], p64, T, case["target"], num_iter)
-    assert int(_ConvLSTMFunction.last_rbp_terms.item()) == terms
+    assert int(m.last_rbp_terms.item()) == terms
     bad = []
     for n, p in m.named_parameters():
         e = rel_err(p.grad, case["grads"][n])

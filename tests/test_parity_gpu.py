@@ -82,10 +82,10 @@ def test_long_horizon_logits_and_all_grads_vs_fp64_reference(name, kind, conv_mo
 # path: operands are rounded to 8 mantissa bits (2^-9 ~ 2e-3 relative per element).  Its error is
 # documented and bounded here; it is opt-in (conv_mode=PTK_CONV_BF16) and never the default.
 BF16_LOGIT_TOL = 2e-2
-BF16_GRAD_TOL = 5e-2
+BF16_GRAD_TOL = 3e-2     # measured worst over these cases: 1.28e-2 (int_tile), 1.17e-2 (hgru_small); T = 64: 3.7e-3 / 6.3e-3 (profiles/r4q_parity_report.txt)
 
 
-@pytest.mark.parametrize("name,kind,kw", [c for c in CASES if c[0] in ("int_small", "int_tile", "int_64px", "hgru_small")])
+@pytest.mark.parametrize("name,kind,kw", [c for c in CASES if c[0] in ("int_small", "int_tile", "int_64px", "hgru_small", "hgru_tile", "int_cfg1")])
 def test_bf16_single_pass_mode_error_is_bounded(name, kind, kw):
     from pathtracker_models_b200 import _lib
     case = load_case(name)
