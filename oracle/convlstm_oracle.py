@@ -117,8 +117,12 @@ def jp_total_grads(x, p, timesteps, target, grad_method="bptt", num_iter=50, wei
         return out, loss, pen.detach(), grads
     out = F.conv2d(F.batch_norm(hT, None, None, p["bn.weight"], p["bn.bias"], True, 0.0, 1e-3), p["conv6.weight"], p["conv6.bias"])
     loss = F.cross_entropy(out, target)
-    pg = torch.autograd.grad(loss + pen.mean() * weight, [p[k] for k in keys], allow_unused=True)
-    return out.detach(), loss.item(), pen.detach(), {k: g for k, g in zip(keys, pg)}
+    wrt = [p[k] for k in keys] + ([x] if x.requires_grad else [])          # bptt: also d total / d x when asked for (saliency)
+    pg = torch.autograd.grad(loss + pen.mean() * weight, wrt, allow_unused=True)
+    grads = {k: g for k, g in zip(keys, pg)}
+    if x.requires_grad:
+        grads["__x__"] = pg[-1]
+    return out.detach(), loss.item(), pen.detach(), grads
 
 
 STATE_KEYS = {"w0": "conv0.weight", "b0": "conv0.bias", "bn_w": "bn.weight", "bn_b": "bn.bias",

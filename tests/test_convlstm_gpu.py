@@ -284,3 +284,47 @@ def test_convlstm_rbp_penalty_value_vs_reference(name):
     m = m.cuda().train()
     _, pen, _ = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
     assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))
+
+
+@pytest.mark.parametrize("method", ["bptt", "rbp"])
+@pytest.mark.parametrize("filt,B,T,H,W", [(15, 3, 5, 32, 64), (7, 1, 8, 64, 32)])
+def test_convlstm_jacobian_penalty_wide_frames_vs_fp64_oracle(filt, B, T, H, W, method):
+    """the in-graph penalty on frames with real halo neighbours, an odd batch and a longer loop (the second-order seeds sit
+    at steps T and T-1 only, whatever T is), with a penalty weight other than the training loop's 10 and the input gradient
+    (saliency through the penalty).  Checker: fp64 double back-propagation (oracle, pinned to the reference on the CPU suite)."""
+    import numpy as np
+    from oracle import convlstm_oracle as CO
+    from oracle.gen_golden import convlstm_weights
+    from pathtracker_models_b200 import convlstm
+    base = load_convlstm_case("convlstm_k7_small")
+    rs = np.random.RandomState(78)
+    like = {k: torch.zeros(s) for k, s in convlstm_shapes(filt).items()}
+    like["conv0.weight"] = base["gabor"].reshape(25, 1, 7, 7).clone()
+    sd = convlstm_weights(like, 6)
+    x = torch.from_numpy(rs.rand(B, 1, H, W))
+    tgt = torch.from_numpy((rs.rand(B, H, W) > 0.5).astype(np.int64))
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=filt, gabor=base["gabor"], grad_method=method, num_iter=6, jacobian_penalty=True)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    xg = x.float().cuda().requires_grad_(True)
+    out, pen, loss = m(xg, 0, 0, tgt.cuda(), torch.nn.CrossEntropyLoss())
+    (loss + 3.0 * pen.mean()).backward()
+    p64 = {k: v.double().cuda().requires_grad_(True) for k, v in sd.items()}
+    x64 = x.cuda().requires_grad_(True)
+    o64, l64, pen64, g64 = CO.jp_total_grads(x64, p64, T, tgt.cuda(), grad_method=method, num_iter=6, weight=3.0)
+    assert rel_err(out, o64) < REL_TOL and abs(loss.item() - l64) < 1e-5
+    assert rel_err(pen, pen64) < 4 * REL_TOL
+    assert float(pen64.max()) > 0
+    # the same rule as the fixture cases (SURVEY 8c): 1e-4, or 4 x the fp32 error of the reference algorithm itself on this input
+    # (conv0.bias is a heavily cancelling sum: the fp32 oracle is 1e-4 off there on the filt-15 cases)
+    p32 = {k: v.float().cuda().requires_grad_(True) for k, v in sd.items()}
+    _, _, _, g32 = CO.jp_total_grads(x.float().cuda(), p32, T, tgt.cuda(), grad_method=method, num_iter=6, weight=3.0)
+    bad = []
+    for n, prm in m.named_parameters():
+        e, allowed = rel_err(prm.grad, g64[n]), max(2 * REL_TOL, NOISE_MULT * rel_err(g32[n], g64[n]))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, bad
+    assert xg.grad is not None and torch.isfinite(xg.grad).all() and float(xg.grad.abs().max()) > 0
+    if method == "bptt":
+        assert rel_err(xg.grad, g64["__x__"]) <= 2 * REL_TOL
