@@ -119,3 +119,49 @@ def test_gru_writes_stay_inside_caller_buffers(conv_mode):
             out.sum().backward()
             _check(live)
         m.zero_grad()
+
+
+@pytest.mark.parametrize("family", ["int", "hgru", "convlstm", "gru"])
+def test_perturbed_cta_scheduling_changes_no_bits(family):
+    """stand-in for racecheck / synccheck: the same forward + backward with and without a second stream saturating the SMs
+    (large GEMMs), which changes which CTAs of a launch are co-resident, in what order they start and how far the
+    programmatic-dependent-launch prologues run ahead.  The last-CTA folds, per-CTA accumulator slots and PDL waits must make
+    the result independent of all that: every output and gradient bit-identical."""
+    from pathtracker_models_b200 import InT, ffhgru_hierarchy, kys, convlstm, synth_pathtracker
+    from tests.convlstm_util import load_convlstm_case
+    torch.manual_seed(3)
+    if family == "convlstm":
+        m = convlstm.ConvLSTM(timesteps=6, filt_size=15, gabor=load_convlstm_case("convlstm_k7_small")["gabor"],
+                              jacobian_penalty=True).cuda().train()
+        x = torch.rand(8, 1, 32, 32, device="cuda")
+        tgt = (torch.rand(8, 32, 32, device="cuda") > 0.5).long()
+
+        def run():
+            m.zero_grad()
+            out, pen, loss = m(x, 0, 0, tgt, torch.nn.CrossEntropyLoss())
+            (loss + pen.mean()).backward()
+            return [out.detach().clone()] + [p.grad.clone() for p in m.parameters()]
+    else:
+        m = {"int": lambda: InT.InT(32, 8, 7), "hgru": lambda: ffhgru_hierarchy.FFhGRU(32, 8, 7),
+             "gru": lambda: kys.GRU(dimensions=64, timesteps=8, kernel_size=7)}[family]().cuda()
+        x, y = synth_pathtracker(16, 8, 32, 32)
+
+        def run():
+            m.zero_grad()
+            out = m(x)[0]
+            torch.nn.functional.binary_cross_entropy_with_logits(out, y.view_as(out)).backward()
+            return [out.detach().clone()] + [p.grad.clone() for p in m.parameters() if p.grad is not None]
+    quiet = run()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    a = torch.randn(6144, 6144, device="cuda", dtype=torch.bfloat16)
+    b = torch.empty_like(a)
+    for rep in range(3):
+        with torch.cuda.stream(side):
+            for _ in range(40 + 20 * rep):
+                torch.mm(a, a, out=b)
+        noisy = run()
+        torch.cuda.synchronize()
+        assert len(noisy) == len(quiet)
+        for i, (u, v) in enumerate(zip(quiet, noisy)):
+            assert torch.equal(u, v), f"tensor {i} differs under perturbed scheduling (repeat {rep})"
