@@ -651,7 +651,8 @@ def run_convlstm(args, dev, world, rank):
     B, T_, HW_ = args.batch, args.frames, args.size
     gabor = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "convlstm_k7_small.npz"))["gabor"]).float()
     torch.manual_seed(0)
-    m = convlstm.ConvLSTM(timesteps=T_, filt_size=15, gabor=gabor).to(dev).train()
+    jp = bool(getattr(args, "jacobian_penalty", False))      # the penalty inside the graph: loss + 10 * penalty.mean() (mainclean.py:192-196)
+    m = convlstm.ConvLSTM(timesteps=T_, filt_size=15, gabor=gabor, jacobian_penalty=jp).to(dev).train()
     m.conv_mode = _lib.PTK_CONV_FP32 if args.conv_mode == "fp32" else _lib.PTK_CONV_BF16X3
     clips, y = synth_pathtracker(B, 2, HW_, HW_, device=dev)
     x = clips[:, 0:1, 0].contiguous()                                               # [B,1,H,W] static image
@@ -661,6 +662,8 @@ def run_convlstm(args, dev, world, rank):
     def step():
         m.zero_grad(set_to_none=True)
         out, pen, loss = m(x, 0, 0, tgt, crit)
+        if jp:
+            loss = loss + pen.mean() * 1e1
         loss.backward()
         return loss
 
@@ -670,7 +673,8 @@ def run_convlstm(args, dev, world, rank):
     print(json.dumps({"metric": metric_name("convlstm", T_), "value": B * steps / (ms / 1e3), "unit": UNIT,
                       "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])" % (T_, B, HW_, HW_),
+                      "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])%s"
+                                             % (T_, B, HW_, HW_, ", jacobian_penalty=True: loss + 10 * penalty.mean()" if jp else ""),
                                  "conv_mode": "fp32" if args.conv_mode == "fp32" else "bf16x3"},
                       "gpu_launches": launches,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
@@ -745,6 +749,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other_configs block (BASELINE configs[2]-[4]) of the default run")
+    ap.add_argument("--jacobian-penalty", action="store_true", help="--model convlstm: jacobian_penalty=True, back-propagate loss + 10 * penalty.mean()")
     ap.add_argument("--model", default="int", choices=["int", "hgru", "convlstm", "gru"], help="non-headline configs (BASELINE configs[2..4])")
     ap.add_argument("--eval", action="store_true", help="forward-only throughput (secondary line)")
     ap.add_argument("--frames", type=int, default=T)
