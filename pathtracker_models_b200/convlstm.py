@@ -66,6 +66,8 @@ class _ConvLSTMFunction(torch.autograd.Function):
         ctx.dims, ctx.saved_buf, ctx.rbp_iters = dims, saved, rbp_iters
         ctx.penalty_in_graph = bool(penalty_in_graph and want_penalty)
         ctx.owner = owner            # the module instance that receives `last_rbp_terms` (per module, not process-wide)
+        ctx.set_materialize_grads(False)   # an unused output arrives as None: no penalty term in the total -> the ordinary backward
+        ctx.out_shape = (B, 2, H, W)
         if want_states:      # testmode of the rbp branch: h_0 .. h_T (models/convlstm.py:127-135); hs is the first saved block
             n = B * 25 * H * W
             states = saved[: (dims.T + 1) * n * 4].view(torch.float32).view(dims.T + 1, B, 25, H, W).clone()
@@ -90,7 +92,7 @@ class _ConvLSTMFunction(torch.autograd.Function):
             ws_bytes = L.ptk_convlstm_workspace_bytes(ctypes.byref(dims))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             dflat = torch.empty_like(flat)
-            dout = dout.contiguous().float()
+            dout = torch.zeros(ctx.out_shape, dtype=torch.float32, device=x.device) if dout is None else dout.contiguous().float()
             stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             if ctx.penalty_in_graph and dpen is not None:
                 # loss + <dpen, penalty>: the penalty's double back-propagation in closed form (ptk_convlstm_backward_penalty)

@@ -254,10 +254,22 @@ def test_convlstm_jacobian_penalty_in_graph_vs_reference(name, conv_mode):
         if not e <= allowed:
             bad.append((n, e, allowed))
     assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)
-    # the penalty alone (no loss term) and the loss alone both go through the same entry point
+    g_total = {n: prm.grad.clone() for n, prm in m.named_parameters()}
+    # linearity: the penalty alone (the output's gradient arrives as None) + the loss alone = the sum
     m.zero_grad()
     out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
-    loss.backward()
+    (pen.mean() * 1e1).backward()
+    g_pen = {n: prm.grad.clone() for n, prm in m.named_parameters()}
+    assert max(float(g.abs().max()) for n, g in g_pen.items() if "unit1.Wh" in n) > 0
+    assert all(float(g_pen[n].abs().max()) == 0.0 for n in ("bn.weight", "bn.bias", "conv6.weight", "conv6.bias"))   # the head is not in the penalty
+    # a zero penalty gradient through the penalty entry point (d pen = 0 tensor: the seeds vanish) ...
+    m.zero_grad()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    (loss + 0.0 * pen.sum()).backward()
+    for n, prm in m.named_parameters():
+        scale = float(g_total[n].abs().max())
+        assert float((g_total[n] - prm.grad - g_pen[n]).abs().max()) <= REL_TOL * scale + 1e-12, n    # fp32 sums in a different grouping
+    # ... equals the ordinary backward of a module without the flag
     m2 = convlstm.ConvLSTM(timesteps=T, filt_size=case["filt"], gabor=case["gabor"], grad_method=method, num_iter=int(z["num_iter"]))
     m2.conv_mode = _mode(conv_mode)
     m2.load_state_dict(case["sd"])
