@@ -441,6 +441,16 @@ def run_other_configs(args, dev, timer, tensor_peak, peak_src):
         v, sec, cores, sample = cpu_port_convlstm(steps=1, warmup=0, batch=1, frames=T, size=HW, gabor=gabor)
         r["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     out.append(r)
+    # ... and its bf16 variant: the same tcgen05 kernels issuing one bf16 product per k-step (not fp32-parity)
+    m.conv_mode = _lib.PTK_CONV_BF16
+    r2 = measure(lstm_step, batches, host, steps, warmup, timer, B_PER_GPU)
+    r2.update({"metric": metric_name("convlstm", T), "unit": UNIT, "steps": steps, "warmup": warmup, "dtype": "f32",
+               "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d], train mode (BASELINE configs[4] shape, bf16 variant: "
+                                      "single-pass bf16 MMAs in the recurrent convolutions, not fp32-parity)" % (T, B_PER_GPU, HW, HW),
+                          "conv_mode": "bf16", "gabor": "reference bank (tests/golden fixture)"},
+               "roofline": roof(r2["value"], flop, False)})
+    r2["roofline"]["note"] += "; recurrent-convolution FLOPs only"
+    out.append(r2)
     return out
 
 
@@ -653,7 +663,7 @@ def run_convlstm(args, dev, world, rank):
     torch.manual_seed(0)
     jp = bool(getattr(args, "jacobian_penalty", False))      # the penalty inside the graph: loss + 10 * penalty.mean() (mainclean.py:192-196)
     m = convlstm.ConvLSTM(timesteps=T_, filt_size=15, gabor=gabor, jacobian_penalty=jp).to(dev).train()
-    m.conv_mode = _lib.PTK_CONV_FP32 if args.conv_mode == "fp32" else _lib.PTK_CONV_BF16X3
+    m.conv_mode = {"fp32": _lib.PTK_CONV_FP32, "bf16": _lib.PTK_CONV_BF16}.get(args.conv_mode, _lib.PTK_CONV_BF16X3)
     clips, y = synth_pathtracker(B, 2, HW_, HW_, device=dev)
     x = clips[:, 0:1, 0].contiguous()                                               # [B,1,H,W] static image
     tgt = (clips[:, 2, 0] > 0).long()
@@ -675,7 +685,7 @@ def run_convlstm(args, dev, world, rank):
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "ConvLSTM timesteps=%d filt 15, x [%d,1,%d,%d] (BASELINE configs[4])%s"
                                              % (T_, B, HW_, HW_, ", jacobian_penalty=True: loss + 10 * penalty.mean()" if jp else ""),
-                                 "conv_mode": "fp32" if args.conv_mode == "fp32" else "bf16x3"},
+                                 "conv_mode": args.conv_mode if args.conv_mode in ("fp32", "bf16") else "bf16x3"},
                       "gpu_launches": launches,
                       "roofline": {"bound": "tensor", "achieved": flop * steps / (ms / 1e3) / 1e12, "unit": "TFLOP/s",
                                    "peak": peak, "frac": flop * steps / (ms / 1e3) / 1e12 / peak,

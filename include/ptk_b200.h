@@ -142,7 +142,8 @@ typedef struct PtkLstmDims {
   int32_t K;           /* filt_size: 15 (default, models/convlstm.py:95) or 7                         */
   int32_t conv_mode;   /* PTK_CONV_FP32: every convolution in strict fp32 on CUDA cores; PTK_CONV_BF16X3: the recurrent
                         * convolution of h and its transpose (the two per-step convolutions of the time loops) as
-                        * 3-pass split-bf16 tcgen05 implicit GEMMs, same parity gate                    */
+                        * 3-pass split-bf16 tcgen05 implicit GEMMs, same parity gate; PTK_CONV_BF16: the same kernels with ONE
+                        * bf16 product per k-step (the bf16 variant: a third of the MMAs, gradients ~1e-2, not fp32-parity) */
   int32_t ckpt_ring;   /* 0: forward keeps h_t, c_t, gates_t of EVERY step (BPTT needs them all).
                         * 1: constant-memory checkpoints for recurrent back-propagation (models/convlstm.py:124-135 runs the
                         *    first T-1 steps under no_grad): two-slot rings, so only steps T-1 and T survive;

@@ -143,7 +143,8 @@ class ConvLSTM(nn.Module):
         init.xavier_normal_(self.conv6.weight)
         init.constant_(self.conv6.bias, math.log((1 - 0.01) / 0.01))
         # the two per-step convolutions of the time loops (h -> gates and its transpose): 3-pass split-bf16 tcgen05
-        # implicit GEMMs (default) or strict-fp32 CUDA cores; same parity gate (tests/test_convlstm_gpu.py)
+        # implicit GEMMs (default) or strict-fp32 CUDA cores; same parity gate (tests/test_convlstm_gpu.py).  _lib.PTK_CONV_BF16 =
+        # the bf16 variant (one bf16 product per k-step, gradients ~1e-2: opt-in, not the parity path)
         self.conv_mode = _lib.PTK_CONV_BF16X3
         self.last_rbp_terms = None      # rbp: accepted Neumann terms of the latest backward (device tensor, 1 float)
 

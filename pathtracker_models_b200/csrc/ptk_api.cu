@@ -388,8 +388,8 @@ size_t ptk_conv7_workspace_bytes(int32_t B, int32_t H, int32_t W) {
 static int lstm_check(const PtkLstmDims* d, const char* who) {
   if (!d) { set_error("%s: dims is NULL", who); return PTK_EINVAL; }
   if (d->K != 7 && d->K != 15) { set_error("%s: filt_size %d not built (7 and 15 are)", who, d->K); return PTK_EUNSUPPORTED; }
-  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3) {
-    set_error("%s: conv_mode %d not built for the ConvLSTM (fp32 and bf16x3 are)", who, d->conv_mode);
+  if (d->conv_mode != PTK_CONV_FP32 && d->conv_mode != PTK_CONV_BF16X3 && d->conv_mode != PTK_CONV_BF16) {
+    set_error("%s: unknown conv_mode %d", who, d->conv_mode);
     return PTK_EUNSUPPORTED;
   }
   if (d->B < 1 || d->T < 1 || d->H < 16 || d->W < 32 || d->H % 16 || d->W % 32) {

@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(256, 1) convk_tc_kernel(ConvKArgs a) {
               const uint32_t dcol = tmem_base + (uint32_t)(j * K::DSTRIDE);
               if (a.dbg != 2 && elect_one()) {
                 umma_bf16(dcol, ((uint64_t)aHiW << 32) | aH, dBh, IDESC, (first_unit && s == 0) ? 0u : 1u);
-                umma_bf16(dcol, ((uint64_t)aHiW << 32) | aH, dBl, IDESC, 1u);
-                umma_bf16(dcol, ((uint64_t)aHiW << 32) | aL, dBh, IDESC, 1u);
+                if (!a.single) {   // the two cross terms of the split; conv_mode = bf16 keeps the leading product only
+                  umma_bf16(dcol, ((uint64_t)aHiW << 32) | aH, dBl, IDESC, 1u);
+                  umma_bf16(dcol, ((uint64_t)aHiW << 32) | aL, dBh, IDESC, 1u);
+                }
               }
             }
           }

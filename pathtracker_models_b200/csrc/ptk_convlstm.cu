@@ -226,12 +226,14 @@ __global__ void __launch_bounds__(512) head_bwd_kernel(const float* __restrict__
 }
 // the wide convolutions (25 -> 100 stacked gates, its transpose, its weight gradient) of the recurrent path (Wh: every
 // step of the time loops) and of the hoisted input path (Wx: once per sequence).
-// conv_mode bf16x3: tcgen05 implicit GEMMs (ptk_convk_tc.cu, ptk_wgradk_tc.cu); fp32: the generic direct kernels.
+// conv_mode bf16x3: tcgen05 implicit GEMMs (ptk_convk_tc.cu, ptk_wgradk_tc.cu) with the 3-pass split; bf16: the same kernels issuing
+// the leading product only (a third of the MMAs, not fp32-parity); fp32: the generic direct kernels.
 template <int KS>
 static int wide_conv(const LstmDev& d, const ConvGArgs& g, bool transposed, bool xpath, cudaStream_t st) {
   if (d.conv_mode == PTK_CONV_FP32) return launch_convg<KS>(g, st);
   const void* w = xpath ? (transposed ? d.wxD_tc : d.wxF_tc) : (transposed ? d.whD_tc : d.whF_tc);
   ConvKArgs k{g.in, w, g.bias, g.addend, g.out, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, g.skip};
+  k.single = (d.conv_mode == PTK_CONV_BF16);
   ProfileScope ps(transposed ? PTK_PROF_CONV_DGRAD : PTK_PROF_CONV_FWD, st);
   return launch_convk_tc<KS>(k, transposed ? 1 : 0, st);
 }
@@ -246,6 +248,7 @@ static int wide_wgrad(const LstmDev& d, const WgradGArgs& g, bool xpath, cudaStr
   int rc = launch_wgradk_prep_dy(g.dy, g.B, g.H, g.W, g.Cout, d.dyc_tc, nullptr, st);
   if (rc) return rc;
   WgradKArgs k{g.in, g.dy, xpath ? d.slots_x_tc : d.slots_h_tc, g.B, g.H, g.W, g.Cin, g.Cout, g.accumulate, nullptr, 0, d.dyc_tc};
+  k.single = (d.conv_mode == PTK_CONV_BF16);
   ProfileScope ps(PTK_PROF_WGRAD, st);
   return launch_wgradk_tc<KS>(k, st);
 }

@@ -69,6 +69,7 @@ struct ConvKArgs {
   int B, H, W, Cin, Cout, accumulate;
   const float* skip = nullptr;   // RBP device state: skip[1] != 0 => do nothing
   int dbg = 0;                   // timing experiments (PTK_CONVK_EXP): 1 = no epilogue stores, 2 = no MMAs
+  int single = 0;                // 1: conv_mode = bf16, ONE product per k-step (Ih x Wh) instead of the 3-pass split: not fp32-parity
 };
 template <int KSZ> size_t convk_tc_weight_bytes(int transposed);
 template <int KSZ> int launch_prep_weights_k(const float* const* w, int transposed, void* dst, cudaStream_t st);
@@ -87,6 +88,7 @@ struct WgradKArgs {
   const float* skip = nullptr;
   long long in_bs = 0;  // elements between samples of `in` (0 = Cin*H*W): a 32-channel block of a wider tensor
   const void* dyc = nullptr;   // dy already split and laid out per tile by launch_wgradk_prep_dy (then `dy` is not read)
+  int single = 0;              // 1: conv_mode = bf16, one product per k-step
 };
 // dy [B,Cout,H,W] fp32 -> per 4x32-pixel tile the kernel's shared-memory image (bf16 hi/lo planes): the weight-gradient
 // CTAs of all kernel rows (and input blocks) then fetch a tile with ONE bulk copy instead of converting it again each

@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(256, 1) wgradk_tc_kernel(WgradKArgs a) {
           const uint32_t ao = (uint32_t)(ks * 16), bo = (uint32_t)((ks >> 1) * K::WP + (ks & 1) * 16 + 2 * pr);
           if (elect_one()) {
             umma_bf16(dcol, dAh + ao, dBh + bo, IDESC, (i | ks) ? 1u : 0u);
-            umma_bf16(dcol, dAh + ao, dBl + bo, IDESC, 1u);
-            umma_bf16(dcol, dAl + ao, dBh + bo, IDESC, 1u);
+            if (!a.single) {   // conv_mode = bf16 keeps the leading product only
+              umma_bf16(dcol, dAh + ao, dBl + bo, IDESC, 1u);
+              umma_bf16(dcol, dAl + ao, dBh + bo, IDESC, 1u);
+            }
           }
         }
       }
