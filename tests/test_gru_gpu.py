@@ -99,7 +99,10 @@ def test_gru_testmode_input_gradient_and_determinism():
     p = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
     x64 = case["x"].clone().requires_grad_(True)
     GO.forward(x64, p).sum().backward()
-    assert rel_err(g1, x64.grad) < 5e-4
+    p32 = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}     # the golden gate: 1e-4 or 4 x the fp32 oracle's own error
+    x32 = case["x"].float().clone().requires_grad_(True)
+    GO.forward(x32, p32).sum().backward()
+    assert rel_err(g1, x64.grad) <= max(REL_TOL, NOISE_MULT * rel_err(x32.grad, x64.grad))
     x2 = case["x"].float().cuda().requires_grad_(True)
     out2, _ = m(x2)
     out2.sum().backward()
