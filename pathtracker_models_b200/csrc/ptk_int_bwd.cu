@@ -2041,7 +2041,14 @@ __global__ void __launch_bounds__(256) int_finalize_kernel(IntDev d, FinalizeArg
       const float* wa = (p == PTK_P_W_EXC) ? d.wacc_exc : d.wacc_inh;
       const int oc = j / (C * TAPS), ic = (j / TAPS) % C, tap = j % TAPS;
       if (f.wgrad_tc > 0) {
-        for (int g = 0; g < f.wgrad_tc; ++g) s += (double)wa[((size_t)g * TAPS + tap) * C * C + oc * C + ic];
+        // slots are [cta][tap][oc][ic]: walk the bank in SLOT order (consecutive threads = consecutive oc*32 + ic of one tap, coalesced
+        // 128-byte reads per slot) and scatter the one result to dW[oc][ic][tap]; same summation order per element as before
+        const int tap2 = j / (C * C), q = j - tap2 * (C * C), oc2 = q / C, ic2 = q - oc2 * C;
+        const float* src = wa + (size_t)tap2 * C * C + q;
+#pragma unroll 8
+        for (int g = 0; g < f.wgrad_tc; ++g) s += (double)__ldcg(src + (size_t)g * TAPS * C * C);
+        d.dparams[f.off[p] + ((int64_t)oc2 * C + ic2) * TAPS + tap2] = (float)s;
+        continue;
       } else {
         for (int g = 0; g < f.wgroups; ++g)
           s += (double)wa[((size_t)(g * 4 + ic / 8) * TAPS + tap) * 256 + oc * 8 + (ic & 7)];
