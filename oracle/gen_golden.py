@@ -322,5 +322,12 @@ if __name__ == "__main__":
             run_convlstm_case("convlstm_k15_t64", 15, 2, 64, 32, 32, seed=64, store_full=False)
         if "gru" in which:
             run_gru_case("gru_t64", 2, 64, 32, 32, seed=65)
+    elif len(sys.argv) > 1 and sys.argv[1] == "long_variants":
+        # the InT variants utils/engine.py builds (nl = tanh :138-146, no_inh :86-93, lesions :94-137) at the headline horizon T = 64
+        RInT, RH = load_reference()
+        run_case("int_tanh_t64", lambda: RInT.InT(dimensions=32, timesteps=64, kernel_size=7, nl=torch.tanh), 4, 64, 32, 32, seed=66, wseed=26)
+        run_case("int_noinh_t64", lambda: RInT.InT(dimensions=32, timesteps=64, kernel_size=7, no_inh=True), 4, 64, 32, 32, seed=67, wseed=27)
+        run_case("int_lesion_t64", lambda: RInT.InT(dimensions=32, timesteps=64, kernel_size=7, lesion_mu=True, lesion_kappa=True),
+                 4, 64, 32, 32, seed=68, wseed=28)
     else:
         main()

@@ -49,13 +49,16 @@ def test_oracle_manual_backward_matches_reference_fp64(name, variant, act):
 
 # the horizons the benchmark is quoted on (BASELINE.json configs[1]-[3]): T = 64 at 32x32 (B = 8), hGRU likewise,
 # T = 128 at 64x64 (B = 2).  Fixtures = the unmodified reference in fp64 (oracle/gen_golden.py long).
-LONG_CASES = [("int_t64", "int"), ("hgru_t64", "hgru"), ("int_t128_64px", "int")]
+# + the InT variants utils/engine.py builds, at T = 64 (B = 4): tanh, no_inh, lesioned (oracle/gen_golden.py long_variants).
+LONG_CASES = [("int_t64", "int", "softplus", False), ("hgru_t64", "hgru", "softplus", False), ("int_t128_64px", "int", "softplus", False),
+              ("int_tanh_t64", "int", "tanh", False), ("int_noinh_t64", "int", "softplus", True),
+              ("int_lesion_t64", "int", "softplus", False)]
 
 
-@pytest.mark.parametrize("name,variant", LONG_CASES)
-def test_oracle_long_horizon_matches_reference_fp64(name, variant):
+@pytest.mark.parametrize("name,variant,act,no_inh", LONG_CASES)
+def test_oracle_long_horizon_matches_reference_fp64(name, variant, act, no_inh):
     case = load_case(name)
-    logits, loss, g = _autograd(case, variant, "softplus", False)
+    logits, loss, g = _autograd(case, variant, act, no_inh)
     assert rel_err(logits, case["logits"]) < 1e-10
     assert abs(loss - case["loss"]) < 1e-10
     for n, g_ref in case["grads"].items():

@@ -62,15 +62,18 @@ def test_logits_and_all_grads_vs_fp64_reference(name, kind, kw, conv_mode):
 # The horizons the benchmark is quoted on: BASELINE.json configs[1] (T = 64, 32x32), configs[3] (hGRU, T = 64) and
 # configs[2] (T = 128, 64x64), per-GPU batch reduced to what the fp64 reference runs in a minute on the CPU.
 # Same gate as the short cases (1e-4 or 4x the fp32 reference's own error), both precisions of the path.
-LONG_CASES = [("int_t64", "int"), ("hgru_t64", "hgru"), ("int_t128_64px", "int")]
+# + the InT variants utils/engine.py builds (tanh, no_inh, lesioned), T = 64, B = 4.
+LONG_CASES = [("int_t64", "int", {}), ("hgru_t64", "hgru", {}), ("int_t128_64px", "int", {}),
+              ("int_tanh_t64", "int", {"nl": torch.tanh}), ("int_noinh_t64", "int", {"no_inh": True}),
+              ("int_lesion_t64", "int", {"lesion_mu": True, "lesion_kappa": True})]
 
 
 @pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
-@pytest.mark.parametrize("name,kind", LONG_CASES)
-def test_long_horizon_logits_and_all_grads_vs_fp64_reference(name, kind, conv_mode):
+@pytest.mark.parametrize("name,kind,kw", LONG_CASES)
+def test_long_horizon_logits_and_all_grads_vs_fp64_reference(name, kind, kw, conv_mode):
     from pathtracker_models_b200 import _lib
     case = load_case(name)
-    m = _model(case, kind)
+    m = _model(case, kind, **kw)
     m.conv_mode = _lib.PTK_CONV_BF16X3 if conv_mode == "bf16x3" else _lib.PTK_CONV_FP32
     out, loss, grads, pen = _run(case, m)
     assert abs(loss.item() - case["loss"]) < 1e-5

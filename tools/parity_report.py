@@ -6,7 +6,7 @@ from tests.golden_util import load_case, rel_err
 from tests.test_parity_gpu import _model, _run, CASES, LONG_CASES
 from pathtracker_models_b200 import _lib
 
-for name, kind, kw in CASES + [(n, k, {}) for n, k in LONG_CASES]:
+for name, kind, kw in CASES + LONG_CASES:
     case = load_case(name)
     for mode, mname in ((0, "fp32"), (1, "bf16x3"), (2, "bf16")):
         m = _model(case, kind, **kw)
