@@ -322,6 +322,10 @@ if __name__ == "__main__":
             run_convlstm_case("convlstm_k15_t64", 15, 2, 64, 32, 32, seed=64, store_full=False)
         if "gru" in which:
             run_gru_case("gru_t64", 2, 64, 32, 32, seed=65)
+    elif len(sys.argv) > 1 and sys.argv[1] == "convlstm_rbp_long":
+        # recurrent back-propagation at configs[4]'s horizon (timesteps = 64, filt 15): 63 steps under no_grad, Neumann series on the last
+        load_reference()
+        run_convlstm_case("convlstm_k15_rbp_t64", 15, 2, 64, 32, 32, seed=75, store_full=False, grad_method='rbp', num_iter=15)
     elif len(sys.argv) > 1 and sys.argv[1] == "long_variants":
         # the InT variants utils/engine.py builds (nl = tanh :138-146, no_inh :86-93, lesions :94-137) at the headline horizon T = 64
         RInT, RH = load_reference()

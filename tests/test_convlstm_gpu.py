@@ -366,3 +366,38 @@ def test_convlstm_bf16_single_pass_mode_error_is_bounded(name):
     assert eo < LSTM_BF16_OUT_TOL
     assert worst[0] < LSTM_BF16_GRAD_TOL, worst
     assert worst[0] > 1e-5          # the mode really ran reduced precision
+
+
+@pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
+def test_convlstm_rbp_long_horizon_k15_t64_vs_reference(conv_mode):
+    """recurrent back-propagation at configs[4]'s horizon (filt 15, timesteps = 64, B = 2) on the constant-memory checkpoint ring:
+    output / loss / penalty against the reference's own fixture, every gradient against the fp64 oracle (held to the fixture's
+    projections on the CPU suite), the accepted Neumann terms against the oracle's count."""
+    import os
+    import numpy as np
+    from oracle import convlstm_oracle as CO
+    from pathtracker_models_b200 import convlstm
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case("convlstm_k15_rbp_t64")
+    z = np.load(os.path.join(GOLDEN, "convlstm_k15_rbp_t64.npz"))
+    num_iter = int(z["num_iter"])
+    B, T, H, W = case["shape"]
+    assert T == 64
+    m = convlstm.ConvLSTM(timesteps=T, filt_size=15, gabor=case["gabor"], grad_method='rbp', num_iter=num_iter)
+    m.conv_mode = _mode(conv_mode)
+    m.load_state_dict(case["sd"])
+    m = m.cuda().train()
+    out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
+    loss.backward()
+    assert rel_err(out, case["output"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
+    assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))
+    p64 = {k: v.double().cuda().requires_grad_(True) for k, v in case["sd"].items()}
+    _, _, g64, terms = CO.rbp_grads(case["x"].cuda(), p64, T, case["target"].cuda(), num_iter)
+    assert int(m.last_rbp_terms.item()) == terms
+    bad = []
+    for n, prm in m.named_parameters():
+        e = rel_err(prm.grad, g64[n])
+        allowed = max(REL_TOL, NOISE_MULT * case["noise"].get(n, 0.0))
+        if not e <= allowed:
+            bad.append((n, e, allowed))
+    assert not bad, "\n".join(f"{n}: err {e:.3e} > allowed {a:.3e}" for n, e, a in bad)

@@ -72,3 +72,23 @@ def test_jacobian_penalty_in_graph_oracle_matches_reference_fp64(name):
             p0 = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
             _, _, g0, _ = CO.rbp_grads(case["x"], p0, case["shape"][1], case["target"], int(z["num_iter"]))
         assert max(rel_err(g0[n], g) for n, g in case["grads"].items() if "unit1.Wh" in n) > 1e-3
+
+
+def test_rbp_oracle_long_horizon_matches_reference_fp64():
+    """grad_method='rbp' at configs[4]'s own horizon (filt 15, timesteps = 64): the reference's gradients through seeded projections"""
+    import os
+    import numpy as _np
+    from oracle import convlstm_oracle as CO
+    from tests.golden_util import GOLDEN
+    case = load_convlstm_case("convlstm_k15_rbp_t64")
+    z = _np.load(os.path.join(GOLDEN, "convlstm_k15_rbp_t64.npz"))
+    num_iter, calls = int(z["num_iter"]), int(z["rbp_grad_calls"])
+    p = {k: v.double().clone().requires_grad_(True) for k, v in case["sd"].items()}
+    out, loss, grads, terms = CO.rbp_grads(case["x"], p, case["shape"][1], case["target"], num_iter)
+    assert rel_err(out, case["output"]) < 1e-10 and abs(loss - case["loss"]) < 1e-10
+    assert terms in (calls, calls - 1) and terms <= num_iter
+    prs = _np.random.RandomState(case["proj_seed"])
+    for n in case["proj"]:
+        g = grads[n].detach().numpy().ravel()
+        v = prs.normal(0, 1, (4, g.size))
+        assert _np.allclose(v @ g, case["proj"][n], rtol=1e-8, atol=1e-12 * max(1.0, case["gmax"][n])), n
