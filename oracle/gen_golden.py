@@ -326,6 +326,10 @@ if __name__ == "__main__":
         # recurrent back-propagation at configs[4]'s horizon (timesteps = 64, filt 15): 63 steps under no_grad, Neumann series on the last
         load_reference()
         run_convlstm_case("convlstm_k15_rbp_t64", 15, 2, 64, 32, 32, seed=75, store_full=False, grad_method='rbp', num_iter=15)
+    elif len(sys.argv) > 1 and sys.argv[1] == "convlstm_jp_long":
+        # the in-graph Jacobian penalty at configs[4]'s horizon: its second-order seeds travel back through all 64 steps
+        load_reference()
+        run_convlstm_case("convlstm_k15_jp_t64", 15, 2, 64, 32, 32, seed=76, store_full=False, jacobian_penalty=True)
     elif len(sys.argv) > 1 and sys.argv[1] == "long_variants":
         # the InT variants utils/engine.py builds (nl = tanh :138-146, no_inh :86-93, lesions :94-137) at the headline horizon T = 64
         RInT, RH = load_reference()

@@ -218,7 +218,7 @@ def test_convlstm_input_gradient_vs_fp64_oracle(grad_method):
 
 
 @pytest.mark.parametrize("conv_mode", ["bf16x3", "fp32"])
-@pytest.mark.parametrize("name", ["convlstm_k7_jp", "convlstm_k7_jp_t2", "convlstm_k15_jp", "convlstm_k7_rbp_jp"])
+@pytest.mark.parametrize("name", ["convlstm_k7_jp", "convlstm_k7_jp_t2", "convlstm_k15_jp", "convlstm_k7_rbp_jp", "convlstm_k15_jp_t64"])
 def test_convlstm_jacobian_penalty_in_graph_vs_reference(name, conv_mode):
     """jacobian_penalty=True (create_graph=True, models/convlstm.py:157-160): the training loop back-propagates
     loss + 10 * penalty.mean() (mainclean.py:192-196).  The CUDA path takes the penalty's double back-propagation in closed
@@ -240,13 +240,20 @@ def test_convlstm_jacobian_penalty_in_graph_vs_reference(name, conv_mode):
     out, pen, loss = m(case["x"].float().cuda(), 0, 0, case["target"].cuda(), torch.nn.CrossEntropyLoss())
     assert pen.requires_grad
     (loss + pen.mean() * 1e1).backward()
-    assert rel_err(out, case["output"]) < REL_TOL and abs(loss.item() - case["loss"]) < 1e-5
+    # the gate of SURVEY 8c for the output too: at timesteps = 64 the fp32 reference itself is 8.5e-5 off its fp64 run on this fixture
+    assert rel_err(out, case["output"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__output__", 0.0))
+    assert abs(loss.item() - case["loss"]) < 1e-5
     assert rel_err(pen, case["penalty"]) < max(REL_TOL, NOISE_MULT * case["noise"].get("__penalty__", 0))
     # checker: the fp64 double back-propagation oracle on the GPU, itself pinned to the reference on the CPU suite
     p64 = {k: v.double().cuda().requires_grad_(True) for k, v in case["sd"].items()}
     _, _, _, g64 = CO.jp_total_grads(case["x"].cuda(), p64, T, case["target"].cuda(), grad_method=method, num_iter=int(z["num_iter"]))
     for n, g in case["grads"].items():
         assert rel_err(g64[n], g) < (2e-7 if g.numel() > 4096 else 1e-9), n
+    prs = np.random.RandomState(case["proj_seed"])
+    for n in case["proj"]:                                  # compact fixtures: the reference's gradients through seeded projections
+        g = g64[n].detach().cpu().numpy().ravel()
+        v = prs.normal(0, 1, (4, g.size))
+        assert np.allclose(v @ g, case["proj"][n], rtol=1e-7, atol=1e-11 * max(1.0, case["gmax"][n])), n
     bad = []
     for n, prm in m.named_parameters():
         e = rel_err(prm.grad, g64[n])

@@ -42,6 +42,8 @@ def test_rbp_oracle_matches_reference_fp64(name):
         assert rel_err(grads[n], g) < (2e-7 if g.numel() > 4096 else 1e-9), n
 
 
+# (convlstm_k15_jp_t64, the same at timesteps = 64, takes 100 s of CPU double back-propagation: the GPU suite holds the oracle to
+# that fixture's projections instead, evaluating it in fp64 on the device)
 @pytest.mark.parametrize("name", ["convlstm_k7_jp", "convlstm_k7_jp_t2", "convlstm_k15_jp", "convlstm_k7_rbp_jp"])
 def test_jacobian_penalty_in_graph_oracle_matches_reference_fp64(name):
     """jacobian_penalty=True (create_graph=True, models/convlstm.py:157-160): gradients of loss + 10 * penalty.mean()
